@@ -1,0 +1,592 @@
+// tcgen05 tensor-core contraction kernel for sm_100a: GEMM / implicit-GEMM convolution (NHWC) /
+// weight-gradient, operands staged global->shared by TMA (cp.async.bulk.tensor, 128B swizzle),
+// tcgen05.mma issued by one elected thread, fp32 accumulators in TMEM, epilogue via tcgen05.ld.
+//
+// Replaces the reference's library calls on the hot path: cudnnConvolutionForward/BackwardData/
+// BackwardFilter (SNIPER-mxnet/src/operator/nn/cudnn/cudnn_convolution-inl.h:144,211-266), cuBLAS
+// via FullyConnected (nn/fully_connected-inl.h) and linalg_gemm in DeformableConvolution
+// (contrib/deformable_convolution-inl.h:148-160).
+//
+// One CTA = one 128 x BLOCK_N output tile (cta_group::1).  Warp roles: warp 0 = TMA producer,
+// warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (one TMEM lane quarter each).
+//
+//   mode 0  GEMM    C[M,N]  = A[M,K] * B[N,K]^T             A,B K-major
+//   mode 1  CONV    C[pix,N] = sum_taps A[n,h+dh,w+dw,c] * B[N,(tap,c)]   A 4-D NHWC, K-major; TMA zero
+//                   fill implements padding, elementStrides implement stride
+//   mode 2  WGRAD   C[Co,(tap,ci)] += sum_pix dY[pix,Co] * X[n,h+dh,w+dw,ci]   both MN-major, split-K
+#include "common.cuh"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace {
+
+enum { MODE_GEMM = 0, MODE_CONV = 1, MODE_WGRAD = 2 };
+enum { DT_TF32 = 0, DT_BF16 = 1 };
+constexpr int kMaxTaps = 16;
+constexpr int kStageABytes = 128 * 128;  // 128 rows x 128 B
+
+struct GemmParams {
+  int mode, dtype;
+  int M, N;               // logical output extent (rows, cols)
+  int block_n;            // 64 / 128 / 256
+  int num_kb;             // k-blocks per CTA
+  int stages;
+  // ---- producer geometry
+  int elems_per_128B;     // 32 (tf32) / 64 (bf16)
+  int cblocks;            // CONV: channel blocks per tap (Cin / elems_per_128B)
+  int ntaps;
+  int tap_dh[kMaxTaps], tap_dw[kMaxTaps];
+  int conv_stride;        // input coordinate = out * conv_stride + tap offset
+  int tile_w, tile_h;     // output pixels per tile = tile_w * tile_h (=128 CONV, = kp WGRAD)
+  int tiles_w, tiles_per_img;
+  int Ho, Wo;             // output spatial extent (CONV/WGRAD pixel space)
+  int kp;                 // WGRAD: pixels per k-block
+  int wg_cin_blocks;      // WGRAD: N tiles per tap = Cin / block_n
+  // ---- descriptors
+  uint32_t idesc;
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // 16-byte units
+  uint32_t a_kadv, b_kadv;              // 16-byte units per MMA k-step
+  int mmas_per_kb;
+  int a_boxes, b_boxes;                 // TMA boxes per stage
+  uint32_t a_box_bytes, b_box_bytes;
+  // ---- epilogue
+  float* C;
+  long ldc;
+  const float* scale;     // per-column multiplier (optional)
+  const float* bias;      // per-column addend (optional)
+  const float* residual;  // same row mapping as C (optional)
+  long ldr;
+  int relu;
+  int atomic;             // accumulate with red.global.add instead of store
+  // row mapping for CONV: output pixel (n,oh,ow) -> row ((n*out_H + oh*out_s + out_oh)*out_W + ow*out_s + out_ow)
+  int out_H, out_W, out_s, out_oh, out_ow;
+  int out_bf16;           // store bf16 instead of fp32
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+template <int DT>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (DT == DT_TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)(lbo16 & 0x3fff) << 16;
+  d |= (uint64_t)(sbo16 & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A 16KB | B block_n*128B)] | barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
+  const uint32_t stage_bytes = kStageABytes + b_stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, tile_n = blockIdx.y, split = blockIdx.z;
+  const uint32_t tmem_cols = p.block_n <= 32 ? 32u : (p.block_n <= 64 ? 64u : (p.block_n <= 128 ? 128u : 256u));
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_smem, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // =============================== TMA producer
+    if (lane == 0) {
+      int n_img = 0, oh0 = 0, ow0 = 0;
+      if (p.mode == MODE_CONV) {
+        n_img = tile_m / p.tiles_per_img;
+        const int r = tile_m - n_img * p.tiles_per_img;
+        const int th = r / p.tiles_w;
+        oh0 = th * p.tile_h;
+        ow0 = (r - th * p.tiles_w) * p.tile_w;
+      }
+      int wg_tap = 0, wg_ci0 = 0;
+      if (p.mode == MODE_WGRAD) {
+        wg_tap = tile_n / p.wg_cin_blocks;
+        wg_ci0 = (tile_n - wg_tap * p.wg_cin_blocks) * p.block_n;
+      }
+      const int E = p.elems_per_128B;
+      for (int i = 0; i < p.num_kb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        uint8_t* sb = sa + kStageABytes;
+        mbar_expect_tx(&full_bar[s], (uint32_t)p.a_boxes * p.a_box_bytes + (uint32_t)p.b_boxes * p.b_box_bytes);
+        const int kb = split * p.num_kb + i;
+        if (p.mode == MODE_GEMM) {
+          tma_load_4d(sa, &tma_a, &full_bar[s], kb * E, tile_m * 128, 0, 0);
+          tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tile_n * p.block_n, 0, 0);
+        } else if (p.mode == MODE_CONV) {
+          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+          tma_load_4d(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
+                      oh0 * p.conv_stride + p.tap_dh[tap], n_img);
+          tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tile_n * p.block_n, 0, 0);
+        } else {
+          // WGRAD: k-block = kp consecutive output pixels of one image row block
+          const int pix0 = kb * p.kp;
+          const int img = pix0 / (p.Ho * p.Wo);
+          const int rem = pix0 - img * (p.Ho * p.Wo);
+          const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+          for (int j = 0; j < p.a_boxes; ++j)
+            tma_load_4d(sa + (size_t)j * p.a_box_bytes, &tma_a, &full_bar[s], tile_m * 128 + j * E, pix0, 0, 0);
+          for (int j = 0; j < p.b_boxes; ++j)
+            tma_load_4d(sb + (size_t)j * p.b_box_bytes, &tma_b, &full_bar[s], wg_ci0 + j * E,
+                        ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer
+    if (lane == 0) {
+      for (int i = 0; i < p.num_kb; ++i) {
+        const int s = i % p.stages;
+        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + kStageABytes;
+        const uint64_t adesc0 = make_smem_desc(sa, p.a_lbo, p.a_sbo);
+        const uint64_t bdesc0 = make_smem_desc(sb, p.b_lbo, p.b_sbo);
+        for (int k = 0; k < p.mmas_per_kb; ++k) {
+          umma<DT>(tmem_base, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
+                   (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // =============================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int m_local = q * 32 + lane;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    long row;
+    bool row_ok;
+    if (p.mode == MODE_CONV) {
+      const int n_img = tile_m / p.tiles_per_img;
+      const int r = tile_m - n_img * p.tiles_per_img;
+      const int th = r / p.tiles_w;
+      const int oh = th * p.tile_h + m_local / p.tile_w;
+      const int ow = (r - th * p.tiles_w) * p.tile_w + m_local % p.tile_w;
+      row = ((long)n_img * p.out_H + (long)oh * p.out_s + p.out_oh) * p.out_W + (long)ow * p.out_s + p.out_ow;
+      row_ok = oh < p.Ho && ow < p.Wo;
+    } else {
+      row = (long)tile_m * 128 + m_local;
+      row_ok = row < p.M;
+    }
+    int col_base = tile_n * p.block_n;
+    if (p.mode == MODE_WGRAD) {
+      const int tap = tile_n / p.wg_cin_blocks;
+      col_base = tap * (p.wg_cin_blocks * p.block_n) + (tile_n - tap * p.wg_cin_blocks) * p.block_n;
+    }
+    for (int c = 0; c < p.block_n; c += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (!row_ok) continue;
+      const int n0 = col_base + c;
+      if (n0 >= p.N) continue;
+      float* crow = p.C + row * p.ldc + n0;
+      const float* rrow = p.residual ? p.residual + row * p.ldr + n0 : nullptr;
+      const bool full = (n0 + 32 <= p.N);
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (full || n0 + j < p.N) {
+          if (p.scale) x *= __ldg(p.scale + n0 + j);
+          if (p.bias) x += __ldg(p.bias + n0 + j);
+          if (rrow) x += __ldg(rrow + j);
+          if (p.relu) x = fmaxf(x, 0.0f);
+        }
+        f[j] = x;
+      }
+      if (p.out_bf16) {
+        __nv_bfloat16* brow = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || n0 + j < p.N) brow[j] = __float2bfloat16(f[j]);
+      } else if (p.atomic) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || n0 + j < p.N) atomicAdd(crow + j, f[j]);
+      } else if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || n0 + j < p.N) crow[j] = f[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 4-D tiled map; dims/strides innermost first; strides in bytes for dims 1..3
+int make_map(CUtensorMap* m, int dtype, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+             const uint32_t box[4], const uint32_t estr[4]) {
+  EncodeTiledFn enc = get_encode();
+  SN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gs[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {estr[0], estr[1], estr[2], estr[3]};
+  CUresult r = enc(m, dtype == DT_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SN_CHECK(r == CUDA_SUCCESS,
+           "cuTensorMapEncodeTiled failed (%d): dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu box=%u,%u,%u,%u es=%u,%u,%u,%u",
+           (int)r, (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)gd[2],
+           (unsigned long long)gd[3], (unsigned long long)gs[0], (unsigned long long)gs[1], (unsigned long long)gs[2],
+           bx[0], bx[1], bx[2], bx[3], es[0], es[1], es[2], es[3]);
+  return 0;
+}
+
+uint32_t make_idesc(int dtype, int a_mn_major, int b_mn_major, int M, int N) {
+  uint32_t d = 0;
+  d |= 1u << 4;                                   // c_format = F32
+  const uint32_t fmt = dtype == DT_TF32 ? 2u : 1u;  // TF32 / BF16
+  d |= fmt << 7;
+  d |= fmt << 10;
+  d |= (uint32_t)(a_mn_major ? 1 : 0) << 15;
+  d |= (uint32_t)(b_mn_major ? 1 : 0) << 16;
+  d |= (uint32_t)(N >> 3) << 17;
+  d |= (uint32_t)(M >> 4) << 24;
+  return d;
+}
+
+int pick_stages(int block_n) {
+  // <=128 columns: ~100 KB per CTA so that two CTAs share an SM (one's epilogue overlaps the
+  // other's main loop); 256 columns: one CTA per SM with a deeper ring.
+  return block_n <= 64 ? 4 : (block_n <= 128 ? 3 : 4);
+}
+
+size_t smem_bytes(int stages, int block_n) {
+  return (size_t)stages * (kStageABytes + block_n * 128) + 1024 + 256;
+}
+
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 grid, cudaStream_t stream) {
+  const size_t smem = smem_bytes(p.stages, p.block_n);
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[p.dtype]) {
+    if (p.dtype == DT_TF32)
+      SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    else
+      SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done[p.dtype] = true;
+  }
+  if (p.dtype == DT_TF32)
+    gemm_tc_kernel<DT_TF32><<<grid, 192, smem, stream>>>(ma, mb, p);
+  else
+    gemm_tc_kernel<DT_BF16><<<grid, 192, smem, stream>>>(ma, mb, p);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int pick_block_n(int N) {
+  if (N <= 64) return 64;
+  if (N <= 128) return 128;
+  if (N % 256 == 0 || N > 1024) return 256;
+  return 128;
+}
+
+void fill_kmajor(GemmParams& p, int dtype, int block_n) {
+  p.dtype = dtype;
+  p.block_n = block_n;
+  p.elems_per_128B = dtype == DT_TF32 ? 32 : 64;
+  p.idesc = make_idesc(dtype, 0, 0, 128, block_n);
+  p.a_lbo = 1; p.a_sbo = 64; p.b_lbo = 1; p.b_sbo = 64;  // SBO = 8 rows x 128 B
+  p.a_kadv = 2; p.b_kadv = 2;                            // 32 B per UMMA_K step
+  p.mmas_per_kb = 4;
+  p.a_boxes = 1; p.b_boxes = 1;
+  p.a_box_bytes = kStageABytes;
+  p.b_box_bytes = (uint32_t)block_n * 128u;
+  p.stages = pick_stages(block_n);
+}
+
+struct Epilogue {
+  const float* scale;
+  const float* bias;
+  const float* residual;
+  long ldr;
+  int relu;
+  int atomic;
+  int out_bf16;
+};
+
+}  // namespace
+
+extern "C" {
+
+// C[M,N] (ldc) = epilogue(A[M,K] (lda) * B[N,K]^T (ldb)).  dtype 0: fp32 storage / TF32 math, 1: bf16.
+// K must be a multiple of 32 (tf32) / 64 (bf16) elements; lda/ldb in elements, 16-byte aligned rows.
+int sniper_gemm_nt(const void* A, long lda, const void* B, long ldb, float* C, long ldc, int M, int N, int K,
+                   int dtype, const float* scale, const float* bias, const float* residual, long ldr, int relu,
+                   int accumulate, int out_bf16, void* stream) {
+  SN_CHECK(dtype == DT_TF32 || dtype == DT_BF16, "gemm: dtype must be 0 (tf32) or 1 (bf16)");
+  const int esz = dtype == DT_TF32 ? 4 : 2;
+  const int E = 128 / esz;
+  SN_CHECK(K % E == 0 && K > 0, "gemm: K (%d) must be a positive multiple of %d", K, E);
+  SN_CHECK(M > 0 && N > 0, "gemm: empty problem");
+  SN_CHECK((lda * esz) % 16 == 0 && (ldb * esz) % 16 == 0, "gemm: row strides must be 16-byte multiples");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int bn = pick_block_n(N);
+  fill_kmajor(p, dtype, bn);
+  p.mode = MODE_GEMM; p.M = M; p.N = N; p.num_kb = K / E;
+  p.C = C; p.ldc = ldc; p.scale = scale; p.bias = bias; p.residual = residual; p.ldr = ldr; p.relu = relu;
+  p.atomic = accumulate; p.out_bf16 = out_bf16;
+  CUtensorMap ma, mb;
+  const uint32_t ones[4] = {1, 1, 1, 1};
+  {
+    const uint64_t d[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
+    const uint64_t s[3] = {(uint64_t)lda * esz, (uint64_t)lda * esz * M, (uint64_t)lda * esz * M};
+    const uint32_t b[4] = {(uint32_t)E, 128, 1, 1};
+    if (make_map(&ma, dtype, A, d, s, b, ones)) return -1;
+  }
+  {
+    const uint64_t d[4] = {(uint64_t)K, (uint64_t)N, 1, 1};
+    const uint64_t s[3] = {(uint64_t)ldb * esz, (uint64_t)ldb * esz * N, (uint64_t)ldb * esz * N};
+    const uint32_t b[4] = {(uint32_t)E, (uint32_t)bn, 1, 1};
+    if (make_map(&mb, dtype, B, d, s, b, ones)) return -1;
+  }
+  dim3 grid(sn::div_up(M, 128), sn::div_up(N, bn), 1);
+  return launch(ma, mb, p, grid, (cudaStream_t)stream);
+}
+
+// NHWC implicit-GEMM convolution forward (also used for stride-1 data gradients with flipped weights):
+//   Y[n,oh,ow,co] = epi( sum_{t<ntaps, c<Cin} X[n, oh*stride + dh[t], ow*stride + dw[t], c] * Wt[co, t*Cin + c] )
+// X: [NB,H,W,Cin] contiguous; Wt: [Cout, ntaps*Cin]; Y row (n,oh,ow) is written at
+// ((n*out_H + oh*out_s + out_oh)*out_W + ow*out_s + out_ow) * ldc.  Out-of-range taps read zeros (TMA fill).
+int sniper_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, const void* Wt, int Cout, int ntaps,
+                       const int* tap_dh, const int* tap_dw, int stride, int Ho, int Wo, float* Y, long ldc,
+                       int out_H, int out_W, int out_s, int out_oh, int out_ow, int dtype, const float* scale,
+                       const float* bias, const float* residual, long ldr, int relu, int accumulate, int out_bf16,
+                       void* stream) {
+  SN_CHECK(dtype == DT_TF32 || dtype == DT_BF16, "conv: dtype must be 0 (tf32) or 1 (bf16)");
+  const int esz = dtype == DT_TF32 ? 4 : 2;
+  const int E = 128 / esz;
+  SN_CHECK(Cin % E == 0, "conv: Cin (%d) must be a multiple of %d", Cin, E);
+  SN_CHECK(ntaps >= 1 && ntaps <= kMaxTaps, "conv: ntaps (%d) out of range", ntaps);
+  SN_CHECK(stride == 1 || stride == 2, "conv: stride must be 1 or 2");
+  int tile_w = Wo >= 128 ? 128 : Wo;
+  SN_CHECK(128 % tile_w == 0 && Wo % tile_w == 0, "conv: Wo (%d) must divide or be a multiple of 128", Wo);
+  int tile_h = 128 / tile_w;
+  SN_CHECK(tile_w * stride <= 256, "conv: TMA box too wide");
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int bn = pick_block_n(Cout);
+  fill_kmajor(p, dtype, bn);
+  p.mode = MODE_CONV; p.N = Cout; p.cblocks = Cin / E; p.ntaps = ntaps; p.num_kb = ntaps * p.cblocks;
+  for (int t = 0; t < ntaps; ++t) { p.tap_dh[t] = tap_dh[t]; p.tap_dw[t] = tap_dw[t]; }
+  p.conv_stride = stride; p.tile_w = tile_w; p.tile_h = tile_h;
+  p.tiles_w = Wo / tile_w; p.tiles_per_img = p.tiles_w * sn::div_up(Ho, tile_h);
+  p.Ho = Ho; p.Wo = Wo; p.M = NB * Ho * Wo;
+  p.C = Y; p.ldc = ldc; p.scale = scale; p.bias = bias; p.residual = residual; p.ldr = ldr; p.relu = relu;
+  p.atomic = accumulate; p.out_bf16 = out_bf16;
+  p.out_H = out_H; p.out_W = out_W; p.out_s = out_s; p.out_oh = out_oh; p.out_ow = out_ow;
+  CUtensorMap ma, mb;
+  {
+    const uint64_t d[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    const uint64_t s[3] = {(uint64_t)Cin * esz, (uint64_t)Cin * esz * W, (uint64_t)Cin * esz * W * H};
+    // with elementStrides the box extent is in un-strided elements
+    const uint32_t b[4] = {(uint32_t)E, (uint32_t)(tile_w * stride), (uint32_t)(tile_h * stride), 1};
+    const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (make_map(&ma, dtype, X, d, s, b, es)) return -1;
+  }
+  {
+    const uint64_t K = (uint64_t)ntaps * Cin;
+    const uint64_t d[4] = {K, (uint64_t)Cout, 1, 1};
+    const uint64_t s[3] = {K * esz, K * esz * Cout, K * esz * Cout};
+    const uint32_t b[4] = {(uint32_t)E, (uint32_t)bn, 1, 1};
+    const uint32_t ones[4] = {1, 1, 1, 1};
+    if (make_map(&mb, dtype, Wt, d, s, b, ones)) return -1;
+  }
+  dim3 grid(NB * p.tiles_per_img, sn::div_up(Cout, bn), 1);
+  return launch(ma, mb, p, grid, (cudaStream_t)stream);
+}
+
+// Weight gradient:  dW[co, t*Cin + ci] += sum_{n,oh,ow} dY[(n,oh,ow), co] * X[n, oh*stride+dh[t], ow*stride+dw[t], ci]
+// dY: [NB*Ho*Wo, Cout] contiguous rows (ld = Cout); X: [NB,H,W,Cin]; dW must be zero-initialised by the caller
+// (accumulated with red.global.add across split-K CTAs).  ntaps = 1, dh=dw=0, H=Ho, W=Wo gives dY^T * X (FC layers).
+int sniper_conv2d_wgrad_nhwc(const void* dY, const void* X, int NB, int H, int W, int Cin, int Cout, int ntaps,
+                             const int* tap_dh, const int* tap_dw, int stride, int Ho, int Wo, float* dW, int dtype,
+                             int splits, void* stream) {
+  SN_CHECK(dtype == DT_TF32 || dtype == DT_BF16, "wgrad: dtype must be 0 (tf32) or 1 (bf16)");
+  const int esz = dtype == DT_TF32 ? 4 : 2;
+  const int E = 128 / esz;       // elements per 128-byte MN chunk
+  const int kp = dtype == DT_TF32 ? 32 : 64;  // pixels per k-block
+  SN_CHECK(Cin % 64 == 0, "wgrad: Cin (%d) must be a multiple of 64", Cin);
+  SN_CHECK(Cout % E == 0, "wgrad: Cout (%d) must be a multiple of %d", Cout, E);
+  SN_CHECK(ntaps >= 1 && ntaps <= kMaxTaps, "wgrad: ntaps out of range");
+  const long pixels = (long)NB * Ho * Wo;
+  SN_CHECK(Wo % kp == 0 || kp % Wo == 0, "wgrad: Wo (%d) incompatible with k-block of %d pixels", Wo, kp);
+  SN_CHECK(pixels % kp == 0 && (Wo >= kp || (Ho * Wo) % kp == 0), "wgrad: pixel count must tile by %d", kp);
+  const int bw = Wo >= kp ? kp : Wo, bh = kp / bw;
+  const int bn = Cin % 128 == 0 ? 128 : 64;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = MODE_WGRAD; p.dtype = dtype; p.block_n = bn; p.elems_per_128B = E;
+  p.M = Cout; p.N = ntaps * Cin;
+  p.idesc = make_idesc(dtype, 1, 1, 128, bn);
+  const uint32_t chunk_bytes = (uint32_t)kp * 128u;
+  p.a_lbo = chunk_bytes >> 4; p.a_sbo = 64; p.b_lbo = chunk_bytes >> 4; p.b_sbo = 64;
+  const int umma_k = 32 / esz;                       // 8 (tf32) / 16 (bf16) k-rows per MMA
+  p.a_kadv = (uint32_t)(umma_k * 128) >> 4; p.b_kadv = p.a_kadv;
+  p.mmas_per_kb = kp / umma_k;
+  p.a_boxes = 128 / E; p.b_boxes = bn / E;
+  p.a_box_bytes = chunk_bytes; p.b_box_bytes = chunk_bytes;
+  p.stages = pick_stages(bn);
+  p.ntaps = ntaps;
+  for (int t = 0; t < ntaps; ++t) { p.tap_dh[t] = tap_dh[t]; p.tap_dw[t] = tap_dw[t]; }
+  p.conv_stride = stride; p.Ho = Ho; p.Wo = Wo; p.kp = kp; p.wg_cin_blocks = Cin / bn;
+  const long total_kb = pixels / kp;
+  if (splits < 1) splits = 1;
+  while (splits > 1 && total_kb % splits != 0) --splits;
+  p.num_kb = (int)(total_kb / splits);
+  p.C = dW; p.ldc = (long)ntaps * Cin; p.atomic = 1;
+  CUtensorMap ma, mb;
+  {
+    const uint64_t d[4] = {(uint64_t)Cout, (uint64_t)pixels, 1, 1};
+    const uint64_t s[3] = {(uint64_t)Cout * esz, (uint64_t)Cout * esz * pixels, (uint64_t)Cout * esz * pixels};
+    const uint32_t b[4] = {(uint32_t)E, (uint32_t)kp, 1, 1};
+    const uint32_t ones[4] = {1, 1, 1, 1};
+    if (make_map(&ma, dtype, dY, d, s, b, ones)) return -1;
+  }
+  {
+    const uint64_t d[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+    const uint64_t s[3] = {(uint64_t)Cin * esz, (uint64_t)Cin * esz * W, (uint64_t)Cin * esz * W * H};
+    const uint32_t b[4] = {(uint32_t)E, (uint32_t)(bw * stride), (uint32_t)(bh * stride), 1};
+    const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (make_map(&mb, dtype, X, d, s, b, es)) return -1;
+  }
+  dim3 grid(Cout / 128 + (Cout % 128 ? 1 : 0), ntaps * p.wg_cin_blocks, splits);
+  return launch(ma, mb, p, grid, (cudaStream_t)stream);
+}
+
+}  // extern "C"

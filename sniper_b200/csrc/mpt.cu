@@ -1,0 +1,462 @@
+// MultiProposalTarget on device, zero host round trips.
+//
+// Replaces SNIPER-mxnet/src/operator/multi_proposal_target.cu (MultiProposalTargetGPUOp::Forward,
+// :362-589): getProps (:263-331) -> mpt_decode_kernel; NonMaximumSuppression (:117-260) plus the
+// host-side GT-append / IoU / label / bbox-target section (:435-588) -> mpt_nms_assign_kernel.
+// Semantics are the reference GPU operator's (not the .cc CPU operator's); arithmetic is written
+// with explicit round-to-nearest intrinsics so that no FMA contraction can change a bit relative
+// to oracle/mpt.c.
+//
+// Layout in HBM (per call workspace):  boxes float4[B*A*H*W] | score float[B*A*H*W] | area float[..]
+// (SoA instead of the reference's 6-float AoS rows: 16-byte box loads, coalesced score scans).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int kMaxAnchors = 64;
+struct AnchorTable {
+  float v[4 * kMaxAnchors];
+};
+
+// Same fixed operation sequence as oracle_expf (oracle/mpt.c): double arithmetic, one rounding.
+__device__ __forceinline__ float sn_expf(float x) {
+  if (x != x) return x;
+  double xd = (double)x;
+  if (xd > 100.0) return __int_as_float(0x7f800000);
+  if (xd < -110.0) return 0.0f;
+  double k = rint(__dmul_rn(xd, 1.4426950408889634));
+  double r = __fma_rn(-k, 0.6931471803691238, xd);
+  r = __fma_rn(-k, 1.9082149292705877e-10, r);
+  double p = 1.0 / 39916800.0;
+  p = __fma_rn(p, r, 1.0 / 3628800.0);
+  p = __fma_rn(p, r, 1.0 / 362880.0);
+  p = __fma_rn(p, r, 1.0 / 40320.0);
+  p = __fma_rn(p, r, 1.0 / 5040.0);
+  p = __fma_rn(p, r, 1.0 / 720.0);
+  p = __fma_rn(p, r, 1.0 / 120.0);
+  p = __fma_rn(p, r, 1.0 / 24.0);
+  p = __fma_rn(p, r, 1.0 / 6.0);
+  p = __fma_rn(p, r, 0.5);
+  p = __fma_rn(p, r, 1.0);
+  p = __fma_rn(p, r, 1.0);
+  long long ki = (long long)k;
+  double s = __longlong_as_double((ki + 1023) << 52);
+  return (float)__dmul_rn(p, s);
+}
+
+// layout 0: NCHW (reference), layout 1: NHWC with channel strides c_score / c_delta.
+struct DecodeArgs {
+  const float* scores;   // fg score of anchor a = channel (A + a)
+  const float* deltas;   // channels 4a..4a+3
+  const float* im_info;  // [B,3] (h, w, scale)
+  const float* valid_ranges;  // [B,2]
+  int B, A, H, W, stride, layout;
+  int score_cstride, delta_cstride;  // NHWC: number of channels per pixel in each tensor
+  float4* boxes;
+  float* score_out;
+  float* area_out;
+};
+
+__global__ void __launch_bounds__(256) mpt_decode_kernel(DecodeArgs p, AnchorTable anchors) {
+  const int HW = p.H * p.W;
+  const int AHW = p.A * HW;
+  const long total = (long)p.B * AHW;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int b = (int)(t / AHW);
+    const int index = (int)(t - (long)b * AHW);
+    const int a = index / HW;
+    const int mat = index - a * HW;
+    const int h = mat / p.W;
+    const int w = mat - h * p.W;
+    float score, dx, dy, dw, dh;
+    if (p.layout == 0) {
+      score = __ldg(p.scores + (size_t)b * AHW * 2 + (size_t)((p.A + a) * p.H + h) * p.W + w);
+      const float* d = p.deltas + (size_t)b * AHW * 4 + (size_t)a * 4 * HW + h * p.W + w;
+      dx = __ldg(d);
+      dy = __ldg(d + HW);
+      dw = __ldg(d + 2 * HW);
+      dh = __ldg(d + 3 * HW);
+    } else {
+      const size_t pix = (size_t)b * HW + mat;
+      score = __ldg(p.scores + pix * p.score_cstride + p.A + a);
+      const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.deltas + pix * p.delta_cstride + 4 * a));
+      dx = d4.x; dy = d4.y; dw = d4.z; dh = d4.w;
+    }
+    float bx0 = __fadd_rn(anchors.v[4 * a + 0], (float)(w * p.stride));
+    float by0 = __fadd_rn(anchors.v[4 * a + 1], (float)(h * p.stride));
+    float bx1 = __fadd_rn(anchors.v[4 * a + 2], (float)(w * p.stride));
+    float by1 = __fadd_rn(anchors.v[4 * a + 3], (float)(h * p.stride));
+    const float width = (float)__dadd_rn((double)__fsub_rn(bx1, bx0), 1.0);
+    const float height = (float)__dadd_rn((double)__fsub_rn(by1, by0), 1.0);
+    const float ctr_x = (float)__dadd_rn((double)bx0, __dmul_rn(0.5, __dadd_rn((double)width, -1.0)));
+    const float ctr_y = (float)__dadd_rn((double)by0, __dmul_rn(0.5, __dadd_rn((double)height, -1.0)));
+    const float pred_ctr_x = __fadd_rn(__fmul_rn(dx, width), ctr_x);
+    const float pred_ctr_y = __fadd_rn(__fmul_rn(dy, height), ctr_y);
+    const float pred_w = __fmul_rn(sn_expf(dw), width);
+    const float pred_h = __fmul_rn(sn_expf(dh), height);
+    const double hw_ = __dmul_rn(0.5, __dadd_rn((double)pred_w, -1.0));
+    const double hh_ = __dmul_rn(0.5, __dadd_rn((double)pred_h, -1.0));
+    float x1 = (float)__dadd_rn((double)pred_ctr_x, -hw_);
+    float y1 = (float)__dadd_rn((double)pred_ctr_y, -hh_);
+    float x2 = (float)__dadd_rn((double)pred_ctr_x, hw_);
+    float y2 = (float)__dadd_rn((double)pred_ctr_y, hh_);
+    const float imw = __fsub_rn(__ldg(p.im_info + 3 * b + 1), 1.0f);
+    const float imh = __fsub_rn(__ldg(p.im_info + 3 * b), 1.0f);
+    x1 = fmaxf(fminf(x1, imw), 0.0f);
+    y1 = fmaxf(fminf(y1, imh), 0.0f);
+    x2 = fmaxf(fminf(x2, imw), 0.0f);
+    y2 = fmaxf(fminf(y2, imh), 0.0f);
+    if (__fsub_rn(y2, y1) < 3.0f && __fsub_rn(x2, x1) < 3.0f) {
+      x1 = __fsub_rn(x1, 1.0f);
+      y1 = __fsub_rn(y1, 1.0f);
+      x2 = __fadd_rn(x2, 1.0f);
+      y2 = __fadd_rn(y2, 1.0f);
+      score = -1.0f;
+    }
+    const float area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+    const float vr0 = __ldg(p.valid_ranges + 2 * b), vr1 = __ldg(p.valid_ranges + 2 * b + 1);
+    if (area >= __fmul_rn(vr1, vr1) || area < __fmul_rn(vr0, vr0)) score = -1.0f;
+    p.boxes[t] = make_float4(x1, y1, x2, y2);
+    p.score_out[t] = score;
+    p.area_out[t] = area;
+  }
+}
+
+__device__ __forceinline__ uint32_t ord_desc(float f) {
+  // monotone map float -> uint32 such that larger float => smaller uint (for min-reduction)
+  uint32_t u = __float_as_uint(f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ~u;
+}
+__device__ __forceinline__ float ord_desc_inv(uint32_t k) {
+  uint32_t u = ~k;
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    unsigned long long o = __shfl_xor_sync(0xffffffffu, v, off);
+    v = o < v ? o : v;
+  }
+  return v;
+}
+
+__device__ __forceinline__ float iou_ref(float ix1, float iy1, float ix2, float iy2, float iarea, float4 d,
+                                         float darea) {
+  // multi_proposal_target.cu:229-237: inter uses +1, areas do not
+  const float xx1 = fmaxf(ix1, d.x), yy1 = fmaxf(iy1, d.y);
+  const float xx2 = fminf(ix2, d.z), yy2 = fminf(iy2, d.w);
+  const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+  const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+  const float inter = __fmul_rn(w, h);
+  return __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, darea), inter));
+}
+
+struct NmsArgs {
+  const float4* boxes;
+  const float* scores;
+  const float* areas;
+  const float* gt_boxes;      // [B,max_gt,5]
+  const float* valid_ranges;  // [B,2]
+  int AHW, R, max_gt;
+  float nms_thresh;
+  float* rois;         // [B*R,5]
+  float* label;        // [B*R]
+  float* bbox_target;  // [B*R,4]
+  float* bbox_weight;  // [B*R,4]
+  int32_t* keep_idx;   // optional [B*R]
+  int32_t* num_kept;   // optional [B]
+  int do_assign;       // 0: proposals only (MultiProposal-style output), 1: full target assignment
+};
+
+constexpr int kNmsThreads = 1024;
+
+// One CTA per chip.  Positions 0..AHW-1 hold (score, id) in shared memory; the reference's row swap
+// (cu:178-199) becomes a 6-byte swap here, the 16-byte boxes never move.  Tie order of the
+// reference's three-level strided argmax (cu:139-176) == lexicographic (lane, warp, stride index)
+// among equal scores, which is what the packed 64-bit key below encodes.
+__global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_assign_kernel(NmsArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* s_score = reinterpret_cast<float*>(smem_raw);
+  uint16_t* s_id = reinterpret_cast<uint16_t*>(s_score + p.AHW);
+  __shared__ unsigned long long s_warpkey[32];
+  __shared__ int s_keep[1024];
+  __shared__ int s_numgt;
+  const int chip = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int AHW = p.AHW;
+  const float4* boxes = p.boxes + (size_t)chip * AHW;
+  const float* areas = p.areas + (size_t)chip * AHW;
+  for (int i = t; i < AHW; i += kNmsThreads) {
+    s_score[i] = p.scores[(size_t)chip * AHW + i];
+    s_id[i] = (uint16_t)i;
+  }
+  if (t == 0) s_numgt = 0;
+  __syncthreads();
+
+  int vct = 0;
+  for (int j = 0; j < AHW && vct < p.R; ++j) {
+    // ---- argmax over positions >= j (cu:139-176)
+    float best = -2.0f;
+    uint32_t besti = 0, bestid = 0;
+    {
+      int i = 0;
+      for (int pos = j + t; pos < AHW; pos += kNmsThreads, ++i) {
+        const float s = s_score[pos];
+        if (s > best) {
+          best = s;
+          besti = i;
+          bestid = s_id[pos];
+        }
+      }
+    }
+    unsigned long long key = ((unsigned long long)ord_desc(best) << 32) |
+                             ((unsigned long long)((lane << 26) | (warp << 21) | (besti << 16) | bestid));
+    key = warp_min_u64(key);
+    if (lane == 0) s_warpkey[warp] = key;
+    __syncthreads();
+    key = warp_min_u64(s_warpkey[lane]);
+    const uint32_t lo = (uint32_t)key;
+    const float sel_score = ord_desc_inv((uint32_t)(key >> 32));
+    const int sel_id = lo & 0xffff;
+    const int m = j + (int)(((lo >> 21) & 31) * 32 + (lo >> 26)) + (int)((lo >> 16) & 31) * kNmsThreads;
+    if (sel_score == -1.0f) break;  // cu:214-216 (uniform across the block)
+    if (t == 0) s_keep[vct] = sel_id;
+    vct++;
+    const float4 sb = __ldg(boxes + sel_id);
+    const float sarea = __ldg(areas + sel_id);
+    // element displaced from position j by the swap lands on position m
+    const float oldj_score = s_score[j];
+    const uint16_t oldj_id = s_id[j];
+    // ---- suppression over positions > j (cu:218-240)
+    for (int pos = j + 1 + t; pos < AHW; pos += kNmsThreads) {
+      float s;
+      int id;
+      if (pos == m) {
+        s = oldj_score;
+        id = oldj_id;
+        s_id[pos] = oldj_id;
+      } else {
+        s = s_score[pos];
+        id = s_id[pos];
+      }
+      if (s != -1.0f) {
+        const float4 d = __ldg(boxes + id);
+        const float da = __ldg(areas + id);
+        const float ovr = iou_ref(sb.x, sb.y, sb.z, sb.w, sarea, d, da);
+        if (ovr > p.nms_thresh) s = -1.0f;
+      }
+      if (pos == m || s == -1.0f) s_score[pos] = s;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+
+  // ---- outputs: kept rows, filler rows (cu:244-258), then the host section (cu:435-588)
+  const int R = p.R;
+  if (p.num_kept && t == 0) p.num_kept[chip] = vct;
+  if (!p.do_assign) {
+    for (int r = t; r < R; r += kNmsThreads) {
+      float4 bx;
+      if (r < vct) {
+        bx = __ldg(boxes + s_keep[r]);
+      } else {
+        const float f = (float)(int)(((long)chip * AHW + r) % 100);
+        bx = make_float4(f, f, f + 200.0f, f + 200.0f);
+      }
+      float* o = p.rois + ((size_t)chip * R + r) * 5;
+      o[0] = (float)chip; o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w;
+      if (p.keep_idx) p.keep_idx[(size_t)chip * R + r] = r < vct ? s_keep[r] : -1;
+    }
+    return;
+  }
+  float* s_gt = s_score;  // reuse: [max_gt*5]
+  const float* gt = p.gt_boxes + (size_t)chip * p.max_gt * 5;
+  for (int i = t; i < p.max_gt * 5; i += kNmsThreads) s_gt[i] = gt[i];
+  __syncthreads();
+  {
+    int c = 0;
+    for (int g = t; g < p.max_gt; g += kNmsThreads) c += (s_gt[g * 5 + 4] != -1.0f);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (lane == 0 && c) atomicAdd(&s_numgt, c);
+  }
+  __syncthreads();
+  const int numgt = s_numgt;
+  const float vr0 = p.valid_ranges[2 * chip], vr1 = p.valid_ranges[2 * chip + 1];
+  for (int r = t; r < R; r += kNmsThreads) {
+    float4 bx;
+    if (r < vct) {
+      bx = __ldg(boxes + s_keep[r]);
+    } else {
+      const float f = (float)(int)(((long)chip * AHW + r) % 100);
+      bx = make_float4(f, f, f + 200.0f, f + 200.0f);
+    }
+    if (r >= R - numgt) {  // GT append, cu:469-479
+      const float* g = s_gt + (r - (R - numgt)) * 5;
+      const float area = __fmul_rn(__fsub_rn(g[2], g[0]), __fsub_rn(g[3], g[1]));
+      if (area >= __fmul_rn(vr0, vr0) && area <= __fmul_rn(vr1, vr1)) bx = make_float4(g[0], g[1], g[2], g[3]);
+    }
+    float lab = 0.0f, maxov = 0.0f;
+    int arg = -1;
+    const float a2 = __fmul_rn(__fsub_rn(bx.z, bx.x), __fsub_rn(bx.w, bx.y));
+    for (int g = 0; g < numgt; ++g) {  // cu:503-531, first max wins ties (strict >)
+      const float* gb = s_gt + g * 5;
+      const float a1 = __fmul_rn(__fsub_rn(gb[2], gb[0]), __fsub_rn(gb[3], gb[1]));
+      const float ovr = iou_ref(gb[0], gb[1], gb[2], gb[3], a1, bx, a2);
+      if (ovr > maxov && ovr > 0.5f) {
+        maxov = ovr;
+        arg = g;
+        lab = gb[4];
+      }
+    }
+    float tg[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    float wt = 0.0f;
+    if (arg >= 0) {  // cu:537-573
+      wt = 1.0f;
+      const float* gb = s_gt + arg * 5;
+      const float gw = __fadd_rn(__fsub_rn(gb[2], gb[0]), 1.0f);
+      const float gh = __fadd_rn(__fsub_rn(gb[3], gb[1]), 1.0f);
+      const float gcx = (float)__dadd_rn((double)gb[0], __dmul_rn((double)gw, 0.5));
+      const float gcy = (float)__dadd_rn((double)gb[1], __dmul_rn((double)gh, 0.5));
+      const float pw = __fadd_rn(__fsub_rn(bx.z, bx.x), 1.0f);
+      const float ph = __fadd_rn(__fsub_rn(bx.w, bx.y), 1.0f);
+      const float pcx = (float)__dadd_rn((double)bx.x, __dmul_rn((double)__fsub_rn(pw, 1.0f), 0.5));
+      const float pcy = (float)__dadd_rn((double)bx.y, __dmul_rn((double)__fsub_rn(ph, 1.0f), 0.5));
+      const double pwe = __dadd_rn((double)pw, 1e-7), phe = __dadd_rn((double)ph, 1e-7);
+      tg[0] = (float)__ddiv_rn((double)__fmul_rn(10.0f, __fsub_rn(gcx, pcx)), pwe);
+      tg[1] = (float)__ddiv_rn((double)__fmul_rn(10.0f, __fsub_rn(gcy, pcy)), phe);
+      tg[2] = (float)__dmul_rn(5.0, log(__ddiv_rn((double)gw, pwe)));
+      tg[3] = (float)__dmul_rn(5.0, log(__ddiv_rn((double)gh, phe)));
+    }
+    const size_t row = (size_t)chip * R + r;
+    float* o = p.rois + row * 5;
+    o[0] = (float)chip; o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w;
+    p.label[row] = lab;
+    reinterpret_cast<float4*>(p.bbox_target)[row] = make_float4(tg[0], tg[1], tg[2], tg[3]);
+    reinterpret_cast<float4*>(p.bbox_weight)[row] = make_float4(wt, wt, wt, wt);
+    if (p.keep_idx) p.keep_idx[row] = r < vct ? s_keep[r] : -1;
+  }
+}
+
+// host twin of multi_proposal_target.cu:75-114 (anchor table is 4*A floats, passed by value)
+int make_anchors(int feat_stride, const float* scales, int ns, const float* ratios, int nr, AnchorTable* out) {
+  const float base2 = (float)(feat_stride - 1.0);
+  int n = 0;
+  for (int j = 0; j < nr; ++j) {
+    for (int k = 0; k < ns; ++k) {
+      const float scale = scales[k], ratio = ratios[j];
+      const float w = base2 - 0.0f + 1.0f, h = base2 - 0.0f + 1.0f;
+      const float x_ctr = (float)(0.0f + 0.5 * (w - 1.0f));
+      const float y_ctr = (float)(0.0f + 0.5 * (h - 1.0f));
+      const float size = w * h;
+      const float size_ratios = floorf(size / ratio);
+      const float new_w = floorf(sqrtf(size_ratios) + 0.5f) * scale;
+      const float new_h = floorf((new_w / scale * ratio) + 0.5f) * scale;
+      out->v[4 * n + 0] = x_ctr - 0.5f * (new_w - 1.0f);
+      out->v[4 * n + 1] = y_ctr - 0.5f * (new_h - 1.0f);
+      out->v[4 * n + 2] = x_ctr + 0.5f * (new_w - 1.0f);
+      out->v[4 * n + 3] = y_ctr + 0.5f * (new_h - 1.0f);
+      ++n;
+    }
+  }
+  return n;
+}
+
+size_t ws_bytes_impl(int B, int A, int H, int W) {
+  const size_t total = (size_t)B * A * H * W;
+  return total * (sizeof(float4) + 2 * sizeof(float)) + 256;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t sniper_multi_proposal_target_workspace_bytes(int B, int A, int H, int W) { return ws_bytes_impl(B, A, H, W); }
+
+int sniper_generate_anchors(int feat_stride, const float* scales, int ns, const float* ratios, int nr, float* out) {
+  SN_CHECK(ns * nr <= kMaxAnchors && ns > 0 && nr > 0, "generate_anchors: need 0 < ns*nr <= %d", kMaxAnchors);
+  AnchorTable t;
+  make_anchors(feat_stride, scales, ns, ratios, nr, &t);
+  memcpy(out, t.v, sizeof(float) * 4 * ns * nr);
+  return 0;
+}
+
+// Stage 1 only (K1): decode + clip + filters.  boxes/score/area are caller-owned device arrays.
+int sniper_proposal_decode(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                           const float* valid_ranges, int B, int A, int H, int W, int feat_stride,
+                           const float* scales, int ns, const float* ratios, int nr, int layout,
+                           int score_cstride, int delta_cstride, float* boxes, float* score, float* area,
+                           void* stream) {
+  SN_CHECK(A == ns * nr, "proposal_decode: A (%d) != ns*nr (%d)", A, ns * nr);
+  SN_CHECK(A <= kMaxAnchors, "proposal_decode: A (%d) > %d", A, kMaxAnchors);
+  SN_CHECK(layout == 0 || layout == 1, "proposal_decode: layout must be 0 (NCHW) or 1 (NHWC)");
+  SN_CHECK(layout == 0 || (delta_cstride % 4 == 0 && ((uintptr_t)bbox_pred & 15) == 0),
+           "proposal_decode: NHWC deltas need 16-byte aligned pixels");
+  AnchorTable t;
+  make_anchors(feat_stride, scales, ns, ratios, nr, &t);
+  DecodeArgs a;
+  a.scores = cls_prob; a.deltas = bbox_pred; a.im_info = im_info; a.valid_ranges = valid_ranges;
+  a.B = B; a.A = A; a.H = H; a.W = W; a.stride = feat_stride; a.layout = layout;
+  a.score_cstride = score_cstride; a.delta_cstride = delta_cstride;
+  a.boxes = reinterpret_cast<float4*>(boxes); a.score_out = score; a.area_out = area;
+  const long total = (long)B * A * H * W;
+  int grid = sn::div_up(total, 256);
+  if (grid > sn::kNumSMs * 8) grid = sn::kNumSMs * 8;
+  mpt_decode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, t);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+static int nms_assign_launch(const float* boxes, const float* score, const float* area, const float* gt_boxes,
+                             const float* valid_ranges, int B, int AHW, int max_gt, int R, float nms_thresh,
+                             float* rois, float* label, float* bbox_target, float* bbox_weight,
+                             int32_t* keep_idx, int32_t* num_kept, int do_assign, void* stream) {
+  SN_CHECK(AHW >= R, "nms: anchors per chip (%d) < post_nms_top_n (%d)", AHW, R);
+  SN_CHECK(AHW <= 32768, "nms: anchors per chip (%d) > 32768", AHW);
+  SN_CHECK(R <= 1024, "nms: post_nms_top_n (%d) > 1024", R);
+  SN_CHECK(!do_assign || (max_gt <= R && max_gt * 5 <= AHW), "nms: max_gt (%d) too large", max_gt);
+  NmsArgs n;
+  n.boxes = reinterpret_cast<const float4*>(boxes); n.scores = score; n.areas = area;
+  n.gt_boxes = gt_boxes; n.valid_ranges = valid_ranges; n.AHW = AHW; n.R = R; n.max_gt = max_gt;
+  n.nms_thresh = nms_thresh; n.rois = rois; n.label = label; n.bbox_target = bbox_target;
+  n.bbox_weight = bbox_weight; n.keep_idx = keep_idx; n.num_kept = num_kept; n.do_assign = do_assign;
+  const size_t smem = (size_t)AHW * 6 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SN_CUDA(cudaFuncSetAttribute(mpt_nms_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  mpt_nms_assign_kernel<<<B, kNmsThreads, smem, (cudaStream_t)stream>>>(n);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Drop-in for MultiProposalTargetGPUOp::Forward.  All pointers are device pointers owned by the
+// caller; no allocation and no synchronisation happen inside.
+int sniper_multi_proposal_target_fwd(const float* cls_prob, const float* bbox_pred, const float* im_info,
+                                     const float* gt_boxes, const float* valid_ranges, int B, int A, int H, int W,
+                                     int max_gt, int post_nms_top_n, int feat_stride, const float* scales, int ns,
+                                     const float* ratios, int nr, float nms_thresh, int layout, int score_cstride,
+                                     int delta_cstride, float* rois, float* label, float* bbox_target,
+                                     float* bbox_weight, int32_t* keep_idx, int32_t* num_kept, void* workspace,
+                                     size_t ws_bytes, void* stream) {
+  SN_CHECK(ws_bytes >= ws_bytes_impl(B, A, H, W), "multi_proposal_target: workspace too small (%zu < %zu)", ws_bytes,
+           ws_bytes_impl(B, A, H, W));
+  SN_CHECK(((uintptr_t)workspace & 15) == 0, "multi_proposal_target: workspace must be 16-byte aligned");
+  SN_CHECK(((uintptr_t)bbox_target & 15) == 0 && ((uintptr_t)bbox_weight & 15) == 0,
+           "multi_proposal_target: bbox_target/bbox_weight must be 16-byte aligned");
+  const size_t total = (size_t)B * A * H * W;
+  float* boxes = reinterpret_cast<float*>(workspace);
+  float* score = boxes + 4 * total;
+  float* area = score + total;
+  if (sniper_proposal_decode(cls_prob, bbox_pred, im_info, valid_ranges, B, A, H, W, feat_stride, scales, ns, ratios,
+                             nr, layout, score_cstride, delta_cstride, boxes, score, area, stream))
+    return -1;
+  return nms_assign_launch(boxes, score, area, gt_boxes, valid_ranges, B, A * H * W, max_gt, post_nms_top_n,
+                           nms_thresh, rois, label, bbox_target, bbox_weight, keep_idx, num_kept, 1, stream);
+}
+
+}  // extern "C"

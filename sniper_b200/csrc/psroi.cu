@@ -1,0 +1,385 @@
+// DeformablePSROIPooling / PSROIPooling forward + backward.
+//
+// Replaces SNIPER-mxnet/src/operator/contrib/deformable_psroi_pooling.cu (fwd :71-161, bwd :203-330,
+// bilinear_interp :49-68) and psroi_pooling.cu (fwd :51-118, bwd :146-210).  Bin / sample geometry is
+// evaluated with explicit round-to-nearest intrinsics in the order of the reference source so that
+// every floor/ceil/clamp index equals oracle/psroi.c bit for bit.
+//
+// Two layouts: 0 = NCHW data, (n,c,ph,pw) output (the reference's, used by the drop-in operator);
+// 1 = NHWC data [B,H,W,C], (n,ph,pw,c) output (the native layout of this framework: a warp owns 32
+// consecutive channels of one bin, so every bilinear corner is one coalesced 128-byte gather and the
+// backward scatter is a coalesced RED).
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+struct PsArgs {
+  const float* data;
+  const float* rois;
+  const float* trans;
+  int num_rois, channels, height, width;
+  float spatial_scale;
+  int output_dim, group_size, pooled, part_size, sample_per_part;
+  float trans_std;
+  int no_trans, num_classes, channels_each_class;
+  int layout;
+  float* top_data;
+  float* top_count;      // optional
+  int32_t* sample_idx;   // optional debug/parity output, oracle order
+  // backward
+  const float* top_diff;
+  float* data_diff;
+  float* trans_diff;
+};
+
+struct Geom {
+  int roi_batch_ind, part_h, part_w, class_id, c;
+  float roi_width, roi_height, wstart, hstart, sub_w, sub_h;
+};
+
+__device__ __forceinline__ void decompose(const PsArgs& p, long index, int& n, int& ctop, int& ph, int& pw) {
+  if (p.layout == 0) {
+    pw = (int)(index % p.pooled);
+    ph = (int)((index / p.pooled) % p.pooled);
+    ctop = (int)((index / p.pooled / p.pooled) % p.output_dim);
+    n = (int)(index / p.pooled / p.pooled / p.output_dim);
+  } else {
+    ctop = (int)(index % p.output_dim);
+    pw = (int)((index / p.output_dim) % p.pooled);
+    ph = (int)((index / p.output_dim / p.pooled) % p.pooled);
+    n = (int)(index / p.output_dim / p.pooled / p.pooled);
+  }
+}
+
+__device__ __forceinline__ long ref_index(const PsArgs& p, int n, int ctop, int ph, int pw) {
+  return (((long)n * p.output_dim + ctop) * p.pooled + ph) * p.pooled + pw;
+}
+
+__device__ __forceinline__ size_t data_off(const PsArgs& p, int b, int c, int y, int x) {
+  return p.layout == 0 ? (((size_t)b * p.channels + c) * p.height + y) * p.width + x
+                       : (((size_t)b * p.height + y) * p.width + x) * p.channels + c;
+}
+
+__device__ __forceinline__ void deform_geom(const PsArgs& p, int n, int ctop, int ph, int pw, Geom& g) {
+  const float* r = p.rois + (size_t)n * 5;
+  g.roi_batch_ind = (int)r[0];
+  const float roi_start_w = (float)__dadd_rn((double)__fmul_rn(roundf(r[1]), p.spatial_scale), -0.5);
+  const float roi_start_h = (float)__dadd_rn((double)__fmul_rn(roundf(r[2]), p.spatial_scale), -0.5);
+  const float roi_end_w =
+      (float)__dadd_rn((double)__fmul_rn((float)__dadd_rn((double)roundf(r[3]), 1.0), p.spatial_scale), -0.5);
+  const float roi_end_h =
+      (float)__dadd_rn((double)__fmul_rn((float)__dadd_rn((double)roundf(r[4]), 1.0), p.spatial_scale), -0.5);
+  g.roi_width = (float)fmax((double)__fsub_rn(roi_end_w, roi_start_w), 0.1);
+  g.roi_height = (float)fmax((double)__fsub_rn(roi_end_h, roi_start_h), 0.1);
+  const float bin_size_h = __fdiv_rn(g.roi_height, (float)p.pooled);
+  const float bin_size_w = __fdiv_rn(g.roi_width, (float)p.pooled);
+  g.sub_h = __fdiv_rn(bin_size_h, (float)p.sample_per_part);
+  g.sub_w = __fdiv_rn(bin_size_w, (float)p.sample_per_part);
+  g.part_h = (int)floorf(__fmul_rn(__fdiv_rn((float)ph, (float)p.pooled), (float)p.part_size));
+  g.part_w = (int)floorf(__fmul_rn(__fdiv_rn((float)pw, (float)p.pooled), (float)p.part_size));
+  g.class_id = ctop / p.channels_each_class;
+  float trans_x = 0.0f, trans_y = 0.0f;
+  if (!p.no_trans) {
+    const size_t tb = (((size_t)(n * p.num_classes + g.class_id) * 2) * p.part_size + g.part_h) * p.part_size + g.part_w;
+    trans_x = __fmul_rn(p.trans[tb], p.trans_std);
+    trans_y = __fmul_rn(p.trans[tb + (size_t)p.part_size * p.part_size], p.trans_std);
+  }
+  float wstart = __fadd_rn(__fmul_rn((float)pw, bin_size_w), roi_start_w);
+  wstart = __fadd_rn(wstart, __fmul_rn(trans_x, g.roi_width));
+  float hstart = __fadd_rn(__fmul_rn((float)ph, bin_size_h), roi_start_h);
+  hstart = __fadd_rn(hstart, __fmul_rn(trans_y, g.roi_height));
+  g.wstart = wstart;
+  g.hstart = hstart;
+  int gw = (int)floorf(__fdiv_rn(__fmul_rn((float)pw, (float)p.group_size), (float)p.pooled));
+  int gh = (int)floorf(__fdiv_rn(__fmul_rn((float)ph, (float)p.group_size), (float)p.pooled));
+  gw = min(max(gw, 0), p.group_size - 1);
+  gh = min(max(gh, 0), p.group_size - 1);
+  g.c = (ctop * p.group_size + gh) * p.group_size + gw;
+}
+
+// returns false if the sample is skipped (deformable_psroi_pooling.cu:147-149)
+__device__ __forceinline__ bool sample_pos(const PsArgs& p, const Geom& g, int ih, int iw, float& w, float& h) {
+  w = __fadd_rn(g.wstart, __fmul_rn((float)iw, g.sub_w));
+  h = __fadd_rn(g.hstart, __fmul_rn((float)ih, g.sub_h));
+  if ((double)w < -0.5 || (double)w > (double)p.width - 0.5 || (double)h < -0.5 || (double)h > (double)p.height - 0.5)
+    return false;
+  w = (float)fmin(fmax((double)w, 0.), (double)p.width - 1.);
+  h = (float)fmin(fmax((double)h, 0.), (double)p.height - 1.);
+  return true;
+}
+
+__global__ void __launch_bounds__(256) deform_psroi_fwd_kernel(PsArgs p, long count) {
+  for (long index = (long)blockIdx.x * blockDim.x + threadIdx.x; index < count; index += (long)gridDim.x * blockDim.x) {
+    int n, ctop, ph, pw;
+    decompose(p, index, n, ctop, ph, pw);
+    Geom g;
+    deform_geom(p, n, ctop, ph, pw, g);
+    float sum = 0.0f;
+    int cnt = 0;
+    const int S = p.sample_per_part;
+    const long ridx = ref_index(p, n, ctop, ph, pw);
+    for (int ih = 0; ih < S; ++ih) {
+      for (int iw = 0; iw < S; ++iw) {
+        float w, h;
+        int32_t* si = p.sample_idx ? p.sample_idx + ((size_t)ridx * S * S + ih * S + iw) * 4 : nullptr;
+        if (!sample_pos(p, g, ih, iw, w, h)) {
+          if (si) si[0] = si[1] = si[2] = si[3] = -1;
+          continue;
+        }
+        const int x1 = (int)floorf(w), x2 = (int)ceilf(w), y1 = (int)floorf(h), y2 = (int)ceilf(h);
+        const float dist_x = __fsub_rn(w, (float)x1), dist_y = __fsub_rn(h, (float)y1);
+        const float v11 = __ldg(p.data + data_off(p, g.roi_batch_ind, g.c, y1, x1));
+        const float v12 = __ldg(p.data + data_off(p, g.roi_batch_ind, g.c, y2, x1));
+        const float v21 = __ldg(p.data + data_off(p, g.roi_batch_ind, g.c, y1, x2));
+        const float v22 = __ldg(p.data + data_off(p, g.roi_batch_ind, g.c, y2, x2));
+        const float omx = __fsub_rn(1.0f, dist_x), omy = __fsub_rn(1.0f, dist_y);
+        float val = __fmul_rn(__fmul_rn(omx, omy), v11);
+        val = __fadd_rn(val, __fmul_rn(__fmul_rn(omx, dist_y), v12));
+        val = __fadd_rn(val, __fmul_rn(__fmul_rn(dist_x, omy), v21));
+        val = __fadd_rn(val, __fmul_rn(__fmul_rn(dist_x, dist_y), v22));
+        sum = __fadd_rn(sum, val);
+        cnt++;
+        if (si) {
+          si[0] = y1 * p.width + x1; si[1] = y2 * p.width + x1;
+          si[2] = y1 * p.width + x2; si[3] = y2 * p.width + x2;
+        }
+      }
+    }
+    p.top_data[index] = cnt == 0 ? 0.0f : __fdiv_rn(sum, (float)cnt);
+    if (p.top_count) p.top_count[index] = (float)cnt;
+  }
+}
+
+__global__ void __launch_bounds__(256) deform_psroi_bwd_kernel(PsArgs p, long count) {
+  const int lane = threadIdx.x & 31;
+  for (long base = (long)blockIdx.x * blockDim.x + threadIdx.x - lane; base < count;
+       base += (long)gridDim.x * blockDim.x) {
+    const long index = base + lane;
+    const bool active = index < count;
+    int n = 0, ctop = 0, ph = 0, pw = 0;
+    Geom g;
+    float diff_val = 0.0f;
+    int cnt = 0;
+    const int S = p.sample_per_part;
+    if (active) {
+      decompose(p, index, n, ctop, ph, pw);
+      deform_geom(p, n, ctop, ph, pw, g);
+      for (int ih = 0; ih < S; ++ih)
+        for (int iw = 0; iw < S; ++iw) {
+          float w, h;
+          cnt += sample_pos(p, g, ih, iw, w, h) ? 1 : 0;
+        }
+      if (cnt > 0) diff_val = __fdiv_rn(p.top_diff[index], (float)cnt);
+    }
+    float tdx = 0.0f, tdy = 0.0f;
+    if (active && cnt > 0) {
+      for (int ih = 0; ih < S; ++ih) {
+        for (int iw = 0; iw < S; ++iw) {
+          float w, h;
+          if (!sample_pos(p, g, ih, iw, w, h)) continue;
+          const int x0 = (int)floorf(w), x1 = (int)ceilf(w), y0 = (int)floorf(h), y1 = (int)ceilf(h);
+          const float dist_x = w - x0, dist_y = h - y0;
+          const float q00 = (1 - dist_x) * (1 - dist_y), q01 = (1 - dist_x) * dist_y;
+          const float q10 = dist_x * (1 - dist_y), q11 = dist_x * dist_y;
+          const size_t o00 = data_off(p, g.roi_batch_ind, g.c, y0, x0), o01 = data_off(p, g.roi_batch_ind, g.c, y1, x0);
+          const size_t o10 = data_off(p, g.roi_batch_ind, g.c, y0, x1), o11 = data_off(p, g.roi_batch_ind, g.c, y1, x1);
+          atomicAdd(p.data_diff + o00, q00 * diff_val);
+          atomicAdd(p.data_diff + o01, q01 * diff_val);
+          atomicAdd(p.data_diff + o10, q10 * diff_val);
+          atomicAdd(p.data_diff + o11, q11 * diff_val);
+          if (p.no_trans) continue;
+          const float U00 = __ldg(p.data + o00), U01 = __ldg(p.data + o01);
+          const float U10 = __ldg(p.data + o10), U11 = __ldg(p.data + o11);
+          float dx = (U11 * dist_y + U10 * (1 - dist_y) - U01 * dist_y - U00 * (1 - dist_y)) * p.trans_std * diff_val;
+          float dy = (U11 * dist_x + U01 * (1 - dist_x) - U10 * dist_x - U00 * (1 - dist_x)) * p.trans_std * diff_val;
+          tdx += dx * g.roi_width;
+          tdy += dy * g.roi_height;
+        }
+      }
+    }
+    if (!p.no_trans) {
+      // NHWC order: the 32 lanes of a warp are 32 channels of one bin -> one atomic per warp when
+      // they share (n, class, part); otherwise fall back to per-lane atomics.
+      const size_t tb = active ? (((size_t)(n * p.num_classes + g.class_id) * 2) * p.part_size + g.part_h) * p.part_size + g.part_w
+                               : (size_t)-1;
+      const size_t tb0 = __shfl_sync(0xffffffffu, tb, 0);
+      const bool uniform = __all_sync(0xffffffffu, tb == tb0 || !active);
+      if (uniform && tb0 != (size_t)-1) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          tdx += __shfl_xor_sync(0xffffffffu, tdx, off);
+          tdy += __shfl_xor_sync(0xffffffffu, tdy, off);
+        }
+        if (lane == 0) {
+          atomicAdd(p.trans_diff + tb0, tdx);
+          atomicAdd(p.trans_diff + tb0 + (size_t)p.part_size * p.part_size, tdy);
+        }
+      } else if (active && cnt > 0) {
+        atomicAdd(p.trans_diff + tb, tdx);
+        atomicAdd(p.trans_diff + tb + (size_t)p.part_size * p.part_size, tdy);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void psroi_bin(const PsArgs& p, int n, int ph, int pw, int& b, int& hstart, int& hend,
+                                          int& wstart, int& wend) {
+  const float* r = p.rois + (size_t)n * 5;
+  b = (int)r[0];
+  const float roi_start_w = __fmul_rn(roundf(r[1]), p.spatial_scale);
+  const float roi_start_h = __fmul_rn(roundf(r[2]), p.spatial_scale);
+  const float roi_end_w = __fmul_rn((float)__dadd_rn((double)roundf(r[3]), 1.0), p.spatial_scale);
+  const float roi_end_h = __fmul_rn((float)__dadd_rn((double)roundf(r[4]), 1.0), p.spatial_scale);
+  const float roi_width = (float)fmax((double)__fsub_rn(roi_end_w, roi_start_w), 0.1);
+  const float roi_height = (float)fmax((double)__fsub_rn(roi_end_h, roi_start_h), 0.1);
+  const float bin_size_h = __fdiv_rn(roi_height, (float)p.pooled);
+  const float bin_size_w = __fdiv_rn(roi_width, (float)p.pooled);
+  hstart = (int)floorf(__fadd_rn(__fmul_rn((float)ph, bin_size_h), roi_start_h));
+  wstart = (int)floorf(__fadd_rn(__fmul_rn((float)pw, bin_size_w), roi_start_w));
+  hend = (int)ceilf(__fadd_rn(__fmul_rn((float)(ph + 1), bin_size_h), roi_start_h));
+  wend = (int)ceilf(__fadd_rn(__fmul_rn((float)(pw + 1), bin_size_w), roi_start_w));
+  hstart = min(max(hstart, 0), p.height);
+  hend = min(max(hend, 0), p.height);
+  wstart = min(max(wstart, 0), p.width);
+  wend = min(max(wend, 0), p.width);
+}
+
+__device__ __forceinline__ int psroi_channel(const PsArgs& p, int ctop, int ph, int pw) {
+  int gw = (int)floorf(__fdiv_rn(__fmul_rn((float)pw, (float)p.group_size), (float)p.pooled));
+  int gh = (int)floorf(__fdiv_rn(__fmul_rn((float)ph, (float)p.group_size), (float)p.pooled));
+  gw = min(max(gw, 0), p.group_size - 1);
+  gh = min(max(gh, 0), p.group_size - 1);
+  return (ctop * p.group_size + gh) * p.group_size + gw;
+}
+
+__global__ void __launch_bounds__(256) psroi_fwd_kernel(PsArgs p, long count) {
+  for (long index = (long)blockIdx.x * blockDim.x + threadIdx.x; index < count; index += (long)gridDim.x * blockDim.x) {
+    int n, ctop, ph, pw, b, hstart, hend, wstart, wend;
+    decompose(p, index, n, ctop, ph, pw);
+    psroi_bin(p, n, ph, pw, b, hstart, hend, wstart, wend);
+    const bool is_empty = (hend <= hstart) || (wend <= wstart);
+    const int c = psroi_channel(p, ctop, ph, pw);
+    float out_sum = 0.0f;
+    for (int h = hstart; h < hend; ++h)
+      for (int w = wstart; w < wend; ++w) out_sum = __fadd_rn(out_sum, __ldg(p.data + data_off(p, b, c, h, w)));
+    const float bin_area = (float)((hend - hstart) * (wend - wstart));
+    p.top_data[index] = is_empty ? 0.0f : __fdiv_rn(out_sum, bin_area);
+    if (p.sample_idx) {
+      int32_t* o = p.sample_idx + ref_index(p, n, ctop, ph, pw) * 4;
+      o[0] = hstart; o[1] = hend; o[2] = wstart; o[3] = wend;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) psroi_bwd_kernel(PsArgs p, long count) {
+  for (long index = (long)blockIdx.x * blockDim.x + threadIdx.x; index < count; index += (long)gridDim.x * blockDim.x) {
+    int n, ctop, ph, pw, b, hstart, hend, wstart, wend;
+    decompose(p, index, n, ctop, ph, pw);
+    psroi_bin(p, n, ph, pw, b, hstart, hend, wstart, wend);
+    const bool is_empty = (hend <= hstart) || (wend <= wstart);
+    if (is_empty) continue;
+    const int c = psroi_channel(p, ctop, ph, pw);
+    const float bin_area = (float)((hend - hstart) * (wend - wstart));
+    const float diff_val = __fdiv_rn(p.top_diff[index], bin_area);
+    for (int h = hstart; h < hend; ++h)
+      for (int w = wstart; w < wend; ++w) atomicAdd(p.data_diff + data_off(p, b, c, h, w), diff_val);
+  }
+}
+
+int grid_for(long count) {
+  long g = (count + 255) / 256;
+  const long cap = (long)sn::kNumSMs * 16;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+int fill_common(PsArgs& a, const float* data, const float* rois, const float* trans, int num_rois, int channels,
+                int height, int width, float spatial_scale, int output_dim, int group_size, int pooled_size,
+                int part_size, int sample_per_part, float trans_std, int no_trans, int num_classes, int layout) {
+  SN_CHECK(layout == 0 || layout == 1, "psroi: layout must be 0 (NCHW) or 1 (NHWC)");
+  SN_CHECK(channels == output_dim * group_size * group_size, "psroi: channels (%d) != output_dim*group_size^2 (%d)",
+           channels, output_dim * group_size * group_size);
+  SN_CHECK(no_trans || (trans != nullptr && num_classes > 0 && output_dim % num_classes == 0),
+           "deformable psroi: bad trans / num_classes");
+  memset(&a, 0, sizeof(a));
+  a.data = data; a.rois = rois; a.trans = no_trans ? nullptr : trans;
+  a.num_rois = num_rois; a.channels = channels; a.height = height; a.width = width;
+  a.spatial_scale = spatial_scale; a.output_dim = output_dim; a.group_size = group_size; a.pooled = pooled_size;
+  a.part_size = part_size == 0 ? pooled_size : part_size; a.sample_per_part = sample_per_part;
+  a.trans_std = trans_std; a.no_trans = no_trans; a.num_classes = no_trans ? 1 : num_classes;
+  a.channels_each_class = no_trans ? output_dim : output_dim / num_classes;
+  a.layout = layout;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sniper_deform_psroi_fwd(const float* data, const float* rois, const float* trans, int num_rois, int channels,
+                            int height, int width, float spatial_scale, int output_dim, int group_size,
+                            int pooled_size, int part_size, int sample_per_part, float trans_std, int no_trans,
+                            int num_classes, int layout, float* top_data, float* top_count, int32_t* sample_idx,
+                            void* stream) {
+  PsArgs a;
+  if (fill_common(a, data, rois, trans, num_rois, channels, height, width, spatial_scale, output_dim, group_size,
+                  pooled_size, part_size, sample_per_part, trans_std, no_trans, num_classes, layout))
+    return -1;
+  a.top_data = top_data; a.top_count = top_count; a.sample_idx = sample_idx;
+  const long count = (long)num_rois * output_dim * pooled_size * pooled_size;
+  if (count == 0) return 0;
+  deform_psroi_fwd_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(a, count);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// data_diff / trans_diff are ACCUMULATED into (req = kAddTo); zero them first for kWriteTo.
+int sniper_deform_psroi_bwd(const float* top_diff, const float* data, const float* rois, const float* trans,
+                            int num_rois, int channels, int height, int width, float spatial_scale, int output_dim,
+                            int group_size, int pooled_size, int part_size, int sample_per_part, float trans_std,
+                            int no_trans, int num_classes, int layout, float* data_diff, float* trans_diff,
+                            void* stream) {
+  PsArgs a;
+  if (fill_common(a, data, rois, trans, num_rois, channels, height, width, spatial_scale, output_dim, group_size,
+                  pooled_size, part_size, sample_per_part, trans_std, no_trans, num_classes, layout))
+    return -1;
+  SN_CHECK(no_trans || trans_diff != nullptr, "deformable psroi bwd: trans_diff is null");
+  a.top_diff = top_diff; a.data_diff = data_diff; a.trans_diff = trans_diff;
+  const long count = (long)num_rois * output_dim * pooled_size * pooled_size;
+  if (count == 0) return 0;
+  deform_psroi_bwd_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(a, count);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_psroi_fwd(const float* data, const float* rois, int num_rois, int channels, int height, int width,
+                     float spatial_scale, int output_dim, int group_size, int pooled_size, int layout,
+                     float* top_data, int32_t* bins, void* stream) {
+  PsArgs a;
+  if (fill_common(a, data, rois, nullptr, num_rois, channels, height, width, spatial_scale, output_dim, group_size,
+                  pooled_size, pooled_size, 1, 0.0f, 1, 1, layout))
+    return -1;
+  a.top_data = top_data; a.sample_idx = bins;
+  const long count = (long)num_rois * output_dim * pooled_size * pooled_size;
+  if (count == 0) return 0;
+  psroi_fwd_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(a, count);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_psroi_bwd(const float* top_diff, const float* rois, int num_rois, int channels, int height, int width,
+                     float spatial_scale, int output_dim, int group_size, int pooled_size, int layout,
+                     float* data_diff, void* stream) {
+  PsArgs a;
+  if (fill_common(a, nullptr, rois, nullptr, num_rois, channels, height, width, spatial_scale, output_dim, group_size,
+                  pooled_size, pooled_size, 1, 0.0f, 1, 1, layout))
+    return -1;
+  a.top_diff = top_diff; a.data_diff = data_diff;
+  const long count = (long)num_rois * output_dim * pooled_size * pooled_size;
+  if (count == 0) return 0;
+  psroi_bwd_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(a, count);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

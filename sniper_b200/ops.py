@@ -1,0 +1,223 @@
+"""Tensor-level wrappers over the C-ABI (torch tensors are only device memory + streams here).
+
+Every function launches on torch's current CUDA stream, allocates outputs with torch, and raises
+`SniperError` when the native call fails.  There is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from ._lib import check, lib
+
+TF32, BF16 = 0, 1
+NCHW, NHWC = 0, 1
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "expected contiguous fp32 CUDA tensor"
+    return t
+
+
+def _farr(v):
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.float32))
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _iarr(v):
+    a = np.ascontiguousarray(np.asarray(v, dtype=np.int32))
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
+def generate_anchors(feat_stride, scales, ratios):
+    """multi_proposal_target.cu:75-114 anchor table, [len(ratios)*len(scales), 4] (ratio-major)."""
+    s, sp = _farr(scales)
+    r, rp = _farr(ratios)
+    out = np.zeros((len(r) * len(s), 4), np.float32)
+    check(lib().sniper_generate_anchors(int(feat_stride), sp, len(s), rp, len(r), out.ctypes.data_as(ctypes.c_void_p)))
+    return out
+
+
+def multi_proposal_target(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, *, feat_stride=16,
+                          scales=(2, 4, 7, 10, 13, 16, 24), ratios=(0.5, 1, 2), rpn_post_nms_top_n=300,
+                          threshold=0.7, layout=NCHW, return_keep=False):
+    """MultiProposalTarget forward (reference GPU-operator semantics, multi_proposal_target.cu:362-589).
+
+    NCHW: cls_prob [B,2A,H,W] (or [B,2,A*H,W]), bbox_pred [B,4A,H,W].  NHWC: [B,H,W,2A] / [B,H,W,4A].
+    Returns rois [B*R,5], label [B*R], bbox_target [B*R,4], bbox_weight [B*R,4] (+ keep_idx, num_kept).
+    """
+    _f32(cls_prob), _f32(bbox_pred), _f32(im_info), _f32(gt_boxes), _f32(valid_ranges)
+    A = len(scales) * len(ratios)
+    if layout == NCHW:
+        B, H, W = bbox_pred.shape[0], bbox_pred.shape[2], bbox_pred.shape[3]
+        assert bbox_pred.shape[1] == 4 * A and cls_prob.numel() == B * 2 * A * H * W
+        sc, dc = 0, 0
+    else:
+        B, H, W = bbox_pred.shape[0], bbox_pred.shape[1], bbox_pred.shape[2]
+        sc, dc = cls_prob.shape[3], bbox_pred.shape[3]
+        assert dc >= 4 * A and sc >= 2 * A
+    R = int(rpn_post_nms_top_n)
+    max_gt = gt_boxes.shape[1]
+    dev = cls_prob.device
+    rois = torch.empty(B * R, 5, device=dev)
+    label = torch.empty(B * R, device=dev)
+    bbox_target = torch.empty(B * R, 4, device=dev)
+    bbox_weight = torch.empty(B * R, 4, device=dev)
+    keep = torch.empty(B * R, dtype=torch.int32, device=dev) if return_keep else None
+    nkept = torch.empty(B, dtype=torch.int32, device=dev) if return_keep else None
+    L = lib()
+    ws_bytes = L.sniper_multi_proposal_target_workspace_bytes(B, A, H, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    s, sp = _farr(scales)
+    r, rp = _farr(ratios)
+    check(L.sniper_multi_proposal_target_fwd(
+        _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), _ptr(gt_boxes), _ptr(valid_ranges), B, A, H, W, max_gt, R,
+        int(feat_stride), sp, len(s), rp, len(r), float(threshold), layout, sc, dc, _ptr(rois), _ptr(label),
+        _ptr(bbox_target), _ptr(bbox_weight), _ptr(keep), _ptr(nkept), _ptr(ws), ws_bytes, _stream()))
+    if return_keep:
+        return rois, label, bbox_target, bbox_weight, keep, nkept
+    return rois, label, bbox_target, bbox_weight
+
+
+def _ps_dims(data, layout):
+    if layout == NCHW:
+        B, C, H, W = data.shape
+    else:
+        B, H, W, C = data.shape
+    return B, C, H, W
+
+
+def deform_psroi_fwd(data, rois, trans, *, spatial_scale, output_dim, group_size, pooled_size, part_size=0,
+                     sample_per_part=1, trans_std=0.0, no_trans=False, layout=NCHW, want_count=True,
+                     want_sample_idx=False):
+    """DeformablePSROIPooling forward (deformable_psroi_pooling.cu:71-161)."""
+    _f32(data), _f32(rois)
+    B, C, H, W = _ps_dims(data, layout)
+    N = rois.shape[0]
+    P = pooled_size
+    shape = (N, output_dim, P, P) if layout == NCHW else (N, P, P, output_dim)
+    out = torch.empty(shape, device=data.device)
+    cnt = torch.empty(shape, device=data.device) if want_count else None
+    S = sample_per_part
+    sidx = torch.empty(N * output_dim * P * P, S * S, 4, dtype=torch.int32, device=data.device) if want_sample_idx else None
+    ncls = 1 if no_trans else trans.shape[1] // 2
+    check(lib().sniper_deform_psroi_fwd(_ptr(data), _ptr(rois), _ptr(None if no_trans else _f32(trans)), N, C, H, W,
+                                        float(spatial_scale), output_dim, group_size, P, part_size, S,
+                                        float(trans_std), int(no_trans), ncls, layout, _ptr(out), _ptr(cnt),
+                                        _ptr(sidx), _stream()))
+    return out, cnt, sidx
+
+
+def deform_psroi_bwd(top_diff, data, rois, trans, *, spatial_scale, output_dim, group_size, pooled_size,
+                     part_size=0, sample_per_part=1, trans_std=0.0, no_trans=False, layout=NCHW,
+                     data_diff=None, trans_diff=None):
+    """DeformablePSROIPooling backward (deformable_psroi_pooling.cu:203-330); returns (data_diff, trans_diff)."""
+    _f32(top_diff), _f32(data), _f32(rois)
+    B, C, H, W = _ps_dims(data, layout)
+    N = rois.shape[0]
+    if data_diff is None:
+        data_diff = torch.zeros_like(data)
+    if trans_diff is None and not no_trans:
+        trans_diff = torch.zeros_like(trans)
+    ncls = 1 if no_trans else trans.shape[1] // 2
+    check(lib().sniper_deform_psroi_bwd(_ptr(top_diff), _ptr(data), _ptr(rois), _ptr(None if no_trans else trans), N, C,
+                                        H, W, float(spatial_scale), output_dim, group_size, pooled_size, part_size,
+                                        sample_per_part, float(trans_std), int(no_trans), ncls, layout,
+                                        _ptr(data_diff), _ptr(trans_diff), _stream()))
+    return data_diff, trans_diff
+
+
+def psroi_fwd(data, rois, *, spatial_scale, output_dim, group_size, pooled_size, layout=NCHW, want_bins=False):
+    """PSROIPooling forward (psroi_pooling.cu:51-118)."""
+    _f32(data), _f32(rois)
+    B, C, H, W = _ps_dims(data, layout)
+    N, P = rois.shape[0], pooled_size
+    shape = (N, output_dim, P, P) if layout == NCHW else (N, P, P, output_dim)
+    out = torch.empty(shape, device=data.device)
+    bins = torch.empty(N * output_dim * P * P, 4, dtype=torch.int32, device=data.device) if want_bins else None
+    check(lib().sniper_psroi_fwd(_ptr(data), _ptr(rois), N, C, H, W, float(spatial_scale), output_dim, group_size, P,
+                                 layout, _ptr(out), _ptr(bins), _stream()))
+    return out, bins
+
+
+def psroi_bwd(top_diff, rois, data_shape, *, spatial_scale, output_dim, group_size, pooled_size, layout=NCHW):
+    """PSROIPooling backward (psroi_pooling.cu:146-210)."""
+    _f32(top_diff), _f32(rois)
+    data_diff = torch.zeros(data_shape, device=top_diff.device)
+    B, C, H, W = _ps_dims(data_diff, layout)
+    check(lib().sniper_psroi_bwd(_ptr(top_diff), _ptr(rois), rois.shape[0], C, H, W, float(spatial_scale), output_dim,
+                                 group_size, pooled_size, layout, _ptr(data_diff), _stream()))
+    return data_diff
+
+
+def _dt(t):
+    return TF32 if t.dtype == torch.float32 else BF16
+
+
+def gemm_nt(a, b, *, out=None, scale=None, bias=None, residual=None, relu=False, accumulate=False, out_bf16=False):
+    """C[M,N] = epi(A[M,K] @ B[N,K]^T) on tcgen05 tensor cores (fp32 storage -> TF32 math, or bf16)."""
+    assert a.is_cuda and a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1] and a.dtype == b.dtype
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    M, K = a.shape
+    N = b.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    check(lib().sniper_gemm_nt(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K, _dt(a),
+                               _ptr(scale), _ptr(bias), _ptr(residual), 0 if residual is None else residual.stride(0),
+                               int(relu), int(accumulate), int(out_bf16), _stream()))
+    return out
+
+
+def conv_taps(kh, kw, dil, pad):
+    """Tap offsets (dh, dw) in input coordinates for a kh x kw kernel, row-major over (kh, kw)."""
+    dh = [i * dil - pad for i in range(kh) for _ in range(kw)]
+    dw = [j * dil - pad for _ in range(kh) for j in range(kw)]
+    return dh, dw
+
+
+def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, bias=None, residual=None, relu=False,
+                accumulate=False, taps=None, out_hw=None, out_map=None):
+    """NHWC implicit-GEMM convolution.  x: [N,H,W,Cin]; w: [Cout, kh*kw*Cin] (tap-major, channel-minor)."""
+    NB, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    dh, dw = taps if taps is not None else conv_taps(kh, kw, dil, pad)
+    ntaps = len(dh)
+    assert w.shape[1] == ntaps * Cin and x.is_contiguous() and w.is_contiguous()
+    if out_hw is None:
+        Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    else:
+        Ho, Wo = out_hw
+    if out is None:
+        out = torch.empty(NB, Ho, Wo, Cout, device=x.device)
+    oH, oW, os_, ooh, oow = (Ho, Wo, 1, 0, 0) if out_map is None else out_map
+    _, dhp = _iarr(dh)
+    _, dwp = _iarr(dw)
+    check(lib().sniper_conv2d_nhwc(_ptr(x), NB, H, W, Cin, _ptr(w), Cout, ntaps, dhp, dwp, stride, Ho, Wo, _ptr(out),
+                                   out.shape[-1], oH, oW, os_, ooh, oow, _dt(x), _ptr(scale), _ptr(bias),
+                                   _ptr(residual), 0 if residual is None else residual.shape[-1], int(relu),
+                                   int(accumulate), 0, _stream()))
+    return out
+
+
+def conv2d_wgrad_nhwc(dy, x, *, kh, kw, stride=1, dil=1, pad=0, dw_out=None, splits=8, taps=None):
+    """dW[Cout, kh*kw*Cin] += dY^T * im2col(X).  dy: [N,Ho,Wo,Cout], x: [N,H,W,Cin]."""
+    NB, H, W, Cin = x.shape
+    _, Ho, Wo, Cout = dy.shape
+    dh, dw = taps if taps is not None else conv_taps(kh, kw, dil, pad)
+    ntaps = len(dh)
+    if dw_out is None:
+        dw_out = torch.zeros(Cout, ntaps * Cin, device=x.device)
+    _, dhp = _iarr(dh)
+    _, dwp = _iarr(dw)
+    check(lib().sniper_conv2d_wgrad_nhwc(_ptr(dy), _ptr(x), NB, H, W, Cin, Cout, ntaps, dhp, dwp, stride, Ho, Wo,
+                                         _ptr(dw_out), _dt(x), splits, _stream()))
+    return dw_out

@@ -1,0 +1,106 @@
+"""tcgen05 GEMM / implicit-GEMM conv / wgrad vs a plain PyTorch fp32 reference of the same op.
+
+Tolerance: TF32 inputs carry 10 explicit mantissa bits -> per-product relative error 2^-10; for
+K-term dot products of O(1) random data |err| <~ 2^-10*sqrt(K)*|a||b|; asserted as
+max|d| <= 4e-3 * sqrt(K) * rms(a) * rms(b)   (bf16: 8x that).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _tol(K, a, b, dtype):
+    import torch
+    base = 4e-3 * (K ** 0.5) * a.float().pow(2).mean().sqrt().item() * b.float().pow(2).mean().sqrt().item()
+    return base * (8 if dtype == torch.bfloat16 else 1) + 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 64, 64), (256, 256, 256), (300, 98, 512), (6000, 1024, 1024),
+                                   (1000, 85, 1024), (20480, 256, 1024)])
+def test_gemm_nt_tf32(M, N, K):
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda")
+    b = torch.randn(N, K, device="cuda")
+    c = ops.gemm_nt(a, b)
+    torch.cuda.synchronize()
+    ref = a.double() @ b.double().t()
+    assert (c.double() - ref).abs().max().item() <= _tol(K, a, b, a.dtype)
+
+
+def test_gemm_epilogue_and_bf16():
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(0)
+    M, N, K = 512, 200, 256
+    a = torch.randn(M, K, device="cuda")
+    b = torch.randn(N, K, device="cuda")
+    bias = torch.randn(N, device="cuda")
+    scale = torch.rand(N, device="cuda") + 0.5
+    res = torch.randn(M, N, device="cuda")
+    c = ops.gemm_nt(a, b, scale=scale, bias=bias, residual=res, relu=True)
+    ref = torch.relu((a.double() @ b.double().t()) * scale.double() + bias.double() + res.double())
+    assert (c.double() - ref).abs().max().item() <= _tol(K, a, b, a.dtype) * 1.5
+    c2 = ops.gemm_nt(a, b, out=c.clone(), accumulate=True)
+    ref2 = ref + a.double() @ b.double().t()
+    assert (c2.double() - ref2).abs().max().item() <= _tol(K, a, b, a.dtype) * 2.5
+    ab, bb = a.bfloat16(), b.bfloat16()
+    c3 = ops.gemm_nt(ab, bb)
+    ref3 = ab.double() @ bb.double().t()
+    assert (c3.double() - ref3).abs().max().item() <= 1e-2  # inputs already bf16: only fp32 accumulation error
+
+
+CONVS = [
+    # NB, H,  W,  Cin, Cout, k, stride, dil, pad
+    (2, 32, 32, 64, 64, 1, 1, 1, 0),
+    (2, 32, 32, 256, 256, 3, 1, 1, 1),
+    (3, 32, 32, 512, 72, 3, 1, 2, 2),
+    (2, 64, 64, 128, 128, 3, 2, 1, 1),
+    (2, 64, 64, 256, 512, 1, 2, 1, 0),
+    (1, 128, 128, 64, 64, 3, 1, 1, 1),
+    (2, 128, 128, 128, 128, 3, 2, 1, 1),
+    (1, 32, 32, 3072, 512, 3, 1, 1, 1),
+]
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,k,stride,dil,pad", CONVS)
+def test_conv2d_nhwc_tf32(NB, H, W, Cin, Cout, k, stride, dil, pad):
+    import torch
+    import torch.nn.functional as F
+    from sniper_b200 import ops
+    torch.manual_seed(H + Cin + Cout + k)
+    x = torch.randn(NB, H, W, Cin, device="cuda")
+    w = torch.randn(Cout, k, k, Cin, device="cuda") * (1.0 / (k * k * Cin) ** 0.5)
+    bias = torch.randn(Cout, device="cuda")
+    y = ops.conv2d_nhwc(x, w.reshape(Cout, -1).contiguous(), kh=k, kw=k, stride=stride, dil=dil, pad=pad, bias=bias,
+                        relu=True)
+    torch.cuda.synchronize()
+    torch.backends.cudnn.allow_tf32 = False
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(0, 3, 1, 2).double(), bias.double(), stride=stride,
+                   padding=pad, dilation=dil).relu().permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert (y.double() - ref).abs().max().item() <= _tol(k * k * Cin, x, w, x.dtype)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,k,stride,dil,pad", CONVS[:5])
+def test_conv2d_wgrad_tf32(NB, H, W, Cin, Cout, k, stride, dil, pad):
+    import torch
+    import torch.nn.functional as F
+    from sniper_b200 import ops
+    torch.manual_seed(1 + H + Cin + Cout + k)
+    x = torch.randn(NB, H, W, Cin, device="cuda")
+    Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
+    if Cout % 32:
+        Cout = 96
+    dy = torch.randn(NB, Ho, Ho, Cout, device="cuda")
+    dw = ops.conv2d_wgrad_nhwc(dy, x, kh=k, kw=k, stride=stride, dil=dil, pad=pad, splits=4)
+    torch.cuda.synchronize()
+    xd = x.permute(0, 3, 1, 2).double().requires_grad_(False)
+    wd = torch.zeros(Cout, Cin, k, k, device="cuda", dtype=torch.double, requires_grad=True)
+    out = F.conv2d(xd, wd, None, stride=stride, padding=pad, dilation=dil)
+    out.backward(dy.permute(0, 3, 1, 2).double())
+    ref = wd.grad.permute(0, 2, 3, 1).reshape(Cout, -1)
+    Kred = NB * Ho * Ho
+    assert (dw.double() - ref).abs().max().item() <= _tol(Kred, x, dy, x.dtype)

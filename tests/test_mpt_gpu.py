@@ -1,0 +1,96 @@
+"""GPU parity: fused MultiProposalTarget (C-ABI) vs the CPU oracle -- bit-exact on rois/keep/labels."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from sniper_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_gpu(cls_prob, bbox_pred, im_info, gts, vr, layout=0, A=21, scales=synth.SCALES_RES101):
+    import torch
+    from sniper_b200 import ops
+    dev = "cuda:0"
+    cp, bp = torch.from_numpy(cls_prob).to(dev), torch.from_numpy(bbox_pred).to(dev)
+    if layout == 1:
+        cp = cp.permute(0, 2, 3, 1).contiguous()
+        bp = bp.permute(0, 2, 3, 1).contiguous()
+    out = ops.multi_proposal_target(cp, bp, torch.from_numpy(im_info).to(dev), torch.from_numpy(gts).to(dev),
+                                    torch.from_numpy(vr).to(dev), scales=scales, layout=layout, return_keep=True)
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in out]
+
+
+def _compare(res, gpu):
+    rois, label, bt, bw, keep, nk = gpu
+    np.testing.assert_array_equal(nk, res["num_kept"])
+    np.testing.assert_array_equal(keep, res["keep_idx"])
+    assert rois.tobytes() == res["rois"].tobytes()          # bit-exact boxes incl. fillers + GT rows
+    np.testing.assert_array_equal(label, res["label"])
+    np.testing.assert_array_equal(bw, res["bbox_weight"])
+    # targets contain log(): double log on both sides, allow 1 float ulp
+    np.testing.assert_allclose(bt, res["bbox_target"], rtol=2e-7, atol=1e-7)
+    assert np.mean(bt != res["bbox_target"]) < 1e-3
+
+
+@pytest.mark.parametrize("seed,B,H,W,layout", [(11, 2, 16, 16, 0), (12, 4, 32, 32, 0), (13, 3, 32, 32, 1)])
+def test_mpt_small(seed, B, H, W, layout):
+    inp = synth.mpt_inputs(seed, B, 21, H, W)
+    res = O.multi_proposal_target(*inp)
+    _compare(res, _run_gpu(*inp, layout=layout))
+
+
+def test_mpt_full_batch20():
+    inp = synth.mpt_inputs(21, 20, 21, 32, 32)
+    res = O.multi_proposal_target(*inp)
+    _compare(res, _run_gpu(*inp))
+
+
+def test_mpt_score_ties_follow_reference_scan_order():
+    # quantised logits -> thousands of exactly equal scores; keep order must follow the reference's
+    # strided 3-level argmax (multi_proposal_target.cu:139-176)
+    inp = synth.mpt_inputs(31, 3, 21, 32, 32, tie_fraction=0.9)
+    res = O.multi_proposal_target(*inp)
+    d = res["dets"][:21 * 32 * 32]
+    v = d[d[:, 4] != -1, 4]
+    assert len(np.unique(v)) < len(v) // 2  # the case really has ties
+    _compare(res, _run_gpu(*inp))
+
+
+def test_mpt_edge_cases():
+    # chip with no GT, chip whose GTs are all out of range, chip where nothing survives the filters
+    cls_prob, bbox_pred, im_info, gts, vr = synth.mpt_inputs(41, 4, 21, 32, 32)
+    gts[0, :, :] = -1
+    vr[1] = (400.0, 512.0)
+    vr[2] = (1000.0, 2000.0)   # every proposal filtered -> 300 filler rows
+    res = O.multi_proposal_target(cls_prob, bbox_pred, im_info, gts, vr)
+    assert res["num_kept"][2] == 0
+    _compare(res, _run_gpu(cls_prob, bbox_pred, im_info, gts, vr))
+
+
+def test_mpt_mobilenet_shape():
+    # config 4 geometry: stride 32, 16x16, A = 5 scales x 3 ratios
+    scales = (1, 2, 4, 8, 12)
+    rng = np.random.RandomState(51)
+    B, A, H, W = 5, 15, 16, 16
+    cls_prob, bbox_pred = synth.rpn_outputs(rng, B, A, H, W)
+    im_info, vr = synth.chip_meta(B)
+    gts = synth.gt_boxes(rng, B)
+    res = O.multi_proposal_target(cls_prob, bbox_pred, im_info, gts, vr, feat_stride=32, scales=scales)
+    import torch
+    from sniper_b200 import ops
+    t = lambda a: torch.from_numpy(a).cuda()
+    out = ops.multi_proposal_target(t(cls_prob), t(bbox_pred), t(im_info), t(gts), t(vr), feat_stride=32,
+                                    scales=scales, return_keep=True)
+    _compare(res, [o.cpu().numpy() for o in out])
+
+
+def test_mpt_error_reporting():
+    import torch
+    from sniper_b200 import ops
+    from sniper_b200._lib import SniperError
+    inp = synth.mpt_inputs(1, 1, 21, 2, 2)  # 84 anchors < 300 -> must be refused, not UB as in the reference
+    t = lambda a: torch.from_numpy(a).cuda()
+    with pytest.raises(SniperError):
+        ops.multi_proposal_target(*[t(a) for a in inp])
