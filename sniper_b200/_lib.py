@@ -24,8 +24,24 @@ SIGNATURES = {
     "sniper_psroi_fwd": ("i", "pp" "iiii" "f" "iiii" "pp" "p"),
     "sniper_psroi_bwd": ("i", "pp" "iiii" "f" "iiii" "p" "p"),
     "sniper_gemm_nt": ("i", "plplpl" "iiii" "ppp" "l" "iii" "p"),
-    "sniper_conv2d_nhwc": ("i", "piiii" "pii" "pp" "iii" "pl" "iiiii" "i" "ppp" "l" "iii" "p"),
-    "sniper_conv2d_wgrad_nhwc": ("i", "pp" "iiiii" "i" "pp" "iii" "p" "ii" "p"),
+    "sniper_conv2d_nhwc": ("i", "pliiii" "pii" "pp" "iii" "pl" "iiiii" "i" "ppp" "l" "iii" "p"),
+    "sniper_conv2d_wgrad_nhwc": ("i", "plpl" "iiiii" "i" "pp" "iii" "p" "ii" "p"),
+    "sniper_affine_act": ("i", "plpppl" "l" "ii" "p"),
+    "sniper_bn_stats": ("i", "pllippffipppppppp"),
+    "sniper_bn_frozen": ("i", "ippppfippp"),
+    "sniper_bn_relu_bwd": ("i", "plplppppp" "pl" "pl" "pp" "li" "p"),
+    "sniper_affine_relu_bwd": ("i", "plplpp" "pl" "pl" "lii" "p"),
+    "sniper_relu_bwd": ("i", "plplplli" "p"),
+    "sniper_maxpool3x3s2_nhwc": ("i", "ppiiiip"),
+    "sniper_stem_conv": ("i", "pppppppiiip"),
+    "sniper_weight_transpose": ("i", "ppiiiipp"),
+    "sniper_colsum": ("i", "pllipp"),
+    "sniper_sgd_mom": ("i", "ppplffffp"),
+    "sniper_count_valid": ("i", "plipp"),
+    "sniper_rpn_softmax_loss": ("i", "pipiiiifppipipp"),
+    "sniper_rpn_smooth_l1_loss": ("i", "pippiiiifpipp"),
+    "sniper_softmax_ce": ("i", "pipiiifppipipp"),
+    "sniper_smooth_l1_loss": ("i", "pipplifpipp"),
 }
 
 _lib = None

@@ -1,0 +1,513 @@
+// HBM-bound layers of the SNIPER training path on NHWC activations viewed as [M rows, C channels]
+// with a row stride `ld` (so that layers can read/write slices of the c4|c5 concat buffer in place).
+//
+// Replaces (reference): BatchNorm train/frozen (src/operator/nn/batch_norm.cu:658-700, cuDNN BN),
+// Activation relu, Pooling max 3x3/2 (nn/pool.cuh), elemwise add, Concat, SoftmaxOutput
+// (softmax_output-inl.h:108-132 fwd, :162-263 bwd incl. the host-side valid count :184-195),
+// smooth_l1 + MakeLoss (mshadow_op.h:642-678), SGD momentum (optimizer_op-inl.h:279-300).
+// All kernels: 128-bit vectorised loads/stores along C, grids sized in multiples of 148 SMs.
+#include "common.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr int kTPB = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// ------------------------------------------------------------------ y = relu?(x*scale[c] + shift[c]) (+add)
+__global__ void __launch_bounds__(kTPB) affine_act_kernel(const float* __restrict__ x, long ldx,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, float* __restrict__ y,
+                                                           long ldy, long M, int C, int relu) {
+  const int c4 = C >> 2;
+  const long total = M * c4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c4;
+    const int c = (int)(i - r * c4) << 2;
+    float4 v = ld4(x + r * ldx + c);
+    const float4 s = ld4(scale + c), t = ld4(shift + c);
+    v.x = fmaf(v.x, s.x, t.x); v.y = fmaf(v.y, s.y, t.y); v.z = fmaf(v.z, s.z, t.z); v.w = fmaf(v.w, s.w, t.w);
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    st4(y + r * ldy + c, v);
+  }
+}
+
+// ------------------------------------------------------------------ per-channel sums over rows
+// blockDim = (32, 8): x -> 4 channels each (128 channels per block), y -> row lanes.
+// MODE 0: sums[c] += x, sums[C+c] += x*x                              (BN forward statistics)
+// MODE 1: g = dy * (x*scale+shift > 0); sums[c] += g; sums[C+c] += g * (x-mean)*invstd   (BN+ReLU backward)
+template <int MODE>
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long ldx,
+                                                      const float* __restrict__ dy, long lddy,
+                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                      long M, int C, int rows_per_block, double* __restrict__ sums) {
+  const int c = (blockIdx.y * 32 + threadIdx.x) * 4;
+  const bool cok = c < C;
+  float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
+  float4 sc, sh, mu, is;
+  if (MODE == 1 && cok) { sc = ld4(scale + c); sh = ld4(shift + c); mu = ld4(mean + c); is = ld4(invstd + c); }
+  const long r0 = (long)blockIdx.x * rows_per_block;
+  const long r1 = min(M, r0 + rows_per_block);
+  if (cok) {
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) {
+      const float4 v = ld4(x + r * ldx + c);
+      if (MODE == 0) {
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+        b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
+      } else {
+        float4 g = ld4(dy + r * lddy + c);
+        g.x = fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
+        g.y = fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
+        g.z = fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
+        g.w = fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
+        a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
+        b.x = fmaf(g.x, (v.x - mu.x) * is.x, b.x); b.y = fmaf(g.y, (v.y - mu.y) * is.y, b.y);
+        b.z = fmaf(g.z, (v.z - mu.z) * is.z, b.z); b.w = fmaf(g.w, (v.w - mu.w) * is.w, b.w);
+      }
+    }
+  }
+  __shared__ float4 sa[8][32], sb[8][32];
+  sa[threadIdx.y][threadIdx.x] = a;
+  sb[threadIdx.y][threadIdx.x] = b;
+  __syncthreads();
+  if (threadIdx.y == 0 && cok) {
+    double ax = 0, ay = 0, az = 0, aw = 0, bx = 0, by = 0, bz = 0, bw = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 p = sa[k][threadIdx.x], q = sb[k][threadIdx.x];
+      ax += p.x; ay += p.y; az += p.z; aw += p.w;
+      bx += q.x; by += q.y; bz += q.z; bw += q.w;
+    }
+    atomicAdd(sums + c, ax); atomicAdd(sums + c + 1, ay); atomicAdd(sums + c + 2, az); atomicAdd(sums + c + 3, aw);
+    atomicAdd(sums + C + c, bx); atomicAdd(sums + C + c + 1, by); atomicAdd(sums + C + c + 2, bz);
+    atomicAdd(sums + C + c + 3, bw);
+  }
+}
+
+// sums -> mean/invstd/scale/shift (+ moving statistics, cuDNN convention: running var unbiased); zeroes sums
+__global__ void bn_finalize_kernel(double* __restrict__ sums, long M, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, int fix_gamma,
+                                   float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ scale,
+                                   float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = sums[c] / (double)M;
+  double var = sums[C + c] / (double)M - m * m;
+  if (var < 0) var = 0;
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = fix_gamma ? 1.0f : gamma[c];
+  mean[c] = (float)m;
+  invstd[c] = is;
+  scale[c] = g * is;
+  shift[c] = beta[c] - (float)m * g * is;
+  if (moving_mean) {
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    moving_mean[c] = moving_mean[c] * momentum + (float)m * (1.0f - momentum);
+    moving_var[c] = moving_var[c] * momentum + (float)unbiased * (1.0f - momentum);
+  }
+}
+
+// frozen BN (use_global_stats): scale/shift from the moving statistics
+__global__ void bn_frozen_kernel(int C, const float* gamma, const float* beta, const float* moving_mean,
+                                 const float* moving_var, float eps, int fix_gamma, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float is = 1.0f / sqrtf(moving_var[c] + eps);
+  const float g = fix_gamma ? 1.0f : gamma[c];
+  scale[c] = g * is;
+  shift[c] = beta[c] - moving_mean[c] * g * is;
+}
+
+// dx = scale * (g - s1/M - xhat * s2/M) (+add);  dgamma += s2, dbeta += s1 (block 0 writes them); zeroes nothing
+__global__ void __launch_bounds__(kTPB) bn_relu_bwd_apply_kernel(const float* __restrict__ x, long ldx,
+                                                                  const float* __restrict__ dy, long lddy,
+                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd,
+                                                                  const double* __restrict__ sums,
+                                                                  const float* __restrict__ add, long ldadd,
+                                                                  float* __restrict__ dx, long lddx, long M, int C) {
+  const int c4 = C >> 2;
+  const long total = M * c4;
+  const float invM = 1.0f / (float)M;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c4;
+    const int c = (int)(i - r * c4) << 2;
+    const float4 v = ld4(x + r * ldx + c);
+    float4 g = ld4(dy + r * lddy + c);
+    const float4 sc = ld4(scale + c), sh = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
+    const float s1[4] = {(float)sums[c] * invM, (float)sums[c + 1] * invM, (float)sums[c + 2] * invM, (float)sums[c + 3] * invM};
+    const float s2[4] = {(float)sums[C + c] * invM, (float)sums[C + c + 1] * invM, (float)sums[C + c + 2] * invM,
+                         (float)sums[C + c + 3] * invM};
+    float vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w};
+    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float gk = fmaf(vv[k], scv[k], shv[k]) > 0.f ? gg[k] : 0.f;
+      const float xhat = (vv[k] - muv[k]) * isv[k];
+      o[k] = scv[k] * (gk - s1[k] - xhat * s2[k]);
+    }
+    if (add) {
+      const float4 ad = ld4(add + r * ldadd + c);
+      o[0] += ad.x; o[1] += ad.y; o[2] += ad.z; o[3] += ad.w;
+    }
+    st4(dx + r * lddx + c, make_float4(o[0], o[1], o[2], o[3]));
+  }
+}
+
+// dgamma[c] = s2, dbeta[c] = s1 (accumulate), then zero the sums for reuse
+__global__ void bn_param_grad_kernel(double* sums, int C, float* dgamma, float* dbeta) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] += (float)sums[c];
+  if (dgamma) dgamma[c] += (float)sums[C + c];
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+
+// frozen BN + ReLU backward: dx = scale * dy * (x*scale+shift > 0) (+add)   [not needed below stage 2, kept for fix_bn]
+__global__ void __launch_bounds__(kTPB) affine_relu_bwd_kernel(const float* __restrict__ x, long ldx,
+                                                                const float* __restrict__ dy, long lddy,
+                                                                const float* __restrict__ scale,
+                                                                const float* __restrict__ shift,
+                                                                const float* __restrict__ add, long ldadd,
+                                                                float* __restrict__ dx, long lddx, long M, int C,
+                                                                int relu) {
+  const int c4 = C >> 2;
+  const long total = M * c4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c4;
+    const int c = (int)(i - r * c4) << 2;
+    const float4 v = ld4(x + r * ldx + c);
+    const float4 g = ld4(dy + r * lddy + c);
+    const float4 sc = ld4(scale + c), sh = ld4(shift + c);
+    float4 o;
+    o.x = (!relu || fmaf(v.x, sc.x, sh.x) > 0.f) ? g.x * sc.x : 0.f;
+    o.y = (!relu || fmaf(v.y, sc.y, sh.y) > 0.f) ? g.y * sc.y : 0.f;
+    o.z = (!relu || fmaf(v.z, sc.z, sh.z) > 0.f) ? g.z * sc.z : 0.f;
+    o.w = (!relu || fmaf(v.w, sc.w, sh.w) > 0.f) ? g.w * sc.w : 0.f;
+    if (add) {
+      const float4 ad = ld4(add + r * ldadd + c);
+      o.x += ad.x; o.y += ad.y; o.z += ad.z; o.w += ad.w;
+    }
+    st4(dx + r * lddx + c, o);
+  }
+}
+
+// relu backward through a stored activation: dx = dy * (y > 0); optional per-column bias gradient
+__global__ void __launch_bounds__(kTPB) relu_bwd_kernel(const float* __restrict__ y, long ldy,
+                                                         const float* __restrict__ dy, long lddy,
+                                                         float* __restrict__ dx, long lddx, long M, int C) {
+  const int c4 = C >> 2;
+  const long total = M * c4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c4;
+    const int c = (int)(i - r * c4) << 2;
+    const float4 v = ld4(y + r * ldy + c);
+    float4 g = ld4(dy + r * lddy + c);
+    g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f; g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;
+    st4(dx + r * lddx + c, g);
+  }
+}
+
+// ------------------------------------------------------------------ max pool 3x3 stride 2 pad 1, NHWC
+__global__ void __launch_bounds__(kTPB) maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y, int NB,
+                                                             int H, int W, int C, int Ho, int Wo) {
+  const int c4 = C >> 2;
+  const long total = (long)NB * Ho * Wo * c4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4) << 2;
+    long p = i / c4;
+    const int ow = (int)(p % Wo); p /= Wo;
+    const int oh = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        const float4 v = ld4(x + (((size_t)n * H + ih) * W + iw) * C + c);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    st4(y + (((size_t)n * Ho + oh) * Wo + ow) * C + c, m);
+  }
+}
+
+// ------------------------------------------------------------------ stem: bn_data -> conv0 7x7/2 -> bn0 -> relu
+// (resnet_mx_101_e2e.py:402-408).  Input NCHW fp32 [NB,3,H,W] (the iterator's layout), output NHWC
+// [NB,H/2,W/2,64].  One block = 8x16 output pixels x 64 channels; weights [64][7][7][3] and the input
+// patch live in shared memory; bn_data is applied to in-bounds pixels only (padding is zero AFTER bn_data).
+constexpr int kStemTH = 8, kStemTW = 16;
+__global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ in_scale,
+                                                         const float* __restrict__ in_shift,
+                                                         const float* __restrict__ out_scale,
+                                                         const float* __restrict__ out_shift, float* __restrict__ y,
+                                                         int NB, int H, int W, int Ho, int Wo) {
+  constexpr int PH = kStemTH * 2 + 5, PW = kStemTW * 2 + 5;  // 21 x 37
+  __shared__ float s_in[3][PH][PW + 1];
+  __shared__ float s_w[147][64];  // [(kh,kw,c)][co]
+  const int n = blockIdx.z;
+  const int oh0 = blockIdx.y * kStemTH, ow0 = blockIdx.x * kStemTW;
+  for (int i = threadIdx.x; i < 147 * 64; i += 128) {
+    const int co = i & 63, k = i >> 6;
+    s_w[k][co] = w[co * 147 + k];
+  }
+  for (int i = threadIdx.x; i < 3 * PH * PW; i += 128) {
+    const int c = i / (PH * PW);
+    const int r = (i / PW) % PH, q = i % PW;
+    const int ih = oh0 * 2 - 3 + r, iw = ow0 * 2 - 3 + q;
+    float v = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+      v = fmaf(x[(((size_t)n * 3 + c) * H + ih) * W + iw], in_scale[c], in_shift[c]);
+    s_in[c][r][q] = v;
+  }
+  __syncthreads();
+  const int ty = threadIdx.x / kStemTW, tx = threadIdx.x % kStemTW;
+  float acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+  for (int kh = 0; kh < 7; ++kh) {
+    for (int kw = 0; kw < 7; ++kw) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = s_in[c][ty * 2 + kh][tx * 2 + kw];
+        const float4* wr = reinterpret_cast<const float4*>(&s_w[(kh * 7 + kw) * 3 + c][0]);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float4 ww = wr[j];
+          acc[4 * j] = fmaf(v, ww.x, acc[4 * j]);
+          acc[4 * j + 1] = fmaf(v, ww.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, ww.z, acc[4 * j + 2]);
+          acc[4 * j + 3] = fmaf(v, ww.w, acc[4 * j + 3]);
+        }
+      }
+    }
+  }
+  const int oh = oh0 + ty, ow = ow0 + tx;
+  if (oh < Ho && ow < Wo) {
+    float* o = y + (((size_t)n * Ho + oh) * Wo + ow) * 64;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 s = ld4(out_scale + 4 * j), t = ld4(out_shift + 4 * j);
+      float4 v;
+      v.x = fmaxf(fmaf(acc[4 * j], s.x, t.x), 0.f);
+      v.y = fmaxf(fmaf(acc[4 * j + 1], s.y, t.y), 0.f);
+      v.z = fmaxf(fmaf(acc[4 * j + 2], s.z, t.z), 0.f);
+      v.w = fmaxf(fmaf(acc[4 * j + 3], s.w, t.w), 0.f);
+      st4(o + 4 * j, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ weight re-layout for data gradients
+// w [Cout, T, Cin] -> wt [Cin, Tsel, Cout] with wt[ci, j, co] = w[co, sel[j], ci]
+__global__ void weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ wt, int Cout, int T, int Cin,
+                                        int Tsel, const int* __restrict__ sel) {
+  __shared__ float tile[32][33];
+  const int j = blockIdx.z;
+  const int t = sel[j];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    tile[r][threadIdx.x] = (co < Cout && ci < Cin) ? w[((size_t)co * T + t) * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < Cin && co < Cout) wt[((size_t)ci * Tsel + j) * Cout + co] = tile[threadIdx.x][r];
+  }
+}
+
+// ------------------------------------------------------------------ column sums of [M,C] (bias gradients)
+__global__ void __launch_bounds__(256) colsum_plain_kernel(const float* __restrict__ x, long ldx, long M, int C,
+                                                            int rows_per_block, float* __restrict__ out) {
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  float a = 0.f;
+  const long r0 = (long)blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  if (c < C)
+    for (long r = r0 + threadIdx.y; r < r1; r += 8) a += x[r * ldx + c];
+  __shared__ float sa[8][33];
+  sa[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += sa[k][threadIdx.x];
+    atomicAdd(out + c, s);
+  }
+}
+
+// ------------------------------------------------------------------ SGD momentum, multi-tensor in one flat buffer
+// optimizer_op-inl.h:279-300: mom = momentum*mom - lr*wd*w - lr*rescale*g ; w += mom.  lr/wd per segment.
+struct SgdSeg { long begin, end; float lr, wd; };
+__global__ void __launch_bounds__(kTPB) sgd_mom_kernel(float* __restrict__ w, float* __restrict__ mom,
+                                                        const float* __restrict__ g, long n, float lr, float wd,
+                                                        float momentum, float rescale) {
+  const long n4 = n >> 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 ww = ld4(w + 4 * i), mm = ld4(mom + 4 * i);
+    const float4 gg = ld4(g + 4 * i);
+    mm.x = momentum * mm.x - lr * wd * ww.x - lr * rescale * gg.x;
+    mm.y = momentum * mm.y - lr * wd * ww.y - lr * rescale * gg.y;
+    mm.z = momentum * mm.z - lr * wd * ww.z - lr * rescale * gg.z;
+    mm.w = momentum * mm.w - lr * wd * ww.w - lr * rescale * gg.w;
+    ww.x += mm.x; ww.y += mm.y; ww.z += mm.z; ww.w += mm.w;
+    st4(w + 4 * i, ww);
+    st4(mom + 4 * i, mm);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long i = (n4 << 2) + threadIdx.x;
+    const float m = momentum * mom[i] - lr * wd * w[i] - lr * rescale * g[i];
+    mom[i] = m;
+    w[i] += m;
+  }
+}
+
+int ew_grid(long work) {
+  long g = (work + kTPB - 1) / kTPB;
+  const long cap = (long)sn::kNumSMs * 8;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+int pick_rows_per_block(long M, int C) {
+  // aim for >= 2 waves of 148 blocks
+  const int cb = sn::div_up(C, 128);
+  long rb = M / ((2 * sn::kNumSMs) / cb + 1);
+  if (rb < 64) rb = 64;
+  if (rb > 4096) rb = 4096;
+  return (int)((rb + 7) / 8 * 8);
+}
+
+}  // namespace
+
+extern "C" {
+
+int sniper_affine_act(const float* x, long ldx, const float* scale, const float* shift, float* y, long ldy, long M,
+                      int C, int relu, void* stream) {
+  SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "affine_act: C/ld must be multiples of 4");
+  affine_act_kernel<<<ew_grid(M * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(x, ldx, scale, shift, y, ldy, M, C, relu);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Train-mode BN statistics of x[M,C] -> (mean, invstd, scale, shift) + moving stats.  `sums` is a
+// caller-owned, zero-initialised double[2*C] scratch that is left zeroed.
+int sniper_bn_stats(const float* x, long ldx, long M, int C, const float* gamma, const float* beta, float eps,
+                    float momentum, int fix_gamma, float* moving_mean, float* moving_var, double* sums, float* mean,
+                    float* invstd, float* scale, float* shift, void* stream) {
+  SN_CHECK(C % 4 == 0 && ldx % 4 == 0, "bn_stats: C/ld must be multiples of 4");
+  const int rpb = pick_rows_per_block(M, C);
+  dim3 grid(sn::div_up(M, rpb), sn::div_up(C, 128)), block(32, 8);
+  colsum_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, M,
+                                                            C, rpb, sums);
+  SN_LAUNCH_CHECK();
+  bn_finalize_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, M, C, gamma, beta, eps, momentum,
+                                                                          fix_gamma, moving_mean, moving_var, mean,
+                                                                          invstd, scale, shift);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_bn_frozen(int C, const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
+                     float eps, int fix_gamma, float* scale, float* shift, void* stream) {
+  bn_frozen_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, moving_mean, moving_var, eps,
+                                                                        fix_gamma, scale, shift);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Backward of y = relu(bn_train(x)):  dx (+add), dgamma += , dbeta += .  sums: zeroed double[2C], left zeroed.
+int sniper_bn_relu_bwd(const float* x, long ldx, const float* dy, long lddy, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, double* sums, const float* add, long ldadd, float* dx,
+                       long lddx, float* dgamma, float* dbeta, long M, int C, void* stream) {
+  SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "bn_relu_bwd: C/ld must be multiples of 4");
+  const int rpb = pick_rows_per_block(M, C);
+  dim3 grid(sn::div_up(M, rpb), sn::div_up(C, 128)), block(32, 8);
+  colsum_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, dy, lddy, scale, shift, mean, invstd, M, C, rpb,
+                                                            sums);
+  SN_LAUNCH_CHECK();
+  bn_relu_bwd_apply_kernel<<<ew_grid(M * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(
+      x, ldx, dy, lddy, scale, shift, mean, invstd, sums, add, ldadd, dx, lddx, M, C);
+  SN_LAUNCH_CHECK();
+  bn_param_grad_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_affine_relu_bwd(const float* x, long ldx, const float* dy, long lddy, const float* scale,
+                           const float* shift, const float* add, long ldadd, float* dx, long lddx, long M, int C,
+                           int relu, void* stream) {
+  SN_CHECK(C % 4 == 0, "affine_relu_bwd: C must be a multiple of 4");
+  affine_relu_bwd_kernel<<<ew_grid(M * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(x, ldx, dy, lddy, scale, shift, add,
+                                                                                 ldadd, dx, lddx, M, C, relu);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_relu_bwd(const float* y, long ldy, const float* dy, long lddy, float* dx, long lddx, long M, int C,
+                    void* stream) {
+  SN_CHECK(C % 4 == 0, "relu_bwd: C must be a multiple of 4");
+  relu_bwd_kernel<<<ew_grid(M * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(y, ldy, dy, lddy, dx, lddx, M, C);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_maxpool3x3s2_nhwc(const float* x, float* y, int NB, int H, int W, int C, void* stream) {
+  SN_CHECK(C % 4 == 0, "maxpool: C must be a multiple of 4");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool3x3s2_kernel<<<ew_grid((long)NB * Ho * Wo * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(x, y, NB, H, W, C, Ho, Wo);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_stem_conv(const float* x_nchw, const float* w /*[64,7,7,3]*/, const float* in_scale, const float* in_shift,
+                     const float* out_scale, const float* out_shift, float* y_nhwc, int NB, int H, int W,
+                     void* stream) {
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  dim3 grid(sn::div_up(Wo, kStemTW), sn::div_up(Ho, kStemTH), NB);
+  stem_conv_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, w, in_scale, in_shift, out_scale, out_shift, y_nhwc,
+                                                          NB, H, W, Ho, Wo);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_weight_transpose(const float* w, float* wt, int Cout, int T, int Cin, int Tsel, const int* sel_dev,
+                            void* stream) {
+  dim3 grid(sn::div_up(Cin, 32), sn::div_up(Cout, 32), Tsel), block(32, 8);
+  weight_transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, wt, Cout, T, Cin, Tsel, sel_dev);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_colsum(const float* x, long ldx, long M, int C, float* out_accum, void* stream) {
+  const int rpb = 512;
+  dim3 grid(sn::div_up(M, rpb), sn::div_up(C, 32)), block(32, 8);
+  colsum_plain_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, M, C, rpb, out_accum);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_sgd_mom(float* w, float* mom, const float* g, long n, float lr, float wd, float momentum, float rescale,
+                   void* stream) {
+  SN_CHECK((((uintptr_t)w | (uintptr_t)mom | (uintptr_t)g) & 15) == 0, "sgd_mom: buffers must be 16-byte aligned");
+  sgd_mom_kernel<<<ew_grid(n / 4 + 1), kTPB, 0, (cudaStream_t)stream>>>(w, mom, g, n, lr, wd, momentum, rescale);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

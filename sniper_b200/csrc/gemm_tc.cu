@@ -46,6 +46,7 @@ struct GemmParams {
   uint32_t idesc;
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;  // 16-byte units
   uint32_t a_kadv, b_kadv;              // 16-byte units per MMA k-step
+  uint32_t layout_type;                 // UMMA LayoutType: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   int mmas_per_kb;
   int a_boxes, b_boxes;                 // TMA boxes per stage
   uint32_t a_box_bytes, b_box_bytes;
@@ -144,13 +145,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo16, uint32_t sbo16, uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3fff);
   d |= (uint64_t)(lbo16 & 0x3fff) << 16;
   d |= (uint64_t)(sbo16 & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 
@@ -246,8 +247,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t sb = sa + kStageABytes;
-        const uint64_t adesc0 = make_smem_desc(sa, p.a_lbo, p.a_sbo);
-        const uint64_t bdesc0 = make_smem_desc(sb, p.b_lbo, p.b_sbo);
+        const uint64_t adesc0 = make_smem_desc(sa, p.a_lbo, p.a_sbo, p.layout_type);
+        const uint64_t bdesc0 = make_smem_desc(sb, p.b_lbo, p.b_sbo, p.layout_type);
         for (int k = 0; k < p.mmas_per_kb; ++k) {
           umma<DT>(tmem_base, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
                    (i | k) != 0 ? 1u : 0u);
@@ -349,7 +350,7 @@ EncodeTiledFn get_encode() {
 
 // 4-D tiled map; dims/strides innermost first; strides in bytes for dims 1..3
 int make_map(CUtensorMap* m, int dtype, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
-             const uint32_t box[4], const uint32_t estr[4]) {
+             const uint32_t box[4], const uint32_t estr[4], int atom32 = 0) {
   EncodeTiledFn enc = get_encode();
   SN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
   cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
@@ -357,7 +358,8 @@ int make_map(CUtensorMap* m, int dtype, const void* base, const uint64_t dims[4]
   cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
   cuuint32_t es[4] = {estr[0], estr[1], estr[2], estr[3]};
   CUresult r = enc(m, dtype == DT_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                   const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SN_CHECK(r == CUDA_SUCCESS,
            "cuTensorMapEncodeTiled failed (%d): dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu box=%u,%u,%u,%u es=%u,%u,%u,%u",
@@ -422,6 +424,7 @@ void fill_kmajor(GemmParams& p, int dtype, int block_n) {
   p.idesc = make_idesc(dtype, 0, 0, 128, block_n);
   p.a_lbo = 1; p.a_sbo = 64; p.b_lbo = 1; p.b_sbo = 64;  // SBO = 8 rows x 128 B
   p.a_kadv = 2; p.b_kadv = 2;                            // 32 B per UMMA_K step
+  p.layout_type = 2;
   p.mmas_per_kb = 4;
   p.a_boxes = 1; p.b_boxes = 1;
   p.a_box_bytes = kStageABytes;
@@ -483,7 +486,7 @@ int sniper_gemm_nt(const void* A, long lda, const void* B, long ldb, float* C, l
 //   Y[n,oh,ow,co] = epi( sum_{t<ntaps, c<Cin} X[n, oh*stride + dh[t], ow*stride + dw[t], c] * Wt[co, t*Cin + c] )
 // X: [NB,H,W,Cin] contiguous; Wt: [Cout, ntaps*Cin]; Y row (n,oh,ow) is written at
 // ((n*out_H + oh*out_s + out_oh)*out_W + ow*out_s + out_ow) * ldc.  Out-of-range taps read zeros (TMA fill).
-int sniper_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, const void* Wt, int Cout, int ntaps,
+int sniper_conv2d_nhwc(const void* X, long x_ld, int NB, int H, int W, int Cin, const void* Wt, int Cout, int ntaps,
                        const int* tap_dh, const int* tap_dw, int stride, int Ho, int Wo, float* Y, long ldc,
                        int out_H, int out_W, int out_s, int out_oh, int out_ow, int dtype, const float* scale,
                        const float* bias, const float* residual, long ldr, int relu, int accumulate, int out_bf16,
@@ -512,8 +515,9 @@ int sniper_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, const void*
   p.out_H = out_H; p.out_W = out_W; p.out_s = out_s; p.out_oh = out_oh; p.out_ow = out_ow;
   CUtensorMap ma, mb;
   {
+    SN_CHECK(x_ld >= Cin && (x_ld * esz) % 16 == 0, "conv: bad x_ld");
     const uint64_t d[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
-    const uint64_t s[3] = {(uint64_t)Cin * esz, (uint64_t)Cin * esz * W, (uint64_t)Cin * esz * W * H};
+    const uint64_t s[3] = {(uint64_t)x_ld * esz, (uint64_t)x_ld * esz * W, (uint64_t)x_ld * esz * W * H};
     // with elementStrides the box extent is in un-strided elements
     const uint32_t b[4] = {(uint32_t)E, (uint32_t)(tile_w * stride), (uint32_t)(tile_h * stride), 1};
     const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
@@ -534,7 +538,8 @@ int sniper_conv2d_nhwc(const void* X, int NB, int H, int W, int Cin, const void*
 // Weight gradient:  dW[co, t*Cin + ci] += sum_{n,oh,ow} dY[(n,oh,ow), co] * X[n, oh*stride+dh[t], ow*stride+dw[t], ci]
 // dY: [NB*Ho*Wo, Cout] contiguous rows (ld = Cout); X: [NB,H,W,Cin]; dW must be zero-initialised by the caller
 // (accumulated with red.global.add across split-K CTAs).  ntaps = 1, dh=dw=0, H=Ho, W=Wo gives dY^T * X (FC layers).
-int sniper_conv2d_wgrad_nhwc(const void* dY, const void* X, int NB, int H, int W, int Cin, int Cout, int ntaps,
+int sniper_conv2d_wgrad_nhwc(const void* dY, long dy_ld, const void* X, long x_ld, int NB, int H, int W, int Cin,
+                             int Cout, int ntaps,
                              const int* tap_dh, const int* tap_dw, int stride, int Ho, int Wo, float* dW, int dtype,
                              int splits, void* stream) {
   SN_CHECK(dtype == DT_TF32 || dtype == DT_BF16, "wgrad: dtype must be 0 (tf32) or 1 (bf16)");
@@ -555,7 +560,13 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, const void* X, int NB, int H, int W
   p.M = Cout; p.N = ntaps * Cin;
   p.idesc = make_idesc(dtype, 1, 1, 128, bn);
   const uint32_t chunk_bytes = (uint32_t)kp * 128u;
-  p.a_lbo = chunk_bytes >> 4; p.a_sbo = 64; p.b_lbo = chunk_bytes >> 4; p.b_sbo = 64;
+  // MN-major: LBO = stride between 128-byte MN atoms, SBO = stride between k-row groups.  32-bit
+  // operands must use the 128B swizzle with 32-byte atoms (UMMA SWIZZLE_128B_BASE32B, TMA
+  // SWIZZLE_128B_ATOM_32B): k-row groups are 4 rows (512 B) instead of 8 (1024 B).
+  const int atom32 = dtype == DT_TF32 ? 1 : 0;
+  p.layout_type = atom32 ? 1u : 2u;
+  const uint32_t sbo = atom32 ? 32u : 64u;
+  p.a_lbo = chunk_bytes >> 4; p.a_sbo = sbo; p.b_lbo = chunk_bytes >> 4; p.b_sbo = sbo;
   const int umma_k = 32 / esz;                       // 8 (tf32) / 16 (bf16) k-rows per MMA
   p.a_kadv = (uint32_t)(umma_k * 128) >> 4; p.b_kadv = p.a_kadv;
   p.mmas_per_kb = kp / umma_k;
@@ -572,18 +583,19 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, const void* X, int NB, int H, int W
   p.C = dW; p.ldc = (long)ntaps * Cin; p.atomic = 1;
   CUtensorMap ma, mb;
   {
+    SN_CHECK(dy_ld >= Cout && x_ld >= Cin && (dy_ld * esz) % 16 == 0 && (x_ld * esz) % 16 == 0, "wgrad: bad ld");
     const uint64_t d[4] = {(uint64_t)Cout, (uint64_t)pixels, 1, 1};
-    const uint64_t s[3] = {(uint64_t)Cout * esz, (uint64_t)Cout * esz * pixels, (uint64_t)Cout * esz * pixels};
+    const uint64_t s[3] = {(uint64_t)dy_ld * esz, (uint64_t)dy_ld * esz * pixels, (uint64_t)dy_ld * esz * pixels};
     const uint32_t b[4] = {(uint32_t)E, (uint32_t)kp, 1, 1};
     const uint32_t ones[4] = {1, 1, 1, 1};
-    if (make_map(&ma, dtype, dY, d, s, b, ones)) return -1;
+    if (make_map(&ma, dtype, dY, d, s, b, ones, atom32)) return -1;
   }
   {
     const uint64_t d[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
-    const uint64_t s[3] = {(uint64_t)Cin * esz, (uint64_t)Cin * esz * W, (uint64_t)Cin * esz * W * H};
+    const uint64_t s[3] = {(uint64_t)x_ld * esz, (uint64_t)x_ld * esz * W, (uint64_t)x_ld * esz * W * H};
     const uint32_t b[4] = {(uint32_t)E, (uint32_t)(bw * stride), (uint32_t)(bh * stride), 1};
     const uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-    if (make_map(&mb, dtype, X, d, s, b, es)) return -1;
+    if (make_map(&mb, dtype, X, d, s, b, es, atom32)) return -1;
   }
   dim3 grid(Cout / 128 + (Cout % 128 ? 1 : 0), ntaps * p.wg_cin_blocks, splits);
   return launch(ma, mb, p, grid, (cudaStream_t)stream);

@@ -190,7 +190,9 @@ def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, b
     Cout = w.shape[0]
     dh, dw = taps if taps is not None else conv_taps(kh, kw, dil, pad)
     ntaps = len(dh)
-    assert w.shape[1] == ntaps * Cin and x.is_contiguous() and w.is_contiguous()
+    assert w.shape[1] == ntaps * Cin and w.is_contiguous() and x.stride(3) == 1
+    x_ld = x.stride(2)
+    assert x.stride(1) == W * x_ld and x.stride(0) == H * W * x_ld
     if out_hw is None:
         Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
@@ -201,9 +203,9 @@ def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, b
     oH, oW, os_, ooh, oow = (Ho, Wo, 1, 0, 0) if out_map is None else out_map
     _, dhp = _iarr(dh)
     _, dwp = _iarr(dw)
-    check(lib().sniper_conv2d_nhwc(_ptr(x), NB, H, W, Cin, _ptr(w), Cout, ntaps, dhp, dwp, stride, Ho, Wo, _ptr(out),
-                                   out.shape[-1], oH, oW, os_, ooh, oow, _dt(x), _ptr(scale), _ptr(bias),
-                                   _ptr(residual), 0 if residual is None else residual.shape[-1], int(relu),
+    check(lib().sniper_conv2d_nhwc(_ptr(x), x_ld, NB, H, W, Cin, _ptr(w), Cout, ntaps, dhp, dwp, stride, Ho, Wo,
+                                   _ptr(out), _rows(out)[2], oH, oW, os_, ooh, oow, _dt(x), _ptr(scale), _ptr(bias),
+                                   _ptr(residual), 0 if residual is None else _rows(residual)[2], int(relu),
                                    int(accumulate), 0, _stream()))
     return out
 
@@ -218,6 +220,153 @@ def conv2d_wgrad_nhwc(dy, x, *, kh, kw, stride=1, dil=1, pad=0, dw_out=None, spl
         dw_out = torch.zeros(Cout, ntaps * Cin, device=x.device)
     _, dhp = _iarr(dh)
     _, dwp = _iarr(dw)
-    check(lib().sniper_conv2d_wgrad_nhwc(_ptr(dy), _ptr(x), NB, H, W, Cin, Cout, ntaps, dhp, dwp, stride, Ho, Wo,
+    check(lib().sniper_conv2d_wgrad_nhwc(_ptr(dy), dy.stride(2), _ptr(x), x.stride(2), NB, H, W, Cin, Cout, ntaps, dhp,
+                                         dwp, stride, Ho, Wo,
                                          _ptr(dw_out), _dt(x), splits, _stream()))
     return dw_out
+
+
+# ---------------------------------------------------------------------------------------------
+# HBM-bound layers ([M, C] views of NHWC tensors; `ld` = row stride in elements)
+# ---------------------------------------------------------------------------------------------
+def _rows(t):
+    """(M, C, ld) of a tensor whose last dim is contiguous and whose leading dims collapse to rows."""
+    C = t.shape[-1]
+    assert t.stride(-1) == 1
+    ld = t.stride(-2) if t.dim() >= 2 else C
+    M = t.numel() // C
+    return M, C, ld
+
+
+def affine_act(x, scale, shift, relu=True, out=None):
+    M, C, ldx = _rows(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device)
+    check(lib().sniper_affine_act(_ptr(x), ldx, _ptr(scale), _ptr(shift), _ptr(out), _rows(out)[2], M, C, int(relu),
+                                  _stream()))
+    return out
+
+
+class BNState:
+    """Per-BN device state: parameters, moving statistics and the per-step (mean, invstd, scale, shift)."""
+
+    def __init__(self, C, device, gamma=None, beta=None, dgamma=None, dbeta=None):
+        z = lambda: torch.zeros(C, device=device)
+        self.C = C
+        self.gamma = gamma if gamma is not None else torch.ones(C, device=device)
+        self.beta = beta if beta is not None else z()
+        self.dgamma, self.dbeta = dgamma, dbeta
+        self.moving_mean, self.moving_var = z(), torch.ones(C, device=device)
+        self.mean, self.invstd, self.scale, self.shift = z(), z(), z(), z()
+        self.sums = torch.zeros(2 * C, dtype=torch.float64, device=device)
+
+
+def bn_stats(x, bn, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=True):
+    """Train-mode BatchNorm statistics of x -> bn.(mean, invstd, scale, shift) (+ moving stats)."""
+    M, C, ldx = _rows(x)
+    check(lib().sniper_bn_stats(_ptr(x), ldx, M, C, _ptr(bn.gamma), _ptr(bn.beta), float(eps), float(momentum),
+                                int(fix_gamma), _ptr(bn.moving_mean if update_moving else None),
+                                _ptr(bn.moving_var if update_moving else None), _ptr(bn.sums), _ptr(bn.mean),
+                                _ptr(bn.invstd), _ptr(bn.scale), _ptr(bn.shift), _stream()))
+
+
+def bn_frozen(bn, eps=2e-5, fix_gamma=False):
+    check(lib().sniper_bn_frozen(bn.C, _ptr(bn.gamma), _ptr(bn.beta), _ptr(bn.moving_mean), _ptr(bn.moving_var),
+                                 float(eps), int(fix_gamma), _ptr(bn.scale), _ptr(bn.shift), _stream()))
+
+
+def bn_relu_bwd(x, dy, bn, add=None, out=None):
+    """Backward of relu(bn_train(x)); accumulates bn.dgamma / bn.dbeta; returns dx (+ add)."""
+    M, C, ldx = _rows(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device)
+    check(lib().sniper_bn_relu_bwd(_ptr(x), ldx, _ptr(dy), _rows(dy)[2], _ptr(bn.scale), _ptr(bn.shift), _ptr(bn.mean),
+                                   _ptr(bn.invstd), _ptr(bn.sums), _ptr(add), 0 if add is None else _rows(add)[2],
+                                   _ptr(out), _rows(out)[2], _ptr(bn.dgamma), _ptr(bn.dbeta), M, C, _stream()))
+    return out
+
+
+def affine_relu_bwd(x, dy, scale, shift, add=None, relu=True, out=None):
+    M, C, ldx = _rows(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device)
+    check(lib().sniper_affine_relu_bwd(_ptr(x), ldx, _ptr(dy), _rows(dy)[2], _ptr(scale), _ptr(shift), _ptr(add),
+                                       0 if add is None else _rows(add)[2], _ptr(out), _rows(out)[2], M, C, int(relu),
+                                       _stream()))
+    return out
+
+
+def relu_bwd(y, dy, out=None):
+    M, C, ldy = _rows(y)
+    if out is None:
+        out = torch.empty(y.shape, device=y.device)
+    check(lib().sniper_relu_bwd(_ptr(y), ldy, _ptr(dy), _rows(dy)[2], _ptr(out), _rows(out)[2], M, C, _stream()))
+    return out
+
+
+def maxpool3x3s2(x):
+    NB, H, W, C = x.shape
+    y = torch.empty(NB, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, device=x.device)
+    check(lib().sniper_maxpool3x3s2_nhwc(_ptr(x), _ptr(y), NB, H, W, C, _stream()))
+    return y
+
+
+def stem_conv(x_nchw, w, in_scale, in_shift, out_scale, out_shift):
+    """bn_data -> conv0 7x7/2 pad 3 -> bn0 -> relu; NCHW fp32 in, NHWC out.  w: [64,7,7,3]."""
+    NB, C, H, W = x_nchw.shape
+    assert C == 3 and w.shape == (64, 7, 7, 3)
+    y = torch.empty(NB, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64, device=x_nchw.device)
+    check(lib().sniper_stem_conv(_ptr(x_nchw), _ptr(w), _ptr(in_scale), _ptr(in_shift), _ptr(out_scale),
+                                 _ptr(out_shift), _ptr(y), NB, H, W, _stream()))
+    return y
+
+
+def weight_transpose(w, Cout, T, Cin, sel_dev, out=None):
+    """w [Cout,T,Cin] -> [Cin, len(sel), Cout] with out[ci,j,co] = w[co, sel[j], ci] (data-gradient operand)."""
+    Tsel = sel_dev.numel()
+    if out is None:
+        out = torch.empty(Cin, Tsel * Cout, device=w.device)
+    check(lib().sniper_weight_transpose(_ptr(w), _ptr(out), Cout, T, Cin, Tsel, _ptr(sel_dev), _stream()))
+    return out
+
+
+def colsum_accum(x, out):
+    M, C, ldx = _rows(x)
+    check(lib().sniper_colsum(_ptr(x), ldx, M, C, _ptr(out), _stream()))
+    return out
+
+
+def sgd_mom(w, mom, g, lr, wd, momentum, rescale=1.0):
+    check(lib().sniper_sgd_mom(_ptr(w), _ptr(mom), _ptr(g), w.numel(), float(lr), float(wd), float(momentum),
+                               float(rescale), _stream()))
+
+
+def count_valid(label, out, ignore=-1):
+    check(lib().sniper_count_valid(_ptr(label), label.numel(), int(ignore), _ptr(out), _stream()))
+
+
+def rpn_softmax_loss(score, label, A, grad_scale, valid_cnt, prob, dscore, loss_sum):
+    """score/prob/dscore: NHWC [B,H,W,>=2A]; label [B, A*H*W] in (a,h,w) order."""
+    B, H, W, ld = score.shape
+    check(lib().sniper_rpn_softmax_loss(_ptr(score), ld, _ptr(label), B, H, W, A, float(grad_scale), _ptr(valid_cnt),
+                                        _ptr(prob), prob.shape[3], _ptr(dscore), 0 if dscore is None else dscore.shape[3],
+                                        _ptr(loss_sum), _stream()))
+
+
+def rpn_smooth_l1_loss(pred, target, weight, C4, grad_scale, dpred, loss_sum):
+    B, H, W, ld = pred.shape
+    check(lib().sniper_rpn_smooth_l1_loss(_ptr(pred), ld, _ptr(target), _ptr(weight), B, H, W, C4, float(grad_scale),
+                                          _ptr(dpred), dpred.shape[3], _ptr(loss_sum), _stream()))
+
+
+def softmax_ce(logits, label, K, grad_scale, valid_cnt, prob, grad, loss_sum, ignore=-1):
+    N, ld = logits.shape
+    check(lib().sniper_softmax_ce(_ptr(logits), ld, _ptr(label), N, K, int(ignore), float(grad_scale), _ptr(valid_cnt),
+                                  _ptr(prob), 0 if prob is None else prob.shape[1], _ptr(grad),
+                                  0 if grad is None else grad.shape[1], _ptr(loss_sum), _stream()))
+
+
+def smooth_l1_loss(pred, target, weight, C, grad_scale, grad, loss_sum):
+    N, ld = pred.shape
+    check(lib().sniper_smooth_l1_loss(_ptr(pred), ld, _ptr(target), _ptr(weight), N, C, float(grad_scale), _ptr(grad),
+                                      grad.shape[1], _ptr(loss_sum), _stream()))

@@ -1,0 +1,138 @@
+"""HBM-bound layers and losses vs plain PyTorch fp32/fp64 references of the same op."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_bn_train_fwd_bwd_matches_torch():
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(0)
+    M, C = 4096 + 40, 256
+    x = (torch.randn(M, C, device="cuda") * 2 + 0.5)
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda")
+    bn = ops.BNState(C, "cuda", gamma.clone(), beta.clone(), torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda"))
+    ops.bn_stats(x, bn, eps=2e-5, momentum=0.9)
+    y = ops.affine_act(x, bn.scale, bn.shift, relu=True)
+    dy = torch.randn(M, C, device="cuda")
+    add = torch.randn(M, C, device="cuda")
+    dx = ops.bn_relu_bwd(x, dy, bn, add=add)
+    xr = x.double().requires_grad_(True)
+    g, b = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    rm, rv = torch.zeros(C, device="cuda", dtype=torch.double), torch.ones(C, device="cuda", dtype=torch.double)
+    yr = torch.relu(torch.nn.functional.batch_norm(xr, rm, rv, g, b, True, 0.1, 2e-5))
+    yr.backward(dy.double())
+    assert (y.double() - yr).abs().max().item() < 1e-4
+    assert (dx.double() - (xr.grad + add.double())).abs().max().item() < 1e-4
+    assert (bn.dgamma.double() - g.grad).abs().max().item() < 2e-2 * g.grad.abs().max().item() * 0.05 + 1e-2
+    assert (bn.dbeta.double() - b.grad).abs().max().item() < 1e-2
+    assert (bn.moving_mean.double() - rm).abs().max().item() < 1e-5
+    assert (bn.moving_var.double() - rv).abs().max().item() < 1e-4
+    assert float(bn.sums.abs().sum()) == 0.0  # scratch left zeroed
+
+
+def test_strided_rows_and_frozen_bn():
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(1)
+    buf = torch.randn(2, 8, 8, 96, device="cuda")
+    x = buf[..., 32:96]          # channel slice: ld = 96
+    bn = ops.BNState(64, "cuda")
+    bn.moving_mean.normal_(); bn.moving_var.uniform_(0.5, 2); bn.gamma.uniform_(0.5, 1.5); bn.beta.normal_()
+    ops.bn_frozen(bn, eps=2e-5)
+    y = ops.affine_act(x, bn.scale, bn.shift, relu=True)
+    ref = torch.relu((x - bn.moving_mean) / torch.sqrt(bn.moving_var + 2e-5) * bn.gamma + bn.beta)
+    assert (y - ref).abs().max().item() < 1e-5
+
+
+def test_maxpool_stem_transpose_sgd():
+    import torch
+    import torch.nn.functional as F
+    from sniper_b200 import ops
+    torch.manual_seed(2)
+    x = torch.randn(2, 18, 22, 64, device="cuda")
+    y = ops.maxpool3x3s2(x)
+    ref = F.max_pool2d(x.permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(y, ref)
+    img = torch.randn(2, 3, 64, 96, device="cuda") * 50
+    w = torch.randn(64, 7, 7, 3, device="cuda") * 0.05
+    isc, ish = torch.rand(3, device="cuda") + 0.5, torch.randn(3, device="cuda")
+    osc, osh = torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda")
+    o = ops.stem_conv(img, w, isc, ish, osc, osh)
+    xin = img * isc.view(1, 3, 1, 1) + ish.view(1, 3, 1, 1)
+    r = F.conv2d(xin.double(), w.permute(0, 3, 1, 2).double(), None, stride=2, padding=3)
+    r = torch.relu(r * osc.double().view(1, 64, 1, 1) + osh.double().view(1, 64, 1, 1)).permute(0, 2, 3, 1)
+    assert o.shape == r.shape and (o.double() - r).abs().max().item() < 1e-3
+    wt = torch.randn(96, 9, 64, device="cuda")
+    sel = torch.tensor([8, 7, 6, 5, 4, 3, 2, 1, 0], dtype=torch.int32, device="cuda")
+    t = ops.weight_transpose(wt, 96, 9, 64, sel).view(64, 9, 96)
+    assert torch.equal(t, wt.flip(1).permute(2, 1, 0).contiguous())
+    n = 1001
+    wv, mom, g = torch.randn(n + 3, device="cuda")[:n], torch.randn(n + 3, device="cuda")[:n], torch.randn(n + 3, device="cuda")[:n]
+    w0, m0 = wv.clone(), mom.clone()
+    ops.sgd_mom(wv, mom, g, lr=0.01, wd=1e-4, momentum=0.9)
+    m1 = 0.9 * m0 - 0.01 * 1e-4 * w0 - 0.01 * g
+    assert (mom - m1).abs().max().item() < 1e-6 and (wv - (w0 + m1)).abs().max().item() < 1e-6
+
+
+def test_losses_match_torch():
+    import torch
+    import torch.nn.functional as F
+    from sniper_b200 import ops
+    torch.manual_seed(3)
+    B, H, W, A = 3, 8, 8, 21
+    score = torch.randn(B, H, W, 128, device="cuda")
+    label = torch.randint(-1, 2, (B, A * H * W), device="cuda").float()
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.count_valid(label, cnt)
+    assert int(cnt) == int((label != -1).sum())
+    prob = torch.zeros(B, H, W, 42, device="cuda")
+    ds = torch.zeros(B, H, W, 128, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    ops.rpn_softmax_loss(score, label, A, 1.0, cnt, prob, ds, loss)
+    s = score[..., :42].double().requires_grad_(True)
+    lg = torch.stack([s[..., :A], s[..., A:]], -1)                       # [B,H,W,A,2]
+    lab = label.view(B, A, H, W).permute(0, 2, 3, 1).long()              # (a,h,w) -> [B,H,W,A]
+    ce = F.cross_entropy(lg.reshape(-1, 2), lab.reshape(-1), ignore_index=-1, reduction="sum")
+    (ce / max(1, int(cnt))).backward()
+    assert (ds[..., :42].double() - s.grad).abs().max().item() < 1e-6
+    assert abs(float(loss) - float(ce)) < 1e-2
+    p = torch.softmax(lg, -1)
+    assert (prob[..., :A].double() - p[..., 0]).abs().max().item() < 1e-6
+    # rpn smooth l1
+    pred = torch.randn(B, H, W, 128, device="cuda") * 2
+    tgt = torch.randn(B, 4 * A, H, W, device="cuda")
+    wgt = (torch.rand(B, 4 * A, H, W, device="cuda") > 0.7).float()
+    dp = torch.zeros(B, H, W, 128, device="cuda")
+    l2 = torch.zeros(1, device="cuda")
+    ops.rpn_smooth_l1_loss(pred, tgt, wgt, 4 * A, 0.25, dp, l2)
+    pr = pred[..., :84].double().requires_grad_(True)
+    d = pr - tgt.permute(0, 2, 3, 1).double()
+    sl = (wgt.permute(0, 2, 3, 1).double() * F.smooth_l1_loss(d, torch.zeros_like(d), reduction="none", beta=1.0)).sum()
+    (sl * 0.25).backward()
+    assert (dp[..., :84].double() - pr.grad).abs().max().item() < 1e-6
+    assert abs(float(l2) - float(sl)) < 1e-2
+    # rcnn softmax / smooth l1
+    N, K = 700, 81
+    lg2 = torch.randn(N, 88, device="cuda")
+    lb = torch.randint(0, K, (N,), device="cuda").float()
+    lb[::17] = -1
+    c2 = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ops.count_valid(lb, c2)
+    pb, gr, l3 = torch.zeros(N, K, device="cuda"), torch.zeros(N, 88, device="cuda"), torch.zeros(1, device="cuda")
+    ops.softmax_ce(lg2, lb, K, 1.0, c2, pb, gr, l3)
+    z = lg2[:, :K].double().requires_grad_(True)
+    ce2 = F.cross_entropy(z, lb.long(), ignore_index=-1, reduction="sum")
+    (ce2 / int(c2)).backward()
+    assert (gr[:, :K].double() - z.grad).abs().max().item() < 1e-6
+    assert abs(float(l3) - float(ce2)) < 5e-2
+    bp = torch.randn(N, 88, device="cuda")
+    bt, bw = torch.randn(N, 4, device="cuda"), (torch.rand(N, 4, device="cuda") > 0.5).float()
+    g4, l4 = torch.zeros(N, 88, device="cuda"), torch.zeros(1, device="cuda")
+    ops.smooth_l1_loss(bp[:, 81:85], bt, bw, 4, 1.0 / 3008, g4[:, 81:85], l4)
+    q = bp[:, 81:85].double().requires_grad_(True)
+    sl2 = (bw.double() * F.smooth_l1_loss(q - bt.double(), torch.zeros(N, 4, device="cuda", dtype=torch.double), reduction="none")).sum()
+    (sl2 / 3008).backward()
+    assert (g4[:, 81:85].double() - q.grad).abs().max().item() < 1e-7
