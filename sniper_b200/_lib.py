@@ -42,6 +42,8 @@ SIGNATURES = {
     "sniper_rpn_smooth_l1_loss": ("i", "pippiiiifpipp"),
     "sniper_softmax_ce": ("i", "pipiiifppipipp"),
     "sniper_smooth_l1_loss": ("i", "pipplifpipp"),
+    "sniper_deform_im2col": ("i", "pp" "iiiiiiiiiii" "pp"),
+    "sniper_deform_col2im": ("i", "ppp" "iiiiiiiiiii" "ppp"),
 }
 
 _lib = None

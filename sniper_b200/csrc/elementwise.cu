@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
       }
     }
   }
-  __shared__ float4 sa[8][32], sb[8][32];
+  __shared__ __align__(16) float4 sa[8][32], sb[8][32];
   sa[threadIdx.y][threadIdx.x] = a;
   sb[threadIdx.y][threadIdx.x] = b;
   __syncthreads();
@@ -259,8 +259,8 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
                                                          const float* __restrict__ out_shift, float* __restrict__ y,
                                                          int NB, int H, int W, int Ho, int Wo) {
   constexpr int PH = kStemTH * 2 + 5, PW = kStemTW * 2 + 5;  // 21 x 37
-  __shared__ float s_in[3][PH][PW + 1];
-  __shared__ float s_w[147][64];  // [(kh,kw,c)][co]
+  __shared__ __align__(16) float s_w[147][64];  // [(kh,kw,c)][co]
+  __shared__ float s_in[3][PH][PW + 1];  // [(kh,kw,c)][co]
   const int n = blockIdx.z;
   const int oh0 = blockIdx.y * kStemTH, ow0 = blockIdx.x * kStemTW;
   for (int i = threadIdx.x; i < 147 * 64; i += 128) {

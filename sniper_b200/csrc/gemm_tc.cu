@@ -550,8 +550,11 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, long dy_ld, const void* X, long x_l
   SN_CHECK(Cout % E == 0, "wgrad: Cout (%d) must be a multiple of %d", Cout, E);
   SN_CHECK(ntaps >= 1 && ntaps <= kMaxTaps, "wgrad: ntaps out of range");
   const long pixels = (long)NB * Ho * Wo;
-  SN_CHECK(Wo % kp == 0 || kp % Wo == 0, "wgrad: Wo (%d) incompatible with k-block of %d pixels", Wo, kp);
-  SN_CHECK(pixels % kp == 0 && (Wo >= kp || (Ho * Wo) % kp == 0), "wgrad: pixel count must tile by %d", kp);
+  // k-blocks are kp consecutive output pixels.  Either they tile rows exactly, or the problem is a single
+  // row (NB == 1, Ho == 1: FC layers viewed as [1,1,N,C]) where the tail is zero-filled by TMA.
+  const bool single_row = (NB == 1 && Ho == 1);
+  SN_CHECK(single_row || ((Wo % kp == 0 || kp % Wo == 0) && pixels % kp == 0 && (Wo >= kp || (Ho * Wo) % kp == 0)),
+           "wgrad: output %dx%d does not tile by %d pixels", Ho, Wo, kp);
   const int bw = Wo >= kp ? kp : Wo, bh = kp / bw;
   const int bn = Cin % 128 == 0 ? 128 : 64;
   GemmParams p;
@@ -576,7 +579,7 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, long dy_ld, const void* X, long x_l
   p.ntaps = ntaps;
   for (int t = 0; t < ntaps; ++t) { p.tap_dh[t] = tap_dh[t]; p.tap_dw[t] = tap_dw[t]; }
   p.conv_stride = stride; p.Ho = Ho; p.Wo = Wo; p.kp = kp; p.wg_cin_blocks = Cin / bn;
-  const long total_kb = pixels / kp;
+  const long total_kb = (pixels + kp - 1) / kp;
   if (splits < 1) splits = 1;
   while (splits > 1 && total_kb % splits != 0) --splits;
   p.num_kb = (int)(total_kb / splits);

@@ -1,0 +1,532 @@
+"""ResNet-101 SNIPER Faster-R-CNN / R-FCN training graph on the sm_100a kernels (NHWC, explicit backward).
+
+Mirrors symbols/faster/resnet_mx_101_e2e.py of the reference layer by layer (names are the reference's
+parameter names so checkpoints map one to one):
+  resnetc4        :394-420   residual_unit :36-69
+  resnetc5        :422-448   residual_unit_deform :106-145
+  get_rpn         :147-155   get_symbol_rcnn (is_train) :227-345   init_weight_rcnn :450-485
+The forward/backward order is fixed at construction (no graph executor, no autograd): every method below
+is a sequence of C-ABI launches on the current CUDA stream, so one training step can be captured into a CUDA
+graph.  Frozen layers (conv0, bn0, stage1 -- FIXED_PARAMS, sniper_res101_e2e.yml:22-25 -- and bn_data) run
+forward only.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+
+SCALES = (2, 4, 7, 10, 13, 16, 24)
+RATIOS = (0.5, 1, 2)
+
+
+class Cfg:
+    """The slice of configs/faster/sniper_res101_e2e.yml the training graph reads."""
+    num_classes = 81
+    num_anchors = 21
+    feat_stride = 16
+    scales = SCALES
+    ratios = RATIOS
+    rpn_post_nms_top_n = 300          # multi_proposal_target-inl.h:70
+    rpn_batch_size = 256              # TRAIN.RPN_BATCH_SIZE
+    batch_images = 16                 # TRAIN.BATCH_IMAGES (per GPU)
+    bn_eps = 2e-5
+    bn_momentum = 0.995               # main_train.py:27
+    lr = 0.015
+    wd = 1e-4
+    momentum = 0.9
+    units = (3, 4, 23, 3)
+    filter_list = (64, 256, 512, 1024, 2048)
+    grad_scale = 1.0                  # TRAIN.scale only applies to fp16
+    wgrad_splits = 8
+
+
+# ------------------------------------------------------------------------------------------------
+class ParamStore:
+    """All trainable parameters in ONE flat fp32 buffer (+ grad, + momentum): one NCCL all-reduce and one
+    fused SGD launch per optimizer group per step (replaces ~330 per-key kvstore push/pull pairs,
+    SNIPER-mxnet/python/mxnet/model.py:126-136).  Groups = (lr_mult, wd_mult) as MXNet derives them:
+    wd_mult 0 for names not ending in _weight/_gamma, lr_mult from the symbol attribute (offset: 0.01)."""
+
+    def __init__(self):
+        self.specs = []   # (name, shape, group)
+        self.views = {}
+        self.grads = {}
+
+    def add(self, name, shape, lr_mult=1.0):
+        wd_mult = 1.0 if (name.endswith("_weight") or name.endswith("_gamma")) else 0.0
+        self.specs.append((name, tuple(shape), (lr_mult, wd_mult)))
+
+    def finalize(self, device):
+        groups = sorted(set(g for _, _, g in self.specs))
+        off = 0
+        self.segments = []
+        layout = {}
+        for g in groups:
+            start = off
+            for name, shape, gg in self.specs:
+                if gg != g:
+                    continue
+                n = int(np.prod(shape))
+                layout[name] = (off, shape)
+                off += (n + 3) // 4 * 4          # keep every tensor 16-byte aligned
+            self.segments.append((start, off, g))
+        self.total = off
+        self.w = torch.zeros(off, device=device)
+        self.g = torch.zeros(off, device=device)
+        self.mom = torch.zeros(off, device=device)
+        for name, (o, shape) in layout.items():
+            n = int(np.prod(shape))
+            self.views[name] = self.w[o:o + n].view(shape)
+            self.grads[name] = self.g[o:o + n].view(shape)
+        self.layout = layout
+
+    def __getitem__(self, name):
+        return self.views[name]
+
+    def grad(self, name):
+        return self.grads[name]
+
+    def sgd_step(self, lr, wd, momentum, rescale=1.0):
+        """optimizer_op-inl.h:279-300 on every segment."""
+        for s, e, (lr_mult, wd_mult) in self.segments:
+            ops.sgd_mom(self.w[s:e], self.mom[s:e], self.g[s:e], lr * lr_mult, wd * wd_mult, momentum, rescale)
+
+
+# ------------------------------------------------------------------------------------------------
+class Conv:
+    """NHWC convolution with weights [Cout, kh*kw*Cin] (tap-major), optional bias; data/weight gradients on
+    the tcgen05 kernels.  Cout is padded up to `cout_pad` with zero rows where the reference's channel
+    count (72, 126, 85, 98) is not a multiple of 32."""
+
+    def __init__(self, P, name, cin, cout, k=1, stride=1, dil=1, pad=0, bias=False, trainable=True, cout_pad=None,
+                 lr_mult=1.0, need_dgrad=True, plain_wt=False):
+        self.name, self.cin, self.cout, self.k = name, cin, cout, k
+        self.stride, self.dil, self.pad, self.bias = stride, dil, pad, bias
+        self.coutp = cout_pad or cout
+        self.trainable, self.need_dgrad, self.plain_wt = trainable, need_dgrad, plain_wt
+        self.K = k * k * cin
+        self.P = P
+        if trainable:
+            P.add(name + "_weight", (self.coutp, self.K), lr_mult)
+            if bias:
+                P.add(name + "_bias", (self.coutp,), lr_mult)
+        self.wt = None
+        self.frozen_w = None
+        self.frozen_b = None
+
+    # ---- parameters
+    @property
+    def w(self):
+        return self.P[self.name + "_weight"] if self.trainable else self.frozen_w
+
+    @property
+    def b(self):
+        if not self.bias:
+            return None
+        return self.P[self.name + "_bias"] if self.trainable else self.frozen_b
+
+    def init(self, std=None, device=None, gen=None):
+        shape = (self.coutp, self.K)
+        if std is None:
+            std = math.sqrt(2.0 / self.K)      # He-normal backbone
+        w = torch.zeros(shape, device=device)
+        if std > 0:
+            w[:self.cout].normal_(0, std, generator=gen)
+        if self.trainable:
+            self.w.copy_(w)
+            if self.bias:
+                self.b.zero_()
+        else:
+            self.frozen_w = w
+            if self.bias:
+                self.frozen_b = torch.zeros(self.coutp, device=device)
+
+    # ---- forward
+    def fwd(self, x, out=None, scale=None, shift=None, relu=False, residual=None):
+        """y = epi(conv(x)); epilogue order: *scale, +shift (or +bias), +residual, relu."""
+        add = shift if shift is not None else self.b
+        return ops.conv2d_nhwc(x, self.w, kh=self.k, kw=self.k, stride=self.stride, dil=self.dil, pad=self.pad, out=out,
+                               scale=scale, bias=add, residual=residual, relu=relu)
+
+    # ---- backward
+    def prepare_bwd(self):
+        """Re-layout of the (just updated) weights for the data gradient: [Cin, taps', Cout]."""
+        if not (self.trainable and self.need_dgrad):
+            return
+        dev = self.w.device
+        k, T = self.k, self.k * self.k
+        if self.plain_wt:
+            # plain 2-D transpose [Cout, K] -> [K, Cout] (deformable conv: the GEMM runs on the im2col buffer)
+            if getattr(self, "_sel", None) is None:
+                self._sel = torch.zeros(1, dtype=torch.int32, device=dev)
+                self.wt = torch.empty(self.K, self.coutp, device=dev)
+            ops.weight_transpose(self.w, self.coutp, 1, self.K, self._sel, out=self.wt)
+        elif self.stride == 1 or k == 1:
+            sel = list(range(T - 1, -1, -1))
+            if getattr(self, "_sel", None) is None:
+                self._sel = torch.tensor(sel, dtype=torch.int32, device=dev)
+                self.wt = torch.empty(self.cin, T * self.coutp, device=dev)
+            ops.weight_transpose(self.w, self.coutp, T, self.cin, self._sel, out=self.wt)
+        else:
+            # stride 2, 3x3, pad 1: four output-parity classes, each a stride-1 conv over dY
+            assert k == 3 and self.stride == 2 and self.pad == 1 and self.dil == 1
+            if getattr(self, "_sel", None) is None:
+                self._sel, self.wt, self._taps = [], [], []
+                for ph in (0, 1):
+                    for pw in (0, 1):
+                        khs = [1] if ph == 0 else [0, 2]
+                        kws = [1] if pw == 0 else [0, 2]
+                        sel = [kh * 3 + kw for kh in khs for kw in kws]
+                        dh = [(ph + 1 - kh) // 2 for kh in khs for _ in kws]
+                        dw = [(pw + 1 - kw) // 2 for _ in khs for kw in kws]
+                        self._sel.append(torch.tensor(sel, dtype=torch.int32, device=dev))
+                        self.wt.append(torch.empty(self.cin, len(sel) * self.coutp, device=dev))
+                        self._taps.append((dh, dw, ph, pw))
+            for s, w in zip(self._sel, self.wt):
+                ops.weight_transpose(self.w, self.coutp, 9, self.cin, s, out=w)
+
+    def bwd_data(self, dy, in_hw, out=None, residual=None):
+        """dX = conv^T(dY).  dy: [N,Ho,Wo,coutp]; returns [N,H,W,Cin] (+ residual)."""
+        NB = dy.shape[0]
+        H, W = in_hw
+        k = self.k
+        if self.stride == 1:
+            padb = self.dil * (k - 1) - self.pad
+            return ops.conv2d_nhwc(dy, self.wt, kh=k, kw=k, stride=1, dil=self.dil, pad=padb, out=out, residual=residual)
+        if out is None:
+            out = torch.zeros(NB, H, W, self.cin, device=dy.device) if residual is None else residual
+        Ho, Wo = dy.shape[1], dy.shape[2]
+        if k == 1:
+            # dX[2a, 2b] = dY[a,b] * W ; other positions receive nothing
+            return ops.conv2d_nhwc(dy, self.wt, kh=1, kw=1, out=out, residual=residual if residual is not None else None,
+                                   out_hw=(Ho, Wo), out_map=(H, W, 2, 0, 0))
+        for wt, (dh, dw, ph, pw) in zip(self.wt, self._taps):
+            ops.conv2d_nhwc(dy, wt, kh=0, kw=0, taps=(dh, dw), out=out, residual=residual if residual is not None else None,
+                            out_hw=(H // 2, W // 2), out_map=(H, W, 2, ph, pw))
+        return out
+
+    def bwd_weight(self, dy, x, splits=8):
+        gw = self.P.grad(self.name + "_weight")
+        ops.conv2d_wgrad_nhwc(dy, x, kh=self.k, kw=self.k, stride=self.stride, dil=self.dil, pad=self.pad, dw_out=gw,
+                              splits=splits)
+        if self.bias:
+            ops.colsum_accum(dy, self.P.grad(self.name + "_bias"))
+
+
+class BN:
+    """BatchNorm + ReLU.  train: batch statistics over this GPU's chips (README.md:10); frozen: moving stats."""
+
+    def __init__(self, P, name, C, frozen, fix_gamma=False):
+        self.name, self.C, self.frozen, self.fix_gamma = name, C, frozen, fix_gamma
+        self.P = P
+        if not frozen:
+            P.add(name + "_gamma", (C,))
+            P.add(name + "_beta", (C,))
+        self.st = None
+
+    def build(self, device):
+        if self.frozen:
+            self.st = ops.BNState(self.C, device)
+        else:
+            self.st = ops.BNState(self.C, device, self.P[self.name + "_gamma"], self.P[self.name + "_beta"],
+                                  self.P.grad(self.name + "_gamma"), self.P.grad(self.name + "_beta"))
+            self.st.gamma.fill_(1.0)
+
+    def fwd(self, x, cfg, relu=True):
+        if self.frozen:
+            return ops.affine_act(x, self.st.scale, self.st.shift, relu=relu)
+        ops.bn_stats(x, self.st, eps=cfg.bn_eps, momentum=cfg.bn_momentum)
+        return ops.affine_act(x, self.st.scale, self.st.shift, relu=relu)
+
+    def bwd(self, x, dy, add=None):
+        return ops.bn_relu_bwd(x, dy, self.st, add=add)
+
+
+# ------------------------------------------------------------------------------------------------
+class Unit:
+    """Pre-activation bottleneck (residual_unit :36-69 / residual_unit_deform :106-145)."""
+
+    def __init__(self, P, name, cin, cout, stride, dim_match, frozen, deform=False, first_trainable=False):
+        mid = cout // 4
+        self.name, self.cin, self.cout, self.mid = name, cin, cout, mid
+        self.stride, self.dim_match, self.frozen, self.deform = stride, dim_match, frozen, deform
+        t = not frozen
+        self.bn1 = BN(P, name + "_bn1", cin, frozen)
+        self.conv1 = Conv(P, name + "_conv1", cin, mid, 1, trainable=t, need_dgrad=not first_trainable)
+        self.bn2 = BN(P, name + "_bn2", mid, frozen)
+        if deform:
+            self.offset = Conv(P, name + "_offset", mid, 72, 3, 1, 2, 2, bias=True, cout_pad=96)
+            self.conv2 = Conv(P, name + "_conv2", mid, mid, 3, 1, 2, 2, trainable=t, plain_wt=True)
+        else:
+            self.conv2 = Conv(P, name + "_conv2", mid, mid, 3, stride, 1, 1, trainable=t)
+        self.bn3 = BN(P, name + "_bn3", mid, frozen)
+        self.conv3 = Conv(P, name + "_conv3", mid, cout, 1, trainable=t)
+        self.sc = None if dim_match else Conv(P, name + "_sc", cin, cout, 1, stride, trainable=t,
+                                              need_dgrad=not first_trainable)
+        self.first_trainable = first_trainable
+        self.saved = None
+
+    def convs(self):
+        cs = [self.conv1, self.conv2, self.conv3]
+        if self.sc is not None:
+            cs.append(self.sc)
+        if self.deform:
+            cs.append(self.offset)
+        return cs
+
+    def bns(self):
+        return [self.bn1, self.bn2, self.bn3]
+
+    def fwd(self, x, cfg, out=None):
+        if self.frozen:
+            a1 = self.bn1.fwd(x, cfg)
+            a2 = self.conv1.fwd(a1, scale=self.bn2.st.scale, shift=self.bn2.st.shift, relu=True)
+            a3 = self.conv2.fwd(a2, scale=self.bn3.st.scale, shift=self.bn3.st.shift, relu=True)
+            res = x if self.dim_match else self.sc.fwd(a1)
+            return self.conv3.fwd(a3, out=out, residual=res)
+        a1 = self.bn1.fwd(x, cfg)
+        c1 = self.conv1.fwd(a1)
+        a2 = self.bn2.fwd(c1, cfg)
+        if self.deform:
+            off = self.offset.fwd(a2)                                          # [N,H,W,96], 72 used
+            col = ops.deform_im2col(a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)
+            c2 = ops.gemm_nt(col, self.conv2.w).view(a2.shape[0], a2.shape[1], a2.shape[2], self.mid)
+        else:
+            off = col = None
+            c2 = self.conv2.fwd(a2)
+        a3 = self.bn3.fwd(c2, cfg)
+        res = x if self.dim_match else self.sc.fwd(a1)
+        y = self.conv3.fwd(a3, out=out, residual=res)
+        self.saved = (x, a1, c1, a2, c2, a3, off, col)
+        return y
+
+    def bwd(self, dout, cfg, extra_add=None):
+        """dout: grad of the unit output [N,Ho,Wo,cout] (may be a channel slice).  Returns grad of the input
+        (+ extra_add, used to merge the c4 half of the concat gradient into stage4_unit1's input gradient)."""
+        x, a1, c1, a2, c2, a3, off, col = self.saved
+        sp = cfg.wgrad_splits
+        hw_in = (x.shape[1], x.shape[2])
+        hw_mid = (c2.shape[1], c2.shape[2])
+        self.conv3.bwd_weight(dout, a3, sp)
+        da3 = self.conv3.bwd_data(dout, hw_mid)
+        dc2 = self.bn3.bwd(c2, da3)
+        if self.deform:
+            M = dc2.numel() // self.mid
+            gw = self.conv2.P.grad(self.conv2.name + "_weight")
+            ops.conv2d_wgrad_nhwc(dc2, col.view(a2.shape[0], a2.shape[1], a2.shape[2], -1), kh=1, kw=1, dw_out=gw, splits=sp)
+            dcol = ops.gemm_nt(dc2.view(M, self.mid), self.conv2.wt)         # wt = W^T [9*mid, mid]
+            da2, doff = ops.deform_col2im(dcol, a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)
+            self.offset.bwd_weight(doff, a2, sp)
+            da2 = self.offset.bwd_data(doff, (a2.shape[1], a2.shape[2]), out=da2, residual=da2)
+        else:
+            self.conv2.bwd_weight(dc2, a2, sp)
+            da2 = self.conv2.bwd_data(dc2, (a2.shape[1], a2.shape[2]))
+        dc1 = self.bn2.bwd(c1, da2)
+        self.conv1.bwd_weight(dc1, a1, sp)
+        if self.sc is not None:
+            self.sc.bwd_weight(dout, a1, sp)
+        if self.first_trainable:
+            # input comes from the frozen stage: nothing to propagate, but bn1's parameters still learn
+            return None
+        da1 = self.conv1.bwd_data(dc1, hw_in)
+        if self.sc is not None:
+            da1 = self.sc.bwd_data(dout, hw_in, out=da1, residual=da1)
+        dx = self.bn1.bwd(x, da1, add=dout if self.dim_match else extra_add)
+        self.saved = None
+        return dx
+
+
+# ------------------------------------------------------------------------------------------------
+class SniperResNet101:
+    """get_symbol_rcnn(cfg, is_train=True) as an executable object (resnet_mx_101_e2e.py:227-345)."""
+
+    def __init__(self, cfg=None, device="cuda", seed=5, deform_offset_std=0.0):
+        self.cfg = cfg or Cfg()
+        cfg = self.cfg
+        self.device = device
+        P = self.P = ParamStore()
+        fl = cfg.filter_list
+        # ---- frozen stem: bn_data, conv0, bn0 (resnetc4 :402-408)
+        self.bn_data = BN(P, "bn_data", 3, frozen=True, fix_gamma=True)
+        self.bn0 = BN(P, "bn0", 64, frozen=True)
+        self.conv0_w = None
+        # ---- stages
+        self.units = []
+        cin = fl[0]
+        for i, n in enumerate(cfg.units):
+            stage = i + 1
+            cout = fl[i + 1]
+            frozen = (stage == 1)
+            deform = (stage == 4)
+            stride = 1 if stage in (1, 4) else 2
+            for j in range(n):
+                u = Unit(P, "stage%d_unit%d" % (stage, j + 1), cin if j == 0 else cout, cout, stride if j == 0 else 1,
+                         dim_match=(j > 0), frozen=frozen, deform=deform, first_trainable=(stage == 2 and j == 0))
+                self.units.append(u)
+            cin = cout
+        A = cfg.num_anchors
+        # ---- heads (get_rpn :147-155, conv_new_1 :256-257, FCs :288-303)
+        self.rpn_conv = Conv(P, "rpn_conv_3x3", 3072, 512, 3, 1, 1, 1, bias=True)
+        # rpn_bbox_pred (4A) and rpn_cls_score (2A) fused into one 1x1 conv: rows [0,4A) | [4A,6A), padded to 128
+        self.rpn_head = Conv(P, "rpn_head", 512, 6 * A, 1, bias=True, cout_pad=128)
+        self.conv_new_1 = Conv(P, "conv_new_1", 3072, 256, 1, bias=True)
+        self.fc_offset = Conv(P, "offset", 7 * 7 * 256, 98, 1, bias=True, cout_pad=128, lr_mult=0.01)
+        self.fc_new_1 = Conv(P, "fc_new_1", 7 * 7 * 256, 1024, 1, bias=True)
+        self.fc_new_2 = Conv(P, "fc_new_2", 1024, 1024, 1, bias=True)
+        # cls_score (81) and bbox_pred (4) fused: rows [0,81) | [81,85), padded to 96
+        self.fc_out = Conv(P, "cls_bbox", 1024, cfg.num_classes + 4, 1, bias=True, cout_pad=96)
+        P.finalize(device)
+        self._init_weights(seed, deform_offset_std)
+        self.loss_buf = torch.zeros(8, device=device)
+        self.cnt_buf = torch.zeros(2, dtype=torch.int32, device=device)
+        self.step_count = 0
+
+    # ---------------------------------------------------------------- init (init_weight_rcnn :450-485)
+    def _init_weights(self, seed, deform_offset_std):
+        dev = self.device
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        cfg = self.cfg
+        self.conv0_w = torch.zeros(64, 7, 7, 3, device=dev).normal_(0, math.sqrt(2.0 / 147), generator=g)
+        for bn in (self.bn_data, self.bn0):
+            bn.build(dev)
+        # bn_data: frozen, fix_gamma; realistic pixel statistics so that conv0 sees O(1) inputs
+        self.bn_data.st.moving_mean.fill_(0.0)
+        self.bn_data.st.moving_var.fill_(60.0 ** 2)
+        ops.bn_frozen(self.bn_data.st, cfg.bn_eps, fix_gamma=True)
+        ops.bn_frozen(self.bn0.st, cfg.bn_eps)
+        for u in self.units:
+            for c in u.convs():
+                if c.name.endswith("_offset"):
+                    c.init(std=deform_offset_std, device=dev, gen=g)      # zeros in the reference (:451-456)
+                else:
+                    c.init(device=dev, gen=g)
+            for bn in u.bns():
+                bn.build(dev)
+                if bn.frozen:
+                    ops.bn_frozen(bn.st, cfg.bn_eps)
+        for c in (self.rpn_conv, self.rpn_head, self.conv_new_1, self.fc_new_1, self.fc_new_2, self.fc_out):
+            c.init(std=0.01, device=dev, gen=g)
+        self.fc_offset.init(std=deform_offset_std and 0.001, device=dev, gen=g)   # zeros in the reference (:476-477)
+
+    def trainable_convs(self):
+        cs = []
+        for u in self.units:
+            if not u.frozen:
+                cs += u.convs()
+        cs += [self.rpn_conv, self.rpn_head, self.conv_new_1, self.fc_offset, self.fc_new_1, self.fc_new_2, self.fc_out]
+        return cs
+
+    # ---------------------------------------------------------------- one training step
+    def forward_backward(self, batch):
+        """batch: dict of device tensors named as MNIteratorE2E provides them (MNIteratorE2E.py:175-219):
+        data [B,3,512,512], label [B,A*H*W], bbox_target/bbox_weight [B,4A,H,W], gt_boxes [B,100,5],
+        valid_ranges [B,2], im_info [B,3].  Leaves parameter gradients in self.P.g and returns the outputs of
+        the reference's Group([rpn_cls_prob, rpn_bbox_loss, cls_prob, bbox_loss, label]) (:338) as a dict."""
+        cfg = self.cfg
+        P = self.P
+        A = cfg.num_anchors
+        data = batch["data"]
+        B = data.shape[0]
+        P.g.zero_()
+        self.loss_buf.zero_()
+        self.cnt_buf.zero_()
+        # weights were updated by the previous step: refresh the data-gradient operands
+        for c in self.trainable_convs():
+            c.prepare_bwd()
+
+        # ---- backbone forward
+        x = ops.stem_conv(data, self.conv0_w, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
+                          self.bn0.st.shift)
+        x = ops.maxpool3x3s2(x)
+        n1, n2, n3, n4 = cfg.units
+        Hf = data.shape[2] // cfg.feat_stride
+        cat = torch.empty(B, Hf, Hf, 3072, device=data.device)           # Concat(c4, c5) written in place
+        last3 = n1 + n2 + n3 - 1
+        for i, u in enumerate(self.units):
+            out = None
+            if i == last3:
+                out = cat[..., :1024]
+            elif i == len(self.units) - 1:
+                out = cat[..., 1024:]
+            x = u.fwd(x, cfg, out=out)
+
+        # ---- RPN (get_rpn) + conv_new_1
+        rpn = self.rpn_conv.fwd(cat, relu=True)
+        head = self.rpn_head.fwd(rpn)                                      # [B,H,W,128]: 4A deltas | 2A scores
+        feat = self.conv_new_1.fwd(cat, relu=True)
+        dhead = torch.zeros_like(head)
+        prob = torch.empty(B, Hf, Hf, 2 * A, device=data.device)
+        ops.count_valid(batch["label"], self.cnt_buf[0:1])
+        ops.rpn_softmax_loss(head[..., 4 * A:6 * A], batch["label"], A, cfg.grad_scale, self.cnt_buf[0:1], prob,
+                             dhead[..., 4 * A:6 * A], self.loss_buf[0:1])
+        ops.rpn_smooth_l1_loss(head, batch["bbox_target"], batch["bbox_weight"], 4 * A,
+                               3.0 * cfg.grad_scale / float(cfg.batch_images * cfg.rpn_batch_size), dhead,
+                               self.loss_buf[1:2])
+        # ---- proposals + targets, all on device
+        rois, label, bbox_target, bbox_weight = ops.multi_proposal_target(
+            prob, head, batch["im_info"], batch["gt_boxes"], batch["valid_ranges"], feat_stride=cfg.feat_stride,
+            scales=cfg.scales, ratios=cfg.ratios, rpn_post_nms_top_n=cfg.rpn_post_nms_top_n, layout=ops.NHWC)
+        N = rois.shape[0]
+        # ---- R-FCN head
+        ps = dict(spatial_scale=1.0 / cfg.feat_stride, output_dim=256, group_size=1, pooled_size=7, part_size=7,
+                  sample_per_part=4, layout=ops.NHWC)
+        offset_t, _, _ = ops.deform_psroi_fwd(feat, rois, None, no_trans=True, want_count=False, **ps)
+        off = ops.gemm_nt(offset_t.view(N, -1), self.fc_offset.w, bias=self.fc_offset.b)          # [N,128], 98 used
+        trans = off[:, :98].contiguous().view(N, 2, 7, 7)
+        pooled, _, _ = ops.deform_psroi_fwd(feat, rois, trans, no_trans=False, trans_std=0.1, want_count=False, **ps)
+        fc1 = ops.gemm_nt(pooled.view(N, -1), self.fc_new_1.w, bias=self.fc_new_1.b, relu=True)
+        fc2 = ops.gemm_nt(fc1, self.fc_new_2.w, bias=self.fc_new_2.b, relu=True)
+        out = ops.gemm_nt(fc2, self.fc_out.w, bias=self.fc_out.b)                                  # [N,96]
+        K = cfg.num_classes
+        dout = torch.zeros_like(out)
+        cls_prob = torch.empty(N, K, device=data.device)
+        ops.count_valid(label, self.cnt_buf[1:2])
+        ops.softmax_ce(out, label, K, cfg.grad_scale, self.cnt_buf[1:2], cls_prob, dout, self.loss_buf[2:3])
+        ops.smooth_l1_loss(out[:, K:K + 4], bbox_target, bbox_weight, 4, cfg.grad_scale / (188.0 * 16.0),
+                           dout[:, K:K + 4], self.loss_buf[3:4])
+
+        # ================= backward =================
+        sp = cfg.wgrad_splits
+        v4 = lambda t: t.view(1, 1, t.shape[0], t.shape[1])
+        self.fc_out.bwd_weight(v4(dout), v4(fc2), sp)
+        dfc2 = ops.relu_bwd(fc2, ops.gemm_nt(dout, self.fc_out.wt))
+        self.fc_new_2.bwd_weight(v4(dfc2), v4(fc1), sp)
+        dfc1 = ops.relu_bwd(fc1, ops.gemm_nt(dfc2, self.fc_new_2.wt))
+        self.fc_new_1.bwd_weight(v4(dfc1), v4(pooled.view(N, -1)), sp)
+        dpooled = ops.gemm_nt(dfc1, self.fc_new_1.wt).view(pooled.shape)
+        dfeat, dtrans = ops.deform_psroi_bwd(dpooled, feat, rois, trans, no_trans=False, trans_std=0.1, **ps)
+        doff = torch.zeros_like(off)
+        doff[:, :98] = dtrans.view(N, 98)
+        self.fc_offset.bwd_weight(v4(doff), v4(offset_t.view(N, -1)), sp)
+        doffset_t = ops.gemm_nt(doff, self.fc_offset.wt).view(offset_t.shape)
+        ops.deform_psroi_bwd(doffset_t, feat, rois, None, no_trans=True, data_diff=dfeat, **ps)
+        dfeat = ops.relu_bwd(feat, dfeat)
+        hw = (Hf, Hf)
+        self.conv_new_1.bwd_weight(dfeat, cat, sp)
+        dcat = self.conv_new_1.bwd_data(dfeat, hw)
+        self.rpn_head.bwd_weight(dhead, rpn, sp)
+        drpn = ops.relu_bwd(rpn, self.rpn_head.bwd_data(dhead, hw))
+        self.rpn_conv.bwd_weight(drpn, cat, sp)
+        dcat = self.rpn_conv.bwd_data(drpn, hw, out=dcat, residual=dcat)
+        # ---- backbone backward (stage 4, then stage 3 with the c4 half of dcat added, then stage 2)
+        g = dcat[..., 1024:]
+        for i in range(len(self.units) - 1, n1 - 1, -1):
+            u = self.units[i]
+            g = u.bwd(g, cfg, extra_add=dcat[..., :1024] if i == last3 + 1 else None)
+        self.step_count += 1
+        return dict(rpn_cls_prob=prob, rpn_bbox_loss=self.loss_buf[1:2], cls_prob=cls_prob, bbox_loss=self.loss_buf[3:4],
+                    label=label, rois=rois, losses=self.loss_buf)
+
+    def update(self, lr=None):
+        cfg = self.cfg
+        self.P.sgd_step(cfg.lr if lr is None else lr, cfg.wd, cfg.momentum)
+
+    def train_step(self, batch, lr=None, allreduce=None):
+        out = self.forward_backward(batch)
+        if allreduce is not None:
+            allreduce(self.P.g)           # ONE collective per step over the flat gradient bucket
+        self.update(lr)
+        return out

@@ -347,26 +347,52 @@ def count_valid(label, out, ignore=-1):
 
 def rpn_softmax_loss(score, label, A, grad_scale, valid_cnt, prob, dscore, loss_sum):
     """score/prob/dscore: NHWC [B,H,W,>=2A]; label [B, A*H*W] in (a,h,w) order."""
-    B, H, W, ld = score.shape
+    B, H, W, _ = score.shape
+    ld = score.stride(2)
     check(lib().sniper_rpn_softmax_loss(_ptr(score), ld, _ptr(label), B, H, W, A, float(grad_scale), _ptr(valid_cnt),
-                                        _ptr(prob), prob.shape[3], _ptr(dscore), 0 if dscore is None else dscore.shape[3],
+                                        _ptr(prob), prob.stride(2), _ptr(dscore), 0 if dscore is None else dscore.stride(2),
                                         _ptr(loss_sum), _stream()))
 
 
 def rpn_smooth_l1_loss(pred, target, weight, C4, grad_scale, dpred, loss_sum):
-    B, H, W, ld = pred.shape
-    check(lib().sniper_rpn_smooth_l1_loss(_ptr(pred), ld, _ptr(target), _ptr(weight), B, H, W, C4, float(grad_scale),
-                                          _ptr(dpred), dpred.shape[3], _ptr(loss_sum), _stream()))
+    B, H, W, _ = pred.shape
+    check(lib().sniper_rpn_smooth_l1_loss(_ptr(pred), pred.stride(2), _ptr(target), _ptr(weight), B, H, W, C4,
+                                          float(grad_scale), _ptr(dpred), dpred.stride(2), _ptr(loss_sum), _stream()))
 
 
 def softmax_ce(logits, label, K, grad_scale, valid_cnt, prob, grad, loss_sum, ignore=-1):
-    N, ld = logits.shape
+    N, ld = logits.shape[0], logits.stride(0)
     check(lib().sniper_softmax_ce(_ptr(logits), ld, _ptr(label), N, K, int(ignore), float(grad_scale), _ptr(valid_cnt),
-                                  _ptr(prob), 0 if prob is None else prob.shape[1], _ptr(grad),
-                                  0 if grad is None else grad.shape[1], _ptr(loss_sum), _stream()))
+                                  _ptr(prob), 0 if prob is None else prob.stride(0), _ptr(grad),
+                                  0 if grad is None else grad.stride(0), _ptr(loss_sum), _stream()))
 
 
 def smooth_l1_loss(pred, target, weight, C, grad_scale, grad, loss_sum):
-    N, ld = pred.shape
+    N, ld = pred.shape[0], pred.stride(0)
     check(lib().sniper_smooth_l1_loss(_ptr(pred), ld, _ptr(target), _ptr(weight), N, C, float(grad_scale), _ptr(grad),
-                                      grad.shape[1], _ptr(loss_sum), _stream()))
+                                      grad.stride(0), _ptr(loss_sum), _stream()))
+
+
+def deform_im2col(x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroups=4, out=None):
+    """Bilinear-sampled im2col (deformable_im2col.cuh:216-263): x [N,H,W,C], offset [N,Ho,Wo,>=dg*2*kh*kw]
+    -> col [N*Ho*Wo, kh*kw*C] (tap-major)."""
+    NB, H, W, C = x.shape
+    Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    if out is None:
+        out = torch.empty(NB * Ho * Wo, kh * kw * C, device=x.device)
+    check(lib().sniper_deform_im2col(_ptr(_f32(x)), _ptr(offset), NB, H, W, C, kh, kw, stride, dil, pad, dgroups,
+                                     offset.stride(2), _ptr(out), _stream()))
+    return out
+
+
+def deform_col2im(dcol, x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroups=4, dx=None, doffset=None):
+    """Transposes of deform_im2col: dx (accumulated) and doffset (deformable_im2col.cuh:317-360, 419-480)."""
+    NB, H, W, C = x.shape
+    if dx is None:
+        dx = torch.zeros_like(x)
+    if doffset is None:
+        doffset = torch.zeros_like(offset)
+    check(lib().sniper_deform_col2im(_ptr(dcol), _ptr(x), _ptr(offset), NB, H, W, C, kh, kw, stride, dil, pad, dgroups,
+                                     offset.stride(2), _ptr(dx), _ptr(doffset), _stream()))
+    return dx, doffset
