@@ -1,0 +1,101 @@
+"""Host-side ops of the path vs the reference's own compiled code (oracle/_ref) and the CPU oracle.
+No GPU, no compute kernels: runs in the CPU test tier."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from sniper_b200 import _lib, host, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_header_matches_library_and_bindings():
+    hdr = open(os.path.join(ROOT, "include", "sniper_b200.h")).read()
+    protos = re.findall(r"\n(?:int|size_t|const char\*)\s+(sniper_\w+)\s*\(([^;]*)\);", hdr)
+    assert len(protos) >= 30
+    L = _lib.lib()
+    for name, args in protos:
+        assert hasattr(L, name), "library does not export " + name
+        assert name in _lib.SIGNATURES, "no ctypes signature for " + name
+        nargs = 0 if args.strip() == "void" else len(args.split(","))
+        assert nargs == len(_lib.SIGNATURES[name][1]), name
+    for name in _lib.SIGNATURES:
+        assert any(n == name for n, _ in protos), name + " missing from the header"
+    assert L.sniper_abi_version() == 1
+
+
+def _config1_boxes(seed, n, W=1333, H=800):
+    """SURVEY 8d config 1 generator: sqrt(area) log-uniform in [8,400], aspect in [0.5,2]."""
+    rng = np.random.RandomState(seed)
+    s = np.exp(rng.uniform(np.log(8), np.log(400), n))
+    ar = np.exp(rng.uniform(np.log(0.5), np.log(2.0), n))
+    w, h = s * np.sqrt(ar), s / np.sqrt(ar)
+    cx, cy = rng.uniform(0, W, n), rng.uniform(0, H, n)
+    b = np.stack([np.clip(cx - w / 2, 0, W - 1), np.clip(cy - h / 2, 0, H - 1), np.clip(cx + w / 2, 0, W - 1),
+                  np.clip(cy + h / 2, 0, H - 1)], 1)
+    return b.astype(np.float32)
+
+
+@pytest.mark.skipif(O.ref_chips() is None, reason="oracle/_ref/libref_chips.so not built")
+@pytest.mark.parametrize("scale,stride,seed", [(3.0, 58, 1), (1.667, 56, 2), (0.8, 59, 3), (0.384, 57, 4)])
+def test_chips_generate_matches_reference_cchips(scale, stride, seed):
+    # config 1: one 1333x800 image, 20 GT + proposals, chip 512; reference lib/chips/cchips.cpp compiled as-is
+    gt = _config1_boxes(0, 20)
+    props = _config1_boxes(1, 400)
+    boxes = np.concatenate([gt, props]) * np.float32(scale)
+    W, H = int(1333 * scale), int(800 * scale)
+    boxes[:, [0, 2]] = np.clip(boxes[:, [0, 2]], 0, W - 1)
+    boxes[:, [1, 3]] = np.clip(boxes[:, [1, 3]], 0, H - 1)
+    ref = O.ref_chips_generate(boxes, W, H, 512, stride, seed=seed)
+    host.srand(seed)
+    ours = host.chips_generate(boxes, W, H, 512, stride)
+    assert ours.shape == ref.shape and ours.tobytes() == ref.tobytes()      # chip indices: bit-exact
+    assert len(ours) > 0
+    # every box that fits into some candidate chip is covered by a returned chip
+    ov = host.ignore_overlaps(ours.astype(np.float64), boxes.astype(np.float64))
+    assert (ov.max(0) == 1).sum() > 0
+
+
+def test_chips_empty_and_tiny_image():
+    assert host.chips_generate(np.zeros((0, 4), np.float32), 600, 400, 512, 32).shape == (0, 4)
+    b = np.array([[10, 10, 50, 60]], np.float32)
+    host.srand(1)
+    c = host.chips_generate(b, 300, 200, 512, 32)      # image smaller than a chip: corner chips only
+    if O.ref_chips() is not None:
+        np.testing.assert_array_equal(c, O.ref_chips_generate(b, 300, 200, 512, 32, seed=1))
+    assert len(c) == 1
+
+
+def test_cpu_nms_and_soft_nms_match_oracle():
+    rng = np.random.RandomState(2)
+    boxes = _config1_boxes(5, 6000)
+    dets = np.concatenate([boxes, rng.rand(6000, 1).astype(np.float32)], 1).astype(np.float32)
+    keep = host.cpu_nms(dets, 0.7)
+    np.testing.assert_array_equal(np.array(keep, np.int32), O.cpu_nms(dets, 0.7))
+    assert 0 < len(keep) < 6000
+    d2 = dets[:1500].copy()
+    out = host.cpu_soft_nms(d2, sigma=0.55).copy()
+    ref = O.cpu_soft_nms(dets[:1500], sigma=0.55)
+    assert out.tobytes() == ref.tobytes()
+    # ties: default order = stable descending
+    dets[:, 4] = np.round(dets[:, 4] * 8) / 8
+    k2 = host.cpu_nms(dets, 0.5, order=None)
+    assert len(k2) > 0
+    assert host.cpu_nms(np.zeros((0, 5), np.float32), 0.5) == []
+
+
+def test_bbox_overlaps_match_oracle():
+    a = _config1_boxes(7, 200).astype(np.float64)
+    b = _config1_boxes(8, 50).astype(np.float64)
+    assert host.bbox_overlaps(a, b).tobytes() == O.bbox_overlaps(a, b).tobytes()
+    assert host.ignore_overlaps(a, b).tobytes() == O.bbox_overlaps(a, b, ignore=True).tobytes()
+
+
+def test_product_path_fails_loudly_without_library(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsniper_b200.so")
+    with pytest.raises(RuntimeError):
+        _lib.lib()

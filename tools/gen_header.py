@@ -1,0 +1,82 @@
+"""Regenerates include/sniper_b200.h from the extern "C" definitions in sniper_b200/csrc/*.cu|cpp plus the
+reference citations below (kept here so that the header and the sources cannot drift apart)."""
+import glob
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DOC = {
+    "sniper_last_error": "Thread-local message of the last failing call.  Mirrors MXGetLastError (SNIPER-mxnet/include/mxnet/c_api.h:196-204).",
+    "sniper_abi_version": "ABI version of this library (bumped on any signature change).",
+    "sniper_multi_proposal_target_workspace_bytes": "Scratch bytes for sniper_multi_proposal_target_fwd: replaces ResourceRequest::kTempSpace of MultiProposalTargetProp (multi_proposal_target-inl.h:143-146).",
+    "sniper_generate_anchors": "Host helper, utils::GenerateAnchors (multi_proposal_target.cu:75-114): out[nr*ns,4], ratio-major.",
+    "sniper_proposal_decode": "K1: utils::getProps (multi_proposal_target.cu:263-331). Anchor shift + bbox_transform_inv + clip + min-size / valid-range filters -> SoA boxes float4[B*A*H*W], score, area. layout 0 = NCHW (reference), 1 = NHWC (channel strides given).",
+    "sniper_multi_proposal_target_fwd": "Drop-in for MultiProposalTargetGPUOp::Forward (multi_proposal_target.cu:362-589; operator surface multi_proposal_target-inl.h:55-177: arguments cls_prob,bbox_pred,im_info,gt_boxes,valid_ranges -> outputs rois,label,bbox_target,bbox_weight). Decode + greedy NMS (reference tie order) + GT append + IoU/label/target assignment, entirely on device: no D2H/H2D, no sync, no allocation. keep_idx/num_kept are optional parity outputs. Backward of the reference operator is a zero fill (cu:591-615) and needs no entry point.",
+    "sniper_deform_psroi_fwd": "DeformablePSROIPoolingOp::Forward (contrib/deformable_psroi_pooling-inl.h:84-125, kernel .cu:71-161). top_count optional (hidden output of the reference), sample_idx optional parity output [count, spp^2, 4].",
+    "sniper_deform_psroi_bwd": "DeformablePSROIPoolingOp::Backward (contrib/deformable_psroi_pooling-inl.h:127-174, kernel .cu:203-330). data_diff/trans_diff are accumulated into (kAddTo); zero them for kWriteTo.",
+    "sniper_psroi_fwd": "PSROIPoolingOp::Forward (contrib/psroi_pooling.cu:51-118). bins optional parity output [count,4] = hstart,hend,wstart,wend.",
+    "sniper_psroi_bwd": "PSROIPoolingOp::Backward (contrib/psroi_pooling.cu:146-210); accumulates into data_diff.",
+    "sniper_gemm_nt": "C[M,N] = epi(A[M,K] * B[N,K]^T) on tcgen05 (TMEM accumulators, TMA operands). Replaces FullyConnected -> cuBLAS (nn/fully_connected-inl.h) and linalg_gemm (contrib/deformable_convolution-inl.h:148-160). dtype 0 = fp32 storage / TF32 math, 1 = bf16. epi: *scale[n], +bias[n], +residual[m,n], relu; accumulate = red.global.add.",
+    "sniper_conv2d_nhwc": "NHWC implicit-GEMM convolution on tcgen05; also the stride-1/stride-2 data gradient (flipped / parity-split weights, strided output map). Replaces cudnnConvolutionForward / BackwardData (nn/cudnn/cudnn_convolution-inl.h:144,211-266).",
+    "sniper_conv2d_wgrad_nhwc": "Weight gradient dW[Cout, taps*Cin] += dY^T * im2col(X) on tcgen05 with MN-major operands and split-K. Replaces cudnnConvolutionBackwardFilter (nn/cudnn/cudnn_convolution-inl.h:211-266).",
+    "sniper_affine_act": "y = relu?(x*scale[c] + shift[c]) on [M,C] rows (BatchNorm apply + Activation; nn/batch_norm.cu:658-700).",
+    "sniper_bn_stats": "Train-mode BatchNorm statistics -> mean, invstd, scale, shift and moving statistics (cuDNN convention, nn/cudnn/cudnn_batch_norm-inl.h).",
+    "sniper_bn_frozen": "use_global_stats BatchNorm: scale/shift from the moving statistics (nn/batch_norm.cu:671-674 path).",
+    "sniper_bn_relu_bwd": "Backward of relu(bn_train(x)): dx (+add), dgamma +=, dbeta +=.",
+    "sniper_affine_relu_bwd": "Backward of relu?(x*scale+shift) for frozen BN.",
+    "sniper_relu_bwd": "dx = dy * (y > 0).",
+    "sniper_maxpool3x3s2_nhwc": "Pooling max 3x3 stride 2 pad 1 (resnet_mx_101_e2e.py:409; nn/pool.cuh).",
+    "sniper_stem_conv": "bn_data -> conv0 7x7/2 -> bn0 -> relu (resnet_mx_101_e2e.py:402-408), NCHW in, NHWC out.",
+    "sniper_weight_transpose": "wt[ci, j, co] = w[co, sel[j], ci]: operand layout for data gradients.",
+    "sniper_colsum": "out[c] += sum_m x[m,c] (bias gradients; cudnnConvolutionBackwardBias).",
+    "sniper_sgd_mom": "SGDMomKernel (optimizer_op-inl.h:279-300) on one flat buffer.",
+    "sniper_count_valid": "Device-side replacement of SoftmaxOutput's host valid count (softmax_output-inl.h:184-195).",
+    "sniper_rpn_softmax_loss": "SoftmaxOutput(multi_output, use_ignore, normalization=valid) for the RPN (softmax_output-inl.h:108-132, 162-206): prob + gradient in one pass.",
+    "sniper_rpn_smooth_l1_loss": "weight * smooth_l1(pred - target) + MakeLoss gradient for the RPN (mshadow_op.h:642-678; resnet_mx_101_e2e.py:330-334).",
+    "sniper_softmax_ce": "SoftmaxOutput(normalization=valid, use_ignore) flat form (softmax_output-inl.h:207-263).",
+    "sniper_smooth_l1_loss": "weight * smooth_l1(pred - target) + MakeLoss gradient (resnet_mx_101_e2e.py:318-319).",
+    "sniper_deform_im2col": "deformable_im2col (contrib/nn/deformable_im2col.cuh:216-263), NHWC, whole batch.",
+    "sniper_deform_col2im": "deformable_col2im + deformable_col2im_coord (contrib/nn/deformable_im2col.cuh:317-360, 419-480).",
+    "sniper_anchor_target": "RPN anchor matching of anchor_worker.worker (lib/data_utils/data_workers.py:164-371) on device.",
+    "sniper_chips_generate": "chips::cgenerate (lib/chips/cchips.cpp:54-177): host-side chip sampling, same rand() stream.",
+    "sniper_cpu_nms": "cpu_nms (lib/nms/cpu_nms.pyx:112-163), host.",
+    "sniper_cpu_soft_nms": "cpu_soft_nms (lib/nms/cpu_nms.pyx:17-110), host, in place.",
+    "sniper_bbox_overlaps": "bbox_overlaps_cython / ignore_overlaps_cython (lib/bbox/bbox.pyx:17-95), host, float64.",
+    "sniper_nms_gpu": "Batched hard NMS on device for per-scale inference NMS (lib/nms/nms_kernel.cu:34-144 replacement).",
+}
+
+
+def signatures():
+    out = []
+    for f in sorted(glob.glob(os.path.join(ROOT, "sniper_b200", "csrc", "*.cu")) +
+                    glob.glob(os.path.join(ROOT, "sniper_b200", "csrc", "*.cpp"))):
+        s = open(f).read()
+        for m in re.finditer(r'\n((?:int|size_t|const char\*)\s+(sniper_\w+)\s*\(([^)]*)\))\s*\{', s):
+            out.append((os.path.basename(f), m.group(2), re.sub(r'\s+', ' ', re.sub(r'/\*.*?\*/', '', m.group(1)))))
+    return out
+
+
+def main():
+    lines = ["/* sniper_b200 C-ABI -- generated by tools/gen_header.py from sniper_b200/csrc (do not edit by hand).",
+             " *",
+             " * Drop-in boundary of the SNIPER 512x512-chip training path: every entry point is extern \"C\", takes",
+             " * plain pointers and sizes (device pointers unless a comment says host), a cudaStream_t passed as",
+             " * void*, returns 0 on success and -1 on failure with the message in sniper_last_error().",
+             " * No entry point allocates device memory or synchronises.  Reference file:line each one replaces",
+             " * is cited above its prototype (paths relative to the reference repo; SNIPER-mxnet/src/operator/ is",
+             " * implied for operator sources).",
+             " */",
+             "#ifndef SNIPER_B200_H_", "#define SNIPER_B200_H_", "#include <stddef.h>", "#include <stdint.h>", "",
+             "#ifdef __cplusplus", 'extern "C" {', "#endif", ""]
+    for f, name, sig in signatures():
+        doc = DOC.get(name, "")
+        lines.append("/* [%s] %s */" % (f, doc))
+        lines.append(sig + ";")
+        lines.append("")
+    lines += ["#ifdef __cplusplus", "}", "#endif", "#endif  /* SNIPER_B200_H_ */", ""]
+    os.makedirs(os.path.join(ROOT, "include"), exist_ok=True)
+    open(os.path.join(ROOT, "include", "sniper_b200.h"), "w").write("\n".join(lines))
+
+
+if __name__ == "__main__":
+    main()
