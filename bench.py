@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""bench.py -- SNIPER 512x512-chip training throughput (chips/sec) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      (CPU reference arm, rank 0 only)
+
+Workload (BASELINE.json configs[1]): ResNet-101 SNIPER Faster-R-CNN/R-FCN, 512x512 chips, 20 chips per
+GPU, fp32 storage with TF32 tensor-core math, synthetic COCO-shaped chips + boxes, random-init weights.
+A step = forward + backward + (N>1: one NCCL gradient all-reduce) + fused SGD-momentum update.
+`value` : chips/sec with the batch already resident in HBM (CUDA-graph replay of the step).
+`e2e`   : chips/sec through Trainer.step(): pinned host batch -> H2D -> step -> D2H of the loss scalars.
+The data batches rotate through a pool larger than L2 (7 x 63 MB of input + >10 GB of activations per step),
+so no timed iteration finds its inputs in L2.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FWD_GFLOP_PER_CHIP = 145.54      # BASELINE.md section 2 / SURVEY.md 8d
+TRAIN_GFLOP_PER_CHIP = 420.2
+CHIPS_PER_GPU = 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = False
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        med = s[len(s) // 2] if s else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def tc_kernel_time(trainer):
+    """CUDA-event time and algorithmic FLOPs of every tcgen05 launch of one (eager) training step."""
+    import torch
+    from sniper_b200 import _lib, ops
+    L = _lib.lib()
+    names = ["sniper_gemm_nt", "sniper_conv2d_nhwc", "sniper_conv2d_wgrad_nhwc"]
+    events, flops = [], [0.0]
+    orig = {}
+
+    def wrap(name, raw):
+        def fn(*a):
+            if name == "sniper_gemm_nt":
+                M, N, K = a[6], a[7], a[8]
+                flops[0] += 2.0 * M * N * K
+            elif name == "sniper_conv2d_nhwc":
+                NB, Cin, Cout, ntaps, Ho, Wo = a[2], a[5], a[7], a[8], a[12], a[13]
+                flops[0] += 2.0 * NB * Ho * Wo * Cout * ntaps * Cin
+            else:
+                NB, Cin, Cout, ntaps, Ho, Wo = a[4], a[7], a[8], a[9], a[13], a[14]
+                flops[0] += 2.0 * NB * Ho * Wo * Cout * ntaps * Cin
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = raw(*a)
+            e1.record()
+            events.append((e0, e1))
+            return r
+        return fn
+    for n in names:
+        orig[n] = getattr(L, n)
+        L._cache[n] = wrap(n, orig[n])
+    try:
+        trainer.net.forward_backward(trainer.static)
+        torch.cuda.synchronize()
+    finally:
+        for n in names:
+            L._cache[n] = orig[n]
+    ms = sum(a.elapsed_time(b) for a, b in events)
+    return ms, flops[0], len(events)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sniper_b200 import model, ops, synth_batch
+    from sniper_b200.trainer import Trainer
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("--gpus %d needs torch.distributed.run (WORLD_SIZE unset)" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    cfg = model.Cfg()
+    cfg.batch_images = args.chips
+    trainer = Trainer(cfg, device="cuda:%d" % local_rank, world_size=world, use_graph=not args.no_graph)
+    pool = [synth_batch.make_batch(args.chips, seed=100 + 17 * rank + i, device="cpu", pinned=True) for i in range(args.pool)]
+    dev_pool = [{k: v.to("cuda:%d" % local_rank) for k, v in b.items()} for b in pool]
+    h2d = sum(v.numel() * v.element_size() for v in pool[0].values())
+    trainer.load(pool[0])
+    trainer.capture()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step(i):
+        b = dev_pool[i % len(dev_pool)]
+        for k, v in b.items():
+            trainer.static[k].copy_(v, non_blocking=True)      # D2D rotate: inputs stay HBM-resident, never L2-hot
+        trainer.step_device()
+
+    for i in range(max(args.warmup, 3)):
+        dev_step(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        dev_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    # ---- end to end through the public API (host batch in, host losses out)
+    for i in range(2):
+        trainer.step(pool[i % len(pool)])
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    losses = None
+    for i in range(args.steps):
+        losses = trainer.step(pool[i % len(pool)])
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    if rank == 0:
+        sampler.stop_flag = True
+    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    result = None
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        chips = args.chips * world * args.steps
+        value = chips / (ms / 1e3)
+        e2e = chips / (ms_e2e / 1e3)
+        tc_ms, tc_flops, tc_n = tc_kernel_time(trainer)
+        # kind::tf32 issues at half the bf16 rate (1.1 vs 2.25 PFLOP/s nominal): TF32 peak = measured bf16 / 2
+        peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
+        achieved = tc_flops / (tc_ms / 1e3) / 1e12
+        cpu = None
+        if not args.skip_cpu:
+            cpu = cpu_baseline(sample_chips=args.cpu_chips)
+        result = {
+            "metric": "512x512 chips/sec train (ResNet-101)", "value": round(value, 2), "unit": "chips/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage)",
+            "data": "synthetic",
+            "config": {"workload": "ResNet-101 SNIPER Faster-R-CNN/R-FCN, 512x512 chips, batch 20/GPU, fp32 I/O + TF32 "
+                                   "tcgen05 math, fwd+bwd+allreduce+SGD (BASELINE.json configs[1])",
+                       "global_batch": args.chips * world, "parallelism": "dp%d" % world,
+                       "l2_hygiene": "inputs rotate through %d distinct batches (%.0f MB each); activations >10 GB/step >> 126 MB L2" % (len(pool), h2d / 1e6),
+                       "cuda_graph": not args.no_graph},
+            "e2e": {"value": round(e2e, 2), "unit": "chips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(trainer.launches_per_step * args.steps),
+            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<tf32> (all tcgen05 GEMM/conv/wgrad launches of a step)",
+                         "achieved": round(achieved, 1), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
+                         "frac": round(achieved / peak_tf, 4), "traffic": None,
+                         "launches_per_step": tc_n, "kernel_ms_per_step": round(tc_ms, 3),
+                         "algorithmic_gflop_per_step": round(tc_flops / 1e9, 1),
+                         "peak_source": "%s bf16_tflops_sustained / 2 (TF32 = half the bf16 issue rate)" % peak_src,
+                         "step_frac": round(value / world * TRAIN_GFLOP_PER_CHIP / 1e3 / peak_tf, 4)},
+            "losses": losses,
+            "clocks": sampler.summary(),
+        }
+        if cpu is not None:
+            result["cpu_baseline"] = cpu
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+def cpu_baseline(sample_chips=1):
+    """Reference-style CPU execution of the same training step on the host cores (kind 'port': the MXNet CPU
+    stack cannot be built offline; dense layers run in PyTorch-CPU fp32, SNIPER ops in the C oracle)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_train_step
+    return cpu_train_step.run(sample_chips)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cpu = cpu_baseline(sample_chips=args.cpu_chips)
+    v = cpu["value"]
+    print(json.dumps({
+        "impl": "reference", "metric": "512x512 chips/sec train (ResNet-101)", "value": v, "unit": "chips/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * args.chips / v, 1) if v else None,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "ResNet-101 SNIPER Faster-R-CNN/R-FCN, 512x512 chips, fp32, CPU host cores (bounded sample)"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": v, "unit": "chips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chips", type=int, default=CHIPS_PER_GPU, help="chips per GPU (BASELINE: 20)")
+    ap.add_argument("--pool", type=int, default=7, help="distinct input batches rotated through")
+    ap.add_argument("--cpu-chips", type=int, default=1, help="chips in the bounded CPU-baseline sample")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,34 @@ SIGNATURES = {
 
 _lib = None
 
+# GPU kernels launched per C-ABI call (host-only entry points: 0)
+KERNELS_PER_CALL = {
+    "sniper_last_error": 0, "sniper_abi_version": 0, "sniper_multi_proposal_target_workspace_bytes": 0,
+    "sniper_generate_anchors": 0, "sniper_chips_generate": 0, "sniper_cpu_nms": 0, "sniper_cpu_soft_nms": 0,
+    "sniper_bbox_overlaps": 0, "sniper_multi_proposal_target_fwd": 2, "sniper_bn_stats": 2, "sniper_bn_relu_bwd": 3,
+}
+launches = [0]
+
+
+class _Counting(object):
+    """Thin proxy over the CDLL that counts the GPU kernels our entry points launch (bench.py gpu_launches)."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw = getattr(self._cdll, name)
+            k = KERNELS_PER_CALL.get(name, 1)
+
+            def fn(*a, _raw=raw, _k=k):
+                launches[0] += _k
+                return _raw(*a)
+            self._cache[name] = fn
+        return fn
+
 
 def lib():
     """Returns the loaded C-ABI library; raises (loudly) if it has not been built."""
@@ -65,7 +93,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = ctypes.c_char_p if res == "s" else _T[res]
             fn.argtypes = [_T[c] for c in args]
-        _lib = L
+        _lib = _Counting(L)
     return _lib
 
 

@@ -8,10 +8,20 @@ import ctypes
 import numpy as np
 import torch
 
+from . import _lib as _libmod
 from ._lib import check, lib
 
 TF32, BF16 = 0, 1
 NCHW, NHWC = 0, 1
+
+
+def reset_launch_count():
+    _libmod.launches[0] = 0
+
+
+def launch_count():
+    """GPU kernels launched through the C-ABI since the last reset."""
+    return _libmod.launches[0]
 
 
 def _ptr(t):
