@@ -1,0 +1,63 @@
+"""N>1 host-side logic on CPU with gloo (world_size 2): the single flat-bucket gradient all-reduce that
+replaces the reference's per-key kvstore push/pull, and the reference arm's rank-0-only contract."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from sniper_b200 import model
+    P = model.ParamStore()
+    P.add("a_weight", (5, 3)); P.add("a_bias", (5,)); P.add("offset_weight", (7,), lr_mult=0.01); P.add("b_gamma", (4,))
+    P.finalize("cpu")
+    # every rank owns different chips -> different gradients; the update must see their SUM (rescale_grad=1)
+    for i, (name, g) in enumerate(sorted(P.grads.items())):
+        g.fill_(float(rank + 1) * (i + 1))
+    dist.all_reduce(P.g, op=dist.ReduceOp.SUM)          # ONE collective over the whole bucket
+    exp = {name: float(sum(r + 1 for r in range(world)) * (i + 1)) for i, name in enumerate(sorted(P.grads))}
+    ok = all(bool((P.grad(n) == v).all()) for n, v in exp.items())
+    # optimizer groups: (lr_mult, wd_mult) as MXNet assigns them
+    groups = sorted(g for _, _, g in P.segments)
+    ok = ok and groups == [(0.01, 1.0), (1.0, 0.0), (1.0, 1.0)]
+    ok = ok and P.total % 4 == 0 and all(o % 4 == 0 for o, _ in P.layout.values())
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, 29611, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_reference_arm_prints_once_under_torchrun():
+    """bench.py --impl reference under a 2-rank launch: rank 0 runs the CPU port and prints ONE JSON line."""
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = "4"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29612", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "chips/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
