@@ -44,6 +44,7 @@ SIGNATURES = {
     "sniper_smooth_l1_loss": ("i", "pipplifpipp"),
     "sniper_deform_im2col": ("i", "pp" "iiiiiiiiiii" "pp"),
     "sniper_deform_col2im": ("i", "ppp" "iiiiiiiiiii" "ppp"),
+    "sniper_anchor_target": ("i", "pipipipp" "iiii" "pipi" "dd" "ppppp" "p"),
     "sniper_chips_generate": ("i", "piiiiipi"),
     "sniper_cpu_nms": ("i", "ppidp"),
     "sniper_cpu_soft_nms": ("i", "pifffu"),
@@ -56,7 +57,7 @@ _lib = None
 KERNELS_PER_CALL = {
     "sniper_last_error": 0, "sniper_abi_version": 0, "sniper_multi_proposal_target_workspace_bytes": 0,
     "sniper_generate_anchors": 0, "sniper_chips_generate": 0, "sniper_cpu_nms": 0, "sniper_cpu_soft_nms": 0,
-    "sniper_bbox_overlaps": 0, "sniper_multi_proposal_target_fwd": 2, "sniper_bn_stats": 2, "sniper_bn_relu_bwd": 3,
+    "sniper_bbox_overlaps": 0, "sniper_multi_proposal_target_fwd": 2, "sniper_anchor_target": 2, "sniper_bn_stats": 2, "sniper_bn_relu_bwd": 3,
 }
 launches = [0]
 

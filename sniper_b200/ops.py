@@ -406,3 +406,28 @@ def deform_col2im(dcol, x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroup
     check(lib().sniper_deform_col2im(_ptr(dcol), _ptr(x), _ptr(offset), NB, H, W, C, kh, kw, stride, dil, pad, dgroups,
                                      offset.stride(2), _ptr(dx), _ptr(doffset), _stream()))
     return dx, doffset
+
+
+def anchor_target(gt_valid, ngt, gt_invalid, ninv, im_info, *, H=32, W=32, feat_stride=16,
+                  scales=(2, 4, 7, 10, 13, 16, 24), ratios=(0.5, 1, 2), pos_thresh=0.5, neg_thresh=0.4, disable=None,
+                  want_argmax=False):
+    """RPN anchor matching of anchor_worker.worker (data_workers.py:194-363) for a whole chip batch.
+    gt_valid [B,G,4] / gt_invalid [B,Gi,4] float32 (first ngt[b] / ninv[b] rows used, int32 counts),
+    disable: optional uint8 [B,H*W*A] (the host's npr.choice subsampling).  Returns label [B,A*H*W],
+    bbox_target, bbox_weight [B,4A,H,W] (+ argmax [B,H*W*A])."""
+    B, G = gt_valid.shape[0], gt_valid.shape[1]
+    Gi = gt_invalid.shape[1]
+    A = len(scales) * len(ratios)
+    dev = gt_valid.device
+    label = torch.empty(B, A * H * W, device=dev)
+    bt = torch.empty(B, 4 * A, H, W, device=dev)
+    bw = torch.empty(B, 4 * A, H, W, device=dev)
+    am = torch.empty(B, H * W * A, dtype=torch.int32, device=dev) if want_argmax else None
+    scratch = torch.zeros(B * max(G, 1), dtype=torch.int64, device=dev)
+    s, sp = _farr(scales)
+    r, rp = _farr(ratios)
+    check(lib().sniper_anchor_target(_ptr(gt_valid), _ptr(ngt), G, _ptr(gt_invalid), _ptr(ninv), Gi, _ptr(im_info),
+                                     _ptr(disable), B, H, W, int(feat_stride), sp, len(s), rp, len(r), float(pos_thresh),
+                                     float(neg_thresh), _ptr(scratch), _ptr(label), _ptr(bt), _ptr(bw), _ptr(am),
+                                     _stream()))
+    return (label, bt, bw, am) if want_argmax else (label, bt, bw)

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 import oracle_lib as O
-from sniper_b200 import operator as op, synth
+from sniper_b200 import operator_py as op, synth
 
 
 def test_register_and_custom_roundtrip_cpu():
