@@ -77,20 +77,24 @@ def tc_kernel_time(trainer):
     from sniper_b200 import _lib, ops
     L = _lib.lib()
     names = ["sniper_gemm_nt", "sniper_conv2d_nhwc", "sniper_conv2d_wgrad_nhwc"]
-    events, flops = [], [0.0]
+    events, flops, descs = [], [0.0], []
     orig = {}
 
     def wrap(name, raw):
         def fn(*a):
             if name == "sniper_gemm_nt":
                 M, N, K = a[6], a[7], a[8]
-                flops[0] += 2.0 * M * N * K
+                fl = 2.0 * M * N * K
+                descs.append(["gemm", M, N, K, fl])
             elif name == "sniper_conv2d_nhwc":
                 NB, Cin, Cout, ntaps, Ho, Wo = a[2], a[5], a[7], a[8], a[12], a[13]
-                flops[0] += 2.0 * NB * Ho * Wo * Cout * ntaps * Cin
+                fl = 2.0 * NB * Ho * Wo * Cout * ntaps * Cin
+                descs.append(["conv", NB * Ho * Wo, Cout, ntaps * Cin, fl])
             else:
                 NB, Cin, Cout, ntaps, Ho, Wo = a[4], a[7], a[8], a[9], a[13], a[14]
-                flops[0] += 2.0 * NB * Ho * Wo * Cout * ntaps * Cin
+                fl = 2.0 * NB * Ho * Wo * Cout * ntaps * Cin
+                descs.append(["wgrad", Cout, ntaps * Cin, NB * Ho * Wo, fl])
+            flops[0] += fl
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             r = raw(*a)
@@ -107,7 +111,21 @@ def tc_kernel_time(trainer):
     finally:
         for n in names:
             L._cache[n] = orig[n]
-    ms = sum(a.elapsed_time(b) for a, b in events)
+    times = [a.elapsed_time(b) for a, b in events]
+    ms = sum(times)
+    dump = os.environ.get("SNIPER_DUMP_GEMM")
+    if dump:
+        agg = {}
+        for d, t in zip(descs, times):
+            k = (d[0], d[1], d[2], d[3])
+            e = agg.setdefault(k, [0, 0.0, 0.0])
+            e[0] += 1; e[1] += t; e[2] += d[4]
+        rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+        with open(dump, "w") as f:
+            f.write("| kind | M | N | K | launches | total ms | TFLOP/s |\n|---|---:|---:|---:|---:|---:|---:|\n")
+            for (kind, M, N, K), (n, t, fl) in rows:
+                f.write("| %s | %d | %d | %d | %d | %.3f | %.1f |\n" % (kind, M, N, K, n, t, fl / (t / 1e3) / 1e12))
+            f.write("\ntotal %.3f ms, %.1f GFLOP\n" % (ms, flops[0] / 1e9))
     return ms, flops[0], len(events)
 
 

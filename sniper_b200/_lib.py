@@ -44,7 +44,7 @@ SIGNATURES = {
     "sniper_smooth_l1_loss": ("i", "pipplifpipp"),
     "sniper_deform_im2col": ("i", "pp" "iiiiiiiiiii" "pp"),
     "sniper_deform_col2im": ("i", "ppp" "iiiiiiiiiii" "ppp"),
-    "sniper_anchor_target": ("i", "pipipipp" "iiii" "pipi" "dd" "ppppp" "p"),
+    "sniper_anchor_target": ("i", "ppippipp" "iiii" "pipi" "dd" "ppppp" "p"),
     "sniper_chips_generate": ("i", "piiiiipi"),
     "sniper_cpu_nms": ("i", "ppidp"),
     "sniper_cpu_soft_nms": ("i", "pifffu"),

@@ -254,7 +254,7 @@ class Unit:
         self.stride, self.dim_match, self.frozen, self.deform = stride, dim_match, frozen, deform
         t = not frozen
         self.bn1 = BN(P, name + "_bn1", cin, frozen)
-        self.conv1 = Conv(P, name + "_conv1", cin, mid, 1, trainable=t, need_dgrad=not first_trainable)
+        self.conv1 = Conv(P, name + "_conv1", cin, mid, 1, trainable=t)
         self.bn2 = BN(P, name + "_bn2", mid, frozen)
         if deform:
             self.offset = Conv(P, name + "_offset", mid, 72, 3, 1, 2, 2, bias=True, cout_pad=96)
@@ -263,8 +263,7 @@ class Unit:
             self.conv2 = Conv(P, name + "_conv2", mid, mid, 3, stride, 1, 1, trainable=t)
         self.bn3 = BN(P, name + "_bn3", mid, frozen)
         self.conv3 = Conv(P, name + "_conv3", mid, cout, 1, trainable=t)
-        self.sc = None if dim_match else Conv(P, name + "_sc", cin, cout, 1, stride, trainable=t,
-                                              need_dgrad=not first_trainable)
+        self.sc = None if dim_match else Conv(P, name + "_sc", cin, cout, 1, stride, trainable=t)
         self.first_trainable = first_trainable
         self.saved = None
 
@@ -327,15 +326,14 @@ class Unit:
         self.conv1.bwd_weight(dc1, a1, sp)
         if self.sc is not None:
             self.sc.bwd_weight(dout, a1, sp)
-        if self.first_trainable:
-            # input comes from the frozen stage: nothing to propagate, but bn1's parameters still learn
-            return None
         da1 = self.conv1.bwd_data(dc1, hw_in)
         if self.sc is not None:
             da1 = self.sc.bwd_data(dout, hw_in, out=da1, residual=da1)
+        # (for the first trainable unit dx itself is unused -- its input comes from the frozen stage -- but
+        #  bn1's gamma/beta gradients are produced by the same pass)
         dx = self.bn1.bwd(x, da1, add=dout if self.dim_match else extra_add)
         self.saved = None
-        return dx
+        return None if self.first_trainable else dx
 
 
 # ------------------------------------------------------------------------------------------------

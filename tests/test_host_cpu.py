@@ -20,8 +20,15 @@ def test_abi_header_matches_library_and_bindings():
     for name, args in protos:
         assert hasattr(L, name), "library does not export " + name
         assert name in _lib.SIGNATURES, "no ctypes signature for " + name
-        nargs = 0 if args.strip() == "void" else len(args.split(","))
-        assert nargs == len(_lib.SIGNATURES[name][1]), name
+        plist = [] if args.strip() == "void" else [a.strip() for a in args.split(",")]
+        codes = ""
+        for a in plist:
+            if "*" in a:
+                codes += "p"
+            else:
+                ty = a.rsplit(" ", 1)[0].strip()
+                codes += {"int": "i", "long": "l", "float": "f", "double": "d", "size_t": "z", "unsigned": "u"}[ty]
+        assert codes == _lib.SIGNATURES[name][1], "%s: header %s vs ctypes %s" % (name, codes, _lib.SIGNATURES[name][1])
     for name in _lib.SIGNATURES:
         assert any(n == name for n, _ in protos), name + " missing from the header"
     assert L.sniper_abi_version() == 1
