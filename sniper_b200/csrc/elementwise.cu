@@ -14,6 +14,24 @@ namespace {
 constexpr int kTPB = 256;
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+
+// i -> (row, 4*col) for rows of c4 float4 groups; shift path when c4 is a power of two (all BN widths are),
+// 32-bit division otherwise -- never 64-bit division in the inner loop.
+struct RowSplit {
+  unsigned c4;
+  int shift;   // log2(c4) or -1
+  __device__ __forceinline__ void split(long i, long& r, int& c) const {
+    if (shift >= 0) {
+      r = i >> shift;
+      c = (int)(i & (c4 - 1)) << 2;
+    } else {
+      const unsigned u = (unsigned)i;
+      const unsigned q = u / c4;
+      r = q;
+      c = (int)(u - q * c4) << 2;
+    }
+  }
+};
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
 // ------------------------------------------------------------------ y = relu?(x*scale[c] + shift[c]) (+add)
@@ -23,9 +41,13 @@ __global__ void __launch_bounds__(kTPB) affine_act_kernel(const float* __restric
                                                            long ldy, long M, int C, int relu) {
   const int c4 = C >> 2;
   const long total = M * c4;
+  RowSplit rs;
+  rs.c4 = (unsigned)c4;
+  rs.shift = (c4 & (c4 - 1)) == 0 ? __ffs(c4) - 1 : -1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / c4;
-    const int c = (int)(i - r * c4) << 2;
+    long r;
+    int c;
+    rs.split(i, r, c);
     float4 v = ld4(x + r * ldx + c);
     const float4 s = ld4(scale + c), t = ld4(shift + c);
     v.x = fmaf(v.x, s.x, t.x); v.y = fmaf(v.y, s.y, t.y); v.z = fmaf(v.z, s.z, t.z); v.w = fmaf(v.w, s.w, t.w);
@@ -137,9 +159,13 @@ __global__ void __launch_bounds__(kTPB) bn_relu_bwd_apply_kernel(const float* __
   const int c4 = C >> 2;
   const long total = M * c4;
   const float invM = 1.0f / (float)M;
+  RowSplit rs;
+  rs.c4 = (unsigned)c4;
+  rs.shift = (c4 & (c4 - 1)) == 0 ? __ffs(c4) - 1 : -1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / c4;
-    const int c = (int)(i - r * c4) << 2;
+    long r;
+    int c;
+    rs.split(i, r, c);
     const float4 v = ld4(x + r * ldx + c);
     float4 g = ld4(dy + r * lddy + c);
     const float4 sc = ld4(scale + c), sh = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
@@ -184,9 +210,13 @@ __global__ void __launch_bounds__(kTPB) affine_relu_bwd_kernel(const float* __re
                                                                 int relu) {
   const int c4 = C >> 2;
   const long total = M * c4;
+  RowSplit rs;
+  rs.c4 = (unsigned)c4;
+  rs.shift = (c4 & (c4 - 1)) == 0 ? __ffs(c4) - 1 : -1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / c4;
-    const int c = (int)(i - r * c4) << 2;
+    long r;
+    int c;
+    rs.split(i, r, c);
     const float4 v = ld4(x + r * ldx + c);
     const float4 g = ld4(dy + r * lddy + c);
     const float4 sc = ld4(scale + c), sh = ld4(shift + c);
@@ -209,9 +239,13 @@ __global__ void __launch_bounds__(kTPB) relu_bwd_kernel(const float* __restrict_
                                                          float* __restrict__ dx, long lddx, long M, int C) {
   const int c4 = C >> 2;
   const long total = M * c4;
+  RowSplit rs;
+  rs.c4 = (unsigned)c4;
+  rs.shift = (c4 & (c4 - 1)) == 0 ? __ffs(c4) - 1 : -1;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / c4;
-    const int c = (int)(i - r * c4) << 2;
+    long r;
+    int c;
+    rs.split(i, r, c);
     const float4 v = ld4(y + r * ldy + c);
     float4 g = ld4(dy + r * lddy + c);
     g.x = v.x > 0.f ? g.x : 0.f; g.y = v.y > 0.f ? g.y : 0.f; g.z = v.z > 0.f ? g.z : 0.f; g.w = v.w > 0.f ? g.w : 0.f;

@@ -29,8 +29,9 @@ struct GemmParams {
   int mode, dtype;
   int M, N;               // logical output extent (rows, cols)
   int block_n;            // 64 / 128 / 256
-  int num_kb;             // k-blocks per CTA
+  int num_kb;             // k-blocks per tile
   int stages;
+  int tiles_m, tiles_n, splits;
   // ---- producer geometry
   int elems_per_128B;     // 32 (tf32) / 64 (bf16)
   int cblocks;            // CONV: channel blocks per tap (Cin / elems_per_128B)
@@ -155,6 +156,26 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo1
   return d;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord {
+  int tile_m, tile_n, split;
+};
+
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t) {
+  TileCoord c;
+  c.tile_n = t % p.tiles_n;
+  const int r = t / p.tiles_n;
+  c.tile_m = r % p.tiles_m;
+  c.split = r / p.tiles_m;
+  return c;
+}
+
+// Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring runs across tile
+// boundaries and the accumulator is double-buffered in TMEM (2 x block_n columns), so the epilogue of tile i
+// overlaps the TMA + MMA of tile i+1.
 template <int DT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -166,12 +187,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t stage_bytes = kStageABytes + b_stage_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y, split = blockIdx.z;
-  const uint32_t tmem_cols = p.block_n <= 32 ? 32u : (p.block_n <= 64 ? 64u : (p.block_n <= 128 ? 128u : 256u));
+  const uint32_t acc_cols = p.block_n <= 32 ? 32u : (p.block_n <= 64 ? 64u : (p.block_n <= 128 ? 128u : 256u));
+  const uint32_t tmem_cols = 2u * acc_cols;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -180,7 +203,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+    }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -193,132 +219,196 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0) {
     // =============================== TMA producer
     if (lane == 0) {
-      int n_img = 0, oh0 = 0, ow0 = 0;
-      if (p.mode == MODE_CONV) {
-        n_img = tile_m / p.tiles_per_img;
-        const int r = tile_m - n_img * p.tiles_per_img;
-        const int th = r / p.tiles_w;
-        oh0 = th * p.tile_h;
-        ow0 = (r - th * p.tiles_w) * p.tile_w;
-      }
-      int wg_tap = 0, wg_ci0 = 0;
-      if (p.mode == MODE_WGRAD) {
-        wg_tap = tile_n / p.wg_cin_blocks;
-        wg_ci0 = (tile_n - wg_tap * p.wg_cin_blocks) * p.block_n;
-      }
       const int E = p.elems_per_128B;
-      for (int i = 0; i < p.num_kb; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        uint8_t* sb = sa + kStageABytes;
-        mbar_expect_tx(&full_bar[s], (uint32_t)p.a_boxes * p.a_box_bytes + (uint32_t)p.b_boxes * p.b_box_bytes);
-        const int kb = split * p.num_kb + i;
-        if (p.mode == MODE_GEMM) {
-          tma_load_4d(sa, &tma_a, &full_bar[s], kb * E, tile_m * 128, 0, 0);
-          tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tile_n * p.block_n, 0, 0);
-        } else if (p.mode == MODE_CONV) {
-          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-          tma_load_4d(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
-                      oh0 * p.conv_stride + p.tap_dh[tap], n_img);
-          tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tile_n * p.block_n, 0, 0);
-        } else {
-          // WGRAD: k-block = kp consecutive output pixels of one image row block
-          const int pix0 = kb * p.kp;
-          const int img = pix0 / (p.Ho * p.Wo);
-          const int rem = pix0 - img * (p.Ho * p.Wo);
-          const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
-          for (int j = 0; j < p.a_boxes; ++j)
-            tma_load_4d(sa + (size_t)j * p.a_box_bytes, &tma_a, &full_bar[s], tile_m * 128 + j * E, pix0, 0, 0);
-          for (int j = 0; j < p.b_boxes; ++j)
-            tma_load_4d(sb + (size_t)j * p.b_box_bytes, &tma_b, &full_bar[s], wg_ci0 + j * E,
-                        ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img);
+      uint32_t it = 0;  // global k-block counter across tiles -> ring slot / phase
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const TileCoord tc = tile_coord(p, t);
+        int n_img = 0, oh0 = 0, ow0 = 0;
+        if (p.mode == MODE_CONV) {
+          n_img = tc.tile_m / p.tiles_per_img;
+          const int r = tc.tile_m - n_img * p.tiles_per_img;
+          const int th = r / p.tiles_w;
+          oh0 = th * p.tile_h;
+          ow0 = (r - th * p.tiles_w) * p.tile_w;
+        }
+        int wg_tap = 0, wg_ci0 = 0;
+        if (p.mode == MODE_WGRAD) {
+          wg_tap = tc.tile_n / p.wg_cin_blocks;
+          wg_ci0 = (tc.tile_n - wg_tap * p.wg_cin_blocks) * p.block_n;
+        }
+        for (int i = 0; i < p.num_kb; ++i, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + kStageABytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)p.a_boxes * p.a_box_bytes + (uint32_t)p.b_boxes * p.b_box_bytes);
+          const int kb = tc.split * p.num_kb + i;
+          if (p.mode == MODE_GEMM) {
+            tma_load_4d(sa, &tma_a, &full_bar[s], kb * E, tc.tile_m * 128, 0, 0);
+            tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
+          } else if (p.mode == MODE_CONV) {
+            const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+            tma_load_4d(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
+                        oh0 * p.conv_stride + p.tap_dh[tap], n_img);
+            tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
+          } else {
+            // WGRAD: k-block = kp consecutive output pixels of one image row block
+            const int pix0 = kb * p.kp;
+            const int img = pix0 / (p.Ho * p.Wo);
+            const int rem = pix0 - img * (p.Ho * p.Wo);
+            const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
+            for (int j = 0; j < p.a_boxes; ++j)
+              tma_load_4d(sa + (size_t)j * p.a_box_bytes, &tma_a, &full_bar[s], tc.tile_m * 128 + j * E, pix0, 0, 0);
+            for (int j = 0; j < p.b_boxes; ++j)
+              tma_load_4d(sb + (size_t)j * p.b_box_bytes, &tma_b, &full_bar[s], wg_ci0 + j * E,
+                          ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer
     if (lane == 0) {
-      for (int i = 0; i < p.num_kb; ++i) {
-        const int s = i % p.stages;
-        const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+        const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + kStageABytes;
-        const uint64_t adesc0 = make_smem_desc(sa, p.a_lbo, p.a_sbo, p.layout_type);
-        const uint64_t bdesc0 = make_smem_desc(sb, p.b_lbo, p.b_sbo, p.layout_type);
-        for (int k = 0; k < p.mmas_per_kb; ++k) {
-          umma<DT>(tmem_base, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
-                   (i | k) != 0 ? 1u : 0u);
+        const uint32_t tmem_d = tmem_base + acc * acc_cols;
+        for (int i = 0; i < p.num_kb; ++i, ++it) {
+          const int s = it % p.stages;
+          const uint32_t ph = (it / p.stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + kStageABytes;
+          const uint64_t adesc0 = make_smem_desc(sa, p.a_lbo, p.a_sbo, p.layout_type);
+          const uint64_t bdesc0 = make_smem_desc(sb, p.b_lbo, p.b_sbo, p.layout_type);
+          for (int k = 0; k < p.mmas_per_kb; ++k) {
+            umma<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
+                     (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);
         }
-        umma_commit(&empty_bar[s]);
+        umma_commit(&tmem_full_bar[acc]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else {
     // =============================== epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
     const int m_local = q * 32 + lane;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    long row;
-    bool row_ok;
-    if (p.mode == MODE_CONV) {
-      const int n_img = tile_m / p.tiles_per_img;
-      const int r = tile_m - n_img * p.tiles_per_img;
-      const int th = r / p.tiles_w;
-      const int oh = th * p.tile_h + m_local / p.tile_w;
-      const int ow = (r - th * p.tiles_w) * p.tile_w + m_local % p.tile_w;
-      row = ((long)n_img * p.out_H + (long)oh * p.out_s + p.out_oh) * p.out_W + (long)ow * p.out_s + p.out_ow;
-      row_ok = oh < p.Ho && ow < p.Wo;
-    } else {
-      row = (long)tile_m * 128 + m_local;
-      row_ok = row < p.M;
-    }
-    int col_base = tile_n * p.block_n;
-    if (p.mode == MODE_WGRAD) {
-      const int tap = tile_n / p.wg_cin_blocks;
-      col_base = tap * (p.wg_cin_blocks * p.block_n) + (tile_n - tap * p.wg_cin_blocks) * p.block_n;
-    }
-    for (int c = 0; c < p.block_n; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (!row_ok) continue;
-      const int n0 = col_base + c;
-      if (n0 >= p.N) continue;
-      float* crow = p.C + row * p.ldc + n0;
-      const float* rrow = p.residual ? p.residual + row * p.ldr + n0 : nullptr;
-      const bool full = (n0 + 32 <= p.N);
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (full || n0 + j < p.N) {
-          if (p.scale) x *= __ldg(p.scale + n0 + j);
-          if (p.bias) x += __ldg(p.bias + n0 + j);
-          if (rrow) x += __ldg(rrow + j);
-          if (p.relu) x = fmaxf(x, 0.0f);
-        }
-        f[j] = x;
-      }
-      if (p.out_bf16) {
-        __nv_bfloat16* brow = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || n0 + j < p.N) brow[j] = __float2bfloat16(f[j]);
-      } else if (p.atomic) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || n0 + j < p.N) atomicAdd(crow + j, f[j]);
-      } else if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      const TileCoord tc = tile_coord(p, t);
+      const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
+      long row;
+      bool row_ok;
+      if (p.mode == MODE_CONV) {
+        const int n_img = tc.tile_m / p.tiles_per_img;
+        const int r = tc.tile_m - n_img * p.tiles_per_img;
+        const int th = r / p.tiles_w;
+        const int oh = th * p.tile_h + m_local / p.tile_w;
+        const int ow = (r - th * p.tiles_w) * p.tile_w + m_local % p.tile_w;
+        row = ((long)n_img * p.out_H + (long)oh * p.out_s + p.out_oh) * p.out_W + (long)ow * p.out_s + p.out_ow;
+        row_ok = oh < p.Ho && ow < p.Wo;
       } else {
+        row = (long)tc.tile_m * 128 + m_local;
+        row_ok = row < p.M;
+      }
+      int col_base = tc.tile_n * p.block_n;
+      if (p.mode == MODE_WGRAD) {
+        const int tap = tc.tile_n / p.wg_cin_blocks;
+        col_base = tap * (p.wg_cin_blocks * p.block_n) + (tc.tile_n - tap * p.wg_cin_blocks) * p.block_n;
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * acc_cols + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_acc + (uint32_t)c, v);
+        if (c + 32 >= p.block_n) {
+          // last chunk is in registers: hand the accumulator back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (!row_ok) continue;
+        const int n0 = col_base + c;
+        if (n0 >= p.N) continue;
+        float* crow = p.C + row * p.ldc + n0;
+        const float* rrow = p.residual ? p.residual + row * p.ldr + n0 : nullptr;
+        const bool full = (n0 + 32 <= p.N);
+        float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || n0 + j < p.N) crow[j] = f[j];
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (full) {
+          if (p.scale) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n0 + j));
+              f[j] *= s4.x; f[j + 1] *= s4.y; f[j + 2] *= s4.z; f[j + 3] *= s4.w;
+            }
+          }
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + j));
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (rrow) {
+            if ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + j));
+                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += __ldg(rrow + j);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n0 + j < p.N) {
+              float x = f[j];
+              if (p.scale) x *= __ldg(p.scale + n0 + j);
+              if (p.bias) x += __ldg(p.bias + n0 + j);
+              if (rrow) x += __ldg(rrow + j);
+              if (p.relu) x = fmaxf(x, 0.0f);
+              f[j] = x;
+            }
+          }
+        }
+        if (p.out_bf16) {
+          __nv_bfloat16* brow = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < p.N) brow[j] = __float2bfloat16(f[j]);
+        } else if (p.atomic) {
+          if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(crow + j), make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || n0 + j < p.N) atomicAdd(crow + j, f[j]);
+          }
+        } else if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < p.N) crow[j] = f[j];
+        }
       }
     }
   }
@@ -383,16 +473,20 @@ uint32_t make_idesc(int dtype, int a_mn_major, int b_mn_major, int M, int N) {
 }
 
 int pick_stages(int block_n) {
-  // <=128 columns: ~100 KB per CTA so that two CTAs share an SM (one's epilogue overlaps the
-  // other's main loop); 256 columns: one CTA per SM with a deeper ring.
-  return block_n <= 64 ? 4 : (block_n <= 128 ? 3 : 4);
+  // one persistent CTA per SM: fill shared memory with the operand ring
+  const int stage = kStageABytes + block_n * 128;
+  int s = (210 * 1024) / stage;
+  return s > 8 ? 8 : s;
 }
 
 size_t smem_bytes(int stages, int block_n) {
   return (size_t)stages * (kStageABytes + block_n * 128) + 1024 + 256;
 }
 
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 grid, cudaStream_t stream) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 tiles, cudaStream_t stream) {
+  p.tiles_m = (int)tiles.x; p.tiles_n = (int)tiles.y; p.splits = (int)tiles.z;
+  const long total = (long)tiles.x * tiles.y * tiles.z;
+  dim3 grid((unsigned)(total < sn::kNumSMs ? total : sn::kNumSMs), 1, 1);
   const size_t smem = smem_bytes(p.stages, p.block_n);
   static bool attr_done[2] = {false, false};
   if (!attr_done[p.dtype]) {

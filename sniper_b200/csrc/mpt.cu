@@ -232,24 +232,47 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_assign_kernel(NmsArgs 
     const float oldj_score = s_score[j];
     const uint16_t oldj_id = s_id[j];
     // ---- suppression over positions > j (cu:218-240)
-    for (int pos = j + 1 + t; pos < AHW; pos += kNmsThreads) {
-      float s;
-      int id;
-      if (pos == m) {
-        s = oldj_score;
-        id = oldj_id;
-        s_id[pos] = oldj_id;
-      } else {
-        s = s_score[pos];
-        id = s_id[pos];
+    // four positions per thread per trip: the (L2-resident) box loads of a trip are independent and in flight
+    // together, which is what bounds this latency-limited loop
+    for (int base = j + 1 + t; base < AHW; base += 4 * kNmsThreads) {
+      float s[4];
+      int id[4];
+      float4 d[4];
+      float da[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pos = base + u * kNmsThreads;
+        s[u] = -1.0f;
+        id[u] = 0;
+        if (pos < AHW) {
+          if (pos == m) {
+            s[u] = oldj_score;
+            id[u] = oldj_id;
+            s_id[pos] = oldj_id;
+          } else {
+            s[u] = s_score[pos];
+            id[u] = s_id[pos];
+          }
+        }
       }
-      if (s != -1.0f) {
-        const float4 d = __ldg(boxes + id);
-        const float da = __ldg(areas + id);
-        const float ovr = iou_ref(sb.x, sb.y, sb.z, sb.w, sarea, d, da);
-        if (ovr > p.nms_thresh) s = -1.0f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s[u] != -1.0f) {
+          d[u] = __ldg(boxes + id[u]);
+          da[u] = __ldg(areas + id[u]);
+        }
       }
-      if (pos == m || s == -1.0f) s_score[pos] = s;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int pos = base + u * kNmsThreads;
+        if (pos >= AHW) continue;
+        float sv = s[u];
+        if (sv != -1.0f) {
+          const float ovr = iou_ref(sb.x, sb.y, sb.z, sb.w, sarea, d[u], da[u]);
+          if (ovr > p.nms_thresh) sv = -1.0f;
+        }
+        if (pos == m || sv == -1.0f) s_score[pos] = sv;
+      }
     }
     __syncthreads();
   }

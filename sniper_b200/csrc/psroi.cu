@@ -223,6 +223,162 @@ __global__ void __launch_bounds__(256) deform_psroi_bwd_kernel(PsArgs p, long co
   }
 }
 
+// ---------------------------------------------------------------- NHWC fast path (group_size 1, one class)
+// One warp = one bin (n, ph, pw): the bin / sample geometry is evaluated once per warp instead of once per
+// channel, every bilinear corner is a coalesced float4 gather over 128 channels, and the pooled values keep
+// the oracle's per-channel operation order (so they stay bit-identical to the generic kernel).
+template <int CC>  // CC = channels / 128
+__global__ void __launch_bounds__(256) deform_psroi_fwd_nhwc_kernel(PsArgs p, long nbins) {
+  const int lane = threadIdx.x & 31;
+  const int S = p.sample_per_part;
+  for (long bin = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; bin < nbins;
+       bin += ((long)gridDim.x * blockDim.x) >> 5) {
+    const int pw = (int)(bin % p.pooled);
+    const int ph = (int)((bin / p.pooled) % p.pooled);
+    const int n = (int)(bin / ((long)p.pooled * p.pooled));
+    Geom g;
+    deform_geom(p, n, 0, ph, pw, g);
+    float4 sum[CC];
+#pragma unroll
+    for (int k = 0; k < CC; ++k) sum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    const float* img = p.data + (size_t)g.roi_batch_ind * p.height * p.width * p.channels + lane * 4;
+    for (int ih = 0; ih < S; ++ih) {
+      for (int iw = 0; iw < S; ++iw) {
+        float w, h;
+        if (!sample_pos(p, g, ih, iw, w, h)) continue;
+        const int x1 = (int)floorf(w), x2 = (int)ceilf(w), y1 = (int)floorf(h), y2 = (int)ceilf(h);
+        const float dist_x = __fsub_rn(w, (float)x1), dist_y = __fsub_rn(h, (float)y1);
+        const float omx = __fsub_rn(1.0f, dist_x), omy = __fsub_rn(1.0f, dist_y);
+        const float w11 = __fmul_rn(omx, omy), w12 = __fmul_rn(omx, dist_y), w21 = __fmul_rn(dist_x, omy),
+                    w22 = __fmul_rn(dist_x, dist_y);
+        const float* p11 = img + ((size_t)y1 * p.width + x1) * p.channels;
+        const float* p12 = img + ((size_t)y2 * p.width + x1) * p.channels;
+        const float* p21 = img + ((size_t)y1 * p.width + x2) * p.channels;
+        const float* p22 = img + ((size_t)y2 * p.width + x2) * p.channels;
+#pragma unroll
+        for (int k = 0; k < CC; ++k) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p11 + k * 128));
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p12 + k * 128));
+          const float4 c = __ldg(reinterpret_cast<const float4*>(p21 + k * 128));
+          const float4 d = __ldg(reinterpret_cast<const float4*>(p22 + k * 128));
+          float4 v;
+          v.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w11, a.x), __fmul_rn(w12, b.x)), __fmul_rn(w21, c.x)), __fmul_rn(w22, d.x));
+          v.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w11, a.y), __fmul_rn(w12, b.y)), __fmul_rn(w21, c.y)), __fmul_rn(w22, d.y));
+          v.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w11, a.z), __fmul_rn(w12, b.z)), __fmul_rn(w21, c.z)), __fmul_rn(w22, d.z));
+          v.w = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w11, a.w), __fmul_rn(w12, b.w)), __fmul_rn(w21, c.w)), __fmul_rn(w22, d.w));
+          sum[k].x = __fadd_rn(sum[k].x, v.x); sum[k].y = __fadd_rn(sum[k].y, v.y);
+          sum[k].z = __fadd_rn(sum[k].z, v.z); sum[k].w = __fadd_rn(sum[k].w, v.w);
+        }
+        cnt++;
+      }
+    }
+    const float fc = (float)cnt;
+    float* o = p.top_data + bin * p.channels + lane * 4;
+#pragma unroll
+    for (int k = 0; k < CC; ++k) {
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cnt) {
+        r.x = __fdiv_rn(sum[k].x, fc); r.y = __fdiv_rn(sum[k].y, fc);
+        r.z = __fdiv_rn(sum[k].z, fc); r.w = __fdiv_rn(sum[k].w, fc);
+      }
+      *reinterpret_cast<float4*>(o + k * 128) = r;
+      if (p.top_count) *reinterpret_cast<float4*>(p.top_count + bin * p.channels + lane * 4 + k * 128) = make_float4(fc, fc, fc, fc);
+    }
+  }
+}
+
+template <int CC>
+__global__ void __launch_bounds__(256) deform_psroi_bwd_nhwc_kernel(PsArgs p, long nbins) {
+  const int lane = threadIdx.x & 31;
+  const int S = p.sample_per_part;
+  for (long bin = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; bin < nbins;
+       bin += ((long)gridDim.x * blockDim.x) >> 5) {
+    const int pw = (int)(bin % p.pooled);
+    const int ph = (int)((bin / p.pooled) % p.pooled);
+    const int n = (int)(bin / ((long)p.pooled * p.pooled));
+    Geom g;
+    deform_geom(p, n, 0, ph, pw, g);
+    int cnt = 0;
+    for (int ih = 0; ih < S; ++ih)
+      for (int iw = 0; iw < S; ++iw) {
+        float w, h;
+        cnt += sample_pos(p, g, ih, iw, w, h) ? 1 : 0;
+      }
+    if (cnt == 0) continue;
+    const float fc = (float)cnt;
+    float4 dv[CC];
+    const float* td = p.top_diff + bin * p.channels + lane * 4;
+#pragma unroll
+    for (int k = 0; k < CC; ++k) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(td + k * 128));
+      dv[k] = make_float4(__fdiv_rn(t.x, fc), __fdiv_rn(t.y, fc), __fdiv_rn(t.z, fc), __fdiv_rn(t.w, fc));
+    }
+    const size_t ibase = (size_t)g.roi_batch_ind * p.height * p.width * p.channels + lane * 4;
+    float tdx = 0.f, tdy = 0.f;
+    for (int ih = 0; ih < S; ++ih) {
+      for (int iw = 0; iw < S; ++iw) {
+        float w, h;
+        if (!sample_pos(p, g, ih, iw, w, h)) continue;
+        const int x0 = (int)floorf(w), x1 = (int)ceilf(w), y0 = (int)floorf(h), y1 = (int)ceilf(h);
+        const float dist_x = w - x0, dist_y = h - y0;
+        const float q00 = (1 - dist_x) * (1 - dist_y), q01 = (1 - dist_x) * dist_y;
+        const float q10 = dist_x * (1 - dist_y), q11 = dist_x * dist_y;
+        const size_t o00 = ibase + ((size_t)y0 * p.width + x0) * p.channels, o01 = ibase + ((size_t)y1 * p.width + x0) * p.channels;
+        const size_t o10 = ibase + ((size_t)y0 * p.width + x1) * p.channels, o11 = ibase + ((size_t)y1 * p.width + x1) * p.channels;
+#pragma unroll
+        for (int k = 0; k < CC; ++k) {
+          const float4 d = dv[k];
+          atomicAdd(reinterpret_cast<float4*>(p.data_diff + o00 + k * 128), make_float4(q00 * d.x, q00 * d.y, q00 * d.z, q00 * d.w));
+          atomicAdd(reinterpret_cast<float4*>(p.data_diff + o01 + k * 128), make_float4(q01 * d.x, q01 * d.y, q01 * d.z, q01 * d.w));
+          atomicAdd(reinterpret_cast<float4*>(p.data_diff + o10 + k * 128), make_float4(q10 * d.x, q10 * d.y, q10 * d.z, q10 * d.w));
+          atomicAdd(reinterpret_cast<float4*>(p.data_diff + o11 + k * 128), make_float4(q11 * d.x, q11 * d.y, q11 * d.z, q11 * d.w));
+          if (!p.no_trans) {
+            const float4 U00 = __ldg(reinterpret_cast<const float4*>(p.data + o00 + k * 128));
+            const float4 U01 = __ldg(reinterpret_cast<const float4*>(p.data + o01 + k * 128));
+            const float4 U10 = __ldg(reinterpret_cast<const float4*>(p.data + o10 + k * 128));
+            const float4 U11 = __ldg(reinterpret_cast<const float4*>(p.data + o11 + k * 128));
+            const float ax = (U11.x * dist_y + U10.x * (1 - dist_y) - U01.x * dist_y - U00.x * (1 - dist_y)) * d.x +
+                             (U11.y * dist_y + U10.y * (1 - dist_y) - U01.y * dist_y - U00.y * (1 - dist_y)) * d.y +
+                             (U11.z * dist_y + U10.z * (1 - dist_y) - U01.z * dist_y - U00.z * (1 - dist_y)) * d.z +
+                             (U11.w * dist_y + U10.w * (1 - dist_y) - U01.w * dist_y - U00.w * (1 - dist_y)) * d.w;
+            const float ay = (U11.x * dist_x + U01.x * (1 - dist_x) - U10.x * dist_x - U00.x * (1 - dist_x)) * d.x +
+                             (U11.y * dist_x + U01.y * (1 - dist_x) - U10.y * dist_x - U00.y * (1 - dist_x)) * d.y +
+                             (U11.z * dist_x + U01.z * (1 - dist_x) - U10.z * dist_x - U00.z * (1 - dist_x)) * d.z +
+                             (U11.w * dist_x + U01.w * (1 - dist_x) - U10.w * dist_x - U00.w * (1 - dist_x)) * d.w;
+            tdx += ax * p.trans_std * g.roi_width;
+            tdy += ay * p.trans_std * g.roi_height;
+          }
+        }
+      }
+    }
+    if (!p.no_trans) {
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        tdx += __shfl_xor_sync(0xffffffffu, tdx, off);
+        tdy += __shfl_xor_sync(0xffffffffu, tdy, off);
+      }
+      if (lane == 0) {
+        const size_t tb = (((size_t)n * 2) * p.part_size + g.part_h) * p.part_size + g.part_w;
+        atomicAdd(p.trans_diff + tb, tdx);
+        atomicAdd(p.trans_diff + tb + (size_t)p.part_size * p.part_size, tdy);
+      }
+    }
+  }
+}
+
+bool fast_nhwc_ok(const PsArgs& a) {
+  return a.layout == 1 && a.group_size == 1 && a.num_classes == 1 && a.sample_idx == nullptr &&
+         (a.channels == 128 || a.channels == 256 || a.channels == 512) &&
+         ((uintptr_t)a.data & 15) == 0;
+}
+
+int fast_grid(long nbins) {
+  long g = (nbins + 7) / 8;
+  const long cap = (long)sn::kNumSMs * 16;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
 __device__ __forceinline__ void psroi_bin(const PsArgs& p, int n, int ph, int pw, int& b, int& hstart, int& hend,
                                           int& wstart, int& wend) {
   const float* r = p.rois + (size_t)n * 5;
@@ -328,6 +484,15 @@ int sniper_deform_psroi_fwd(const float* data, const float* rois, const float* t
   a.top_data = top_data; a.top_count = top_count; a.sample_idx = sample_idx;
   const long count = (long)num_rois * output_dim * pooled_size * pooled_size;
   if (count == 0) return 0;
+  if (fast_nhwc_ok(a)) {
+    const long nbins = (long)num_rois * pooled_size * pooled_size;
+    const int g = fast_grid(nbins);
+    if (channels == 128) deform_psroi_fwd_nhwc_kernel<1><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+    else if (channels == 256) deform_psroi_fwd_nhwc_kernel<2><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+    else deform_psroi_fwd_nhwc_kernel<4><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+    SN_LAUNCH_CHECK();
+    return 0;
+  }
   deform_psroi_fwd_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(a, count);
   SN_LAUNCH_CHECK();
   return 0;
@@ -347,6 +512,15 @@ int sniper_deform_psroi_bwd(const float* top_diff, const float* data, const floa
   a.top_diff = top_diff; a.data_diff = data_diff; a.trans_diff = trans_diff;
   const long count = (long)num_rois * output_dim * pooled_size * pooled_size;
   if (count == 0) return 0;
+  if (fast_nhwc_ok(a) && ((uintptr_t)data_diff & 15) == 0 && ((uintptr_t)top_diff & 15) == 0) {
+    const long nbins = (long)num_rois * pooled_size * pooled_size;
+    const int g = fast_grid(nbins);
+    if (channels == 128) deform_psroi_bwd_nhwc_kernel<1><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+    else if (channels == 256) deform_psroi_bwd_nhwc_kernel<2><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+    else deform_psroi_bwd_nhwc_kernel<4><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+    SN_LAUNCH_CHECK();
+    return 0;
+  }
   deform_psroi_bwd_kernel<<<grid_for(count), 256, 0, (cudaStream_t)stream>>>(a, count);
   SN_LAUNCH_CHECK();
   return 0;
