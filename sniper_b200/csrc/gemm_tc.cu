@@ -8,7 +8,7 @@
 // (contrib/deformable_convolution-inl.h:148-160).
 //
 // One CTA = one 128 x BLOCK_N output tile (cta_group::1).  Warp roles: warp 0 = TMA producer,
-// warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (one TMEM lane quarter each).
+// warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue (TMEM lane quarter x column half each).
 //
 //   mode 0  GEMM    C[M,N]  = A[M,K] * B[N,K]^T             A,B K-major
 //   mode 1  CONV    C[pix,N] = sum_taps A[n,h+dh,w+dw,c] * B[N,(tap,c)]   A 4-D NHWC, K-major; TMA zero
@@ -177,7 +177,7 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t) {
 // boundaries and the accumulator is double-buffered in TMEM (2 x block_n columns), so the epilogue of tile i
 // overlaps the TMA + MMA of tile i+1.
 template <int DT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -205,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], 8);   // one arrival per epilogue warp
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -295,9 +295,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5)
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // =============================== epilogue (warps 2..9): TMEM lane quarter q = warp & 3, column half h
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int m_local = q * 32 + lane;
+    const int cols_per_warp = p.block_n >> 1;   // block_n >= 64
     uint32_t lt = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
       const TileCoord tc = tile_coord(p, t);
@@ -321,13 +323,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int tap = tc.tile_n / p.wg_cin_blocks;
         col_base = tap * (p.wg_cin_blocks * p.block_n) + (tc.tile_n - tap * p.wg_cin_blocks) * p.block_n;
       }
+      col_base += half * cols_per_warp;
+      const float* rbase = (p.residual && row_ok) ? p.residual + row * p.ldr + col_base : nullptr;
+      const bool r_vec = rbase && ((reinterpret_cast<uintptr_t>(rbase) & 15) == 0) && (col_base + cols_per_warp <= p.N);
+      // residual of the first chunk is requested before the accumulator is even ready
+      float4 rn[8];
+      if (r_vec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) rn[j] = __ldg(reinterpret_cast<const float4*>(rbase) + j);
+      }
       mbar_wait(&tmem_full_bar[acc], acc_ph);
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + acc * acc_cols + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < p.block_n; c += 32) {
+      const uint32_t tmem_acc = tmem_base + acc * acc_cols + (uint32_t)(half * cols_per_warp) + ((uint32_t)(q * 32) << 16);
+      for (int c = 0; c < cols_per_warp; c += 32) {
         uint32_t v[32];
         tmem_ld32(tmem_acc + (uint32_t)c, v);
-        if (c + 32 >= p.block_n) {
+        float4 rc[8];
+        if (r_vec) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) rc[j] = rn[j];
+          if (c + 32 < cols_per_warp) {   // prefetch the next chunk's residual while this one is processed
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rn[j] = __ldg(reinterpret_cast<const float4*>(rbase + c + 32) + j);
+          }
+        }
+        if (c + 32 >= cols_per_warp) {
           // last chunk is in registers: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -337,7 +357,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int n0 = col_base + c;
         if (n0 >= p.N) continue;
         float* crow = p.C + row * p.ldc + n0;
-        const float* rrow = p.residual ? p.residual + row * p.ldr + n0 : nullptr;
         const bool full = (n0 + 32 <= p.N);
         float f[32];
 #pragma unroll
@@ -357,17 +376,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
             }
           }
-          if (rrow) {
-            if ((reinterpret_cast<uintptr_t>(rrow) & 15) == 0) {
+          if (r_vec) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rrow + j));
-                f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += __ldg(rrow + j);
+            for (int j = 0; j < 8; ++j) {
+              f[4 * j] += rc[j].x; f[4 * j + 1] += rc[j].y; f[4 * j + 2] += rc[j].z; f[4 * j + 3] += rc[j].w;
             }
+          } else if (rbase) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __ldg(rbase + c + j);
           }
           if (p.relu) {
 #pragma unroll
@@ -380,7 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               float x = f[j];
               if (p.scale) x *= __ldg(p.scale + n0 + j);
               if (p.bias) x += __ldg(p.bias + n0 + j);
-              if (rrow) x += __ldg(rrow + j);
+              if (rbase) x += __ldg(rbase + c + j);
               if (p.relu) x = fmaxf(x, 0.0f);
               f[j] = x;
             }
@@ -497,9 +513,9 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
     attr_done[p.dtype] = true;
   }
   if (p.dtype == DT_TF32)
-    gemm_tc_kernel<DT_TF32><<<grid, 192, smem, stream>>>(ma, mb, p);
+    gemm_tc_kernel<DT_TF32><<<grid, 320, smem, stream>>>(ma, mb, p);
   else
-    gemm_tc_kernel<DT_BF16><<<grid, 192, smem, stream>>>(ma, mb, p);
+    gemm_tc_kernel<DT_BF16><<<grid, 320, smem, stream>>>(ma, mb, p);
   SN_LAUNCH_CHECK();
   return 0;
 }
@@ -650,7 +666,9 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, long dy_ld, const void* X, long x_l
   SN_CHECK(single_row || ((Wo % kp == 0 || kp % Wo == 0) && pixels % kp == 0 && (Wo >= kp || (Ho * Wo) % kp == 0)),
            "wgrad: output %dx%d does not tile by %d pixels", Ho, Wo, kp);
   const int bw = Wo >= kp ? kp : Wo, bh = kp / bw;
-  const int bn = Cin % 128 == 0 ? 128 : 64;
+  // wide N tiles: fp32 operands make the 128x128 tile L2-bandwidth bound (128 B/clk/SM of operand traffic);
+  // 128x256 needs 96 B/clk and halves the number of split-K atomics
+  const int bn = Cin % 256 == 0 ? 256 : (Cin % 128 == 0 ? 128 : 64);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.mode = MODE_WGRAD; p.dtype = dtype; p.block_n = bn; p.elems_per_128B = E;
@@ -674,7 +692,13 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, long dy_ld, const void* X, long x_l
   for (int t = 0; t < ntaps; ++t) { p.tap_dh[t] = tap_dh[t]; p.tap_dw[t] = tap_dw[t]; }
   p.conv_stride = stride; p.Ho = Ho; p.Wo = Wo; p.kp = kp; p.wg_cin_blocks = Cin / bn;
   const long total_kb = (pixels + kp - 1) / kp;
-  if (splits < 1) splits = 1;
+  if (splits < 1) {
+    // auto: fill one wave of 148 persistent CTAs (two if the tiles are tiny), at least 8 k-blocks per split
+    const long base_tiles = (long)(Cout / 128 + (Cout % 128 ? 1 : 0)) * ntaps * p.wg_cin_blocks;
+    long s = base_tiles >= sn::kNumSMs ? 1 : (sn::kNumSMs + base_tiles / 2) / base_tiles;
+    if (s > total_kb / 8) s = total_kb / 8;
+    splits = s < 1 ? 1 : (int)s;
+  }
   while (splits > 1 && total_kb % splits != 0) --splits;
   p.num_kb = (int)(total_kb / splits);
   p.C = dW; p.ldc = (long)ntaps * Cin; p.atomic = 1;

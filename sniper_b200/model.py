@@ -39,7 +39,7 @@ class Cfg:
     units = (3, 4, 23, 3)
     filter_list = (64, 256, 512, 1024, 2048)
     grad_scale = 1.0                  # TRAIN.scale only applies to fp16
-    wgrad_splits = 8
+    wgrad_splits = 0                  # 0 = choose per layer (fill one wave of 148 persistent CTAs)
 
 
 # ------------------------------------------------------------------------------------------------
