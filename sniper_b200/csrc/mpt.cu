@@ -11,6 +11,7 @@
 // (SoA instead of the reference's 6-float AoS rows: 16-byte box loads, coalesced score scans).
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -170,9 +171,203 @@ struct NmsArgs {
   int32_t* keep_idx;   // optional [B*R]
   int32_t* num_kept;   // optional [B]
   int do_assign;       // 0: proposals only (MultiProposal-style output), 1: full target assignment
+  const int32_t* fast_keep;      // optional results of mpt_nms_fast_kernel: [B,1024], [B], [B]
+  const int32_t* fast_nkept;
+  const int32_t* fast_fallback;
 };
 
 constexpr int kNmsThreads = 1024;
+
+// ------------------------------------------------------------------------------------------------
+// Fast path of the greedy NMS: top-score selection (uniform score histogram), exact sort, then 64-wide
+// blocks resolved with IoU bit masks (ballot/shuffle reductions).  It produces exactly the keep list of the
+// sequential reference algorithm whenever no two selected candidates have equal scores; on an exact score
+// tie (where the reference's keep order depends on its strided scan), when the selection does not fit or
+// is exhausted before R boxes are kept, it raises `fallback` and mpt_nms_assign_kernel runs the faithful
+// round-by-round emulation instead.
+constexpr int kFastCap = 4096;          // candidates sorted per chip
+constexpr int kFastBins = 4096;
+
+struct FastArgs {
+  const float4* boxes;
+  const float* scores;
+  const float* areas;
+  int AHW, R;
+  float nms_thresh;
+  int32_t* keep_ids;   // [B,1024]
+  int32_t* nkept;      // [B]
+  int32_t* fallback;   // [B]
+};
+
+__global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_fast_kernel(FastArgs p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);              // [kFastCap]
+  float4* s_box = reinterpret_cast<float4*>(s_key + kFastCap);                              // [kFastCap]
+  float* s_area = reinterpret_cast<float*>(s_box + kFastCap);                               // [kFastCap]
+  int* s_hist = reinterpret_cast<int*>(s_area + kFastCap);                                  // [kFastBins]
+  float4* s_kbox = reinterpret_cast<float4*>(s_hist + kFastBins);                           // [1024]
+  float* s_karea = reinterpret_cast<float*>(s_kbox + 1024);                                 // [1024]
+  unsigned long long* s_mask = reinterpret_cast<unsigned long long*>(s_karea + 1024);       // [64]
+  int* s_alive = reinterpret_cast<int*>(s_mask + 64);                                       // [64]
+  __shared__ int s_qstar, s_nsel, s_nvalid, s_tie, s_nk, s_wsum[32];
+  const int chip = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int AHW = p.AHW;
+  const float* sc = p.scores + (size_t)chip * AHW;
+  const float4* boxes = p.boxes + (size_t)chip * AHW;
+  const float* areas = p.areas + (size_t)chip * AHW;
+  for (int i = t; i < kFastBins; i += kNmsThreads) s_hist[i] = 0;
+  if (t == 0) { s_nsel = 0; s_nvalid = 0; s_tie = 0; s_nk = 0; s_qstar = 0; }
+  __syncthreads();
+  // ---- 1. histogram of quantised scores (monotone in the score, so "q >= q*" is a top set)
+  int nv = 0;
+  for (int i = t; i < AHW; i += kNmsThreads) {
+    const float s = sc[i];
+    if (s != -1.0f) {
+      int q = (int)(fminf(fmaxf(s, 0.0f), 1.0f) * (float)(kFastBins - 1));
+      atomicAdd(&s_hist[q], 1);
+      ++nv;
+    }
+  }
+  nv = __reduce_add_sync(0xffffffffu, nv);
+  if (lane == 0 && nv) atomicAdd(&s_nvalid, nv);
+  __syncthreads();
+  // ---- 2. largest top set of bins with at most kFastCap members: scan the bins from the top score down;
+  //         the cumulative count is monotone, so the admissible bins form a prefix of that order
+  {
+    int h[4];
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { h[u] = s_hist[kFastBins - 1 - (4 * t + u)]; mine += h[u]; }
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (lane == 31) s_wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_wsum[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += v;
+      }
+      s_wsum[lane] = w;
+    }
+    __syncthreads();
+    int c = incl - mine + (warp ? s_wsum[warp - 1] : 0);
+    int ok = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { c += h[u]; ok += (c <= kFastCap); }
+    ok = __reduce_add_sync(0xffffffffu, ok);
+    if (lane == 0 && ok) atomicAdd(&s_qstar, ok);   // s_qstar = D = number of admissible bins
+  }
+  __syncthreads();
+  const int qstar = kFastBins - s_qstar;   // select scores with bin >= q*
+  // ---- 3. gather the selected candidates as 64-bit keys (score descending, then index)
+  for (int i = t; i < kFastCap; i += kNmsThreads) s_key[i] = ~0ull;
+  __syncthreads();
+  for (int i = t; i < AHW; i += kNmsThreads) {
+    const float s = sc[i];
+    if (s != -1.0f) {
+      const int q = (int)(fminf(fmaxf(s, 0.0f), 1.0f) * (float)(kFastBins - 1));
+      if (q >= qstar) {
+        const int slot = atomicAdd(&s_nsel, 1);
+        if (slot < kFastCap) s_key[slot] = ((unsigned long long)ord_desc(s) << 32) | (unsigned)i;
+      }
+    }
+  }
+  __syncthreads();
+  const int nsel = s_nsel;
+  bool bad = nsel > kFastCap;
+  // ---- 4. bitonic sort of kFastCap keys (padding = ~0 sorts last)
+  if (!bad) {
+    for (int k = 2; k <= kFastCap; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = t; i < kFastCap; i += kNmsThreads) {
+          const int l = i ^ j;
+          if (l > i) {
+            const unsigned long long a = s_key[i], b = s_key[l];
+            const bool up = ((i & k) == 0);
+            if ((a > b) == up) { s_key[i] = b; s_key[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // exact score ties among the selected -> the reference's order is scan-dependent -> fallback
+    int tie = 0;
+    for (int i = t; i + 1 < nsel; i += kNmsThreads) tie |= ((s_key[i] >> 32) == (s_key[i + 1] >> 32));
+    if (__any_sync(0xffffffffu, tie) && lane == 0) s_tie = 1;
+    for (int i = t; i < nsel; i += kNmsThreads) {
+      const int id = (int)(unsigned)s_key[i];
+      s_box[i] = boxes[id];
+      s_area[i] = areas[id];
+    }
+  }
+  __syncthreads();
+  bad = bad || s_tie;
+  // ---- 5. greedy NMS over the sorted list, 64 candidates per trip
+  const int grp = t >> 4, sub = t & 15;   // 64 groups of 16 threads: one candidate each
+  if (!bad) {
+    for (int base = 0; base < nsel; base += 64) {
+      const int nk = s_nk;
+      if (nk >= p.R) break;
+      const int ci = base + grp;
+      const bool have = ci < nsel;
+      float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+      float ca = 0.f;
+      if (have) { cb = s_box[ci]; ca = s_area[ci]; }
+      // (a) against everything kept so far
+      int dead = 0;
+      if (have)
+        for (int k = sub; k < nk; k += 16) dead |= (iou_ref(s_kbox[k].x, s_kbox[k].y, s_kbox[k].z, s_kbox[k].w, s_karea[k], cb, ca) > p.nms_thresh);
+      const unsigned dm = __ballot_sync(0xffffffffu, dead);
+      const bool alive = have && (((dm >> (lane & 16)) & 0xffffu) == 0);
+      // (b) against the later members of this trip: 4 columns per thread
+      unsigned long long m = 0;
+      if (have) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = sub * 4 + u;
+          if (j > grp && base + j < nsel) {
+            const float4 ob = s_box[base + j];
+            if (iou_ref(cb.x, cb.y, cb.z, cb.w, ca, ob, s_area[base + j]) > p.nms_thresh) m |= 1ull << j;
+          }
+        }
+      }
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, off);
+      if (sub == 0) { s_mask[grp] = m; s_alive[grp] = alive ? 1 : 0; }
+      __syncthreads();
+      // (c) sequential resolve by one thread
+      if (t == 0) {
+        unsigned long long removed = 0;
+        int k = nk;
+        for (int i = 0; i < 64 && k < p.R; ++i) {
+          if (s_alive[i] && !((removed >> i) & 1ull)) {
+            s_kbox[k] = s_box[base + i];
+            s_karea[k] = s_area[base + i];
+            p.keep_ids[(size_t)chip * 1024 + k] = (int)(unsigned)s_key[base + i];
+            ++k;
+            removed |= s_mask[i];
+          }
+        }
+        s_nk = k;
+      }
+      __syncthreads();
+    }
+  }
+  if (t == 0) {
+    const int nk = s_nk;
+    // not enough: there are valid candidates outside the selection that the reference would still visit
+    const bool exhausted = !bad && nk < p.R && nsel < s_nvalid;
+    p.nkept[chip] = nk;
+    p.fallback[chip] = (bad || exhausted) ? 1 : 0;
+  }
+}
+
 
 // One CTA per chip.  Positions 0..AHW-1 hold (score, id) in shared memory; the reference's row swap
 // (cu:178-199) becomes a 6-byte swap here, the 16-byte boxes never move.  Tie order of the
@@ -190,15 +385,21 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_assign_kernel(NmsArgs 
   const int AHW = p.AHW;
   const float4* boxes = p.boxes + (size_t)chip * AHW;
   const float* areas = p.areas + (size_t)chip * AHW;
-  for (int i = t; i < AHW; i += kNmsThreads) {
-    s_score[i] = p.scores[(size_t)chip * AHW + i];
-    s_id[i] = (uint16_t)i;
+  const bool use_fast = p.fast_fallback != nullptr && p.fast_fallback[chip] == 0;
+  int vct = 0;
+  if (use_fast) {
+    vct = p.fast_nkept[chip];
+    for (int i = t; i < vct; i += kNmsThreads) s_keep[i] = p.fast_keep[(size_t)chip * 1024 + i];
+  } else {
+    for (int i = t; i < AHW; i += kNmsThreads) {
+      s_score[i] = p.scores[(size_t)chip * AHW + i];
+      s_id[i] = (uint16_t)i;
+    }
   }
   if (t == 0) s_numgt = 0;
   __syncthreads();
 
-  int vct = 0;
-  for (int j = 0; j < AHW && vct < p.R; ++j) {
+  for (int j = 0; !use_fast && j < AHW && vct < p.R; ++j) {
     // ---- argmax over positions >= j (cu:139-176)
     float best = -2.0f;
     uint32_t besti = 0, bestid = 0;
@@ -390,10 +591,16 @@ int make_anchors(int feat_stride, const float* scales, int ns, const float* rati
 
 size_t ws_bytes_impl(int B, int A, int H, int W) {
   const size_t total = (size_t)B * A * H * W;
-  return total * (sizeof(float4) + 2 * sizeof(float)) + 256;
+  return total * (sizeof(float4) + 2 * sizeof(float)) + 256 + (size_t)B * (1024 + 2) * sizeof(int32_t) + 64;
 }
 
 }  // namespace
+
+// SNIPER_NMS_FAST=0 forces the sequential emulation (used by the parity tests to exercise both paths)
+bool nms_fast_enabled() {
+  const char* e = getenv("SNIPER_NMS_FAST");
+  return !(e && e[0] == '0');
+}
 
 extern "C" {
 
@@ -436,7 +643,8 @@ int sniper_proposal_decode(const float* cls_prob, const float* bbox_pred, const 
 static int nms_assign_launch(const float* boxes, const float* score, const float* area, const float* gt_boxes,
                              const float* valid_ranges, int B, int AHW, int max_gt, int R, float nms_thresh,
                              float* rois, float* label, float* bbox_target, float* bbox_weight,
-                             int32_t* keep_idx, int32_t* num_kept, int do_assign, void* stream) {
+                             int32_t* keep_idx, int32_t* num_kept, int do_assign, int32_t* fast_scratch,
+                             void* stream) {
   SN_CHECK(AHW >= R, "nms: anchors per chip (%d) < post_nms_top_n (%d)", AHW, R);
   SN_CHECK(AHW <= 32768, "nms: anchors per chip (%d) > 32768", AHW);
   SN_CHECK(R <= 1024, "nms: post_nms_top_n (%d) > 1024", R);
@@ -448,9 +656,20 @@ static int nms_assign_launch(const float* boxes, const float* score, const float
   n.bbox_weight = bbox_weight; n.keep_idx = keep_idx; n.num_kept = num_kept; n.do_assign = do_assign;
   const size_t smem = (size_t)AHW * 6 + 16;
   static bool attr_set = false;
+  const size_t fast_smem = (size_t)kFastCap * (8 + 16 + 4) + kFastBins * 4 + 1024 * 20 + 64 * 8 + 64 * 4 + 64;
   if (!attr_set) {
     SN_CUDA(cudaFuncSetAttribute(mpt_nms_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    SN_CUDA(cudaFuncSetAttribute(mpt_nms_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
+  }
+  n.fast_keep = nullptr; n.fast_nkept = nullptr; n.fast_fallback = nullptr;
+  if (fast_scratch) {
+    FastArgs f;
+    f.boxes = n.boxes; f.scores = score; f.areas = area; f.AHW = AHW; f.R = R; f.nms_thresh = nms_thresh;
+    f.keep_ids = fast_scratch; f.nkept = fast_scratch + (size_t)B * 1024; f.fallback = f.nkept + B;
+    mpt_nms_fast_kernel<<<B, kNmsThreads, fast_smem, (cudaStream_t)stream>>>(f);
+    SN_LAUNCH_CHECK();
+    n.fast_keep = f.keep_ids; n.fast_nkept = f.nkept; n.fast_fallback = f.fallback;
   }
   mpt_nms_assign_kernel<<<B, kNmsThreads, smem, (cudaStream_t)stream>>>(n);
   SN_LAUNCH_CHECK();
@@ -478,8 +697,10 @@ int sniper_multi_proposal_target_fwd(const float* cls_prob, const float* bbox_pr
   if (sniper_proposal_decode(cls_prob, bbox_pred, im_info, valid_ranges, B, A, H, W, feat_stride, scales, ns, ratios,
                              nr, layout, score_cstride, delta_cstride, boxes, score, area, stream))
     return -1;
+  int32_t* fast_scratch = reinterpret_cast<int32_t*>(area + total + 16);
   return nms_assign_launch(boxes, score, area, gt_boxes, valid_ranges, B, A * H * W, max_gt, post_nms_top_n,
-                           nms_thresh, rois, label, bbox_target, bbox_weight, keep_idx, num_kept, 1, stream);
+                           nms_thresh, rois, label, bbox_target, bbox_weight, keep_idx, num_kept, 1,
+                           nms_fast_enabled() ? fast_scratch : nullptr, stream);
 }
 
 }  // extern "C"

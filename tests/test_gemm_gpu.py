@@ -2,7 +2,7 @@
 
 Tolerance: TF32 inputs carry 10 explicit mantissa bits -> per-product relative error 2^-10; for
 K-term dot products of O(1) random data |err| <~ 2^-10*sqrt(K)*|a||b|; asserted as
-max|d| <= 4e-3 * sqrt(K) * rms(a) * rms(b)   (bf16: 8x that).
+max|d| <= 6e-3 * sqrt(K) * rms(a) * rms(b)   (bf16: 8x that).
 """
 import numpy as np
 import pytest
@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 def _tol(K, a, b, dtype):
     import torch
-    base = 4e-3 * (K ** 0.5) * a.float().pow(2).mean().sqrt().item() * b.float().pow(2).mean().sqrt().item()
+    base = 6e-3 * (K ** 0.5) * a.float().pow(2).mean().sqrt().item() * b.float().pow(2).mean().sqrt().item()
     return base * (8 if dtype == torch.bfloat16 else 1) + 1e-5
 
 

@@ -47,6 +47,23 @@ def test_mpt_full_batch20():
     _compare(res, _run_gpu(*inp))
 
 
+def test_mpt_fast_and_sequential_nms_agree(monkeypatch):
+    # the sorted/bit-mask fast path and the round-by-round emulation must give the same bits as the oracle
+    inp = synth.mpt_inputs(61, 6, 21, 32, 32)
+    res = O.multi_proposal_target(*inp)
+    monkeypatch.setenv("SNIPER_NMS_FAST", "1")
+    _compare(res, _run_gpu(*inp))
+    monkeypatch.setenv("SNIPER_NMS_FAST", "0")
+    _compare(res, _run_gpu(*inp))
+    # few valid candidates (narrow valid range): fewer than 300 kept, fillers must match too
+    cls_prob, bbox_pred, im_info, gts, vr = synth.mpt_inputs(62, 3, 21, 32, 32)
+    vr[:] = (200.0, 230.0)
+    res = O.multi_proposal_target(cls_prob, bbox_pred, im_info, gts, vr)
+    assert res["num_kept"].max() < 300
+    monkeypatch.setenv("SNIPER_NMS_FAST", "1")
+    _compare(res, _run_gpu(cls_prob, bbox_pred, im_info, gts, vr))
+
+
 def test_mpt_score_ties_follow_reference_scan_order():
     # quantised logits -> thousands of exactly equal scores; keep order must follow the reference's
     # strided 3-level argmax (multi_proposal_target.cu:139-176)
