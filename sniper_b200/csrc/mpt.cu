@@ -179,12 +179,13 @@ struct NmsArgs {
 constexpr int kNmsThreads = 1024;
 
 // ------------------------------------------------------------------------------------------------
-// Fast path of the greedy NMS: top-score selection (uniform score histogram), exact sort, then 64-wide
-// blocks resolved with IoU bit masks (ballot/shuffle reductions).  It produces exactly the keep list of the
-// sequential reference algorithm whenever no two selected candidates have equal scores; on an exact score
-// tie (where the reference's keep order depends on its strided scan), when the selection does not fit or
-// is exhausted before R boxes are kept, it raises `fallback` and mpt_nms_assign_kernel runs the faithful
-// round-by-round emulation instead.
+// Fast path of the greedy NMS: two-level score histogram -> top <= 4096 candidates -> exact bitonic sort ->
+// trips of <= 64 candidates resolved with IoU bit masks (ballot / shuffle reductions) by one thread that
+// also replays the reference's row swaps, so exact score ties are broken in the reference's scan order
+// (lexicographic (d%32, (d%1024)/32, d/1024) of the candidate's current row distance d to the front).
+// It falls back (flag) to the round-by-round emulation in mpt_nms_assign_kernel when a run of equal scores
+// is longer than a trip, when more than 4096 candidates share the boundary sub-bin, or when the selection
+// is exhausted before R boxes are kept while unselected valid candidates remain.
 constexpr int kFastCap = 4096;          // candidates sorted per chip
 constexpr int kFastBins = 4096;
 
@@ -199,6 +200,55 @@ struct FastArgs {
   int32_t* fallback;   // [B]
 };
 
+__device__ __forceinline__ int score_bin(float s) {
+  return (int)(fminf(fmaxf(s, 0.0f), 1.0f) * (float)(kFastBins - 1));
+}
+// position of s inside its coarse bin, again kFastBins levels; monotone in s for a fixed coarse bin
+__device__ __forceinline__ int score_subbin(float s, int q) {
+  const float f = fminf(fmaxf(s, 0.0f), 1.0f) * (float)(kFastBins - 1) - (float)q;   // in [0,1)
+  const int r = (int)(f * (float)kFastBins);
+  return r < 0 ? 0 : (r > kFastBins - 1 ? kFastBins - 1 : r);
+}
+
+// Scans s_hist from the top bin down (thread t owns 4 bins) and returns, in *out, the number D of leading
+// bins whose cumulative count stays <= cap, and in *cum_out the count inside those D bins.
+__device__ __forceinline__ void top_prefix(const int* s_hist, int cap, int t, int lane, int warp, int* s_wsum,
+                                           int* out_D, int* out_cum) {
+  int h[4];
+  int mine = 0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { h[u] = s_hist[kFastBins - 1 - (4 * t + u)]; mine += h[u]; }
+  int incl = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_wsum[lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, off);
+      if (lane >= off) w += v;
+    }
+    s_wsum[lane] = w;
+  }
+  __syncthreads();
+  int c = incl - mine + (warp ? s_wsum[warp - 1] : 0);
+  int ok = 0, okc = 0;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    c += h[u];
+    if (c <= cap) { ++ok; okc += h[u]; }
+  }
+  ok = __reduce_add_sync(0xffffffffu, ok);
+  okc = __reduce_add_sync(0xffffffffu, okc);
+  if (lane == 0 && ok) { atomicAdd(out_D, ok); atomicAdd(out_cum, okc); }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_fast_kernel(FastArgs p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* s_key = reinterpret_cast<unsigned long long*>(smem_raw);              // [kFastCap]
@@ -209,165 +259,181 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_fast_kernel(FastArgs p
   float* s_karea = reinterpret_cast<float*>(s_kbox + 1024);                                 // [1024]
   unsigned long long* s_mask = reinterpret_cast<unsigned long long*>(s_karea + 1024);       // [64]
   int* s_alive = reinterpret_cast<int*>(s_mask + 64);                                       // [64]
-  __shared__ int s_qstar, s_nsel, s_nvalid, s_tie, s_nk, s_wsum[32];
+  unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_alive + 64);                  // [kFastCap] current row
+  short* s_atpos = reinterpret_cast<short*>(s_pos + kFastCap);                              // [1024] row -> sorted idx
+  __shared__ int s_D, s_cum, s_D2, s_cum2, s_nsel, s_nvalid, s_bad, s_nk, s_wsum[32];
   const int chip = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int AHW = p.AHW;
   const float* sc = p.scores + (size_t)chip * AHW;
   const float4* boxes = p.boxes + (size_t)chip * AHW;
   const float* areas = p.areas + (size_t)chip * AHW;
   for (int i = t; i < kFastBins; i += kNmsThreads) s_hist[i] = 0;
-  if (t == 0) { s_nsel = 0; s_nvalid = 0; s_tie = 0; s_nk = 0; s_qstar = 0; }
+  if (t == 0) { s_nsel = 0; s_nvalid = 0; s_bad = 0; s_nk = 0; s_D = 0; s_cum = 0; s_D2 = 0; s_cum2 = 0; }
   __syncthreads();
-  // ---- 1. histogram of quantised scores (monotone in the score, so "q >= q*" is a top set)
+  // ---- 1. coarse histogram of the scores (bins are monotone in the score)
   int nv = 0;
   for (int i = t; i < AHW; i += kNmsThreads) {
     const float s = sc[i];
     if (s != -1.0f) {
-      int q = (int)(fminf(fmaxf(s, 0.0f), 1.0f) * (float)(kFastBins - 1));
-      atomicAdd(&s_hist[q], 1);
+      atomicAdd(&s_hist[score_bin(s)], 1);
       ++nv;
     }
   }
   nv = __reduce_add_sync(0xffffffffu, nv);
   if (lane == 0 && nv) atomicAdd(&s_nvalid, nv);
   __syncthreads();
-  // ---- 2. largest top set of bins with at most kFastCap members: scan the bins from the top score down;
-  //         the cumulative count is monotone, so the admissible bins form a prefix of that order
-  {
-    int h[4];
-    int mine = 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { h[u] = s_hist[kFastBins - 1 - (4 * t + u)]; mine += h[u]; }
-    int incl = mine;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += v;
-    }
-    if (lane == 31) s_wsum[warp] = incl;
+  top_prefix(s_hist, kFastCap, t, lane, warp, s_wsum, &s_D, &s_cum);
+  const int qb = kFastBins - 1 - s_D;   // boundary bin: taken only partially (or -1 if everything fits)
+  const int above = s_cum;              // candidates in bins > qb
+  // ---- 2. refine inside the boundary bin
+  int sub_star = kFastBins;             // sub-bins >= sub_star of bin qb are selected
+  if (qb >= 0) {
+    for (int i = t; i < kFastBins; i += kNmsThreads) s_hist[i] = 0;
     __syncthreads();
-    if (warp == 0) {
-      int w = s_wsum[lane];
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, w, off);
-        if (lane >= off) w += v;
-      }
-      s_wsum[lane] = w;
+    for (int i = t; i < AHW; i += kNmsThreads) {
+      const float s = sc[i];
+      if (s != -1.0f && score_bin(s) == qb) atomicAdd(&s_hist[score_subbin(s, qb)], 1);
     }
     __syncthreads();
-    int c = incl - mine + (warp ? s_wsum[warp - 1] : 0);
-    int ok = 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { c += h[u]; ok += (c <= kFastCap); }
-    ok = __reduce_add_sync(0xffffffffu, ok);
-    if (lane == 0 && ok) atomicAdd(&s_qstar, ok);   // s_qstar = D = number of admissible bins
+    top_prefix(s_hist, kFastCap - above, t, lane, warp, s_wsum, &s_D2, &s_cum2);
+    sub_star = kFastBins - s_D2;
   }
-  __syncthreads();
-  const int qstar = kFastBins - s_qstar;   // select scores with bin >= q*
   // ---- 3. gather the selected candidates as 64-bit keys (score descending, then index)
   for (int i = t; i < kFastCap; i += kNmsThreads) s_key[i] = ~0ull;
+  for (int i = t; i < 1024; i += kNmsThreads) s_atpos[i] = -1;
   __syncthreads();
   for (int i = t; i < AHW; i += kNmsThreads) {
     const float s = sc[i];
     if (s != -1.0f) {
-      const int q = (int)(fminf(fmaxf(s, 0.0f), 1.0f) * (float)(kFastBins - 1));
-      if (q >= qstar) {
+      const int q = score_bin(s);
+      if (q > qb || (q == qb && score_subbin(s, q) >= sub_star)) {
         const int slot = atomicAdd(&s_nsel, 1);
         if (slot < kFastCap) s_key[slot] = ((unsigned long long)ord_desc(s) << 32) | (unsigned)i;
       }
     }
   }
   __syncthreads();
-  const int nsel = s_nsel;
-  bool bad = nsel > kFastCap;
-  // ---- 4. bitonic sort of kFastCap keys (padding = ~0 sorts last)
-  if (!bad) {
-    for (int k = 2; k <= kFastCap; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = t; i < kFastCap; i += kNmsThreads) {
-          const int l = i ^ j;
-          if (l > i) {
-            const unsigned long long a = s_key[i], b = s_key[l];
-            const bool up = ((i & k) == 0);
-            if ((a > b) == up) { s_key[i] = b; s_key[l] = a; }
-          }
+  const int nsel = s_nsel;   // <= kFastCap by construction
+  // ---- 4. bitonic sort (padding = ~0 sorts last)
+  for (int k = 2; k <= kFastCap; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < kFastCap; i += kNmsThreads) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = s_key[i], b = s_key[l];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { s_key[i] = b; s_key[l] = a; }
         }
-        __syncthreads();
       }
+      __syncthreads();
     }
-    // exact score ties among the selected -> the reference's order is scan-dependent -> fallback
-    int tie = 0;
-    for (int i = t; i + 1 < nsel; i += kNmsThreads) tie |= ((s_key[i] >> 32) == (s_key[i + 1] >> 32));
-    if (__any_sync(0xffffffffu, tie) && lane == 0) s_tie = 1;
-    for (int i = t; i < nsel; i += kNmsThreads) {
-      const int id = (int)(unsigned)s_key[i];
-      s_box[i] = boxes[id];
-      s_area[i] = areas[id];
-    }
+  }
+  for (int i = t; i < nsel; i += kNmsThreads) {
+    const int id = (int)(unsigned)s_key[i];
+    s_box[i] = boxes[id];
+    s_area[i] = areas[id];
+    s_pos[i] = (unsigned short)id;
+    if (id < 1024) s_atpos[id] = (short)i;
   }
   __syncthreads();
-  bad = bad || s_tie;
-  // ---- 5. greedy NMS over the sorted list, 64 candidates per trip
+  // ---- 5. greedy NMS over the sorted list, trips of <= 64 candidates that never split a run of equal scores
   const int grp = t >> 4, sub = t & 15;   // 64 groups of 16 threads: one candidate each
-  if (!bad) {
-    for (int base = 0; base < nsel; base += 64) {
-      const int nk = s_nk;
-      if (nk >= p.R) break;
-      const int ci = base + grp;
-      const bool have = ci < nsel;
-      float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
-      float ca = 0.f;
-      if (have) { cb = s_box[ci]; ca = s_area[ci]; }
-      // (a) against everything kept so far
-      int dead = 0;
-      if (have)
-        for (int k = sub; k < nk; k += 16) dead |= (iou_ref(s_kbox[k].x, s_kbox[k].y, s_kbox[k].z, s_kbox[k].w, s_karea[k], cb, ca) > p.nms_thresh);
-      const unsigned dm = __ballot_sync(0xffffffffu, dead);
-      const bool alive = have && (((dm >> (lane & 16)) & 0xffffu) == 0);
-      // (b) against the later members of this trip: 4 columns per thread
-      unsigned long long m = 0;
-      if (have) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = sub * 4 + u;
-          if (j > grp && base + j < nsel) {
-            const float4 ob = s_box[base + j];
-            if (iou_ref(cb.x, cb.y, cb.z, cb.w, ca, ob, s_area[base + j]) > p.nms_thresh) m |= 1ull << j;
-          }
-        }
-      }
-#pragma unroll
-      for (int off = 8; off > 0; off >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, off);
-      if (sub == 0) { s_mask[grp] = m; s_alive[grp] = alive ? 1 : 0; }
-      __syncthreads();
-      // (c) sequential resolve by one thread
-      if (t == 0) {
-        unsigned long long removed = 0;
-        int k = nk;
-        for (int i = 0; i < 64 && k < p.R; ++i) {
-          if (s_alive[i] && !((removed >> i) & 1ull)) {
-            s_kbox[k] = s_box[base + i];
-            s_karea[k] = s_area[base + i];
-            p.keep_ids[(size_t)chip * 1024 + k] = (int)(unsigned)s_key[base + i];
-            ++k;
-            removed |= s_mask[i];
-          }
-        }
-        s_nk = k;
-      }
-      __syncthreads();
+  int base = 0;
+  while (base < nsel) {
+    const int nk = s_nk;
+    if (nk >= p.R || s_bad) break;
+    int end = min(base + 64, nsel);
+    if (end < nsel)
+      while (end > base && (unsigned)(s_key[end - 1] >> 32) == (unsigned)(s_key[end] >> 32)) --end;
+    if (end == base) {   // a run of equal scores longer than a trip
+      if (t == 0) s_bad = 1;
+      break;
     }
+    const int len = end - base;
+    const int ci = base + grp;
+    const bool have = grp < len;
+    float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ca = 0.f;
+    if (have) { cb = s_box[ci]; ca = s_area[ci]; }
+    // (a) against everything kept so far
+    int dead = 0;
+    if (have)
+      for (int k = sub; k < nk; k += 16)
+        dead |= (iou_ref(s_kbox[k].x, s_kbox[k].y, s_kbox[k].z, s_kbox[k].w, s_karea[k], cb, ca) > p.nms_thresh);
+    const unsigned dm = __ballot_sync(0xffffffffu, dead);
+    const bool alive = have && (((dm >> (lane & 16)) & 0xffffu) == 0);
+    // (b) against every other member of this trip (symmetric: inside a tie run the order is not known yet)
+    unsigned long long m = 0;
+    if (have) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = sub * 4 + u;
+        if (j != grp && j < len) {
+          const float4 ob = s_box[base + j];
+          const float oa = s_area[base + j];
+          // the reference evaluates IoU with the selected box first; float min/max/add are symmetric
+          if (iou_ref(cb.x, cb.y, cb.z, cb.w, ca, ob, oa) > p.nms_thresh) m |= 1ull << j;
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, off);
+    if (sub == 0) { s_mask[grp] = m; s_alive[grp] = alive ? 1 : 0; }
+    __syncthreads();
+    // (c) sequential resolve by one thread, replaying the reference's swaps for its tie order
+    if (t == 0) {
+      unsigned long long removed = 0;   // suppressed or already selected
+      int k = nk;
+      int i = 0;
+      while (i < len && k < p.R) {
+        int e = i + 1;
+        const unsigned sc_i = (unsigned)(s_key[base + i] >> 32);
+        while (e < len && (unsigned)(s_key[base + e] >> 32) == sc_i) ++e;
+        while (k < p.R) {
+          int best = -1;
+          unsigned bestkey = 0xffffffffu;
+          for (int c = i; c < e; ++c) {
+            if (!s_alive[c] || ((removed >> c) & 1ull)) continue;
+            const unsigned d = (unsigned)((int)s_pos[base + c] - k);   // row distance to the front (row k)
+            const unsigned key = ((d & 31u) << 10) | (((d >> 5) & 31u) << 5) | (d >> 10);
+            if (key < bestkey) { bestkey = key; best = c; }
+          }
+          if (best < 0) break;
+          const int ci2 = base + best;
+          s_kbox[k] = s_box[ci2];
+          s_karea[k] = s_area[ci2];
+          p.keep_ids[(size_t)chip * 1024 + k] = (int)(unsigned)s_key[ci2];
+          // swap rows k and pos(best) (multi_proposal_target.cu:178-199)
+          const int pb = s_pos[ci2];
+          const int f = s_atpos[k];      // k < R <= 1024
+          if (f >= 0 && f != ci2) {
+            s_pos[f] = (unsigned short)pb;
+            if (pb < 1024) s_atpos[pb] = (short)f;
+          } else if (f < 0 && pb < 1024) {
+            s_atpos[pb] = -1;            // an unselected row moved there
+          }
+          s_atpos[k] = (short)ci2;
+          s_pos[ci2] = (unsigned short)k;
+          removed |= s_mask[best] | (1ull << best);
+          ++k;
+        }
+        i = e;
+      }
+      s_nk = k;
+    }
+    __syncthreads();
+    base = end;
   }
+  __syncthreads();
   if (t == 0) {
     const int nk = s_nk;
+    const bool bad = s_bad != 0;
     // not enough: there are valid candidates outside the selection that the reference would still visit
     const bool exhausted = !bad && nk < p.R && nsel < s_nvalid;
     p.nkept[chip] = nk;
     p.fallback[chip] = (bad || exhausted) ? 1 : 0;
   }
 }
-
 
 // One CTA per chip.  Positions 0..AHW-1 hold (score, id) in shared memory; the reference's row swap
 // (cu:178-199) becomes a 6-byte swap here, the 16-byte boxes never move.  Tie order of the
@@ -656,7 +722,7 @@ static int nms_assign_launch(const float* boxes, const float* score, const float
   n.bbox_weight = bbox_weight; n.keep_idx = keep_idx; n.num_kept = num_kept; n.do_assign = do_assign;
   const size_t smem = (size_t)AHW * 6 + 16;
   static bool attr_set = false;
-  const size_t fast_smem = (size_t)kFastCap * (8 + 16 + 4) + kFastBins * 4 + 1024 * 20 + 64 * 8 + 64 * 4 + 64;
+  const size_t fast_smem = (size_t)kFastCap * (8 + 16 + 4 + 2) + kFastBins * 4 + 1024 * (20 + 2) + 64 * 8 + 64 * 4 + 64;
   if (!attr_set) {
     SN_CUDA(cudaFuncSetAttribute(mpt_nms_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     SN_CUDA(cudaFuncSetAttribute(mpt_nms_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -58,7 +58,7 @@ def generate_anchors(feat_stride, scales, ratios):
 
 def multi_proposal_target(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, *, feat_stride=16,
                           scales=(2, 4, 7, 10, 13, 16, 24), ratios=(0.5, 1, 2), rpn_post_nms_top_n=300,
-                          threshold=0.7, layout=NCHW, return_keep=False):
+                          threshold=0.7, layout=NCHW, return_keep=False, return_fallback=False):
     """MultiProposalTarget forward (reference GPU-operator semantics, multi_proposal_target.cu:362-589).
 
     NCHW: cls_prob [B,2A,H,W] (or [B,2,A*H,W]), bbox_pred [B,4A,H,W].  NHWC: [B,H,W,2A] / [B,H,W,4A].
@@ -92,6 +92,11 @@ def multi_proposal_target(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, 
         _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), _ptr(gt_boxes), _ptr(valid_ranges), B, A, H, W, max_gt, R,
         int(feat_stride), sp, len(s), rp, len(r), float(threshold), layout, sc, dc, _ptr(rois), _ptr(label),
         _ptr(bbox_target), _ptr(bbox_weight), _ptr(keep), _ptr(nkept), _ptr(ws), ws_bytes, _stream()))
+    if return_fallback:
+        # per-chip flag written by mpt_nms_fast_kernel into the workspace tail (1 = sequential emulation was used)
+        off = B * A * H * W * 24 + 64
+        fb = ws[off:off + B * 1026 * 4].view(torch.int32)[B * 1025:B * 1026].clone()
+        return rois, label, bbox_target, bbox_weight, keep, nkept, fb
     if return_keep:
         return rois, label, bbox_target, bbox_weight, keep, nkept
     return rois, label, bbox_target, bbox_weight

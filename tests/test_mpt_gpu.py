@@ -64,6 +64,37 @@ def test_mpt_fast_and_sequential_nms_agree(monkeypatch):
     _compare(res, _run_gpu(cls_prob, bbox_pred, im_info, gts, vr))
 
 
+def test_mpt_fast_path_is_taken_and_handles_ties(monkeypatch):
+    """The fast path must really run (fallback flag 0) on ordinary inputs, on near-constant scores (the
+    random-init regime of bench.py: thousands of scores within 1e-2 of 0.5, exact float ties among them) and on
+    quantised scores with short tie runs; only runs of > 64 equal scores may fall back."""
+    import torch
+    from sniper_b200 import ops
+    monkeypatch.setenv("SNIPER_NMS_FAST", "1")
+    rng = np.random.RandomState(71)
+    B, A, H, W = 4, 21, 32, 32
+    cases = []
+    cases.append(synth.mpt_inputs(72, B, A, H, W))
+    cp, bp, im, gt, vr = synth.mpt_inputs(73, B, A, H, W)
+    lg = (rng.randn(B, 2, A * H * W) * 0.01).astype(np.float32)      # random-init regime
+    e = np.exp(lg - lg.max(1, keepdims=True))
+    cases.append(((e / e.sum(1, keepdims=True)).astype(np.float32).reshape(B, 2 * A, H, W), bp, im, gt, vr))
+    lg = np.round(rng.randn(B, 2, A * H * W) * 64).astype(np.float32) / 64   # many short tie runs
+    e = np.exp(lg - lg.max(1, keepdims=True))
+    cases.append(((e / e.sum(1, keepdims=True)).astype(np.float32).reshape(B, 2 * A, H, W), bp, im, gt, vr))
+    for ci, inp in enumerate(cases):
+        res = O.multi_proposal_target(*inp)
+        t = [torch.from_numpy(a).cuda() for a in inp]
+        out = ops.multi_proposal_target(*t, return_keep=True, return_fallback=True)
+        got = [o.cpu().numpy() for o in out]
+        _compare(res, got[:6])
+        if ci < 2:
+            assert got[6].sum() == 0, "fast path fell back on case %d: %s" % (ci, got[6])
+    d = res["dets"][:A * H * W]
+    v = d[d[:, 4] != -1, 4]
+    assert len(np.unique(v)) < len(v)      # the last case really contains exact ties
+
+
 def test_mpt_score_ties_follow_reference_scan_order():
     # quantised logits -> thousands of exactly equal scores; keep order must follow the reference's
     # strided 3-level argmax (multi_proposal_target.cu:139-176)
