@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -32,6 +33,8 @@ struct GemmParams {
   int num_kb;             // k-blocks per tile
   int stages;
   int tiles_m, tiles_n, splits;
+  int cluster;            // 1, or 2 = CTA pair along M sharing the B tile by TMA multicast
+  uint32_t stage_tx_bytes;  // bytes landing in one ring stage of ONE CTA (A + full B)
   // ---- producer geometry
   int elems_per_128B;     // 32 (tf32) / 64 (bf16)
   int cblocks;            // CONV: channel blocks per tap (Cin / elems_per_128B)
@@ -97,6 +100,30 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               int c2, int c3, uint16_t cta_mask) {
+  // multicast: the box lands at the same shared-memory offset of every CTA in cta_mask and signals the
+  // mbarrier at the same offset in each of them
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -164,12 +191,14 @@ struct TileCoord {
   int tile_m, tile_n, split;
 };
 
-__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int t) {
+// work unit u of a cluster -> tile of this CTA (cluster of 2: consecutive M tiles, same N tile)
+__device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int cta_rank) {
   TileCoord c;
-  c.tile_n = t % p.tiles_n;
-  const int r = t / p.tiles_n;
-  c.tile_m = r % p.tiles_m;
-  c.split = r / p.tiles_m;
+  const int tiles_mp = (p.tiles_m + p.cluster - 1) / p.cluster;
+  c.tile_n = u % p.tiles_n;
+  const int r = u / p.tiles_n;
+  c.tile_m = (r % tiles_mp) * p.cluster + cta_rank;
+  c.split = r / tiles_mp;
   return c;
 }
 
@@ -194,14 +223,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t acc_cols = p.block_n <= 32 ? 32u : (p.block_n <= 64 ? 64u : (p.block_n <= 128 ? 128u : 256u));
   const uint32_t tmem_cols = 2u * acc_cols;
-  const int total_tiles = p.tiles_m * p.tiles_n * p.splits;
+  const int cta_rank = p.cluster == 2 ? (int)cluster_ctarank() : 0;
+  const int unit0 = p.cluster == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = p.cluster == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = ((p.tiles_m + p.cluster - 1) / p.cluster) * p.tiles_n * p.splits;   // work units
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (uint32_t)p.cluster);   // every CTA sharing the stage must have consumed it
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
@@ -213,6 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 1) tmem_alloc(tmem_ptr_smem, tmem_cols);
   tc_fence_before();
   __syncthreads();
+  if (p.cluster == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -221,8 +254,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (lane == 0) {
       const int E = p.elems_per_128B;
       uint32_t it = 0;  // global k-block counter across tiles -> ring slot / phase
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = tile_coord(p, t);
+      for (int t = unit0; t < total_tiles; t += unit_step) {
+        const TileCoord tc = tile_coord(p, t, cta_rank);
         int n_img = 0, oh0 = 0, ow0 = 0;
         if (p.mode == MODE_CONV) {
           n_img = tc.tile_m / p.tiles_per_img;
@@ -242,16 +275,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + kStageABytes;
-          mbar_expect_tx(&full_bar[s], (uint32_t)p.a_boxes * p.a_box_bytes + (uint32_t)p.b_boxes * p.b_box_bytes);
+          mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
           const int kb = tc.split * p.num_kb + i;
           if (p.mode == MODE_GEMM) {
             tma_load_4d(sa, &tma_a, &full_bar[s], kb * E, tc.tile_m * 128, 0, 0);
-            tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
+            if (p.cluster == 2)
+              tma_load_4d_mc(sb + (size_t)cta_rank * p.b_box_bytes, &tma_b, &full_bar[s], kb * E,
+                             tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0, 3);
+            else
+              tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
           } else if (p.mode == MODE_CONV) {
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
             tma_load_4d(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
                         oh0 * p.conv_stride + p.tap_dh[tap], n_img);
-            tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
+            if (p.cluster == 2)
+              tma_load_4d_mc(sb + (size_t)cta_rank * p.b_box_bytes, &tma_b, &full_bar[s], kb * E,
+                             tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0, 3);
+            else
+              tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
           } else {
             // WGRAD: k-block = kp consecutive output pixels of one image row block
             const int pix0 = kb * p.kp;
@@ -260,9 +301,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
             for (int j = 0; j < p.a_boxes; ++j)
               tma_load_4d(sa + (size_t)j * p.a_box_bytes, &tma_a, &full_bar[s], tc.tile_m * 128 + j * E, pix0, 0, 0);
-            for (int j = 0; j < p.b_boxes; ++j)
-              tma_load_4d(sb + (size_t)j * p.b_box_bytes, &tma_b, &full_bar[s], wg_ci0 + j * E,
-                          ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img);
+            if (p.cluster == 2) {
+              const int hb = p.b_boxes >> 1;
+              for (int j = cta_rank * hb; j < (cta_rank + 1) * hb; ++j)
+                tma_load_4d_mc(sb + (size_t)j * p.b_box_bytes, &tma_b, &full_bar[s], wg_ci0 + j * E,
+                               ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img, 3);
+            } else {
+              for (int j = 0; j < p.b_boxes; ++j)
+                tma_load_4d(sb + (size_t)j * p.b_box_bytes, &tma_b, &full_bar[s], wg_ci0 + j * E,
+                            ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img);
+            }
           }
         }
       }
@@ -271,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // =============================== MMA issuer
     if (lane == 0) {
       uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+      for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
         const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
@@ -289,7 +337,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             umma<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
                      (i | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);
+          if (p.cluster == 2) umma_commit_mc(&empty_bar[s], 3);   // frees the stage in both CTAs' rings
+          else umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full_bar[acc]);
       }
@@ -301,8 +350,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int m_local = q * 32 + lane;
     const int cols_per_warp = p.block_n >> 1;   // block_n >= 64
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-      const TileCoord tc = tile_coord(p, t);
+    for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
+      const TileCoord tc = tile_coord(p, t, cta_rank);
       const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
       long row;
       bool row_ok;
@@ -313,10 +362,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int oh = th * p.tile_h + m_local / p.tile_w;
         const int ow = (r - th * p.tiles_w) * p.tile_w + m_local % p.tile_w;
         row = ((long)n_img * p.out_H + (long)oh * p.out_s + p.out_oh) * p.out_W + (long)ow * p.out_s + p.out_ow;
-        row_ok = oh < p.Ho && ow < p.Wo;
+        row_ok = oh < p.Ho && ow < p.Wo && tc.tile_m < p.tiles_m;
       } else {
         row = (long)tc.tile_m * 128 + m_local;
-        row_ok = row < p.M;
+        row_ok = row < p.M && tc.tile_m < p.tiles_m;
       }
       int col_base = tc.tile_n * p.block_n;
       if (p.mode == MODE_WGRAD) {
@@ -430,6 +479,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cluster == 2) cluster_sync_all();   // nobody exits while the peer may still multicast into it
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -501,8 +551,9 @@ size_t smem_bytes(int stages, int block_n) {
 
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 tiles, cudaStream_t stream) {
   p.tiles_m = (int)tiles.x; p.tiles_n = (int)tiles.y; p.splits = (int)tiles.z;
-  const long total = (long)tiles.x * tiles.y * tiles.z;
-  dim3 grid((unsigned)(total < sn::kNumSMs ? total : sn::kNumSMs), 1, 1);
+  const long units = (long)((tiles.x + p.cluster - 1) / p.cluster) * tiles.y * tiles.z;
+  const long max_units = sn::kNumSMs / p.cluster;
+  dim3 grid((unsigned)((units < max_units ? units : max_units) * p.cluster), 1, 1);
   const size_t smem = smem_bytes(p.stages, p.block_n);
   static bool attr_done[2] = {false, false};
   if (!attr_done[p.dtype]) {
@@ -512,10 +563,23 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
       SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done[p.dtype] = true;
   }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(320, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   if (p.dtype == DT_TF32)
-    gemm_tc_kernel<DT_TF32><<<grid, 320, smem, stream>>>(ma, mb, p);
+    SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_TF32>, ma, mb, p));
   else
-    gemm_tc_kernel<DT_BF16><<<grid, 320, smem, stream>>>(ma, mb, p);
+    SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_BF16>, ma, mb, p));
   SN_LAUNCH_CHECK();
   return 0;
 }
@@ -525,6 +589,18 @@ int pick_block_n(int N) {
   if (N <= 128) return 128;
   if (N % 256 == 0 || N > 1024) return 256;
   return 128;
+}
+
+// CTA pairs (cluster of 2 along M) share the B tile through TMA multicast: with fp32 operands a 128 x 256 tile
+// needs 96 B/clk/SM of L2->SM operand traffic at full MMA rate; sharing B brings it to 64 B/clk.
+// SNIPER_GEMM_CLUSTER=0 disables it (A/B measurements).
+int pick_cluster(int tiles_m) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("SNIPER_GEMM_CLUSTER");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  return (enabled && tiles_m >= 2) ? 2 : 1;
 }
 
 void fill_kmajor(GemmParams& p, int dtype, int block_n) {
@@ -538,7 +614,8 @@ void fill_kmajor(GemmParams& p, int dtype, int block_n) {
   p.mmas_per_kb = 4;
   p.a_boxes = 1; p.b_boxes = 1;
   p.a_box_bytes = kStageABytes;
-  p.b_box_bytes = (uint32_t)block_n * 128u;
+  p.b_box_bytes = (uint32_t)(block_n / p.cluster) * 128u;   // each CTA of a pair loads (and multicasts) half of B
+  p.stage_tx_bytes = kStageABytes + (uint32_t)block_n * 128u;
   p.stages = pick_stages(block_n);
 }
 
@@ -570,6 +647,7 @@ int sniper_gemm_nt(const void* A, long lda, const void* B, long ldb, float* C, l
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const int bn = pick_block_n(N);
+  p.cluster = pick_cluster(sn::div_up(M, 128));
   fill_kmajor(p, dtype, bn);
   p.mode = MODE_GEMM; p.M = M; p.N = N; p.num_kb = K / E;
   p.C = C; p.ldc = ldc; p.scale = scale; p.bias = bias; p.residual = residual; p.ldr = ldr; p.relu = relu;
@@ -585,7 +663,7 @@ int sniper_gemm_nt(const void* A, long lda, const void* B, long ldb, float* C, l
   {
     const uint64_t d[4] = {(uint64_t)K, (uint64_t)N, 1, 1};
     const uint64_t s[3] = {(uint64_t)ldb * esz, (uint64_t)ldb * esz * N, (uint64_t)ldb * esz * N};
-    const uint32_t b[4] = {(uint32_t)E, (uint32_t)bn, 1, 1};
+    const uint32_t b[4] = {(uint32_t)E, (uint32_t)(bn / p.cluster), 1, 1};
     if (make_map(&mb, dtype, B, d, s, b, ones)) return -1;
   }
   dim3 grid(sn::div_up(M, 128), sn::div_up(N, bn), 1);
@@ -614,6 +692,7 @@ int sniper_conv2d_nhwc(const void* X, long x_ld, int NB, int H, int W, int Cin, 
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const int bn = pick_block_n(Cout);
+  p.cluster = pick_cluster(NB * (Wo / tile_w) * sn::div_up(Ho, tile_h));
   fill_kmajor(p, dtype, bn);
   p.mode = MODE_CONV; p.N = Cout; p.cblocks = Cin / E; p.ntaps = ntaps; p.num_kb = ntaps * p.cblocks;
   for (int t = 0; t < ntaps; ++t) { p.tap_dh[t] = tap_dh[t]; p.tap_dw[t] = tap_dw[t]; }
@@ -637,7 +716,7 @@ int sniper_conv2d_nhwc(const void* X, long x_ld, int NB, int H, int W, int Cin, 
     const uint64_t K = (uint64_t)ntaps * Cin;
     const uint64_t d[4] = {K, (uint64_t)Cout, 1, 1};
     const uint64_t s[3] = {K * esz, K * esz * Cout, K * esz * Cout};
-    const uint32_t b[4] = {(uint32_t)E, (uint32_t)bn, 1, 1};
+    const uint32_t b[4] = {(uint32_t)E, (uint32_t)(bn / p.cluster), 1, 1};
     const uint32_t ones[4] = {1, 1, 1, 1};
     if (make_map(&mb, dtype, Wt, d, s, b, ones)) return -1;
   }
@@ -687,6 +766,8 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, long dy_ld, const void* X, long x_l
   p.mmas_per_kb = kp / umma_k;
   p.a_boxes = 128 / E; p.b_boxes = bn / E;
   p.a_box_bytes = chunk_bytes; p.b_box_bytes = chunk_bytes;
+  p.cluster = (p.b_boxes % 2 == 0) ? pick_cluster(Cout / 128 + (Cout % 128 ? 1 : 0)) : 1;
+  p.stage_tx_bytes = (uint32_t)(p.a_boxes + p.b_boxes) * chunk_bytes;
   p.stages = pick_stages(bn);
   p.ntaps = ntaps;
   for (int t = 0; t < ntaps; ++t) { p.tap_dh[t] = tap_dh[t]; p.tap_dw[t] = tap_dw[t]; }

@@ -1,0 +1,66 @@
+"""Generates the committed golden fixtures (run in the build container, where /root/reference exists).
+
+  chips_config1.npz : output of the REFERENCE's own lib/chips/cchips.cpp (compiled as it lies into
+                      oracle/_ref/libref_chips.so by oracle/Makefile) on BASELINE config 1: one 1333x800 image,
+                      20 GT boxes + 400 proposals, three scales, chip 512, fixed stride, srand(seed).
+  mpt_small.npz     : oracle/mpt.c on a seeded 2-chip input (the reference ships no vectors for this operator).
+  psroi_small.npz   : oracle/psroi.c on the reference's own test shapes (test_operator.py:4358-4389).
+Usage: python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as O  # noqa: E402
+from sniper_b200 import synth  # noqa: E402
+
+
+def config1_boxes(seed, n, W=1333, H=800):
+    rng = np.random.RandomState(seed)
+    s = np.exp(rng.uniform(np.log(8), np.log(400), n))
+    ar = np.exp(rng.uniform(np.log(0.5), np.log(2.0), n))
+    w, h = s * np.sqrt(ar), s / np.sqrt(ar)
+    cx, cy = rng.uniform(0, W, n), rng.uniform(0, H, n)
+    return np.stack([np.clip(cx - w / 2, 0, W - 1), np.clip(cy - h / 2, 0, H - 1), np.clip(cx + w / 2, 0, W - 1),
+                     np.clip(cy + h / 2, 0, H - 1)], 1).astype(np.float32)
+
+
+def main():
+    assert O.ref_chips() is not None, "build oracle/_ref first (make -C oracle ref)"
+    out = {}
+    boxes0 = np.concatenate([config1_boxes(0, 20), config1_boxes(1, 400)])
+    for k, (scale, stride, seed) in enumerate([(3.0, 58, 1), (1.667, 58, 1), (0.384, 58, 1)]):
+        W, H = int(1333 * scale), int(800 * scale)
+        b = boxes0 * np.float32(scale)
+        b[:, [0, 2]] = np.clip(b[:, [0, 2]], 0, W - 1)
+        b[:, [1, 3]] = np.clip(b[:, [1, 3]], 0, H - 1)
+        out["boxes%d" % k] = b
+        out["meta%d" % k] = np.array([W, H, 512, stride, seed], np.int64)
+        out["chips%d" % k] = O.ref_chips_generate(b, W, H, 512, stride, seed=seed)
+    np.savez_compressed(os.path.join(HERE, "chips_config1.npz"), **out)
+
+    inp = synth.mpt_inputs(1234, 2, 21, 16, 16)
+    res = O.multi_proposal_target(*inp)
+    np.savez_compressed(os.path.join(HERE, "mpt_small.npz"), cls_prob=inp[0], bbox_pred=inp[1], im_info=inp[2],
+                        gt_boxes=inp[3], valid_ranges=inp[4], rois=res["rois"], label=res["label"],
+                        bbox_target=res["bbox_target"], bbox_weight=res["bbox_weight"], keep_idx=res["keep_idx"],
+                        num_kept=res["num_kept"])
+
+    rng = np.random.RandomState(3)
+    data = rng.rand(1, 18, 14, 14).astype(np.float32)
+    rois = np.array([[0, 10, 22, 161, 173], [0, 20, 15, 154, 160]], np.float32)
+    trans = (rng.rand(2, 4, 3, 3).astype(np.float32) - 0.5)
+    o, c, si = O.deform_psroi_fwd(data, rois, trans, 0.0625, 2, 3, 3, 3, 4, 0.1, False)
+    o2, bins = O.psroi_fwd(data, rois, 0.0625, 2, 3, 3)
+    np.savez_compressed(os.path.join(HERE, "psroi_small.npz"), data=data, rois=rois, trans=trans, deform_out=o,
+                        deform_count=c, deform_sample_idx=si, psroi_out=o2, psroi_bins=bins)
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()
