@@ -23,11 +23,12 @@ SIGNATURES = {
     "sniper_deform_psroi_bwd": ("i", "pppp" "iiii" "f" "iiiii" "f" "iii" "pp" "p"),
     "sniper_psroi_fwd": ("i", "pp" "iiii" "f" "iiii" "pp" "p"),
     "sniper_psroi_bwd": ("i", "pp" "iiii" "f" "iiii" "p" "p"),
-    "sniper_gemm_nt": ("i", "plplpl" "iiii" "ppp" "l" "iii" "p"),
-    "sniper_conv2d_nhwc": ("i", "pliiii" "pii" "pp" "iii" "pl" "iiiii" "i" "ppp" "l" "iii" "p"),
+    "sniper_gemm_nt": ("i", "plplpl" "iiii" "ppp" "l" "iii" "pp"),
+    "sniper_conv2d_nhwc": ("i", "pliiii" "pii" "pp" "iii" "pl" "iiiii" "i" "ppp" "l" "iii" "pp"),
     "sniper_conv2d_wgrad_nhwc": ("i", "plpl" "iiiii" "i" "pp" "iii" "p" "ii" "p"),
     "sniper_affine_act": ("i", "plpppl" "l" "ii" "p"),
     "sniper_bn_stats": ("i", "pllippffipppppppp"),
+    "sniper_bn_finalize": ("i", "plippffippppppp"),
     "sniper_bn_frozen": ("i", "ippppfippp"),
     "sniper_bn_relu_bwd": ("i", "plplppppp" "pl" "pl" "pp" "li" "p"),
     "sniper_affine_relu_bwd": ("i", "plplpp" "pl" "pl" "lii" "p"),

@@ -457,6 +457,17 @@ int sniper_bn_stats(const float* x, long ldx, long M, int C, const float* gamma,
   return 0;
 }
 
+// Second half of sniper_bn_stats for producers that already accumulated the column sums (tcgen05 epilogue).
+int sniper_bn_finalize(double* sums, long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                       int fix_gamma, float* moving_mean, float* moving_var, float* mean, float* invstd, float* scale,
+                       float* shift, void* stream) {
+  bn_finalize_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, M, C, gamma, beta, eps, momentum,
+                                                                          fix_gamma, moving_mean, moving_var, mean,
+                                                                          invstd, scale, shift);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
 int sniper_bn_frozen(int C, const float* gamma, const float* beta, const float* moving_mean, const float* moving_var,
                      float eps, int fix_gamma, float* scale, float* shift, void* stream) {
   bn_frozen_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, moving_mean, moving_var, eps,

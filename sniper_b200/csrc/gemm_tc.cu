@@ -66,6 +66,8 @@ struct GemmParams {
   // row mapping for CONV: output pixel (n,oh,ow) -> row ((n*out_H + oh*out_s + out_oh)*out_W + ow*out_s + out_ow)
   int out_H, out_W, out_s, out_oh, out_ow;
   int out_bf16;           // store bf16 instead of fp32
+  double* stats;          // optional [2*N]: += per-column sum and sum of squares of the stored values
+                          // (train-mode BatchNorm statistics of the consumer, fused into the producer)
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -402,9 +404,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (!row_ok) continue;
         const int n0 = col_base + c;
-        if (n0 >= p.N) continue;
+        if (n0 >= p.N) continue;                   // warp-uniform
+        if (!row_ok && !p.stats) continue;         // with fused statistics every lane stays for the shuffles
         float* crow = p.C + row * p.ldc + n0;
         const bool full = (n0 + 32 <= p.N);
         float f[32];
@@ -450,6 +452,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               f[j] = x;
             }
           }
+        }
+        if (p.stats) {
+          // column sums over the 32 rows of this warp by recursive halving: after the loop lane l holds column l
+          float sm[32], sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = row_ok ? f[j] : 0.0f;
+            sm[j] = x;
+            sq[j] = x * x;
+          }
+#pragma unroll
+          for (int n = 16; n >= 1; n >>= 1) {
+            const bool upper = (lane & n) != 0;
+#pragma unroll
+            for (int j = 0; j < n; ++j) {
+              const float keep_s = upper ? sm[j + n] : sm[j], send_s = upper ? sm[j] : sm[j + n];
+              const float keep_q = upper ? sq[j + n] : sq[j], send_q = upper ? sq[j] : sq[j + n];
+              sm[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, n);
+              sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, n);
+            }
+          }
+          if (n0 + lane < p.N) {
+            atomicAdd(p.stats + n0 + lane, (double)sm[0]);
+            atomicAdd(p.stats + p.N + n0 + lane, (double)sq[0]);
+          }
+          if (!row_ok) continue;
         }
         if (p.out_bf16) {
           __nv_bfloat16* brow = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0;
@@ -591,14 +619,16 @@ int pick_block_n(int N) {
   return 128;
 }
 
-// CTA pairs (cluster of 2 along M) share the B tile through TMA multicast: with fp32 operands a 128 x 256 tile
-// needs 96 B/clk/SM of L2->SM operand traffic at full MMA rate; sharing B brings it to 64 B/clk.
-// SNIPER_GEMM_CLUSTER=0 disables it (A/B measurements).
+// Optional CTA pairs (cluster of 2 along M) sharing the B tile through TMA multicast (SNIPER_GEMM_CLUSTER=1).
+// Measured on B200 (profiles/gemm_shapes_r01_v3_multicast.md): correct but ~20 % SLOWER on the K-major shapes
+// -- multicast halves the L2 reads of B, but each SM still receives and re-reads the full 48 KB per k-block, and
+// the shared-memory port (96 B/clk TMA fill + 96 B/clk MMA operand reads vs 128 B/clk) is what bounds a
+// 128x256 fp32-operand tile; the pair only adds lock-step stalls.  Off by default; cta_group::2 is the fix.
 int pick_cluster(int tiles_m) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("SNIPER_GEMM_CLUSTER");
-    enabled = (e && e[0] == '0') ? 0 : 1;
+    enabled = (e && e[0] == '1') ? 1 : 0;
   }
   return (enabled && tiles_m >= 2) ? 2 : 1;
 }
@@ -637,7 +667,7 @@ extern "C" {
 // K must be a multiple of 32 (tf32) / 64 (bf16) elements; lda/ldb in elements, 16-byte aligned rows.
 int sniper_gemm_nt(const void* A, long lda, const void* B, long ldb, float* C, long ldc, int M, int N, int K,
                    int dtype, const float* scale, const float* bias, const float* residual, long ldr, int relu,
-                   int accumulate, int out_bf16, void* stream) {
+                   int accumulate, int out_bf16, double* stats, void* stream) {
   SN_CHECK(dtype == DT_TF32 || dtype == DT_BF16, "gemm: dtype must be 0 (tf32) or 1 (bf16)");
   const int esz = dtype == DT_TF32 ? 4 : 2;
   const int E = 128 / esz;
@@ -651,7 +681,7 @@ int sniper_gemm_nt(const void* A, long lda, const void* B, long ldb, float* C, l
   fill_kmajor(p, dtype, bn);
   p.mode = MODE_GEMM; p.M = M; p.N = N; p.num_kb = K / E;
   p.C = C; p.ldc = ldc; p.scale = scale; p.bias = bias; p.residual = residual; p.ldr = ldr; p.relu = relu;
-  p.atomic = accumulate; p.out_bf16 = out_bf16;
+  p.atomic = accumulate; p.out_bf16 = out_bf16; p.stats = stats;
   CUtensorMap ma, mb;
   const uint32_t ones[4] = {1, 1, 1, 1};
   {
@@ -678,7 +708,7 @@ int sniper_conv2d_nhwc(const void* X, long x_ld, int NB, int H, int W, int Cin, 
                        const int* tap_dh, const int* tap_dw, int stride, int Ho, int Wo, float* Y, long ldc,
                        int out_H, int out_W, int out_s, int out_oh, int out_ow, int dtype, const float* scale,
                        const float* bias, const float* residual, long ldr, int relu, int accumulate, int out_bf16,
-                       void* stream) {
+                       double* stats, void* stream) {
   SN_CHECK(dtype == DT_TF32 || dtype == DT_BF16, "conv: dtype must be 0 (tf32) or 1 (bf16)");
   const int esz = dtype == DT_TF32 ? 4 : 2;
   const int E = 128 / esz;
@@ -700,7 +730,7 @@ int sniper_conv2d_nhwc(const void* X, long x_ld, int NB, int H, int W, int Cin, 
   p.tiles_w = Wo / tile_w; p.tiles_per_img = p.tiles_w * sn::div_up(Ho, tile_h);
   p.Ho = Ho; p.Wo = Wo; p.M = NB * Ho * Wo;
   p.C = Y; p.ldc = ldc; p.scale = scale; p.bias = bias; p.residual = residual; p.ldr = ldr; p.relu = relu;
-  p.atomic = accumulate; p.out_bf16 = out_bf16;
+  p.atomic = accumulate; p.out_bf16 = out_bf16; p.stats = stats;
   p.out_H = out_H; p.out_W = out_W; p.out_s = out_s; p.out_oh = out_oh; p.out_ow = out_ow;
   CUtensorMap ma, mb;
   {

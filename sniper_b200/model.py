@@ -144,11 +144,12 @@ class Conv:
                 self.frozen_b = torch.zeros(self.coutp, device=device)
 
     # ---- forward
-    def fwd(self, x, out=None, scale=None, shift=None, relu=False, residual=None):
-        """y = epi(conv(x)); epilogue order: *scale, +shift (or +bias), +residual, relu."""
+    def fwd(self, x, out=None, scale=None, shift=None, relu=False, residual=None, stats=None):
+        """y = epi(conv(x)); epilogue order: *scale, +shift (or +bias), +residual, relu; `stats` (a BN's
+        double[2C] scratch) receives the column sums of y for the consumer's train-mode statistics."""
         add = shift if shift is not None else self.b
         return ops.conv2d_nhwc(x, self.w, kh=self.k, kw=self.k, stride=self.stride, dil=self.dil, pad=self.pad, out=out,
-                               scale=scale, bias=add, residual=residual, relu=relu)
+                               scale=scale, bias=add, residual=residual, relu=relu, stats=stats)
 
     # ---- backward
     def prepare_bwd(self):
@@ -234,11 +235,19 @@ class BN:
                                   self.P.grad(self.name + "_gamma"), self.P.grad(self.name + "_beta"))
             self.st.gamma.fill_(1.0)
 
-    def fwd(self, x, cfg, relu=True):
+    def fwd(self, x, cfg, relu=True, have_stats=False):
+        """have_stats: the producer of x already accumulated sum / sum-of-squares into self.st.sums."""
         if self.frozen:
             return ops.affine_act(x, self.st.scale, self.st.shift, relu=relu)
-        ops.bn_stats(x, self.st, eps=cfg.bn_eps, momentum=cfg.bn_momentum)
+        if have_stats:
+            ops.bn_finalize(self.st, x.numel() // self.C, eps=cfg.bn_eps, momentum=cfg.bn_momentum)
+        else:
+            ops.bn_stats(x, self.st, eps=cfg.bn_eps, momentum=cfg.bn_momentum)
         return ops.affine_act(x, self.st.scale, self.st.shift, relu=relu)
+
+    def stats_sink(self):
+        """The scratch a producer may accumulate this BN's input statistics into (None for frozen BNs)."""
+        return None if self.frozen else self.st.sums
 
     def bwd(self, x, dy, add=None):
         return ops.bn_relu_bwd(x, dy, self.st, add=add)
@@ -278,26 +287,30 @@ class Unit:
     def bns(self):
         return [self.bn1, self.bn2, self.bn3]
 
-    def fwd(self, x, cfg, out=None):
+    def fwd(self, x, cfg, out=None, x_has_stats=False, next_bn=None):
+        """x_has_stats: the producer of x already accumulated bn1's statistics; next_bn: the BN that consumes
+        this unit's output (its statistics are accumulated by conv3's epilogue)."""
+        sink = next_bn.stats_sink() if next_bn is not None else None
         if self.frozen:
             a1 = self.bn1.fwd(x, cfg)
             a2 = self.conv1.fwd(a1, scale=self.bn2.st.scale, shift=self.bn2.st.shift, relu=True)
             a3 = self.conv2.fwd(a2, scale=self.bn3.st.scale, shift=self.bn3.st.shift, relu=True)
             res = x if self.dim_match else self.sc.fwd(a1)
-            return self.conv3.fwd(a3, out=out, residual=res)
-        a1 = self.bn1.fwd(x, cfg)
-        c1 = self.conv1.fwd(a1)
-        a2 = self.bn2.fwd(c1, cfg)
+            return self.conv3.fwd(a3, out=out, residual=res, stats=sink)
+        a1 = self.bn1.fwd(x, cfg, have_stats=x_has_stats)
+        c1 = self.conv1.fwd(a1, stats=self.bn2.stats_sink())
+        a2 = self.bn2.fwd(c1, cfg, have_stats=True)
         if self.deform:
             off = self.offset.fwd(a2)                                          # [N,H,W,96], 72 used
             col = ops.deform_im2col(a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)
-            c2 = ops.gemm_nt(col, self.conv2.w).view(a2.shape[0], a2.shape[1], a2.shape[2], self.mid)
+            c2 = ops.gemm_nt(col, self.conv2.w, stats=self.bn3.stats_sink())
+            c2 = c2.view(a2.shape[0], a2.shape[1], a2.shape[2], self.mid)
         else:
             off = col = None
-            c2 = self.conv2.fwd(a2)
-        a3 = self.bn3.fwd(c2, cfg)
+            c2 = self.conv2.fwd(a2, stats=self.bn3.stats_sink())
+        a3 = self.bn3.fwd(c2, cfg, have_stats=True)
         res = x if self.dim_match else self.sc.fwd(a1)
-        y = self.conv3.fwd(a3, out=out, residual=res)
+        y = self.conv3.fwd(a3, out=out, residual=res, stats=sink)
         self.saved = (x, a1, c1, a2, c2, a3, off, col)
         return y
 
@@ -443,13 +456,16 @@ class SniperResNet101:
         Hf = data.shape[2] // cfg.feat_stride
         cat = torch.empty(B, Hf, Hf, 3072, device=data.device)           # Concat(c4, c5) written in place
         last3 = n1 + n2 + n3 - 1
+        has_stats = False
         for i, u in enumerate(self.units):
             out = None
             if i == last3:
                 out = cat[..., :1024]
             elif i == len(self.units) - 1:
                 out = cat[..., 1024:]
-            x = u.fwd(x, cfg, out=out)
+            nxt = self.units[i + 1].bn1 if i + 1 < len(self.units) else None
+            x = u.fwd(x, cfg, out=out, x_has_stats=has_stats, next_bn=nxt)
+            has_stats = nxt is not None and not nxt.frozen
 
         # ---- RPN (get_rpn) + conv_new_1
         rpn = self.rpn_conv.fwd(cat, relu=True)

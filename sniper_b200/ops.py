@@ -177,7 +177,8 @@ def _dt(t):
     return TF32 if t.dtype == torch.float32 else BF16
 
 
-def gemm_nt(a, b, *, out=None, scale=None, bias=None, residual=None, relu=False, accumulate=False, out_bf16=False):
+def gemm_nt(a, b, *, out=None, scale=None, bias=None, residual=None, relu=False, accumulate=False, out_bf16=False,
+            stats=None):
     """C[M,N] = epi(A[M,K] @ B[N,K]^T) on tcgen05 tensor cores (fp32 storage -> TF32 math, or bf16)."""
     assert a.is_cuda and a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1] and a.dtype == b.dtype
     assert a.stride(1) == 1 and b.stride(1) == 1
@@ -187,7 +188,7 @@ def gemm_nt(a, b, *, out=None, scale=None, bias=None, residual=None, relu=False,
         out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
     check(lib().sniper_gemm_nt(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K, _dt(a),
                                _ptr(scale), _ptr(bias), _ptr(residual), 0 if residual is None else residual.stride(0),
-                               int(relu), int(accumulate), int(out_bf16), _stream()))
+                               int(relu), int(accumulate), int(out_bf16), _ptr(stats), _stream()))
     return out
 
 
@@ -199,7 +200,7 @@ def conv_taps(kh, kw, dil, pad):
 
 
 def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, bias=None, residual=None, relu=False,
-                accumulate=False, taps=None, out_hw=None, out_map=None):
+                accumulate=False, taps=None, out_hw=None, out_map=None, stats=None):
     """NHWC implicit-GEMM convolution.  x: [N,H,W,Cin]; w: [Cout, kh*kw*Cin] (tap-major, channel-minor)."""
     NB, H, W, Cin = x.shape
     Cout = w.shape[0]
@@ -221,7 +222,7 @@ def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, b
     check(lib().sniper_conv2d_nhwc(_ptr(x), x_ld, NB, H, W, Cin, _ptr(w), Cout, ntaps, dhp, dwp, stride, Ho, Wo,
                                    _ptr(out), _rows(out)[2], oH, oW, os_, ooh, oow, _dt(x), _ptr(scale), _ptr(bias),
                                    _ptr(residual), 0 if residual is None else _rows(residual)[2], int(relu),
-                                   int(accumulate), 0, _stream()))
+                                   int(accumulate), 0, _ptr(stats), _stream()))
     return out
 
 
@@ -283,6 +284,14 @@ def bn_stats(x, bn, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=True)
                                 int(fix_gamma), _ptr(bn.moving_mean if update_moving else None),
                                 _ptr(bn.moving_var if update_moving else None), _ptr(bn.sums), _ptr(bn.mean),
                                 _ptr(bn.invstd), _ptr(bn.scale), _ptr(bn.shift), _stream()))
+
+
+def bn_finalize(bn, M, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=True):
+    """Same as bn_stats when bn.sums was already accumulated by the producing conv's epilogue (stats=bn.sums)."""
+    check(lib().sniper_bn_finalize(_ptr(bn.sums), M, bn.C, _ptr(bn.gamma), _ptr(bn.beta), float(eps), float(momentum),
+                                   int(fix_gamma), _ptr(bn.moving_mean if update_moving else None),
+                                   _ptr(bn.moving_var if update_moving else None), _ptr(bn.mean), _ptr(bn.invstd),
+                                   _ptr(bn.scale), _ptr(bn.shift), _stream()))
 
 
 def bn_frozen(bn, eps=2e-5, fix_gamma=False):
