@@ -33,8 +33,9 @@ struct GemmParams {
   int num_kb;             // k-blocks per tile
   int stages;
   int tiles_m, tiles_n, splits;
-  int cluster;            // 1, or 2 = CTA pair along M sharing the B tile by TMA multicast
-  uint32_t stage_tx_bytes;  // bytes landing in one ring stage of ONE CTA (A + full B)
+  int cluster;            // 1 = cta_group::1 (128 x block_n tile per CTA); 2 = cta_group::2: a CTA pair computes a
+                          // 256 x block_n tile, each CTA stages its 128 rows of A and HALF of B in its own smem
+  uint32_t stage_tx_bytes;  // bytes credited to the (leader's) full barrier per ring stage
   // ---- producer geometry
   int elems_per_128B;     // 32 (tf32) / 64 (bf16)
   int cblocks;            // CONV: channel blocks per tap (Cin / elems_per_128B)
@@ -103,14 +104,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                               int c2, int c3, uint16_t cta_mask) {
-  // multicast: the box lands at the same shared-memory offset of every CTA in cta_mask and signals the
-  // mbarrier at the same offset in each of them
+// 2-SM (cta_group::2) loads: the box lands in THIS CTA's shared memory, the transaction bytes are credited to the
+// LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared), which is the one the MMA thread waits on.
+__device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -122,10 +123,44 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+// commit of cta_group::2 MMAs: one arrival on the barrier at the same offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(cta_mask)
                : "memory");
+}
+// arrive on the barrier at the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <int DT>
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (DT == 0) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+  }
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -235,19 +270,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], (uint32_t)p.cluster);   // every CTA sharing the stage must have consumed it
+      mbar_init(&empty_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 8);   // one arrival per epilogue warp
+      mbar_init(&tmem_empty_bar[s], 8u * (uint32_t)p.cluster);   // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_smem, tmem_cols);
+  if (p.cluster == 2) {
+    __syncthreads();
+    cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / peer-credited TMA
+    if (warp == 1) tmem_alloc_2sm(tmem_ptr_smem, tmem_cols);
+  } else if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, tmem_cols);
+  }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster == 2) cluster_sync_all();   // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -277,38 +317,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + kStageABytes;
-          mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
+          if (cta_rank == 0) mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
           const int kb = tc.split * p.num_kb + i;
           if (p.mode == MODE_GEMM) {
-            tma_load_4d(sa, &tma_a, &full_bar[s], kb * E, tc.tile_m * 128, 0, 0);
-            if (p.cluster == 2)
-              tma_load_4d_mc(sb + (size_t)cta_rank * p.b_box_bytes, &tma_b, &full_bar[s], kb * E,
-                             tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0, 3);
-            else
+            if (p.cluster == 2) {
+              tma_load_4d_2sm(sa, &tma_a, &full_bar[s], kb * E, tc.tile_m * 128, 0, 0);
+              tma_load_4d_2sm(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0);
+            } else {
+              tma_load_4d(sa, &tma_a, &full_bar[s], kb * E, tc.tile_m * 128, 0, 0);
               tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
+            }
           } else if (p.mode == MODE_CONV) {
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-            tma_load_4d(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
-                        oh0 * p.conv_stride + p.tap_dh[tap], n_img);
-            if (p.cluster == 2)
-              tma_load_4d_mc(sb + (size_t)cta_rank * p.b_box_bytes, &tma_b, &full_bar[s], kb * E,
-                             tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0, 3);
-            else
+            if (p.cluster == 2) {
+              tma_load_4d_2sm(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
+                              oh0 * p.conv_stride + p.tap_dh[tap], n_img);
+              tma_load_4d_2sm(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0);
+            } else {
+              tma_load_4d(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
+                          oh0 * p.conv_stride + p.tap_dh[tap], n_img);
               tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
+            }
           } else {
             // WGRAD: k-block = kp consecutive output pixels of one image row block
             const int pix0 = kb * p.kp;
             const int img = pix0 / (p.Ho * p.Wo);
             const int rem = pix0 - img * (p.Ho * p.Wo);
             const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
-            for (int j = 0; j < p.a_boxes; ++j)
-              tma_load_4d(sa + (size_t)j * p.a_box_bytes, &tma_a, &full_bar[s], tc.tile_m * 128 + j * E, pix0, 0, 0);
             if (p.cluster == 2) {
+              // each CTA: its 128 output channels of dY, and its half of the input-channel chunks of X
+              for (int j = 0; j < p.a_boxes; ++j)
+                tma_load_4d_2sm(sa + (size_t)j * p.a_box_bytes, &tma_a, &full_bar[s], tc.tile_m * 128 + j * E, pix0, 0, 0);
               const int hb = p.b_boxes >> 1;
-              for (int j = cta_rank * hb; j < (cta_rank + 1) * hb; ++j)
-                tma_load_4d_mc(sb + (size_t)j * p.b_box_bytes, &tma_b, &full_bar[s], wg_ci0 + j * E,
-                               ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img, 3);
+              for (int j = 0; j < hb; ++j)
+                tma_load_4d_2sm(sb + (size_t)j * p.b_box_bytes, &tma_b, &full_bar[s], wg_ci0 + (cta_rank * hb + j) * E,
+                                ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img);
             } else {
+              for (int j = 0; j < p.a_boxes; ++j)
+                tma_load_4d(sa + (size_t)j * p.a_box_bytes, &tma_a, &full_bar[s], tc.tile_m * 128 + j * E, pix0, 0, 0);
               for (int j = 0; j < p.b_boxes; ++j)
                 tma_load_4d(sb + (size_t)j * p.b_box_bytes, &tma_b, &full_bar[s], wg_ci0 + j * E,
                             ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img);
@@ -318,8 +364,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer
-    if (lane == 0) {
+    // =============================== MMA issuer (2-SM mode: the leader CTA issues for the pair)
+    if (lane == 0 && cta_rank == 0) {
       uint32_t it = 0, lt = 0;
       for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
         const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
@@ -335,14 +381,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t sb = sa + kStageABytes;
           const uint64_t adesc0 = make_smem_desc(sa, p.a_lbo, p.a_sbo, p.layout_type);
           const uint64_t bdesc0 = make_smem_desc(sb, p.b_lbo, p.b_sbo, p.layout_type);
-          for (int k = 0; k < p.mmas_per_kb; ++k) {
-            umma<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
-                     (i | k) != 0 ? 1u : 0u);
+          if (p.cluster == 2) {
+            for (int k = 0; k < p.mmas_per_kb; ++k)
+              umma_2sm<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
+                           (i | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[s], 3);   // frees the stage in both CTAs' rings
+          } else {
+            for (int k = 0; k < p.mmas_per_kb; ++k)
+              umma<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
+                       (i | k) != 0 ? 1u : 0u);
+            umma_commit(&empty_bar[s]);
           }
-          if (p.cluster == 2) umma_commit_mc(&empty_bar[s], 3);   // frees the stage in both CTAs' rings
-          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&tmem_full_bar[acc]);
+        if (p.cluster == 2) umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulator halves ready in both CTAs
+        else umma_commit(&tmem_full_bar[acc]);
       }
     }
   } else {
@@ -402,7 +454,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           // last chunk is in registers: hand the accumulator back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) {
+            if (p.cluster == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread waits on it
+            else mbar_arrive(&tmem_empty_bar[acc]);
+          }
         }
         const int n0 = col_base + c;
         if (n0 >= p.N) continue;                   // warp-uniform
@@ -507,11 +562,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster == 2) cluster_sync_all();   // nobody exits while the peer may still multicast into it
+  if (p.cluster == 2) cluster_sync_all();   // nobody frees TMEM or exits while the peer still uses the pair
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (p.cluster == 2) tmem_dealloc_2sm(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -619,16 +675,16 @@ int pick_block_n(int N) {
   return 128;
 }
 
-// Optional CTA pairs (cluster of 2 along M) sharing the B tile through TMA multicast (SNIPER_GEMM_CLUSTER=1).
-// Measured on B200 (profiles/gemm_shapes_r01_v3_multicast.md): correct but ~20 % SLOWER on the K-major shapes
-// -- multicast halves the L2 reads of B, but each SM still receives and re-reads the full 48 KB per k-block, and
-// the shared-memory port (96 B/clk TMA fill + 96 B/clk MMA operand reads vs 128 B/clk) is what bounds a
-// 128x256 fp32-operand tile; the pair only adds lock-step stalls.  Off by default; cta_group::2 is the fix.
+// cta_group::2: a CTA pair (cluster of 2, consecutive M tiles) issues 256 x block_n MMAs from the leader CTA; each
+// CTA stages its own 128 rows of A and HALF of B.  A 128 x 256 fp32-operand tile on ONE SM needs 96 B/clk of TMA fill
+// plus 96 B/clk of MMA operand reads from a 128 B/clk shared-memory port (<= 67 % tensor utilisation); the pair needs
+// 64 + 64.  (A plain cluster with TMA multicast of B was measured ~20 % slower, profiles/gemm_shapes_r01_v3_multicast.md:
+// it saves L2 reads, not shared-memory traffic.)  SNIPER_GEMM_2SM=0 disables it for A/B measurements.
 int pick_cluster(int tiles_m) {
   static int enabled = -1;
   if (enabled < 0) {
-    const char* e = getenv("SNIPER_GEMM_CLUSTER");
-    enabled = (e && e[0] == '1') ? 1 : 0;
+    const char* e = getenv("SNIPER_GEMM_2SM");
+    enabled = (e && e[0] == '0') ? 0 : 1;
   }
   return (enabled && tiles_m >= 2) ? 2 : 1;
 }
@@ -637,15 +693,15 @@ void fill_kmajor(GemmParams& p, int dtype, int block_n) {
   p.dtype = dtype;
   p.block_n = block_n;
   p.elems_per_128B = dtype == DT_TF32 ? 32 : 64;
-  p.idesc = make_idesc(dtype, 0, 0, 128, block_n);
+  p.idesc = make_idesc(dtype, 0, 0, 128 * p.cluster, block_n);
   p.a_lbo = 1; p.a_sbo = 64; p.b_lbo = 1; p.b_sbo = 64;  // SBO = 8 rows x 128 B
   p.a_kadv = 2; p.b_kadv = 2;                            // 32 B per UMMA_K step
   p.layout_type = 2;
   p.mmas_per_kb = 4;
   p.a_boxes = 1; p.b_boxes = 1;
   p.a_box_bytes = kStageABytes;
-  p.b_box_bytes = (uint32_t)(block_n / p.cluster) * 128u;   // each CTA of a pair loads (and multicasts) half of B
-  p.stage_tx_bytes = kStageABytes + (uint32_t)block_n * 128u;
+  p.b_box_bytes = (uint32_t)(block_n / p.cluster) * 128u;   // 2-SM: each CTA stages half of the B rows
+  p.stage_tx_bytes = (uint32_t)p.cluster * (kStageABytes + p.b_box_bytes);
   p.stages = pick_stages(block_n);
 }
 
@@ -797,7 +853,8 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, long dy_ld, const void* X, long x_l
   p.a_boxes = 128 / E; p.b_boxes = bn / E;
   p.a_box_bytes = chunk_bytes; p.b_box_bytes = chunk_bytes;
   p.cluster = (p.b_boxes % 2 == 0) ? pick_cluster(Cout / 128 + (Cout % 128 ? 1 : 0)) : 1;
-  p.stage_tx_bytes = (uint32_t)(p.a_boxes + p.b_boxes) * chunk_bytes;
+  p.stage_tx_bytes = (uint32_t)p.cluster * (uint32_t)(p.a_boxes + p.b_boxes / p.cluster) * chunk_bytes;
+  p.idesc = make_idesc(dtype, 1, 1, 128 * p.cluster, bn);
   p.stages = pick_stages(bn);
   p.ntaps = ntaps;
   for (int t = 0; t < ntaps; ++t) { p.tap_dh[t] = tap_dh[t]; p.tap_dw[t] = tap_dw[t]; }

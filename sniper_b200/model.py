@@ -40,6 +40,9 @@ class Cfg:
     filter_list = (64, 256, 512, 1024, 2048)
     grad_scale = 1.0                  # TRAIN.scale only applies to fp16
     wgrad_splits = 0                  # 0 = choose per layer (fill one wave of 148 persistent CTAs)
+    # BN statistics accumulated by the producing conv's epilogue (warp-shuffle column sums + double REDs).
+    # Measured on B200: +6.5 ms of tcgen05 time per step vs 1.8 ms saved in colsum kernels -> off by default.
+    fuse_bn_stats = False
 
 
 # ------------------------------------------------------------------------------------------------
@@ -245,9 +248,11 @@ class BN:
             ops.bn_stats(x, self.st, eps=cfg.bn_eps, momentum=cfg.bn_momentum)
         return ops.affine_act(x, self.st.scale, self.st.shift, relu=relu)
 
+    fuse = False   # set from Cfg.fuse_bn_stats by SniperResNet101
+
     def stats_sink(self):
-        """The scratch a producer may accumulate this BN's input statistics into (None for frozen BNs)."""
-        return None if self.frozen else self.st.sums
+        """The scratch a producer may accumulate this BN's input statistics into (None: compute them here)."""
+        return None if (self.frozen or not BN.fuse) else self.st.sums
 
     def bwd(self, x, dy, add=None):
         return ops.bn_relu_bwd(x, dy, self.st, add=add)
@@ -297,9 +302,10 @@ class Unit:
             a3 = self.conv2.fwd(a2, scale=self.bn3.st.scale, shift=self.bn3.st.shift, relu=True)
             res = x if self.dim_match else self.sc.fwd(a1)
             return self.conv3.fwd(a3, out=out, residual=res, stats=sink)
-        a1 = self.bn1.fwd(x, cfg, have_stats=x_has_stats)
+        fused = BN.fuse
+        a1 = self.bn1.fwd(x, cfg, have_stats=x_has_stats and fused)
         c1 = self.conv1.fwd(a1, stats=self.bn2.stats_sink())
-        a2 = self.bn2.fwd(c1, cfg, have_stats=True)
+        a2 = self.bn2.fwd(c1, cfg, have_stats=fused)
         if self.deform:
             off = self.offset.fwd(a2)                                          # [N,H,W,96], 72 used
             col = ops.deform_im2col(a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)
@@ -308,7 +314,7 @@ class Unit:
         else:
             off = col = None
             c2 = self.conv2.fwd(a2, stats=self.bn3.stats_sink())
-        a3 = self.bn3.fwd(c2, cfg, have_stats=True)
+        a3 = self.bn3.fwd(c2, cfg, have_stats=fused)
         res = x if self.dim_match else self.sc.fwd(a1)
         y = self.conv3.fwd(a3, out=out, residual=res, stats=sink)
         self.saved = (x, a1, c1, a2, c2, a3, off, col)
@@ -357,6 +363,7 @@ class SniperResNet101:
         self.cfg = cfg or Cfg()
         cfg = self.cfg
         self.device = device
+        BN.fuse = bool(cfg.fuse_bn_stats)
         P = self.P = ParamStore()
         fl = cfg.filter_list
         # ---- frozen stem: bn_data, conv0, bn0 (resnetc4 :402-408)

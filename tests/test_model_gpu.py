@@ -215,3 +215,20 @@ def test_full_training_step_smoke():
     assert torch.isfinite(l1).all()
     assert float(l1[2]) < float(l0[2])          # R-CNN classification loss goes down on the same batch
     assert out["rois"].shape == (600, 5) and out["cls_prob"].shape == (600, 81)
+
+
+def test_fused_bn_statistics_match_separate_pass():
+    """Column sums accumulated by the tcgen05 epilogue (stats=) == the colsum kernel's statistics."""
+    import torch
+    from sniper_b200 import model, ops
+    torch.manual_seed(11)
+    P, c = _mk_conv(128, 256, 3, 1, 1, 1)
+    x = torch.randn(2, 32, 32, 128, device="cuda")
+    a = ops.BNState(256, "cuda")
+    b = ops.BNState(256, "cuda")
+    y = c.fwd(x, stats=a.sums)
+    ops.bn_finalize(a, y.numel() // 256, eps=2e-5, momentum=0.9)
+    ops.bn_stats(y, b, eps=2e-5, momentum=0.9)
+    assert (a.mean - b.mean).abs().max().item() < 1e-5
+    assert ((a.invstd - b.invstd).abs() / b.invstd).max().item() < 1e-4
+    assert float(a.sums.abs().sum()) == 0.0
