@@ -242,7 +242,8 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int 
 // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the smem ring runs across tile
 // boundaries and the accumulator is double-buffered in TMEM (2 x block_n columns), so the epilogue of tile i
 // overlaps the TMA + MMA of tile i+1.
-template <int DT>
+// CG = tcgen05 cta_group of this instantiation (a kernel may not mix cta_group::1 and ::2 instructions).
+template <int DT, int CG>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ GemmParams p) {
@@ -260,10 +261,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t acc_cols = p.block_n <= 32 ? 32u : (p.block_n <= 64 ? 64u : (p.block_n <= 128 ? 128u : 256u));
   const uint32_t tmem_cols = 2u * acc_cols;
-  const int cta_rank = p.cluster == 2 ? (int)cluster_ctarank() : 0;
-  const int unit0 = p.cluster == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_step = p.cluster == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int total_tiles = ((p.tiles_m + p.cluster - 1) / p.cluster) * p.tiles_n * p.splits;   // work units
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int unit0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int total_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n * p.splits;   // work units
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -274,12 +275,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 8u * (uint32_t)p.cluster);   // one arrival per epilogue warp (of both CTAs)
+      mbar_init(&tmem_empty_bar[s], 8u * (uint32_t)CG);   // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (p.cluster == 2) {
+  if (CG == 2) {
     __syncthreads();
     cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / peer-credited TMA
     if (warp == 1) tmem_alloc_2sm(tmem_ptr_smem, tmem_cols);
@@ -320,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (cta_rank == 0) mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
           const int kb = tc.split * p.num_kb + i;
           if (p.mode == MODE_GEMM) {
-            if (p.cluster == 2) {
+            if (CG == 2) {
               tma_load_4d_2sm(sa, &tma_a, &full_bar[s], kb * E, tc.tile_m * 128, 0, 0);
               tma_load_4d_2sm(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0);
             } else {
@@ -329,7 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           } else if (p.mode == MODE_CONV) {
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-            if (p.cluster == 2) {
+            if (CG == 2) {
               tma_load_4d_2sm(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
                               oh0 * p.conv_stride + p.tap_dh[tap], n_img);
               tma_load_4d_2sm(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0);
@@ -344,7 +345,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int img = pix0 / (p.Ho * p.Wo);
             const int rem = pix0 - img * (p.Ho * p.Wo);
             const int oh = rem / p.Wo, ow = rem - oh * p.Wo;
-            if (p.cluster == 2) {
+            if (CG == 2) {
               // each CTA: its 128 output channels of dY, and its half of the input-channel chunks of X
               for (int j = 0; j < p.a_boxes; ++j)
                 tma_load_4d_2sm(sa + (size_t)j * p.a_box_bytes, &tma_a, &full_bar[s], tc.tile_m * 128 + j * E, pix0, 0, 0);
@@ -381,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t sb = sa + kStageABytes;
           const uint64_t adesc0 = make_smem_desc(sa, p.a_lbo, p.a_sbo, p.layout_type);
           const uint64_t bdesc0 = make_smem_desc(sb, p.b_lbo, p.b_sbo, p.layout_type);
-          if (p.cluster == 2) {
+          if (CG == 2) {
             for (int k = 0; k < p.mmas_per_kb; ++k)
               umma_2sm<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
                            (i | k) != 0 ? 1u : 0u);
@@ -393,7 +394,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             umma_commit(&empty_bar[s]);
           }
         }
-        if (p.cluster == 2) umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulator halves ready in both CTAs
+        if (CG == 2) umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulator halves ready in both CTAs
         else umma_commit(&tmem_full_bar[acc]);
       }
     }
@@ -455,7 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
-            if (p.cluster == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread waits on it
+            if (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread waits on it
             else mbar_arrive(&tmem_empty_bar[acc]);
           }
         }
@@ -562,11 +563,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (p.cluster == 2) cluster_sync_all();   // nobody frees TMEM or exits while the peer still uses the pair
+  if (CG == 2) cluster_sync_all();   // nobody frees TMEM or exits while the peer still uses the pair
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    if (p.cluster == 2) tmem_dealloc_2sm(tmem_base, tmem_cols);
+    if (CG == 2) tmem_dealloc_2sm(tmem_base, tmem_cols);
     else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
@@ -639,13 +640,13 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
   const long max_units = sn::kNumSMs / p.cluster;
   dim3 grid((unsigned)((units < max_units ? units : max_units) * p.cluster), 1, 1);
   const size_t smem = smem_bytes(p.stages, p.block_n);
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[p.dtype]) {
-    if (p.dtype == DT_TF32)
-      SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    else
-      SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done[p.dtype] = true;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_TF32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_TF32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_BF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -660,10 +661,13 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  if (p.dtype == DT_TF32)
-    SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_TF32>, ma, mb, p));
-  else
-    SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_BF16>, ma, mb, p));
+  if (p.dtype == DT_TF32) {
+    if (p.cluster == 2) SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_TF32, 2>, ma, mb, p));
+    else SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_TF32, 1>, ma, mb, p));
+  } else {
+    if (p.cluster == 2) SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_BF16, 2>, ma, mb, p));
+    else SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_BF16, 1>, ma, mb, p));
+  }
   SN_LAUNCH_CHECK();
   return 0;
 }
