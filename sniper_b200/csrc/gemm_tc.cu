@@ -672,23 +672,43 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
   return 0;
 }
 
-int pick_block_n(int N) {
-  if (N <= 64) return 64;
-  if (N <= 128) return 128;
-  if (N % 256 == 0 || N > 1024) return 256;
-  return 128;
+// Tile width: the persistent grid has 148 CTAs, so a launch costs rounds(bn) = ceil(tiles_m * ceil(N/bn) / 148) tile
+// times; a tile costs ~ (bn + overhead) MMA columns.  E.g. M = 20480 (160 M-tiles), N = 256: bn = 256 -> 2 rounds
+// x 256 = 512, bn = 128 -> 3 rounds x 128 = 384.  SNIPER_GEMM_BN=<64|128|256> forces a width (A/B measurements).
+int pick_block_n(int N, long tiles_m) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("SNIPER_GEMM_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  int cap = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  if (forced == 64 || forced == 128 || forced == 256) return forced < cap ? forced : cap;
+  int best = cap;
+  long best_cost = -1;
+  for (int bn = cap; bn >= 64; bn >>= 1) {
+    const long tiles = tiles_m * ((N + bn - 1) / bn);
+    const long rounds = (tiles + sn::kNumSMs - 1) / sn::kNumSMs;
+    const long cost = rounds * (bn + 48);   // 48 columns ~ per-tile prologue/epilogue exposure
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
 }
 
 // cta_group::2: a CTA pair (cluster of 2, consecutive M tiles) issues 256 x block_n MMAs from the leader CTA; each
 // CTA stages its own 128 rows of A and HALF of B.  A 128 x 256 fp32-operand tile on ONE SM needs 96 B/clk of TMA fill
 // plus 96 B/clk of MMA operand reads from a 128 B/clk shared-memory port (<= 67 % tensor utilisation); the pair needs
 // 64 + 64.  (A plain cluster with TMA multicast of B was measured ~20 % slower, profiles/gemm_shapes_r01_v3_multicast.md:
-// it saves L2 reads, not shared-memory traffic.)  SNIPER_GEMM_2SM=0 disables it for A/B measurements.
+// it saves L2 reads, not shared-memory traffic.)  Measured (profiles/gemm_shapes_r01_v4_2sm.md): correct, but the
+// K-major shapes run 10-15 % slower than the 1-SM kernel (the largest conv already reaches 674 TFLOP/s = 79 % of
+// the measured TF32 burst peak with cta_group::1, i.e. it is not operand-bound), so it is opt-in: SNIPER_GEMM_2SM=1.
 int pick_cluster(int tiles_m) {
   static int enabled = -1;
   if (enabled < 0) {
     const char* e = getenv("SNIPER_GEMM_2SM");
-    enabled = (e && e[0] == '0') ? 0 : 1;
+    enabled = (e && e[0] == '1') ? 1 : 0;   // measured 8 % slower overall on this workload: opt-in
   }
   return (enabled && tiles_m >= 2) ? 2 : 1;
 }
@@ -736,7 +756,7 @@ int sniper_gemm_nt(const void* A, long lda, const void* B, long ldb, float* C, l
   SN_CHECK((lda * esz) % 16 == 0 && (ldb * esz) % 16 == 0, "gemm: row strides must be 16-byte multiples");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  const int bn = pick_block_n(N);
+  const int bn = pick_block_n(N, sn::div_up(M, 128));
   p.cluster = pick_cluster(sn::div_up(M, 128));
   fill_kmajor(p, dtype, bn);
   p.mode = MODE_GEMM; p.M = M; p.N = N; p.num_kb = K / E;
@@ -781,7 +801,7 @@ int sniper_conv2d_nhwc(const void* X, long x_ld, int NB, int H, int W, int Cin, 
   SN_CHECK(tile_w * stride <= 256, "conv: TMA box too wide");
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  const int bn = pick_block_n(Cout);
+  const int bn = pick_block_n(Cout, (long)NB * (Wo / tile_w) * sn::div_up(Ho, tile_h));
   p.cluster = pick_cluster(NB * (Wo / tile_w) * sn::div_up(Ho, tile_h));
   fill_kmajor(p, dtype, bn);
   p.mode = MODE_CONV; p.N = Cout; p.cblocks = Cin / E; p.ntaps = ntaps; p.num_kb = ntaps * p.cblocks;
