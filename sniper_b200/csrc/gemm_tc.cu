@@ -23,8 +23,10 @@ namespace {
 
 enum { MODE_GEMM = 0, MODE_CONV = 1, MODE_WGRAD = 2 };
 enum { DT_TF32 = 0, DT_BF16 = 1 };
+enum { EPI_DIRECT = 0, EPI_STATS = 1, EPI_TMA = 2 };
 constexpr int kMaxTaps = 16;
 constexpr int kStageABytes = 128 * 128;  // 128 rows x 128 B
+constexpr int kStagingBytes = 8 * 4096;  // epilogue: one 32-row x 128-byte swizzled chunk per epilogue warp
 
 struct GemmParams {
   int mode, dtype;
@@ -67,6 +69,7 @@ struct GemmParams {
   // row mapping for CONV: output pixel (n,oh,ow) -> row ((n*out_H + oh*out_s + out_oh)*out_W + ow*out_s + out_ow)
   int out_H, out_W, out_s, out_oh, out_ow;
   int out_bf16;           // store bf16 instead of fp32
+  int epi_tma;            // 1: epilogue stages 32 x 32 chunks in shared memory and stores / reduces them by TMA (tma_c)
   double* stats;          // optional [2*N]: += per-column sum and sum of squares of the stored values
                           // (train-mode BatchNorm statistics of the consumer, fused into the producer)
 };
@@ -114,6 +117,20 @@ __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMa
       ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// epilogue: shared -> global tile store / reduction through the TMA (bulk async-group completion)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -224,6 +241,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// one lane of a converged warp (the same one every time for a full mask)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 struct TileCoord {
   int tile_m, tile_n, split;
 };
@@ -243,16 +267,20 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int 
 // boundaries and the accumulator is double-buffered in TMEM (2 x block_n columns), so the epilogue of tile i
 // overlaps the TMA + MMA of tile i+1.
 // CG = tcgen05 cta_group of this instantiation (a kernel may not mix cta_group::1 and ::2 instructions).
-template <int DT, int CG>
+// EPI = epilogue variant (separate instantiations: 10 warps cap the kernel at 168 registers/thread, and sharing one
+// body made the plain epilogue spill -- measured +3.8 ms/step): EPI_DIRECT = per-lane row stores (any alignment,
+// bf16 output, ragged N), EPI_STATS = EPI_DIRECT + fused BatchNorm statistics, EPI_TMA = staged TMA store / reduce.
+template <int DT, int CG, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ GemmParams p) {
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages x (A 16KB | B block_n*128B)] | barriers
+  // carve: [stages x (A 16KB | B block_n*128B)] | epilogue staging 8 warps x 4 KB | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t stage_bytes = kStageABytes + b_stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* staging = smem + (size_t)p.stages * stage_bytes;   // 1024-byte aligned (stage sizes are multiples of 1 KB)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
@@ -269,6 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (EPI == EPI_TMA) tma_prefetch_desc(&tma_c);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -293,10 +322,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // =============================== TMA producer
-    if (lane == 0) {
+    // =============================== TMA producer.  The whole warp walks the (warp-uniform) loops so that indices and
+    // coordinates live in uniform registers; one elected lane issues the copies.
+    {
+      const bool leader = elect_one();
       const int E = p.elems_per_128B;
-      uint32_t it = 0;  // global k-block counter across tiles -> ring slot / phase
+      int s = 0;          // ring slot / phase, carried across tiles
+      uint32_t ph = 0;
       for (int t = unit0; t < total_tiles; t += unit_step) {
         const TileCoord tc = tile_coord(p, t, cta_rank);
         int n_img = 0, oh0 = 0, ow0 = 0;
@@ -312,15 +344,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           wg_tap = tc.tile_n / p.wg_cin_blocks;
           wg_ci0 = (tc.tile_n - wg_tap * p.wg_cin_blocks) * p.block_n;
         }
-        for (int i = 0; i < p.num_kb; ++i, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
+        for (int i = 0; i < p.num_kb; ++i) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + kStageABytes;
-          if (cta_rank == 0) mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
           const int kb = tc.split * p.num_kb + i;
-          if (p.mode == MODE_GEMM) {
+          if (!leader) {
+            // nothing to issue
+          } else if (p.mode == MODE_GEMM) {
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
             if (CG == 2) {
               tma_load_4d_2sm(sa, &tma_a, &full_bar[s], kb * E, tc.tile_m * 128, 0, 0);
               tma_load_4d_2sm(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0);
@@ -329,6 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
             }
           } else if (p.mode == MODE_CONV) {
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
             if (CG == 2) {
               tma_load_4d_2sm(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
@@ -341,6 +374,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           } else {
             // WGRAD: k-block = kp consecutive output pixels of one image row block
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
             const int pix0 = kb * p.kp;
             const int img = pix0 / (p.Ho * p.Wo);
             const int rem = pix0 - img * (p.Ho * p.Wo);
@@ -361,41 +395,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             ow * p.conv_stride + p.tap_dw[wg_tap], oh * p.conv_stride + p.tap_dh[wg_tap], img);
             }
           }
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer (2-SM mode: the leader CTA issues for the pair)
-    if (lane == 0 && cta_rank == 0) {
-      uint32_t it = 0, lt = 0;
+    // =============================== MMA issuer (2-SM mode: the leader CTA issues for the pair).  All 32 lanes run the
+    // loop -- descriptors and ring indices stay in uniform registers -- and one elected lane issues MMAs + commits
+    // (with `if (lane == 0)` around the loop ptxas kept everything in vector registers and re-broadcast five
+    // values per tcgen05.mma: the issue loop, not the tensor pipe, bounded the 128-wide tiles).
+    if (cta_rank == 0) {
+      const bool leader = elect_one();
+      int s = 0;
+      uint32_t ph = 0, lt = 0;
       for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
         const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_cols;
-        for (int i = 0; i < p.num_kb; ++i, ++it) {
-          const int s = it % p.stages;
-          const uint32_t ph = (it / p.stages) & 1u;
+        for (int i = 0; i < p.num_kb; ++i) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
           const uint32_t sb = sa + kStageABytes;
           const uint64_t adesc0 = make_smem_desc(sa, p.a_lbo, p.a_sbo, p.layout_type);
           const uint64_t bdesc0 = make_smem_desc(sb, p.b_lbo, p.b_sbo, p.layout_type);
-          if (CG == 2) {
-            for (int k = 0; k < p.mmas_per_kb; ++k)
-              umma_2sm<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
-                           (i | k) != 0 ? 1u : 0u);
-            umma_commit_2sm(&empty_bar[s], 3);   // frees the stage in both CTAs' rings
-          } else {
-            for (int k = 0; k < p.mmas_per_kb; ++k)
-              umma<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
-                       (i | k) != 0 ? 1u : 0u);
-            umma_commit(&empty_bar[s]);
+          if (leader) {
+            if (CG == 2) {
+              for (int k = 0; k < p.mmas_per_kb; ++k)
+                umma_2sm<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
+                             (i | k) != 0 ? 1u : 0u);
+              umma_commit_2sm(&empty_bar[s], 3);   // frees the stage in both CTAs' rings
+            } else {
+              for (int k = 0; k < p.mmas_per_kb; ++k)
+                umma<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
+                         (i | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[s]);
+            }
           }
+          if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-        if (CG == 2) umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulator halves ready in both CTAs
-        else umma_commit(&tmem_full_bar[acc]);
+        if (leader) {
+          if (CG == 2) umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulator halves ready in both CTAs
+          else umma_commit(&tmem_full_bar[acc]);
+        }
       }
     }
   } else {
@@ -428,6 +471,115 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         col_base = tap * (p.wg_cin_blocks * p.block_n) + (tc.tile_n - tap * p.wg_cin_blocks) * p.block_n;
       }
       col_base += half * cols_per_warp;
+      if (EPI == EPI_TMA) {
+        // ---------------- TMA-store epilogue.  Per 32-column chunk a warp transposes its 32 x 32 accumulator
+        // block through a 128B-swizzled 4 KB staging buffer and ONE lane stores (or reduce-adds) it with a bulk
+        // tensor copy: global writes are full 128-byte lines instead of 32 row-strided 16-byte pieces per
+        // instruction, rows outside the tensor are clipped by the TMA.  The residual is read coalesced (4 rows x
+        // 128 B per instruction) into the same buffer one chunk ahead.
+        uint8_t* stg = staging + (size_t)(warp - 2) * 4096;
+        const uint32_t stg_u32 = smem_u32(stg);
+        const int sw = lane & 7;
+        int c_ow = 0, c_oh = 0, c_n = 0;        // TMA coordinates of this warp's 32 rows
+        int rowi[8];                            // residual rows read by this lane (coalesced layout), -1 = none
+        const bool tile_ok = tc.tile_m < p.tiles_m;
+        if (p.mode == MODE_CONV) {
+          const int n_img = tc.tile_m / p.tiles_per_img;
+          const int r = tc.tile_m - n_img * p.tiles_per_img;
+          const int th = r / p.tiles_w;
+          const int oh0 = th * p.tile_h, ow0 = (r - th * p.tiles_w) * p.tile_w;
+          const int m0 = q * 32;
+          c_n = n_img; c_oh = oh0 + m0 / p.tile_w; c_ow = ow0 + m0 % p.tile_w;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = m0 + i * 4 + (lane >> 3);
+            const int oh = oh0 + m / p.tile_w, ow = ow0 + m % p.tile_w;
+            rowi[i] = (oh < p.Ho && tile_ok)
+                          ? ((n_img * p.out_H + oh * p.out_s + p.out_oh) * p.out_W + ow * p.out_s + p.out_ow) : -1;
+          }
+        } else {
+          c_ow = tc.tile_m * 128 + q * 32;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = c_ow + i * 4 + (lane >> 3);
+            rowi[i] = (rr < p.M && tile_ok) ? rr : -1;
+          }
+        }
+        const bool has_res = p.residual != nullptr;
+        float4 rn[8];
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            rn[i] = (rowi[i] >= 0 && col_base < p.N)
+                        ? __ldg(reinterpret_cast<const float4*>(p.residual + (long)rowi[i] * p.ldr + col_base) + sw)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        mbar_wait(&tmem_full_bar[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc * acc_cols + (uint32_t)(half * cols_per_warp) + ((uint32_t)(q * 32) << 16);
+        for (int c = 0; c < cols_per_warp; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_acc + (uint32_t)c, v);
+          if (c + 32 >= cols_per_warp) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+              else mbar_arrive(&tmem_empty_bar[acc]);
+            }
+          }
+          const int n0 = col_base + c;
+          if (n0 >= p.N || !tile_ok) continue;       // warp-uniform
+          // the previous chunk's bulk store must have finished READING the staging buffer
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = i * 4 + (lane >> 3);
+              *reinterpret_cast<float4*>(stg + r * 128 + ((sw ^ (r & 7)) << 4)) = rn[i];
+            }
+            if (c + 32 < cols_per_warp && n0 + 32 < p.N) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                rn[i] = rowi[i] >= 0
+                            ? __ldg(reinterpret_cast<const float4*>(p.residual + (long)rowi[i] * p.ldr + n0 + 32) + sw)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                   __uint_as_float(v[4 * j + 3]));
+            if (p.scale) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + j);
+              f.x *= s4.x; f.y *= s4.y; f.z *= s4.z; f.w *= s4.w;
+            }
+            if (p.bias) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+              f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
+            }
+            float4* slot = reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ sw) << 4));
+            if (has_res) {
+              const float4 r4 = *slot;
+              f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
+            }
+            if (p.relu) {
+              f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
+            }
+            *slot = f;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.atomic) tma_reduce_add_4d(&tma_c, stg, n0, c_ow, c_oh, c_n);
+            else tma_store_4d(&tma_c, stg, n0, c_ow, c_oh, c_n);
+            bulk_commit();
+          }
+        }
+        continue;
+      }
       const float* rbase = (p.residual && row_ok) ? p.residual + row * p.ldr + col_base : nullptr;
       const bool r_vec = rbase && ((reinterpret_cast<uintptr_t>(rbase) & 15) == 0) && (col_base + cols_per_warp <= p.N);
       // residual of the first chunk is requested before the accumulator is even ready
@@ -462,7 +614,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         const int n0 = col_base + c;
         if (n0 >= p.N) continue;                   // warp-uniform
-        if (!row_ok && !p.stats) continue;         // with fused statistics every lane stays for the shuffles
+        if (!row_ok && EPI != EPI_STATS) continue;         // with fused statistics every lane stays for the shuffles
         float* crow = p.C + row * p.ldc + n0;
         const bool full = (n0 + 32 <= p.N);
         float f[32];
@@ -509,7 +661,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         }
-        if (p.stats) {
+        if (EPI == EPI_STATS) {
           // column sums over the 32 rows of this warp by recursive halving: after the loop lane l holds column l
           float sm[32], sq[32];
 #pragma unroll
@@ -561,6 +713,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   }
+  if (EPI == EPI_TMA && warp >= 2 && lane == 0) bulk_wait_read0();   // staging buffers are read by in-flight bulk stores
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();   // nobody frees TMEM or exits while the peer still uses the pair
@@ -626,26 +779,66 @@ uint32_t make_idesc(int dtype, int a_mn_major, int b_mn_major, int M, int N) {
 int pick_stages(int block_n) {
   // one persistent CTA per SM: fill shared memory with the operand ring
   const int stage = kStageABytes + block_n * 128;
-  int s = (210 * 1024) / stage;
+  int s = (227 * 1024 - kStagingBytes - 1024 - 256) / stage;
   return s > 8 ? 8 : s;
 }
 
 size_t smem_bytes(int stages, int block_n) {
-  return (size_t)stages * (kStageABytes + block_n * 128) + 1024 + 256;
+  return (size_t)stages * (kStageABytes + block_n * 128) + kStagingBytes + 1024 + 256;
+}
+
+// Output tensor map for the TMA-store epilogue: fp32, 4-D (cols, w, h, n) with the row mapping's strides; box =
+// 32 columns x the 32 rows one epilogue warp owns.  Returns 0 and sets p.epi_tma = 1 when the epilogue qualifies.
+int make_out_map(CUtensorMap* mc, GemmParams& p) {
+  const char* e = getenv("SNIPER_GEMM_TMA_STORE");   // read per call: the parity tests flip it between launches
+  const bool enabled = !(e && e[0] == '0');
+  memset(mc, 0, sizeof(*mc));
+  p.epi_tma = 0;
+  const bool ok = enabled && !p.out_bf16 && !p.stats && p.N % 32 == 0 && p.ldc % 4 == 0 &&
+                  (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
+                  (!p.residual || (p.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) &&
+                  (!p.scale || (reinterpret_cast<uintptr_t>(p.scale) & 15) == 0) &&
+                  (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+  if (!ok) return 0;
+  const uint32_t ones[4] = {1, 1, 1, 1};
+  const uint64_t rb = (uint64_t)p.ldc * 4;
+  if (p.mode == MODE_CONV) {
+    const uint32_t bw = p.tile_w < 32 ? (uint32_t)p.tile_w : 32u;
+    const uint64_t d[4] = {(uint64_t)p.N, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)(p.M / (p.Ho * p.Wo))};
+    const uint64_t st[3] = {rb * p.out_s, rb * p.out_s * p.out_W, rb * p.out_H * p.out_W};
+    const uint32_t b[4] = {32, bw, 32u / bw, 1};
+    const float* base = p.C + ((long)p.out_oh * p.out_W + p.out_ow) * p.ldc;
+    if (make_map(mc, DT_TF32, base, d, st, b, ones)) return -1;
+  } else {
+    const uint64_t d[4] = {(uint64_t)p.N, (uint64_t)p.M, 1, 1};
+    const uint64_t st[3] = {rb, rb * p.M, rb * p.M};
+    const uint32_t b[4] = {32, 32, 1, 1};
+    if (make_map(mc, DT_TF32, p.C, d, st, b, ones)) return -1;
+  }
+  p.epi_tma = 1;
+  return 0;
 }
 
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 tiles, cudaStream_t stream) {
+  CUtensorMap mc;
+  if (make_out_map(&mc, p)) return -1;
   p.tiles_m = (int)tiles.x; p.tiles_n = (int)tiles.y; p.splits = (int)tiles.z;
   const long units = (long)((tiles.x + p.cluster - 1) / p.cluster) * tiles.y * tiles.z;
   const long max_units = sn::kNumSMs / p.cluster;
   dim3 grid((unsigned)((units < max_units ? units : max_units) * p.cluster), 1, 1);
   const size_t smem = smem_bytes(p.stages, p.block_n);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+  static const KernelFn kernels[2][2][3] = {
+      {{gemm_tc_kernel<DT_TF32, 1, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 1, EPI_STATS>, gemm_tc_kernel<DT_TF32, 1, EPI_TMA>},
+       {gemm_tc_kernel<DT_TF32, 2, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 2, EPI_STATS>, gemm_tc_kernel<DT_TF32, 2, EPI_TMA>}},
+      {{gemm_tc_kernel<DT_BF16, 1, EPI_DIRECT>, gemm_tc_kernel<DT_BF16, 1, EPI_STATS>, gemm_tc_kernel<DT_BF16, 1, EPI_TMA>},
+       {gemm_tc_kernel<DT_BF16, 2, EPI_DIRECT>, gemm_tc_kernel<DT_BF16, 2, EPI_STATS>, gemm_tc_kernel<DT_BF16, 2, EPI_TMA>}}};
   static bool attr_done = false;
   if (!attr_done) {
-    SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_TF32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_TF32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_BF16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SN_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<DT_BF16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b)
+        for (int c = 0; c < 3; ++c)
+          SN_CUDA(cudaFuncSetAttribute(kernels[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
   cudaLaunchConfig_t cfg;
@@ -660,41 +853,32 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  if (p.dtype == DT_TF32) {
-    if (p.cluster == 2) SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_TF32, 2>, ma, mb, p));
-    else SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_TF32, 1>, ma, mb, p));
-  } else {
-    if (p.cluster == 2) SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_BF16, 2>, ma, mb, p));
-    else SN_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<DT_BF16, 1>, ma, mb, p));
+  {
+    const char* e = getenv("SNIPER_GEMM_CLUSTER_ATTR");   // A/B: force the (1,1,1) cluster attribute on 1-SM launches
+    cfg.numAttrs = (p.cluster > 1 || (e && e[0] == '1')) ? 1 : 0;
   }
+  SN_CUDA(cudaLaunchKernelEx(&cfg, kernels[p.dtype == DT_TF32 ? 0 : 1][p.cluster == 2 ? 1 : 0][p.epi_tma ? EPI_TMA : (p.stats ? EPI_STATS : EPI_DIRECT)], ma, mb, mc, p));
   SN_LAUNCH_CHECK();
   return 0;
 }
 
-// Tile width: the persistent grid has 148 CTAs, so a launch costs rounds(bn) = ceil(tiles_m * ceil(N/bn) / 148) tile
-// times; a tile costs ~ (bn + overhead) MMA columns.  E.g. M = 20480 (160 M-tiles), N = 256: bn = 256 -> 2 rounds
-// x 256 = 512, bn = 128 -> 3 rounds x 128 = 384.  SNIPER_GEMM_BN=<64|128|256> forces a width (A/B measurements).
+// Tile width.  Measured on B200 (profiles/gemm_shapes_r01_v5_tilewidth.md): a 128 x 128 tile moves 1.33x the
+// L2 -> shared-memory bytes per flop of a 128 x 256 tile and the K-major kernels are bound by exactly that traffic
+// (conv 20480 x 512 x 27648: 674 TFLOP/s with block_n = 256, 276 with 128), so wide tiles win even where they
+// quantise worse over the 148 SMs (M = 20480, N = 256: 160 tiles).  A wave-quantisation cost model
+// (rounds x (bn + overhead)) was tried and lost 8 ms/step.  SNIPER_GEMM_BN=<64|128|256> forces a width (A/B runs).
 int pick_block_n(int N, long tiles_m) {
+  (void)tiles_m;
   static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("SNIPER_GEMM_BN");
     forced = e ? atoi(e) : 0;
   }
-  int cap = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  const int cap = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   if (forced == 64 || forced == 128 || forced == 256) return forced < cap ? forced : cap;
-  int best = cap;
-  long best_cost = -1;
-  for (int bn = cap; bn >= 64; bn >>= 1) {
-    const long tiles = tiles_m * ((N + bn - 1) / bn);
-    const long rounds = (tiles + sn::kNumSMs - 1) / sn::kNumSMs;
-    const long cost = rounds * (bn + 48);   // 48 columns ~ per-tile prologue/epilogue exposure
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = bn;
-    }
-  }
-  return best;
+  if (N <= 128) return cap;
+  if (N % 256 == 0 || N > 1024) return 256;
+  return 128;
 }
 
 // cta_group::2: a CTA pair (cluster of 2, consecutive M tiles) issues 256 x block_n MMAs from the leader CTA; each

@@ -11,6 +11,7 @@ graph.  Frozen layers (conv0, bn0, stage1 -- FIXED_PARAMS, sniper_res101_e2e.yml
 forward only.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -42,7 +43,38 @@ class Cfg:
     wgrad_splits = 0                  # 0 = choose per layer (fill one wave of 148 persistent CTAs)
     # BN statistics accumulated by the producing conv's epilogue (warp-shuffle column sums + double REDs).
     # Measured on B200: +6.5 ms of tcgen05 time per step vs 1.8 ms saved in colsum kernels -> off by default.
-    fuse_bn_stats = False
+    fuse_bn_stats = os.environ.get("SNIPER_FUSE_BN", "0") == "1"
+    # run weight gradients on a second stream (see WgradScheduler); SNIPER_WGRAD_STREAM=0/1 overrides for A/B runs
+    wgrad_stream = os.environ.get("SNIPER_WGRAD_STREAM", "1") == "1"
+
+
+# ------------------------------------------------------------------------------------------------
+class WgradScheduler:
+    """Weight gradients are off the critical path of the backward pass (nothing but the optimizer reads them), so
+    they can run on a second stream next to the HBM-bound BatchNorm / elementwise kernels of the data-gradient
+    chain.  fork() makes the side stream wait for everything enqueued so far on the main stream, join() makes the
+    main stream wait for the side stream; tensors handed to the side stream are kept alive until join()."""
+
+    def __init__(self, enabled):
+        self.enabled = enabled
+        self.side = None
+        self.keep = []
+
+    def __call__(self, fn, *args):
+        if not self.enabled:
+            return fn(*args)
+        if self.side is None:
+            self.side = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        self.keep.append(args)
+        with torch.cuda.stream(self.side):
+            fn(*args)
+
+    def join(self):
+        if self.enabled and self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self.keep = []
 
 
 # ------------------------------------------------------------------------------------------------
@@ -325,26 +357,28 @@ class Unit:
         (+ extra_add, used to merge the c4 half of the concat gradient into stage4_unit1's input gradient)."""
         x, a1, c1, a2, c2, a3, off, col = self.saved
         sp = cfg.wgrad_splits
+        W = cfg.wsched
         hw_in = (x.shape[1], x.shape[2])
         hw_mid = (c2.shape[1], c2.shape[2])
-        self.conv3.bwd_weight(dout, a3, sp)
+        W(self.conv3.bwd_weight, dout, a3, sp)
         da3 = self.conv3.bwd_data(dout, hw_mid)
         dc2 = self.bn3.bwd(c2, da3)
         if self.deform:
             M = dc2.numel() // self.mid
             gw = self.conv2.P.grad(self.conv2.name + "_weight")
-            ops.conv2d_wgrad_nhwc(dc2, col.view(a2.shape[0], a2.shape[1], a2.shape[2], -1), kh=1, kw=1, dw_out=gw, splits=sp)
+            W(lambda d, c: ops.conv2d_wgrad_nhwc(d, c, kh=1, kw=1, dw_out=gw, splits=sp), dc2,
+              col.view(a2.shape[0], a2.shape[1], a2.shape[2], -1))
             dcol = ops.gemm_nt(dc2.view(M, self.mid), self.conv2.wt)         # wt = W^T [9*mid, mid]
             da2, doff = ops.deform_col2im(dcol, a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)
-            self.offset.bwd_weight(doff, a2, sp)
+            W(self.offset.bwd_weight, doff, a2, sp)
             da2 = self.offset.bwd_data(doff, (a2.shape[1], a2.shape[2]), out=da2, residual=da2)
         else:
-            self.conv2.bwd_weight(dc2, a2, sp)
+            W(self.conv2.bwd_weight, dc2, a2, sp)
             da2 = self.conv2.bwd_data(dc2, (a2.shape[1], a2.shape[2]))
         dc1 = self.bn2.bwd(c1, da2)
-        self.conv1.bwd_weight(dc1, a1, sp)
+        W(self.conv1.bwd_weight, dc1, a1, sp)
         if self.sc is not None:
-            self.sc.bwd_weight(dout, a1, sp)
+            W(self.sc.bwd_weight, dout, a1, sp)
         da1 = self.conv1.bwd_data(dc1, hw_in)
         if self.sc is not None:
             da1 = self.sc.bwd_data(dout, hw_in, out=da1, residual=da1)
@@ -364,6 +398,7 @@ class SniperResNet101:
         cfg = self.cfg
         self.device = device
         BN.fuse = bool(cfg.fuse_bn_stats)
+        cfg.wsched = WgradScheduler(bool(cfg.wgrad_stream))
         P = self.P = ParamStore()
         fl = cfg.filter_list
         # ---- frozen stem: bn_data, conv0, bn0 (resnetc4 :402-408)
@@ -511,32 +546,34 @@ class SniperResNet101:
 
         # ================= backward =================
         sp = cfg.wgrad_splits
+        W = cfg.wsched
         v4 = lambda t: t.view(1, 1, t.shape[0], t.shape[1])
-        self.fc_out.bwd_weight(v4(dout), v4(fc2), sp)
+        W(self.fc_out.bwd_weight, v4(dout), v4(fc2), sp)
         dfc2 = ops.relu_bwd(fc2, ops.gemm_nt(dout, self.fc_out.wt))
-        self.fc_new_2.bwd_weight(v4(dfc2), v4(fc1), sp)
+        W(self.fc_new_2.bwd_weight, v4(dfc2), v4(fc1), sp)
         dfc1 = ops.relu_bwd(fc1, ops.gemm_nt(dfc2, self.fc_new_2.wt))
-        self.fc_new_1.bwd_weight(v4(dfc1), v4(pooled.view(N, -1)), sp)
+        W(self.fc_new_1.bwd_weight, v4(dfc1), v4(pooled.view(N, -1)), sp)
         dpooled = ops.gemm_nt(dfc1, self.fc_new_1.wt).view(pooled.shape)
         dfeat, dtrans = ops.deform_psroi_bwd(dpooled, feat, rois, trans, no_trans=False, trans_std=0.1, **ps)
         doff = torch.zeros_like(off)
         doff[:, :98] = dtrans.view(N, 98)
-        self.fc_offset.bwd_weight(v4(doff), v4(offset_t.view(N, -1)), sp)
+        W(self.fc_offset.bwd_weight, v4(doff), v4(offset_t.view(N, -1)), sp)
         doffset_t = ops.gemm_nt(doff, self.fc_offset.wt).view(offset_t.shape)
         ops.deform_psroi_bwd(doffset_t, feat, rois, None, no_trans=True, data_diff=dfeat, **ps)
         dfeat = ops.relu_bwd(feat, dfeat)
         hw = (Hf, Hf)
-        self.conv_new_1.bwd_weight(dfeat, cat, sp)
+        W(self.conv_new_1.bwd_weight, dfeat, cat, sp)
         dcat = self.conv_new_1.bwd_data(dfeat, hw)
-        self.rpn_head.bwd_weight(dhead, rpn, sp)
+        W(self.rpn_head.bwd_weight, dhead, rpn, sp)
         drpn = ops.relu_bwd(rpn, self.rpn_head.bwd_data(dhead, hw))
-        self.rpn_conv.bwd_weight(drpn, cat, sp)
+        W(self.rpn_conv.bwd_weight, drpn, cat, sp)
         dcat = self.rpn_conv.bwd_data(drpn, hw, out=dcat, residual=dcat)
         # ---- backbone backward (stage 4, then stage 3 with the c4 half of dcat added, then stage 2)
         g = dcat[..., 1024:]
         for i in range(len(self.units) - 1, n1 - 1, -1):
             u = self.units[i]
             g = u.bwd(g, cfg, extra_add=dcat[..., :1024] if i == last3 + 1 else None)
+        W.join()
         self.step_count += 1
         return dict(rpn_cls_prob=prob, rpn_bbox_loss=self.loss_buf[1:2], cls_prob=cls_prob, bbox_loss=self.loss_buf[3:4],
                     label=label, rois=rois, losses=self.loss_buf)

@@ -104,3 +104,98 @@ def test_conv2d_wgrad_tf32(NB, H, W, Cin, Cout, k, stride, dil, pad):
     ref = wd.grad.permute(0, 2, 3, 1).reshape(Cout, -1)
     Kred = NB * Ho * Ho
     assert (dw.double() - ref).abs().max().item() <= _tol(Kred, x, dy, x.dtype)
+
+
+def _both_epilogues(fn):
+    """Runs fn() with the direct (per-lane row stores) and the staged TMA-store epilogue of the tcgen05 kernel."""
+    import os
+    res = []
+    for flag in ("0", "1"):
+        os.environ["SNIPER_GEMM_TMA_STORE"] = flag
+        try:
+            res.append(fn())
+        finally:
+            os.environ.pop("SNIPER_GEMM_TMA_STORE", None)
+    import torch
+    torch.cuda.synchronize()
+    return res
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (300, 96, 256), (6000, 1024, 512), (20480, 256, 128), (777, 512, 96)])
+def test_tma_store_epilogue_matches_direct_gemm(M, N, K):
+    """Same accumulators, same fp32 epilogue arithmetic -> the staged TMA-store epilogue is BIT-identical to the
+    direct one: plain, scale+bias+relu, residual (separate and in place), ragged M (rows clipped by the TMA)."""
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(M + N)
+    a = torch.randn(M, K, device="cuda")
+    b = torch.randn(N, K, device="cuda")
+    sc = torch.rand(N, device="cuda") + 0.5
+    bi = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    d, t = _both_epilogues(lambda: ops.gemm_nt(a, b))
+    assert torch.equal(d, t)
+    d, t = _both_epilogues(lambda: ops.gemm_nt(a, b, scale=sc, bias=bi, relu=True))
+    assert torch.equal(d, t)
+    d, t = _both_epilogues(lambda: ops.gemm_nt(a, b, bias=bi, residual=res))
+    assert torch.equal(d, t)
+    assert torch.equal(d, ops.gemm_nt(a, b, bias=bi) + res) or (d - (ops.gemm_nt(a, b, bias=bi) + res)).abs().max() < 1e-4
+
+    def inplace():
+        o = res.clone()
+        ops.gemm_nt(a, b, out=o, residual=o, relu=True)
+        return o
+    d, t = _both_epilogues(inplace)
+    assert torch.equal(d, t)
+    # column-sliced output / residual views (ld > N), as the concat buffers of the network use them
+    big = torch.zeros(M, N + 64, device="cuda")
+
+    def sliced():
+        o = big.clone()
+        ops.gemm_nt(a, b, out=o[:, 32:32 + N], residual=res)
+        return o
+    d, t = _both_epilogues(sliced)
+    assert torch.equal(d, t) and float(t[:, :32].abs().sum()) == 0.0 and float(t[:, 32 + N:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,k,stride,dil,pad", CONVS)
+def test_tma_store_epilogue_matches_direct_conv(NB, H, W, Cin, Cout, k, stride, dil, pad):
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(H + Cout)
+    x = torch.randn(NB, H, W, Cin, device="cuda")
+    w = torch.randn(Cout, k * k * Cin, device="cuda") * 0.05
+    bi = torch.randn(Cout, device="cuda")
+    d, t = _both_epilogues(lambda: ops.conv2d_nhwc(x, w, kh=k, kw=k, stride=stride, dil=dil, pad=pad, bias=bi, relu=True))
+    assert torch.equal(d, t)
+    res = torch.randn_like(d)
+    d, t = _both_epilogues(lambda: ops.conv2d_nhwc(x, w, kh=k, kw=k, stride=stride, dil=dil, pad=pad, residual=res))
+    assert torch.equal(d, t)
+    # accumulate=True: red.global.add vs TMA reduce-add onto the same initial values (one contribution per element)
+    d, t = _both_epilogues(lambda: ops.conv2d_nhwc(x, w, kh=k, kw=k, stride=stride, dil=dil, pad=pad, out=res.clone(),
+                                                   accumulate=True))
+    assert torch.equal(d, t)
+    # weight gradient (split-K accumulation order differs run to run -> tolerance)
+    dy = torch.randn_like(d)
+    if (NB, H, W, Cin, Cout, k, stride, dil, pad) in CONVS[:5] and Cout % 32 == 0:
+        d, t = _both_epilogues(lambda: ops.conv2d_wgrad_nhwc(dy, x, kh=k, kw=k, stride=stride, dil=dil, pad=pad, splits=0))
+        assert float((d - t).norm() / d.norm()) < 1e-5
+
+
+def test_tma_store_epilogue_strided_output_map():
+    """Stride-2 data gradient: the GEMM rows land on every other pixel of the (pre-zeroed / residual) output."""
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(2)
+    NB, Ho, Wo, Cout, Cin = 2, 32, 32, 128, 256
+    dy = torch.randn(NB, Ho, Wo, Cout, device="cuda")
+    wt = torch.randn(Cin, Cout, device="cuda") * 0.05
+    base = torch.randn(NB, 2 * Ho, 2 * Wo, Cin, device="cuda")
+
+    def run():
+        o = base.clone()
+        ops.conv2d_nhwc(dy, wt, kh=1, kw=1, out=o, residual=o, out_hw=(Ho, Wo), out_map=(2 * Ho, 2 * Wo, 2, 1, 1))
+        return o
+    d, t = _both_epilogues(run)
+    assert torch.equal(d, t)
+    assert torch.equal(t[:, 0::2], base[:, 0::2]) and not torch.equal(t[:, 1::2, 1::2], base[:, 1::2, 1::2])
