@@ -34,30 +34,58 @@ struct RowSplit {
 };
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-// ------------------------------------------------------------------ y = relu?(x*scale[c] + shift[c]) (+add)
-__global__ void __launch_bounds__(kTPB) affine_act_kernel(const float* __restrict__ x, long ldx,
-                                                           const float* __restrict__ scale,
-                                                           const float* __restrict__ shift, float* __restrict__ y,
-                                                           long ldy, long M, int C, int relu) {
-  const int c4 = C >> 2;
-  const long total = M * c4;
-  RowSplit rs;
-  rs.c4 = (unsigned)c4;
-  rs.shift = (c4 & (c4 - 1)) == 0 ? __ffs(c4) - 1 : -1;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long r;
-    int c;
-    rs.split(i, r, c);
-    float4 v = ld4(x + r * ldx + c);
-    const float4 s = ld4(scale + c), t = ld4(shift + c);
-    v.x = fmaf(v.x, s.x, t.x); v.y = fmaf(v.y, s.y, t.y); v.z = fmaf(v.z, s.z, t.z); v.w = fmaf(v.w, s.w, t.w);
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    st4(y + r * ldy + c, v);
+// ------------------------------------------------------------------ row-blocked [M, C] kernels
+// A block of 256 threads covers LX*4 channels (LX = 32 lanes, 16 when C == 64) x RY = 256/LX row lanes.  Each
+// thread keeps the per-channel constants of its 4 channels in registers (the flat grid-stride versions re-loaded
+// 2-6 float4 of constants per float4 of data) and streams rows r0 + ry, + RY, ... with kUnroll independent
+// 16-byte loads per operand in flight (HBM latency x bandwidth needs ~6 MB outstanding across the 148 SMs).
+constexpr int kUnroll = 4;
+
+struct RowBlock {
+  int lx_shift;         // log2(LX)
+  int rows_per_block;   // multiple of kUnroll * RY
+  dim3 grid;
+};
+
+__device__ __forceinline__ bool rb_setup(int lx_shift, int C, int rows_per_block, long M, int& c, int& ry, int& RY,
+                                         long& r0, long& r1) {
+  const int lx = 1 << lx_shift;
+  c = ((int)blockIdx.y * lx + ((int)threadIdx.x & (lx - 1))) * 4;
+  ry = (int)threadIdx.x >> lx_shift;
+  RY = 256 >> lx_shift;
+  r0 = (long)blockIdx.x * rows_per_block;
+  r1 = min(M, r0 + rows_per_block);
+  return c < C;
+}
+
+// y = relu?(x*scale[c] + shift[c])
+__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, long ldx,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, float* __restrict__ y,
+                                                          long ldy, long M, int C, int relu, int lx_shift,
+                                                          int rows_per_block) {
+  int c, ry, RY;
+  long r0, r1;
+  if (!rb_setup(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1)) return;
+  const float4 s = ld4(scale + c), t = ld4(shift + c);
+  for (long r = r0 + ry; r < r1; r += (long)kUnroll * RY) {
+    float4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+      if (r + (long)u * RY < r1) v[u] = ld4(x + (r + (long)u * RY) * ldx + c);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long rr = r + (long)u * RY;
+      if (rr >= r1) break;
+      float4 o = v[u];
+      o.x = fmaf(o.x, s.x, t.x); o.y = fmaf(o.y, s.y, t.y); o.z = fmaf(o.z, s.z, t.z); o.w = fmaf(o.w, s.w, t.w);
+      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+      st4(y + rr * ldy + c, o);
+    }
   }
 }
 
 // ------------------------------------------------------------------ per-channel sums over rows
-// blockDim = (32, 8): x -> 4 channels each (128 channels per block), y -> row lanes.
 // MODE 0: sums[c] += x, sums[C+c] += x*x                              (BN forward statistics)
 // MODE 1: g = dy * (x*scale+shift > 0); sums[c] += g; sums[C+c] += g * (x-mean)*invstd   (BN+ReLU backward)
 template <int MODE>
@@ -65,41 +93,56 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
                                                       const float* __restrict__ dy, long lddy,
                                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                      long M, int C, int rows_per_block, double* __restrict__ sums) {
-  const int c = (blockIdx.y * 32 + threadIdx.x) * 4;
-  const bool cok = c < C;
+                                                      long M, int C, int lx_shift, int rows_per_block,
+                                                      double* __restrict__ sums) {
+  int c, ry, RY;
+  long r0, r1;
+  const bool cok = rb_setup(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1);
   float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
-  float4 sc, sh, mu, is;
-  if (MODE == 1 && cok) { sc = ld4(scale + c); sh = ld4(shift + c); mu = ld4(mean + c); is = ld4(invstd + c); }
-  const long r0 = (long)blockIdx.x * rows_per_block;
-  const long r1 = min(M, r0 + rows_per_block);
   if (cok) {
-    for (long r = r0 + threadIdx.y; r < r1; r += 8) {
-      const float4 v = ld4(x + r * ldx + c);
-      if (MODE == 0) {
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
-      } else {
-        float4 g = ld4(dy + r * lddy + c);
-        g.x = fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : 0.f;
-        g.y = fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : 0.f;
-        g.z = fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : 0.f;
-        g.w = fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : 0.f;
-        a.x += g.x; a.y += g.y; a.z += g.z; a.w += g.w;
-        b.x = fmaf(g.x, (v.x - mu.x) * is.x, b.x); b.y = fmaf(g.y, (v.y - mu.y) * is.y, b.y);
-        b.z = fmaf(g.z, (v.z - mu.z) * is.z, b.z); b.w = fmaf(g.w, (v.w - mu.w) * is.w, b.w);
+    float4 sc, sh, mu, is;
+    if (MODE == 1) { sc = ld4(scale + c); sh = ld4(shift + c); mu = ld4(mean + c); is = ld4(invstd + c); }
+    for (long r = r0 + ry; r < r1; r += (long)kUnroll * RY) {
+      float4 v[kUnroll], g[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const long rr = r + (long)u * RY;
+        if (rr < r1) {
+          v[u] = ld4(x + rr * ldx + c);
+          if (MODE == 1) g[u] = ld4(dy + rr * lddy + c);
+        } else {
+          v[u] = make_float4(0, 0, 0, 0);           // contributes nothing in either mode (MODE 1: g = 0)
+          if (MODE == 1) g[u] = make_float4(0, 0, 0, 0);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        if (MODE == 0) {
+          a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
+          b.x = fmaf(v[u].x, v[u].x, b.x); b.y = fmaf(v[u].y, v[u].y, b.y);
+          b.z = fmaf(v[u].z, v[u].z, b.z); b.w = fmaf(v[u].w, v[u].w, b.w);
+        } else {
+          float4 gg = g[u];
+          gg.x = fmaf(v[u].x, sc.x, sh.x) > 0.f ? gg.x : 0.f;
+          gg.y = fmaf(v[u].y, sc.y, sh.y) > 0.f ? gg.y : 0.f;
+          gg.z = fmaf(v[u].z, sc.z, sh.z) > 0.f ? gg.z : 0.f;
+          gg.w = fmaf(v[u].w, sc.w, sh.w) > 0.f ? gg.w : 0.f;
+          a.x += gg.x; a.y += gg.y; a.z += gg.z; a.w += gg.w;
+          b.x = fmaf(gg.x, (v[u].x - mu.x) * is.x, b.x); b.y = fmaf(gg.y, (v[u].y - mu.y) * is.y, b.y);
+          b.z = fmaf(gg.z, (v[u].z - mu.z) * is.z, b.z); b.w = fmaf(gg.w, (v[u].w - mu.w) * is.w, b.w);
+        }
       }
     }
   }
-  __shared__ __align__(16) float4 sa[8][32], sb[8][32];
-  sa[threadIdx.y][threadIdx.x] = a;
-  sb[threadIdx.y][threadIdx.x] = b;
+  __shared__ __align__(16) float4 sa[256], sb[256];
+  sa[threadIdx.x] = a;
+  sb[threadIdx.x] = b;
   __syncthreads();
-  if (threadIdx.y == 0 && cok) {
+  if (ry == 0 && cok) {
+    const int lx = 1 << lx_shift;
     double ax = 0, ay = 0, az = 0, aw = 0, bx = 0, by = 0, bz = 0, bw = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4 p = sa[k][threadIdx.x], q = sb[k][threadIdx.x];
+    for (int k = 0; k < RY; ++k) {
+      const float4 p = sa[k * lx + threadIdx.x], q = sb[k * lx + threadIdx.x];
       ax += p.x; ay += p.y; az += p.z; aw += p.w;
       bx += q.x; by += q.y; bz += q.z; bw += q.w;
     }
@@ -146,47 +189,56 @@ __global__ void bn_frozen_kernel(int C, const float* gamma, const float* beta, c
   shift[c] = beta[c] - moving_mean[c] * g * is;
 }
 
-// dx = scale * (g - s1/M - xhat * s2/M) (+add);  dgamma += s2, dbeta += s1 (block 0 writes them); zeroes nothing
-__global__ void __launch_bounds__(kTPB) bn_relu_bwd_apply_kernel(const float* __restrict__ x, long ldx,
-                                                                  const float* __restrict__ dy, long lddy,
-                                                                  const float* __restrict__ scale,
-                                                                  const float* __restrict__ shift,
-                                                                  const float* __restrict__ mean,
-                                                                  const float* __restrict__ invstd,
-                                                                  const double* __restrict__ sums,
-                                                                  const float* __restrict__ add, long ldadd,
-                                                                  float* __restrict__ dx, long lddx, long M, int C) {
-  const int c4 = C >> 2;
-  const long total = M * c4;
+// dx = scale * (g - s1/M - xhat * s2/M) (+add), g = dy * (x*scale+shift > 0), xhat = (x-mean)*invstd; sums = (s1, s2)
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __restrict__ x, long ldx,
+                                                                 const float* __restrict__ dy, long lddy,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 const float* __restrict__ mean,
+                                                                 const float* __restrict__ invstd,
+                                                                 const double* __restrict__ sums,
+                                                                 const float* __restrict__ add, long ldadd,
+                                                                 float* __restrict__ dx, long lddx, long M, int C,
+                                                                 int lx_shift, int rows_per_block) {
+  int c, ry, RY;
+  long r0, r1;
+  if (!rb_setup(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1)) return;
   const float invM = 1.0f / (float)M;
-  RowSplit rs;
-  rs.c4 = (unsigned)c4;
-  rs.shift = (c4 & (c4 - 1)) == 0 ? __ffs(c4) - 1 : -1;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    long r;
-    int c;
-    rs.split(i, r, c);
-    const float4 v = ld4(x + r * ldx + c);
-    float4 g = ld4(dy + r * lddy + c);
-    const float4 sc = ld4(scale + c), sh = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
-    const float s1[4] = {(float)sums[c] * invM, (float)sums[c + 1] * invM, (float)sums[c + 2] * invM, (float)sums[c + 3] * invM};
-    const float s2[4] = {(float)sums[C + c] * invM, (float)sums[C + c + 1] * invM, (float)sums[C + c + 2] * invM,
-                         (float)sums[C + c + 3] * invM};
-    float vv[4] = {v.x, v.y, v.z, v.w}, gg[4] = {g.x, g.y, g.z, g.w};
-    const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
-    const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, isv[4] = {is.x, is.y, is.z, is.w};
-    float o[4];
+  const float4 sc4 = ld4(scale + c), sh4 = ld4(shift + c), mu4 = ld4(mean + c), is4 = ld4(invstd + c);
+  const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+  const float muv[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, isv[4] = {is4.x, is4.y, is4.z, is4.w};
+  float s1[4], s2[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float gk = fmaf(vv[k], scv[k], shv[k]) > 0.f ? gg[k] : 0.f;
-      const float xhat = (vv[k] - muv[k]) * isv[k];
-      o[k] = scv[k] * (gk - s1[k] - xhat * s2[k]);
+  for (int k = 0; k < 4; ++k) {
+    s1[k] = (float)sums[c + k] * invM;
+    s2[k] = (float)sums[C + c + k] * invM;
+  }
+  for (long r = r0 + ry; r < r1; r += (long)kUnroll * RY) {
+    float4 v[kUnroll], g[kUnroll], ad[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long rr = r + (long)u * RY;
+      if (rr < r1) {
+        v[u] = ld4(x + rr * ldx + c);
+        g[u] = ld4(dy + rr * lddy + c);
+        if (add) ad[u] = ld4(add + rr * ldadd + c);
+      }
     }
-    if (add) {
-      const float4 ad = ld4(add + r * ldadd + c);
-      o[0] += ad.x; o[1] += ad.y; o[2] += ad.z; o[3] += ad.w;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long rr = r + (long)u * RY;
+      if (rr >= r1) break;
+      const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, gg[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
+      float o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float gk = fmaf(vv[k], scv[k], shv[k]) > 0.f ? gg[k] : 0.f;
+        const float xhat = (vv[k] - muv[k]) * isv[k];
+        o[k] = scv[k] * (gk - s1[k] - xhat * s2[k]);
+      }
+      if (add) { o[0] += ad[u].x; o[1] += ad[u].y; o[2] += ad[u].z; o[3] += ad[u].w; }
+      st4(dx + rr * lddx + c, make_float4(o[0], o[1], o[2], o[3]));
     }
-    st4(dx + r * lddx + c, make_float4(o[0], o[1], o[2], o[3]));
   }
 }
 
@@ -418,13 +470,20 @@ int ew_grid(long work) {
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
-int pick_rows_per_block(long M, int C) {
-  // aim for >= 2 waves of 148 blocks
-  const int cb = sn::div_up(C, 128);
-  long rb = M / ((2 * sn::kNumSMs) / cb + 1);
-  if (rb < 64) rb = 64;
-  if (rb > 4096) rb = 4096;
-  return (int)((rb + 7) / 8 * 8);
+// Row-blocked launch geometry: ~8 blocks per SM, rows per block a multiple of kUnroll * RY.
+RowBlock row_block(long M, int C) {
+  RowBlock rb;
+  const int c4 = C / 4;
+  rb.lx_shift = c4 >= 32 ? 5 : 4;
+  const int lx = 1 << rb.lx_shift, RY = 256 >> rb.lx_shift;
+  const int by = sn::div_up(c4, lx);
+  const int step = kUnroll * RY;
+  long rpb = sn::div_up(M * by, (long)sn::kNumSMs * 8);
+  rpb = (rpb + step - 1) / step * step;
+  if (rpb < step) rpb = step;
+  rb.rows_per_block = (int)rpb;
+  rb.grid = dim3((unsigned)sn::div_up(M, rpb), (unsigned)by, 1);
+  return rb;
 }
 
 }  // namespace
@@ -434,7 +493,9 @@ extern "C" {
 int sniper_affine_act(const float* x, long ldx, const float* scale, const float* shift, float* y, long ldy, long M,
                       int C, int relu, void* stream) {
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "affine_act: C/ld must be multiples of 4");
-  affine_act_kernel<<<ew_grid(M * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(x, ldx, scale, shift, y, ldy, M, C, relu);
+  const RowBlock rb = row_block(M, C);
+  affine_act_kernel<<<rb.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, scale, shift, y, ldy, M, C, relu, rb.lx_shift,
+                                                                rb.rows_per_block);
   SN_LAUNCH_CHECK();
   return 0;
 }
@@ -445,10 +506,9 @@ int sniper_bn_stats(const float* x, long ldx, long M, int C, const float* gamma,
                     float momentum, int fix_gamma, float* moving_mean, float* moving_var, double* sums, float* mean,
                     float* invstd, float* scale, float* shift, void* stream) {
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0, "bn_stats: C/ld must be multiples of 4");
-  const int rpb = pick_rows_per_block(M, C);
-  dim3 grid(sn::div_up(M, rpb), sn::div_up(C, 128)), block(32, 8);
-  colsum_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, M,
-                                                            C, rpb, sums);
+  const RowBlock rb = row_block(M, C);
+  colsum_kernel<0><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, M,
+                                                              C, rb.lx_shift, rb.rows_per_block, sums);
   SN_LAUNCH_CHECK();
   bn_finalize_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, M, C, gamma, beta, eps, momentum,
                                                                           fix_gamma, moving_mean, moving_var, mean,
@@ -481,13 +541,12 @@ int sniper_bn_relu_bwd(const float* x, long ldx, const float* dy, long lddy, con
                        const float* mean, const float* invstd, double* sums, const float* add, long ldadd, float* dx,
                        long lddx, float* dgamma, float* dbeta, long M, int C, void* stream) {
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "bn_relu_bwd: C/ld must be multiples of 4");
-  const int rpb = pick_rows_per_block(M, C);
-  dim3 grid(sn::div_up(M, rpb), sn::div_up(C, 128)), block(32, 8);
-  colsum_kernel<1><<<grid, block, 0, (cudaStream_t)stream>>>(x, ldx, dy, lddy, scale, shift, mean, invstd, M, C, rpb,
-                                                            sums);
+  const RowBlock rb = row_block(M, C);
+  colsum_kernel<1><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, dy, lddy, scale, shift, mean, invstd, M, C,
+                                                              rb.lx_shift, rb.rows_per_block, sums);
   SN_LAUNCH_CHECK();
-  bn_relu_bwd_apply_kernel<<<ew_grid(M * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(
-      x, ldx, dy, lddy, scale, shift, mean, invstd, sums, add, ldadd, dx, lddx, M, C);
+  bn_relu_bwd_apply_kernel<<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
+      x, ldx, dy, lddy, scale, shift, mean, invstd, sums, add, ldadd, dx, lddx, M, C, rb.lx_shift, rb.rows_per_block);
   SN_LAUNCH_CHECK();
   bn_param_grad_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta);
   SN_LAUNCH_CHECK();
