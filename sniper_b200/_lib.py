@@ -36,6 +36,8 @@ SIGNATURES = {
     "sniper_maxpool3x3s2_nhwc": ("i", "ppiiiip"),
     "sniper_stem_conv": ("i", "pppppppiiip"),
     "sniper_weight_transpose": ("i", "ppiiiipp"),
+    "sniper_weight_transpose_batched": ("i", "piip"),
+    "sniper_bn_param_grad_batched": ("i", "pip"),
     "sniper_colsum": ("i", "pllipp"),
     "sniper_sgd_mom": ("i", "ppplffffp"),
     "sniper_count_valid": ("i", "plipp"),

@@ -419,6 +419,52 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, float* __re
   }
 }
 
+// All re-layouts of a training step in ONE launch.  jobs: njobs x 8 int64 = {w, wt, sel, Cout, T, Cin, Tsel, block0}
+// (block0 = first block of the job, ascending); the block finds its job by bisection.
+__global__ void weight_transpose_batched_kernel(const long long* __restrict__ jobs, int njobs) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid * 8 + 7] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const long long* jb = jobs + lo * 8;
+  const float* __restrict__ w = reinterpret_cast<const float*>(jb[0]);
+  float* __restrict__ wt = reinterpret_cast<float*>(jb[1]);
+  const int* __restrict__ sel = reinterpret_cast<const int*>(jb[2]);
+  const int Cout = (int)jb[3], T = (int)jb[4], Cin = (int)jb[5], Tsel = (int)jb[6];
+  const int local = (int)((long long)blockIdx.x - jb[7]);
+  const int nbx = (Cin + 31) >> 5, nby = (Cout + 31) >> 5;
+  const int bx = local % nbx, by = (local / nbx) % nby, j = local / (nbx * nby);
+  const int t = sel[j];
+  const int ci0 = bx * 32, co0 = by * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    tile[r][threadIdx.x] = (co < Cout && ci < Cin) ? w[((size_t)co * T + t) * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < Cin && co < Cout) wt[((size_t)ci * Tsel + j) * Cout + co] = tile[threadIdx.x][r];
+  }
+}
+
+// dgamma / dbeta of every BatchNorm of the network in ONE launch.  jobs: njobs x 4 int64 = {sums, dgamma, dbeta, C};
+// block = job, threads stride over the channels; accumulates and zeroes the sums (as bn_param_grad_kernel).
+__global__ void bn_param_grad_batched_kernel(const long long* __restrict__ jobs) {
+  const long long* jb = jobs + (size_t)blockIdx.x * 4;
+  double* sums = reinterpret_cast<double*>(jb[0]);
+  float* dgamma = reinterpret_cast<float*>(jb[1]);
+  float* dbeta = reinterpret_cast<float*>(jb[2]);
+  const int C = (int)jb[3];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (dbeta) dbeta[c] += (float)sums[c];
+    if (dgamma) dgamma[c] += (float)sums[C + c];
+    sums[c] = 0.0;
+    sums[C + c] = 0.0;
+  }
+}
+
 // ------------------------------------------------------------------ column sums of [M,C] (bias gradients)
 __global__ void __launch_bounds__(256) colsum_plain_kernel(const float* __restrict__ x, long ldx, long M, int C,
                                                             int rows_per_block, float* __restrict__ out) {
@@ -548,8 +594,10 @@ int sniper_bn_relu_bwd(const float* x, long ldx, const float* dy, long lddy, con
   bn_relu_bwd_apply_kernel<<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
       x, ldx, dy, lddy, scale, shift, mean, invstd, sums, add, ldadd, dx, lddx, M, C, rb.lx_shift, rb.rows_per_block);
   SN_LAUNCH_CHECK();
-  bn_param_grad_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta);
-  SN_LAUNCH_CHECK();
+  if (dgamma || dbeta) {   // both null: the caller finishes with sniper_bn_param_grad_batched (sums stay live)
+    bn_param_grad_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta);
+    SN_LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -594,6 +642,25 @@ int sniper_weight_transpose(const float* w, float* wt, int Cout, int T, int Cin,
                             void* stream) {
   dim3 grid(sn::div_up(Cin, 32), sn::div_up(Cout, 32), Tsel), block(32, 8);
   weight_transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(w, wt, Cout, T, Cin, Tsel, sel_dev);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// jobs_dev: device array of njobs x 8 int64 {w, wt, sel_dev, Cout, T, Cin, Tsel, block0} with block0 the running sum
+// of ceil(Cin/32) * ceil(Cout/32) * Tsel; total_blocks = that sum over all jobs.
+int sniper_weight_transpose_batched(const void* jobs_dev, int njobs, int total_blocks, void* stream) {
+  if (njobs <= 0 || total_blocks <= 0) return 0;
+  weight_transpose_batched_kernel<<<total_blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      static_cast<const long long*>(jobs_dev), njobs);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// Second half of sniper_bn_relu_bwd for callers that defer it (defer_param_grad != 0 there): jobs_dev = njobs x 4
+// int64 {sums, dgamma, dbeta, C}.  dgamma += s2, dbeta += s1, sums zeroed.
+int sniper_bn_param_grad_batched(const void* jobs_dev, int njobs, void* stream) {
+  if (njobs <= 0) return 0;
+  bn_param_grad_batched_kernel<<<njobs, 256, 0, (cudaStream_t)stream>>>(static_cast<const long long*>(jobs_dev));
   SN_LAUNCH_CHECK();
   return 0;
 }

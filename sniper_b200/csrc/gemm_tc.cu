@@ -481,6 +481,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t stg_u32 = smem_u32(stg);
         const int sw = lane & 7;
         int c_ow = 0, c_oh = 0, c_n = 0;        // TMA coordinates of this warp's 32 rows
+        int nvalid = 0;                         // how many of them exist in the tensor (always a prefix)
         int rowi[8];                            // residual rows read by this lane (coalesced layout), -1 = none
         const bool tile_ok = tc.tile_m < p.tiles_m;
         if (p.mode == MODE_CONV) {
@@ -490,6 +491,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const int oh0 = th * p.tile_h, ow0 = (r - th * p.tiles_w) * p.tile_w;
           const int m0 = q * 32;
           c_n = n_img; c_oh = oh0 + m0 / p.tile_w; c_ow = ow0 + m0 % p.tile_w;
+          nvalid = !tile_ok || c_oh >= p.Ho ? 0 : (p.tile_w >= 32 ? 32 : min(32, (p.Ho - c_oh) * p.tile_w));
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = m0 + i * 4 + (lane >> 3);
@@ -499,6 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         } else {
           c_ow = tc.tile_m * 128 + q * 32;
+          nvalid = tile_ok ? max(0, min(32, p.M - c_ow)) : 0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = c_ow + i * 4 + (lane >> 3);
@@ -572,6 +575,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           fence_proxy_async();
           __syncwarp();
+          if (p.stats) {
+            // fused BatchNorm statistics of the consumer: lane l sums column n0 + l of the staged chunk over the
+            // rows that exist in the tensor (a prefix of the 32), conflict-free through the 128B swizzle
+            float sm = 0.f, sq = 0.f;
+            const uint8_t* colp = stg + ((lane & 3) << 2);
+            const int jc = lane >> 2;
+#pragma unroll 8
+            for (int r = 0; r < nvalid; ++r) {
+              const float xv = *reinterpret_cast<const float*>(colp + r * 128 + ((jc ^ (r & 7)) << 4));
+              sm += xv;
+              sq = fmaf(xv, xv, sq);
+            }
+            if (nvalid > 0) {
+              atomicAdd(p.stats + n0 + lane, (double)sm);
+              atomicAdd(p.stats + p.N + n0 + lane, (double)sq);
+            }
+          }
           if (lane == 0) {
             if (p.atomic) tma_reduce_add_4d(&tma_c, stg, n0, c_ow, c_oh, c_n);
             else tma_store_4d(&tma_c, stg, n0, c_ow, c_oh, c_n);
@@ -794,7 +814,7 @@ int make_out_map(CUtensorMap* mc, GemmParams& p) {
   const bool enabled = !(e && e[0] == '0');
   memset(mc, 0, sizeof(*mc));
   p.epi_tma = 0;
-  const bool ok = enabled && !p.out_bf16 && !p.stats && p.N % 32 == 0 && p.ldc % 4 == 0 &&
+  const bool ok = enabled && !p.out_bf16 && p.N % 32 == 0 && p.ldc % 4 == 0 &&
                   (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
                   (!p.residual || (p.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) &&
                   (!p.scale || (reinterpret_cast<uintptr_t>(p.scale) & 15) == 0) &&

@@ -43,7 +43,7 @@ class Cfg:
     wgrad_splits = 0                  # 0 = choose per layer (fill one wave of 148 persistent CTAs)
     # BN statistics accumulated by the producing conv's epilogue (warp-shuffle column sums + double REDs).
     # Measured on B200: +6.5 ms of tcgen05 time per step vs 1.8 ms saved in colsum kernels -> off by default.
-    fuse_bn_stats = os.environ.get("SNIPER_FUSE_BN", "0") == "1"
+    fuse_bn_stats = os.environ.get("SNIPER_FUSE_BN", "1") == "1"
     # run weight gradients on a second stream (see WgradScheduler); SNIPER_WGRAD_STREAM=0/1 overrides for A/B runs
     wgrad_stream = os.environ.get("SNIPER_WGRAD_STREAM", "1") == "1"
 
@@ -187,10 +187,11 @@ class Conv:
                                scale=scale, bias=add, residual=residual, relu=relu, stats=stats)
 
     # ---- backward
-    def prepare_bwd(self):
-        """Re-layout of the (just updated) weights for the data gradient: [Cin, taps', Cout]."""
+    def bwd_jobs(self):
+        """Re-layout jobs of the (just updated) weights for the data gradient, [Cin, taps', Cout]: a list of
+        (w, wt, sel, Cout, T, Cin) for ops.weight_transpose_jobs (all of them run as ONE launch per step)."""
         if not (self.trainable and self.need_dgrad):
-            return
+            return []
         dev = self.w.device
         k, T = self.k, self.k * self.k
         if self.plain_wt:
@@ -198,30 +199,32 @@ class Conv:
             if getattr(self, "_sel", None) is None:
                 self._sel = torch.zeros(1, dtype=torch.int32, device=dev)
                 self.wt = torch.empty(self.K, self.coutp, device=dev)
-            ops.weight_transpose(self.w, self.coutp, 1, self.K, self._sel, out=self.wt)
-        elif self.stride == 1 or k == 1:
+            return [(self.w, self.wt, self._sel, self.coutp, 1, self.K)]
+        if self.stride == 1 or k == 1:
             sel = list(range(T - 1, -1, -1))
             if getattr(self, "_sel", None) is None:
                 self._sel = torch.tensor(sel, dtype=torch.int32, device=dev)
                 self.wt = torch.empty(self.cin, T * self.coutp, device=dev)
-            ops.weight_transpose(self.w, self.coutp, T, self.cin, self._sel, out=self.wt)
-        else:
-            # stride 2, 3x3, pad 1: four output-parity classes, each a stride-1 conv over dY
-            assert k == 3 and self.stride == 2 and self.pad == 1 and self.dil == 1
-            if getattr(self, "_sel", None) is None:
-                self._sel, self.wt, self._taps = [], [], []
-                for ph in (0, 1):
-                    for pw in (0, 1):
-                        khs = [1] if ph == 0 else [0, 2]
-                        kws = [1] if pw == 0 else [0, 2]
-                        sel = [kh * 3 + kw for kh in khs for kw in kws]
-                        dh = [(ph + 1 - kh) // 2 for kh in khs for _ in kws]
-                        dw = [(pw + 1 - kw) // 2 for _ in khs for kw in kws]
-                        self._sel.append(torch.tensor(sel, dtype=torch.int32, device=dev))
-                        self.wt.append(torch.empty(self.cin, len(sel) * self.coutp, device=dev))
-                        self._taps.append((dh, dw, ph, pw))
-            for s, w in zip(self._sel, self.wt):
-                ops.weight_transpose(self.w, self.coutp, 9, self.cin, s, out=w)
+            return [(self.w, self.wt, self._sel, self.coutp, T, self.cin)]
+        # stride 2, 3x3, pad 1: four output-parity classes, each a stride-1 conv over dY
+        assert k == 3 and self.stride == 2 and self.pad == 1 and self.dil == 1
+        if getattr(self, "_sel", None) is None:
+            self._sel, self.wt, self._taps = [], [], []
+            for ph in (0, 1):
+                for pw in (0, 1):
+                    khs = [1] if ph == 0 else [0, 2]
+                    kws = [1] if pw == 0 else [0, 2]
+                    sel = [kh * 3 + kw for kh in khs for kw in kws]
+                    dh = [(ph + 1 - kh) // 2 for kh in khs for _ in kws]
+                    dw = [(pw + 1 - kw) // 2 for _ in khs for kw in kws]
+                    self._sel.append(torch.tensor(sel, dtype=torch.int32, device=dev))
+                    self.wt.append(torch.empty(self.cin, len(sel) * self.coutp, device=dev))
+                    self._taps.append((dh, dw, ph, pw))
+        return [(self.w, w, s, self.coutp, 9, self.cin) for s, w in zip(self._sel, self.wt)]
+
+    def prepare_bwd(self):
+        for w, wt, sel, Cout, T, Cin in self.bwd_jobs():
+            ops.weight_transpose(w, Cout, T, Cin, sel, out=wt)
 
     def bwd_data(self, dy, in_hw, out=None, residual=None):
         """dX = conv^T(dY).  dy: [N,Ho,Wo,coutp]; returns [N,H,W,Cin] (+ residual)."""
@@ -286,8 +289,10 @@ class BN:
         """The scratch a producer may accumulate this BN's input statistics into (None: compute them here)."""
         return None if (self.frozen or not BN.fuse) else self.st.sums
 
+    defer = False   # set per instance by SniperResNet101: dgamma/dbeta of all layers by one bn_param_grad_batched launch
+
     def bwd(self, x, dy, add=None):
-        return ops.bn_relu_bwd(x, dy, self.st, add=add)
+        return ops.bn_relu_bwd(x, dy, self.st, add=add, defer=self.defer)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -399,6 +404,8 @@ class SniperResNet101:
         self.device = device
         BN.fuse = bool(cfg.fuse_bn_stats)
         cfg.wsched = WgradScheduler(bool(cfg.wgrad_stream))
+        self._wt_table = None
+        self._bn_table = None
         P = self.P = ParamStore()
         fl = cfg.filter_list
         # ---- frozen stem: bn_data, conv0, bn0 (resnetc4 :402-408)
@@ -464,6 +471,9 @@ class SniperResNet101:
             c.init(std=0.01, device=dev, gen=g)
         self.fc_offset.init(std=deform_offset_std and 0.001, device=dev, gen=g)   # zeros in the reference (:476-477)
 
+    def train_bns(self):
+        return [b for u in self.units if not u.frozen for b in u.bns()]
+
     def trainable_convs(self):
         cs = []
         for u in self.units:
@@ -487,8 +497,13 @@ class SniperResNet101:
         self.loss_buf.zero_()
         self.cnt_buf.zero_()
         # weights were updated by the previous step: refresh the data-gradient operands
-        for c in self.trainable_convs():
-            c.prepare_bwd()
+        if self._wt_table is None:
+            jobs = [j for c in self.trainable_convs() for j in c.bwd_jobs()]
+            self._wt_table = ops.weight_transpose_jobs(jobs, data.device)
+            for b in self.train_bns():
+                b.defer = True
+            self._bn_table = ops.bn_param_grad_jobs([b.st for b in self.train_bns()], data.device)
+        ops.weight_transpose_batched(self._wt_table)
 
         # ---- backbone forward
         x = ops.stem_conv(data, self.conv0_w, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
@@ -573,6 +588,7 @@ class SniperResNet101:
         for i in range(len(self.units) - 1, n1 - 1, -1):
             u = self.units[i]
             g = u.bwd(g, cfg, extra_add=dcat[..., :1024] if i == last3 + 1 else None)
+        ops.bn_param_grad_batched(self._bn_table)
         W.join()
         self.step_count += 1
         return dict(rpn_cls_prob=prob, rpn_bbox_loss=self.loss_buf[1:2], cls_prob=cls_prob, bbox_loss=self.loss_buf[3:4],

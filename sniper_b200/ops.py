@@ -299,14 +299,16 @@ def bn_frozen(bn, eps=2e-5, fix_gamma=False):
                                  float(eps), int(fix_gamma), _ptr(bn.scale), _ptr(bn.shift), _stream()))
 
 
-def bn_relu_bwd(x, dy, bn, add=None, out=None):
-    """Backward of relu(bn_train(x)); accumulates bn.dgamma / bn.dbeta; returns dx (+ add)."""
+def bn_relu_bwd(x, dy, bn, add=None, out=None, defer=False):
+    """Backward of relu(bn_train(x)); accumulates bn.dgamma / bn.dbeta; returns dx (+ add).
+    defer=True leaves (s1, s2) in bn.sums for one bn_param_grad_batched call at the end of the backward pass."""
     M, C, ldx = _rows(x)
     if out is None:
         out = torch.empty(x.shape, device=x.device)
     check(lib().sniper_bn_relu_bwd(_ptr(x), ldx, _ptr(dy), _rows(dy)[2], _ptr(bn.scale), _ptr(bn.shift), _ptr(bn.mean),
                                    _ptr(bn.invstd), _ptr(bn.sums), _ptr(add), 0 if add is None else _rows(add)[2],
-                                   _ptr(out), _rows(out)[2], _ptr(bn.dgamma), _ptr(bn.dbeta), M, C, _stream()))
+                                   _ptr(out), _rows(out)[2], None if defer else _ptr(bn.dgamma),
+                                   None if defer else _ptr(bn.dbeta), M, C, _stream()))
     return out
 
 
@@ -352,6 +354,33 @@ def weight_transpose(w, Cout, T, Cin, sel_dev, out=None):
         out = torch.empty(Cin, Tsel * Cout, device=w.device)
     check(lib().sniper_weight_transpose(_ptr(w), _ptr(out), Cout, T, Cin, Tsel, _ptr(sel_dev), _stream()))
     return out
+
+
+def weight_transpose_jobs(jobs, device):
+    """jobs: list of (w, wt, sel_dev, Cout, T, Cin).  Returns the device job table for weight_transpose_batched."""
+    rows, b0 = [], 0
+    for w, wt, sel, Cout, T, Cin in jobs:
+        Tsel = sel.numel()
+        rows.append([w.data_ptr(), wt.data_ptr(), sel.data_ptr(), Cout, T, Cin, Tsel, b0])
+        b0 += ((Cin + 31) // 32) * ((Cout + 31) // 32) * Tsel
+    return torch.tensor(rows, dtype=torch.int64, device=device), len(rows), b0
+
+
+def weight_transpose_batched(table):
+    t, n, blocks = table
+    check(lib().sniper_weight_transpose_batched(_ptr(t), n, blocks, _stream()))
+
+
+def bn_param_grad_jobs(states, device):
+    """states: BNState objects whose backward ran with defer=True."""
+    rows = [[b.sums.data_ptr(), 0 if b.dgamma is None else b.dgamma.data_ptr(),
+             0 if b.dbeta is None else b.dbeta.data_ptr(), b.C] for b in states]
+    return torch.tensor(rows, dtype=torch.int64, device=device), len(rows)
+
+
+def bn_param_grad_batched(table):
+    t, n = table
+    check(lib().sniper_bn_param_grad_batched(_ptr(t), n, _stream()))
 
 
 def colsum_accum(x, out):

@@ -136,3 +136,32 @@ def test_losses_match_torch():
     sl2 = (bw.double() * F.smooth_l1_loss(q - bt.double(), torch.zeros(N, 4, device="cuda", dtype=torch.double), reduction="none")).sum()
     (sl2 / 3008).backward()
     assert (g4[:, 81:85].double() - q.grad).abs().max().item() < 1e-7
+
+
+@pytest.mark.gpu
+def test_batched_weight_transpose_and_bn_param_grad():
+    """One-launch-per-step variants == the per-layer entry points."""
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(4)
+    jobs, refs = [], []
+    for (Cout, T, Cin, sel) in [(96, 9, 64, [8, 7, 6, 5, 4, 3, 2, 1, 0]), (256, 1, 1024, [0]), (512, 9, 512, [0, 2, 6, 8]),
+                                (72, 9, 40, [4])]:
+        w = torch.randn(Cout, T * Cin, device="cuda")
+        s = torch.tensor(sel, dtype=torch.int32, device="cuda")
+        out = torch.zeros(Cin, len(sel) * Cout, device="cuda")
+        jobs.append((w, out, s, Cout, T, Cin))
+        refs.append(ops.weight_transpose(w, Cout, T, Cin, s))
+    table = ops.weight_transpose_jobs(jobs, "cuda")
+    ops.weight_transpose_batched(table)
+    for (_, out, *_), ref in zip(jobs, refs):
+        assert torch.equal(out, ref)
+    states = []
+    for C in (64, 256, 1000):
+        b = ops.BNState(C, "cuda", dgamma=torch.randn(C, device="cuda"), dbeta=torch.randn(C, device="cuda"))
+        b.sums.copy_(torch.randn(2 * C, dtype=torch.float64, device="cuda"))
+        states.append((b, b.dgamma.clone(), b.dbeta.clone(), b.sums.clone()))
+    ops.bn_param_grad_batched(ops.bn_param_grad_jobs([t[0] for t in states], "cuda"))
+    for b, g0, b0, s0 in states:
+        assert torch.equal(b.dbeta, b0 + s0[:b.C].float()) and torch.equal(b.dgamma, g0 + s0[b.C:].float())
+        assert float(b.sums.abs().sum()) == 0.0

@@ -199,3 +199,34 @@ def test_tma_store_epilogue_strided_output_map():
     d, t = _both_epilogues(run)
     assert torch.equal(d, t)
     assert torch.equal(t[:, 0::2], base[:, 0::2]) and not torch.equal(t[:, 1::2, 1::2], base[:, 1::2, 1::2])
+
+
+@pytest.mark.parametrize("tma", ["0", "1"])
+def test_fused_column_statistics(tma):
+    """stats= (BatchNorm statistics of the consumer fused into the epilogue): per-column sum and sum of squares of the
+    STORED values, over exactly the rows that exist (ragged M, partial conv tiles), with both epilogue variants."""
+    import os
+    import torch
+    from sniper_b200 import ops
+    os.environ["SNIPER_GEMM_TMA_STORE"] = tma
+    try:
+        torch.manual_seed(5)
+        for (M, N, K) in [(300, 96, 64), (20480, 256, 128), (130, 512, 32)]:
+            a = torch.randn(M, K, device="cuda")
+            b = torch.randn(N, K, device="cuda")
+            bi = torch.randn(N, device="cuda")
+            st = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+            c = ops.gemm_nt(a, b, bias=bi, stats=st)
+            ref = torch.cat([c.double().sum(0), (c.double() ** 2).sum(0)])
+            assert ((st - ref).abs() / (ref.abs() + 1.0)).max().item() < 1e-5
+        # conv with a partial last tile row (Ho = 20, tile = 16 x 8 pixels) and a residual
+        x = torch.randn(3, 20, 16, 64, device="cuda")
+        w = torch.randn(128, 9 * 64, device="cuda") * 0.05
+        res = torch.randn(3, 20, 16, 128, device="cuda")
+        st = torch.zeros(256, dtype=torch.float64, device="cuda")
+        y = ops.conv2d_nhwc(x, w, kh=3, kw=3, pad=1, residual=res, stats=st)
+        y2 = y.double().reshape(-1, 128)
+        ref = torch.cat([y2.sum(0), (y2 ** 2).sum(0)])
+        assert ((st - ref).abs() / (ref.abs() + 1.0)).max().item() < 1e-5
+    finally:
+        os.environ.pop("SNIPER_GEMM_TMA_STORE", None)

@@ -28,6 +28,8 @@ DOC = {
     "sniper_maxpool3x3s2_nhwc": "Pooling max 3x3 stride 2 pad 1 (resnet_mx_101_e2e.py:409; nn/pool.cuh).",
     "sniper_stem_conv": "bn_data -> conv0 7x7/2 -> bn0 -> relu (resnet_mx_101_e2e.py:402-408), NCHW in, NHWC out.",
     "sniper_weight_transpose": "wt[ci, j, co] = w[co, sel[j], ci]: operand layout for data gradients.",
+    "sniper_weight_transpose_batched": "Every sniper_weight_transpose of a training step in one launch (device job table).",
+    "sniper_bn_param_grad_batched": "dgamma/dbeta of every BatchNorm in one launch (second half of sniper_bn_relu_bwd when it is called with dgamma = dbeta = NULL).",
     "sniper_colsum": "out[c] += sum_m x[m,c] (bias gradients; cudnnConvolutionBackwardBias).",
     "sniper_sgd_mom": "SGDMomKernel (optimizer_op-inl.h:279-300) on one flat buffer.",
     "sniper_count_valid": "Device-side replacement of SoftmaxOutput's host valid count (softmax_output-inl.h:184-195).",
