@@ -70,6 +70,13 @@ struct GemmParams {
   int out_H, out_W, out_s, out_oh, out_ow;
   int out_bf16;           // store bf16 instead of fp32
   int epi_tma;            // 1: epilogue stages 32 x 32 chunks in shared memory and stores / reduces them by TMA (tma_c)
+  // ---- tail split (K-major modes): work units [0, tail_first) are whole tiles; every tile >= tail_first (the
+  // last, partial wave over the persistent grid) is cut into tail_s K-slices that run on different CTAs.  Slices
+  // park their raw accumulators in tail_ws; the LAST slice to arrive (per epilogue warp, counted in tail_cnt) sums
+  // all slices in index order (deterministic) and runs the normal epilogue.  tail_s = 0: off.
+  int tail_first, tail_s;
+  float4* tail_ws;
+  int* tail_cnt;
   double* stats;          // optional [2*N]: += per-column sum and sum of squares of the stored values
                           // (train-mode BatchNorm statistics of the consumer, fused into the producer)
 };
@@ -250,11 +257,23 @@ __device__ __forceinline__ bool elect_one() {
 
 struct TileCoord {
   int tile_m, tile_n, split;
+  int kb0, nkb;       // k-block range of this work unit
+  int slice, tail;    // tail split: K-slice index and tail-tile index (slice = -1: whole tile)
 };
 
 // work unit u of a cluster -> tile of this CTA (cluster of 2: consecutive M tiles, same N tile)
 __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int cta_rank) {
   TileCoord c;
+  c.kb0 = 0; c.nkb = p.num_kb; c.slice = -1; c.tail = 0;
+  if (p.tail_s > 0 && u >= p.tail_first) {
+    const int v = u - p.tail_first;
+    c.tail = v / p.tail_s;
+    c.slice = v - c.tail * p.tail_s;
+    const int base = p.num_kb / p.tail_s, rem = p.num_kb - base * p.tail_s;
+    c.kb0 = c.slice * base + min(c.slice, rem);
+    c.nkb = base + (c.slice < rem ? 1 : 0);
+    u = p.tail_first + c.tail;
+  }
   const int tiles_mp = (p.tiles_m + p.cluster - 1) / p.cluster;
   c.tile_n = u % p.tiles_n;
   const int r = u / p.tiles_n;
@@ -292,7 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
   const int unit0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int unit_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int total_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n * p.splits;   // work units
+  const int whole_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n * p.splits;
+  const int total_tiles = p.tail_s > 0 ? p.tail_first + (whole_tiles - p.tail_first) * p.tail_s : whole_tiles;  // units
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
@@ -344,11 +364,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           wg_tap = tc.tile_n / p.wg_cin_blocks;
           wg_ci0 = (tc.tile_n - wg_tap * p.wg_cin_blocks) * p.block_n;
         }
-        for (int i = 0; i < p.num_kb; ++i) {
+        for (int i = 0; i < tc.nkb; ++i) {
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + kStageABytes;
-          const int kb = tc.split * p.num_kb + i;
+          const int kb = tc.split * p.num_kb + tc.kb0 + i;
           if (!leader) {
             // nothing to issue
           } else if (p.mode == MODE_GEMM) {
@@ -413,7 +433,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_cols;
-        for (int i = 0; i < p.num_kb; ++i) {
+        const int nkb = tile_coord(p, t, 0).nkb;
+        for (int i = 0; i < nkb; ++i) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
@@ -520,15 +541,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(&tmem_full_bar[acc], acc_ph);
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + acc * acc_cols + (uint32_t)(half * cols_per_warp) + ((uint32_t)(q * 32) << 16);
+        const bool sliced = tc.slice >= 0;
+        const int nchunks = cols_per_warp >> 5;
+        // float4 index of (slice 0, this warp, chunk 0, j 0, lane) in the tail workspace; one slice = 32 * block_n float4
+        const size_t ws_warp = ((size_t)tc.tail * p.tail_s * 8 + (size_t)(warp - 2)) * nchunks * 256 + lane;
+        const size_t ws_slice = (size_t)8 * nchunks * 256;
+        if (sliced) {
+          // park this K-slice's raw accumulators (coalesced: instruction j writes 32 lanes x 16 B contiguous)
+          float4* dst = p.tail_ws + ws_warp + (size_t)tc.slice * ws_slice;
+          for (int c = 0; c < cols_per_warp; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_acc + (uint32_t)c, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[(c >> 5) * 256 + j * 32] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
+          tc_fence_before();
+          __threadfence();
+          __syncwarp();
+          int old = 0;
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+            else mbar_arrive(&tmem_empty_bar[acc]);
+            old = atomicAdd(p.tail_cnt + tc.tail * 8 + (warp - 2), 1);
+          }
+          old = __shfl_sync(0xffffffffu, old, 0);
+          if (old != p.tail_s - 1) continue;          // another slice's warp finishes this part of the tile
+          if (lane == 0) p.tail_cnt[tc.tail * 8 + (warp - 2)] = 0;   // self-cleaning for the next launch
+          __threadfence();
+        }
         for (int c = 0; c < cols_per_warp; c += 32) {
           uint32_t v[32];
-          tmem_ld32(tmem_acc + (uint32_t)c, v);
-          if (c + 32 >= cols_per_warp) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-              if (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
-              else mbar_arrive(&tmem_empty_bar[acc]);
+          if (sliced) {
+            // sum the slices in index order (deterministic); .cg loads: the data was written by other SMs
+            const float4* src = p.tail_ws + ws_warp + (size_t)(c >> 5) * 256;
+            float4 a4[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a4[j] = __ldcg(src + j * 32);
+            for (int sl = 1; sl < p.tail_s; ++sl) {
+              const float4* s2 = src + (size_t)sl * ws_slice;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldcg(s2 + j * 32);
+                a4[j].x += b4.x; a4[j].y += b4.y; a4[j].z += b4.z; a4[j].w += b4.w;
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] = __float_as_uint(a4[j].x); v[4 * j + 1] = __float_as_uint(a4[j].y);
+              v[4 * j + 2] = __float_as_uint(a4[j].z); v[4 * j + 3] = __float_as_uint(a4[j].w);
+            }
+          } else {
+            tmem_ld32(tmem_acc + (uint32_t)c, v);
+            if (c + 32 >= cols_per_warp) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+                else mbar_arrive(&tmem_empty_bar[acc]);
+              }
             }
           }
           const int n0 = col_base + c;
@@ -839,12 +911,87 @@ int make_out_map(CUtensorMap* mc, GemmParams& p) {
   return 0;
 }
 
+// Tail-split workspaces: kTailSlots buffers (one per stream using the kernel concurrently), allocated together on
+// first use so that no allocation happens later inside a CUDA-graph capture.  One buffer holds the parked
+// accumulators of at most 148 slices (128 x 256 fp32 each) + 148 x 8 arrival counters.
+constexpr int kTailSlots = 4;
+constexpr size_t kTailWsBytes = (size_t)sn::kNumSMs * 128 * 256 * 4;
+struct TailSlot {
+  cudaStream_t stream;
+  bool used;
+  float4* ws;
+  int* cnt;
+};
+TailSlot g_tail[kTailSlots];
+bool g_tail_ready = false;
+
+TailSlot* tail_slot(cudaStream_t stream) {
+  if (!g_tail_ready) {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+    for (int i = 0; i < kTailSlots; ++i) {
+      void* w = nullptr;
+      void* c = nullptr;
+      if (cudaMalloc(&w, kTailWsBytes) != cudaSuccess || cudaMalloc(&c, sn::kNumSMs * 8 * sizeof(int)) != cudaSuccess ||
+          cudaMemset(c, 0, sn::kNumSMs * 8 * sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+      g_tail[i].stream = nullptr; g_tail[i].used = false;
+      g_tail[i].ws = static_cast<float4*>(w); g_tail[i].cnt = static_cast<int*>(c);
+    }
+    g_tail_ready = true;
+  }
+  for (int i = 0; i < kTailSlots; ++i)
+    if (g_tail[i].used && g_tail[i].stream == stream) return &g_tail[i];
+  for (int i = 0; i < kTailSlots; ++i)
+    if (!g_tail[i].used) {
+      g_tail[i].used = true;
+      g_tail[i].stream = stream;
+      return &g_tail[i];
+    }
+  return nullptr;   // more concurrent streams than slots: run without the tail split
+}
+
+// Decide the tail split of a K-major launch (see GemmParams::tail_*).  SNIPER_GEMM_TAIL=0 disables it.
+void plan_tail(GemmParams& p, long tiles, long grid_units, cudaStream_t stream) {
+  p.tail_s = 0; p.tail_first = 0; p.tail_ws = nullptr; p.tail_cnt = nullptr;
+  const char* e = getenv("SNIPER_GEMM_TAIL");
+  if (e && e[0] == '0') return;
+  if (p.mode == MODE_WGRAD || p.cluster != 1 || !p.epi_tma || p.splits != 1) return;
+  const long tail = tiles % grid_units;
+  if (tail == 0 || tail * 2 > grid_units) return;
+  // Cost model fitted to tools/gemm_time.py on B200: a 128 x 256 tile costs ~0.43 us per k-block; parking the
+  // slices, the arrival counter and the late epilogue cost ~(9 + 2.4 S) us.  The split pays off for K >~ 2000 only
+  // (K = 2304: 62 -> 56 us with S = 4; K = 1024: 41 -> 43 us, so it stays off there).
+  const double t_tile = 0.43 * p.num_kb * p.block_n / 256.0;
+  long max_s = grid_units / tail;
+  if (max_s > p.num_kb / 4) max_s = p.num_kb / 4;      // at least 4 k-blocks per slice
+  if (max_s > 8) max_s = 8;
+  if (const char* m = getenv("SNIPER_GEMM_TAIL_MAXS")) max_s = max_s < atoi(m) ? max_s : atoi(m);
+  long s = 0;
+  double best = 3.0;                                   // minimum predicted gain, us
+  for (long c = 2; c <= max_s; ++c) {
+    const double gain = (1.0 - 1.0 / c) * t_tile - (9.0 + 2.4 * c);
+    if (gain > best) { best = gain; s = c; }
+  }
+  if (s < 2) return;
+  TailSlot* slot = tail_slot(stream);
+  if (!slot) return;
+  p.tail_s = (int)s;
+  p.tail_first = (int)(tiles - tail);
+  p.tail_ws = slot->ws;
+  p.tail_cnt = slot->cnt;
+}
+
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 tiles, cudaStream_t stream) {
   CUtensorMap mc;
   if (make_out_map(&mc, p)) return -1;
   p.tiles_m = (int)tiles.x; p.tiles_n = (int)tiles.y; p.splits = (int)tiles.z;
-  const long units = (long)((tiles.x + p.cluster - 1) / p.cluster) * tiles.y * tiles.z;
+  long units = (long)((tiles.x + p.cluster - 1) / p.cluster) * tiles.y * tiles.z;
   const long max_units = sn::kNumSMs / p.cluster;
+  plan_tail(p, units, max_units, stream);
+  if (p.tail_s > 0) units = p.tail_first + (units - p.tail_first) * p.tail_s;
   dim3 grid((unsigned)((units < max_units ? units : max_units) * p.cluster), 1, 1);
   const size_t smem = smem_bytes(p.stages, p.block_n);
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);

@@ -110,12 +110,14 @@ def _both_epilogues(fn):
     """Runs fn() with the direct (per-lane row stores) and the staged TMA-store epilogue of the tcgen05 kernel."""
     import os
     res = []
+    os.environ["SNIPER_GEMM_TAIL"] = "0"      # the tail split re-associates the K sum (TMA epilogue only)
     for flag in ("0", "1"):
         os.environ["SNIPER_GEMM_TMA_STORE"] = flag
         try:
             res.append(fn())
         finally:
             os.environ.pop("SNIPER_GEMM_TMA_STORE", None)
+    os.environ.pop("SNIPER_GEMM_TAIL", None)
     import torch
     torch.cuda.synchronize()
     return res
@@ -230,3 +232,49 @@ def test_fused_column_statistics(tma):
         assert ((st - ref).abs() / (ref.abs() + 1.0)).max().item() < 1e-5
     finally:
         os.environ.pop("SNIPER_GEMM_TMA_STORE", None)
+
+
+def test_tail_split_matches_whole_tiles_and_is_deterministic():
+    """The last partial wave of tiles is cut into K-slices whose parked accumulators are summed (in slice order) by
+    the last arriving slice: same result as whole tiles up to fp32 re-association, bit-identical run to run, epilogue
+    (bias, residual, fused statistics) applied exactly once."""
+    import os
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(8)
+    cases = [(20480, 256, 2304), (6000, 128, 12544), (20480, 512, 4608), (300, 64, 8192)]
+    for (M, N, K) in cases:
+        a = torch.randn(M, K, device="cuda")
+        b = torch.randn(N, K, device="cuda")
+        bi = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda")
+
+        def run():
+            st = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+            c = ops.gemm_nt(a, b, bias=bi, residual=res, stats=st)
+            return c, st
+        os.environ["SNIPER_GEMM_TAIL"] = "0"
+        try:
+            c0, s0 = run()
+        finally:
+            os.environ.pop("SNIPER_GEMM_TAIL", None)
+        c1, s1 = run()
+        c2, s2 = run()
+        torch.cuda.synchronize()
+        assert torch.equal(c1, c2)
+        scale = float(c0.abs().max())
+        assert float((c0 - c1).abs().max()) <= 2e-5 * scale + 1e-4
+        # statistics are those of the values actually stored, counted exactly once
+        ref1 = torch.cat([c1.double().sum(0), (c1.double() ** 2).sum(0)])
+        den = torch.cat([c1.double().abs().sum(0), (c1.double() ** 2).sum(0)]) + 1.0
+        assert ((s1 - ref1).abs() / den).max().item() < 1e-5
+    # NHWC conv (3x3, 160 tiles of 128 pixels) with the tail split on vs off
+    x = torch.randn(20, 32, 32, 128, device="cuda")
+    w = torch.randn(256, 9 * 128, device="cuda") * 0.05
+    os.environ["SNIPER_GEMM_TAIL"] = "0"
+    try:
+        y0 = ops.conv2d_nhwc(x, w, kh=3, kw=3, pad=1, relu=True)
+    finally:
+        os.environ.pop("SNIPER_GEMM_TAIL", None)
+    y1 = ops.conv2d_nhwc(x, w, kh=3, kw=3, pad=1, relu=True)
+    assert float((y0 - y1).abs().max()) <= 2e-5 * float(y0.abs().max()) + 1e-5

@@ -1,0 +1,54 @@
+"""Times single tcgen05 launches (CUDA events, rotating operands larger than L2) under different env settings.
+Usage: python tools/gemm_time.py  (edit CASES / SETTINGS below)"""
+import os
+import sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from sniper_b200 import ops
+
+CASES = [("conv3x3", 20, 32, 32, 256, 256), ("gemm", 20480, 256, 1024), ("gemm", 20480, 1024, 256),
+         ("gemm", 20480, 512, 4608), ("gemm", 6000, 128, 12544), ("conv3x3", 20, 32, 32, 3072, 512)]
+SETTINGS = [{"SNIPER_GEMM_TAIL": "0"}, {"SNIPER_GEMM_TAIL_MAXS": "2"}, {"SNIPER_GEMM_TAIL_MAXS": "3"},
+            {"SNIPER_GEMM_TAIL_MAXS": "4"}, {"SNIPER_GEMM_TAIL_MAXS": "6"}, {"SNIPER_GEMM_TAIL_MAXS": "16"}]
+if len(sys.argv) > 1:
+    SETTINGS = [dict(kv.split("=") for kv in a.split(",") if kv) for a in sys.argv[1:]]
+
+
+def timed(fn, reps=20):
+    for _ in range(3):
+        fn(0)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for i, (a, b) in enumerate(ev):
+        a.record(); fn(i); b.record()
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    return ts[len(ts) // 2] * 1e3
+
+
+for case in CASES:
+    if case[0] == "gemm":
+        _, M, N, K = case
+        nbuf = max(2, int(300e6 // (4 * (M * K + M * N))) + 1)
+        A = [torch.randn(M, K, device="cuda") for _ in range(nbuf)]
+        B = torch.randn(N, K, device="cuda")
+        C = [torch.empty(M, N, device="cuda") for _ in range(nbuf)]
+        fn = lambda i: ops.gemm_nt(A[i % nbuf], B, out=C[i % nbuf])
+        flop = 2.0 * M * N * K
+    else:
+        _, NB, H, W, Cin, Cout = case
+        nbuf = max(2, int(300e6 // (4 * NB * H * W * (Cin + Cout))) + 1)
+        X = [torch.randn(NB, H, W, Cin, device="cuda") for _ in range(nbuf)]
+        Wt = torch.randn(Cout, 9 * Cin, device="cuda") * 0.02
+        Y = [torch.empty(NB, H, W, Cout, device="cuda") for _ in range(nbuf)]
+        fn = lambda i: ops.conv2d_nhwc(X[i % nbuf], Wt, kh=3, kw=3, pad=1, out=Y[i % nbuf])
+        flop = 2.0 * NB * H * W * Cout * 9 * Cin
+    out = []
+    for st in SETTINGS:
+        for k in ("SNIPER_GEMM_TAIL", "SNIPER_GEMM_TAIL_MAXS", "SNIPER_GEMM_BN", "SNIPER_GEMM_2SM", "SNIPER_GEMM_TMA_STORE"):
+            os.environ.pop(k, None)
+        os.environ.update(st)
+        us = timed(fn)
+        out.append("%s: %.1f us %.0f TF/s" % (",".join("%s=%s" % kv for kv in st.items()).replace("SNIPER_GEMM_", ""), us, flop / us / 1e6))
+    print(case, " | ".join(out), flush=True)
+    del fn
