@@ -71,6 +71,15 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def ncu_traffic():
+    """DRAM bytes per tcgen05 launch from the committed ncu capture (profiles/gemm_dram_r01.json); None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "gemm_dram_r01.json")))
+        return d["dram_read_bytes_per_launch"] + d["dram_write_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def tc_kernel_time(trainer):
     """CUDA-event time and algorithmic FLOPs of every tcgen05 launch of one (eager) training step."""
     import torch
@@ -105,10 +114,13 @@ def tc_kernel_time(trainer):
     for n in names:
         orig[n] = getattr(L, n)
         L._cache[n] = wrap(n, orig[n])
+    ws = trainer.net.cfg.wsched
+    ws_enabled, ws.enabled = ws.enabled, False     # single stream: per-launch events must not overlap other kernels
     try:
         trainer.net.forward_backward(trainer.static)
         torch.cuda.synchronize()
     finally:
+        ws.enabled = ws_enabled
         for n in names:
             L._cache[n] = orig[n]
     times = [a.elapsed_time(b) for a, b in events]
@@ -222,7 +234,7 @@ def run_ours(args):
             "gpu_launches": int(trainer.launches_per_step * args.steps),
             "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<tf32> (all tcgen05 GEMM/conv/wgrad launches of a step)",
                          "achieved": round(achieved, 1), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
-                         "frac": round(achieved / peak_tf, 4), "traffic": None,
+                         "frac": round(achieved / peak_tf, 4), "traffic": ncu_traffic(),
                          "launches_per_step": tc_n, "kernel_ms_per_step": round(tc_ms, 3),
                          "algorithmic_gflop_per_step": round(tc_flops / 1e9, 1),
                          "peak_source": "%s bf16_tflops_sustained / 2 (TF32 = half the bf16 issue rate)" % peak_src,

@@ -263,7 +263,8 @@ def test_tail_split_matches_whole_tiles_and_is_deterministic():
         torch.cuda.synchronize()
         assert torch.equal(c1, c2)
         scale = float(c0.abs().max())
-        assert float((c0 - c1).abs().max()) <= 2e-5 * scale + 1e-4
+        # the K sum is re-associated (slices accumulate separately in TMEM): far below the TF32 operand rounding
+        assert float((c0 - c1).abs().max()) <= 1e-4 * scale
         # statistics are those of the values actually stored, counted exactly once
         ref1 = torch.cat([c1.double().sum(0), (c1.double() ** 2).sum(0)])
         den = torch.cat([c1.double().abs().sum(0), (c1.double() ** 2).sum(0)]) + 1.0
@@ -277,4 +278,4 @@ def test_tail_split_matches_whole_tiles_and_is_deterministic():
     finally:
         os.environ.pop("SNIPER_GEMM_TAIL", None)
     y1 = ops.conv2d_nhwc(x, w, kh=3, kw=3, pad=1, relu=True)
-    assert float((y0 - y1).abs().max()) <= 2e-5 * float(y0.abs().max()) + 1e-5
+    assert float((y0 - y1).abs().max()) <= 1e-4 * float(y0.abs().max())
