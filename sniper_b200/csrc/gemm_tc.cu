@@ -77,6 +77,11 @@ struct GemmParams {
   int tail_first, tail_s;
   float4* tail_ws;
   int* tail_cnt;
+  // ---- tail N-split (preferred when block_n = 256): every tile >= tail_first is cut into tail_p column pieces of
+  // block_n / tail_p columns (own TMA box tma_bp, own instruction descriptor), one piece per CTA.  Same K order as a
+  // whole tile -> bit-identical results, no fix-up.  tail_p = 0: off.  (tail_s and tail_p are mutually exclusive.)
+  int tail_p;
+  uint32_t idesc_piece;
   double* stats;          // optional [2*N]: += per-column sum and sum of squares of the stored values
                           // (train-mode BatchNorm statistics of the consumer, fused into the producer)
 };
@@ -259,6 +264,8 @@ struct TileCoord {
   int tile_m, tile_n, split;
   int kb0, nkb;       // k-block range of this work unit
   int slice, tail;    // tail split: K-slice index and tail-tile index (slice = -1: whole tile)
+  int col0, ncols;    // output columns of this work unit (K-major modes)
+  int piece;          // 1 if this unit is a column piece of a tail tile
 };
 
 // work unit u of a cluster -> tile of this CTA (cluster of 2: consecutive M tiles, same N tile)
@@ -274,11 +281,23 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int 
     c.nkb = base + (c.slice < rem ? 1 : 0);
     u = p.tail_first + c.tail;
   }
+  int pc = 0;
+  c.piece = 0;
+  c.ncols = p.block_n;
+  if (p.tail_p > 0 && u >= p.tail_first) {
+    const int v = u - p.tail_first;
+    const int tt = v / p.tail_p;
+    pc = v - tt * p.tail_p;
+    c.piece = 1;
+    c.ncols = p.block_n / p.tail_p;
+    u = p.tail_first + tt;
+  }
   const int tiles_mp = (p.tiles_m + p.cluster - 1) / p.cluster;
   c.tile_n = u % p.tiles_n;
   const int r = u / p.tiles_n;
   c.tile_m = (r % tiles_mp) * p.cluster + cta_rank;
   c.split = r / tiles_mp;
+  c.col0 = c.tile_n * p.block_n + pc * c.ncols;
   return c;
 }
 
@@ -292,7 +311,8 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int 
 template <int DT, int CG, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ GemmParams p) {
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_bp,
+               const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A 16KB | B block_n*128B)] | epilogue staging 8 warps x 4 KB | barriers
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -312,12 +332,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int unit0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int unit_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int whole_tiles = ((p.tiles_m + CG - 1) / CG) * p.tiles_n * p.splits;
-  const int total_tiles = p.tail_s > 0 ? p.tail_first + (whole_tiles - p.tail_first) * p.tail_s : whole_tiles;  // units
+  const int tail_mult = p.tail_s > 0 ? p.tail_s : (p.tail_p > 0 ? p.tail_p : 1);
+  const int total_tiles = p.tail_first + (whole_tiles - p.tail_first) * tail_mult;   // work units
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (EPI == EPI_TMA) tma_prefetch_desc(&tma_c);
+    if (p.tail_p > 0) tma_prefetch_desc(&tma_bp);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -372,16 +394,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (!leader) {
             // nothing to issue
           } else if (p.mode == MODE_GEMM) {
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
+            if (cta_rank == 0)
+              mbar_expect_tx(&full_bar[s], tc.piece ? (uint32_t)(kStageABytes + tc.ncols * 128) : p.stage_tx_bytes);
             if (CG == 2) {
               tma_load_4d_2sm(sa, &tma_a, &full_bar[s], kb * E, tc.tile_m * 128, 0, 0);
               tma_load_4d_2sm(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n + cta_rank * (p.block_n >> 1), 0, 0);
             } else {
               tma_load_4d(sa, &tma_a, &full_bar[s], kb * E, tc.tile_m * 128, 0, 0);
-              tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
+              tma_load_4d(sb, tc.piece ? &tma_bp : &tma_b, &full_bar[s], kb * E, tc.col0, 0, 0);
             }
           } else if (p.mode == MODE_CONV) {
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], p.stage_tx_bytes);
+            if (cta_rank == 0)
+              mbar_expect_tx(&full_bar[s], tc.piece ? (uint32_t)(kStageABytes + tc.ncols * 128) : p.stage_tx_bytes);
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
             if (CG == 2) {
               tma_load_4d_2sm(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
@@ -390,7 +414,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             } else {
               tma_load_4d(sa, &tma_a, &full_bar[s], cb * E, ow0 * p.conv_stride + p.tap_dw[tap],
                           oh0 * p.conv_stride + p.tap_dh[tap], n_img);
-              tma_load_4d(sb, &tma_b, &full_bar[s], kb * E, tc.tile_n * p.block_n, 0, 0);
+              tma_load_4d(sb, tc.piece ? &tma_bp : &tma_b, &full_bar[s], kb * E, tc.col0, 0, 0);
             }
           } else {
             // WGRAD: k-block = kp consecutive output pixels of one image row block
@@ -433,7 +457,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1u);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_cols;
-        const int nkb = tile_coord(p, t, 0).nkb;
+        const TileCoord mtc = tile_coord(p, t, 0);
+        const int nkb = mtc.nkb;
+        const uint32_t idesc = mtc.piece ? p.idesc_piece : p.idesc;
         for (int i = 0; i < nkb; ++i) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
@@ -449,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               umma_commit_2sm(&empty_bar[s], 3);   // frees the stage in both CTAs' rings
             } else {
               for (int k = 0; k < p.mmas_per_kb; ++k)
-                umma<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), p.idesc,
+                umma<DT>(tmem_d, adesc0 + (uint64_t)(k * p.a_kadv), bdesc0 + (uint64_t)(k * p.b_kadv), idesc,
                          (i | k) != 0 ? 1u : 0u);
               umma_commit(&empty_bar[s]);
             }
@@ -467,7 +493,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int m_local = q * 32 + lane;
-    const int cols_per_warp = p.block_n >> 1;   // block_n >= 64
     uint32_t lt = 0;
     for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
       const TileCoord tc = tile_coord(p, t, cta_rank);
@@ -486,7 +511,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         row = (long)tc.tile_m * 128 + m_local;
         row_ok = row < p.M && tc.tile_m < p.tiles_m;
       }
-      int col_base = tc.tile_n * p.block_n;
+      const int cols_per_warp = tc.ncols >> 1;   // unit width >= 64
+      int col_base = tc.col0;
       if (p.mode == MODE_WGRAD) {
         const int tap = tc.tile_n / p.wg_cin_blocks;
         col_base = tap * (p.wg_cin_blocks * p.block_n) + (tc.tile_n - tap * p.wg_cin_blocks) * p.block_n;
@@ -955,12 +981,24 @@ TailSlot* tail_slot(cudaStream_t stream) {
 
 // Decide the tail split of a K-major launch (see GemmParams::tail_*).  SNIPER_GEMM_TAIL=0 disables it.
 void plan_tail(GemmParams& p, long tiles, long grid_units, cudaStream_t stream) {
-  p.tail_s = 0; p.tail_first = 0; p.tail_ws = nullptr; p.tail_cnt = nullptr;
-  const char* e = getenv("SNIPER_GEMM_TAIL");
-  if (e && e[0] == '0') return;
+  p.tail_s = 0; p.tail_p = 0; p.tail_first = (int)tiles; p.tail_ws = nullptr; p.tail_cnt = nullptr;
+  const char* e = getenv("SNIPER_GEMM_TAIL");   // 0 = off, 1 = K-slices only, 2 (default) = column pieces, else K-slices
+  const int mode = e ? atoi(e) : 2;
+  if (mode == 0) return;
   if (p.mode == MODE_WGRAD || p.cluster != 1 || !p.epi_tma || p.splits != 1) return;
   const long tail = tiles % grid_units;
   if (tail == 0 || tail * 2 > grid_units) return;
+  if (mode == 2 && p.block_n == 256 && tiles > grid_units) {
+    // column pieces: 4 x 64 columns if they fit one wave, else 2 x 128
+    long pcs = tail * 4 <= grid_units ? 4 : 2;
+    if (const char* m = getenv("SNIPER_GEMM_TAIL_MAXP")) pcs = pcs < atoi(m) ? pcs : atoi(m);
+    if (pcs >= 2) {
+      p.tail_p = (int)pcs;
+      p.tail_first = (int)(tiles - tail);
+      p.idesc_piece = make_idesc(p.dtype, 0, 0, 128, (int)(p.block_n / pcs));
+      return;
+    }
+  }
   // Cost model fitted to tools/gemm_time.py on B200: a 128 x 256 tile costs ~0.43 us per k-block; parking the
   // slices, the arrival counter and the late epilogue cost ~(9 + 2.4 S) us.  The split pays off for K >~ 2000 only
   // (K = 2304: 62 -> 56 us with S = 4; K = 1024: 41 -> 43 us, so it stays off there).
@@ -984,17 +1022,34 @@ void plan_tail(GemmParams& p, long tiles, long grid_units, cudaStream_t stream) 
   p.tail_cnt = slot->cnt;
 }
 
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 tiles, cudaStream_t stream) {
-  CUtensorMap mc;
+// K-major B operand [N rows, K] as launch() needs it to build the TMA map of a column piece
+struct BOperand {
+  const void* ptr;
+  uint64_t K, N, ld_bytes;
+};
+
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 tiles, cudaStream_t stream,
+           const BOperand* bop = nullptr) {
+  CUtensorMap mc, mbp;
+  memset(&mbp, 0, sizeof(mbp));
   if (make_out_map(&mc, p)) return -1;
   p.tiles_m = (int)tiles.x; p.tiles_n = (int)tiles.y; p.splits = (int)tiles.z;
   long units = (long)((tiles.x + p.cluster - 1) / p.cluster) * tiles.y * tiles.z;
   const long max_units = sn::kNumSMs / p.cluster;
   plan_tail(p, units, max_units, stream);
+  if (p.tail_p > 0 && !bop) { p.tail_p = 0; p.tail_first = (int)units; }
+  if (p.tail_p > 0) {
+    const uint64_t d[4] = {bop->K, bop->N, 1, 1};
+    const uint64_t st[3] = {bop->ld_bytes, bop->ld_bytes * bop->N, bop->ld_bytes * bop->N};
+    const uint32_t b[4] = {(uint32_t)p.elems_per_128B, (uint32_t)(p.block_n / p.tail_p), 1, 1};
+    const uint32_t ones[4] = {1, 1, 1, 1};
+    if (make_map(&mbp, p.dtype, bop->ptr, d, st, b, ones)) return -1;
+  }
   if (p.tail_s > 0) units = p.tail_first + (units - p.tail_first) * p.tail_s;
+  if (p.tail_p > 0) units = p.tail_first + (units - p.tail_first) * p.tail_p;
   dim3 grid((unsigned)((units < max_units ? units : max_units) * p.cluster), 1, 1);
   const size_t smem = smem_bytes(p.stages, p.block_n);
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
   static const KernelFn kernels[2][2][3] = {
       {{gemm_tc_kernel<DT_TF32, 1, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 1, EPI_STATS>, gemm_tc_kernel<DT_TF32, 1, EPI_TMA>},
        {gemm_tc_kernel<DT_TF32, 2, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 2, EPI_STATS>, gemm_tc_kernel<DT_TF32, 2, EPI_TMA>}},
@@ -1024,7 +1079,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
     const char* e = getenv("SNIPER_GEMM_CLUSTER_ATTR");   // A/B: force the (1,1,1) cluster attribute on 1-SM launches
     cfg.numAttrs = (p.cluster > 1 || (e && e[0] == '1')) ? 1 : 0;
   }
-  SN_CUDA(cudaLaunchKernelEx(&cfg, kernels[p.dtype == DT_TF32 ? 0 : 1][p.cluster == 2 ? 1 : 0][p.epi_tma ? EPI_TMA : (p.stats ? EPI_STATS : EPI_DIRECT)], ma, mb, mc, p));
+  SN_CUDA(cudaLaunchKernelEx(&cfg, kernels[p.dtype == DT_TF32 ? 0 : 1][p.cluster == 2 ? 1 : 0][p.epi_tma ? EPI_TMA : (p.stats ? EPI_STATS : EPI_DIRECT)], ma, mb, mc, mbp, p));
   SN_LAUNCH_CHECK();
   return 0;
 }
@@ -1128,7 +1183,8 @@ int sniper_gemm_nt(const void* A, long lda, const void* B, long ldb, float* C, l
     if (make_map(&mb, dtype, B, d, s, b, ones)) return -1;
   }
   dim3 grid(sn::div_up(M, 128), sn::div_up(N, bn), 1);
-  return launch(ma, mb, p, grid, (cudaStream_t)stream);
+  const BOperand bop = {B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * esz};
+  return launch(ma, mb, p, grid, (cudaStream_t)stream, &bop);
 }
 
 // NHWC implicit-GEMM convolution forward (also used for stride-1 data gradients with flipped weights):
@@ -1182,7 +1238,8 @@ int sniper_conv2d_nhwc(const void* X, long x_ld, int NB, int H, int W, int Cin, 
     if (make_map(&mb, dtype, Wt, d, s, b, ones)) return -1;
   }
   dim3 grid(NB * p.tiles_per_img, sn::div_up(Cout, bn), 1);
-  return launch(ma, mb, p, grid, (cudaStream_t)stream);
+  const BOperand bop = {Wt, (uint64_t)ntaps * Cin, (uint64_t)Cout, (uint64_t)ntaps * Cin * esz};
+  return launch(ma, mb, p, grid, (cudaStream_t)stream, &bop);
 }
 
 // Weight gradient:  dW[co, t*Cin + ci] += sum_{n,oh,ow} dY[(n,oh,ow), co] * X[n, oh*stride+dh[t], ow*stride+dw[t], ci]

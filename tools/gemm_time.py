@@ -8,8 +8,8 @@ from sniper_b200 import ops
 
 CASES = [("conv3x3", 20, 32, 32, 256, 256), ("gemm", 20480, 256, 1024), ("gemm", 20480, 1024, 256),
          ("gemm", 20480, 512, 4608), ("gemm", 6000, 128, 12544), ("conv3x3", 20, 32, 32, 3072, 512)]
-SETTINGS = [{"SNIPER_GEMM_TAIL": "0"}, {"SNIPER_GEMM_TAIL_MAXS": "2"}, {"SNIPER_GEMM_TAIL_MAXS": "3"},
-            {"SNIPER_GEMM_TAIL_MAXS": "4"}, {"SNIPER_GEMM_TAIL_MAXS": "6"}, {"SNIPER_GEMM_TAIL_MAXS": "16"}]
+SETTINGS = [{"SNIPER_GEMM_TAIL": "0"}, {"SNIPER_GEMM_TAIL": "1"}, {"SNIPER_GEMM_TAIL": "2", "SNIPER_GEMM_TAIL_MAXP": "2"},
+            {"SNIPER_GEMM_TAIL": "2"}]
 if len(sys.argv) > 1:
     SETTINGS = [dict(kv.split("=") for kv in a.split(",") if kv) for a in sys.argv[1:]]
 
@@ -45,7 +45,7 @@ for case in CASES:
         flop = 2.0 * NB * H * W * Cout * 9 * Cin
     out = []
     for st in SETTINGS:
-        for k in ("SNIPER_GEMM_TAIL", "SNIPER_GEMM_TAIL_MAXS", "SNIPER_GEMM_BN", "SNIPER_GEMM_2SM", "SNIPER_GEMM_TMA_STORE"):
+        for k in ("SNIPER_GEMM_TAIL", "SNIPER_GEMM_TAIL_MAXS", "SNIPER_GEMM_TAIL_MAXP", "SNIPER_GEMM_BN", "SNIPER_GEMM_2SM", "SNIPER_GEMM_TMA_STORE"):
             os.environ.pop(k, None)
         os.environ.update(st)
         us = timed(fn)
