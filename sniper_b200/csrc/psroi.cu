@@ -9,6 +9,7 @@
 // 1 = NHWC data [B,H,W,C], (n,ph,pw,c) output (the native layout of this framework: a warp owns 32
 // consecutive channels of one bin, so every bilinear corner is one coalesced 128-byte gather and the
 // backward scatter is a coalesced RED).
+#include <stdlib.h>
 #include "common.cuh"
 #include <math.h>
 
@@ -388,6 +389,57 @@ __global__ void __launch_bounds__(256) deform_psroi_bwd_nhwc_kernel(PsArgs p, lo
   }
 }
 
+// Forward in the same separable form (default on the product path; SNIPER_PSROI_EXACT=1 selects the kernel above,
+// which keeps the oracle's per-sample operation order and is bit-identical to it).  A bin's 4 x 4 sample grid
+// touches only ~3 x 3 distinct feature pixels, so gathering each pixel once with the summed weight Wy[y] * Wx[x]
+// replaces 64 float4 corner loads per 128 channels by ~9-16 (the exact kernel ran at ~50 % of the L1 bandwidth).
+// Results agree with the per-sample order to fp32 rounding (|rel| ~ 1e-6); count = valid samples, as the reference.
+template <int CC>
+__global__ void __launch_bounds__(256) deform_psroi_fwd_sep_nhwc_kernel(PsArgs p, long nbins) {
+  const int lane = threadIdx.x & 31;
+  const int S = p.sample_per_part;
+  for (long bin = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; bin < nbins;
+       bin += ((long)gridDim.x * blockDim.x) >> 5) {
+    const int pw = (int)(bin % p.pooled);
+    const int ph = (int)((bin / p.pooled) % p.pooled);
+    const int n = (int)(bin / ((long)p.pooled * p.pooled));
+    Geom g;
+    deform_geom(p, n, 0, ph, pw, g);
+    AxisTab ax, ay;
+    axis_build(ax, g.wstart, g.sub_w, S, p.width);
+    axis_build(ay, g.hstart, g.sub_h, S, p.height);
+    const int cnt = ax.nvalid * ay.nvalid;
+    float4 sum[CC];
+#pragma unroll
+    for (int k = 0; k < CC; ++k) sum[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* img = p.data + (size_t)g.roi_batch_ind * p.height * p.width * p.channels + lane * 4;
+    if (cnt) {
+      for (int a = 0; a < ay.n; ++a) {
+        const float* rowp = img + (size_t)ay.idx[a] * p.width * p.channels;
+        for (int b = 0; b < ax.n; ++b) {
+          const float wgt = ay.w[a] * ax.w[b];
+          if (wgt == 0.f) continue;
+          const float* px = rowp + (size_t)ax.idx[b] * p.channels;
+#pragma unroll
+          for (int k = 0; k < CC; ++k) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(px + k * 128));
+            sum[k].x = fmaf(wgt, v.x, sum[k].x); sum[k].y = fmaf(wgt, v.y, sum[k].y);
+            sum[k].z = fmaf(wgt, v.z, sum[k].z); sum[k].w = fmaf(wgt, v.w, sum[k].w);
+          }
+        }
+      }
+    }
+    const float fc = (float)cnt;
+    const float inv = cnt ? 1.0f / fc : 0.f;
+    float* o = p.top_data + bin * p.channels + lane * 4;
+#pragma unroll
+    for (int k = 0; k < CC; ++k) {
+      *reinterpret_cast<float4*>(o + k * 128) = make_float4(sum[k].x * inv, sum[k].y * inv, sum[k].z * inv, sum[k].w * inv);
+      if (p.top_count) *reinterpret_cast<float4*>(p.top_count + bin * p.channels + lane * 4 + k * 128) = make_float4(fc, fc, fc, fc);
+    }
+  }
+}
+
 bool fast_nhwc_ok(const PsArgs& a) {
   return a.layout == 1 && a.group_size == 1 && a.num_classes == 1 && a.sample_idx == nullptr &&
          a.sample_per_part <= 4 &&
@@ -509,9 +561,16 @@ int sniper_deform_psroi_fwd(const float* data, const float* rois, const float* t
   if (fast_nhwc_ok(a)) {
     const long nbins = (long)num_rois * pooled_size * pooled_size;
     const int g = fast_grid(nbins);
-    if (channels == 128) deform_psroi_fwd_nhwc_kernel<1><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
-    else if (channels == 256) deform_psroi_fwd_nhwc_kernel<2><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
-    else deform_psroi_fwd_nhwc_kernel<4><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+    const char* ex = getenv("SNIPER_PSROI_EXACT");
+    if (ex && ex[0] == '1') {
+      if (channels == 128) deform_psroi_fwd_nhwc_kernel<1><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+      else if (channels == 256) deform_psroi_fwd_nhwc_kernel<2><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+      else deform_psroi_fwd_nhwc_kernel<4><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+    } else {
+      if (channels == 128) deform_psroi_fwd_sep_nhwc_kernel<1><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+      else if (channels == 256) deform_psroi_fwd_sep_nhwc_kernel<2><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+      else deform_psroi_fwd_sep_nhwc_kernel<4><<<g, 256, 0, (cudaStream_t)stream>>>(a, nbins);
+    }
     SN_LAUNCH_CHECK();
     return 0;
   }

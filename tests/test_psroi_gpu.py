@@ -70,11 +70,23 @@ def test_deform_psroi_sniper_shape():
             np.testing.assert_array_equal(g_cnt, cnt)
             assert g_out.tobytes() == np.ascontiguousarray(out).tobytes()
             if layout == 1:
-                # warp-per-bin fast path (taken when no sample indices are requested): same bits
-                f_out, f_cnt, _ = ops.deform_psroi_fwd(d, _t(rois), _t(trans), pooled_size=7, part_size=7,
-                                                       sample_per_part=4, no_trans=no_trans, layout=1, **kw)
+                import os
+                # warp-per-bin kernels (taken when no sample indices are requested).  SNIPER_PSROI_EXACT=1: per-sample
+                # operation order of the oracle -> same bits; default: separable form (each touched pixel gathered
+                # once with the summed weight) -> same counts, values to fp32 rounding (tolerance 2e-6 * max|data|).
+                os.environ["SNIPER_PSROI_EXACT"] = "1"
+                try:
+                    f_out, f_cnt, _ = ops.deform_psroi_fwd(d, _t(rois), _t(trans), pooled_size=7, part_size=7,
+                                                           sample_per_part=4, no_trans=no_trans, layout=1, **kw)
+                finally:
+                    os.environ.pop("SNIPER_PSROI_EXACT", None)
                 assert f_out.cpu().numpy().transpose(0, 3, 1, 2).tobytes() == g_out.tobytes()
                 np.testing.assert_array_equal(f_cnt.cpu().numpy().transpose(0, 3, 1, 2), cnt)
+                s_out, s_cnt, _ = ops.deform_psroi_fwd(d, _t(rois), _t(trans), pooled_size=7, part_size=7,
+                                                       sample_per_part=4, no_trans=no_trans, layout=1, **kw)
+                np.testing.assert_array_equal(s_cnt.cpu().numpy().transpose(0, 3, 1, 2), cnt)
+                err = np.abs(s_out.cpu().numpy().transpose(0, 3, 1, 2) - out).max()
+                assert err <= 2e-6 * np.abs(data).max(), err
     g = rng.randn(200, 256, 7, 7).astype(np.float32)
     dd, td = O.deform_psroi_bwd(g, cnt, data, rois, trans, pooled=7, part_size=7, spp=4, no_trans=False, **kw)
     g_dd, g_td = ops.deform_psroi_bwd(_t(g.transpose(0, 2, 3, 1)), _t(data.transpose(0, 2, 3, 1)), _t(rois), _t(trans),
