@@ -80,6 +80,53 @@ def ncu_traffic():
         return None
 
 
+def entry_point_breakdown(trainer, path):
+    """CUDA-event time per C-ABI entry point over one eager, single-stream training step -> markdown table at `path`
+    (a cheap complement to the ncu launch list: SNIPER_BREAKDOWN=<file>)."""
+    import torch
+    from sniper_b200 import _lib
+    L = _lib.lib()
+    names = [n for n in _lib.SIGNATURES if _lib.KERNELS_PER_CALL.get(n, 1) > 0]
+    rec, orig = [], {}
+
+    def wrap(name, raw):
+        def fn(*a):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = raw(*a)
+            e1.record()
+            rec.append((name, e0, e1))
+            return r
+        return fn
+    for n in names:
+        orig[n] = getattr(L, n)
+        L._cache[n] = wrap(n, orig[n])
+    ws = trainer.net.cfg.wsched
+    ws_enabled, ws.enabled = ws.enabled, False
+    try:
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        trainer.net.forward_backward(trainer.static)
+        trainer.net.update()
+        t1.record()
+        torch.cuda.synchronize()
+    finally:
+        ws.enabled = ws_enabled
+        for n in names:
+            L._cache[n] = orig[n]
+    agg = {}
+    for n, a, b in rec:
+        c = agg.setdefault(n, [0, 0.0])
+        c[0] += 1
+        c[1] += a.elapsed_time(b)
+    tot = sum(v[1] for v in agg.values())
+    with open(path, "w") as f:
+        f.write("| entry point | calls | total ms | share |\n|---|---:|---:|---:|\n")
+        for n, (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("| `%s` | %d | %.3f | %.1f%% |\n" % (n, c, ms, 100 * ms / tot))
+        f.write("\nsum of entry points %.2f ms; eager single-stream step (incl. launch gaps) %.2f ms\n" % (tot, t0.elapsed_time(t1)))
+
+
 def tc_kernel_time(trainer):
     """CUDA-event time and algorithmic FLOPs of every tcgen05 launch of one (eager) training step."""
     import torch
@@ -212,6 +259,8 @@ def run_ours(args):
         chips = args.chips * world * args.steps
         value = chips / (ms / 1e3)
         e2e = chips / (ms_e2e / 1e3)
+        if os.environ.get("SNIPER_BREAKDOWN"):
+            entry_point_breakdown(trainer, os.environ["SNIPER_BREAKDOWN"])
         tc_ms, tc_flops, tc_n = tc_kernel_time(trainer)
         # kind::tf32 issues at half the bf16 rate (1.1 vs 2.25 PFLOP/s nominal): TF32 peak = measured bf16 / 2
         peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0

@@ -69,6 +69,7 @@ struct GemmParams {
   // row mapping for CONV: output pixel (n,oh,ow) -> row ((n*out_H + oh*out_s + out_oh)*out_W + ow*out_s + out_ow)
   int out_H, out_W, out_s, out_oh, out_ow;
   int out_bf16;           // store bf16 instead of fp32
+  int stg_bufs;           // staging buffers per epilogue warp (1, or 2 for short-K launches whose epilogue is exposed)
   int epi_tma;            // 1: epilogue stages 32 x 32 chunks in shared memory and stores / reduces them by TMA (tma_c)
   // ---- tail split (K-major modes): work units [0, tail_first) are whole tiles; every tile >= tail_first (the
   // last, partial wave over the persistent grid) is cut into tail_s K-slices that run on different CTAs.  Slices
@@ -143,6 +144,7 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const 
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -319,7 +321,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const uint32_t b_stage_bytes = (uint32_t)p.block_n * 128u;
   const uint32_t stage_bytes = kStageABytes + b_stage_bytes;
   uint8_t* staging = smem + (size_t)p.stages * stage_bytes;   // 1024-byte aligned (stage sizes are multiples of 1 KB)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (size_t)kStagingBytes * p.stg_bufs);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
@@ -493,6 +495,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int m_local = q * 32 + lane;
+    int sbuf = 0;   // staging buffer the next chunk uses (EPI_TMA)
     uint32_t lt = 0;
     for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
       const TileCoord tc = tile_coord(p, t, cta_rank);
@@ -524,8 +527,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // tensor copy: global writes are full 128-byte lines instead of 32 row-strided 16-byte pieces per
         // instruction, rows outside the tensor are clipped by the TMA.  The residual is read coalesced (4 rows x
         // 128 B per instruction) into the same buffer one chunk ahead.
-        uint8_t* stg = staging + (size_t)(warp - 2) * 4096;
-        const uint32_t stg_u32 = smem_u32(stg);
+        // (with two buffers per warp the store of chunk i is still reading its buffer while chunk i+1 is staged)
+        uint8_t* const stg_base = staging + (size_t)(warp - 2) * p.stg_bufs * 4096;
         const int sw = lane & 7;
         int c_ow = 0, c_oh = 0, c_n = 0;        // TMA coordinates of this warp's 32 rows
         int nvalid = 0;                         // how many of them exist in the tensor (always a prefix)
@@ -631,8 +634,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           const int n0 = col_base + c;
           if (n0 >= p.N || !tile_ok) continue;       // warp-uniform
-          // the previous chunk's bulk store must have finished READING the staging buffer
-          if (lane == 0) bulk_wait_read0();
+          // the bulk store that last used this staging buffer must have finished READING it
+          uint8_t* stg = stg_base + (size_t)sbuf * 4096;
+          if (lane == 0) {
+            if (p.stg_bufs == 2) bulk_wait_read1(); else bulk_wait_read0();
+          }
+          if (p.stg_bufs == 2) sbuf ^= 1;
           __syncwarp();
           if (has_res) {
 #pragma unroll
@@ -894,15 +901,15 @@ uint32_t make_idesc(int dtype, int a_mn_major, int b_mn_major, int M, int N) {
   return d;
 }
 
-int pick_stages(int block_n) {
+int pick_stages(int block_n, int stg_bufs = 1) {
   // one persistent CTA per SM: fill shared memory with the operand ring
   const int stage = kStageABytes + block_n * 128;
-  int s = (227 * 1024 - kStagingBytes - 1024 - 256) / stage;
+  int s = (227 * 1024 - kStagingBytes * stg_bufs - 1024 - 256) / stage;
   return s > 8 ? 8 : s;
 }
 
-size_t smem_bytes(int stages, int block_n) {
-  return (size_t)stages * (kStageABytes + block_n * 128) + kStagingBytes + 1024 + 256;
+size_t smem_bytes(int stages, int block_n, int stg_bufs) {
+  return (size_t)stages * (kStageABytes + block_n * 128) + (size_t)kStagingBytes * stg_bufs + 1024 + 256;
 }
 
 // Output tensor map for the TMA-store epilogue: fp32, 4-D (cols, w, h, n) with the row mapping's strides; box =
@@ -1048,7 +1055,16 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
   if (p.tail_s > 0) units = p.tail_first + (units - p.tail_first) * p.tail_s;
   if (p.tail_p > 0) units = p.tail_first + (units - p.tail_first) * p.tail_p;
   dim3 grid((unsigned)((units < max_units ? units : max_units) * p.cluster), 1, 1);
-  const size_t smem = smem_bytes(p.stages, p.block_n);
+  // Short-K launches are bound by the epilogue (a 128 x 256 tile's MMAs take 0.43 us per k-block, its stores ~7 us):
+  // give each epilogue warp a second staging buffer so that staging chunk i+1 overlaps the bulk store of chunk i,
+  // at the price of one ring stage.  SNIPER_GEMM_STG=1|2 forces a setting (A/B runs).
+  p.stg_bufs = 1;
+  if (p.mode != MODE_WGRAD && p.epi_tma) {
+    p.stg_bufs = p.num_kb <= 24 ? 2 : 1;
+    if (const char* e = getenv("SNIPER_GEMM_STG")) p.stg_bufs = atoi(e) == 2 ? 2 : 1;
+    p.stages = pick_stages(p.block_n, p.stg_bufs);
+  }
+  const size_t smem = smem_bytes(p.stages, p.block_n, p.stg_bufs);
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
   static const KernelFn kernels[2][2][3] = {
       {{gemm_tc_kernel<DT_TF32, 1, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 1, EPI_STATS>, gemm_tc_kernel<DT_TF32, 1, EPI_TMA>},

@@ -6,10 +6,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sniper_b200 import ops
 
-CASES = [("conv3x3", 20, 32, 32, 256, 256), ("gemm", 20480, 256, 1024), ("gemm", 20480, 1024, 256),
-         ("gemm", 20480, 512, 4608), ("gemm", 6000, 128, 12544), ("conv3x3", 20, 32, 32, 3072, 512)]
-SETTINGS = [{"SNIPER_GEMM_TAIL": "0"}, {"SNIPER_GEMM_TAIL": "1"}, {"SNIPER_GEMM_TAIL": "2", "SNIPER_GEMM_TAIL_MAXP": "2"},
-            {"SNIPER_GEMM_TAIL": "2"}]
+CASES = [("gemm", 20480, 1024, 256), ("gemmres", 20480, 1024, 256), ("gemm", 327680, 256, 64), ("gemm", 81920, 512, 128),
+         ("gemm", 81920, 128, 512), ("gemm", 20480, 256, 1024), ("conv3x3", 20, 32, 32, 256, 256)]
+SETTINGS = [{"SNIPER_GEMM_STG": "1"}, {"SNIPER_GEMM_STG": "2"}]
 if len(sys.argv) > 1:
     SETTINGS = [dict(kv.split("=") for kv in a.split(",") if kv) for a in sys.argv[1:]]
 
@@ -27,13 +26,18 @@ def timed(fn, reps=20):
 
 
 for case in CASES:
-    if case[0] == "gemm":
+    if case[0] in ("gemm", "gemmres"):
         _, M, N, K = case
         nbuf = max(2, int(300e6 // (4 * (M * K + M * N))) + 1)
         A = [torch.randn(M, K, device="cuda") for _ in range(nbuf)]
         B = torch.randn(N, K, device="cuda")
         C = [torch.empty(M, N, device="cuda") for _ in range(nbuf)]
-        fn = lambda i: ops.gemm_nt(A[i % nbuf], B, out=C[i % nbuf])
+        if case[0] == "gemmres":
+            R = [torch.randn(M, N, device="cuda") for _ in range(nbuf)]
+            stats_buf = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
+            fn = lambda i: ops.gemm_nt(A[i % nbuf], B, out=C[i % nbuf], residual=R[(i + 1) % nbuf], stats=stats_buf)
+        else:
+            fn = lambda i: ops.gemm_nt(A[i % nbuf], B, out=C[i % nbuf])
         flop = 2.0 * M * N * K
     else:
         _, NB, H, W, Cin, Cout = case
@@ -45,7 +49,7 @@ for case in CASES:
         flop = 2.0 * NB * H * W * Cout * 9 * Cin
     out = []
     for st in SETTINGS:
-        for k in ("SNIPER_GEMM_TAIL", "SNIPER_GEMM_TAIL_MAXS", "SNIPER_GEMM_TAIL_MAXP", "SNIPER_GEMM_BN", "SNIPER_GEMM_2SM", "SNIPER_GEMM_TMA_STORE"):
+        for k in ("SNIPER_GEMM_STG", "SNIPER_GEMM_TAIL", "SNIPER_GEMM_TAIL_MAXS", "SNIPER_GEMM_TAIL_MAXP", "SNIPER_GEMM_BN", "SNIPER_GEMM_2SM", "SNIPER_GEMM_TMA_STORE"):
             os.environ.pop(k, None)
         os.environ.update(st)
         us = timed(fn)
