@@ -5,6 +5,10 @@
                       20 GT boxes + 400 proposals, three scales, chip 512, fixed stride, srand(seed).
   mpt_small.npz     : oracle/mpt.c on a seeded 2-chip input (the reference ships no vectors for this operator).
   psroi_small.npz   : oracle/psroi.c on the reference's own test shapes (test_operator.py:4358-4389).
+  mpt_refcpu.npz    : output of the REFERENCE's own CPU operators -- MultiProposalTargetOp<cpu>::Forward
+                      (multi_proposal_target.cc) and MultiProposalGPUOp<cpu>::Forward (multi_proposal.cc), compiled as
+                      they lie into oracle/_ref/libref_mpt.so / libref_mp.so -- on a seeded 1-chip input with tie-free
+                      scores (inputs are regenerated from the seed by the test).
 Usage: python tests/golden/make_golden.py
 """
 import os
@@ -59,6 +63,21 @@ def main():
     o2, bins = O.psroi_fwd(data, rois, 0.0625, 2, 3, 3)
     np.savez_compressed(os.path.join(HERE, "psroi_small.npz"), data=data, rois=rois, trans=trans, deform_out=o,
                         deform_count=c, deform_sample_idx=si, psroi_out=o2, psroi_bins=bins)
+    # reference CPU operators (the binaries built from /root/reference)
+    seed, B = 77, 1
+    cls_prob, bbox_pred, im_info, gts, vr = synth.mpt_inputs(seed, B)
+    n = cls_prob[:, 21:].size
+    fg = ((np.random.RandomState(1000 + seed).permutation(n) + 1.0) / (n + 1.0)).astype(np.float32).reshape(B, 21, 32, 32)
+    cls_prob = cls_prob.copy()
+    cls_prob[:, 21:] = fg
+    cls_prob[:, :21] = 1.0 - fg
+    ref = O.ref_multi_proposal_target(cls_prob, bbox_pred, im_info, gts, vr, bbox_scale=1.0)
+    assert ref is not None, "build oracle/_ref first (make -C oracle ref)"
+    prois, pscores = O.ref_multi_proposal(cls_prob, bbox_pred, im_info)
+    kept = int((pscores > 0).sum())
+    np.savez_compressed(os.path.join(HERE, "mpt_refcpu.npz"), seed=np.int64(seed), fg=fg, rois=ref["rois"],
+                        label=ref["label"], bbox_target=ref["bbox_target"], bbox_weight=ref["bbox_weight"],
+                        proposal_rois=prois[:kept], proposal_scores=pscores[:kept])
     print("golden fixtures written to", HERE)
 
 

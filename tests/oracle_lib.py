@@ -74,6 +74,84 @@ def multi_proposal_target(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, 
     return dict(rois=rois, label=label, bbox_target=bt, bbox_weight=bw, keep_idx=keep, num_kept=nk, dets=dets)
 
 
+def multi_proposal_target_cpuop(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, feat_stride=16,
+                                scales=(2, 4, 7, 10, 13, 16, 24), ratios=(0.5, 1, 2), post=300, bbox_scale=1.0):
+    """oracle/mpt_cpuop.c: restatement of the reference CPU operator (multi_proposal_target.cc).  gt_boxes [B,100,5]."""
+    cls_prob, bbox_pred = f32(cls_prob), f32(bbox_pred)
+    im_info, gt_boxes, valid_ranges = f32(im_info), f32(gt_boxes), f32(valid_ranges)
+    B, A4, H, W = bbox_pred.shape
+    A = A4 // 4
+    assert gt_boxes.shape[1] == 100
+    s, r = f32(scales), f32(ratios)
+    rois = np.zeros((B * post, 5), np.float32)
+    label = np.zeros((B * post,), np.float32)
+    bt = np.zeros((B * post, 4), np.float32)
+    bw = np.zeros((B * post, 4), np.float32)
+    keep = np.zeros((B * post,), np.int32)
+    nk = np.zeros((B,), np.int32)
+    dets = np.zeros((B * A * H * W, 5), np.float32)
+    rc = lib().oracle_multi_proposal_target_cpuop(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(gt_boxes), _p(valid_ranges),
+                                                  I(B), I(A), I(H), I(W), I(post), I(feat_stride), _p(s), I(len(s)),
+                                                  _p(r), I(len(r)), F(bbox_scale), _p(rois), _p(label), _p(bt), _p(bw),
+                                                  _p(keep), _p(nk), _p(dets))
+    assert rc == 0
+    return dict(rois=rois, label=label, bbox_target=bt, bbox_weight=bw, keep_idx=keep, num_kept=nk, dets=dets)
+
+
+_REF_OPS = {}
+
+
+def ref_op_lib(name):
+    """oracle/_ref/libref_mpt.so / libref_mp.so: the reference's own CPU operators (multi_proposal_target.cc,
+    multi_proposal.cc) compiled from /root/reference by oracle/Makefile.  None if not built."""
+    if name not in _REF_OPS:
+        so = os.path.join(ORACLE_DIR, "_ref", name)
+        _REF_OPS[name] = ctypes.CDLL(so) if os.path.exists(so) else None
+    return _REF_OPS[name]
+
+
+def ref_multi_proposal_target(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, feat_stride=16,
+                              scales=(2, 4, 7, 10, 13, 16, 24), ratios=(0.5, 1, 2), post=300, bbox_scale=1.0,
+                              threshold=0.7):
+    """Runs MultiProposalTargetOp<cpu>::Forward of the REFERENCE binary.  Returns None if the binary is absent."""
+    L = ref_op_lib("libref_mpt.so")
+    if L is None:
+        return None
+    cls_prob, bbox_pred = f32(cls_prob).copy(), f32(bbox_pred).copy()
+    im_info, gt_boxes, valid_ranges = f32(im_info).copy(), f32(gt_boxes).copy(), f32(valid_ranges).copy()
+    B, A4, H, W = bbox_pred.shape
+    A = A4 // 4
+    s, r = f32(scales), f32(ratios)
+    rois = np.zeros((B * post, 5), np.float32)
+    label = np.zeros((B * post, 1), np.float32)
+    bt = np.zeros((B * post, 4), np.float32)
+    bw = np.zeros((B * post, 4), np.float32)
+    rc = L.ref_multi_proposal_target(_p(cls_prob), _p(bbox_pred), _p(im_info), _p(gt_boxes), _p(valid_ranges), I(B), I(A),
+                                     I(H), I(W), I(post), I(feat_stride), _p(s), I(len(s)), _p(r), I(len(r)),
+                                     F(threshold), F(bbox_scale), _p(rois), _p(label), _p(bt), _p(bw))
+    assert rc == 0
+    return dict(rois=rois, label=label[:, 0], bbox_target=bt, bbox_weight=bw)
+
+
+def ref_multi_proposal(cls_prob, bbox_pred, im_info, feat_stride=16, scales=(2, 4, 7, 10, 13, 16, 24),
+                       ratios=(0.5, 1, 2), pre=12000, post=300, min_size=3, threshold=0.7):
+    """Runs MultiProposalGPUOp<cpu>::Forward (multi_proposal.cc) of the REFERENCE binary: (rois, scores)."""
+    L = ref_op_lib("libref_mp.so")
+    if L is None:
+        return None
+    cls_prob, bbox_pred, im_info = f32(cls_prob).copy(), f32(bbox_pred).copy(), f32(im_info).copy()
+    B, A4, H, W = bbox_pred.shape
+    A = A4 // 4
+    s, r = f32(scales), f32(ratios)
+    rois = np.zeros((B * post, 5), np.float32)
+    scores = np.zeros((B * post,), np.float32)
+    rc = L.ref_multi_proposal(_p(cls_prob), _p(bbox_pred), _p(im_info), I(B), I(A), I(H), I(W), I(pre), I(post),
+                              I(min_size), I(feat_stride), _p(s), I(len(s)), _p(r), I(len(r)), F(threshold), _p(rois),
+                              _p(scores))
+    assert rc == 0
+    return rois, scores
+
+
 def deform_psroi_fwd(data, rois, trans, spatial_scale, output_dim, group_size, pooled, part_size, spp, trans_std,
                      no_trans):
     data, rois = f32(data), f32(rois)
