@@ -98,6 +98,25 @@ def multi_proposal_target_cpuop(cls_prob, bbox_pred, im_info, gt_boxes, valid_ra
     return dict(rois=rois, label=label, bbox_target=bt, bbox_weight=bw, keep_idx=keep, num_kept=nk, dets=dets)
 
 
+def multi_proposal(cls_prob, bbox_pred, im_info, feat_stride=16, scales=(2, 4, 7, 10, 13, 16, 24), ratios=(0.5, 1, 2),
+                   pre=12000, post=300, flags=0, roi_iou_thresh=0.3, libm_exp=False):
+    """oracle/mp_cpuop.c: the inference proposal operator (multi_proposal.cc; flags 1 = anchor-type suppression,
+    2 = FastNMS of multi_proposal.cu).  Returns dict(rois, scores, keep_idx, num_kept)."""
+    cls_prob, bbox_pred, im_info = f32(cls_prob), f32(bbox_pred), f32(im_info)
+    B, A4, H, W = bbox_pred.shape
+    A = A4 // 4
+    s, r = f32(scales), f32(ratios)
+    rois = np.zeros((B * post, 5), np.float32)
+    scores = np.zeros((B * post,), np.float32)
+    keep = np.zeros((B * post,), np.int32)
+    nk = np.zeros((B,), np.int32)
+    rc = lib().oracle_multi_proposal(_p(cls_prob), _p(bbox_pred), _p(im_info), I(B), I(A), I(H), I(W), I(pre), I(post),
+                                     I(feat_stride), _p(s), I(len(s)), _p(r), I(len(r)), I(flags), F(roi_iou_thresh),
+                                     I(int(libm_exp)), _p(rois), _p(scores), _p(keep), _p(nk))
+    assert rc == 0
+    return dict(rois=rois, scores=scores, keep_idx=keep, num_kept=nk)
+
+
 _REF_OPS = {}
 
 

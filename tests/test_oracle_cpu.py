@@ -325,3 +325,37 @@ def test_reference_inference_operator_runs():
     k = int((scores > 0).sum())
     assert k > 50 and (np.diff(scores[:k]) <= 0).all()
     assert (rois[:k, 1:] >= 0).all() and (rois[:k, [1, 3]] <= im_info[0, 1] - 1).all()
+
+
+@pytest.mark.parametrize("seed,B,HW", [(11, 1, 32), (12, 2, 32), (13, 1, 20)])
+def test_inference_op_restatement_is_bit_identical_to_the_reference_cpu_operator(seed, B, HW):
+    """oracle/mp_cpuop.c (flags = 0, libm exp) == MultiProposalGPUOp<cpu>::Forward of the reference binary on the kept
+    rows (boxes and scores); the rows after them are rand() fillers in the reference.  HW=20: 8400 anchors < 12000."""
+    cls_prob, bbox_pred, im_info, gts, vr = synth.mpt_inputs(seed, B, 21, HW, HW)
+    cls_prob = _tie_free(cls_prob, seed)
+    rois, scores = _need_ref(O.ref_multi_proposal(cls_prob, bbox_pred, im_info))
+    mine = O.multi_proposal(cls_prob, bbox_pred, im_info, libm_exp=True)
+    for b in range(B):
+        k = int(mine["num_kept"][b])
+        assert k > 50
+        sl = slice(b * 300, b * 300 + k)
+        assert mine["rois"][sl].tobytes() == rois[sl].tobytes()
+        assert mine["scores"][sl].tobytes() == scores[sl].tobytes()
+        assert (scores[b * 300 + k:(b + 1) * 300] == 0).all()       # the reference's filler rows carry score 0
+
+
+def test_inference_op_gpu_build_extras():
+    """The two extras of multi_proposal.cu (pinned by the .cu text only): anchor-type suppression removes exactly the
+    anchor types (i+4)%7==0 / (i+2)%7==0 from the output; FastNMS keeps a superset-or-equal of rows early in the list
+    (it tests fewer pairs) and is identical to the plain NMS when the overlap map admits every pair (thresh <= 0)."""
+    cls_prob, bbox_pred, im_info, gts, vr = synth.mpt_inputs(21, 1)
+    cls_prob = _tie_free(cls_prob, 21)
+    plain = O.multi_proposal(cls_prob, bbox_pred, im_info)
+    sup = O.multi_proposal(cls_prob, bbox_pred, im_info, flags=1)
+    types = sup["keep_idx"][:int(sup["num_kept"][0])] // (32 * 32)
+    assert not np.isin(types % 7, [3, 5]).any()
+    assert np.isin(plain["keep_idx"][:300] // 1024 % 7, [3, 5]).any()
+    fast_all = O.multi_proposal(cls_prob, bbox_pred, im_info, flags=2, roi_iou_thresh=-1.0)
+    assert fast_all["rois"].tobytes() == plain["rois"].tobytes()
+    fast = O.multi_proposal(cls_prob, bbox_pred, im_info, flags=2, roi_iou_thresh=0.3)
+    assert fast["keep_idx"][0] == plain["keep_idx"][0] and int(fast["num_kept"][0]) == 300
