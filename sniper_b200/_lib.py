@@ -19,6 +19,8 @@ SIGNATURES = {
     "sniper_generate_anchors": ("i", "ipipip"),
     "sniper_proposal_decode": ("i", "pppp" "iiiii" "pipi" "iii" "ppp" "p"),
     "sniper_multi_proposal_target_fwd": ("i", "ppppp" "iiiiiii" "pipi" "f" "iii" "pppp" "pp" "pz" "p"),
+    "sniper_multi_proposal_workspace_bytes": ("z", "iiiii"),
+    "sniper_multi_proposal_fwd": ("i", "ppp" "iiiiiii" "pipi" "f" "iiii" "pppp" "pz" "p"),
     "sniper_deform_psroi_fwd": ("i", "ppp" "iiii" "f" "iiiii" "f" "iii" "ppp" "p"),
     "sniper_deform_psroi_bwd": ("i", "pppp" "iiii" "f" "iiiii" "f" "iii" "pp" "p"),
     "sniper_psroi_fwd": ("i", "pp" "iiii" "f" "iiii" "pp" "p"),
@@ -60,7 +62,7 @@ _lib = None
 KERNELS_PER_CALL = {
     "sniper_last_error": 0, "sniper_abi_version": 0, "sniper_multi_proposal_target_workspace_bytes": 0,
     "sniper_generate_anchors": 0, "sniper_chips_generate": 0, "sniper_cpu_nms": 0, "sniper_cpu_soft_nms": 0,
-    "sniper_bbox_overlaps": 0, "sniper_multi_proposal_target_fwd": 2, "sniper_anchor_target": 2, "sniper_bn_stats": 2, "sniper_bn_relu_bwd": 3,
+    "sniper_bbox_overlaps": 0, "sniper_multi_proposal_target_fwd": 2, "sniper_multi_proposal_workspace_bytes": 0, "sniper_multi_proposal_fwd": 4, "sniper_anchor_target": 2, "sniper_bn_stats": 2, "sniper_bn_relu_bwd": 3,
 }
 launches = [0]
 

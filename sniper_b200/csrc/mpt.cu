@@ -54,6 +54,10 @@ struct DecodeArgs {
   const float* valid_ranges;  // [B,2]
   int B, A, H, W, stride, layout;
   int score_cstride, delta_cstride;  // NHWC: number of channels per pixel in each tensor
+  int variant;         // 0: MultiProposalTarget (multi_proposal_target.cu:263-331); 1: MultiProposal inference
+                       //    (multi_proposal.cc:91-105,176: min-size test with +1 and ||, box grown by 1.5, area with +1,
+                       //    no valid-range filter)
+  int suppress_types;  // variant 1: anchor types (a+4)%7==0 || (a+2)%7==0 get score -1 (multi_proposal.cu:505-508)
   float4* boxes;
   float* score_out;
   float* area_out;
@@ -108,16 +112,30 @@ __global__ void __launch_bounds__(256) mpt_decode_kernel(DecodeArgs p, AnchorTab
     y1 = fmaxf(fminf(y1, imh), 0.0f);
     x2 = fmaxf(fminf(x2, imw), 0.0f);
     y2 = fmaxf(fminf(y2, imh), 0.0f);
-    if (__fsub_rn(y2, y1) < 3.0f && __fsub_rn(x2, x1) < 3.0f) {
-      x1 = __fsub_rn(x1, 1.0f);
-      y1 = __fsub_rn(y1, 1.0f);
-      x2 = __fadd_rn(x2, 1.0f);
-      y2 = __fadd_rn(y2, 1.0f);
-      score = -1.0f;
+    float area;
+    if (p.variant == 0) {
+      if (__fsub_rn(y2, y1) < 3.0f && __fsub_rn(x2, x1) < 3.0f) {
+        x1 = __fsub_rn(x1, 1.0f);
+        y1 = __fsub_rn(y1, 1.0f);
+        x2 = __fadd_rn(x2, 1.0f);
+        y2 = __fadd_rn(y2, 1.0f);
+        score = -1.0f;
+      }
+      area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
+      const float vr0 = __ldg(p.valid_ranges + 2 * b), vr1 = __ldg(p.valid_ranges + 2 * b + 1);
+      if (area >= __fmul_rn(vr1, vr1) || area < __fmul_rn(vr0, vr0)) score = -1.0f;
+    } else {
+      if (p.suppress_types && ((a + 4) % 7 == 0 || (a + 2) % 7 == 0)) score = -1.0f;
+      const float iw = __fadd_rn(__fsub_rn(x2, x1), 1.0f), ih = __fadd_rn(__fsub_rn(y2, y1), 1.0f);
+      if (iw < 3.0f || ih < 3.0f) {
+        x1 = __fsub_rn(x1, 1.5f);
+        y1 = __fsub_rn(y1, 1.5f);
+        x2 = __fadd_rn(x2, 1.5f);
+        y2 = __fadd_rn(y2, 1.5f);
+        score = -1.0f;
+      }
+      area = __fmul_rn(__fadd_rn(__fsub_rn(x2, x1), 1.0f), __fadd_rn(__fsub_rn(y2, y1), 1.0f));
     }
-    const float area = __fmul_rn(__fsub_rn(x2, x1), __fsub_rn(y2, y1));
-    const float vr0 = __ldg(p.valid_ranges + 2 * b), vr1 = __ldg(p.valid_ranges + 2 * b + 1);
-    if (area >= __fmul_rn(vr1, vr1) || area < __fmul_rn(vr0, vr0)) score = -1.0f;
     p.boxes[t] = make_float4(x1, y1, x2, y2);
     p.score_out[t] = score;
     p.area_out[t] = area;
@@ -171,6 +189,9 @@ struct NmsArgs {
   int32_t* keep_idx;   // optional [B*R]
   int32_t* num_kept;   // optional [B]
   int do_assign;       // 0: proposals only (MultiProposal-style output), 1: full target assignment
+  const int32_t* id_map;   // optional [B*AHW]: original anchor index of every (compacted) row, reported in keep_idx
+  float* score_out;        // optional [B*R]: score of the kept rows, 0 for filler rows (do_assign = 0)
+  long filler_stride;      // rows per chip used by the filler rule (cu:244-249); AHW unless the rows are compacted
   const int32_t* fast_keep;      // optional results of mpt_nms_fast_kernel: [B,1024], [B], [B]
   const int32_t* fast_nkept;
   const int32_t* fast_fallback;
@@ -554,12 +575,15 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_assign_kernel(NmsArgs 
       if (r < vct) {
         bx = __ldg(boxes + s_keep[r]);
       } else {
-        const float f = (float)(int)(((long)chip * AHW + r) % 100);
+        const float f = (float)(int)(((long)chip * p.filler_stride + r) % 100);
         bx = make_float4(f, f, f + 200.0f, f + 200.0f);
       }
       float* o = p.rois + ((size_t)chip * R + r) * 5;
       o[0] = (float)chip; o[1] = bx.x; o[2] = bx.y; o[3] = bx.z; o[4] = bx.w;
-      if (p.keep_idx) p.keep_idx[(size_t)chip * R + r] = r < vct ? s_keep[r] : -1;
+      if (p.keep_idx)
+        p.keep_idx[(size_t)chip * R + r] =
+            r < vct ? (p.id_map ? p.id_map[(size_t)chip * AHW + s_keep[r]] : s_keep[r]) : -1;
+      if (p.score_out) p.score_out[(size_t)chip * R + r] = r < vct ? p.scores[(size_t)chip * AHW + s_keep[r]] : 0.0f;
     }
     return;
   }
@@ -631,6 +655,102 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_assign_kernel(NmsArgs 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pre-NMS selection of the inference operator (multi_proposal.cc:176-199: only the pre_nms_top_n best-scoring
+// anchors of an image enter the NMS).  One CTA per image: exact K-th key by a 3-pass MSB radix select over the
+// order-preserving 32-bit score keys, then an index-ordered compaction of the K best rows (ties at the K-th score
+// are taken in index order; the reference's std::sort leaves them unspecified).
+struct SelectArgs {
+  const float4* boxes;
+  const float* scores;
+  const float* areas;
+  int AHW, K;
+  float4* boxes_c;   // [B*K]
+  float* scores_c;
+  float* areas_c;
+  int32_t* ids_c;    // original anchor index
+};
+
+__global__ void __launch_bounds__(1024, 1) mp_select_kernel(SelectArgs p) {
+  __shared__ int s_hist[2048];
+  __shared__ uint32_t s_prefix, s_mask;
+  __shared__ int s_remaining;
+  __shared__ int s_warp[32];
+  __shared__ int s_base_lt, s_base_eq;
+  const int img = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const float* sc = p.scores + (size_t)img * p.AHW;
+  if (t == 0) { s_prefix = 0; s_mask = 0; s_remaining = p.K; }
+  __syncthreads();
+  const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+  for (int pass = 0; pass < 3; ++pass) {
+    for (int i = t; i < 2048; i += 1024) s_hist[i] = 0;
+    __syncthreads();
+    const uint32_t prefix = s_prefix, mask = s_mask;
+    const int sh = shifts[pass];
+    const uint32_t bm = (1u << bits[pass]) - 1u;
+    for (int i = t; i < p.AHW; i += 1024) {
+      const uint32_t k = ord_desc(sc[i]);
+      if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> sh) & bm], 1);
+    }
+    __syncthreads();
+    if (t == 0) {
+      int rem = s_remaining, b = 0;
+      while (s_hist[b] < rem) { rem -= s_hist[b]; ++b; }     // terminates: the matching rows number >= rem
+      s_remaining = rem;
+      s_prefix = prefix | ((uint32_t)b << sh);
+      s_mask = mask | (bm << sh);
+    }
+    __syncthreads();
+  }
+  const uint32_t kth = s_prefix;
+  const int take_eq = s_remaining;   // rows equal to the K-th key that still fit
+  if (t == 0) { s_base_lt = 0; s_base_eq = 0; }
+  __syncthreads();
+  for (int i0 = 0; i0 < p.AHW; i0 += 1024) {
+    const int i = i0 + t;
+    uint32_t k = 0xffffffffu;
+    if (i < p.AHW) k = ord_desc(sc[i]);
+    const int lt = (i < p.AHW && k < kth) ? 1 : 0, eq = (i < p.AHW && k == kth) ? 1 : 0;
+    int v = lt | (eq << 16), incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int o = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += o;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += o;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int excl = incl - v + (warp ? s_warp[warp - 1] : 0);
+    const int lt_before = s_base_lt + (excl & 0xffff), eq_before = s_base_eq + (excl >> 16);
+    const int eq_taken_before = eq_before < take_eq ? eq_before : take_eq;
+    const bool take = lt || (eq && eq_before < take_eq);
+    if (take) {
+      const size_t dst = (size_t)img * p.K + lt_before + eq_taken_before;
+      const size_t src = (size_t)img * p.AHW + i;
+      p.boxes_c[dst] = p.boxes[src];
+      p.scores_c[dst] = sc[i];
+      p.areas_c[dst] = p.areas[src];
+      p.ids_c[dst] = i;
+    }
+    __syncthreads();
+    if (t == 0) {
+      const int total = s_warp[31];
+      s_base_lt += total & 0xffff;
+      s_base_eq += total >> 16;
+    }
+    __syncthreads();
+  }
+}
+
 // host twin of multi_proposal_target.cu:75-114 (anchor table is 4*A floats, passed by value)
 int make_anchors(int feat_stride, const float* scales, int ns, const float* ratios, int nr, AnchorTable* out) {
   const float base2 = (float)(feat_stride - 1.0);
@@ -697,6 +817,7 @@ int sniper_proposal_decode(const float* cls_prob, const float* bbox_pred, const 
   a.scores = cls_prob; a.deltas = bbox_pred; a.im_info = im_info; a.valid_ranges = valid_ranges;
   a.B = B; a.A = A; a.H = H; a.W = W; a.stride = feat_stride; a.layout = layout;
   a.score_cstride = score_cstride; a.delta_cstride = delta_cstride;
+  a.variant = 0; a.suppress_types = 0;
   a.boxes = reinterpret_cast<float4*>(boxes); a.score_out = score; a.area_out = area;
   const long total = (long)B * A * H * W;
   int grid = sn::div_up(total, 256);
@@ -710,7 +831,8 @@ static int nms_assign_launch(const float* boxes, const float* score, const float
                              const float* valid_ranges, int B, int AHW, int max_gt, int R, float nms_thresh,
                              float* rois, float* label, float* bbox_target, float* bbox_weight,
                              int32_t* keep_idx, int32_t* num_kept, int do_assign, int32_t* fast_scratch,
-                             void* stream) {
+                             void* stream, const int32_t* id_map = nullptr, float* score_out = nullptr,
+                             long filler_stride = 0) {
   SN_CHECK(AHW >= R, "nms: anchors per chip (%d) < post_nms_top_n (%d)", AHW, R);
   SN_CHECK(AHW <= 32768, "nms: anchors per chip (%d) > 32768", AHW);
   SN_CHECK(R <= 1024, "nms: post_nms_top_n (%d) > 1024", R);
@@ -720,6 +842,7 @@ static int nms_assign_launch(const float* boxes, const float* score, const float
   n.gt_boxes = gt_boxes; n.valid_ranges = valid_ranges; n.AHW = AHW; n.R = R; n.max_gt = max_gt;
   n.nms_thresh = nms_thresh; n.rois = rois; n.label = label; n.bbox_target = bbox_target;
   n.bbox_weight = bbox_weight; n.keep_idx = keep_idx; n.num_kept = num_kept; n.do_assign = do_assign;
+  n.id_map = id_map; n.score_out = score_out; n.filler_stride = filler_stride > 0 ? filler_stride : AHW;
   const size_t smem = (size_t)AHW * 6 + 16;
   static bool attr_set = false;
   const size_t fast_smem = (size_t)kFastCap * (8 + 16 + 4 + 2) + kFastBins * 4 + 1024 * (20 + 2) + 64 * 8 + 64 * 4 + 64;
@@ -767,6 +890,74 @@ int sniper_multi_proposal_target_fwd(const float* cls_prob, const float* bbox_pr
   return nms_assign_launch(boxes, score, area, gt_boxes, valid_ranges, B, A * H * W, max_gt, post_nms_top_n,
                            nms_thresh, rois, label, bbox_target, bbox_weight, keep_idx, num_kept, 1,
                            nms_fast_enabled() ? fast_scratch : nullptr, stream);
+}
+
+// Workspace of sniper_multi_proposal_fwd: decoded rows of every anchor + the compacted pre_nms_top_n rows per image.
+size_t sniper_multi_proposal_workspace_bytes(int B, int A, int H, int W, int pre_nms_top_n) {
+  const size_t total = (size_t)B * A * H * W;
+  const size_t K = (size_t)(pre_nms_top_n < A * H * W ? pre_nms_top_n : A * H * W);
+  return total * 24 + 64 + (size_t)B * K * 28 + 64 + (size_t)B * (1024 + 2) * sizeof(int32_t) + 256;
+}
+
+// Inference proposal operator: drop-in for MultiProposal (multi_proposal-inl.h:55-167; CPU op multi_proposal.cc:273-374,
+// GPU-build op multi_proposal.cu:400-631) entirely on device -- decode, min-size filter, top pre_nms_top_n selection,
+// greedy NMS (> 0.7 as the reference hard-codes; nms_thresh is passed through), rois [B*post,5] and scores [B*post].
+// flags: 1 = anchor-type suppression of the GPU build (.cu:505-508).  The GPU build's FastNMS (flags 2) approximates
+// the NMS through a precomputed anchor-overlap map; this entry point runs the exact NMS of the CPU operator.
+// Rows after the kept ones are rand() boxes in the reference; here the deterministic filler of the training operator
+// with score 0.  keep_idx / num_kept: optional parity outputs (original anchor indices).
+int sniper_multi_proposal_fwd(const float* cls_prob, const float* bbox_pred, const float* im_info, int B, int A, int H,
+                              int W, int pre_nms_top_n, int post_nms_top_n, int feat_stride, const float* scales, int ns,
+                              const float* ratios, int nr, float nms_thresh, int flags, int layout, int score_cstride,
+                              int delta_cstride, float* rois, float* scores, int32_t* keep_idx, int32_t* num_kept,
+                              void* workspace, size_t ws_bytes, void* stream) {
+  SN_CHECK(A == ns * nr && A <= kMaxAnchors, "multi_proposal: A (%d) must equal ns*nr and be <= %d", A, kMaxAnchors);
+  SN_CHECK((flags & ~1) == 0, "multi_proposal: unsupported flags %d (FastNMS of the GPU build is not provided)", flags);
+  SN_CHECK(layout == 0 || layout == 1, "multi_proposal: layout must be 0 (NCHW) or 1 (NHWC)");
+  SN_CHECK(layout == 0 || (delta_cstride % 4 == 0 && ((uintptr_t)bbox_pred & 15) == 0),
+           "multi_proposal: NHWC deltas need 16-byte aligned pixels");
+  SN_CHECK(ws_bytes >= sniper_multi_proposal_workspace_bytes(B, A, H, W, pre_nms_top_n),
+           "multi_proposal: workspace too small");
+  SN_CHECK(((uintptr_t)workspace & 15) == 0, "multi_proposal: workspace must be 16-byte aligned");
+  const int AHW = A * H * W;
+  const int K = pre_nms_top_n < AHW ? pre_nms_top_n : AHW;
+  SN_CHECK(K >= post_nms_top_n && K <= 32768, "multi_proposal: need post_nms_top_n <= min(pre_nms_top_n, A*H*W) <= 32768");
+  const size_t total = (size_t)B * AHW;
+  // carve the workspace (every array 16-byte aligned)
+  unsigned char* wp = static_cast<unsigned char*>(workspace);
+  auto carve = [&wp](size_t bytes) { void* r = wp; wp += (bytes + 15) & ~(size_t)15; return r; };
+  float* boxes = static_cast<float*>(carve(16 * total));
+  float* score = static_cast<float*>(carve(4 * total));
+  float* area = static_cast<float*>(carve(4 * total));
+  float* boxes_c = static_cast<float*>(carve(16 * (size_t)B * K));
+  float* score_c = static_cast<float*>(carve(4 * (size_t)B * K));
+  float* area_c = static_cast<float*>(carve(4 * (size_t)B * K));
+  int32_t* ids_c = static_cast<int32_t*>(carve(4 * (size_t)B * K));
+  int32_t* fast_scratch = static_cast<int32_t*>(carve((size_t)B * (1024 + 2) * sizeof(int32_t)));
+  AnchorTable t;
+  make_anchors(feat_stride, scales, ns, ratios, nr, &t);
+  DecodeArgs a;
+  a.scores = cls_prob; a.deltas = bbox_pred; a.im_info = im_info; a.valid_ranges = nullptr;
+  a.B = B; a.A = A; a.H = H; a.W = W; a.stride = feat_stride; a.layout = layout;
+  a.score_cstride = score_cstride; a.delta_cstride = delta_cstride;
+  a.variant = 1; a.suppress_types = flags & 1;
+  a.boxes = reinterpret_cast<float4*>(boxes); a.score_out = score; a.area_out = area;
+  int grid = sn::div_up((long)total, 256);
+  if (grid > sn::kNumSMs * 8) grid = sn::kNumSMs * 8;
+  mpt_decode_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a, t);
+  SN_LAUNCH_CHECK();
+  const int32_t* id_map = nullptr;
+  if (K < AHW) {
+    SelectArgs sa;
+    sa.boxes = reinterpret_cast<const float4*>(boxes); sa.scores = score; sa.areas = area; sa.AHW = AHW; sa.K = K;
+    sa.boxes_c = reinterpret_cast<float4*>(boxes_c); sa.scores_c = score_c; sa.areas_c = area_c; sa.ids_c = ids_c;
+    mp_select_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(sa);
+    SN_LAUNCH_CHECK();
+    boxes = boxes_c; score = score_c; area = area_c; id_map = ids_c;
+  }
+  return nms_assign_launch(boxes, score, area, nullptr, nullptr, B, K, 0, post_nms_top_n, nms_thresh, rois, nullptr,
+                           nullptr, nullptr, keep_idx, num_kept, 0, nms_fast_enabled() ? fast_scratch : nullptr, stream,
+                           id_map, scores, (long)AHW);
 }
 
 }  // extern "C"

@@ -167,6 +167,61 @@ def MultiProposalTarget(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, **
                   valid_ranges=valid_ranges, op_type='MultiProposalTarget', **kw)
 
 
+@register('MultiProposal')
+class MultiProposalProp(CustomOpProp):
+    """MultiProposalParam (multi_proposal-inl.h:55-100): same keyword names and defaults; outputs `output`, `score`
+    (multi_proposal-inl.h:147-155).  `roi_iou_thresh` belongs to the GPU build's FastNMS overlap map and is accepted
+    and ignored (the exact NMS of the CPU operator runs); `suppress_anchor_types` selects the GPU build's anchor-type
+    suppression (multi_proposal.cu:505-508)."""
+
+    def __init__(self, batch_size=16, rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300, threshold=0.7, rpn_min_size=4,
+                 scales=(2, 4, 7, 10, 13, 16, 24), ratios=(0.5, 1, 2), feature_stride=16, bbox_scale=1.0,
+                 roi_iou_thresh=0.3, workspace=128, suppress_anchor_types=False, layout=ops.NCHW):
+        super(MultiProposalProp, self).__init__(need_top_grad=False)
+        self.post = int(rpn_post_nms_top_n)
+        self.threshold = float(threshold)
+        self.scales = _tuple(scales)
+        self.ratios = _tuple(ratios)
+        self.stride = int(feature_stride)
+        self.layout = int(layout)
+        self.suppress = str(suppress_anchor_types) in ("True", "true", "1")
+        # the reference ignores rpn_pre_nms_top_n and always sorts min(12000, A*H*W) rows (multi_proposal.cc:176)
+        self.pre = 12000
+
+    def list_arguments(self):
+        return ['cls_prob', 'bbox_pred', 'im_info']
+
+    def list_outputs(self):
+        return ['output', 'score']
+
+    def infer_shape(self, in_shape):
+        n = in_shape[0][0] * self.post
+        return in_shape, [[n, 5], [n, 1]], []
+
+    def create_operator(self, ctx, shapes, dtypes):
+        prop = self
+
+        class _Op(CustomOp):
+            def forward(self, is_train, req, in_data, out_data, aux):
+                r = ops.multi_proposal(in_data[0].contiguous(), in_data[1].contiguous(), in_data[2],
+                                       feat_stride=prop.stride, scales=prop.scales, ratios=prop.ratios,
+                                       rpn_pre_nms_top_n=prop.pre, rpn_post_nms_top_n=prop.post,
+                                       threshold=prop.threshold, suppress_anchor_types=prop.suppress,
+                                       layout=prop.layout)
+                for i, t in enumerate(r):
+                    self.assign(out_data[i], req[i], t.view(out_data[i].shape))
+
+            def backward(self, req, out_grad, in_data, out_data, in_grad, aux):
+                for i in range(len(in_grad)):          # multi_proposal.cc:376-394
+                    self.assign(in_grad[i], req[i], 0)
+        return _Op()
+
+
+def MultiProposal(cls_prob, bbox_pred, im_info, **kw):
+    """mx.sym.MultiProposal(...) -> (rois, score)."""
+    return Custom(cls_prob=cls_prob, bbox_pred=bbox_pred, im_info=im_info, op_type='MultiProposal', **kw)
+
+
 class _PoolFn(torch.autograd.Function):
     """Differentiable wrappers so user code written against autograd can call the pooling ops directly."""
 

@@ -56,6 +56,42 @@ def generate_anchors(feat_stride, scales, ratios):
     return out
 
 
+def multi_proposal(cls_prob, bbox_pred, im_info, *, feat_stride=16, scales=(2, 4, 7, 10, 13, 16, 24),
+                   ratios=(0.5, 1, 2), rpn_pre_nms_top_n=12000, rpn_post_nms_top_n=300, threshold=0.7,
+                   suppress_anchor_types=False, layout=NCHW, return_keep=False):
+    """MultiProposal forward -- the inference proposal operator (multi_proposal.cc:273-374 semantics: decode, min-size
+    filter, the rpn_pre_nms_top_n best anchors, greedy NMS), on device.  Returns rois [B*R,5], scores [B*R]
+    (+ keep_idx [B*R] original anchor indices / -1 for filler rows, num_kept [B])."""
+    _f32(cls_prob), _f32(bbox_pred), _f32(im_info)
+    A = len(scales) * len(ratios)
+    if layout == NCHW:
+        B, H, W = bbox_pred.shape[0], bbox_pred.shape[2], bbox_pred.shape[3]
+        assert bbox_pred.shape[1] == 4 * A and cls_prob.numel() == B * 2 * A * H * W
+        sc, dc = 0, 0
+    else:
+        B, H, W = bbox_pred.shape[0], bbox_pred.shape[1], bbox_pred.shape[2]
+        sc, dc = cls_prob.shape[3], bbox_pred.shape[3]
+        assert dc >= 4 * A and sc >= 2 * A
+    R = int(rpn_post_nms_top_n)
+    dev = cls_prob.device
+    rois = torch.empty(B * R, 5, device=dev)
+    scores = torch.empty(B * R, device=dev)
+    keep = torch.empty(B * R, dtype=torch.int32, device=dev) if return_keep else None
+    nkept = torch.empty(B, dtype=torch.int32, device=dev) if return_keep else None
+    L = lib()
+    ws_bytes = L.sniper_multi_proposal_workspace_bytes(B, A, H, W, int(rpn_pre_nms_top_n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    s, sp = _farr(scales)
+    r, rp = _farr(ratios)
+    check(L.sniper_multi_proposal_fwd(
+        _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), B, A, H, W, int(rpn_pre_nms_top_n), R, int(feat_stride), sp,
+        len(s), rp, len(r), float(threshold), 1 if suppress_anchor_types else 0, layout, sc, dc, _ptr(rois),
+        _ptr(scores), _ptr(keep), _ptr(nkept), _ptr(ws), ws_bytes, _stream()))
+    if return_keep:
+        return rois, scores, keep, nkept
+    return rois, scores
+
+
 def multi_proposal_target(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, *, feat_stride=16,
                           scales=(2, 4, 7, 10, 13, 16, 24), ratios=(0.5, 1, 2), rpn_post_nms_top_n=300,
                           threshold=0.7, layout=NCHW, return_keep=False, return_fallback=False):

@@ -142,3 +142,68 @@ def test_mpt_error_reporting():
     t = lambda a: torch.from_numpy(a).cuda()
     with pytest.raises(SniperError):
         ops.multi_proposal_target(*[t(a) for a in inp])
+
+
+# ------------------------------------------------------------------------------------------------
+# Inference proposal operator (MultiProposal): CUDA path vs oracle/mp_cpuop.c (itself bit-identical to the reference's
+# CPU operator binary with libm exp, tests/test_oracle_cpu.py); here both sides use the correctly rounded exp.
+# ------------------------------------------------------------------------------------------------
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _tie_free_scores(cls_prob, seed):
+    B, A2, H, W = cls_prob.shape
+    A = A2 // 2
+    n = B * A * H * W
+    fg = ((np.random.RandomState(1000 + seed).permutation(n) + 1.0) / (n + 1.0)).astype(np.float32).reshape(B, A, H, W)
+    out = cls_prob.copy()
+    out[:, A:] = fg
+    out[:, :A] = 1.0 - fg
+    return out
+
+
+@pytest.mark.parametrize("seed,B,HW,fast", [(31, 2, 32, "1"), (32, 3, 32, "0"), (33, 1, 20, "1"), (34, 20, 32, "1")])
+def test_multi_proposal_inference_op_bit_exact(seed, B, HW, fast):
+    """rois, scores, kept anchor indices and counts == oracle, bit for bit; HW=32: 21504 anchors > 12000 (the exact
+    top-12000 selection + compaction runs), HW=20: 8400 anchors (no selection); fast = sorted bit-mask NMS / sequential
+    emulation; NCHW and NHWC inputs."""
+    import os
+    import torch
+    from sniper_b200 import ops
+    cls_prob, bbox_pred, im_info, gts, vr = synth.mpt_inputs(seed, B, 21, HW, HW)
+    cls_prob = _tie_free_scores(cls_prob, seed)
+    ref = O.multi_proposal(cls_prob, bbox_pred, im_info, libm_exp=False)
+    os.environ["SNIPER_NMS_FAST"] = fast
+    try:
+        rois, scores, keep, nk = ops.multi_proposal(_t(cls_prob), _t(bbox_pred), _t(im_info), return_keep=True)
+        cn = _t(np.ascontiguousarray(cls_prob.transpose(0, 2, 3, 1)))
+        bn = _t(np.ascontiguousarray(bbox_pred.transpose(0, 2, 3, 1)))
+        rois2, scores2 = ops.multi_proposal(cn, bn, _t(im_info), layout=ops.NHWC)
+    finally:
+        os.environ.pop("SNIPER_NMS_FAST", None)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(nk.cpu().numpy(), ref["num_kept"])
+    np.testing.assert_array_equal(keep.cpu().numpy(), ref["keep_idx"])
+    assert rois.cpu().numpy().tobytes() == ref["rois"].tobytes()
+    assert scores.cpu().numpy().tobytes() == ref["scores"].tobytes()
+    assert rois2.cpu().numpy().tobytes() == ref["rois"].tobytes() and scores2.cpu().numpy().tobytes() == ref["scores"].tobytes()
+
+
+def test_multi_proposal_anchor_type_suppression_and_operator_api():
+    import torch
+    from sniper_b200 import ops, operator_py
+    cls_prob, bbox_pred, im_info, gts, vr = synth.mpt_inputs(41, 2)
+    cls_prob = _tie_free_scores(cls_prob, 41)
+    ref = O.multi_proposal(cls_prob, bbox_pred, im_info, flags=1, libm_exp=False)
+    rois, scores, keep, nk = ops.multi_proposal(_t(cls_prob), _t(bbox_pred), _t(im_info), suppress_anchor_types=True,
+                                                return_keep=True)
+    np.testing.assert_array_equal(keep.cpu().numpy(), ref["keep_idx"])
+    assert rois.cpu().numpy().tobytes() == ref["rois"].tobytes()
+    plain = O.multi_proposal(cls_prob, bbox_pred, im_info, libm_exp=False)
+    out, score = operator_py.MultiProposal(_t(cls_prob), _t(bbox_pred), _t(im_info), batch_size="2",
+                                           rpn_post_nms_top_n="300", feature_stride="16")
+    assert out.shape == (600, 5) and score.shape == (600, 1)
+    assert out.cpu().numpy().tobytes() == plain["rois"].tobytes()
+    assert score.cpu().numpy().ravel().tobytes() == plain["scores"].tobytes()

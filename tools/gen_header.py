@@ -12,6 +12,8 @@ DOC = {
     "sniper_generate_anchors": "Host helper, utils::GenerateAnchors (multi_proposal_target.cu:75-114): out[nr*ns,4], ratio-major.",
     "sniper_proposal_decode": "K1: utils::getProps (multi_proposal_target.cu:263-331). Anchor shift + bbox_transform_inv + clip + min-size / valid-range filters -> SoA boxes float4[B*A*H*W], score, area. layout 0 = NCHW (reference), 1 = NHWC (channel strides given).",
     "sniper_multi_proposal_target_fwd": "Drop-in for MultiProposalTargetGPUOp::Forward (multi_proposal_target.cu:362-589; operator surface multi_proposal_target-inl.h:55-177: arguments cls_prob,bbox_pred,im_info,gt_boxes,valid_ranges -> outputs rois,label,bbox_target,bbox_weight). Decode + greedy NMS (reference tie order) + GT append + IoU/label/target assignment, entirely on device: no D2H/H2D, no sync, no allocation. keep_idx/num_kept are optional parity outputs. Backward of the reference operator is a zero fill (cu:591-615) and needs no entry point.",
+    "sniper_multi_proposal_workspace_bytes": "Scratch bytes for sniper_multi_proposal_fwd.",
+    "sniper_multi_proposal_fwd": "Drop-in for the inference proposal operator MultiProposal (multi_proposal-inl.h:55-167: arguments cls_prob,bbox_pred,im_info -> outputs output(rois),score; CPU op multi_proposal.cc:273-374, GPU-build op multi_proposal.cu:400-631, which is host code with D2H copies). Decode + min-size filter + exact top-pre_nms_top_n selection + greedy NMS on device; flags 1 = the GPU build's anchor-type suppression. Rows after the kept ones: deterministic filler instead of the reference's rand() boxes.",
     "sniper_deform_psroi_fwd": "DeformablePSROIPoolingOp::Forward (contrib/deformable_psroi_pooling-inl.h:84-125, kernel .cu:71-161). top_count optional (hidden output of the reference), sample_idx optional parity output [count, spp^2, 4].",
     "sniper_deform_psroi_bwd": "DeformablePSROIPoolingOp::Backward (contrib/deformable_psroi_pooling-inl.h:127-174, kernel .cu:203-330). data_diff/trans_diff are accumulated into (kAddTo); zero them for kWriteTo.",
     "sniper_psroi_fwd": "PSROIPoolingOp::Forward (contrib/psroi_pooling.cu:51-118). bins optional parity output [count,4] = hstart,hend,wstart,wend.",
