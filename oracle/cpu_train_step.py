@@ -139,7 +139,10 @@ def run(sample_chips=1, threads=None):
     sc2 = cls_score.view(B, 2, -1)
     rpn_loss = F.cross_entropy(sc2, label.clamp(min=-1), ignore_index=-1)
     prob = torch.softmax(sc2, 1).view(B, 42, 32, 32)
-    res = O.multi_proposal_target(prob.detach().numpy(), bbox_pred.detach().numpy(), im_info, gts, vr)
+    # the reference's OWN CPU operator binary where it was built (oracle/_ref/libref_mpt.so), else the C restatement
+    res = O.ref_multi_proposal_target(prob.detach().numpy(), bbox_pred.detach().numpy(), im_info, gts, vr)
+    if res is None:
+        res = O.multi_proposal_target(prob.detach().numpy(), bbox_pred.detach().numpy(), im_info, gts, vr)
     rois = res["rois"]
     featn = feat.detach().numpy()
     kw = dict(spatial_scale=0.0625, output_dim=256, group_size=1, pooled=7, part_size=7, spp=4, trans_std=0.1)
@@ -177,7 +180,7 @@ def run(sample_chips=1, threads=None):
         pass
     return {"value": round(B / sec, 4), "unit": "chips/s", "cores": threads, "kind": "port",
             "sample": "%d chip(s) of the same workload, one full training step in %.1f s (PyTorch-CPU fp32 dense layers + "
-                      "C-oracle SNIPER ops; stand-in for the MXNet CPU stack, which cannot be built offline)" % (B, sec),
+                      "reference CPU MultiProposalTarget binary + C-oracle PSROI; stand-in for the MXNet CPU stack, which cannot be built offline)" % (B, sec),
             "cpu": cpu_model}
 
 

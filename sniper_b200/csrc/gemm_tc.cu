@@ -1127,11 +1127,8 @@ int pick_block_n(int N, long tiles_m) {
 // K-major shapes run 10-15 % slower than the 1-SM kernel (the largest conv already reaches 674 TFLOP/s = 79 % of
 // the measured TF32 burst peak with cta_group::1, i.e. it is not operand-bound), so it is opt-in: SNIPER_GEMM_2SM=1.
 int pick_cluster(int tiles_m) {
-  static int enabled = -1;
-  if (enabled < 0) {
-    const char* e = getenv("SNIPER_GEMM_2SM");
-    enabled = (e && e[0] == '1') ? 1 : 0;   // measured 8 % slower overall on this workload: opt-in
-  }
+  const char* e = getenv("SNIPER_GEMM_2SM");   // read per call (A/B runs flip it between launches)
+  const int enabled = (e && e[0] == '1') ? 1 : 0;
   return (enabled && tiles_m >= 2) ? 2 : 1;
 }
 

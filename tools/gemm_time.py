@@ -8,7 +8,7 @@ from sniper_b200 import ops
 
 CASES = [("gemm", 20480, 1024, 256), ("gemmres", 20480, 1024, 256), ("gemm", 327680, 256, 64), ("gemm", 81920, 512, 128),
          ("gemm", 81920, 128, 512), ("gemm", 20480, 256, 1024), ("conv3x3", 20, 32, 32, 256, 256)]
-SETTINGS = [{"SNIPER_GEMM_STG": "1"}, {"SNIPER_GEMM_STG": "2"}]
+SETTINGS = [{"SNIPER_GEMM_2SM": "0"}, {"SNIPER_GEMM_2SM": "1"}]
 if len(sys.argv) > 1:
     SETTINGS = [dict(kv.split("=") for kv in a.split(",") if kv) for a in sys.argv[1:]]
 
