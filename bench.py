@@ -236,14 +236,16 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     # ---- end to end through the public API (host batch in, host losses out)
     for i in range(2):
-        trainer.step(pool[i % len(pool)])
+        trainer.step(pool[i % len(pool)], prefetch=pool[(i + 1) % len(pool)])
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record()
     losses = None
     for i in range(args.steps):
-        losses = trainer.step(pool[i % len(pool)])
+        # every step: H2D of the next step's inputs (copy stream, overlapped), D2D into the graph's static buffers,
+        # forward+backward, all-reduce, update, D2H of the losses + stream sync
+        losses = trainer.step(pool[(i + 2) % len(pool)], prefetch=pool[(i + 3) % len(pool)])
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)

@@ -258,3 +258,23 @@ def test_wgrad_side_stream_matches_single_stream():
     print("run-to-run noise %.3e, side-stream difference %.3e" % (noise, diff))
     assert torch.isfinite(grads[2]).all()
     assert diff <= max(4.0 * noise, 1e-6), (noise, diff)
+
+
+def test_trainer_prefetch_pipeline_delivers_the_right_batch():
+    """Trainer.step(batch, prefetch=next): the H2D of the next batch runs on the copy stream into a staging set while the
+    current step computes.  After every step the graph's static input buffers must hold exactly the batch that was
+    passed to that step (prefetched or not), and the losses must be finite."""
+    import math
+    import torch
+    from sniper_b200 import model, synth_batch, trainer
+    batches = [synth_batch.make_batch(1, seed=s, device="cpu", pinned=True) for s in (1, 2, 3)]
+    cfg = model.Cfg()
+    cfg.batch_images = 1
+    tr = trainer.Trainer(cfg, use_graph=True, seed=5)
+    order = [0, 1, 2, 0, 2, 1, 1]
+    for n, i in enumerate(order):
+        nxt = batches[order[n + 1]] if n + 1 < len(order) and n != 3 else None      # step 4 is NOT prefetched
+        losses = tr.step(batches[i], prefetch=nxt)
+        assert all(math.isfinite(v) for v in losses.values())
+        for k, v in batches[i].items():
+            assert torch.equal(tr.static[k].cpu(), v), (n, k)
