@@ -357,6 +357,21 @@ class Unit:
         self.saved = (x, a1, c1, a2, c2, a3, off, col)
         return y
 
+    def fwd_infer(self, x, cfg, out=None):
+        """Inference forward (is_train=False: every BatchNorm uses its moving statistics, resnet_mx_101_e2e.py:36-69 with
+        use_global_stats): BN + ReLU ride in the producing conv's epilogue as per-channel scale/shift."""
+        a1 = ops.affine_act(x, self.bn1.st.scale, self.bn1.st.shift, relu=True)
+        a2 = self.conv1.fwd(a1, scale=self.bn2.st.scale, shift=self.bn2.st.shift, relu=True)
+        if self.deform:
+            off = self.offset.fwd(a2)
+            col = ops.deform_im2col(a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)
+            a3 = ops.gemm_nt(col, self.conv2.w, scale=self.bn3.st.scale, bias=self.bn3.st.shift, relu=True)
+            a3 = a3.view(a2.shape[0], a2.shape[1], a2.shape[2], self.mid)
+        else:
+            a3 = self.conv2.fwd(a2, scale=self.bn3.st.scale, shift=self.bn3.st.shift, relu=True)
+        res = x if self.dim_match else self.sc.fwd(a1)
+        return self.conv3.fwd(a3, out=out, residual=res)
+
     def bwd(self, dout, cfg, extra_add=None):
         """dout: grad of the unit output [N,Ho,Wo,cout] (may be a channel slice).  Returns grad of the input
         (+ extra_add, used to merge the c4 half of the concat gradient into stage4_unit1's input gradient)."""
@@ -593,6 +608,52 @@ class SniperResNet101:
         self.step_count += 1
         return dict(rpn_cls_prob=prob, rpn_bbox_loss=self.loss_buf[1:2], cls_prob=cls_prob, bbox_loss=self.loss_buf[3:4],
                     label=label, rois=rois, losses=self.loss_buf)
+
+    def forward_inference(self, data, im_info, suppress_anchor_types=False):
+        """get_symbol_rcnn(cfg, is_train=False) (resnet_mx_101_e2e.py:227-345 with the test branch :258-266, 321-326):
+        backbone with moving-statistics BN -> RPN -> MultiProposal (device inference proposal op) -> deformable
+        R-FCN head -> (rois [B*R,5], rpn scores [B*R], cls_prob [B*R,K], bbox_pred [B*R,4]).  No parameter is touched."""
+        cfg = self.cfg
+        A = cfg.num_anchors
+        B = data.shape[0]
+        for b in self.train_bns():
+            ops.bn_frozen(b.st, cfg.bn_eps)        # scale/shift from the moving statistics (the next training step
+        x = ops.stem_conv(data, self.conv0_w, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
+                          self.bn0.st.shift)       # recomputes them from batch statistics)
+        x = ops.maxpool3x3s2(x)
+        n1, n2, n3, n4 = cfg.units
+        Hf, Wf = data.shape[2] // cfg.feat_stride, data.shape[3] // cfg.feat_stride
+        cat = torch.empty(B, Hf, Wf, 3072, device=data.device)
+        last3 = n1 + n2 + n3 - 1
+        for i, u in enumerate(self.units):
+            out = cat[..., :1024] if i == last3 else (cat[..., 1024:] if i == len(self.units) - 1 else None)
+            x = u.fwd_infer(x, cfg, out=out)
+        rpn = self.rpn_conv.fwd(cat, relu=True)
+        head = self.rpn_head.fwd(rpn)
+        feat = self.conv_new_1.fwd(cat, relu=True)
+        prob = torch.empty(B, Hf, Wf, 2 * A, device=data.device)
+        ignore = torch.full((B, A * Hf * Wf), -1.0, device=data.device)
+        cnt = torch.ones(1, dtype=torch.int32, device=data.device)
+        loss = torch.zeros(1, device=data.device)
+        ops.rpn_softmax_loss(head[..., 4 * A:6 * A], ignore, A, 1.0, cnt, prob, None, loss)
+        rois, scores = ops.multi_proposal(prob, head, im_info, feat_stride=cfg.feat_stride, scales=cfg.scales,
+                                          ratios=cfg.ratios, rpn_post_nms_top_n=cfg.rpn_post_nms_top_n,
+                                          suppress_anchor_types=suppress_anchor_types, layout=ops.NHWC)
+        N = rois.shape[0]
+        ps = dict(spatial_scale=1.0 / cfg.feat_stride, output_dim=256, group_size=1, pooled_size=7, part_size=7,
+                  sample_per_part=4, layout=ops.NHWC)
+        offset_t, _, _ = ops.deform_psroi_fwd(feat, rois, None, no_trans=True, want_count=False, **ps)
+        off = ops.gemm_nt(offset_t.view(N, -1), self.fc_offset.w, bias=self.fc_offset.b)
+        trans = off[:, :98].contiguous().view(N, 2, 7, 7)
+        pooled, _, _ = ops.deform_psroi_fwd(feat, rois, trans, no_trans=False, trans_std=0.1, want_count=False, **ps)
+        fc1 = ops.gemm_nt(pooled.view(N, -1), self.fc_new_1.w, bias=self.fc_new_1.b, relu=True)
+        fc2 = ops.gemm_nt(fc1, self.fc_new_2.w, bias=self.fc_new_2.b, relu=True)
+        out = ops.gemm_nt(fc2, self.fc_out.w, bias=self.fc_out.b)
+        K = cfg.num_classes
+        cls_prob = torch.empty(N, K, device=data.device)
+        lab = torch.full((N,), -1.0, device=data.device)
+        ops.softmax_ce(out, lab, K, 1.0, cnt, cls_prob, None, loss)
+        return rois, scores, cls_prob, out[:, K:K + 4]
 
     def update(self, lr=None):
         cfg = self.cfg

@@ -278,3 +278,64 @@ def test_trainer_prefetch_pipeline_delivers_the_right_batch():
         assert all(math.isfinite(v) for v in losses.values())
         for k, v in batches[i].items():
             assert torch.equal(tr.static[k].cpu(), v), (n, k)
+
+
+@pytest.mark.parametrize("cin,cout,stride,dim_match,H", [(256, 256, 1, True, 32), (128, 256, 2, False, 64)])
+def test_residual_unit_inference_bn(cin, cout, stride, dim_match, H):
+    """Unit.fwd_infer (BN with moving statistics folded into the conv epilogues) vs PyTorch fp64 eval-mode BN."""
+    import torch
+    import torch.nn.functional as F
+    from sniper_b200 import model, ops
+    cfg = model.Cfg()
+    P = model.ParamStore()
+    u = model.Unit(P, "u", cin, cout, stride, dim_match, frozen=False)
+    P.finalize("cuda")
+    g = torch.Generator(device="cuda"); g.manual_seed(2)
+    for c in u.convs():
+        c.init(device="cuda", gen=g)
+    for b in u.bns():
+        b.build("cuda")
+        b.st.gamma.uniform_(0.5, 1.5)
+        b.st.beta.normal_(0, 0.2)
+        b.st.moving_mean.normal_(0, 0.3)
+        b.st.moving_var.uniform_(0.5, 2.0)
+        ops.bn_frozen(b.st, cfg.bn_eps)
+    torch.manual_seed(3)
+    x = torch.randn(2, H, H, cin, device="cuda")
+    y = u.fwd_infer(x, cfg)
+
+    def W(c):
+        return c.w.view(c.coutp, c.k, c.k, c.cin).permute(0, 3, 1, 2).double()
+
+    def bn(b, t):
+        return torch.relu(F.batch_norm(t, b.st.moving_mean.double(), b.st.moving_var.double(), b.st.gamma.double(),
+                                       b.st.beta.double(), False, 0.0, cfg.bn_eps))
+    xd = x.permute(0, 3, 1, 2).double()
+    a1 = bn(u.bn1, xd)
+    a2 = bn(u.bn2, F.conv2d(a1, W(u.conv1)))
+    a3 = bn(u.bn3, F.conv2d(a2, W(u.conv2), stride=u.conv2.stride, padding=u.conv2.pad, dilation=u.conv2.dil))
+    yr = F.conv2d(a3, W(u.conv3)) + (xd if dim_match else F.conv2d(a1, W(u.sc), stride=u.sc.stride))
+    assert _rel(y, yr.permute(0, 2, 3, 1)) < 5e-3
+
+
+def test_inference_forward_path():
+    """get_symbol_rcnn(is_train=False) as SniperResNet101.forward_inference: proposals from the device MultiProposal op,
+    class probabilities that sum to one, boxes inside the chip, bit-identical on a second call, parameters untouched."""
+    import torch
+    from sniper_b200 import model, synth_batch
+    cfg = model.Cfg()
+    cfg.batch_images = 2
+    net = model.SniperResNet101(cfg, deform_offset_std=0.01)
+    batch = synth_batch.make_batch(2, seed=7, device="cuda")
+    net.train_step(batch, lr=0.001)                       # moving statistics become non-trivial
+    w0 = net.P.w.clone()
+    rois, scores, cls_prob, bbox_pred = net.forward_inference(batch["data"], batch["im_info"])
+    torch.cuda.synchronize()
+    assert rois.shape == (600, 5) and scores.shape == (600,) and cls_prob.shape == (600, 81) and bbox_pred.shape == (600, 4)
+    assert torch.isfinite(cls_prob).all() and torch.isfinite(bbox_pred).all()
+    assert (cls_prob.sum(1) - 1).abs().max().item() < 1e-4
+    assert (rois[:, 1:] >= 0).all() and (rois[:, 1:] <= 511).all()
+    assert (scores[:300][:-1] >= scores[:300][1:]).all() or (scores[:300] == 0).any()   # sorted kept rows (+ fillers)
+    r2 = net.forward_inference(batch["data"], batch["im_info"])
+    assert all(torch.equal(a, b) for a, b in zip((rois, scores, cls_prob, bbox_pred), r2))
+    assert torch.equal(w0, net.P.w)
