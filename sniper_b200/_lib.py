@@ -20,7 +20,7 @@ SIGNATURES = {
     "sniper_proposal_decode": ("i", "pppp" "iiiii" "pipi" "iii" "ppp" "p"),
     "sniper_multi_proposal_target_fwd": ("i", "ppppp" "iiiiiii" "pipi" "f" "iii" "pppp" "pp" "pz" "p"),
     "sniper_multi_proposal_workspace_bytes": ("z", "iiiii"),
-    "sniper_multi_proposal_fwd": ("i", "ppp" "iiiiiii" "pipi" "f" "iiii" "pppp" "pz" "p"),
+    "sniper_multi_proposal_fwd": ("i", "ppp" "iiiiiii" "pipi" "f" "i" "f" "iii" "pppp" "pz" "p"),
     "sniper_deform_psroi_fwd": ("i", "ppp" "iiii" "f" "iiiii" "f" "iii" "ppp" "p"),
     "sniper_deform_psroi_bwd": ("i", "pppp" "iiii" "f" "iiiii" "f" "iii" "pp" "p"),
     "sniper_psroi_fwd": ("i", "pp" "iiii" "f" "iiii" "pp" "p"),

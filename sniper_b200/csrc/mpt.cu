@@ -174,6 +174,42 @@ __device__ __forceinline__ float iou_ref(float ix1, float iy1, float ix2, float 
   return __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, darea), inter));
 }
 
+// "FastNMS" of the reference's GPU-build inference operator (multi_proposal.cu:267-387, 511-575): a kept proposal only
+// tests the anchors listed in a precomputed anchor-overlap map -- anchor type c2 at grid offset (row j, column k) is
+// listed for c1 iff the IoU of the two UNDECODED anchors is >= roi_iou_thresh -- and the reference applies the stored
+// (row, column) offsets as (dw, dh), i.e. swapped.  The map is a pure function of (c1, c2, |dw|, |dh|) and is evaluated
+// on the fly here.  enabled = 0: every pair is tested (exact NMS).
+struct OverlapMap {
+  int enabled;
+  int H, W, stride;
+  float thresh;
+  const int32_t* id_map;   // row of the (compacted) arrays -> original anchor index a*H*W + h*W + w; null = identity
+  float anchors[4 * kMaxAnchors];
+  float area[kMaxAnchors];
+};
+
+__device__ __forceinline__ bool overlap_listed(const OverlapMap& m, int id1, int id2) {
+  const int hw = m.H * m.W;
+  const int c1 = id1 / hw, r1 = id1 - c1 * hw, h1 = r1 / m.W, w1 = r1 - h1 * m.W;
+  const int c2 = id2 / hw, r2 = id2 - c2 * hw, h2 = r2 / m.W, w2 = r2 - h2 * m.W;
+  const int j = abs(w2 - w1), k = abs(h2 - h1);      // dx = +-j is a ROW offset of the map, dy = +-k a COLUMN offset
+  if (j >= m.H || k >= m.W) return false;
+  if (j == 0 && k == 0 && c2 == c1) return false;
+  const float sx = (float)(k * m.stride), sy = (float)(j * m.stride);
+  const float xx1 = fmaxf(m.anchors[4 * c1], __fadd_rn(m.anchors[4 * c2], sx));
+  const float yy1 = fmaxf(m.anchors[4 * c1 + 1], __fadd_rn(m.anchors[4 * c2 + 1], sy));
+  const float xx2 = fminf(m.anchors[4 * c1 + 2], __fadd_rn(m.anchors[4 * c2 + 2], sx));
+  const float yy2 = fminf(m.anchors[4 * c1 + 3], __fadd_rn(m.anchors[4 * c2 + 3], sy));
+  const float w = fmaxf(0.0f, __fadd_rn(__fsub_rn(xx2, xx1), 1.0f));
+  const float h = fmaxf(0.0f, __fadd_rn(__fsub_rn(yy2, yy1), 1.0f));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(m.area[c1], m.area[c2]), inter));
+  return ovr >= m.thresh;
+}
+__device__ __forceinline__ int orig_id(const OverlapMap& m, size_t chip_base, int row) {
+  return m.id_map ? m.id_map[chip_base + row] : row;
+}
+
 struct NmsArgs {
   const float4* boxes;
   const float* scores;
@@ -192,6 +228,7 @@ struct NmsArgs {
   const int32_t* id_map;   // optional [B*AHW]: original anchor index of every (compacted) row, reported in keep_idx
   float* score_out;        // optional [B*R]: score of the kept rows, 0 for filler rows (do_assign = 0)
   long filler_stride;      // rows per chip used by the filler rule (cu:244-249); AHW unless the rows are compacted
+  OverlapMap omap;         // FastNMS pair restriction (inference operator, GPU build); enabled = 0 otherwise
   const int32_t* fast_keep;      // optional results of mpt_nms_fast_kernel: [B,1024], [B], [B]
   const int32_t* fast_nkept;
   const int32_t* fast_fallback;
@@ -219,6 +256,7 @@ struct FastArgs {
   int32_t* keep_ids;   // [B,1024]
   int32_t* nkept;      // [B]
   int32_t* fallback;   // [B]
+  OverlapMap omap;
 };
 
 __device__ __forceinline__ int score_bin(float s) {
@@ -283,8 +321,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_fast_kernel(FastArgs p
   unsigned short* s_pos = reinterpret_cast<unsigned short*>(s_alive + 64);                  // [kFastCap] current row
   short* s_atpos = reinterpret_cast<short*>(s_pos + kFastCap);                              // [1024] row -> sorted idx
   __shared__ int s_D, s_cum, s_D2, s_cum2, s_nsel, s_nvalid, s_bad, s_nk, s_wsum[32];
+  __shared__ int s_koid[1024];   // original anchor index of the kept boxes (FastNMS map)
   const int chip = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const int AHW = p.AHW;
+  const size_t chip_base = (size_t)chip * AHW;
   const float* sc = p.scores + (size_t)chip * AHW;
   const float4* boxes = p.boxes + (size_t)chip * AHW;
   const float* areas = p.areas + (size_t)chip * AHW;
@@ -375,12 +415,18 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_fast_kernel(FastArgs p
     const bool have = grp < len;
     float4 cb = make_float4(0.f, 0.f, 0.f, 0.f);
     float ca = 0.f;
-    if (have) { cb = s_box[ci]; ca = s_area[ci]; }
+    int coid = 0;
+    if (have) {
+      cb = s_box[ci]; ca = s_area[ci];
+      if (p.omap.enabled) coid = orig_id(p.omap, chip_base, (int)(unsigned)s_key[ci]);
+    }
     // (a) against everything kept so far
     int dead = 0;
     if (have)
-      for (int k = sub; k < nk; k += 16)
+      for (int k = sub; k < nk; k += 16) {
+        if (p.omap.enabled && !overlap_listed(p.omap, s_koid[k], coid)) continue;
         dead |= (iou_ref(s_kbox[k].x, s_kbox[k].y, s_kbox[k].z, s_kbox[k].w, s_karea[k], cb, ca) > p.nms_thresh);
+      }
     const unsigned dm = __ballot_sync(0xffffffffu, dead);
     const bool alive = have && (((dm >> (lane & 16)) & 0xffffu) == 0);
     // (b) against every other member of this trip (symmetric: inside a tie run the order is not known yet)
@@ -392,6 +438,10 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_fast_kernel(FastArgs p
         if (j != grp && j < len) {
           const float4 ob = s_box[base + j];
           const float oa = s_area[base + j];
+          // bit j of mask[grp]: candidate grp, once kept, suppresses candidate j
+          if (p.omap.enabled &&
+              !overlap_listed(p.omap, coid, orig_id(p.omap, chip_base, (int)(unsigned)s_key[base + j])))
+            continue;
           // the reference evaluates IoU with the selected box first; float min/max/add are symmetric
           if (iou_ref(cb.x, cb.y, cb.z, cb.w, ca, ob, oa) > p.nms_thresh) m |= 1ull << j;
         }
@@ -423,6 +473,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_fast_kernel(FastArgs p
           const int ci2 = base + best;
           s_kbox[k] = s_box[ci2];
           s_karea[k] = s_area[ci2];
+          if (p.omap.enabled) s_koid[k] = orig_id(p.omap, chip_base, (int)(unsigned)s_key[ci2]);
           p.keep_ids[(size_t)chip * 1024 + k] = (int)(unsigned)s_key[ci2];
           // swap rows k and pos(best) (multi_proposal_target.cu:178-199)
           const int pb = s_pos[ci2];
@@ -516,6 +567,7 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_assign_kernel(NmsArgs 
     vct++;
     const float4 sb = __ldg(boxes + sel_id);
     const float sarea = __ldg(areas + sel_id);
+    const int sel_oid = p.omap.enabled ? orig_id(p.omap, (size_t)chip * AHW, sel_id) : 0;
     // element displaced from position j by the swap lands on position m
     const float oldj_score = s_score[j];
     const uint16_t oldj_id = s_id[j];
@@ -555,7 +607,8 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_assign_kernel(NmsArgs 
         const int pos = base + u * kNmsThreads;
         if (pos >= AHW) continue;
         float sv = s[u];
-        if (sv != -1.0f) {
+        if (sv != -1.0f &&
+            (!p.omap.enabled || overlap_listed(p.omap, sel_oid, orig_id(p.omap, (size_t)chip * AHW, id[u])))) {
           const float ovr = iou_ref(sb.x, sb.y, sb.z, sb.w, sarea, d[u], da[u]);
           if (ovr > p.nms_thresh) sv = -1.0f;
         }
@@ -583,7 +636,22 @@ __global__ void __launch_bounds__(kNmsThreads, 1) mpt_nms_assign_kernel(NmsArgs 
       if (p.keep_idx)
         p.keep_idx[(size_t)chip * R + r] =
             r < vct ? (p.id_map ? p.id_map[(size_t)chip * AHW + s_keep[r]] : s_keep[r]) : -1;
-      if (p.score_out) p.score_out[(size_t)chip * R + r] = r < vct ? p.scores[(size_t)chip * AHW + s_keep[r]] : 0.0f;
+      if (p.score_out) {
+        float so = r < vct ? p.scores[(size_t)chip * AHW + s_keep[r]] : 0.0f;
+        if (p.omap.enabled && r < vct) {
+          // the map is not applied symmetrically: a box kept LATER may list this one and mark it (the reference reads
+          // the scores after the NMS, multi_proposal.cu:592, so such a row is output with score -1)
+          const int my = orig_id(p.omap, (size_t)chip * AHW, s_keep[r]);
+          const float ma = __ldg(areas + s_keep[r]);
+          for (int q = r + 1; q < vct; ++q) {
+            const int qo = orig_id(p.omap, (size_t)chip * AHW, s_keep[q]);
+            if (!overlap_listed(p.omap, qo, my)) continue;
+            const float4 qb = __ldg(boxes + s_keep[q]);
+            if (iou_ref(qb.x, qb.y, qb.z, qb.w, __ldg(areas + s_keep[q]), bx, ma) > p.nms_thresh) { so = -1.0f; break; }
+          }
+        }
+        p.score_out[(size_t)chip * R + r] = so;
+      }
     }
     return;
   }
@@ -832,7 +900,7 @@ static int nms_assign_launch(const float* boxes, const float* score, const float
                              float* rois, float* label, float* bbox_target, float* bbox_weight,
                              int32_t* keep_idx, int32_t* num_kept, int do_assign, int32_t* fast_scratch,
                              void* stream, const int32_t* id_map = nullptr, float* score_out = nullptr,
-                             long filler_stride = 0) {
+                             long filler_stride = 0, const OverlapMap* omap = nullptr) {
   SN_CHECK(AHW >= R, "nms: anchors per chip (%d) < post_nms_top_n (%d)", AHW, R);
   SN_CHECK(AHW <= 32768, "nms: anchors per chip (%d) > 32768", AHW);
   SN_CHECK(R <= 1024, "nms: post_nms_top_n (%d) > 1024", R);
@@ -843,6 +911,7 @@ static int nms_assign_launch(const float* boxes, const float* score, const float
   n.nms_thresh = nms_thresh; n.rois = rois; n.label = label; n.bbox_target = bbox_target;
   n.bbox_weight = bbox_weight; n.keep_idx = keep_idx; n.num_kept = num_kept; n.do_assign = do_assign;
   n.id_map = id_map; n.score_out = score_out; n.filler_stride = filler_stride > 0 ? filler_stride : AHW;
+  if (omap) n.omap = *omap; else { memset(&n.omap, 0, sizeof(n.omap)); }
   const size_t smem = (size_t)AHW * 6 + 16;
   static bool attr_set = false;
   const size_t fast_smem = (size_t)kFastCap * (8 + 16 + 4 + 2) + kFastBins * 4 + 1024 * (20 + 2) + 64 * 8 + 64 * 4 + 64;
@@ -856,6 +925,7 @@ static int nms_assign_launch(const float* boxes, const float* score, const float
     FastArgs f;
     f.boxes = n.boxes; f.scores = score; f.areas = area; f.AHW = AHW; f.R = R; f.nms_thresh = nms_thresh;
     f.keep_ids = fast_scratch; f.nkept = fast_scratch + (size_t)B * 1024; f.fallback = f.nkept + B;
+    f.omap = n.omap;
     mpt_nms_fast_kernel<<<B, kNmsThreads, fast_smem, (cudaStream_t)stream>>>(f);
     SN_LAUNCH_CHECK();
     n.fast_keep = f.keep_ids; n.fast_nkept = f.nkept; n.fast_fallback = f.fallback;
@@ -902,17 +972,18 @@ size_t sniper_multi_proposal_workspace_bytes(int B, int A, int H, int W, int pre
 // Inference proposal operator: drop-in for MultiProposal (multi_proposal-inl.h:55-167; CPU op multi_proposal.cc:273-374,
 // GPU-build op multi_proposal.cu:400-631) entirely on device -- decode, min-size filter, top pre_nms_top_n selection,
 // greedy NMS (> 0.7 as the reference hard-codes; nms_thresh is passed through), rois [B*post,5] and scores [B*post].
-// flags: 1 = anchor-type suppression of the GPU build (.cu:505-508).  The GPU build's FastNMS (flags 2) approximates
-// the NMS through a precomputed anchor-overlap map; this entry point runs the exact NMS of the CPU operator.
+// flags: 1 = anchor-type suppression of the GPU build (.cu:505-508); 2 = the GPU build's FastNMS (a kept box only tests
+// the anchors of its precomputed anchor-overlap map, roi_iou_thresh; .cu:267-387) instead of the exact NMS of the CPU op.
 // Rows after the kept ones are rand() boxes in the reference; here the deterministic filler of the training operator
 // with score 0.  keep_idx / num_kept: optional parity outputs (original anchor indices).
 int sniper_multi_proposal_fwd(const float* cls_prob, const float* bbox_pred, const float* im_info, int B, int A, int H,
                               int W, int pre_nms_top_n, int post_nms_top_n, int feat_stride, const float* scales, int ns,
-                              const float* ratios, int nr, float nms_thresh, int flags, int layout, int score_cstride,
+                              const float* ratios, int nr, float nms_thresh, int flags, float roi_iou_thresh, int layout,
+                              int score_cstride,
                               int delta_cstride, float* rois, float* scores, int32_t* keep_idx, int32_t* num_kept,
                               void* workspace, size_t ws_bytes, void* stream) {
   SN_CHECK(A == ns * nr && A <= kMaxAnchors, "multi_proposal: A (%d) must equal ns*nr and be <= %d", A, kMaxAnchors);
-  SN_CHECK((flags & ~1) == 0, "multi_proposal: unsupported flags %d (FastNMS of the GPU build is not provided)", flags);
+  SN_CHECK((flags & ~3) == 0, "multi_proposal: unsupported flags %d", flags);
   SN_CHECK(layout == 0 || layout == 1, "multi_proposal: layout must be 0 (NCHW) or 1 (NHWC)");
   SN_CHECK(layout == 0 || (delta_cstride % 4 == 0 && ((uintptr_t)bbox_pred & 15) == 0),
            "multi_proposal: NHWC deltas need 16-byte aligned pixels");
@@ -955,9 +1026,17 @@ int sniper_multi_proposal_fwd(const float* cls_prob, const float* bbox_pred, con
     SN_LAUNCH_CHECK();
     boxes = boxes_c; score = score_c; area = area_c; id_map = ids_c;
   }
+  OverlapMap om;
+  memset(&om, 0, sizeof(om));
+  if (flags & 2) {
+    om.enabled = 1; om.H = H; om.W = W; om.stride = feat_stride; om.thresh = roi_iou_thresh; om.id_map = id_map;
+    memcpy(om.anchors, t.v, sizeof(float) * 4 * A);
+    for (int i = 0; i < A; ++i)   // multi_proposal.cu:489-496
+      om.area[i] = (t.v[4 * i + 2] - t.v[4 * i] + 1) * (t.v[4 * i + 3] - t.v[4 * i + 1] + 1);
+  }
   return nms_assign_launch(boxes, score, area, nullptr, nullptr, B, K, 0, post_nms_top_n, nms_thresh, rois, nullptr,
                            nullptr, nullptr, keep_idx, num_kept, 0, nms_fast_enabled() ? fast_scratch : nullptr, stream,
-                           id_map, scores, (long)AHW);
+                           id_map, scores, (long)AHW, &om);
 }
 
 }  // extern "C"

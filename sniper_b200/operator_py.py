@@ -170,14 +170,16 @@ def MultiProposalTarget(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, **
 @register('MultiProposal')
 class MultiProposalProp(CustomOpProp):
     """MultiProposalParam (multi_proposal-inl.h:55-100): same keyword names and defaults; outputs `output`, `score`
-    (multi_proposal-inl.h:147-155).  `roi_iou_thresh` belongs to the GPU build's FastNMS overlap map and is accepted
-    and ignored (the exact NMS of the CPU operator runs); `suppress_anchor_types` selects the GPU build's anchor-type
-    suppression (multi_proposal.cu:505-508)."""
+    (multi_proposal-inl.h:147-155).  The exact NMS of the CPU operator (multi_proposal.cc) runs by default;
+    `fast_nms=True` selects the GPU build's FastNMS restricted to the anchor-overlap map of `roi_iou_thresh`
+    (multi_proposal.cu:267-387) and `suppress_anchor_types=True` its anchor-type suppression (multi_proposal.cu:505-508)."""
 
     def __init__(self, batch_size=16, rpn_pre_nms_top_n=6000, rpn_post_nms_top_n=300, threshold=0.7, rpn_min_size=4,
                  scales=(2, 4, 7, 10, 13, 16, 24), ratios=(0.5, 1, 2), feature_stride=16, bbox_scale=1.0,
-                 roi_iou_thresh=0.3, workspace=128, suppress_anchor_types=False, layout=ops.NCHW):
+                 roi_iou_thresh=0.3, workspace=128, suppress_anchor_types=False, fast_nms=False, layout=ops.NCHW):
         super(MultiProposalProp, self).__init__(need_top_grad=False)
+        self.fast_nms = str(fast_nms) in ("True", "true", "1")
+        self.roi_iou_thresh = float(roi_iou_thresh)
         self.post = int(rpn_post_nms_top_n)
         self.threshold = float(threshold)
         self.scales = _tuple(scales)
@@ -207,7 +209,7 @@ class MultiProposalProp(CustomOpProp):
                                        feat_stride=prop.stride, scales=prop.scales, ratios=prop.ratios,
                                        rpn_pre_nms_top_n=prop.pre, rpn_post_nms_top_n=prop.post,
                                        threshold=prop.threshold, suppress_anchor_types=prop.suppress,
-                                       layout=prop.layout)
+                                       fast_nms=prop.fast_nms, roi_iou_thresh=prop.roi_iou_thresh, layout=prop.layout)
                 for i, t in enumerate(r):
                     self.assign(out_data[i], req[i], t.view(out_data[i].shape))
 

@@ -58,9 +58,10 @@ def generate_anchors(feat_stride, scales, ratios):
 
 def multi_proposal(cls_prob, bbox_pred, im_info, *, feat_stride=16, scales=(2, 4, 7, 10, 13, 16, 24),
                    ratios=(0.5, 1, 2), rpn_pre_nms_top_n=12000, rpn_post_nms_top_n=300, threshold=0.7,
-                   suppress_anchor_types=False, layout=NCHW, return_keep=False):
+                   suppress_anchor_types=False, fast_nms=False, roi_iou_thresh=0.3, layout=NCHW, return_keep=False):
     """MultiProposal forward -- the inference proposal operator (multi_proposal.cc:273-374 semantics: decode, min-size
-    filter, the rpn_pre_nms_top_n best anchors, greedy NMS), on device.  Returns rois [B*R,5], scores [B*R]
+    filter, the rpn_pre_nms_top_n best anchors, greedy NMS), on device; suppress_anchor_types / fast_nms select the two
+    extras of the reference's GPU build (multi_proposal.cu:505-508, 267-387).  Returns rois [B*R,5], scores [B*R]
     (+ keep_idx [B*R] original anchor indices / -1 for filler rows, num_kept [B])."""
     _f32(cls_prob), _f32(bbox_pred), _f32(im_info)
     A = len(scales) * len(ratios)
@@ -85,7 +86,8 @@ def multi_proposal(cls_prob, bbox_pred, im_info, *, feat_stride=16, scales=(2, 4
     r, rp = _farr(ratios)
     check(L.sniper_multi_proposal_fwd(
         _ptr(cls_prob), _ptr(bbox_pred), _ptr(im_info), B, A, H, W, int(rpn_pre_nms_top_n), R, int(feat_stride), sp,
-        len(s), rp, len(r), float(threshold), 1 if suppress_anchor_types else 0, layout, sc, dc, _ptr(rois),
+        len(s), rp, len(r), float(threshold), (1 if suppress_anchor_types else 0) | (2 if fast_nms else 0),
+        float(roi_iou_thresh), layout, sc, dc, _ptr(rois),
         _ptr(scores), _ptr(keep), _ptr(nkept), _ptr(ws), ws_bytes, _stream()))
     if return_keep:
         return rois, scores, keep, nkept

@@ -207,3 +207,30 @@ def test_multi_proposal_anchor_type_suppression_and_operator_api():
     assert out.shape == (600, 5) and score.shape == (600, 1)
     assert out.cpu().numpy().tobytes() == plain["rois"].tobytes()
     assert score.cpu().numpy().ravel().tobytes() == plain["scores"].tobytes()
+
+
+@pytest.mark.parametrize("seed,B,HW,fast,flags", [(51, 2, 32, "1", 2), (52, 2, 32, "0", 2), (53, 1, 20, "1", 3), (54, 3, 32, "1", 3)])
+def test_multi_proposal_fast_nms_variant_bit_exact(seed, B, HW, fast, flags):
+    """FastNMS of the reference's GPU build (pair tests restricted to the anchor-overlap map, multi_proposal.cu:267-387)
+    +/- anchor-type suppression: rois, scores (incl. the -1 of rows marked after they were kept), keep indices ==
+    oracle/mp_cpuop.c, for the bit-mask and the sequential kernels."""
+    import os
+    import torch
+    from sniper_b200 import ops
+    cls_prob, bbox_pred, im_info, gts, vr = synth.mpt_inputs(seed, B, 21, HW, HW)
+    cls_prob = _tie_free_scores(cls_prob, seed)
+    ref = O.multi_proposal(cls_prob, bbox_pred, im_info, flags=flags, roi_iou_thresh=0.3, libm_exp=False)
+    os.environ["SNIPER_NMS_FAST"] = fast
+    try:
+        rois, scores, keep, nk = ops.multi_proposal(_t(cls_prob), _t(bbox_pred), _t(im_info), fast_nms=True,
+                                                    suppress_anchor_types=bool(flags & 1), roi_iou_thresh=0.3,
+                                                    return_keep=True)
+    finally:
+        os.environ.pop("SNIPER_NMS_FAST", None)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(nk.cpu().numpy(), ref["num_kept"])
+    np.testing.assert_array_equal(keep.cpu().numpy(), ref["keep_idx"])
+    assert rois.cpu().numpy().tobytes() == ref["rois"].tobytes()
+    assert scores.cpu().numpy().tobytes() == ref["scores"].tobytes()
+    plain = O.multi_proposal(cls_prob, bbox_pred, im_info, flags=flags & 1, libm_exp=False)
+    assert not np.array_equal(plain["keep_idx"], ref["keep_idx"])          # the restriction does change the result
