@@ -18,6 +18,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
+#include <mutex>
 
 namespace {
 
@@ -957,8 +958,10 @@ struct TailSlot {
 };
 TailSlot g_tail[kTailSlots];
 bool g_tail_ready = false;
+std::mutex g_tail_mutex;   // entry points may be called from several host threads (one per stream)
 
 TailSlot* tail_slot(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lock(g_tail_mutex);
   if (!g_tail_ready) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;

@@ -32,7 +32,7 @@ class Trainer:
         self.stage = [None, None]
         self.stage_ready = [None, None]      # event: H2D into stage[i] finished
         self.stage_free = [None, None]       # event: the step that consumed stage[i] has copied it out
-        self.stage_owner = [None, None]      # id() of the host batch sitting in stage[i]
+        self.stage_owner = [None, None]      # the host batch object sitting in stage[i] (kept alive: identity match)
         self.next_stage = 0
 
     # ---- device-resident step (inputs already in HBM)
@@ -60,12 +60,12 @@ class Trainer:
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
         self.stage_ready[i] = ev
-        self.stage_owner[i] = id(host_batch)
+        self.stage_owner[i] = host_batch
 
     def _load_or_take(self, host_batch):
         """Brings `host_batch` into the static buffers: from its staging set if it was prefetched, else by H2D now."""
         for i in (0, 1):
-            if self.stage_owner[i] == id(host_batch) and self.stage_ready[i] is not None:
+            if self.stage_owner[i] is host_batch and self.stage_ready[i] is not None:
                 if self.static is None:
                     self._alloc_static(host_batch)
                 cur = torch.cuda.current_stream()
