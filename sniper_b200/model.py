@@ -655,6 +655,54 @@ class SniperResNet101:
         ops.softmax_ce(out, lab, K, 1.0, cnt, cls_prob, None, loss)
         return rois, scores, cls_prob, out[:, K:K + 4]
 
+    # ---------------------------------------------------------------- reference checkpoints (utils.py:45-100)
+    def _named_convs(self):
+        cs = [c for u in self.units for c in u.convs()]
+        return cs + [self.rpn_conv, self.rpn_head, self.conv_new_1, self.fc_offset, self.fc_new_1, self.fc_new_2, self.fc_out]
+
+    def _named_bns(self):
+        return [self.bn_data, self.bn0] + [b for u in self.units for b in u.bns()]
+
+    def load_reference(self, arg, aux):
+        """Loads a reference checkpoint (`arg_params`, `aux_params` as numpy dicts, e.g. checkpoint.read_params of a
+        released SNIPER `.params` file): OIHW -> tap-major rows, NCHW-flattened FC inputs -> NHWC, fused heads."""
+        from . import checkpoint as ck
+        cfg = self.cfg
+        dev = self.device
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        self.conv0_w.copy_(t(arg["conv0_weight"].transpose(0, 2, 3, 1)))
+        for c in self._named_convs():
+            w, b = ck.conv_from_reference(c.name, c.cout, c.coutp, c.cin, c.k, c.bias, arg)
+            c.w.copy_(t(w))
+            if c.bias:
+                c.b.copy_(t(b))
+        for bn in self._named_bns():
+            bn.st.gamma.copy_(t(arg[bn.name + "_gamma"]))
+            bn.st.beta.copy_(t(arg[bn.name + "_beta"]))
+            bn.st.moving_mean.copy_(t(aux[bn.name + "_moving_mean"]))
+            bn.st.moving_var.copy_(t(aux[bn.name + "_moving_var"]))
+            if bn.frozen:
+                ops.bn_frozen(bn.st, cfg.bn_eps, fix_gamma=bn.fix_gamma)
+        self._wt_table = None      # data-gradient operands are rebuilt from the new weights on the next step
+
+    def export_reference(self):
+        """The inverse of load_reference: (arg_params, aux_params) under the reference's names and layouts."""
+        from . import checkpoint as ck
+        cfg = self.cfg
+        A, K = cfg.num_anchors, cfg.num_classes
+        n = lambda x: x.detach().cpu().numpy().copy()
+        arg, aux = {}, {}
+        arg["conv0_weight"] = np.ascontiguousarray(n(self.conv0_w).transpose(0, 3, 1, 2))
+        parts = {"rpn_head": (4 * A, 2 * A), "cls_bbox": (K, 4)}
+        for c in self._named_convs():
+            ck.conv_to_reference(c.name, c.cout, c.cin, c.k, n(c.w), n(c.b) if c.bias else None, parts.get(c.name), arg)
+        for bn in self._named_bns():
+            arg[bn.name + "_gamma"] = n(bn.st.gamma)
+            arg[bn.name + "_beta"] = n(bn.st.beta)
+            aux[bn.name + "_moving_mean"] = n(bn.st.moving_mean)
+            aux[bn.name + "_moving_var"] = n(bn.st.moving_var)
+        return arg, aux
+
     def update(self, lr=None):
         cfg = self.cfg
         self.P.sgd_step(cfg.lr if lr is None else lr, cfg.wd, cfg.momentum)
