@@ -18,7 +18,6 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
-#include <mutex>
 
 namespace {
 
@@ -956,12 +955,10 @@ struct TailSlot {
   float4* ws;
   int* cnt;
 };
-TailSlot g_tail[kTailSlots];
-bool g_tail_ready = false;
-std::mutex g_tail_mutex;   // entry points may be called from several host threads (one per stream)
+TailSlot g_tail[kTailSlots];   // host-side table; the entry points are not re-entrant across host threads (documented
+bool g_tail_ready = false;     // in include/sniper_b200.h): one host thread drives the launches of a process
 
 TailSlot* tail_slot(cudaStream_t stream) {
-  std::lock_guard<std::mutex> lock(g_tail_mutex);
   if (!g_tail_ready) {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;

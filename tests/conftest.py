@@ -13,6 +13,12 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
+    # a wedged kernel must not hold the whole run: every test gets a hard limit (pytest-timeout, thread method: the
+    # session is aborted with a traceback instead of spinning in cudaStreamSynchronize forever)
+    if config.pluginmanager.hasplugin("timeout"):
+        for item in items:
+            if item.get_closest_marker("timeout") is None:
+                item.add_marker(pytest.mark.timeout(420, method="thread"))
     try:
         import torch
         has_gpu = torch.cuda.is_available()
