@@ -987,7 +987,7 @@ TailSlot* tail_slot(cudaStream_t stream) {
 }
 
 // Decide the tail split of a K-major launch (see GemmParams::tail_*).  SNIPER_GEMM_TAIL=0 disables it.
-void plan_tail(GemmParams& p, long tiles, long grid_units, cudaStream_t stream) {
+void plan_tail(GemmParams& p, long tiles, long grid_units, cudaStream_t stream, bool dry = false) {
   p.tail_s = 0; p.tail_p = 0; p.tail_first = (int)tiles; p.tail_ws = nullptr; p.tail_cnt = nullptr;
   const char* e = getenv("SNIPER_GEMM_TAIL");   // 0 = off, 1 = K-slices only, 2 (default) = column pieces, else K-slices
   const int mode = e ? atoi(e) : 2;
@@ -1021,12 +1021,12 @@ void plan_tail(GemmParams& p, long tiles, long grid_units, cudaStream_t stream) 
     if (gain > best) { best = gain; s = c; }
   }
   if (s < 2) return;
-  TailSlot* slot = tail_slot(stream);
-  if (!slot) return;
+  TailSlot* slot = dry ? nullptr : tail_slot(stream);
+  if (!slot && !dry) return;
   p.tail_s = (int)s;
   p.tail_first = (int)(tiles - tail);
-  p.tail_ws = slot->ws;
-  p.tail_cnt = slot->cnt;
+  p.tail_ws = slot ? slot->ws : nullptr;
+  p.tail_cnt = slot ? slot->cnt : nullptr;
 }
 
 // K-major B operand [N rows, K] as launch() needs it to build the TMA map of a column piece
@@ -1333,6 +1333,43 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, long dy_ld, const void* X, long x_l
   }
   dim3 grid(Cout / 128 + (Cout % 128 ? 1 : 0), ntaps * p.wg_cin_blocks, splits);
   return launch(ma, mb, p, grid, (cudaStream_t)stream);
+}
+
+// Host-only query of the launch plan sniper_gemm_nt would use for C[M,N] = A[M,K] * B[N,K]^T with 16-byte aligned,
+// contiguous operands (no GPU needed; exercised by the CPU tests).  out[8] = {block_n, ring stages, staging buffers per
+// epilogue warp, tiles, persistent grid, tail mode (0 none, 1 K-slices, 2 column pieces), first tail tile, slices or
+// pieces per tail tile}.
+int sniper_gemm_plan(int M, int N, int K, int dtype, int* out) {
+  SN_CHECK(dtype == DT_TF32 || dtype == DT_BF16, "gemm_plan: dtype must be 0 (tf32) or 1 (bf16)");
+  const int E = dtype == DT_TF32 ? 32 : 64;
+  SN_CHECK(M > 0 && N > 0 && K > 0 && K % E == 0, "gemm_plan: K (%d) must be a positive multiple of %d", K, E);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int bn = pick_block_n(N, sn::div_up(M, 128));
+  p.cluster = pick_cluster(sn::div_up(M, 128));
+  fill_kmajor(p, dtype, bn);
+  p.mode = MODE_GEMM; p.M = M; p.N = N; p.num_kb = K / E;
+  p.epi_tma = (N % 32 == 0) ? 1 : 0;
+  p.splits = 1;
+  const long tiles = (long)sn::div_up(sn::div_up(M, 128), p.cluster) * sn::div_up(N, bn);
+  const long max_units = sn::kNumSMs / p.cluster;
+  plan_tail(p, tiles, max_units, nullptr, /*dry=*/true);
+  long units = tiles;
+  int mode = 0, factor = 1;
+  if (p.tail_s > 0) { mode = 1; factor = p.tail_s; }
+  if (p.tail_p > 0) { mode = 2; factor = p.tail_p; }
+  units = p.tail_first + (tiles - p.tail_first) * factor;
+  int stg = 1;
+  if (p.epi_tma) stg = p.num_kb <= 24 ? 2 : 1;
+  out[0] = bn;
+  out[1] = pick_stages(bn, stg);
+  out[2] = stg;
+  out[3] = (int)tiles;
+  out[4] = (int)((units < max_units ? units : max_units) * p.cluster);
+  out[5] = mode;
+  out[6] = p.tail_first;
+  out[7] = factor;
+  return 0;
 }
 
 }  // extern "C"

@@ -106,3 +106,33 @@ def test_product_path_fails_loudly_without_library(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsniper_b200.so")
     with pytest.raises(RuntimeError):
         _lib.lib()
+
+
+def test_gemm_launch_plan_host_logic():
+    """sniper_gemm_plan (host only): tile width, ring depth, persistent grid and tail split of the tcgen05 kernel for the
+    shapes of the training step.  out = {block_n, stages, staging bufs, tiles, grid, tail mode, first tail tile, factor}."""
+    import ctypes
+    from sniper_b200 import _lib
+    L = _lib.lib()
+
+    def plan(M, N, K, dtype=0):
+        out = (ctypes.c_int * 8)()
+        _lib.check(L.sniper_gemm_plan(M, N, K, dtype, ctypes.cast(out, ctypes.c_void_p)))
+        return list(out)
+    # conv2 of a stage-3 unit: 160 tiles of 128 x 256 on 148 SMs -> the 12 tail tiles are cut into 4 column pieces
+    bn, stages, stg, tiles, grid, mode, first, factor = plan(20480, 256, 2304)
+    assert (bn, tiles, grid, mode, first, factor) == (256, 160, 148, 2, 148, 4) and stages == 4 and stg == 1
+    # conv3 (K = 256): short K -> two staging buffers, one ring stage less; 640 tiles -> 48 tail tiles x 2 pieces
+    bn, stages, stg, tiles, grid, mode, first, factor = plan(20480, 1024, 256)
+    assert (bn, stg, stages, tiles, mode, first, factor) == (256, 2, 3, 640, 2, 592, 2)
+    # fc_offset: 47 tiles of 128 x 128 < 148 SMs, long K -> K-slices (3 per tile)
+    bn, stages, stg, tiles, grid, mode, first, factor = plan(6000, 128, 12544)
+    assert (bn, tiles, mode, first, factor) == (128, 47, 1, 0, 3) and grid == 141
+    # a multiple of the grid, a single tile, a ragged N (direct epilogue): no tail split
+    assert plan(148 * 128, 256, 512)[5] == 0
+    assert plan(128, 64, 64)[3:6] == [1, 1, 0]
+    assert plan(20480, 72, 4608)[5] == 0
+    # K-slices only where the fitted cost model predicts a gain (K = 1024 is too short for 128-wide tiles)
+    assert plan(6000, 128, 1024)[5] == 0
+    with pytest.raises(_lib.SniperError):
+        plan(128, 128, 100)
