@@ -6,9 +6,10 @@
  *                                                  because numpy's tie order is the reference's tie order)
  *                         cpu_soft_nms  :17-110   (method 2 = gaussian as used by nms.py:7-12; in-place swaps)
  *   lib/bbox/bbox.pyx     bbox_overlaps_cython :17-57, ignore_overlaps_cython :59-95 (float64, +1 convention)
- * PARITY PIN: the reference has no tests for these; tests/ pins this file against an independent
- * numpy restatement (oracle/host_np.py) and the pure-python twin bbox_overlaps_py semantics
- * (lib/bbox/bbox_transform.py:12-32).
+ * PARITY PIN: tests/test_host_cpu.py checks this file (and the product's host_ops.cpp) against the reference's OWN
+ * Cython modules, compiled from /root/reference by oracle/build_ref_cython.py into oracle/_ref: keep lists, surviving
+ * rows and their order, overlaps bit for bit; soft-NMS scores bit for bit (linear, hard) / within 2e-7 (Gaussian: the
+ * reference calls numpy's exp).
  */
 #include <math.h>
 #include <stdint.h>
@@ -68,18 +69,18 @@ int oracle_cpu_soft_nms(float* boxes, int N, float sigma, float Nt, float thresh
     pos = i + 1;
     while (pos < N) {
       float x1 = boxes[5 * pos], y1 = boxes[5 * pos + 1], x2 = boxes[5 * pos + 2], y2 = boxes[5 * pos + 3];
-      float area = (x2 - x1 + 1) * (y2 - y1 + 1);
-      float iw = (fminf(tx2, x2) - fmaxf(tx1, x1) + 1);
+      /* Cython promotes the Python-int literal in `x2 - x1 + 1` to the C double 1.0 (generated C: ((x2 - x1) + 1.0)):
+       * the sums and the products below run in double and are narrowed once, on the assignment to a float variable */
+      float area = (float)(((double)(x2 - x1) + 1.0) * ((double)(y2 - y1) + 1.0));
+      float iw = (float)((double)(fminf(tx2, x2) - fmaxf(tx1, x1)) + 1.0);
       if (iw > 0) {
-        float ih = (fminf(ty2, y2) - fmaxf(ty1, y1) + 1);
+        float ih = (float)((double)(fminf(ty2, y2) - fmaxf(ty1, y1)) + 1.0);
         if (ih > 0) {
-          float t0 = (tx2 - tx1 + 1) * (ty2 - ty1 + 1);
-          float t1 = t0 + area;
           float t2 = iw * ih;
-          float ua = t1 - t2;
-          float ov = iw * ih / ua;
+          float ua = (float)(((((double)(tx2 - tx1) + 1.0) * ((double)(ty2 - ty1) + 1.0)) + (double)area) - (double)t2);
+          float ov = t2 / ua;
           float weight;
-          if (method == 1) weight = ov > Nt ? 1 - ov : 1;
+          if (method == 1) weight = ov > Nt ? (float)(1.0 - (double)ov) : 1;
           else if (method == 2) {
             float q = -(ov * ov) / sigma;
             weight = (float)exp((double)q);

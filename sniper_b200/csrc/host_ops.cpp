@@ -157,15 +157,19 @@ int sniper_cpu_soft_nms(float* b, int N, float sigma, float Nt, float threshold,
     int pos = i + 1;
     while (pos < N) {
       const float x1 = b[5 * pos], y1 = b[5 * pos + 1], x2 = b[5 * pos + 2], y2 = b[5 * pos + 3];
-      const float area = (x2 - x1 + 1) * (y2 - y1 + 1);
-      const float iw = std::min(t[2], x2) - std::max(t[0], x1) + 1;
+      // the reference's Cython turns the int literal of `x2 - x1 + 1` into the double 1.0: sums / products in double,
+      // narrowed to float on assignment (lib/nms/cpu_nms.pyx:73-80 as cythonized)
+      const float area = (float)(((double)(x2 - x1) + 1.0) * ((double)(y2 - y1) + 1.0));
+      const float iw = (float)((double)(std::min(t[2], x2) - std::max(t[0], x1)) + 1.0);
       if (iw > 0) {
-        const float ih = std::min(t[3], y2) - std::max(t[1], y1) + 1;
+        const float ih = (float)((double)(std::min(t[3], y2) - std::max(t[1], y1)) + 1.0);
         if (ih > 0) {
-          const float ua = (t[2] - t[0] + 1) * (t[3] - t[1] + 1) + area - iw * ih;
-          const float ov = iw * ih / ua;
+          const float inter = iw * ih;
+          const float ua = (float)(((((double)(t[2] - t[0]) + 1.0) * ((double)(t[3] - t[1]) + 1.0)) + (double)area) -
+                                   (double)inter);
+          const float ov = inter / ua;
           float weight;
-          if (method == 1) weight = ov > Nt ? 1 - ov : 1;
+          if (method == 1) weight = ov > Nt ? (float)(1.0 - (double)ov) : 1;
           else if (method == 2) weight = (float)exp((double)(-(ov * ov) / sigma));
           else weight = ov > Nt ? 0 : 1;
           b[5 * pos + 4] = weight * b[5 * pos + 4];

@@ -78,6 +78,20 @@ def main():
     np.savez_compressed(os.path.join(HERE, "mpt_refcpu.npz"), seed=np.int64(seed), fg=fg, rois=ref["rois"],
                         label=ref["label"], bbox_target=ref["bbox_target"], bbox_weight=ref["bbox_weight"],
                         proposal_rois=prois[:kept], proposal_scores=pscores[:kept])
+    # reference Cython host code (oracle/_ref/ref_cpu_nms, ref_bbox built by oracle/build_ref_cython.py)
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+    import ref_bbox
+    import ref_cpu_nms
+    rng = np.random.RandomState(5)
+    n = 500
+    r = synth.rois_for_pool(rng, n, 1)
+    dets = np.concatenate([r[:, 1:], (rng.permutation(n).reshape(-1, 1) + 1.0) / (n + 1.0)], 1).astype(np.float32)
+    keep = np.array(ref_cpu_nms.cpu_nms(dets.copy(), 0.7), np.int32)
+    soft = {m: np.array(ref_cpu_nms.cpu_soft_nms(dets.copy(), sigma=0.55, Nt=0.3, threshold=0.001, method=m)) for m in (0, 1, 2)}
+    qa = synth.rois_for_pool(rng, 60, 1)[:, 1:].astype(np.float64)
+    ov = ref_bbox.bbox_overlaps_cython(dets[:, :4].astype(np.float64), qa)
+    np.savez_compressed(os.path.join(HERE, "host_refcython.npz"), dets=dets, keep=keep, soft0=soft[0], soft1=soft[1],
+                        soft2=soft[2], query=qa, overlaps=ov)
     print("golden fixtures written to", HERE)
 
 

@@ -2,6 +2,7 @@
 No GPU, no compute kernels: runs in the CPU test tier."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -136,3 +137,63 @@ def test_gemm_launch_plan_host_logic():
     assert plan(6000, 128, 1024)[5] == 0
     with pytest.raises(_lib.SniperError):
         plan(128, 128, 100)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pinning against the reference's OWN Cython host code (lib/nms/cpu_nms.pyx, lib/bbox/bbox.pyx), compiled from
+# /root/reference by oracle/build_ref_cython.py into oracle/_ref (4 dead tokens rewritten on the fly, see that file).
+# ---------------------------------------------------------------------------------------------------------------
+def _ref_cython(name):
+    import importlib
+    ref_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        return importlib.import_module(name)
+    except ImportError:
+        pytest.skip("oracle/_ref/%s not built (needs /root/reference and Cython at build time)" % name)
+
+
+@pytest.mark.parametrize("seed,n,thresh", [(0, 600, 0.7), (1, 2000, 0.5), (2, 50, 0.3)])
+def test_cpu_nms_matches_reference_cython(seed, n, thresh):
+    ref = _ref_cython("ref_cpu_nms")
+    rng = np.random.RandomState(seed)
+    rois = synth.rois_for_pool(rng, n, 1)
+    dets = np.concatenate([rois[:, 1:], rng.permutation(n).reshape(-1, 1) / float(n)], 1).astype(np.float32)   # tie-free
+    want = [int(i) for i in ref.cpu_nms(dets.copy(), thresh)]
+    assert host.cpu_nms(dets, thresh) == want                       # product (libsniper_b200.so, host_ops.cpp)
+    assert O.cpu_nms(dets, thresh).tolist() == want                 # oracle (oracle/host.c)
+    assert 0 < len(want) < n
+
+
+@pytest.mark.parametrize("method,sigma,Nt", [(2, 0.55, 0.3), (1, 0.5, 0.3), (0, 0.5, 0.45)])
+def test_cpu_soft_nms_matches_reference_cython(method, sigma, Nt):
+    """Gaussian (SNIPER's setting sigma 0.55, yml:225), linear and hard variants: same surviving rows in the same
+    order; scores bit-identical for linear / hard, within 1 ulp for the Gaussian (the reference calls np.exp on a
+    float32 scalar, the restatements double exp)."""
+    ref = _ref_cython("ref_cpu_nms")
+    rng = np.random.RandomState(7 + method)
+    n = 400
+    rois = synth.rois_for_pool(rng, n, 1)
+    boxes = np.concatenate([rois[:, 1:], (rng.permutation(n).reshape(-1, 1) + 1.0) / (n + 1.0)], 1).astype(np.float32)
+    want = np.array(ref.cpu_soft_nms(boxes.copy(), sigma=sigma, Nt=Nt, threshold=0.001, method=method))
+    got = host.cpu_soft_nms(boxes.copy(), sigma=sigma, Nt=Nt, threshold=0.001, method=method)
+    orc = O.cpu_soft_nms(boxes.copy(), sigma=sigma, Nt=Nt, threshold=0.001, method=method)
+    assert got.shape == want.shape and orc.shape == want.shape and 0 < want.shape[0] <= n
+    assert np.array_equal(got[:, :4], want[:, :4]) and np.array_equal(orc[:, :4], want[:, :4])
+    if method == 2:
+        assert np.abs(got[:, 4] - want[:, 4]).max() <= 2e-7 and np.abs(orc[:, 4] - want[:, 4]).max() <= 2e-7
+    else:
+        assert np.array_equal(got[:, 4], want[:, 4]) and np.array_equal(orc[:, 4], want[:, 4])
+
+
+def test_bbox_overlaps_match_reference_cython():
+    ref = _ref_cython("ref_bbox")
+    rng = np.random.RandomState(3)
+    a = synth.rois_for_pool(rng, 300, 1)[:, 1:].astype(np.float64)
+    b = synth.rois_for_pool(rng, 80, 1)[:, 1:].astype(np.float64)
+    want = ref.bbox_overlaps_cython(a, b)
+    assert np.array_equal(host.bbox_overlaps(a, b), want) and np.array_equal(O.bbox_overlaps(a, b), want)
+    want_i = ref.ignore_overlaps_cython(a, b)
+    assert np.array_equal(host.ignore_overlaps(a, b), want_i) and np.array_equal(O.bbox_overlaps(a, b, ignore=True), want_i)
+    assert (want > 0).sum() > 100
