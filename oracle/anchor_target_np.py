@@ -7,8 +7,10 @@ NumPy (Python 3) restatement of the reference's RPN anchor matching,
 with the RNG subsampling (npr.choice, :328-338) factored out into `subsample()` so that the pre-subsample
 labels can be compared bit-exactly and the chosen disable indices fed to the device op.
 Inputs are the already cropped/scaled/rounded/clipped/size-filtered boxes (the part of worker() before
-:262 is dataset bookkeeping).  PARITY PIN: the reference has no tests for this path and is Py2+mxnet
-(cannot be imported); "parity unpinned", cross-checked in tests/ against bbox_overlaps_py semantics.
+:262 is dataset bookkeeping).  PARITY PIN: tests/test_oracle_cpu.py runs the reference's OWN anchor_worker.worker
+(oracle/run_ref_anchor_worker.py executes the class from /root/reference with its generate_anchors, bbox_transform
+and Cython bbox_overlaps; four Python-2 tokens rewritten in memory) and this file reproduces its labels (after the
+reference's npr.choice subsampling), positive indices and targets bit for bit; fixture tests/golden/anchor_target_ref.npz.
 """
 import numpy as np
 

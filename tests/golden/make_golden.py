@@ -5,6 +5,8 @@
                       20 GT boxes + 400 proposals, three scales, chip 512, fixed stride, srand(seed).
   mpt_small.npz     : oracle/mpt.c on a seeded 2-chip input (the reference ships no vectors for this operator).
   psroi_small.npz   : oracle/psroi.c on the reference's own test shapes (test_operator.py:4358-4389).
+  host_refcython.npz / anchor_target_ref.npz : outputs of the reference's own Cython host code (cpu_nms, cpu_soft_nms,
+                      bbox overlaps; oracle/build_ref_cython.py) and of its anchor_worker.worker (oracle/run_ref_anchor_worker.py).
   mpt_refcpu.npz    : output of the REFERENCE's own CPU operators -- MultiProposalTargetOp<cpu>::Forward
                       (multi_proposal_target.cc) and MultiProposalGPUOp<cpu>::Forward (multi_proposal.cc), compiled as
                       they lie into oracle/_ref/libref_mpt.so / libref_mp.so -- on a seeded 1-chip input with tie-free
@@ -92,6 +94,14 @@ def main():
     ov = ref_bbox.bbox_overlaps_cython(dets[:, :4].astype(np.float64), qa)
     np.savez_compressed(os.path.join(HERE, "host_refcython.npz"), dets=dets, keep=keep, soft0=soft[0], soft1=soft[1],
                         soft2=soft[2], query=qa, overlaps=ov)
+    # the reference's own anchor_worker.worker (oracle/run_ref_anchor_worker.py)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import run_ref_anchor_worker as R
+    worker = R.load_reference_worker()(R.make_cfg(), 512)
+    boxes, classes, gtids, nids = R.synth_case(4, 60, 41)
+    lab, tg, pids, fgt = R.run_reference(worker, boxes, classes, gtids, nids, seed=104)
+    np.savez_compressed(os.path.join(HERE, "anchor_target_ref.npz"), boxes=boxes, n_valid=np.int64(41), seed=np.int64(104),
+                        labels=lab, targets_pos=tg, pids=pids)
     print("golden fixtures written to", HERE)
 
 

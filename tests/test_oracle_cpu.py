@@ -1,11 +1,15 @@
 """CPU checks that pin the oracle itself (no GPU, no product code)."""
 import ctypes
+import os
+import sys
 
 import numpy as np
 import pytest
 
 import oracle_lib as O
 from sniper_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_oracle_expf_is_correctly_rounded():
@@ -359,3 +363,35 @@ def test_inference_op_gpu_build_extras():
     assert fast_all["rois"].tobytes() == plain["rois"].tobytes()
     fast = O.multi_proposal(cls_prob, bbox_pred, im_info, flags=2, roi_iou_thresh=0.3)
     assert fast["keep_idx"][0] == plain["keep_idx"][0] and int(fast["num_kept"][0]) == 300
+
+
+@pytest.mark.parametrize("seed,n_gt,n_valid", [(0, 12, 9), (1, 30, 30), (2, 5, 2), (3, 1, 0), (4, 60, 41)])
+def test_anchor_target_oracle_matches_the_reference_anchor_worker(seed, n_gt, n_valid):
+    """oracle/anchor_target_np.py == the reference's own anchor_worker.worker (data_workers.py:130-371, executed here by
+    oracle/run_ref_anchor_worker.py with its own generate_anchors / bbox_transform / Cython bbox_overlaps): labels after
+    the reference's npr.choice subsampling, positive-anchor indices and their regression targets, bit for bit."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import anchor_target_np as AT
+    try:
+        import run_ref_anchor_worker as R
+        worker = R.load_reference_worker()(R.make_cfg(), 512)
+    except (ImportError, OSError) as e:
+        pytest.skip("reference anchor_worker not runnable here: %s" % e)
+    boxes, classes, gtids, nids = R.synth_case(seed, n_gt, n_valid)
+    lab_ref, tg_ref, pids_ref, fgt = R.run_reference(worker, boxes, classes, gtids, nids, seed=100 + seed)
+    valid = np.zeros(n_gt, bool)
+    valid[nids] = True
+    for i in range(n_gt):                         # a GT identical to a valid one counts as valid (mov == 1, :262-272)
+        if not valid[i] and n_valid and (boxes[nids] == boxes[i]).all(1).any():
+            valid[i] = True
+    res = AT.anchor_target(boxes[valid], boxes[~valid], np.array([512, 512, 1.0]))
+    disable = AT.subsample(res["labels"], np.random.RandomState(100 + seed))
+    labels = res["labels"].copy()
+    labels[disable] = -1
+    lab, tg, w = AT.pack(labels, res["targets"], 32, 32, res["A"])
+    assert lab.tobytes() == lab_ref.tobytes()
+    pids = np.stack(np.where(w == 1))
+    assert np.array_equal(pids, pids_ref)
+    assert tg[tuple(pids)].tobytes() == tg_ref.tobytes()
+    assert (lab_ref == 1).sum() <= 128 and (lab_ref >= 0).sum() <= 256
+    assert np.array_equal(fgt[:n_gt, :4], boxes) and (fgt[n_gt:] == -1).all()
