@@ -395,3 +395,33 @@ def test_anchor_target_oracle_matches_the_reference_anchor_worker(seed, n_gt, n_
     assert tg[tuple(pids)].tobytes() == tg_ref.tobytes()
     assert (lab_ref == 1).sum() <= 128 and (lab_ref >= 0).sum() <= 256
     assert np.array_equal(fgt[:n_gt, :4], boxes) and (fgt[n_gt:] == -1).all()
+
+
+@pytest.mark.parametrize("case", ["no_gt", "hundred_gt", "everything_filtered", "B17", "tiny_boxes"])
+def test_cpuop_restatement_edge_cases_against_the_reference_binary(case):
+    """Edge cases of the reference CPU operator reproduced bit for bit: no ground truth, all 100 GT slots used, a valid
+    range that filters every proposal (only filler rows + GT rows remain), B = 17 (> the 16 images the reference's GPU
+    operator sizes its host buffers for), deltas that shrink every box below the min-size test."""
+    B = 17 if case == "B17" else 2
+    cls_prob, bbox_pred, im_info, gts, vr = synth.mpt_inputs(40, B)
+    cls_prob = _tie_free(cls_prob, 40)
+    if case == "no_gt":
+        gts = np.full_like(gts, -1.0)
+    elif case == "hundred_gt":
+        rng = np.random.RandomState(9)
+        x1 = rng.uniform(0, 400, (B, 100)); y1 = rng.uniform(0, 400, (B, 100))
+        gts = np.stack([x1, y1, x1 + rng.uniform(20, 100, (B, 100)), y1 + rng.uniform(20, 100, (B, 100)),
+                        rng.randint(1, 81, (B, 100)).astype(np.float64)], 2).astype(np.float32)
+    elif case == "everything_filtered":
+        vr = np.tile(np.array([[600.0, 601.0]], np.float32), (B, 1))
+    elif case == "tiny_boxes":
+        bbox_pred = bbox_pred.copy()
+        bbox_pred.reshape(B, 21, 4, 32, 32)[:, :, 2:] = -8.0          # exp(-8) * anchor size < 3 px
+    ref = _need_ref(O.ref_multi_proposal_target(cls_prob, bbox_pred, im_info, gts, vr))
+    mine = O.multi_proposal_target_cpuop(cls_prob, bbox_pred, im_info, gts, vr)
+    for k in ("rois", "label", "bbox_weight", "bbox_target"):
+        assert mine[k].tobytes() == ref[k].tobytes(), (case, k)
+    if case in ("everything_filtered", "tiny_boxes"):
+        assert (mine["num_kept"] == 0).all() and (ref["rois"][0, 1:] == [0, 0, 100, 100]).all()
+    if case == "hundred_gt":
+        assert (ref["label"] > 0).sum() > 50          # GT rows inside the valid range are appended and match themselves
