@@ -43,8 +43,13 @@ def test_register_and_custom_roundtrip_cpu():
     assert float(g.sum()) == 12.0
     with pytest.raises(KeyError):
         op.Custom(data=x, op_type='NoSuchOp')
-    for name in ('MultiProposalTarget',):
+    for name in ('MultiProposalTarget', 'MultiProposal'):
         assert name in op.get_all_registered_operators()
+    q = op.MultiProposalProp(batch_size='4', rpn_post_nms_top_n='300', roi_iou_thresh='0.3', fast_nms='True',
+                             suppress_anchor_types='True')      # kwargs arrive as strings (box_annotator_ohem.py:86-120)
+    assert q.list_arguments() == ['cls_prob', 'bbox_pred', 'im_info'] and q.list_outputs() == ['output', 'score']
+    assert q.infer_shape([[4, 42, 32, 32], [4, 84, 32, 32], [4, 3]])[1] == [[1200, 5], [1200, 1]]
+    assert q.fast_nms and q.suppress and q.pre == 12000 and abs(q.roi_iou_thresh - 0.3) < 1e-9
     p = op.MultiProposalTargetProp(batch_size='20', scales='(2,4,7,10,13,16,24)', ratios='(0.5,1,2)', crowd_boxes='x')
     assert p.list_arguments() == ['cls_prob', 'bbox_pred', 'im_info', 'gt_boxes', 'valid_ranges']
     assert p.list_outputs() == ['rois', 'label', 'bbox_target', 'bbox_weight']
