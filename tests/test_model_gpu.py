@@ -244,11 +244,11 @@ def test_wgrad_side_stream_matches_single_stream():
     grads = []
     for side in (False, False, True):
         cfg = model.Cfg()
-        cfg.batch_images = 2
+        cfg.batch_images = 1
         cfg.wgrad_splits = 1
         cfg.wgrad_stream = side
         net = model.SniperResNet101(cfg, deform_offset_std=0.01, seed=5)
-        batch = synth_batch.make_batch(2, seed=9, device="cuda")
+        batch = synth_batch.make_batch(1, seed=9, device="cuda")
         net.forward_backward(batch)
         torch.cuda.synchronize()
         grads.append(net.P.g.clone())
