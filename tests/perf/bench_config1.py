@@ -2,14 +2,14 @@
 synthetic 1333x800 image (20 GT boxes + 2000 proposal boxes), then cpu_nms (thresh 0.7) and cpu_soft_nms (sigma 0.55) on
 6000 detections.  Times this repo's host entry points (libsniper_b200.so, host_ops.cpp) next to the reference's own code
 built into oracle/_ref (cchips.cpp compiled as it lies; cpu_nms.pyx cythonized) and checks that the outputs are identical.
-Usage: python tools/bench_config1.py > profiles/config1_host_rNN.md"""
+Usage: python tests/perf/bench_config1.py > profiles/config1_host_rNN.md"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))

@@ -1,7 +1,7 @@
 """Times the two proposal operators on the GPU (CUDA events) next to the REFERENCE's own CPU operator binaries
 (oracle/_ref/libref_mpt.so / libref_mp.so, compiled from multi_proposal_target.cc / multi_proposal.cc) on the host
 cores of the same box.  B = 20 chips of 512x512 (21504 anchors each), 300 rois per chip.
-Usage: python tools/bench_ops.py > profiles/proposal_ops_rNN.md"""
+Usage: python tests/perf/bench_ops.py > profiles/proposal_ops_rNN.md"""
 import os
 import sys
 import time
@@ -9,7 +9,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O  # noqa: E402  (checker / CPU baseline only)
