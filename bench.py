@@ -269,7 +269,7 @@ def run_ours(args):
         achieved = tc_flops / (tc_ms / 1e3) / 1e12
         cpu = None
         if not args.skip_cpu:
-            cpu = cpu_baseline(sample_chips=args.cpu_chips)
+            cpu = cpu_baseline(sample_chips=args.cpu_chips, steps=3, warmup=1)
         result = {
             "metric": "512x512 chips/sec train (ResNet-101)", "value": round(value, 2), "unit": "chips/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
@@ -302,25 +302,30 @@ def run_ours(args):
     return result
 
 
-def cpu_baseline(sample_chips=1):
+def cpu_baseline(sample_chips=1, steps=2, warmup=1, budget_s=None):
     """Reference-style CPU execution of the same training step on the host cores (kind 'port': the MXNet CPU
-    stack cannot be built offline; dense layers run in PyTorch-CPU fp32, SNIPER ops in the C oracle)."""
+    stack cannot be built offline; dense layers run in PyTorch-CPU fp32, SNIPER ops in the C oracle / the reference's
+    own CPU MultiProposalTarget binary).  Warm steps only: `warmup` untimed steps precede the `steps` timed ones."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_train_step
-    return cpu_train_step.run(sample_chips)
+    return cpu_train_step.run(sample_chips, steps=steps, warmup=warmup, budget_s=budget_s)
 
 
 def run_reference(args):
+    """The reference arm: `--steps K --warmup W` training steps of a bounded sample (--cpu-chips chips per step) of the
+    same workload on the host cores; stops after ~3 minutes of timed steps and reports the steps really timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cpu = cpu_baseline(sample_chips=args.cpu_chips)
+    cpu = cpu_baseline(sample_chips=args.cpu_chips, steps=args.steps, warmup=min(args.warmup, 3), budget_s=180.0)
     v = cpu["value"]
     print(json.dumps({
         "impl": "reference", "metric": "512x512 chips/sec train (ResNet-101)", "value": v, "unit": "chips/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * args.chips / v, 1) if v else None,
+        "n_gpus": args.gpus, "steps": cpu["steps_timed"], "warmup": cpu["warmup_steps"],
+        "ms_per_step": round(1e3 * cpu["sec_per_step"], 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": "ResNet-101 SNIPER Faster-R-CNN/R-FCN, 512x512 chips, fp32, CPU host cores (bounded sample)"},
+        "config": {"workload": "ResNet-101 SNIPER Faster-R-CNN/R-FCN, 512x512 chips, fp32, CPU host cores; each step = "
+                               "%d chip(s) (bounded sample of the 20-chip batch)" % args.cpu_chips},
         "cpu_baseline": cpu,
         "e2e": {"value": v, "unit": "chips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)

@@ -112,6 +112,7 @@ void oracle_deform_psroi_fwd(const float* bottom_data, const float* bottom_rois,
   int channels_each_class = no_trans ? output_dim : output_dim / num_classes;
   long count = (long)num_rois * output_dim * pooled_height * pooled_width;
   int S2 = sample_per_part * sample_per_part;
+#pragma omp parallel for schedule(static)
   for (long index = 0; index < count; ++index) {
     int pw = index % pooled_width;
     int ph = (index / pooled_width) % pooled_height;
@@ -156,52 +157,63 @@ void oracle_deform_psroi_bwd(const float* top_diff, const float* top_count, cons
   int pooled_height = pooled_size, pooled_width = pooled_size;
   if (no_trans) num_classes = 1;
   int channels_each_class = no_trans ? output_dim : output_dim / num_classes;
-  long count = (long)num_rois * output_dim * pooled_height * pooled_width;
-  for (long index = 0; index < count; ++index) {
-    int pw = index % pooled_width;
-    int ph = (index / pooled_width) % pooled_height;
-    int ctop = (index / pooled_width / pooled_height) % output_dim;
-    int n = index / pooled_width / pooled_height / output_dim;
-    bin_geom g;
-    deform_geom(bottom_rois, bottom_trans, no_trans, trans_std, spatial_scale, n, ctop, ph, pw, pooled_height,
-                pooled_width, sample_per_part, group_size, part_size, num_classes, channels_each_class, &g);
-    if (top_count[index] <= 0) continue;
-    float diff_val = top_diff[index] / top_count[index];
-    size_t img = (size_t)g.roi_batch_ind * channels * height * width;
-    for (int ih = 0; ih < sample_per_part; ih++) {
-      for (int iw = 0; iw < sample_per_part; iw++) {
-        float tw = iw * g.sub_bin_size_w;
-        float w = g.wstart + tw;
-        float th = ih * g.sub_bin_size_h;
-        float h = g.hstart + th;
-        if (w < -0.5 || w > width - 0.5 || h < -0.5 || h > height - 0.5) continue;
-        w = (float)fmin(fmax(w, 0.), width - 1.);
-        h = (float)fmin(fmax(h, 0.), height - 1.);
-        int c = (ctop * group_size + g.gh) * group_size + g.gw;
-        int x0 = (int)floorf(w), x1 = (int)ceilf(w), y0 = (int)floorf(h), y1 = (int)ceilf(h);
-        float dist_x = w - x0, dist_y = h - y0;
-        float q00 = (1 - dist_x) * (1 - dist_y);
-        float q01 = (1 - dist_x) * dist_y;
-        float q10 = dist_x * (1 - dist_y);
-        float q11 = dist_x * dist_y;
-        size_t base = img + (size_t)c * height * width;
-        bottom_data_diff[base + y0 * width + x0] += q00 * diff_val;
-        bottom_data_diff[base + y1 * width + x0] += q01 * diff_val;
-        bottom_data_diff[base + y0 * width + x1] += q10 * diff_val;
-        bottom_data_diff[base + y1 * width + x1] += q11 * diff_val;
-        if (no_trans) continue;
-        float U00 = bottom_data[base + y0 * width + x0];
-        float U01 = bottom_data[base + y1 * width + x0];
-        float U10 = bottom_data[base + y0 * width + x1];
-        float U11 = bottom_data[base + y1 * width + x1];
-        float diff_x = (U11 * dist_y + U10 * (1 - dist_y) - U01 * dist_y - U00 * (1 - dist_y)) * trans_std * diff_val;
-        diff_x *= g.roi_width;
-        float diff_y = (U11 * dist_x + U01 * (1 - dist_x) - U10 * dist_x - U00 * (1 - dist_x)) * trans_std * diff_val;
-        diff_y *= g.roi_height;
-        bottom_trans_diff[(((n * num_classes + g.class_id) * 2) * part_size + g.part_h) * part_size + g.part_w] += diff_x;
-        bottom_trans_diff[(((n * num_classes + g.class_id) * 2 + 1) * part_size + g.part_h) * part_size + g.part_w] += diff_y;
-      }
-    }
+  /* Two race-free passes so that the host threads can share the work WITHOUT changing any summation order: pass 0
+   * accumulates bottom_data_diff, parallel over the output channel (a bottom channel receives from one ctop only, and
+   * for a fixed channel the (n, ph, pw) order below is the sequential one); pass 1 accumulates bottom_trans_diff,
+   * parallel over the roi (fixed n: sequential (ctop, ph, pw) order).  Bit-identical to the single loop. */
+  for (int pass = 0; pass < (no_trans ? 1 : 2); ++pass) {
+    const int outer = pass == 0 ? output_dim : num_rois;
+    const int inner = pass == 0 ? num_rois : output_dim;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int o = 0; o < outer; ++o)
+      for (int i = 0; i < inner; ++i)
+        for (int ph = 0; ph < pooled_height; ++ph)
+          for (int pw = 0; pw < pooled_width; ++pw) {
+            const int ctop = pass == 0 ? o : i, n = pass == 0 ? i : o;
+            const long index = (((long)n * output_dim + ctop) * pooled_height + ph) * pooled_width + pw;
+            bin_geom g;
+            deform_geom(bottom_rois, bottom_trans, no_trans, trans_std, spatial_scale, n, ctop, ph, pw, pooled_height,
+                        pooled_width, sample_per_part, group_size, part_size, num_classes, channels_each_class, &g);
+            if (top_count[index] <= 0) continue;
+            float diff_val = top_diff[index] / top_count[index];
+            size_t img = (size_t)g.roi_batch_ind * channels * height * width;
+            for (int ih = 0; ih < sample_per_part; ih++) {
+              for (int iw = 0; iw < sample_per_part; iw++) {
+                float tw = iw * g.sub_bin_size_w;
+                float w = g.wstart + tw;
+                float th = ih * g.sub_bin_size_h;
+                float h = g.hstart + th;
+                if (w < -0.5 || w > width - 0.5 || h < -0.5 || h > height - 0.5) continue;
+                w = (float)fmin(fmax(w, 0.), width - 1.);
+                h = (float)fmin(fmax(h, 0.), height - 1.);
+                int c = (ctop * group_size + g.gh) * group_size + g.gw;
+                int x0 = (int)floorf(w), x1 = (int)ceilf(w), y0 = (int)floorf(h), y1 = (int)ceilf(h);
+                float dist_x = w - x0, dist_y = h - y0;
+                float q00 = (1 - dist_x) * (1 - dist_y);
+                float q01 = (1 - dist_x) * dist_y;
+                float q10 = dist_x * (1 - dist_y);
+                float q11 = dist_x * dist_y;
+                size_t base = img + (size_t)c * height * width;
+                if (pass == 0) {
+                  bottom_data_diff[base + y0 * width + x0] += q00 * diff_val;
+                  bottom_data_diff[base + y1 * width + x0] += q01 * diff_val;
+                  bottom_data_diff[base + y0 * width + x1] += q10 * diff_val;
+                  bottom_data_diff[base + y1 * width + x1] += q11 * diff_val;
+                  continue;
+                }
+                float U00 = bottom_data[base + y0 * width + x0];
+                float U01 = bottom_data[base + y1 * width + x0];
+                float U10 = bottom_data[base + y0 * width + x1];
+                float U11 = bottom_data[base + y1 * width + x1];
+                float diff_x = (U11 * dist_y + U10 * (1 - dist_y) - U01 * dist_y - U00 * (1 - dist_y)) * trans_std * diff_val;
+                diff_x *= g.roi_width;
+                float diff_y = (U11 * dist_x + U01 * (1 - dist_x) - U10 * dist_x - U00 * (1 - dist_x)) * trans_std * diff_val;
+                diff_y *= g.roi_height;
+                bottom_trans_diff[(((n * num_classes + g.class_id) * 2) * part_size + g.part_h) * part_size + g.part_w] += diff_x;
+                bottom_trans_diff[(((n * num_classes + g.class_id) * 2 + 1) * part_size + g.part_h) * part_size + g.part_w] += diff_y;
+              }
+            }
+          }
   }
 }
 

@@ -1,0 +1,225 @@
+"""ORACLE -- test & measurement infrastructure only (never imported by the product path).
+
+`get_symbol_rcnn(cfg, is_train=True)` of the reference (symbols/faster/resnet_mx_101_e2e.py:227-345, with
+resnetc4 :394-420, resnetc5 :422-448, residual_unit :36-69, residual_unit_deform :106-145, get_rpn :147-155) restated
+as a PyTorch autograd graph over tensors carrying the REFERENCE's parameter names and layouts (OIHW convolutions,
+NCHW-flattened FullyConnected inputs, separate rpn_cls_score / rpn_bbox_pred and cls_score / bbox_pred heads).  Runs
+in float64 (the parity oracle of tests/test_graph_parity_gpu.py) or float32 (the CPU baseline of bench.py).
+
+Operators with no PyTorch equivalent:
+  * DeformableConvolution: `deform_conv2d` below, a differentiable gather formulation of deformable_im2col.cuh:78-113,
+    216-263 (+ the GEMM of deformable_convolution-inl.h:111-168);
+  * DeformablePSROIPooling: `DeformPSROI`, an autograd.Function around the C oracle (oracle/psroi.c, restating
+    deformable_psroi_pooling.cu:71-161 forward and :203-330 backward);
+  * MultiProposalTarget: a callback (the tests pass the C oracle, oracle/mpt.c); its backward is a zero fill
+    (multi_proposal_target.cu:591-615), so rois / labels / targets enter the graph as constants.
+Gradient conventions follow the reference operators, not PyTorch's defaults: SoftmaxOutput(normalization='valid',
+use_ignore) back-propagates (p - onehot) * grad_scale / #valid (softmax_output-inl.h:162-263) = the gradient of the
+mean cross entropy over valid labels; MakeLoss back-propagates grad_scale * d(sum) (make_loss-inl.h).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+UNITS = (3, 4, 23, 3)
+FILTERS = (64, 256, 512, 1024, 2048)
+FIXED = ("conv0", "bn0", "stage1", "bn_data")        # FIXED_PARAMS, sniper_res101_e2e.yml:22-25 (+ use_global_stats bn_data)
+
+
+def is_fixed(name):
+    return any(f in name for f in FIXED)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def deform_conv2d(x, offset, w, dil=2, pad=2, dg=4):
+    """DeformableConvolution forward, kernel 3x3, stride 1 (resnet_mx_101_e2e.py:124-130).  x [N,C,H,W], offset
+    [N, dg*2*9, H, W] with channel g*18 + 2*tap (+1) = (dy, dx) of tap (i,j)=divmod(tap,3) in deformable group g
+    (deformable_im2col.cuh:237-246), w [Cout,C,3,3].  Sampling rule of deformable_im2col.cuh:78-113 + :247-258: a
+    sample contributes iff 0 <= h < H and 0 <= w < W; `h_low >= H-1` clamps both corners to the last row (same for
+    columns)."""
+    N, C, H, W = x.shape
+    cpg = C // dg
+    dev = x.device
+    hh, ww = torch.meshgrid(torch.arange(H, device=dev), torch.arange(W, device=dev), indexing="ij")
+    n_idx = torch.arange(N, device=dev).view(N, 1, 1).expand(N, H, W)
+    xh = x.permute(0, 2, 3, 1)                                        # [N,H,W,C]
+    cols = []
+    for tap in range(9):
+        i, j = divmod(tap, 3)
+        per_g = []
+        for g in range(dg):
+            oh = offset[:, g * 18 + 2 * tap]
+            ow = offset[:, g * 18 + 2 * tap + 1]
+            h_im = (hh - pad + i * dil).to(x.dtype) + oh
+            w_im = (ww - pad + j * dil).to(x.dtype) + ow
+            valid = (h_im >= 0) & (w_im >= 0) & (h_im < H) & (w_im < W)
+            h_low = torch.floor(h_im).clamp(max=H - 1)
+            w_low = torch.floor(w_im).clamp(max=W - 1)
+            hc = torch.where(torch.floor(h_im) >= H - 1, h_low, h_im)
+            wc = torch.where(torch.floor(w_im) >= W - 1, w_low, w_im)
+            h_high = (h_low + 1).clamp(max=H - 1)
+            w_high = (w_low + 1).clamp(max=W - 1)
+            lh, lw = hc - h_low, wc - w_low
+            xg = xh[..., g * cpg:(g + 1) * cpg]
+
+            def at(hi, wi, xg=xg):
+                return xg[n_idx, hi.long().clamp(0, H - 1), wi.long().clamp(0, W - 1)]
+            v = ((1 - lh) * (1 - lw)).unsqueeze(-1) * at(h_low, w_low) + ((1 - lh) * lw).unsqueeze(-1) * at(h_low, w_high) \
+                + (lh * (1 - lw)).unsqueeze(-1) * at(h_high, w_low) + (lh * lw).unsqueeze(-1) * at(h_high, w_high)
+            per_g.append(v * valid.unsqueeze(-1).to(x.dtype))
+        cols.append(torch.cat(per_g, -1))
+    col = torch.stack(cols, 3)                                        # [N,H,W,9,C]
+    wt = w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, C)              # [Cout, tap, C]
+    return torch.einsum("nhwtc,otc->nohw", col, wt)
+
+
+class DeformPSROI(torch.autograd.Function):
+    """DeformablePSROIPooling through the C oracle (float32 inside; rois are constants)."""
+
+    @staticmethod
+    def forward(ctx, data, trans, rois_np, kw):
+        import oracle_lib as O
+        d = data.detach().cpu().numpy().astype(np.float32)
+        t = None if trans is None else trans.detach().cpu().numpy().astype(np.float32)
+        out, cnt, _ = O.deform_psroi_fwd(d, rois_np, t, no_trans=t is None, **kw)
+        ctx.saved = (d, t, rois_np, cnt, kw, data.dtype, data.device)
+        return torch.from_numpy(out).to(device=data.device, dtype=data.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        import oracle_lib as O
+        d, t, rois_np, cnt, kw, dt, dev = ctx.saved
+        dd, td = O.deform_psroi_bwd(g.detach().cpu().numpy().astype(np.float32), cnt, d, rois_np, t, no_trans=t is None,
+                                    **kw)
+        gd = torch.from_numpy(dd).to(device=dev, dtype=dt)
+        gt = None if t is None else torch.from_numpy(td).to(device=dev, dtype=dt)
+        return gd, gt, None, None
+
+
+PSROI_KW = dict(spatial_scale=0.0625, output_dim=256, group_size=1, pooled=7, part_size=7, spp=4, trans_std=0.1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def params_to_torch(arg, aux, dtype=torch.float64, device="cpu"):
+    """numpy (arg_params, aux_params) of a reference checkpoint -> torch; trainable tensors get requires_grad."""
+    P = {}
+    for k, v in arg.items():
+        t = torch.from_numpy(np.ascontiguousarray(v)).to(device=device, dtype=dtype)
+        P[k] = t.requires_grad_(not is_fixed(k))
+    A = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device=device, dtype=dtype) for k, v in aux.items()}
+    return P, A
+
+
+def _bn(P, A, x, name, eps, train, relu=True, fix_gamma=False):
+    g, b = P[name + "_gamma"], P[name + "_beta"]
+    if train:
+        y = F.batch_norm(x, None, None, g, b, True, 0.0, eps)
+    else:
+        if fix_gamma:
+            g = torch.ones_like(g)
+        y = F.batch_norm(x, A[name + "_moving_mean"], A[name + "_moving_var"], g.detach(), b.detach(), False, 0.0, eps)
+    return F.relu(y) if relu else y
+
+
+def _unit(P, A, x, name, stride, dim_match, train, deform, eps, taps=None):
+    """residual_unit :36-69 / residual_unit_deform :106-145.  The shortcut convolution reads act1, not data."""
+    a1 = _bn(P, A, x, name + "_bn1", eps, train)
+    c1 = F.conv2d(a1, P[name + "_conv1_weight"])
+    a2 = _bn(P, A, c1, name + "_bn2", eps, train)
+    if deform:
+        off = F.conv2d(a2, P[name + "_offset_weight"], P[name + "_offset_bias"], padding=2, dilation=2)
+        c2 = deform_conv2d(a2, off, P[name + "_conv2_weight"])
+    else:
+        c2 = F.conv2d(a2, P[name + "_conv2_weight"], stride=stride, padding=1)
+    a3 = _bn(P, A, c2, name + "_bn3", eps, train)
+    c3 = F.conv2d(a3, P[name + "_conv3_weight"])
+    sc = x if dim_match else F.conv2d(a1, P[name + "_sc_weight"], stride=stride)
+    if taps is not None:
+        taps[name] = dict(a1=a1, c1=c1, c2=c2)
+    return c3 + sc
+
+
+def backbone(P, A, data, eps=2e-5, taps=None):
+    """resnetc4 + resnetc5(deform=True) + Concat (:243-249).  Returns relu1 = cat(conv_feat, relut) [B,3072,H/16,W/16]."""
+    x = _bn(P, A, data, "bn_data", eps, False, relu=False, fix_gamma=True)
+    x = F.conv2d(x, P["conv0_weight"], stride=2, padding=3)
+    x = _bn(P, A, x, "bn0", eps, False)
+    x = F.max_pool2d(x, 3, 2, 1)
+    c4 = None
+    for si, n in enumerate(UNITS):
+        stage = si + 1
+        for j in range(n):
+            name = "stage%d_unit%d" % (stage, j + 1)
+            stride = 2 if (j == 0 and stage in (2, 3)) else 1
+            x = _unit(P, A, x, name, stride, j > 0, train=stage > 1, deform=stage == 4, eps=eps, taps=taps)
+        if stage == 3:
+            c4 = x
+    return torch.cat([c4, x], 1)
+
+
+def forward_train(P, A, batch, proposals, batch_images, rpn_batch_size=256, num_anchors=21, num_classes=81,
+                  grad_scale=1.0, eps=2e-5, taps=None):
+    """The training graph.  batch: tensors named as MNIteratorE2E provides them (data NCHW, label [B,A*H*W],
+    bbox_target / bbox_weight [B,4A,H,W], gt_boxes, valid_ranges, im_info).  proposals(rpn_cls_prob [B,2A,H,W],
+    rpn_bbox_pred [B,4A,H,W]) -> dict(rois [N,5], label [N], bbox_target [N,4], bbox_weight [N,4]) as numpy arrays.
+    Returns (objective, out) where d(objective)/d(param) is what the reference's backward leaves in the gradient
+    arrays, and out holds the graph outputs + the un-normalised loss sums the product path reports."""
+    data = batch["data"]
+    B = data.shape[0]
+    An = num_anchors
+    relu1 = backbone(P, A, data, eps, taps)
+    rpn = F.relu(F.conv2d(relu1, P["rpn_conv_3x3_weight"], P["rpn_conv_3x3_bias"], padding=1))
+    rpn_cls_score = F.conv2d(rpn, P["rpn_cls_score_weight"], P["rpn_cls_score_bias"])
+    rpn_bbox_pred = F.conv2d(rpn, P["rpn_bbox_pred_weight"], P["rpn_bbox_pred_bias"])
+    feat = F.relu(F.conv2d(relu1, P["conv_new_1_weight"], P["conv_new_1_bias"]))
+    H, W = rpn_cls_score.shape[2], rpn_cls_score.shape[3]
+    score2 = rpn_cls_score.reshape(B, 2, An * H, W)                       # rpn_cls_score_reshape (0, 2, -1, 0)
+    rpn_label = batch["label"].reshape(B, An * H, W).long()
+    logp = F.log_softmax(score2, 1)
+    rpn_prob = logp.exp()
+    valid = rpn_label != -1
+    nll = -(logp.gather(1, rpn_label.clamp(min=0).unsqueeze(1)).squeeze(1))[valid]
+    rpn_cls_sum = nll.sum()
+    rpn_cls_obj = grad_scale * rpn_cls_sum / max(int(valid.sum()), 1)
+    d = rpn_bbox_pred - batch["bbox_target"]
+    sl1 = torch.where(d.abs() < 1, 0.5 * d * d, d.abs() - 0.5)
+    rpn_bbox_sum = (batch["bbox_weight"] * sl1).sum()
+    rpn_bbox_obj = (3.0 * grad_scale / float(batch_images * rpn_batch_size)) * rpn_bbox_sum
+
+    prop = proposals(rpn_prob.reshape(B, 2 * An, H, W).detach(), rpn_bbox_pred.detach())
+    rois = np.ascontiguousarray(prop["rois"], dtype=np.float32)
+    N = rois.shape[0]
+    dev, dt = data.device, data.dtype
+    label = torch.from_numpy(np.asarray(prop["label"]).reshape(-1)).to(dev).long()
+    bbox_target = torch.from_numpy(np.asarray(prop["bbox_target"])).to(device=dev, dtype=dt)
+    bbox_weight = torch.from_numpy(np.asarray(prop["bbox_weight"])).to(device=dev, dtype=dt)
+
+    offset_t = DeformPSROI.apply(feat, None, rois, PSROI_KW)             # [N,256,7,7]
+    offset = F.linear(offset_t.reshape(N, -1), P["offset_weight"], P["offset_bias"])
+    trans = offset.reshape(N, 2, 7, 7)
+    pooled = DeformPSROI.apply(feat, trans, rois, PSROI_KW)
+    fc1 = F.relu(F.linear(pooled.reshape(N, -1), P["fc_new_1_weight"], P["fc_new_1_bias"]))
+    fc2 = F.relu(F.linear(fc1, P["fc_new_2_weight"], P["fc_new_2_bias"]))
+    cls_score = F.linear(fc2, P["cls_score_weight"], P["cls_score_bias"])
+    bbox_pred = F.linear(fc2, P["bbox_pred_weight"], P["bbox_pred_bias"])
+    lp = F.log_softmax(cls_score, 1)
+    cvalid = label != -1
+    cls_sum = -(lp.gather(1, label.clamp(min=0).unsqueeze(1)).squeeze(1))[cvalid].sum()
+    cls_obj = grad_scale * cls_sum / max(int(cvalid.sum()), 1)
+    d2 = bbox_pred - bbox_target
+    sl2 = torch.where(d2.abs() < 1, 0.5 * d2 * d2, d2.abs() - 0.5)
+    bbox_sum = (bbox_weight * sl2).sum()
+    bbox_obj = (grad_scale / (188.0 * 16.0)) * bbox_sum
+    objective = rpn_cls_obj + rpn_bbox_obj + cls_obj + bbox_obj
+    out = dict(rpn_cls_prob=rpn_prob.reshape(B, 2 * An, H, W), rpn_bbox_pred=rpn_bbox_pred, feat=feat, relu1=relu1,
+               cls_prob=lp.exp(), bbox_pred=bbox_pred, trans=trans, pooled=pooled, offset_t=offset_t,
+               loss_sums=torch.stack([rpn_cls_sum, rpn_bbox_sum, cls_sum, bbox_sum]).detach(), rois=rois, label=label)
+    return objective, out

@@ -43,6 +43,7 @@ SIGNATURES = {
     "sniper_bn_param_grad_batched": ("i", "pip"),
     "sniper_colsum": ("i", "pllipp"),
     "sniper_sgd_mom": ("i", "ppplffffp"),
+    "sniper_sgd_mom_dev": ("i", "ppplpffffpp"),
     "sniper_count_valid": ("i", "plipp"),
     "sniper_rpn_softmax_loss": ("i", "pipiiiifppipipp"),
     "sniper_rpn_smooth_l1_loss": ("i", "pippiiiifpipp"),

@@ -7,6 +7,7 @@
 // smooth_l1 + MakeLoss (mshadow_op.h:642-678), SGD momentum (optimizer_op-inl.h:279-300).
 // All kernels: 128-bit vectorised loads/stores along C, grids sized in multiples of 148 SMs.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <math.h>
 
 namespace {
@@ -510,6 +511,46 @@ __global__ void __launch_bounds__(kTPB) sgd_mom_kernel(float* __restrict__ w, fl
   }
 }
 
+// Same update with the learning rate and weight decay read from DEVICE memory (hyper[0] = lr, hyper[1] = wd), so a
+// CUDA graph that captured the launch follows a learning-rate schedule (WarmupMultiBatchScheduler,
+// lib/train_utils/lr_scheduler.py:43-66) by a 8-byte H2D copy before each replay.  lr_mult / wd_mult are the
+// per-group multipliers MXNet derives from the symbol attributes (optimizer.py _get_lr/_get_wd).  w16 (optional):
+// bf16 copy of the updated weights = the multi_precision path (MP_SGDMomKernel, optimizer_op-inl.h:377-404: fp32
+// master weights + momentum, low-precision weights rewritten every step).
+__global__ void __launch_bounds__(kTPB) sgd_mom_dev_kernel(float* __restrict__ w, float* __restrict__ mom,
+                                                            const float* __restrict__ g, long n,
+                                                            const float* __restrict__ hyper, float lr_mult,
+                                                            float wd_mult, float momentum, float rescale,
+                                                            __nv_bfloat16* __restrict__ w16) {
+  const float lr = hyper[0] * lr_mult, wd = hyper[1] * wd_mult;
+  const long n4 = n >> 2;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 ww = ld4(w + 4 * i), mm = ld4(mom + 4 * i);
+    const float4 gg = ld4(g + 4 * i);
+    mm.x = momentum * mm.x - lr * wd * ww.x - lr * rescale * gg.x;
+    mm.y = momentum * mm.y - lr * wd * ww.y - lr * rescale * gg.y;
+    mm.z = momentum * mm.z - lr * wd * ww.z - lr * rescale * gg.z;
+    mm.w = momentum * mm.w - lr * wd * ww.w - lr * rescale * gg.w;
+    ww.x += mm.x; ww.y += mm.y; ww.z += mm.z; ww.w += mm.w;
+    st4(w + 4 * i, ww);
+    st4(mom + 4 * i, mm);
+    if (w16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(ww.x, ww.y), hi = __floats2bfloat162_rn(ww.z, ww.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(w16 + 4 * i) = pk;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long i = (n4 << 2) + threadIdx.x;
+    const float m = momentum * mom[i] - lr * wd * w[i] - lr * rescale * g[i];
+    mom[i] = m;
+    w[i] += m;
+    if (w16) w16[i] = __float2bfloat16(w[i]);
+  }
+}
+
 int ew_grid(long work) {
   long g = (work + kTPB - 1) / kTPB;
   const long cap = (long)sn::kNumSMs * 8;
@@ -677,6 +718,18 @@ int sniper_sgd_mom(float* w, float* mom, const float* g, long n, float lr, float
                    void* stream) {
   SN_CHECK((((uintptr_t)w | (uintptr_t)mom | (uintptr_t)g) & 15) == 0, "sgd_mom: buffers must be 16-byte aligned");
   sgd_mom_kernel<<<ew_grid(n / 4 + 1), kTPB, 0, (cudaStream_t)stream>>>(w, mom, g, n, lr, wd, momentum, rescale);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// hyper: device float[2] = {lr, wd}.  w_bf16: optional bf16 copy of the updated weights (8-byte aligned).
+int sniper_sgd_mom_dev(float* w, float* mom, const float* g, long n, const float* hyper, float lr_mult, float wd_mult,
+                       float momentum, float rescale, void* w_bf16, void* stream) {
+  SN_CHECK((((uintptr_t)w | (uintptr_t)mom | (uintptr_t)g) & 15) == 0, "sgd_mom_dev: buffers must be 16-byte aligned");
+  SN_CHECK(hyper != nullptr, "sgd_mom_dev: hyper (device {lr, wd}) is required");
+  SN_CHECK(((uintptr_t)w_bf16 & 7) == 0, "sgd_mom_dev: w_bf16 must be 8-byte aligned");
+  sgd_mom_dev_kernel<<<ew_grid(n / 4 + 1), kTPB, 0, (cudaStream_t)stream>>>(
+      w, mom, g, n, hyper, lr_mult, wd_mult, momentum, rescale, static_cast<__nv_bfloat16*>(w_bf16));
   SN_LAUNCH_CHECK();
   return 0;
 }

@@ -34,15 +34,21 @@ class Cfg:
     batch_images = 16                 # TRAIN.BATCH_IMAGES (per GPU)
     bn_eps = 2e-5
     bn_momentum = 0.995               # main_train.py:27
-    lr = 0.015
+    lr = 0.015                        # TRAIN.lr .. warmup_step: sniper_res101_e2e.yml:104-111
+    lr_step = "5.33"
+    lr_factor = 0.1
+    warmup = True
+    warmup_lr = 0.0005
+    warmup_step = 1000
     wd = 1e-4
     momentum = 0.9
     units = (3, 4, 23, 3)
     filter_list = (64, 256, 512, 1024, 2048)
     grad_scale = 1.0                  # TRAIN.scale only applies to fp16
     wgrad_splits = 0                  # 0 = choose per layer (fill one wave of 148 persistent CTAs)
-    # BN statistics accumulated by the producing conv's epilogue (warp-shuffle column sums + double REDs).
-    # Measured on B200: +6.5 ms of tcgen05 time per step vs 1.8 ms saved in colsum kernels -> off by default.
+    # BN statistics accumulated by the producing conv's TMA-store epilogue (column sums of the staged chunk + double
+    # REDs) instead of a separate colsum pass.  Measured on B200: 39.1 -> 37.8 ms/step, so ON by default
+    # (SNIPER_FUSE_BN=0 restores the separate pass for A/B runs).
     fuse_bn_stats = os.environ.get("SNIPER_FUSE_BN", "1") == "1"
     # run weight gradients on a second stream (see WgradScheduler); SNIPER_WGRAD_STREAM=0/1 overrides for A/B runs
     wgrad_stream = os.environ.get("SNIPER_WGRAD_STREAM", "1") == "1"
@@ -111,6 +117,9 @@ class ParamStore:
         self.w = torch.zeros(off, device=device)
         self.g = torch.zeros(off, device=device)
         self.mom = torch.zeros(off, device=device)
+        # [lr, wd] on the device: read by sgd_mom_dev_kernel, so a captured update graph follows the LR schedule
+        self.hyper = torch.zeros(2, device=device)
+        self._hyper_host = (None, None)
         for name, (o, shape) in layout.items():
             n = int(np.prod(shape))
             self.views[name] = self.w[o:o + n].view(shape)
@@ -123,10 +132,16 @@ class ParamStore:
     def grad(self, name):
         return self.grads[name]
 
-    def sgd_step(self, lr, wd, momentum, rescale=1.0):
-        """optimizer_op-inl.h:279-300 on every segment."""
+    def set_hyper(self, lr, wd):
+        """Stream-ordered 8-byte H2D of (lr, wd); call OUTSIDE graph capture (the captured update only reads it)."""
+        if (lr, wd) != self._hyper_host:
+            self.hyper.copy_(torch.tensor([lr, wd], dtype=torch.float32))
+            self._hyper_host = (lr, wd)
+
+    def sgd_step(self, momentum, rescale=1.0):
+        """optimizer_op-inl.h:279-300 on every (lr_mult, wd_mult) segment, lr / wd taken from self.hyper."""
         for s, e, (lr_mult, wd_mult) in self.segments:
-            ops.sgd_mom(self.w[s:e], self.mom[s:e], self.g[s:e], lr * lr_mult, wd * wd_mult, momentum, rescale)
+            ops.sgd_mom_dev(self.w[s:e], self.mom[s:e], self.g[s:e], self.hyper, lr_mult, wd_mult, momentum, rescale)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -265,13 +280,16 @@ class BN:
             P.add(name + "_beta", (C,))
         self.st = None
 
-    def build(self, device):
+    def build(self, device, pool=None):
+        """pool: an ops.BNPool shared by all layers of a model (one allocation, one H2D); gamma of a trainable layer is
+        then initialised by the caller in the flat parameter buffer."""
         if self.frozen:
-            self.st = ops.BNState(self.C, device)
+            self.st = ops.BNState(self.C, device, pool=pool)
         else:
             self.st = ops.BNState(self.C, device, self.P[self.name + "_gamma"], self.P[self.name + "_beta"],
-                                  self.P.grad(self.name + "_gamma"), self.P.grad(self.name + "_beta"))
-            self.st.gamma.fill_(1.0)
+                                  self.P.grad(self.name + "_gamma"), self.P.grad(self.name + "_beta"), pool=pool)
+            if pool is None:
+                self.st.gamma.fill_(1.0)
 
     def fwd(self, x, cfg, relu=True, have_stats=False):
         """have_stats: the producer of x already accumulated sum / sum-of-squares into self.st.sums."""
@@ -460,31 +478,54 @@ class SniperResNet101:
 
     # ---------------------------------------------------------------- init (init_weight_rcnn :450-485)
     def _init_weights(self, seed, deform_offset_std):
+        """Random initialisation generated on the HOST (CPU generator) into one flat image of the parameter buffer and
+        moved with a single H2D copy; all BatchNorm state comes from one pooled allocation.  (Per-tensor device fills
+        cost ~800 tiny launches at start-up and pushed the real kernels out of the driver's launch window.)"""
         dev = self.device
-        g = torch.Generator(device=dev)
+        g = torch.Generator()
         g.manual_seed(seed)
         cfg = self.cfg
-        self.conv0_w = torch.zeros(64, 7, 7, 3, device=dev).normal_(0, math.sqrt(2.0 / 147), generator=g)
-        for bn in (self.bn_data, self.bn0):
-            bn.build(dev)
-        # bn_data: frozen, fix_gamma; realistic pixel statistics so that conv0 sees O(1) inputs
-        self.bn_data.st.moving_mean.fill_(0.0)
-        self.bn_data.st.moving_var.fill_(60.0 ** 2)
-        ops.bn_frozen(self.bn_data.st, cfg.bn_eps, fix_gamma=True)
-        ops.bn_frozen(self.bn0.st, cfg.bn_eps)
+        P = self.P
+        host = torch.zeros(P.total)
+
+        def fill(c, std=None):
+            if std is None:
+                std = math.sqrt(2.0 / c.K)      # He-normal backbone (SURVEY 8d config 2)
+            w = torch.zeros(c.coutp, c.K)
+            if std > 0:
+                w[:c.cout].normal_(0, std, generator=g)
+            if c.trainable:
+                o, _ = P.layout[c.name + "_weight"]
+                host[o:o + w.numel()] = w.view(-1)
+            else:
+                c.frozen_w = w.to(dev)
+                if c.bias:
+                    c.frozen_b = torch.zeros(c.coutp).to(dev)
+
+        self.conv0_w = torch.zeros(64, 7, 7, 3).normal_(0, math.sqrt(2.0 / 147), generator=g).to(dev)
+        all_bns = [self.bn_data, self.bn0] + [b for u in self.units for b in u.bns()]
+        pool = ops.BNPool(sum(b.C for b in all_bns), dev)
+        for bn in all_bns:
+            bn.build(dev, pool)
+            if not bn.frozen:
+                o, _ = P.layout[bn.name + "_gamma"]
+                host[o:o + bn.C] = 1.0
         for u in self.units:
             for c in u.convs():
-                if c.name.endswith("_offset"):
-                    c.init(std=deform_offset_std, device=dev, gen=g)      # zeros in the reference (:451-456)
-                else:
-                    c.init(device=dev, gen=g)
-            for bn in u.bns():
-                bn.build(dev)
-                if bn.frozen:
-                    ops.bn_frozen(bn.st, cfg.bn_eps)
+                # offset convolutions: zeros in the reference (:451-456)
+                fill(c, deform_offset_std if c.name.endswith("_offset") else None)
         for c in (self.rpn_conv, self.rpn_head, self.conv_new_1, self.fc_new_1, self.fc_new_2, self.fc_out):
-            c.init(std=0.01, device=dev, gen=g)
-        self.fc_offset.init(std=deform_offset_std and 0.001, device=dev, gen=g)   # zeros in the reference (:476-477)
+            fill(c, 0.01)
+        fill(self.fc_offset, deform_offset_std and 0.001)                  # zeros in the reference (:476-477)
+        P.w.copy_(host)
+        pool.finalize()
+        self.bn_pool = pool
+        # bn_data: frozen, fix_gamma; realistic pixel statistics so that conv0 sees O(1) inputs
+        self.bn_data.st.moving_var.fill_(60.0 ** 2)
+        ops.bn_frozen(self.bn_data.st, cfg.bn_eps, fix_gamma=True)
+        for bn in all_bns[1:]:
+            if bn.frozen:
+                ops.bn_frozen(bn.st, cfg.bn_eps)
 
     def train_bns(self):
         return [b for u in self.units if not u.frozen for b in u.bns()]
@@ -607,7 +648,8 @@ class SniperResNet101:
         W.join()
         self.step_count += 1
         return dict(rpn_cls_prob=prob, rpn_bbox_loss=self.loss_buf[1:2], cls_prob=cls_prob, bbox_loss=self.loss_buf[3:4],
-                    label=label, rois=rois, losses=self.loss_buf)
+                    label=label, rois=rois, losses=self.loss_buf, rpn_head=head, cat=cat, bbox_target=bbox_target,
+                    bbox_weight=bbox_weight)
 
     def forward_inference(self, data, im_info, suppress_anchor_types=False):
         """get_symbol_rcnn(cfg, is_train=False) (resnet_mx_101_e2e.py:227-345 with the test branch :258-266, 321-326):
@@ -685,27 +727,46 @@ class SniperResNet101:
                 ops.bn_frozen(bn.st, cfg.bn_eps, fix_gamma=bn.fix_gamma)
         self._wt_table = None      # data-gradient operands are rebuilt from the new weights on the next step
 
-    def export_reference(self):
-        """The inverse of load_reference: (arg_params, aux_params) under the reference's names and layouts."""
+    def export_reference(self, grads=False):
+        """The inverse of load_reference: (arg_params, aux_params) under the reference's names and layouts.
+        grads=True: the parameter GRADIENTS of the last forward_backward in the same names / layouts (what
+        `executor.grad_dict` holds in the reference; trainable tensors only, aux empty)."""
         from . import checkpoint as ck
         cfg = self.cfg
         A, K = cfg.num_anchors, cfg.num_classes
         n = lambda x: x.detach().cpu().numpy().copy()
         arg, aux = {}, {}
-        arg["conv0_weight"] = np.ascontiguousarray(n(self.conv0_w).transpose(0, 3, 1, 2))
+        if not grads:
+            arg["conv0_weight"] = np.ascontiguousarray(n(self.conv0_w).transpose(0, 3, 1, 2))
         parts = {"rpn_head": (4 * A, 2 * A), "cls_bbox": (K, 4)}
         for c in self._named_convs():
-            ck.conv_to_reference(c.name, c.cout, c.cin, c.k, n(c.w), n(c.b) if c.bias else None, parts.get(c.name), arg)
+            if grads and not c.trainable:
+                continue
+            w = self.P.grad(c.name + "_weight") if grads else c.w
+            b = (self.P.grad(c.name + "_bias") if grads else c.b) if c.bias else None
+            ck.conv_to_reference(c.name, c.cout, c.cin, c.k, n(w), n(b) if c.bias else None, parts.get(c.name), arg)
         for bn in self._named_bns():
+            if grads:
+                if not bn.frozen:
+                    arg[bn.name + "_gamma"] = n(bn.st.dgamma)
+                    arg[bn.name + "_beta"] = n(bn.st.dbeta)
+                continue
             arg[bn.name + "_gamma"] = n(bn.st.gamma)
             arg[bn.name + "_beta"] = n(bn.st.beta)
             aux[bn.name + "_moving_mean"] = n(bn.st.moving_mean)
             aux[bn.name + "_moving_var"] = n(bn.st.moving_var)
         return arg, aux
 
+    def set_lr(self, lr=None):
+        """Writes (lr, wd) into the device hyper-parameter buffer the update kernels read (outside graph capture)."""
+        self.P.set_hyper(float(self.cfg.lr if lr is None else lr), float(self.cfg.wd))
+
     def update(self, lr=None):
-        cfg = self.cfg
-        self.P.sgd_step(cfg.lr if lr is None else lr, cfg.wd, cfg.momentum)
+        """SGD-momentum on every trainable tensor.  lr=None: keep whatever set_lr() last wrote (the form that is
+        captured into the update graph); a number: set it first (eager use)."""
+        if lr is not None or self.P._hyper_host[0] is None:
+            self.set_lr(lr)
+        self.P.sgd_step(self.cfg.momentum)
 
     def train_step(self, batch, lr=None, allreduce=None):
         out = self.forward_backward(batch)

@@ -301,18 +301,67 @@ def affine_act(x, scale, shift, relu=True, out=None):
     return out
 
 
+class BNPool:
+    """One device allocation for the state of every BatchNorm of a model (filled by ONE H2D copy instead of ~9 fill
+    kernels per layer): per layer 6 float vectors [gamma? beta? moving_mean moving_var mean invstd scale shift] and a
+    double[2C] statistics scratch."""
+
+    def __init__(self, total_channels, device):
+        self.device = device
+        self.f = torch.zeros(8 * total_channels)         # host side until finalize()
+        self.d_len = 2 * total_channels
+        self.fo = 0
+        self.do = 0
+        self.pending = []
+
+    def take(self, C, ones=False):
+        o = self.fo
+        self.fo += (C + 3) // 4 * 4          # keep every vector 16-byte aligned
+        if ones:
+            self.f[o:o + C] = 1.0
+        return o
+
+    def take_sums(self, C):
+        o = self.do
+        self.do += 2 * C
+        return o
+
+    def finalize(self):
+        self.f = self.f[:max(self.fo, 1)].to(self.device)
+        self.d = torch.zeros(max(self.do, 1), dtype=torch.float64, device=self.device)
+        for fn in self.pending:
+            fn()
+        self.pending = []
+
+
 class BNState:
     """Per-BN device state: parameters, moving statistics and the per-step (mean, invstd, scale, shift)."""
 
-    def __init__(self, C, device, gamma=None, beta=None, dgamma=None, dbeta=None):
-        z = lambda: torch.zeros(C, device=device)
+    def __init__(self, C, device, gamma=None, beta=None, dgamma=None, dbeta=None, pool=None):
         self.C = C
-        self.gamma = gamma if gamma is not None else torch.ones(C, device=device)
-        self.beta = beta if beta is not None else z()
         self.dgamma, self.dbeta = dgamma, dbeta
-        self.moving_mean, self.moving_var = z(), torch.ones(C, device=device)
-        self.mean, self.invstd, self.scale, self.shift = z(), z(), z(), z()
-        self.sums = torch.zeros(2 * C, dtype=torch.float64, device=device)
+        if pool is None:
+            z = lambda: torch.zeros(C, device=device)
+            self.gamma = gamma if gamma is not None else torch.ones(C, device=device)
+            self.beta = beta if beta is not None else z()
+            self.moving_mean, self.moving_var = z(), torch.ones(C, device=device)
+            self.mean, self.invstd, self.scale, self.shift = z(), z(), z(), z()
+            self.sums = torch.zeros(2 * C, dtype=torch.float64, device=device)
+            return
+        og = pool.take(C, ones=True) if gamma is None else None
+        ob = pool.take(C) if beta is None else None
+        om, ov = pool.take(C), pool.take(C, ones=True)
+        rest = [pool.take(C) for _ in range(4)]
+        osum = pool.take_sums(C)
+
+        def bind():
+            v = lambda o: pool.f[o:o + C]
+            self.gamma = gamma if gamma is not None else v(og)
+            self.beta = beta if beta is not None else v(ob)
+            self.moving_mean, self.moving_var = v(om), v(ov)
+            self.mean, self.invstd, self.scale, self.shift = [v(o) for o in rest]
+            self.sums = pool.d[osum:osum + 2 * C]
+        pool.pending.append(bind)
 
 
 def bn_stats(x, bn, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=True):
@@ -430,6 +479,13 @@ def colsum_accum(x, out):
 def sgd_mom(w, mom, g, lr, wd, momentum, rescale=1.0):
     check(lib().sniper_sgd_mom(_ptr(w), _ptr(mom), _ptr(g), w.numel(), float(lr), float(wd), float(momentum),
                                float(rescale), _stream()))
+
+
+def sgd_mom_dev(w, mom, g, hyper, lr_mult, wd_mult, momentum, rescale=1.0, w_bf16=None):
+    """SGD-momentum with lr / wd read from the device buffer `hyper` = [lr, wd] (graph-replay safe schedule);
+    w_bf16: optional bf16 shadow of the updated weights (multi_precision, optimizer_op-inl.h:377-404)."""
+    check(lib().sniper_sgd_mom_dev(_ptr(w), _ptr(mom), _ptr(g), w.numel(), _ptr(hyper), float(lr_mult), float(wd_mult),
+                                   float(momentum), float(rescale), _ptr(w_bf16), _stream()))
 
 
 def count_valid(label, out, ignore=-1):

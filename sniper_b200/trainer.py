@@ -10,11 +10,14 @@ metrics read with asnumpy(), lib/train_utils/metric.py:109-125).
 """
 import torch
 
-from . import model, ops
+from . import lr_scheduler, model, ops
 
 
 class Trainer:
-    def __init__(self, cfg=None, device="cuda:0", world_size=1, use_graph=True, seed=5, deform_offset_std=0.0):
+    def __init__(self, cfg=None, device="cuda:0", world_size=1, use_graph=True, seed=5, deform_offset_std=0.0,
+                 scheduler="config"):
+        """scheduler: "config" = the reference's WarmupMultiBatchScheduler built from cfg (lr, lr_step, warmup*), None =
+        constant cfg.lr, or any callable num_update -> lr."""
         self.cfg = cfg or model.Cfg()
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
@@ -34,6 +37,26 @@ class Trainer:
         self.stage_free = [None, None]       # event: the step that consumed stage[i] has copied it out
         self.stage_owner = [None, None]      # the host batch object sitting in stage[i] (kept alive: identity match)
         self.next_stage = 0
+        # optimizer state of mxnet.optimizer.SGD that lives on the host: update count and LR schedule
+        self.num_update = 0
+        if scheduler == "config":
+            c = self.cfg
+            scheduler = lr_scheduler.from_config(lr=c.lr, lr_step=getattr(c, "lr_step", "5.33"),
+                                                 lr_factor=getattr(c, "lr_factor", 0.1), warmup=getattr(c, "warmup", True),
+                                                 warmup_lr=getattr(c, "warmup_lr", 0.0005),
+                                                 warmup_step=getattr(c, "warmup_step", 1000),
+                                                 roidb_len=getattr(c, "roidb_len", None),
+                                                 batch_size=getattr(c, "batch_images", 16) * world_size)
+        self.scheduler = scheduler
+        self.lr = self.cfg.lr
+
+    def next_lr(self, lr=None):
+        """mxnet.optimizer: `_update_count` then `_get_lr` -> scheduler(num_update) with the incremented count."""
+        self.num_update += 1
+        if lr is None:
+            lr = self.scheduler(self.num_update) if self.scheduler is not None else self.cfg.lr
+        self.lr = float(lr)
+        return self.lr
 
     # ---- device-resident step (inputs already in HBM)
     def _alloc_static(self, batch):
@@ -83,11 +106,29 @@ class Trainer:
         if self.world_size > 1:
             torch.distributed.all_reduce(self.net.P.g, op=torch.distributed.ReduceOp.SUM)
 
+    def _snapshot(self):
+        P = self.net.P
+        bns = self.net.train_bns()
+        return (P.w.clone(), P.mom.clone(), [(b.st.moving_mean.clone(), b.st.moving_var.clone()) for b in bns])
+
+    def _restore(self, snap):
+        P = self.net.P
+        P.w.copy_(snap[0])
+        P.mom.copy_(snap[1])
+        for b, (m, v) in zip(self.net.train_bns(), snap[2]):
+            b.st.moving_mean.copy_(m)
+            b.st.moving_var.copy_(v)
+
     def capture(self):
-        """Warm up eagerly, then capture forward+backward and the optimizer update as two CUDA graphs."""
+        """Warm up eagerly, then capture forward+backward and the optimizer update as two CUDA graphs.  The warm-up runs
+        complete training steps on whatever sits in the static buffers; weights, momentum and the BN moving statistics
+        are snapshotted before and restored afterwards, so capture() leaves the model exactly as it found it (a freshly
+        loaded checkpoint is not disturbed and the first step() applies ONE update, like the reference's)."""
+        snap = self._snapshot()
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
+            self.net.set_lr(0.0)
             for _ in range(2):
                 ops.reset_launch_count()
                 self.out = self.net.forward_backward(self.static)
@@ -96,6 +137,7 @@ class Trainer:
                 self.launches_per_step = ops.launch_count()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
+        self._restore(snap)
         if not self.use_graph:
             return
         self.g_fb = torch.cuda.CUDAGraph()
@@ -106,8 +148,10 @@ class Trainer:
             self.net.update()
         torch.cuda.synchronize()
 
-    def step_device(self):
-        """One training step on the batch currently in the static buffers."""
+    def step_device(self, lr=None):
+        """One training step on the batch currently in the static buffers.  The learning rate comes from the schedule
+        (or `lr`) and reaches the captured update graph through the device hyper-parameter buffer."""
+        self.net.set_lr(self.next_lr(lr))
         if self.g_fb is not None:
             self.g_fb.replay()
             self._allreduce()
@@ -119,16 +163,17 @@ class Trainer:
         return self.out
 
     # ---- public end-to-end step: host batch in, host losses out
-    def step(self, host_batch, prefetch=None):
+    def step(self, host_batch, prefetch=None, lr=None):
         """One training step on `host_batch` (pinned host tensors) -> host loss scalars.  `prefetch`: the batch of the
-        NEXT call; its H2D copy is issued now on the copy stream and overlaps this step's compute."""
+        NEXT call; its H2D copy is issued now on the copy stream and overlaps this step's compute.  `lr` overrides the
+        schedule for this update."""
         self._load_or_take(host_batch)
         if prefetch is not None:
             self.prefetch(prefetch)
         if self.g_fb is None and self.use_graph:
             self.capture()
-        out = self.step_device()
+        out = self.step_device(lr)
         self.loss_host.copy_(out["losses"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return {"rpn_cls_loss": float(self.loss_host[0]), "rpn_bbox_loss": float(self.loss_host[1]),
-                "rcnn_cls_loss": float(self.loss_host[2]), "rcnn_bbox_loss": float(self.loss_host[3])}
+                "rcnn_cls_loss": float(self.loss_host[2]), "rcnn_bbox_loss": float(self.loss_host[3]), "lr": self.lr}

@@ -1,0 +1,26 @@
+"""NCCL-side correctness of the data-parallel step: needs >= 2 GPUs on the box (skipped otherwise; run with
+`gpurun --gpus 2 -- python -m pytest tests/test_nccl_gpu.py -m gpu`)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_two_rank_gradient_allreduce_and_replicated_update(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "nccl.json")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "nccl_worker.py"), out]
+    subprocess.run(cmd, check=True, timeout=900)
+    res = json.load(open(out))
+    print(res)
+    assert res["allreduce_equals_sum_of_locals"] is True
+    assert res["weights_identical"] is True
+    assert res["vs_sequential_rel"] < 1e-4

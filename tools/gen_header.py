@@ -35,6 +35,7 @@ DOC = {
     "sniper_bn_param_grad_batched": "dgamma/dbeta of every BatchNorm in one launch (second half of sniper_bn_relu_bwd when it is called with dgamma = dbeta = NULL).",
     "sniper_colsum": "out[c] += sum_m x[m,c] (bias gradients; cudnnConvolutionBackwardBias).",
     "sniper_sgd_mom": "SGDMomKernel (optimizer_op-inl.h:279-300) on one flat buffer.",
+    "sniper_sgd_mom_dev": "SGDMomKernel / MP_SGDMomKernel (optimizer_op-inl.h:279-300, 377-404) with lr and wd read from device memory, so that a captured CUDA graph follows WarmupMultiBatchScheduler (lib/train_utils/lr_scheduler.py:43-66); optional bf16 weight shadow = multi_precision.",
     "sniper_count_valid": "Device-side replacement of SoftmaxOutput's host valid count (softmax_output-inl.h:184-195).",
     "sniper_rpn_softmax_loss": "SoftmaxOutput(multi_output, use_ignore, normalization=valid) for the RPN (softmax_output-inl.h:108-132, 162-206): prob + gradient in one pass.",
     "sniper_rpn_smooth_l1_loss": "weight * smooth_l1(pred - target) + MakeLoss gradient for the RPN (mshadow_op.h:642-678; resnet_mx_101_e2e.py:330-334).",
