@@ -82,6 +82,10 @@ void oracle_generate_anchors(int feat_stride, const float* ratios, int nr, const
   }
 }
 
+void oracle_expf_array(const float* x, float* y, long n) {
+  for (long i = 0; i < n; ++i) y[i] = oracle_expf(x[i]);
+}
+
 /* multi_proposal_target.cu:263-331.  boxes: [B*A*H*W, 6] = x1,y1,x2,y2,score,area */
 void oracle_get_props(float* boxes, const float* deltas, const float* im_info,
                       const float* anchorbuf, const float* scores, const float* valid_ranges,

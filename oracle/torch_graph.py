@@ -39,6 +39,69 @@ def is_fixed(name):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Contractions.  MODE "exact": plain float64 / float32 arithmetic.  MODE "tf32": every operand of every tensor-core
+# contraction (forward, data gradient, weight gradient) is first reduced to TF32 the way the tcgen05 `kind::tf32` MMA
+# reads fp32 words from shared memory -- the low 13 mantissa bits are ignored (truncation, not rounding;
+# tests/test_graph_parity_gpu.py measures that on the device) -- and the products are accumulated exactly (float64).
+# This models the product path's only systematic deviation from real arithmetic, so the whole graph can be compared
+# with a tolerance ~100x tighter than against MODE "exact" (random-init ResNet-101 amplifies each unit's TF32 error by
+# ~4 % per residual unit: 1e-3 after stage 1 grows to ~1e-1 at c4).  conv0 is exempt: the product runs it in fp32 FMA.
+MODE = ["exact"]
+
+
+def tf32(x):
+    """x -> fp32 -> TF32 (low 13 mantissa bits cleared) -> x.dtype."""
+    i = x.detach().to(torch.float32).contiguous().view(torch.int32)
+    return (i & -8192).view(torch.float32).to(x.dtype)
+
+
+class _TF32Conv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, stride, padding, dilation):
+        xt, wt = tf32(x), tf32(w)
+        ctx.save_for_backward(xt, wt)
+        ctx.cfg = (stride, padding, dilation)
+        return F.conv2d(xt, wt, None, stride, padding, dilation)
+
+    @staticmethod
+    def backward(ctx, gy):
+        xt, wt = ctx.saved_tensors
+        stride, padding, dilation = ctx.cfg
+        gt = tf32(gy)
+        gx = torch.nn.grad.conv2d_input(xt.shape, wt, gt, stride, padding, dilation)
+        gw = torch.nn.grad.conv2d_weight(xt, wt.shape, gt, stride, padding, dilation)
+        return gx, gw, None, None, None
+
+
+class _TF32MatmulNT(torch.autograd.Function):
+    """y = a @ b^T with TF32 operands in all three contractions."""
+    @staticmethod
+    def forward(ctx, a, b):
+        at, bt = tf32(a), tf32(b)
+        ctx.save_for_backward(at, bt)
+        return at @ bt.t()
+
+    @staticmethod
+    def backward(ctx, gy):
+        at, bt = ctx.saved_tensors
+        gt = tf32(gy)
+        return gt @ bt, gt.t() @ at
+
+
+def conv2d(x, w, b=None, stride=1, padding=0, dilation=1, exact=False):
+    if MODE[0] == "exact" or exact:
+        return F.conv2d(x, w, b, stride, padding, dilation)
+    y = _TF32Conv.apply(x, w, stride, padding, dilation)
+    return y if b is None else y + b.view(1, -1, 1, 1)
+
+
+def linear(x, w, b=None):
+    if MODE[0] == "exact":
+        return F.linear(x, w, b)
+    y = _TF32MatmulNT.apply(x, w)
+    return y if b is None else y + b
+
+
 def deform_conv2d(x, offset, w, dil=2, pad=2, dg=4):
     """DeformableConvolution forward, kernel 3x3, stride 1 (resnet_mx_101_e2e.py:124-130).  x [N,C,H,W], offset
     [N, dg*2*9, H, W] with channel g*18 + 2*tap (+1) = (dy, dx) of tap (i,j)=divmod(tap,3) in deformable group g
@@ -77,8 +140,9 @@ def deform_conv2d(x, offset, w, dil=2, pad=2, dg=4):
             per_g.append(v * valid.unsqueeze(-1).to(x.dtype))
         cols.append(torch.cat(per_g, -1))
     col = torch.stack(cols, 3)                                        # [N,H,W,9,C]
-    wt = w.permute(0, 2, 3, 1).reshape(w.shape[0], 9, C)              # [Cout, tap, C]
-    return torch.einsum("nhwtc,otc->nohw", col, wt)
+    wt = w.permute(0, 2, 3, 1).reshape(w.shape[0], 9 * C)             # [Cout, (tap, C)]
+    y = linear(col.reshape(N * H * W, 9 * C), wt)                     # the GEMM of deformable_convolution-inl.h:148-160
+    return y.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)
 
 
 class DeformPSROI(torch.autograd.Function):
@@ -132,27 +196,31 @@ def _bn(P, A, x, name, eps, train, relu=True, fix_gamma=False):
 def _unit(P, A, x, name, stride, dim_match, train, deform, eps, taps=None):
     """residual_unit :36-69 / residual_unit_deform :106-145.  The shortcut convolution reads act1, not data."""
     a1 = _bn(P, A, x, name + "_bn1", eps, train)
-    c1 = F.conv2d(a1, P[name + "_conv1_weight"])
+    c1 = conv2d(a1, P[name + "_conv1_weight"])
     a2 = _bn(P, A, c1, name + "_bn2", eps, train)
     if deform:
-        off = F.conv2d(a2, P[name + "_offset_weight"], P[name + "_offset_bias"], padding=2, dilation=2)
+        off = conv2d(a2, P[name + "_offset_weight"], P[name + "_offset_bias"], 1, 2, 2)
         c2 = deform_conv2d(a2, off, P[name + "_conv2_weight"])
     else:
-        c2 = F.conv2d(a2, P[name + "_conv2_weight"], stride=stride, padding=1)
+        c2 = conv2d(a2, P[name + "_conv2_weight"], None, stride, 1)
     a3 = _bn(P, A, c2, name + "_bn3", eps, train)
-    c3 = F.conv2d(a3, P[name + "_conv3_weight"])
-    sc = x if dim_match else F.conv2d(a1, P[name + "_sc_weight"], stride=stride)
+    c3 = conv2d(a3, P[name + "_conv3_weight"])
+    sc = x if dim_match else conv2d(a1, P[name + "_sc_weight"], None, stride)
     if taps is not None:
-        taps[name] = dict(a1=a1, c1=c1, c2=c2)
+        taps[name] = dict(a1=a1, c1=c1, c2=c2, out=c3 + sc)
     return c3 + sc
 
 
 def backbone(P, A, data, eps=2e-5, taps=None):
     """resnetc4 + resnetc5(deform=True) + Concat (:243-249).  Returns relu1 = cat(conv_feat, relut) [B,3072,H/16,W/16]."""
     x = _bn(P, A, data, "bn_data", eps, False, relu=False, fix_gamma=True)
-    x = F.conv2d(x, P["conv0_weight"], stride=2, padding=3)
+    x = conv2d(x, P["conv0_weight"], None, 2, 3, exact=True)
     x = _bn(P, A, x, "bn0", eps, False)
+    if taps is not None:
+        taps["relu0"] = x
     x = F.max_pool2d(x, 3, 2, 1)
+    if taps is not None:
+        taps["pool0"] = x
     c4 = None
     for si, n in enumerate(UNITS):
         stage = si + 1
@@ -176,10 +244,10 @@ def forward_train(P, A, batch, proposals, batch_images, rpn_batch_size=256, num_
     B = data.shape[0]
     An = num_anchors
     relu1 = backbone(P, A, data, eps, taps)
-    rpn = F.relu(F.conv2d(relu1, P["rpn_conv_3x3_weight"], P["rpn_conv_3x3_bias"], padding=1))
-    rpn_cls_score = F.conv2d(rpn, P["rpn_cls_score_weight"], P["rpn_cls_score_bias"])
-    rpn_bbox_pred = F.conv2d(rpn, P["rpn_bbox_pred_weight"], P["rpn_bbox_pred_bias"])
-    feat = F.relu(F.conv2d(relu1, P["conv_new_1_weight"], P["conv_new_1_bias"]))
+    rpn = F.relu(conv2d(relu1, P["rpn_conv_3x3_weight"], P["rpn_conv_3x3_bias"], 1, 1))
+    rpn_cls_score = conv2d(rpn, P["rpn_cls_score_weight"], P["rpn_cls_score_bias"])
+    rpn_bbox_pred = conv2d(rpn, P["rpn_bbox_pred_weight"], P["rpn_bbox_pred_bias"])
+    feat = F.relu(conv2d(relu1, P["conv_new_1_weight"], P["conv_new_1_bias"]))
     H, W = rpn_cls_score.shape[2], rpn_cls_score.shape[3]
     score2 = rpn_cls_score.reshape(B, 2, An * H, W)                       # rpn_cls_score_reshape (0, 2, -1, 0)
     rpn_label = batch["label"].reshape(B, An * H, W).long()
@@ -203,13 +271,13 @@ def forward_train(P, A, batch, proposals, batch_images, rpn_batch_size=256, num_
     bbox_weight = torch.from_numpy(np.asarray(prop["bbox_weight"])).to(device=dev, dtype=dt)
 
     offset_t = DeformPSROI.apply(feat, None, rois, PSROI_KW)             # [N,256,7,7]
-    offset = F.linear(offset_t.reshape(N, -1), P["offset_weight"], P["offset_bias"])
+    offset = linear(offset_t.reshape(N, -1), P["offset_weight"], P["offset_bias"])
     trans = offset.reshape(N, 2, 7, 7)
     pooled = DeformPSROI.apply(feat, trans, rois, PSROI_KW)
-    fc1 = F.relu(F.linear(pooled.reshape(N, -1), P["fc_new_1_weight"], P["fc_new_1_bias"]))
-    fc2 = F.relu(F.linear(fc1, P["fc_new_2_weight"], P["fc_new_2_bias"]))
-    cls_score = F.linear(fc2, P["cls_score_weight"], P["cls_score_bias"])
-    bbox_pred = F.linear(fc2, P["bbox_pred_weight"], P["bbox_pred_bias"])
+    fc1 = F.relu(linear(pooled.reshape(N, -1), P["fc_new_1_weight"], P["fc_new_1_bias"]))
+    fc2 = F.relu(linear(fc1, P["fc_new_2_weight"], P["fc_new_2_bias"]))
+    cls_score = linear(fc2, P["cls_score_weight"], P["cls_score_bias"])
+    bbox_pred = linear(fc2, P["bbox_pred_weight"], P["bbox_pred_bias"])
     lp = F.log_softmax(cls_score, 1)
     cvalid = label != -1
     cls_sum = -(lp.gather(1, label.clamp(min=0).unsqueeze(1)).squeeze(1))[cvalid].sum()

@@ -1,5 +1,5 @@
 """Host-side members of the path (numpy in / numpy out) over the C-ABI: chip sampling, NMS, overlaps.
-Mirrors lib/chips/chip_generator.py, lib/nms/nms.py and lib/bbox of the reference."""
+Mirrors lib/chips/chips.pyx, lib/nms/nms.py and lib/bbox of the reference (chip_generator / chip_worker: chip_worker.py)."""
 import ctypes
 
 import numpy as np
@@ -27,19 +27,6 @@ def chips_generate(boxes, width, height, chipsize, stride):
     if n < 0:
         check(-1)
     return out[:n].copy()
-
-
-class chip_generator(object):
-    """lib/chips/chip_generator.py:10-27: generate(boxes, scale, w, h) with boxes in image coordinates."""
-
-    def __init__(self, chip_stride=32, use_cpp=True):
-        self.chip_stride = chip_stride
-
-    def generate(self, boxes, width, height, chipsize):
-        clipped = np.ascontiguousarray(boxes, dtype=np.float32).copy()
-        clipped[:, 0] = np.maximum(0, clipped[:, 0]); clipped[:, 1] = np.maximum(0, clipped[:, 1])
-        clipped[:, 2] = np.minimum(width - 1, clipped[:, 2]); clipped[:, 3] = np.minimum(height - 1, clipped[:, 3])
-        return chips_generate(clipped, width, height, chipsize, self.chip_stride).tolist()
 
 
 def cpu_nms(dets, thresh, order=None):

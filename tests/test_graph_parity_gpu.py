@@ -9,10 +9,15 @@ Discrete outputs (graded bit-exact): rois and labels of the product path == the 
 (oracle/mpt.c) run on the product path's own RPN outputs.  The float64 graph is then fed those rois, so both sides
 pool the same regions.
 
-Tolerances (TF32 tensor-core products have a 10-bit mantissa, ~5e-4 relative per product; the backbone chains ~100
-contractions and 99 train-mode BatchNorm+ReLU whose masks flip on near-zero pre-activations):
-  activations  rel. Frobenius <= 1e-2;  loss sums rel <= 2e-3 (|.| <= 1e-3 abs for the tiny R-CNN box loss);
-  every parameter gradient rel. Frobenius <= 6e-2, median over the ~330 tensors <= 1.5e-2.
+Two float64 references (oracle/torch_graph.MODE):
+  "tf32"  -- the operands of every tensor-core contraction (forward, data and weight gradients) are reduced to TF32 by
+             dropping the low 13 mantissa bits, exactly what `tcgen05.mma kind::tf32` does with fp32 words
+             (test_tcgen05_tf32_reads_truncate measures it), products accumulated exactly.  This is the sharp test: the
+             product path must agree to accumulation-order noise.  Tolerances: activations 2e-3 rel. Frobenius, loss sums
+             1e-3 rel, EVERY parameter gradient 2e-2 rel. Frobenius (median 3e-3).
+  "exact" -- real arithmetic.  Documents the cost of TF32 itself: a random-init ResNet-101 amplifies each residual
+             unit's ~1.5e-3 TF32 error by a few percent per unit (measured: 4e-3 after stage 1, 9e-2 at c4, 3e-1 at c5),
+             so only loose bounds make sense here: losses 5e-2 rel, RPN probabilities 5e-2.
 """
 import os
 import sys
@@ -54,7 +59,35 @@ def _build(B, seed, bf16=False):
     return cfg, net, batch
 
 
-def _reference(net, cfg, batch, prob_nchw, bbox_nchw):
+def _tf32_trunc(x):
+    import torch
+    return (x.float().contiguous().view(torch.int32) & -8192).view(torch.float32).double()
+
+
+def _tf32_rne(x):
+    import torch
+    i = x.float().contiguous().view(torch.int32)
+    i = i + 0x0FFF + ((i >> 13) & 1)
+    return (i & -8192).view(torch.float32).double()
+
+
+def test_tcgen05_tf32_reads_truncate():
+    """kind::tf32 ignores the low 13 mantissa bits of the fp32 words it reads (no rounding): the product GEMM equals
+    the exact product of TRUNCATED operands to accumulation noise, and is ~100x further from round-to-nearest operands."""
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(0)
+    a = torch.randn(512, 1024, device="cuda")
+    b = torch.randn(256, 1024, device="cuda")
+    y = ops.gemm_nt(a, b).double()
+    yt = _tf32_trunc(a) @ _tf32_trunc(b).t()
+    yr = _tf32_rne(a) @ _tf32_rne(b).t()
+    et, er = _rel(y, yt), _rel(y, yr)
+    print("vs truncated operands %.2e, vs RNE operands %.2e" % (et, er))
+    assert et < 5e-6 and er > 20 * et
+
+
+def _reference(net, cfg, batch, prob_nchw, bbox_nchw, mode):
     """float64 graph on the exported parameters; proposals = the C oracle on the product path's RPN outputs."""
     import torch
     import oracle_lib as O
@@ -64,10 +97,13 @@ def _reference(net, cfg, batch, prob_nchw, bbox_nchw):
                                   batch["gt_boxes"].cpu().numpy(), batch["valid_ranges"].cpu().numpy())
     P, A = TG.params_to_torch(arg, aux, torch.float64, "cuda")
     b64 = {k: v.double() for k, v in batch.items()}
-    taps = {}
-    obj, ref = TG.forward_train(P, A, b64, lambda *_: res, batch_images=cfg.batch_images, taps=taps)
-    obj.backward()
-    return P, ref, res, taps
+    TG.MODE[0] = mode
+    try:
+        obj, ref = TG.forward_train(P, A, b64, lambda *_: res, batch_images=cfg.batch_images)
+        obj.backward()
+    finally:
+        TG.MODE[0] = "exact"
+    return P, ref, res
 
 
 def test_training_graph_matches_float64_reference():
@@ -78,40 +114,53 @@ def test_training_graph_matches_float64_reference():
     A = cfg.num_anchors
     prob = out["rpn_cls_prob"].permute(0, 3, 1, 2).contiguous()                    # NHWC [..,2A] -> [B,2A,H,W]
     bbox = out["rpn_head"][..., :4 * A].permute(0, 3, 1, 2).contiguous()
-    P, ref, res, _ = _reference(net, cfg, batch, prob, bbox)
+    garg, _ = net.export_reference(grads=True)
+    ls = out["losses"][:4].double().cpu()
 
+    # ================= sharp: float64 with TF32-truncated contraction operands
+    P, ref, res = _reference(net, cfg, batch, prob, bbox, "tf32")
     # ---- discrete outputs: bit-exact against the oracle on the same RPN outputs
     assert out["rois"].cpu().numpy().tobytes() == res["rois"].tobytes()
     assert np.array_equal(out["label"].cpu().numpy(), res["label"].reshape(-1))
     assert int((res["label"] > 0).sum()) > 0, "test batch yields no foreground roi"
-
-    # ---- activations
-    assert _rel(out["cat"].permute(0, 3, 1, 2), ref["relu1"]) < 1e-2
-    assert _rel(prob, ref["rpn_cls_prob"]) < 1e-2
-    assert _rel(bbox, ref["rpn_bbox_pred"]) < 1e-2
-    assert _rel(out["cls_prob"], ref["cls_prob"]) < 1e-2
-    # ---- losses (un-normalised sums, as the product path reports them)
-    ls, lr = out["losses"][:4].double().cpu(), ref["loss_sums"].cpu()
-    print("losses ours", ls.tolist(), "ref", lr.tolist())
-    for i in range(4):
-        assert abs(ls[i] - lr[i]) <= 2e-3 * abs(lr[i]) + 1e-3, (i, ls[i].item(), lr[i].item())
-
-    # ---- every parameter gradient, in the reference's names and layouts
-    garg, _ = net.export_reference(grads=True)
+    acts = dict(cat=_rel(out["cat"].permute(0, 3, 1, 2), ref["relu1"]), rpn_prob=_rel(prob, ref["rpn_cls_prob"]),
+                rpn_bbox=_rel(bbox, ref["rpn_bbox_pred"]), cls_prob=_rel(out["cls_prob"], ref["cls_prob"]))
+    print("activation errors (tf32 reference):", {k: "%.2e" % v for k, v in acts.items()})
+    lr = ref["loss_sums"].cpu()
+    print("losses ours", ls.tolist(), "tf32-ref", lr.tolist())
     rows = []
     for name, p in P.items():
         if not p.requires_grad:
-            assert name not in garg or "stage1" in name or "bn0" in name or "conv0" in name
+            assert name not in garg
             continue
         assert p.grad is not None, name
         ours = torch.from_numpy(garg[name]).cuda()
         assert ours.shape == p.grad.shape, (name, ours.shape, p.grad.shape)
-        rows.append((_rel(ours, p.grad), name, p.grad.norm().item()))
+        rows.append((_rel(ours, p.grad), name, p.grad.norm().item(), ours.double().norm().item()))
+    if os.environ.get("SNIPER_GRAD_TABLE"):
+        with open(os.environ["SNIPER_GRAD_TABLE"], "w") as f:
+            for r in rows:
+                f.write("%-40s rel %.3e  |ref| %.3e  |ours| %.3e\n" % (r[1], r[0], r[2], r[3]))
     rows.sort(reverse=True)
-    print("worst gradient errors:", [(round(r, 4), n) for r, n, _ in rows[:8]])
+    print("worst gradient errors:", [(round(r[0], 5), r[1]) for r in rows[:8]])
     med = rows[len(rows) // 2][0]
-    print("median gradient error %.4f over %d tensors" % (med, len(rows)))
-    assert len(rows) > 300
-    for r, name, nrm in rows:
-        assert r < 6e-2 or nrm < 1e-9, (name, r, nrm)
-    assert med < 1.5e-2
+    print("median gradient error %.2e over %d tensors" % (med, len(rows)))
+    assert len(rows) == 297
+    for k, v in acts.items():
+        assert v < 2e-3, (k, v)
+    for i in range(4):
+        assert abs(ls[i] - lr[i]) <= 1e-3 * abs(lr[i]) + 1e-4, (i, ls[i].item(), lr[i].item())
+    for r, name, nrm, _ in rows:
+        assert r < 2e-2 or nrm < 1e-9, (name, r, nrm)
+    assert med < 3e-3
+
+    # ================= loose: real arithmetic (what TF32 costs on this network)
+    P2, ref2, _ = _reference(net, cfg, batch, prob, bbox, "exact")
+    l2 = ref2["loss_sums"].cpu()
+    e_prob = _rel(prob, ref2["rpn_cls_prob"])
+    g2 = sorted(_rel(torch.from_numpy(garg[n]).cuda(), p.grad) for n, p in P2.items() if p.requires_grad)
+    print("exact reference: losses", l2.tolist(), "rpn_prob err %.2e, c4|c5 err %.2e, gradient err median %.2e max %.2e"
+          % (e_prob, _rel(out["cat"].permute(0, 3, 1, 2), ref2["relu1"]), g2[len(g2) // 2], g2[-1]))
+    assert e_prob < 5e-2
+    for i in range(4):
+        assert abs(ls[i] - l2[i]) <= 5e-2 * abs(l2[i]) + 1e-2, (i, ls[i].item(), l2[i].item())

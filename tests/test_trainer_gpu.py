@@ -74,22 +74,33 @@ def test_capture_leaves_model_untouched_and_first_step_is_one_update():
 
 
 def test_graph_and_eager_steps_agree_under_a_changing_lr():
+    """One update from the same state at three learning rates, CUDA-graph replay vs eager launches.  (Longer runs
+    cannot be compared: the proposals are a discrete function of near-tied RPN scores, so float-atomic noise of 1e-3
+    in the first gradient selects different rois in the second step.)"""
     import torch
     from sniper_b200 import model, synth_batch, trainer
     batch = synth_batch.make_batch(1, seed=4, device="cpu", pinned=True)
-    ws = []
+    deltas = []
     for use_graph in (True, False):
         cfg = model.Cfg()
         cfg.batch_images = 1
         tr = trainer.Trainer(cfg, use_graph=use_graph, seed=5, deform_offset_std=0.01)
+        snap = tr._snapshot()
         w0 = tr.net.P.w.clone()
+        ds = []
         for lr in (0.001, 0.004, 0.0005):
+            tr._restore(snap)
             tr.step(batch, lr=lr)
-        torch.cuda.synchronize()
-        ws.append((tr.net.P.w - w0).double())
-    d = (ws[0] - ws[1]).norm().item() / ws[1].norm().item()
-    print("graph vs eager weight-delta difference %.3e" % d)
-    assert d < 2e-3        # float-atomic ordering noise of the backward kernels only
+            torch.cuda.synchronize()
+            ds.append((tr.net.P.w - w0).double())
+        deltas.append(ds)
+        # momentum starts from zero each time: the update is linear in lr
+        assert abs(ds[1].norm().item() / ds[0].norm().item() - 4.0) < 0.05
+        assert abs(ds[2].norm().item() / ds[0].norm().item() - 0.5) < 0.01
+    for a, b in zip(*deltas):
+        d = (a - b).norm().item() / b.norm().item()
+        print("graph vs eager weight-delta difference %.3e" % d)
+        assert d < 1e-2        # float-atomic ordering noise of the backward kernels only (measured 1.5e-3)
 
 
 def test_reference_warmup_run_stays_finite_and_learns():
