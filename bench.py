@@ -127,10 +127,12 @@ def entry_point_breakdown(trainer, path):
         f.write("\nsum of entry points %.2f ms; eager single-stream step (incl. launch gaps) %.2f ms\n" % (tot, t0.elapsed_time(t1)))
 
 
-def tc_kernel_time(trainer):
-    """CUDA-event time and algorithmic FLOPs of every tcgen05 launch of one (eager) training step."""
+def tc_kernel_time(trainer, peak_bf16):
+    """CUDA-event time and algorithmic FLOPs of every tcgen05 launch of one (eager, single-stream) training step.
+    Returns (ms, flops, launches, ideal_ms): ideal_ms = sum over launches of flops / peak of the launch's operand type
+    (bf16: the measured cuBLAS bf16 figure; fp32 operands = kind::tf32, half that issue rate)."""
     import torch
-    from sniper_b200 import _lib, ops
+    from sniper_b200 import _lib
     L = _lib.lib()
     names = ["sniper_gemm_nt", "sniper_conv2d_nhwc", "sniper_conv2d_wgrad_nhwc"]
     events, flops, descs = [], [0.0], []
@@ -139,17 +141,17 @@ def tc_kernel_time(trainer):
     def wrap(name, raw):
         def fn(*a):
             if name == "sniper_gemm_nt":
-                M, N, K = a[6], a[7], a[8]
+                M, N, K, dt = a[6], a[7], a[8], a[9]
                 fl = 2.0 * M * N * K
-                descs.append(["gemm", M, N, K, fl])
+                descs.append(["gemm", M, N, K, fl, dt])
             elif name == "sniper_conv2d_nhwc":
-                NB, Cin, Cout, ntaps, Ho, Wo = a[2], a[5], a[7], a[8], a[12], a[13]
+                NB, Cin, Cout, ntaps, Ho, Wo, dt = a[2], a[5], a[7], a[8], a[12], a[13], a[21]
                 fl = 2.0 * NB * Ho * Wo * Cout * ntaps * Cin
-                descs.append(["conv", NB * Ho * Wo, Cout, ntaps * Cin, fl])
+                descs.append(["conv", NB * Ho * Wo, Cout, ntaps * Cin, fl, dt])
             else:
-                NB, Cin, Cout, ntaps, Ho, Wo = a[4], a[7], a[8], a[9], a[13], a[14]
+                NB, Cin, Cout, ntaps, Ho, Wo, dt = a[4], a[7], a[8], a[9], a[13], a[14], a[16]
                 fl = 2.0 * NB * Ho * Wo * Cout * ntaps * Cin
-                descs.append(["wgrad", Cout, ntaps * Cin, NB * Ho * Wo, fl])
+                descs.append(["wgrad", Cout, ntaps * Cin, NB * Ho * Wo, fl, dt])
             flops[0] += fl
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -172,41 +174,31 @@ def tc_kernel_time(trainer):
             L._cache[n] = orig[n]
     times = [a.elapsed_time(b) for a, b in events]
     ms = sum(times)
+    ideal_ms = sum(d[4] / ((peak_bf16 if d[5] == 1 else peak_bf16 / 2.0) * 1e12) * 1e3 for d in descs)
     dump = os.environ.get("SNIPER_DUMP_GEMM")
     if dump:
+        if getattr(trainer.net.cfg, "bf16", False):
+            dump = dump.replace(".md", "") + "_bf16.md"
         agg = {}
         for d, t in zip(descs, times):
-            k = (d[0], d[1], d[2], d[3])
+            k = (d[0], d[1], d[2], d[3], "bf16" if d[5] == 1 else "tf32")
             e = agg.setdefault(k, [0, 0.0, 0.0])
             e[0] += 1; e[1] += t; e[2] += d[4]
         rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
         with open(dump, "w") as f:
-            f.write("| kind | M | N | K | launches | total ms | TFLOP/s |\n|---|---:|---:|---:|---:|---:|---:|\n")
-            for (kind, M, N, K), (n, t, fl) in rows:
-                f.write("| %s | %d | %d | %d | %d | %.3f | %.1f |\n" % (kind, M, N, K, n, t, fl / (t / 1e3) / 1e12))
+            f.write("| kind | M | N | K | operands | launches | total ms | TFLOP/s |\n|---|---:|---:|---:|---|---:|---:|---:|\n")
+            for (kind, M, N, K, dt), (n, t, fl) in rows:
+                f.write("| %s | %d | %d | %d | %s | %d | %.3f | %.1f |\n" % (kind, M, N, K, dt, n, t, fl / (t / 1e3) / 1e12))
             f.write("\ntotal %.3f ms, %.1f GFLOP\n" % (ms, flops[0] / 1e9))
-    return ms, flops[0], len(events)
+    return ms, flops[0], len(events), ideal_ms
 
 
-def run_ours(args):
+def measure(args, cfg, rank, local_rank, world, pool, dev_pool, sampler=None):
+    """Device-resident and end-to-end timing of one configuration; returns a dict (identical on every rank)."""
     import torch
     import torch.distributed as dist
-    from sniper_b200 import model, ops, synth_batch
     from sniper_b200.trainer import Trainer
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.gpus > 1 and world == 1:
-        raise SystemExit("--gpus %d needs torch.distributed.run (WORLD_SIZE unset)" % args.gpus)
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    cfg = model.Cfg()
-    cfg.batch_images = args.chips
     trainer = Trainer(cfg, device="cuda:%d" % local_rank, world_size=world, use_graph=not args.no_graph)
-    pool = [synth_batch.make_batch(args.chips, seed=100 + 17 * rank + i, device="cpu", pinned=True) for i in range(args.pool)]
-    dev_pool = [{k: v.to("cuda:%d" % local_rank) for k, v in b.items()} for b in pool]
-    h2d = sum(v.numel() * v.element_size() for v in pool[0].values())
     trainer.load(pool[0])
     trainer.capture()
 
@@ -223,8 +215,7 @@ def run_ours(args):
 
     for i in range(max(args.warmup, 3)):
         dev_step(i)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if sampler is not None and rank == 0:
         sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -249,50 +240,115 @@ def run_ours(args):
     t1.record()
     barrier()
     ms_e2e = t0.elapsed_time(t1)
-    if rank == 0:
+    if sampler is not None and rank == 0:
         sampler.stop_flag = True
     t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    result = None
+    out = {"ms": ms, "ms_e2e": ms_e2e, "losses": losses, "launches_per_step": trainer.launches_per_step}
     if rank == 0:
         peaks, peak_src = load_peaks()
-        chips = args.chips * world * args.steps
-        value = chips / (ms / 1e3)
-        e2e = chips / (ms_e2e / 1e3)
+        peak_bf16 = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         if os.environ.get("SNIPER_BREAKDOWN"):
-            entry_point_breakdown(trainer, os.environ["SNIPER_BREAKDOWN"])
-        tc_ms, tc_flops, tc_n = tc_kernel_time(trainer)
-        # kind::tf32 issues at half the bf16 rate (1.1 vs 2.25 PFLOP/s nominal): TF32 peak = measured bf16 / 2
-        peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) / 2.0
-        achieved = tc_flops / (tc_ms / 1e3) / 1e12
+            path = os.environ["SNIPER_BREAKDOWN"]
+            entry_point_breakdown(trainer, path.replace(".md", "") + "_bf16.md" if cfg.bf16 else path)
+        tc_ms, tc_flops, tc_n, ideal_ms = tc_kernel_time(trainer, peak_bf16)
+        out.update(tc_ms=tc_ms, tc_flops=tc_flops, tc_n=tc_n, ideal_ms=ideal_ms, peak_bf16=peak_bf16, peak_src=peak_src)
+    del trainer
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sniper_b200 import model, synth_batch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("--gpus %d needs torch.distributed.run (WORLD_SIZE unset)" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pool = [synth_batch.make_batch(args.chips, seed=100 + 17 * rank + i, device="cpu", pinned=True) for i in range(args.pool)]
+    dev_pool = [{k: v.to("cuda:%d" % local_rank) for k, v in b.items()} for b in pool]
+    h2d = sum(v.numel() * v.element_size() for v in pool[0].values())
+    sampler = ClockSampler(local_rank)
+    # ---- the metric's configuration: BASELINE.json configs[1] (fp32 storage, TF32 tensor-core math)
+    cfg = model.Cfg()
+    cfg.batch_images = args.chips
+    cfg.bf16 = bool(args.bf16)
+    m = measure(args, cfg, rank, local_rank, world, pool, dev_pool, sampler)
+    # ---- configs[2]'s precision (bf16 backbone + fp32 master weights) on the same N GPUs, reported as an extra block
+    m3 = None
+    if not args.bf16 and not args.skip_config3:
+        cfg3 = model.Cfg()
+        cfg3.batch_images = args.chips
+        cfg3.bf16 = True
+        m3 = measure(args, cfg3, rank, local_rank, world, pool, dev_pool)
+    result = None
+    if rank == 0:
+        chips = args.chips * world * args.steps
+
+        def block(mm, bf16):
+            value = chips / (mm["ms"] / 1e3)
+            peak_tf = mm["peak_bf16"] / 2.0
+            achieved = mm["tc_flops"] / (mm["tc_ms"] / 1e3) / 1e12
+            # mixed launches (bf16 backbone + TF32 heads): peak = the FLOP-weighted peak of the launch mix, i.e.
+            # frac = (time the launches would take at their operand type's peak) / (time they took)
+            frac = mm["ideal_ms"] / mm["tc_ms"]
+            eff_peak = achieved / frac
+            step_ideal = mm["ideal_ms"] * (TRAIN_GFLOP_PER_CHIP * args.chips * 1e9 / mm["tc_flops"])
+            return value, {
+                "bound": "tensor",
+                "kernel": "gemm_tc_kernel (all tcgen05 GEMM/conv/wgrad launches of a step; %s)" % (
+                    "bf16 backbone launches + TF32 head launches" if bf16 else "kind::tf32"),
+                "achieved": round(achieved, 1), "peak": round(eff_peak if bf16 else peak_tf, 1), "unit": "TFLOP/s",
+                "frac": round(frac, 4), "traffic": None if bf16 else ncu_traffic(),
+                "launches_per_step": mm["tc_n"], "kernel_ms_per_step": round(mm["tc_ms"], 3),
+                "algorithmic_gflop_per_step": round(mm["tc_flops"] / 1e9, 1),
+                "peak_source": "%s bf16_tflops_sustained (%.0f) for bf16 operands, half of it for fp32 operands "
+                               "(kind::tf32 issues at half the bf16 rate)" % (mm["peak_src"], mm["peak_bf16"]),
+                "step_frac": round(step_ideal / (mm["ms"] / args.steps), 4)}
+
+        value, roof = block(m, bool(args.bf16))
+        e2e = chips / (m["ms_e2e"] / 1e3)
         cpu = None
         if not args.skip_cpu:
             cpu = cpu_baseline(sample_chips=args.cpu_chips, steps=3, warmup=1)
+        prec = ("bf16 backbone activations/weights + fp32 master weights, fp32 (TF32 math) heads" if args.bf16
+                else "fp32 I/O + TF32 tcgen05 math")
         result = {
             "metric": "512x512 chips/sec train (ResNet-101)", "value": round(value, 2), "unit": "chips/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage)",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(m["ms"] / args.steps, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 (fp32 master, fp32 heads)" if args.bf16 else "tf32 (fp32 storage)",
             "data": "synthetic",
-            "config": {"workload": "ResNet-101 SNIPER Faster-R-CNN/R-FCN, 512x512 chips, batch 20/GPU, fp32 I/O + TF32 "
-                                   "tcgen05 math, fwd+bwd+allreduce+SGD (BASELINE.json configs[1])",
+            "config": {"workload": "ResNet-101 SNIPER Faster-R-CNN/R-FCN, 512x512 chips, batch %d/GPU, %s, "
+                                   "fwd+bwd+allreduce+SGD with the reference warm-up LR schedule (BASELINE.json configs[%d])"
+                                   % (args.chips, prec, 2 if args.bf16 else 1),
                        "global_batch": args.chips * world, "parallelism": "dp%d" % world,
                        "l2_hygiene": "inputs rotate through %d distinct batches (%.0f MB each); activations >10 GB/step >> 126 MB L2" % (len(pool), h2d / 1e6),
                        "cuda_graph": not args.no_graph},
             "e2e": {"value": round(e2e, 2), "unit": "chips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 32,
-                    "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": int(trainer.launches_per_step * args.steps),
-            "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<tf32> (all tcgen05 GEMM/conv/wgrad launches of a step)",
-                         "achieved": round(achieved, 1), "peak": round(peak_tf, 1), "unit": "TFLOP/s",
-                         "frac": round(achieved / peak_tf, 4), "traffic": ncu_traffic(),
-                         "launches_per_step": tc_n, "kernel_ms_per_step": round(tc_ms, 3),
-                         "algorithmic_gflop_per_step": round(tc_flops / 1e9, 1),
-                         "peak_source": "%s bf16_tflops_sustained / 2 (TF32 = half the bf16 issue rate)" % peak_src,
-                         "step_frac": round(value / world * TRAIN_GFLOP_PER_CHIP / 1e3 / peak_tf, 4)},
-            "losses": losses,
+                    "ms_per_step": round(m["ms_e2e"] / args.steps, 3)},
+            "gpu_launches": int(m["launches_per_step"] * args.steps),
+            "roofline": roof,
+            "losses": m["losses"],
             "clocks": sampler.summary(),
         }
+        if m3 is not None:
+            v3, roof3 = block(m3, True)
+            result["config3"] = {
+                "workload": "same graph, bf16 backbone activations/weights + fp32 master weights + fp32 (TF32) heads "
+                            "(BASELINE.json configs[2] precision) on %d GPU(s), batch %d/GPU" % (world, args.chips),
+                "value": round(v3, 2), "unit": "chips/s", "ms_per_step": round(m3["ms"] / args.steps, 3),
+                "e2e": {"value": round(chips / (m3["ms_e2e"] / 1e3), 2), "unit": "chips/s",
+                        "ms_per_step": round(m3["ms_e2e"] / args.steps, 3)},
+                "speedup_vs_tf32": round(v3 / value, 3), "roofline": roof3, "losses": m3["losses"]}
         if cpu is not None:
             result["cpu_baseline"] = cpu
         print(json.dumps(result), flush=True)
@@ -342,6 +398,8 @@ def main():
     ap.add_argument("--cpu-chips", type=int, default=1, help="chips in the bounded CPU-baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--bf16", action="store_true", help="run the main measurement in mixed precision (configs[2])")
+    ap.add_argument("--skip-config3", action="store_true", help="do not append the bf16 block to the JSON line")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -189,9 +189,11 @@ int ref_deform_col2im_coord(const float* data_col, const float* data_im, const f
                             int height, int width, int kh, int kw, int pad, int stride, int dil, int dgroups,
                             int height_col, int width_col, float* grad_offset) {
   const int n = height_col * width_col * 2 * kh * kw * dgroups;
+  // NB: this kernel's `channel_per_deformable_group` counts COLUMN channels, col_shape[0] / deformable_group
+  // (deformable_im2col.cuh:499), unlike the other two kernels (im_shape[1] / deformable_group)
   refdc::deformable_col2im_coord_gpu_kernel<float><<<num_blocks(n), kBaseThreadNum>>>(
       n, data_col, data_im, data_offset, channels, height, width, kh, kw, pad, pad, stride, stride, dil, dil,
-      channels / dgroups, height_col, width_col, grad_offset, kWriteTo);
+      channels * kh * kw / dgroups, height_col, width_col, grad_offset, kWriteTo);
   return done("deformable_col2im_coord_gpu_kernel");
 }
 

@@ -46,7 +46,45 @@ def is_fixed(name):
 # This models the product path's only systematic deviation from real arithmetic, so the whole graph can be compared
 # with a tolerance ~100x tighter than against MODE "exact" (random-init ResNet-101 amplifies each unit's TF32 error by
 # ~4 % per residual unit: 1e-3 after stage 1 grows to ~1e-1 at c4).  conv0 is exempt: the product runs it in fp32 FMA.
+# MODE "bf16": the mixed-precision path (Cfg.bf16).  Inside the backbone (LOWP) every tensor the product STORES --
+# activations, the im2col buffer, the bf16 weight copies, and on the way back the gradients of those activations -- is
+# rounded to bf16 (round-to-nearest-even), contractions accumulate exactly; the heads behave as in MODE "tf32".
 MODE = ["exact"]
+LOWP = [False]
+
+
+def _bf16(x):
+    return x.detach().to(torch.float32).to(torch.bfloat16).to(x.dtype)
+
+
+class _RoundStored(torch.autograd.Function):
+    """a stored activation: rounded on the way forward, its gradient rounded on the way back"""
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+class _RoundWeight(torch.autograd.Function):
+    """the bf16 copy of an fp32 master weight: rounded forward, gradient passed to the master unchanged"""
+    @staticmethod
+    def forward(ctx, w):
+        return _bf16(w)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def qs(x):
+    return _RoundStored.apply(x) if (MODE[0] == "bf16" and LOWP[0]) else x
+
+
+def qw(w):
+    return _RoundWeight.apply(w) if (MODE[0] == "bf16" and LOWP[0]) else w
 
 
 def tf32(x):
@@ -91,6 +129,8 @@ class _TF32MatmulNT(torch.autograd.Function):
 def conv2d(x, w, b=None, stride=1, padding=0, dilation=1, exact=False):
     if MODE[0] == "exact" or exact:
         return F.conv2d(x, w, b, stride, padding, dilation)
+    if MODE[0] == "bf16" and LOWP[0]:          # operands are stored bf16 tensors already; exact accumulation
+        return F.conv2d(x, qw(w), b, stride, padding, dilation)
     y = _TF32Conv.apply(x, w, stride, padding, dilation)
     return y if b is None else y + b.view(1, -1, 1, 1)
 
@@ -98,6 +138,8 @@ def conv2d(x, w, b=None, stride=1, padding=0, dilation=1, exact=False):
 def linear(x, w, b=None):
     if MODE[0] == "exact":
         return F.linear(x, w, b)
+    if MODE[0] == "bf16" and LOWP[0]:
+        return F.linear(x, qw(w), b)
     y = _TF32MatmulNT.apply(x, w)
     return y if b is None else y + b
 
@@ -139,7 +181,7 @@ def deform_conv2d(x, offset, w, dil=2, pad=2, dg=4):
                 + (lh * (1 - lw)).unsqueeze(-1) * at(h_high, w_low) + (lh * lw).unsqueeze(-1) * at(h_high, w_high)
             per_g.append(v * valid.unsqueeze(-1).to(x.dtype))
         cols.append(torch.cat(per_g, -1))
-    col = torch.stack(cols, 3)                                        # [N,H,W,9,C]
+    col = qs(torch.stack(cols, 3))                                    # [N,H,W,9,C]; a stored (bf16) buffer in MODE "bf16"
     wt = w.permute(0, 2, 3, 1).reshape(w.shape[0], 9 * C)             # [Cout, (tap, C)]
     y = linear(col.reshape(N * H * W, 9 * C), wt)                     # the GEMM of deformable_convolution-inl.h:148-160
     return y.view(N, H, W, w.shape[0]).permute(0, 3, 1, 2)
@@ -195,27 +237,32 @@ def _bn(P, A, x, name, eps, train, relu=True, fix_gamma=False):
 
 def _unit(P, A, x, name, stride, dim_match, train, deform, eps, taps=None):
     """residual_unit :36-69 / residual_unit_deform :106-145.  The shortcut convolution reads act1, not data."""
-    a1 = _bn(P, A, x, name + "_bn1", eps, train)
-    c1 = conv2d(a1, P[name + "_conv1_weight"])
-    a2 = _bn(P, A, c1, name + "_bn2", eps, train)
+    # Stored tensors (MODE "bf16"): a trainable unit stores every conv output (its BatchNorm needs batch statistics of
+    # it); a frozen unit folds BN + ReLU into the producing conv's epilogue, so c1 / c2 never exist in memory there.
+    qc = qs if train else (lambda t: t)
+    a1 = qs(_bn(P, A, x, name + "_bn1", eps, train))
+    c1 = qc(conv2d(a1, P[name + "_conv1_weight"]))
+    a2 = qs(_bn(P, A, c1, name + "_bn2", eps, train))
     if deform:
-        off = conv2d(a2, P[name + "_offset_weight"], P[name + "_offset_bias"], 1, 2, 2)
-        c2 = deform_conv2d(a2, off, P[name + "_conv2_weight"])
+        off = conv2d(a2, P[name + "_offset_weight"], P[name + "_offset_bias"], 1, 2, 2)     # kept fp32 by the product
+        c2 = qc(deform_conv2d(a2, off, P[name + "_conv2_weight"]))
     else:
-        c2 = conv2d(a2, P[name + "_conv2_weight"], None, stride, 1)
-    a3 = _bn(P, A, c2, name + "_bn3", eps, train)
+        c2 = qc(conv2d(a2, P[name + "_conv2_weight"], None, stride, 1))
+    a3 = qs(_bn(P, A, c2, name + "_bn3", eps, train))
     c3 = conv2d(a3, P[name + "_conv3_weight"])
-    sc = x if dim_match else conv2d(a1, P[name + "_sc_weight"], None, stride)
+    sc = x if dim_match else qs(conv2d(a1, P[name + "_sc_weight"], None, stride))
+    out = qs(c3 + sc)                    # the residual is added in the fp32 epilogue, the sum stored once
     if taps is not None:
-        taps[name] = dict(a1=a1, c1=c1, c2=c2, out=c3 + sc)
-    return c3 + sc
+        taps[name] = dict(a1=a1, c1=c1, c2=c2, out=out)
+    return out
 
 
 def backbone(P, A, data, eps=2e-5, taps=None):
     """resnetc4 + resnetc5(deform=True) + Concat (:243-249).  Returns relu1 = cat(conv_feat, relut) [B,3072,H/16,W/16]."""
     x = _bn(P, A, data, "bn_data", eps, False, relu=False, fix_gamma=True)
     x = conv2d(x, P["conv0_weight"], None, 2, 3, exact=True)
-    x = _bn(P, A, x, "bn0", eps, False)
+    LOWP[0] = True                        # the reference's Cast(float16) sits here (:405-406)
+    x = qs(_bn(P, A, x, "bn0", eps, False))
     if taps is not None:
         taps["relu0"] = x
     x = F.max_pool2d(x, 3, 2, 1)
@@ -230,6 +277,7 @@ def backbone(P, A, data, eps=2e-5, taps=None):
             x = _unit(P, A, x, name, stride, j > 0, train=stage > 1, deform=stage == 4, eps=eps, taps=taps)
         if stage == 3:
             c4 = x
+    LOWP[0] = False                       # Cast(relu1, float32) (:250-252): the heads are fp32
     return torch.cat([c4, x], 1)
 
 

@@ -27,17 +27,20 @@ SIGNATURES = {
     "sniper_psroi_bwd": ("i", "pp" "iiii" "f" "iiii" "p" "p"),
     "sniper_gemm_nt": ("i", "plplpl" "iiii" "ppp" "l" "iii" "pp"),
     "sniper_gemm_plan": ("i", "iiiip"),
+    "sniper_gemm_tail_workspace_bytes": ("z", ""),
+    "sniper_gemm_set_tail_workspace": ("i", "pzi"),
     "sniper_conv2d_nhwc": ("i", "pliiii" "pii" "pp" "iii" "pl" "iiiii" "i" "ppp" "l" "iii" "pp"),
     "sniper_conv2d_wgrad_nhwc": ("i", "plpl" "iiiii" "i" "pp" "iii" "p" "ii" "p"),
-    "sniper_affine_act": ("i", "plpppl" "l" "ii" "p"),
-    "sniper_bn_stats": ("i", "pllippffipppppppp"),
+    "sniper_affine_act": ("i", "plpppl" "l" "iii" "p"),
+    "sniper_bn_stats": ("i", "pllippffipppppppip"),
     "sniper_bn_finalize": ("i", "plippffippppppp"),
     "sniper_bn_frozen": ("i", "ippppfippp"),
-    "sniper_bn_relu_bwd": ("i", "plplppppp" "pl" "pl" "pp" "li" "p"),
+    "sniper_bn_relu_bwd": ("i", "plplppppp" "pl" "pl" "pp" "lii" "p"),
     "sniper_affine_relu_bwd": ("i", "plplpp" "pl" "pl" "lii" "p"),
-    "sniper_relu_bwd": ("i", "plplplli" "p"),
-    "sniper_maxpool3x3s2_nhwc": ("i", "ppiiiip"),
-    "sniper_stem_conv": ("i", "pppppppiiip"),
+    "sniper_relu_bwd": ("i", "plplplli" "i" "p"),
+    "sniper_cast_rows": ("i", "plipli" "li" "p"),
+    "sniper_maxpool3x3s2_nhwc": ("i", "ppiiiiip"),
+    "sniper_stem_conv": ("i", "pppppppiiiip"),
     "sniper_weight_transpose": ("i", "ppiiiipp"),
     "sniper_weight_transpose_batched": ("i", "piip"),
     "sniper_bn_param_grad_batched": ("i", "pip"),
@@ -49,8 +52,8 @@ SIGNATURES = {
     "sniper_rpn_smooth_l1_loss": ("i", "pippiiiifpipp"),
     "sniper_softmax_ce": ("i", "pipiiifppipipp"),
     "sniper_smooth_l1_loss": ("i", "pipplifpipp"),
-    "sniper_deform_im2col": ("i", "pp" "iiiiiiiiiii" "pp"),
-    "sniper_deform_col2im": ("i", "ppp" "iiiiiiiiiii" "ppp"),
+    "sniper_deform_im2col": ("i", "pp" "iiiiiiiiiii" "pip"),
+    "sniper_deform_col2im": ("i", "ppp" "iiiiiiiiiii" "ppip"),
     "sniper_anchor_target": ("i", "ppippipp" "iiii" "pipi" "dd" "ppppp" "p"),
     "sniper_chips_generate": ("i", "piiiiipi"),
     "sniper_cpu_nms": ("i", "ppidp"),
@@ -64,7 +67,7 @@ _lib = None
 KERNELS_PER_CALL = {
     "sniper_last_error": 0, "sniper_abi_version": 0, "sniper_multi_proposal_target_workspace_bytes": 0,
     "sniper_generate_anchors": 0, "sniper_chips_generate": 0, "sniper_cpu_nms": 0, "sniper_cpu_soft_nms": 0,
-    "sniper_bbox_overlaps": 0, "sniper_gemm_plan": 0, "sniper_multi_proposal_target_fwd": 2, "sniper_multi_proposal_workspace_bytes": 0, "sniper_multi_proposal_fwd": 4, "sniper_anchor_target": 2, "sniper_bn_stats": 2, "sniper_bn_relu_bwd": 3,
+    "sniper_bbox_overlaps": 0, "sniper_gemm_plan": 0, "sniper_gemm_tail_workspace_bytes": 0, "sniper_gemm_set_tail_workspace": 0, "sniper_multi_proposal_target_fwd": 2, "sniper_multi_proposal_workspace_bytes": 0, "sniper_multi_proposal_fwd": 4, "sniper_anchor_target": 2, "sniper_bn_stats": 2, "sniper_bn_relu_bwd": 3,
 }
 launches = [0]
 

@@ -17,5 +17,5 @@ void set_error(const char* fmt, ...) {
 
 extern "C" {
 const char* sniper_last_error(void) { return sn::last_error_buf(); }
-int sniper_abi_version(void) { return 1; }
+int sniper_abi_version(void) { return 2; }
 }

@@ -11,15 +11,20 @@
 // K order of weights stored as [Cout, kh, kw, Cin].
 // One warp = one (pixel, tap, 128-channel block): 32 lanes x float4.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <math.h>
 
 namespace {
 
+typedef __nv_bfloat16 bf16;
+
+// x and col are fp32 or bf16 (template parameter T of the kernel; the mixed-precision backbone keeps activations and
+// the im2col buffer in bf16); offsets, their gradient and the accumulated dx are always fp32.
 struct DcArgs {
-  const float* x;
+  const void* x;
   const float* offset;
   int NB, H, W, C, Ho, Wo, KH, KW, stride, dil, pad, dgroups, off_ld;
-  float* col;        // fwd out / bwd in (dcol)
+  void* col;         // fwd out / bwd in (dcol)
   float* dx;         // bwd out (atomically accumulated, zero-init by caller)
   float* doffset;    // bwd out [NB,Ho,Wo,off_ld] (written, each element owned by one warp)
 };
@@ -49,8 +54,22 @@ __device__ __forceinline__ Sample make_sample(const DcArgs& p, int h_in, int w_i
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&lo);
+  u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
 
-template <bool BWD>
+template <bool BWD, typename T>
 __global__ void __launch_bounds__(256) deform_im2col_kernel(DcArgs p) {
   const int lane = threadIdx.x & 31;
   const int KK = p.KH * p.KW;
@@ -73,8 +92,8 @@ __global__ void __launch_bounds__(256) deform_im2col_kernel(DcArgs p) {
     const float off_h = __ldg(offp), off_w = __ldg(offp + 1);
     const int h_in = ho * p.stride - p.pad, w_in = wo * p.stride - p.pad;
     const Sample s = make_sample(p, h_in, w_in, i, j, off_h, off_w);
-    float* colp = p.col + m * (long)KK * p.C + (long)tap * p.C + c;
-    const float* xb = p.x + (size_t)n * p.H * p.W * p.C + c;
+    T* colp = static_cast<T*>(p.col) + m * (long)KK * p.C + (long)tap * p.C + c;
+    const T* xb = static_cast<const T*>(p.x) + (size_t)n * p.H * p.W * p.C + c;
     if (!BWD) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (s.valid) {
@@ -89,7 +108,7 @@ __global__ void __launch_bounds__(256) deform_im2col_kernel(DcArgs p) {
         v.z = w1 * v1.z + w2 * v2.z + w3 * v3.z + w4 * v4.z;
         v.w = w1 * v1.w + w2 * v2.w + w3 * v3.w + w4 * v4.w;
       }
-      *reinterpret_cast<float4*>(colp) = v;
+      st4(colp, v);
     } else {
       float gh = 0.f, gw = 0.f;
       if (s.valid) {
@@ -129,7 +148,7 @@ __global__ void __launch_bounds__(256) deform_im2col_kernel(DcArgs p) {
   }
 }
 
-int fill(DcArgs& a, const float* x, const float* offset, int NB, int H, int W, int C, int KH, int KW, int stride,
+int fill(DcArgs& a, const void* x, const float* offset, int NB, int H, int W, int C, int KH, int KW, int stride,
          int dil, int pad, int dgroups, int off_ld) {
   SN_CHECK(C % 128 == 0, "deform conv: C (%d) must be a multiple of 128", C);
   SN_CHECK(dgroups > 0 && C % dgroups == 0 && (C / dgroups) % 128 == 0,
@@ -154,25 +173,31 @@ int dc_grid(const DcArgs& a) {
 
 extern "C" {
 
-int sniper_deform_im2col(const float* x, const float* offset, int NB, int H, int W, int C, int KH, int KW, int stride,
-                         int dil, int pad, int dgroups, int off_ld, float* col, void* stream) {
+// dtype: storage of x and col, 0 = fp32, 1 = bf16 (offset is fp32)
+int sniper_deform_im2col(const void* x, const float* offset, int NB, int H, int W, int C, int KH, int KW, int stride,
+                         int dil, int pad, int dgroups, int off_ld, void* col, int dtype, void* stream) {
   DcArgs a;
+  SN_CHECK(dtype == 0 || dtype == 1, "deform_im2col: dtype must be 0 (fp32) or 1 (bf16)");
   if (fill(a, x, offset, NB, H, W, C, KH, KW, stride, dil, pad, dgroups, off_ld)) return -1;
   a.col = col;
-  deform_im2col_kernel<false><<<dc_grid(a), 256, 0, (cudaStream_t)stream>>>(a);
+  if (dtype == 0) deform_im2col_kernel<false, float><<<dc_grid(a), 256, 0, (cudaStream_t)stream>>>(a);
+  else deform_im2col_kernel<false, bf16><<<dc_grid(a), 256, 0, (cudaStream_t)stream>>>(a);
   SN_LAUNCH_CHECK();
   return 0;
 }
 
 // dx is accumulated into (zero it first); doffset rows are fully overwritten when C/dgroups == 128,
 // accumulated otherwise (zero it first in that case).
-int sniper_deform_col2im(const float* dcol, const float* x, const float* offset, int NB, int H, int W, int C, int KH,
+// dtype: storage of dcol and x (0 = fp32, 1 = bf16); dx and doffset are fp32 (accumulated with float atomics).
+int sniper_deform_col2im(const void* dcol, const void* x, const float* offset, int NB, int H, int W, int C, int KH,
                          int KW, int stride, int dil, int pad, int dgroups, int off_ld, float* dx, float* doffset,
-                         void* stream) {
+                         int dtype, void* stream) {
   DcArgs a;
+  SN_CHECK(dtype == 0 || dtype == 1, "deform_col2im: dtype must be 0 (fp32) or 1 (bf16)");
   if (fill(a, x, offset, NB, H, W, C, KH, KW, stride, dil, pad, dgroups, off_ld)) return -1;
-  a.col = const_cast<float*>(dcol); a.dx = dx; a.doffset = doffset;
-  deform_im2col_kernel<true><<<dc_grid(a), 256, 0, (cudaStream_t)stream>>>(a);
+  a.col = const_cast<void*>(dcol); a.dx = dx; a.doffset = doffset;
+  if (dtype == 0) deform_im2col_kernel<true, float><<<dc_grid(a), 256, 0, (cudaStream_t)stream>>>(a);
+  else deform_im2col_kernel<true, bf16><<<dc_grid(a), 256, 0, (cudaStream_t)stream>>>(a);
   SN_LAUNCH_CHECK();
   return 0;
 }

@@ -15,6 +15,15 @@ namespace {
 constexpr int kTPB = 256;
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+typedef __nv_bfloat16 bf16;
+// 4 consecutive channels as float4, from fp32 (16 bytes) or bf16 (8 bytes) storage: the mixed-precision path keeps
+// activations in bf16 and does all arithmetic in fp32 registers (dtype codes of the C-ABI: 0 = fp32, 1 = bf16)
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 
 // i -> (row, 4*col) for rows of c4 float4 groups; shift path when c4 is a power of two (all BN widths are),
 // 32-bit division otherwise -- never 64-bit division in the inner loop.
@@ -34,6 +43,13 @@ struct RowSplit {
   }
 };
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 u;
+  u.x = *reinterpret_cast<const uint32_t*>(&lo);
+  u.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p) = u;
+}
 
 // ------------------------------------------------------------------ row-blocked [M, C] kernels
 // A block of 256 threads covers LX*4 channels (LX = 32 lanes, 16 when C == 64) x RY = 256/LX row lanes.  Each
@@ -60,9 +76,10 @@ __device__ __forceinline__ bool rb_setup(int lx_shift, int C, int rows_per_block
 }
 
 // y = relu?(x*scale[c] + shift[c])
-__global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict__ x, long ldx,
+template <typename T>
+__global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x, long ldx,
                                                           const float* __restrict__ scale,
-                                                          const float* __restrict__ shift, float* __restrict__ y,
+                                                          const float* __restrict__ shift, T* __restrict__ y,
                                                           long ldy, long M, int C, int relu, int lx_shift,
                                                           int rows_per_block) {
   int c, ry, RY;
@@ -89,9 +106,9 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const float* __restrict
 // ------------------------------------------------------------------ per-channel sums over rows
 // MODE 0: sums[c] += x, sums[C+c] += x*x                              (BN forward statistics)
 // MODE 1: g = dy * (x*scale+shift > 0); sums[c] += g; sums[C+c] += g * (x-mean)*invstd   (BN+ReLU backward)
-template <int MODE>
-__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long ldx,
-                                                      const float* __restrict__ dy, long lddy,
+template <int MODE, typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ldx,
+                                                      const T* __restrict__ dy, long lddy,
                                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                       long M, int C, int lx_shift, int rows_per_block,
@@ -191,15 +208,16 @@ __global__ void bn_frozen_kernel(int C, const float* gamma, const float* beta, c
 }
 
 // dx = scale * (g - s1/M - xhat * s2/M) (+add), g = dy * (x*scale+shift > 0), xhat = (x-mean)*invstd; sums = (s1, s2)
-__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const float* __restrict__ x, long ldx,
-                                                                 const float* __restrict__ dy, long lddy,
+template <typename T>
+__global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const T* __restrict__ x, long ldx,
+                                                                 const T* __restrict__ dy, long lddy,
                                                                  const float* __restrict__ scale,
                                                                  const float* __restrict__ shift,
                                                                  const float* __restrict__ mean,
                                                                  const float* __restrict__ invstd,
                                                                  const double* __restrict__ sums,
-                                                                 const float* __restrict__ add, long ldadd,
-                                                                 float* __restrict__ dx, long lddx, long M, int C,
+                                                                 const T* __restrict__ add, long ldadd,
+                                                                 T* __restrict__ dx, long lddx, long M, int C,
                                                                  int lx_shift, int rows_per_block) {
   int c, ry, RY;
   long r0, r1;
@@ -287,9 +305,10 @@ __global__ void __launch_bounds__(kTPB) affine_relu_bwd_kernel(const float* __re
 }
 
 // relu backward through a stored activation: dx = dy * (y > 0); optional per-column bias gradient
-__global__ void __launch_bounds__(kTPB) relu_bwd_kernel(const float* __restrict__ y, long ldy,
-                                                         const float* __restrict__ dy, long lddy,
-                                                         float* __restrict__ dx, long lddx, long M, int C) {
+template <typename T>
+__global__ void __launch_bounds__(kTPB) relu_bwd_kernel(const T* __restrict__ y, long ldy,
+                                                         const T* __restrict__ dy, long lddy,
+                                                         T* __restrict__ dx, long lddx, long M, int C) {
   const int c4 = C >> 2;
   const long total = M * c4;
   RowSplit rs;
@@ -307,7 +326,8 @@ __global__ void __launch_bounds__(kTPB) relu_bwd_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------ max pool 3x3 stride 2 pad 1, NHWC
-__global__ void __launch_bounds__(kTPB) maxpool3x3s2_kernel(const float* __restrict__ x, float* __restrict__ y, int NB,
+template <typename T>
+__global__ void __launch_bounds__(kTPB) maxpool3x3s2_kernel(const T* __restrict__ x, T* __restrict__ y, int NB,
                                                              int H, int W, int C, int Ho, int Wo) {
   const int c4 = C >> 2;
   const long total = (long)NB * Ho * Wo * c4;
@@ -339,11 +359,12 @@ __global__ void __launch_bounds__(kTPB) maxpool3x3s2_kernel(const float* __restr
 // [NB,H/2,W/2,64].  One block = 8x16 output pixels x 64 channels; weights [64][7][7][3] and the input
 // patch live in shared memory; bn_data is applied to in-bounds pixels only (padding is zero AFTER bn_data).
 constexpr int kStemTH = 8, kStemTW = 16;
+template <typename T>
 __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ in_scale,
                                                          const float* __restrict__ in_shift,
                                                          const float* __restrict__ out_scale,
-                                                         const float* __restrict__ out_shift, float* __restrict__ y,
+                                                         const float* __restrict__ out_shift, T* __restrict__ y,
                                                          int NB, int H, int W, int Ho, int Wo) {
   constexpr int PH = kStemTH * 2 + 5, PW = kStemTW * 2 + 5;  // 21 x 37
   __shared__ __align__(16) float s_w[147][64];  // [(kh,kw,c)][co]
@@ -387,7 +408,7 @@ __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict_
   }
   const int oh = oh0 + ty, ow = ow0 + tx;
   if (oh < Ho && ow < Wo) {
-    float* o = y + (((size_t)n * Ho + oh) * Wo + ow) * 64;
+    T* o = y + (((size_t)n * Ho + oh) * Wo + ow) * 64;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const float4 s = ld4(out_scale + 4 * j), t = ld4(out_shift + 4 * j);
@@ -420,16 +441,17 @@ __global__ void weight_transpose_kernel(const float* __restrict__ w, float* __re
   }
 }
 
-// All re-layouts of a training step in ONE launch.  jobs: njobs x 8 int64 = {w, wt, sel, Cout, T, Cin, Tsel, block0}
-// (block0 = first block of the job, ascending); the block finds its job by bisection.
+// All re-layouts of a training step in ONE launch.  jobs: njobs x 9 int64 = {w, wt, sel, Cout, T, Cin, Tsel, block0,
+// wt_is_bf16} (block0 = first block of the job, ascending); the block finds its job by bisection.  The source is
+// always the fp32 (master) weight; the data-gradient operand is written in fp32 or bf16.
 __global__ void weight_transpose_batched_kernel(const long long* __restrict__ jobs, int njobs) {
   __shared__ float tile[32][33];
   int lo = 0, hi = njobs - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (jobs[mid * 8 + 7] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+    if (jobs[mid * 9 + 7] <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
   }
-  const long long* jb = jobs + lo * 8;
+  const long long* jb = jobs + lo * 9;
   const float* __restrict__ w = reinterpret_cast<const float*>(jb[0]);
   float* __restrict__ wt = reinterpret_cast<float*>(jb[1]);
   const int* __restrict__ sel = reinterpret_cast<const int*>(jb[2]);
@@ -446,7 +468,11 @@ __global__ void weight_transpose_batched_kernel(const long long* __restrict__ jo
   __syncthreads();
   for (int r = threadIdx.y; r < 32; r += 8) {
     const int ci = ci0 + r, co = co0 + threadIdx.x;
-    if (ci < Cin && co < Cout) wt[((size_t)ci * Tsel + j) * Cout + co] = tile[threadIdx.x][r];
+    if (ci < Cin && co < Cout) {
+      const size_t o = ((size_t)ci * Tsel + j) * Cout + co;
+      if (jb[8]) reinterpret_cast<bf16*>(wt)[o] = __float2bfloat16(tile[threadIdx.x][r]);
+      else wt[o] = tile[threadIdx.x][r];
+    }
   }
 }
 
@@ -551,6 +577,20 @@ __global__ void __launch_bounds__(kTPB) sgd_mom_dev_kernel(float* __restrict__ w
   }
 }
 
+// Cast of Concat's output / its gradient between the bf16 backbone and the fp32 heads (resnet_mx_101_e2e.py:250-252
+// `mx.sym.Cast` after the concat): rows of C channels with independent strides (channel slices of the concat buffer).
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kTPB) cast_rows_kernel(const TI* __restrict__ x, long ldx, TO* __restrict__ y, long ldy,
+                                                          long M, int C) {
+  const int c4 = C >> 2;
+  const long total = M * c4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / c4;
+    const int c = (int)(i - r * c4) << 2;
+    st4(y + r * ldy + c, ld4(x + r * ldx + c));
+  }
+}
+
 int ew_grid(long work) {
   long g = (work + kTPB - 1) / kTPB;
   const long cap = (long)sn::kNumSMs * 8;
@@ -577,25 +617,40 @@ RowBlock row_block(long M, int C) {
 
 extern "C" {
 
-int sniper_affine_act(const float* x, long ldx, const float* scale, const float* shift, float* y, long ldy, long M,
-                      int C, int relu, void* stream) {
+// dtype (here and below): storage type of the activation tensors, 0 = fp32, 1 = bf16 (arithmetic is fp32 either way)
+int sniper_affine_act(const void* x, long ldx, const float* scale, const float* shift, void* y, long ldy, long M,
+                      int C, int relu, int dtype, void* stream) {
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "affine_act: C/ld must be multiples of 4");
+  SN_CHECK(dtype == 0 || dtype == 1, "affine_act: dtype must be 0 (fp32) or 1 (bf16)");
   const RowBlock rb = row_block(M, C);
-  affine_act_kernel<<<rb.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, scale, shift, y, ldy, M, C, relu, rb.lx_shift,
-                                                                rb.rows_per_block);
+  if (dtype == 0)
+    affine_act_kernel<float><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const float*>(x), ldx, scale, shift, static_cast<float*>(y), ldy, M, C, relu, rb.lx_shift,
+        rb.rows_per_block);
+  else
+    affine_act_kernel<bf16><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const bf16*>(x), ldx, scale, shift, static_cast<bf16*>(y), ldy, M, C, relu, rb.lx_shift,
+        rb.rows_per_block);
   SN_LAUNCH_CHECK();
   return 0;
 }
 
 // Train-mode BN statistics of x[M,C] -> (mean, invstd, scale, shift) + moving stats.  `sums` is a
 // caller-owned, zero-initialised double[2*C] scratch that is left zeroed.
-int sniper_bn_stats(const float* x, long ldx, long M, int C, const float* gamma, const float* beta, float eps,
+int sniper_bn_stats(const void* x, long ldx, long M, int C, const float* gamma, const float* beta, float eps,
                     float momentum, int fix_gamma, float* moving_mean, float* moving_var, double* sums, float* mean,
-                    float* invstd, float* scale, float* shift, void* stream) {
+                    float* invstd, float* scale, float* shift, int dtype, void* stream) {
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0, "bn_stats: C/ld must be multiples of 4");
+  SN_CHECK(dtype == 0 || dtype == 1, "bn_stats: dtype must be 0 (fp32) or 1 (bf16)");
   const RowBlock rb = row_block(M, C);
-  colsum_kernel<0><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, M,
-                                                              C, rb.lx_shift, rb.rows_per_block, sums);
+  if (dtype == 0)
+    colsum_kernel<0, float><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const float*>(x), ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, M, C, rb.lx_shift,
+        rb.rows_per_block, sums);
+  else
+    colsum_kernel<0, bf16><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const bf16*>(x), ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, M, C, rb.lx_shift,
+        rb.rows_per_block, sums);
   SN_LAUNCH_CHECK();
   bn_finalize_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, M, C, gamma, beta, eps, momentum,
                                                                           fix_gamma, moving_mean, moving_var, mean,
@@ -624,16 +679,30 @@ int sniper_bn_frozen(int C, const float* gamma, const float* beta, const float* 
 }
 
 // Backward of y = relu(bn_train(x)):  dx (+add), dgamma += , dbeta += .  sums: zeroed double[2C], left zeroed.
-int sniper_bn_relu_bwd(const float* x, long ldx, const float* dy, long lddy, const float* scale, const float* shift,
-                       const float* mean, const float* invstd, double* sums, const float* add, long ldadd, float* dx,
-                       long lddx, float* dgamma, float* dbeta, long M, int C, void* stream) {
+int sniper_bn_relu_bwd(const void* x, long ldx, const void* dy, long lddy, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, double* sums, const void* add, long ldadd, void* dx,
+                       long lddx, float* dgamma, float* dbeta, long M, int C, int dtype, void* stream) {
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "bn_relu_bwd: C/ld must be multiples of 4");
+  SN_CHECK(dtype == 0 || dtype == 1, "bn_relu_bwd: dtype must be 0 (fp32) or 1 (bf16)");
   const RowBlock rb = row_block(M, C);
-  colsum_kernel<1><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, dy, lddy, scale, shift, mean, invstd, M, C,
-                                                              rb.lx_shift, rb.rows_per_block, sums);
-  SN_LAUNCH_CHECK();
-  bn_relu_bwd_apply_kernel<<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
-      x, ldx, dy, lddy, scale, shift, mean, invstd, sums, add, ldadd, dx, lddx, M, C, rb.lx_shift, rb.rows_per_block);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 0) {
+    colsum_kernel<1, float><<<rb.grid, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<const float*>(dy),
+                                                     lddy, scale, shift, mean, invstd, M, C, rb.lx_shift,
+                                                     rb.rows_per_block, sums);
+    SN_LAUNCH_CHECK();
+    bn_relu_bwd_apply_kernel<float><<<rb.grid, 256, 0, st>>>(
+        static_cast<const float*>(x), ldx, static_cast<const float*>(dy), lddy, scale, shift, mean, invstd, sums,
+        static_cast<const float*>(add), ldadd, static_cast<float*>(dx), lddx, M, C, rb.lx_shift, rb.rows_per_block);
+  } else {
+    colsum_kernel<1, bf16><<<rb.grid, 256, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(dy),
+                                                    lddy, scale, shift, mean, invstd, M, C, rb.lx_shift,
+                                                    rb.rows_per_block, sums);
+    SN_LAUNCH_CHECK();
+    bn_relu_bwd_apply_kernel<bf16><<<rb.grid, 256, 0, st>>>(
+        static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(dy), lddy, scale, shift, mean, invstd, sums,
+        static_cast<const bf16*>(add), ldadd, static_cast<bf16*>(dx), lddx, M, C, rb.lx_shift, rb.rows_per_block);
+  }
   SN_LAUNCH_CHECK();
   if (dgamma || dbeta) {   // both null: the caller finishes with sniper_bn_param_grad_batched (sums stay live)
     bn_param_grad_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta);
@@ -652,29 +721,65 @@ int sniper_affine_relu_bwd(const float* x, long ldx, const float* dy, long lddy,
   return 0;
 }
 
-int sniper_relu_bwd(const float* y, long ldy, const float* dy, long lddy, float* dx, long lddx, long M, int C,
+int sniper_relu_bwd(const void* y, long ldy, const void* dy, long lddy, void* dx, long lddx, long M, int C, int dtype,
                     void* stream) {
   SN_CHECK(C % 4 == 0, "relu_bwd: C must be a multiple of 4");
-  relu_bwd_kernel<<<ew_grid(M * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(y, ldy, dy, lddy, dx, lddx, M, C);
+  SN_CHECK(dtype == 0 || dtype == 1, "relu_bwd: dtype must be 0 (fp32) or 1 (bf16)");
+  if (dtype == 0)
+    relu_bwd_kernel<float><<<ew_grid(M * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(
+        static_cast<const float*>(y), ldy, static_cast<const float*>(dy), lddy, static_cast<float*>(dx), lddx, M, C);
+  else
+    relu_bwd_kernel<bf16><<<ew_grid(M * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(
+        static_cast<const bf16*>(y), ldy, static_cast<const bf16*>(dy), lddy, static_cast<bf16*>(dx), lddx, M, C);
   SN_LAUNCH_CHECK();
   return 0;
 }
 
-int sniper_maxpool3x3s2_nhwc(const float* x, float* y, int NB, int H, int W, int C, void* stream) {
+// y[M,C] (ldy) = cast(x[M,C] (ldx)); dtypes 0 = fp32, 1 = bf16.
+int sniper_cast_rows(const void* x, long ldx, int x_dtype, void* y, long ldy, int y_dtype, long M, int C, void* stream) {
+  SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "cast_rows: C/ld must be multiples of 4");
+  SN_CHECK((x_dtype | y_dtype | 1) == 1, "cast_rows: dtypes must be 0 (fp32) or 1 (bf16)");
+  const int g = ew_grid(M * (C / 4));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == 0 && y_dtype == 0)
+    cast_rows_kernel<float, float><<<g, kTPB, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<float*>(y), ldy, M, C);
+  else if (x_dtype == 0)
+    cast_rows_kernel<float, bf16><<<g, kTPB, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<bf16*>(y), ldy, M, C);
+  else if (y_dtype == 0)
+    cast_rows_kernel<bf16, float><<<g, kTPB, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<float*>(y), ldy, M, C);
+  else
+    cast_rows_kernel<bf16, bf16><<<g, kTPB, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<bf16*>(y), ldy, M, C);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+int sniper_maxpool3x3s2_nhwc(const void* x, void* y, int NB, int H, int W, int C, int dtype, void* stream) {
   SN_CHECK(C % 4 == 0, "maxpool: C must be a multiple of 4");
+  SN_CHECK(dtype == 0 || dtype == 1, "maxpool: dtype must be 0 (fp32) or 1 (bf16)");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool3x3s2_kernel<<<ew_grid((long)NB * Ho * Wo * (C / 4)), kTPB, 0, (cudaStream_t)stream>>>(x, y, NB, H, W, C, Ho, Wo);
+  const int g = ew_grid((long)NB * Ho * Wo * (C / 4));
+  if (dtype == 0)
+    maxpool3x3s2_kernel<float><<<g, kTPB, 0, (cudaStream_t)stream>>>(static_cast<const float*>(x), static_cast<float*>(y),
+                                                                      NB, H, W, C, Ho, Wo);
+  else
+    maxpool3x3s2_kernel<bf16><<<g, kTPB, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y),
+                                                                     NB, H, W, C, Ho, Wo);
   SN_LAUNCH_CHECK();
   return 0;
 }
 
 int sniper_stem_conv(const float* x_nchw, const float* w /*[64,7,7,3]*/, const float* in_scale, const float* in_shift,
-                     const float* out_scale, const float* out_shift, float* y_nhwc, int NB, int H, int W,
-                     void* stream) {
+                     const float* out_scale, const float* out_shift, void* y_nhwc, int NB, int H, int W,
+                     int out_dtype, void* stream) {
+  SN_CHECK(out_dtype == 0 || out_dtype == 1, "stem_conv: out_dtype must be 0 (fp32) or 1 (bf16)");
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   dim3 grid(sn::div_up(Wo, kStemTW), sn::div_up(Ho, kStemTH), NB);
-  stem_conv_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, w, in_scale, in_shift, out_scale, out_shift, y_nhwc,
-                                                          NB, H, W, Ho, Wo);
+  if (out_dtype == 0)
+    stem_conv_kernel<float><<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, w, in_scale, in_shift, out_scale, out_shift,
+                                                                    static_cast<float*>(y_nhwc), NB, H, W, Ho, Wo);
+  else   // the reference casts to fp16 right after conv0 (resnet_mx_101_e2e.py:405-406); bn0 + relu ride in the same pass
+    stem_conv_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, w, in_scale, in_shift, out_scale, out_shift,
+                                                                   static_cast<bf16*>(y_nhwc), NB, H, W, Ho, Wo);
   SN_LAUNCH_CHECK();
   return 0;
 }
@@ -687,8 +792,8 @@ int sniper_weight_transpose(const float* w, float* wt, int Cout, int T, int Cin,
   return 0;
 }
 
-// jobs_dev: device array of njobs x 8 int64 {w, wt, sel_dev, Cout, T, Cin, Tsel, block0} with block0 the running sum
-// of ceil(Cin/32) * ceil(Cout/32) * Tsel; total_blocks = that sum over all jobs.
+// jobs_dev: device array of njobs x 9 int64 {w, wt, sel_dev, Cout, T, Cin, Tsel, block0, wt_is_bf16} with block0 the
+// running sum of ceil(Cin/32) * ceil(Cout/32) * Tsel; total_blocks = that sum over all jobs.
 int sniper_weight_transpose_batched(const void* jobs_dev, int njobs, int total_blocks, void* stream) {
   if (njobs <= 0 || total_blocks <= 0) return 0;
   weight_transpose_batched_kernel<<<total_blocks, dim3(32, 8), 0, (cudaStream_t)stream>>>(

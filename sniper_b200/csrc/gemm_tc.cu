@@ -23,7 +23,7 @@ namespace {
 
 enum { MODE_GEMM = 0, MODE_CONV = 1, MODE_WGRAD = 2 };
 enum { DT_TF32 = 0, DT_BF16 = 1 };
-enum { EPI_DIRECT = 0, EPI_STATS = 1, EPI_TMA = 2 };
+enum { EPI_DIRECT = 0, EPI_STATS = 1, EPI_TMA = 2, EPI_TMA16 = 3 };
 constexpr int kMaxTaps = 16;
 constexpr int kStageABytes = 128 * 128;  // 128 rows x 128 B
 constexpr int kStagingBytes = 8 * 4096;  // epilogue: one 32-row x 128-byte swizzled chunk per epilogue warp
@@ -309,7 +309,9 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int 
 // CG = tcgen05 cta_group of this instantiation (a kernel may not mix cta_group::1 and ::2 instructions).
 // EPI = epilogue variant (separate instantiations: 10 warps cap the kernel at 168 registers/thread, and sharing one
 // body made the plain epilogue spill -- measured +3.8 ms/step): EPI_DIRECT = per-lane row stores (any alignment,
-// bf16 output, ragged N), EPI_STATS = EPI_DIRECT + fused BatchNorm statistics, EPI_TMA = staged TMA store / reduce.
+// bf16 output, ragged N), EPI_STATS = EPI_DIRECT + fused BatchNorm statistics, EPI_TMA = staged TMA store / reduce,
+// EPI_TMA16 = the same for bf16 output (and bf16 residual): 32 x 32 chunks staged as 32 rows x 64 B with the 64-byte
+// TMA swizzle.
 template <int DT, int CG, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
@@ -340,7 +342,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
-    if (EPI == EPI_TMA) tma_prefetch_desc(&tma_c);
+    if (EPI == EPI_TMA || EPI == EPI_TMA16) tma_prefetch_desc(&tma_c);
     if (p.tail_p > 0) tma_prefetch_desc(&tma_bp);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -521,6 +523,156 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         col_base = tap * (p.wg_cin_blocks * p.block_n) + (tc.tile_n - tap * p.wg_cin_blocks) * p.block_n;
       }
       col_base += half * cols_per_warp;
+      if (EPI == EPI_TMA16) {
+        // ---------------- bf16 TMA-store epilogue (activations of the mixed-precision path).  Per 32-column chunk a
+        // warp converts its 32 x 32 accumulator block to bf16 into a 2 KB staging buffer laid out as 32 rows x 64 B
+        // with the 64-byte swizzle (16-byte chunk index ^ ((row >> 1) & 3)) and one lane stores it with a bulk tensor
+        // copy.  The bf16 residual is read coalesced (8 rows x 64 B per instruction) into the same buffer one chunk
+        // ahead.  BatchNorm statistics (optional) are taken from the ROUNDED values the consumer will read.
+        uint8_t* const stg_base = staging + (size_t)(warp - 2) * p.stg_bufs * 4096;
+        const int ch = lane & 3;
+        int c_ow = 0, c_oh = 0, c_n = 0;
+        int nvalid = 0;
+        int rowi[4];
+        const bool tile_ok = tc.tile_m < p.tiles_m;
+        if (p.mode == MODE_CONV) {
+          const int n_img = tc.tile_m / p.tiles_per_img;
+          const int r = tc.tile_m - n_img * p.tiles_per_img;
+          const int th = r / p.tiles_w;
+          const int oh0 = th * p.tile_h, ow0 = (r - th * p.tiles_w) * p.tile_w;
+          const int m0 = q * 32;
+          c_n = n_img; c_oh = oh0 + m0 / p.tile_w; c_ow = ow0 + m0 % p.tile_w;
+          nvalid = !tile_ok || c_oh >= p.Ho ? 0 : (p.tile_w >= 32 ? 32 : min(32, (p.Ho - c_oh) * p.tile_w));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = m0 + i * 8 + (lane >> 2);
+            const int oh = oh0 + m / p.tile_w, ow = ow0 + m % p.tile_w;
+            rowi[i] = (oh < p.Ho && tile_ok)
+                          ? ((n_img * p.out_H + oh * p.out_s + p.out_oh) * p.out_W + ow * p.out_s + p.out_ow) : -1;
+          }
+        } else {
+          c_ow = tc.tile_m * 128 + q * 32;
+          nvalid = tile_ok ? max(0, min(32, p.M - c_ow)) : 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = c_ow + i * 8 + (lane >> 2);
+            rowi[i] = (rr < p.M && tile_ok) ? rr : -1;
+          }
+        }
+        const __nv_bfloat16* res16 = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+        const bool has_res = res16 != nullptr;
+        uint4 rn[4];
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            rn[i] = (rowi[i] >= 0 && col_base < p.N)
+                        ? __ldg(reinterpret_cast<const uint4*>(res16 + (long)rowi[i] * p.ldr + col_base) + ch)
+                        : make_uint4(0u, 0u, 0u, 0u);
+        }
+        mbar_wait(&tmem_full_bar[acc], acc_ph);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + acc * acc_cols + (uint32_t)(half * cols_per_warp) + ((uint32_t)(q * 32) << 16);
+        const int swr = (lane >> 1) & 3;
+        for (int c = 0; c < cols_per_warp; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_acc + (uint32_t)c, v);
+          if (c + 32 >= cols_per_warp) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+              else mbar_arrive(&tmem_empty_bar[acc]);
+            }
+          }
+          const int n0 = col_base + c;
+          if (n0 >= p.N || !tile_ok) continue;       // warp-uniform
+          uint8_t* stg = stg_base + (size_t)sbuf * 4096;
+          if (lane == 0) {
+            if (p.stg_bufs == 2) bulk_wait_read1(); else bulk_wait_read0();
+          }
+          if (p.stg_bufs == 2) sbuf ^= 1;
+          __syncwarp();
+          if (has_res) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + (lane >> 2);
+              *reinterpret_cast<uint4*>(stg + r * 64 + ((ch ^ ((r >> 1) & 3)) << 4)) = rn[i];
+            }
+            if (c + 32 < cols_per_warp && n0 + 32 < p.N) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                rn[i] = rowi[i] >= 0
+                            ? __ldg(reinterpret_cast<const uint4*>(res16 + (long)rowi[i] * p.ldr + n0 + 32) + ch)
+                            : make_uint4(0u, 0u, 0u, 0u);
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
+            if (p.scale) {
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + 2 * j);
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + 2 * j + 1);
+              f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
+              f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
+            }
+            if (p.bias) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * j);
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * j + 1);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            uint4* slot = reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ swr) << 4));
+            if (has_res) {
+              const uint4 r4 = *slot;
+              const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 rf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[e]));
+                f[2 * e] += rf.x;
+                f[2 * e + 1] += rf.y;
+              }
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            uint32_t ow4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              ow4[e] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            *slot = make_uint4(ow4[0], ow4[1], ow4[2], ow4[3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (p.stats) {
+            // lane l sums column n0 + l of the staged (rounded) chunk over the rows that exist in the tensor
+            float sm = 0.f, sq = 0.f;
+            const uint8_t* colp = stg + ((lane & 7) << 1);
+            const int jc = lane >> 3;
+#pragma unroll 8
+            for (int r = 0; r < nvalid; ++r) {
+              const float xv = __bfloat162float(
+                  *reinterpret_cast<const __nv_bfloat16*>(colp + r * 64 + ((jc ^ ((r >> 1) & 3)) << 4)));
+              sm += xv;
+              sq = fmaf(xv, xv, sq);
+            }
+            if (nvalid > 0) {
+              atomicAdd(p.stats + n0 + lane, (double)sm);
+              atomicAdd(p.stats + p.N + n0 + lane, (double)sq);
+            }
+          }
+          if (lane == 0) {
+            tma_store_4d(&tma_c, stg, n0, c_ow, c_oh, c_n);
+            bulk_commit();
+          }
+        }
+        continue;
+      }
       if (EPI == EPI_TMA) {
         // ---------------- TMA-store epilogue.  Per 32-column chunk a warp transposes its 32 x 32 accumulator
         // block through a 128B-swizzled 4 KB staging buffer and ONE lane stores (or reduce-adds) it with a bulk
@@ -705,7 +857,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         continue;
       }
-      const float* rbase = (p.residual && row_ok) ? p.residual + row * p.ldr + col_base : nullptr;
+      // bf16 output implies a bf16 residual (mixed-precision activations); fp32 otherwise
+      const float* rbase = (p.residual && row_ok && !p.out_bf16) ? p.residual + row * p.ldr + col_base : nullptr;
+      const __nv_bfloat16* rbase16 = (p.residual && row_ok && p.out_bf16)
+                                         ? reinterpret_cast<const __nv_bfloat16*>(p.residual) + row * p.ldr + col_base
+                                         : nullptr;
       const bool r_vec = rbase && ((reinterpret_cast<uintptr_t>(rbase) & 15) == 0) && (col_base + cols_per_warp <= p.N);
       // residual of the first chunk is requested before the accumulator is even ready
       float4 rn[8];
@@ -768,6 +924,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           } else if (rbase) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += __ldg(rbase + c + j);
+          } else if (rbase16) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += __bfloat162float(rbase16[c + j]);
           }
           if (p.relu) {
 #pragma unroll
@@ -781,6 +940,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if (p.scale) x *= __ldg(p.scale + n0 + j);
               if (p.bias) x += __ldg(p.bias + n0 + j);
               if (rbase) x += __ldg(rbase + c + j);
+              if (rbase16) x += __bfloat162float(rbase16[c + j]);
               if (p.relu) x = fmaxf(x, 0.0f);
               f[j] = x;
             }
@@ -814,9 +974,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         if (p.out_bf16) {
           __nv_bfloat16* brow = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + n0;
+          if (full && ((reinterpret_cast<uintptr_t>(brow) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + j < p.N) brow[j] = __float2bfloat16(f[j]);
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t w4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 2 * e], f[j + 2 * e + 1]);
+                w4[e] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(brow + j) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || n0 + j < p.N) brow[j] = __float2bfloat16(f[j]);
+          }
         } else if (p.atomic) {
           if (full && ((reinterpret_cast<uintptr_t>(crow) & 15) == 0)) {
 #pragma unroll
@@ -838,7 +1011,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   }
-  if (EPI == EPI_TMA && warp >= 2 && lane == 0) bulk_wait_read0();   // staging buffers are read by in-flight bulk stores
+  if ((EPI == EPI_TMA || EPI == EPI_TMA16) && warp >= 2 && lane == 0) bulk_wait_read0();   // staging buffers are read by in-flight bulk stores
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();   // nobody frees TMEM or exits while the peer still uses the pair
@@ -867,7 +1040,8 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 4-D tiled map; dims/strides innermost first; strides in bytes for dims 1..3
+// 4-D tiled map; dims/strides innermost first; strides in bytes for dims 1..3.  atom32: 0 = SWIZZLE_128B,
+// 1 = SWIZZLE_128B_ATOM_32B (MN-major fp32 operands), 2 = SWIZZLE_64B (bf16 epilogue staging)
 int make_map(CUtensorMap* m, int dtype, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
              const uint32_t box[4], const uint32_t estr[4], int atom32 = 0) {
   EncodeTiledFn enc = get_encode();
@@ -878,7 +1052,8 @@ int make_map(CUtensorMap* m, int dtype, const void* base, const uint64_t dims[4]
   cuuint32_t es[4] = {estr[0], estr[1], estr[2], estr[3]};
   CUresult r = enc(m, dtype == DT_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                    const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   atom32 == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                               : (atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SN_CHECK(r == CUDA_SUCCESS,
            "cuTensorMapEncodeTiled failed (%d): dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu box=%u,%u,%u,%u es=%u,%u,%u,%u",
@@ -919,69 +1094,68 @@ int make_out_map(CUtensorMap* mc, GemmParams& p) {
   const bool enabled = !(e && e[0] == '0');
   memset(mc, 0, sizeof(*mc));
   p.epi_tma = 0;
-  const bool ok = enabled && !p.out_bf16 && p.N % 32 == 0 && p.ldc % 4 == 0 &&
+  const int osz = p.out_bf16 ? 2 : 4;                 // bf16 output implies a bf16 residual
+  const long ld_align = p.out_bf16 ? 8 : 4;             // 16-byte rows
+  const bool ok = enabled && p.N % 32 == 0 && p.ldc % ld_align == 0 &&
+                  (!p.out_bf16 || !p.atomic) &&
                   (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 &&
-                  (!p.residual || (p.ldr % 4 == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) &&
+                  (!p.residual || (p.ldr % ld_align == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0)) &&
                   (!p.scale || (reinterpret_cast<uintptr_t>(p.scale) & 15) == 0) &&
                   (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
   if (!ok) return 0;
   const uint32_t ones[4] = {1, 1, 1, 1};
-  const uint64_t rb = (uint64_t)p.ldc * 4;
+  const uint64_t rb = (uint64_t)p.ldc * osz;
+  const int odt = p.out_bf16 ? DT_BF16 : DT_TF32;
+  const int oswz = p.out_bf16 ? 2 : 0;
   if (p.mode == MODE_CONV) {
     const uint32_t bw = p.tile_w < 32 ? (uint32_t)p.tile_w : 32u;
     const uint64_t d[4] = {(uint64_t)p.N, (uint64_t)p.Wo, (uint64_t)p.Ho, (uint64_t)(p.M / (p.Ho * p.Wo))};
     const uint64_t st[3] = {rb * p.out_s, rb * p.out_s * p.out_W, rb * p.out_H * p.out_W};
     const uint32_t b[4] = {32, bw, 32u / bw, 1};
-    const float* base = p.C + ((long)p.out_oh * p.out_W + p.out_ow) * p.ldc;
-    if (make_map(mc, DT_TF32, base, d, st, b, ones)) return -1;
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(p.C) + ((long)p.out_oh * p.out_W + p.out_ow) * p.ldc * osz;
+    if (make_map(mc, odt, base, d, st, b, ones, oswz)) return -1;
   } else {
     const uint64_t d[4] = {(uint64_t)p.N, (uint64_t)p.M, 1, 1};
     const uint64_t st[3] = {rb, rb * p.M, rb * p.M};
     const uint32_t b[4] = {32, 32, 1, 1};
-    if (make_map(mc, DT_TF32, p.C, d, st, b, ones)) return -1;
+    if (make_map(mc, odt, p.C, d, st, b, ones, oswz)) return -1;
   }
   p.epi_tma = 1;
   return 0;
 }
 
-// Tail-split workspaces: kTailSlots buffers (one per stream using the kernel concurrently), allocated together on
-// first use so that no allocation happens later inside a CUDA-graph capture.  One buffer holds the parked
-// accumulators of at most 148 slices (128 x 256 fp32 each) + 148 x 8 arrival counters.
+// Tail-split workspaces: kTailSlots buffers per device (one per stream using the kernel concurrently) carved out of
+// ONE caller-provided allocation (sniper_gemm_set_tail_workspace; the library itself never allocates).  One buffer
+// holds the parked accumulators of at most 148 slices (128 x 256 fp32 each) + 148 x 8 arrival counters.  Without a
+// registered workspace the K-slice tail split is simply not used (results differ only in summation order).
 constexpr int kTailSlots = 4;
+constexpr int kMaxDevices = 64;
 constexpr size_t kTailWsBytes = (size_t)sn::kNumSMs * 128 * 256 * 4;
+constexpr size_t kTailCntBytes = ((size_t)sn::kNumSMs * 8 * sizeof(int) + 255) / 256 * 256;
 struct TailSlot {
   cudaStream_t stream;
   bool used;
   float4* ws;
   int* cnt;
 };
-TailSlot g_tail[kTailSlots];   // host-side table; the entry points are not re-entrant across host threads (documented
-bool g_tail_ready = false;     // in include/sniper_b200.h): one host thread drives the launches of a process
+struct TailDevice {
+  bool ready;
+  TailSlot slot[kTailSlots];
+};
+TailDevice g_tail[kMaxDevices];   // host-side table; the entry points are not re-entrant across host threads
+                                  // (documented in include/sniper_b200.h): one host thread drives a device's launches
 
 TailSlot* tail_slot(cudaStream_t stream) {
-  if (!g_tail_ready) {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
-    for (int i = 0; i < kTailSlots; ++i) {
-      void* w = nullptr;
-      void* c = nullptr;
-      if (cudaMalloc(&w, kTailWsBytes) != cudaSuccess || cudaMalloc(&c, sn::kNumSMs * 8 * sizeof(int)) != cudaSuccess ||
-          cudaMemset(c, 0, sn::kNumSMs * 8 * sizeof(int)) != cudaSuccess) {
-        cudaGetLastError();
-        return nullptr;
-      }
-      g_tail[i].stream = nullptr; g_tail[i].used = false;
-      g_tail[i].ws = static_cast<float4*>(w); g_tail[i].cnt = static_cast<int*>(c);
-    }
-    g_tail_ready = true;
-  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices || !g_tail[dev].ready) return nullptr;
+  TailSlot* sl = g_tail[dev].slot;
   for (int i = 0; i < kTailSlots; ++i)
-    if (g_tail[i].used && g_tail[i].stream == stream) return &g_tail[i];
+    if (sl[i].used && sl[i].stream == stream) return &sl[i];
   for (int i = 0; i < kTailSlots; ++i)
-    if (!g_tail[i].used) {
-      g_tail[i].used = true;
-      g_tail[i].stream = stream;
-      return &g_tail[i];
+    if (!sl[i].used) {
+      sl[i].used = true;
+      sl[i].stream = stream;
+      return &sl[i];
     }
   return nullptr;   // more concurrent streams than slots: run without the tail split
 }
@@ -1006,6 +1180,7 @@ void plan_tail(GemmParams& p, long tiles, long grid_units, cudaStream_t stream, 
       return;
     }
   }
+  if (p.out_bf16) return;   // K-slices park fp32 accumulators and re-enter the fp32 epilogue: not wired for bf16 output
   // Cost model fitted to tools/gemm_time.py on B200: a 128 x 256 tile costs ~0.43 us per k-block; parking the
   // slices, the arrival counter and the late epilogue cost ~(9 + 2.4 S) us.  The split pays off for K >~ 2000 only
   // (K = 2304: 62 -> 56 us with S = 4; K = 1024: 41 -> 43 us, so it stays off there).
@@ -1066,18 +1241,25 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
   }
   const size_t smem = smem_bytes(p.stages, p.block_n, p.stg_bufs);
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
-  static const KernelFn kernels[2][2][3] = {
-      {{gemm_tc_kernel<DT_TF32, 1, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 1, EPI_STATS>, gemm_tc_kernel<DT_TF32, 1, EPI_TMA>},
-       {gemm_tc_kernel<DT_TF32, 2, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 2, EPI_STATS>, gemm_tc_kernel<DT_TF32, 2, EPI_TMA>}},
-      {{gemm_tc_kernel<DT_BF16, 1, EPI_DIRECT>, gemm_tc_kernel<DT_BF16, 1, EPI_STATS>, gemm_tc_kernel<DT_BF16, 1, EPI_TMA>},
-       {gemm_tc_kernel<DT_BF16, 2, EPI_DIRECT>, gemm_tc_kernel<DT_BF16, 2, EPI_STATS>, gemm_tc_kernel<DT_BF16, 2, EPI_TMA>}}};
-  static bool attr_done = false;
-  if (!attr_done) {
+  static const KernelFn kernels[2][2][4] = {
+      {{gemm_tc_kernel<DT_TF32, 1, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 1, EPI_STATS>, gemm_tc_kernel<DT_TF32, 1, EPI_TMA>,
+        gemm_tc_kernel<DT_TF32, 1, EPI_TMA16>},
+       {gemm_tc_kernel<DT_TF32, 2, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 2, EPI_STATS>, gemm_tc_kernel<DT_TF32, 2, EPI_TMA>,
+        gemm_tc_kernel<DT_TF32, 2, EPI_TMA16>}},
+      {{gemm_tc_kernel<DT_BF16, 1, EPI_DIRECT>, gemm_tc_kernel<DT_BF16, 1, EPI_STATS>, gemm_tc_kernel<DT_BF16, 1, EPI_TMA>,
+        gemm_tc_kernel<DT_BF16, 1, EPI_TMA16>},
+       {gemm_tc_kernel<DT_BF16, 2, EPI_DIRECT>, gemm_tc_kernel<DT_BF16, 2, EPI_STATS>, gemm_tc_kernel<DT_BF16, 2, EPI_TMA>,
+        gemm_tc_kernel<DT_BF16, 2, EPI_TMA16>}}};
+  // per-device one-time setup (a process may drive several GPUs)
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  SN_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !attr_done[dev]) {
     for (int a = 0; a < 2; ++a)
       for (int b = 0; b < 2; ++b)
-        for (int c = 0; c < 3; ++c)
+        for (int c = 0; c < 4; ++c)
           SN_CUDA(cudaFuncSetAttribute(kernels[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1095,7 +1277,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
     const char* e = getenv("SNIPER_GEMM_CLUSTER_ATTR");   // A/B: force the (1,1,1) cluster attribute on 1-SM launches
     cfg.numAttrs = (p.cluster > 1 || (e && e[0] == '1')) ? 1 : 0;
   }
-  SN_CUDA(cudaLaunchKernelEx(&cfg, kernels[p.dtype == DT_TF32 ? 0 : 1][p.cluster == 2 ? 1 : 0][p.epi_tma ? EPI_TMA : (p.stats ? EPI_STATS : EPI_DIRECT)], ma, mb, mc, mbp, p));
+  SN_CUDA(cudaLaunchKernelEx(&cfg, kernels[p.dtype == DT_TF32 ? 0 : 1][p.cluster == 2 ? 1 : 0][p.epi_tma ? (p.out_bf16 ? EPI_TMA16 : EPI_TMA) : (p.stats ? EPI_STATS : EPI_DIRECT)], ma, mb, mc, mbp, p));
   SN_LAUNCH_CHECK();
   return 0;
 }
@@ -1333,6 +1515,31 @@ int sniper_conv2d_wgrad_nhwc(const void* dY, long dy_ld, const void* X, long x_l
   }
   dim3 grid(Cout / 128 + (Cout % 128 ? 1 : 0), ntaps * p.wg_cin_blocks, splits);
   return launch(ma, mb, p, grid, (cudaStream_t)stream);
+}
+
+// Bytes sniper_gemm_set_tail_workspace expects (per device).
+size_t sniper_gemm_tail_workspace_bytes(void) { return (size_t)kTailSlots * (kTailWsBytes + kTailCntBytes); }
+
+// Registers a caller-owned, ZERO-FILLED device buffer of sniper_gemm_tail_workspace_bytes() bytes for `device`; it must
+// outlive every later launch on that device.  Enables the K-slice split of the last partial wave (GemmParams::tail_s).
+// ws = NULL unregisters.
+int sniper_gemm_set_tail_workspace(void* ws, size_t bytes, int device) {
+  SN_CHECK(device >= 0 && device < kMaxDevices, "gemm_set_tail_workspace: device %d out of range", device);
+  TailDevice& d = g_tail[device];
+  d.ready = false;
+  if (ws == nullptr) return 0;
+  SN_CHECK(bytes >= sniper_gemm_tail_workspace_bytes(), "gemm_set_tail_workspace: %zu bytes given, %zu needed", bytes,
+           sniper_gemm_tail_workspace_bytes());
+  SN_CHECK((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "gemm_set_tail_workspace: buffer must be 256-byte aligned");
+  uint8_t* p8 = static_cast<uint8_t*>(ws);
+  for (int i = 0; i < kTailSlots; ++i) {
+    d.slot[i].stream = nullptr;
+    d.slot[i].used = false;
+    d.slot[i].ws = reinterpret_cast<float4*>(p8 + (size_t)i * (kTailWsBytes + kTailCntBytes));
+    d.slot[i].cnt = reinterpret_cast<int*>(p8 + (size_t)i * (kTailWsBytes + kTailCntBytes) + kTailWsBytes);
+  }
+  d.ready = true;
+  return 0;
 }
 
 // Host-only query of the launch plan sniper_gemm_nt would use for C[M,N] = A[M,K] * B[N,K]^T with 16-byte aligned,

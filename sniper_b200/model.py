@@ -44,7 +44,13 @@ class Cfg:
     momentum = 0.9
     units = (3, 4, 23, 3)
     filter_list = (64, 256, 512, 1024, 2048)
-    grad_scale = 1.0                  # TRAIN.scale only applies to fp16
+    grad_scale = 1.0                  # TRAIN.scale only applies to fp16 (bf16 has fp32's exponent range: no loss scale)
+    # Mixed precision (BASELINE config 3; the reference's TRAIN.fp16, sniper_res101_e2e.yml:107): the backbone from the
+    # output of conv0 to the concat stores activations, weights and gradients of activations in bf16 (the reference:
+    # fp16 between the two Casts, resnet_mx_101_e2e.py:405-406 and :250-252), BatchNorm arithmetic and statistics stay
+    # fp32, the RPN / R-FCN heads stay fp32 (TF32 math) exactly where the reference keeps them fp32, and the optimizer
+    # keeps fp32 master weights + momentum and rewrites the bf16 copies every step (multi_precision SGD).
+    bf16 = os.environ.get("SNIPER_BF16", "0") == "1"
     wgrad_splits = 0                  # 0 = choose per layer (fill one wave of 148 persistent CTAs)
     # BN statistics accumulated by the producing conv's TMA-store epilogue (column sums of the staged chunk + double
     # REDs) instead of a separate colsum pass.  Measured on B200: 39.1 -> 37.8 ms/step, so ON by default
@@ -99,7 +105,8 @@ class ParamStore:
         wd_mult = 1.0 if (name.endswith("_weight") or name.endswith("_gamma")) else 0.0
         self.specs.append((name, tuple(shape), (lr_mult, wd_mult)))
 
-    def finalize(self, device):
+    def finalize(self, device, lowp=False):
+        """lowp: also keep a bf16 copy of the whole buffer (`w16`, same offsets) for the mixed-precision backbone."""
         groups = sorted(set(g for _, _, g in self.specs))
         off = 0
         self.segments = []
@@ -120,11 +127,21 @@ class ParamStore:
         # [lr, wd] on the device: read by sgd_mom_dev_kernel, so a captured update graph follows the LR schedule
         self.hyper = torch.zeros(2, device=device)
         self._hyper_host = (None, None)
+        self.w16 = torch.zeros(off, device=device, dtype=torch.bfloat16) if lowp else None
+        self.views16 = {}
         for name, (o, shape) in layout.items():
             n = int(np.prod(shape))
             self.views[name] = self.w[o:o + n].view(shape)
             self.grads[name] = self.g[o:o + n].view(shape)
+            if lowp:
+                self.views16[name] = self.w16[o:o + n].view(shape)
         self.layout = layout
+
+    def sync_lowp(self):
+        """bf16 copies := round(fp32 masters); after initialisation / checkpoint loading (the update kernel keeps them
+        in step afterwards)."""
+        if self.w16 is not None:
+            self.w16.copy_(self.w)
 
     def __getitem__(self, name):
         return self.views[name]
@@ -141,7 +158,8 @@ class ParamStore:
     def sgd_step(self, momentum, rescale=1.0):
         """optimizer_op-inl.h:279-300 on every (lr_mult, wd_mult) segment, lr / wd taken from self.hyper."""
         for s, e, (lr_mult, wd_mult) in self.segments:
-            ops.sgd_mom_dev(self.w[s:e], self.mom[s:e], self.g[s:e], self.hyper, lr_mult, wd_mult, momentum, rescale)
+            ops.sgd_mom_dev(self.w[s:e], self.mom[s:e], self.g[s:e], self.hyper, lr_mult, wd_mult, momentum, rescale,
+                            None if self.w16 is None else self.w16[s:e])
 
 
 # ------------------------------------------------------------------------------------------------
@@ -151,7 +169,10 @@ class Conv:
     count (72, 126, 85, 98) is not a multiple of 32."""
 
     def __init__(self, P, name, cin, cout, k=1, stride=1, dil=1, pad=0, bias=False, trainable=True, cout_pad=None,
-                 lr_mult=1.0, need_dgrad=True, plain_wt=False):
+                 lr_mult=1.0, need_dgrad=True, plain_wt=False, lowp=False):
+        """lowp: this layer reads bf16 activations -> bf16 weights (the ParamStore's bf16 copy; fp32 master + gradient)."""
+        self.lowp = lowp
+        self.wdtype = torch.bfloat16 if lowp else torch.float32
         self.name, self.cin, self.cout, self.k = name, cin, cout, k
         self.stride, self.dil, self.pad, self.bias = stride, dil, pad, bias
         self.coutp = cout_pad or cout
@@ -169,6 +190,14 @@ class Conv:
     # ---- parameters
     @property
     def w(self):
+        """the operand the kernels read: bf16 copy for a mixed-precision layer, else the fp32 parameter"""
+        if not self.trainable:
+            return self.frozen_w
+        return self.P.views16[self.name + "_weight"] if self.lowp else self.P[self.name + "_weight"]
+
+    @property
+    def master(self):
+        """the fp32 parameter the optimizer updates (frozen layers: the stored weight itself)"""
         return self.P[self.name + "_weight"] if self.trainable else self.frozen_w
 
     @property
@@ -185,21 +214,23 @@ class Conv:
         if std > 0:
             w[:self.cout].normal_(0, std, generator=gen)
         if self.trainable:
-            self.w.copy_(w)
+            self.master.copy_(w)
+            if self.lowp:
+                self.w.copy_(w)
             if self.bias:
                 self.b.zero_()
         else:
-            self.frozen_w = w
+            self.frozen_w = w.to(self.wdtype)
             if self.bias:
                 self.frozen_b = torch.zeros(self.coutp, device=device)
 
     # ---- forward
-    def fwd(self, x, out=None, scale=None, shift=None, relu=False, residual=None, stats=None):
+    def fwd(self, x, out=None, scale=None, shift=None, relu=False, residual=None, stats=None, out_dtype=None):
         """y = epi(conv(x)); epilogue order: *scale, +shift (or +bias), +residual, relu; `stats` (a BN's
         double[2C] scratch) receives the column sums of y for the consumer's train-mode statistics."""
         add = shift if shift is not None else self.b
         return ops.conv2d_nhwc(x, self.w, kh=self.k, kw=self.k, stride=self.stride, dil=self.dil, pad=self.pad, out=out,
-                               scale=scale, bias=add, residual=residual, relu=relu, stats=stats)
+                               scale=scale, bias=add, residual=residual, relu=relu, stats=stats, out_dtype=out_dtype)
 
     # ---- backward
     def bwd_jobs(self):
@@ -213,14 +244,14 @@ class Conv:
             # plain 2-D transpose [Cout, K] -> [K, Cout] (deformable conv: the GEMM runs on the im2col buffer)
             if getattr(self, "_sel", None) is None:
                 self._sel = torch.zeros(1, dtype=torch.int32, device=dev)
-                self.wt = torch.empty(self.K, self.coutp, device=dev)
-            return [(self.w, self.wt, self._sel, self.coutp, 1, self.K)]
+                self.wt = torch.empty(self.K, self.coutp, device=dev, dtype=self.wdtype)
+            return [(self.master, self.wt, self._sel, self.coutp, 1, self.K)]
         if self.stride == 1 or k == 1:
             sel = list(range(T - 1, -1, -1))
             if getattr(self, "_sel", None) is None:
                 self._sel = torch.tensor(sel, dtype=torch.int32, device=dev)
-                self.wt = torch.empty(self.cin, T * self.coutp, device=dev)
-            return [(self.w, self.wt, self._sel, self.coutp, T, self.cin)]
+                self.wt = torch.empty(self.cin, T * self.coutp, device=dev, dtype=self.wdtype)
+            return [(self.master, self.wt, self._sel, self.coutp, T, self.cin)]
         # stride 2, 3x3, pad 1: four output-parity classes, each a stride-1 conv over dY
         assert k == 3 and self.stride == 2 and self.pad == 1 and self.dil == 1
         if getattr(self, "_sel", None) is None:
@@ -233,13 +264,16 @@ class Conv:
                     dh = [(ph + 1 - kh) // 2 for kh in khs for _ in kws]
                     dw = [(pw + 1 - kw) // 2 for _ in khs for kw in kws]
                     self._sel.append(torch.tensor(sel, dtype=torch.int32, device=dev))
-                    self.wt.append(torch.empty(self.cin, len(sel) * self.coutp, device=dev))
+                    self.wt.append(torch.empty(self.cin, len(sel) * self.coutp, device=dev, dtype=self.wdtype))
                     self._taps.append((dh, dw, ph, pw))
-        return [(self.w, w, s, self.coutp, 9, self.cin) for s, w in zip(self._sel, self.wt)]
+        return [(self.master, w, s, self.coutp, 9, self.cin) for s, w in zip(self._sel, self.wt)]
 
     def prepare_bwd(self):
-        for w, wt, sel, Cout, T, Cin in self.bwd_jobs():
-            ops.weight_transpose(w, Cout, T, Cin, sel, out=wt)
+        """Rebuilds this layer's data-gradient operands from the fp32 master weights (one small batched launch; the
+        model does it for all layers at once)."""
+        jobs = self.bwd_jobs()
+        if jobs:
+            ops.weight_transpose_batched(ops.weight_transpose_jobs(jobs, jobs[0][0].device))
 
     def bwd_data(self, dy, in_hw, out=None, residual=None):
         """dX = conv^T(dY).  dy: [N,Ho,Wo,coutp]; returns [N,H,W,Cin] (+ residual)."""
@@ -250,7 +284,7 @@ class Conv:
             padb = self.dil * (k - 1) - self.pad
             return ops.conv2d_nhwc(dy, self.wt, kh=k, kw=k, stride=1, dil=self.dil, pad=padb, out=out, residual=residual)
         if out is None:
-            out = torch.zeros(NB, H, W, self.cin, device=dy.device) if residual is None else residual
+            out = torch.zeros(NB, H, W, self.cin, device=dy.device, dtype=dy.dtype) if residual is None else residual
         Ho, Wo = dy.shape[1], dy.shape[2]
         if k == 1:
             # dX[2a, 2b] = dY[a,b] * W ; other positions receive nothing
@@ -261,12 +295,13 @@ class Conv:
                             out_hw=(H // 2, W // 2), out_map=(H, W, 2, ph, pw))
         return out
 
-    def bwd_weight(self, dy, x, splits=8):
+    def bwd_weight(self, dy, x, splits=8, dy32=None):
+        """dy32: fp32 form of dy for the bias gradient when dy itself is bf16 (the bias-gradient kernel reads fp32)."""
         gw = self.P.grad(self.name + "_weight")
         ops.conv2d_wgrad_nhwc(dy, x, kh=self.k, kw=self.k, stride=self.stride, dil=self.dil, pad=self.pad, dw_out=gw,
                               splits=splits)
         if self.bias:
-            ops.colsum_accum(dy, self.P.grad(self.name + "_bias"))
+            ops.colsum_accum(dy if dy32 is None else dy32, self.P.grad(self.name + "_bias"))
 
 
 class BN:
@@ -317,22 +352,24 @@ class BN:
 class Unit:
     """Pre-activation bottleneck (residual_unit :36-69 / residual_unit_deform :106-145)."""
 
-    def __init__(self, P, name, cin, cout, stride, dim_match, frozen, deform=False, first_trainable=False):
+    def __init__(self, P, name, cin, cout, stride, dim_match, frozen, deform=False, first_trainable=False, lowp=False):
         mid = cout // 4
         self.name, self.cin, self.cout, self.mid = name, cin, cout, mid
         self.stride, self.dim_match, self.frozen, self.deform = stride, dim_match, frozen, deform
+        self.lowp = lowp
         t = not frozen
         self.bn1 = BN(P, name + "_bn1", cin, frozen)
-        self.conv1 = Conv(P, name + "_conv1", cin, mid, 1, trainable=t)
+        self.conv1 = Conv(P, name + "_conv1", cin, mid, 1, trainable=t, lowp=lowp)
         self.bn2 = BN(P, name + "_bn2", mid, frozen)
         if deform:
-            self.offset = Conv(P, name + "_offset", mid, 72, 3, 1, 2, 2, bias=True, cout_pad=96)
-            self.conv2 = Conv(P, name + "_conv2", mid, mid, 3, 1, 2, 2, trainable=t, plain_wt=True)
+            # 72 offset channels, zero-padded to a width the MMA / TMA tiles accept (bf16 weight gradients: x64)
+            self.offset = Conv(P, name + "_offset", mid, 72, 3, 1, 2, 2, bias=True, cout_pad=128 if lowp else 96, lowp=lowp)
+            self.conv2 = Conv(P, name + "_conv2", mid, mid, 3, 1, 2, 2, trainable=t, plain_wt=True, lowp=lowp)
         else:
-            self.conv2 = Conv(P, name + "_conv2", mid, mid, 3, stride, 1, 1, trainable=t)
+            self.conv2 = Conv(P, name + "_conv2", mid, mid, 3, stride, 1, 1, trainable=t, lowp=lowp)
         self.bn3 = BN(P, name + "_bn3", mid, frozen)
-        self.conv3 = Conv(P, name + "_conv3", mid, cout, 1, trainable=t)
-        self.sc = None if dim_match else Conv(P, name + "_sc", cin, cout, 1, stride, trainable=t)
+        self.conv3 = Conv(P, name + "_conv3", mid, cout, 1, trainable=t, lowp=lowp)
+        self.sc = None if dim_match else Conv(P, name + "_sc", cin, cout, 1, stride, trainable=t, lowp=lowp)
         self.first_trainable = first_trainable
         self.saved = None
 
@@ -362,7 +399,7 @@ class Unit:
         c1 = self.conv1.fwd(a1, stats=self.bn2.stats_sink())
         a2 = self.bn2.fwd(c1, cfg, have_stats=fused)
         if self.deform:
-            off = self.offset.fwd(a2)                                          # [N,H,W,96], 72 used
+            off = self.offset.fwd(a2, out_dtype=torch.float32)                 # [N,H,W,96] fp32, 72 used
             col = ops.deform_im2col(a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)
             c2 = ops.gemm_nt(col, self.conv2.w, stats=self.bn3.stats_sink())
             c2 = c2.view(a2.shape[0], a2.shape[1], a2.shape[2], self.mid)
@@ -381,7 +418,7 @@ class Unit:
         a1 = ops.affine_act(x, self.bn1.st.scale, self.bn1.st.shift, relu=True)
         a2 = self.conv1.fwd(a1, scale=self.bn2.st.scale, shift=self.bn2.st.shift, relu=True)
         if self.deform:
-            off = self.offset.fwd(a2)
+            off = self.offset.fwd(a2, out_dtype=torch.float32)
             col = ops.deform_im2col(a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)
             a3 = ops.gemm_nt(col, self.conv2.w, scale=self.bn3.st.scale, bias=self.bn3.st.shift, relu=True)
             a3 = a3.view(a2.shape[0], a2.shape[1], a2.shape[2], self.mid)
@@ -407,9 +444,15 @@ class Unit:
             W(lambda d, c: ops.conv2d_wgrad_nhwc(d, c, kh=1, kw=1, dw_out=gw, splits=sp), dc2,
               col.view(a2.shape[0], a2.shape[1], a2.shape[2], -1))
             dcol = ops.gemm_nt(dc2.view(M, self.mid), self.conv2.wt)         # wt = W^T [9*mid, mid]
-            da2, doff = ops.deform_col2im(dcol, a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)
-            W(self.offset.bwd_weight, doff, a2, sp)
-            da2 = self.offset.bwd_data(doff, (a2.shape[1], a2.shape[2]), out=da2, residual=da2)
+            da2, doff = ops.deform_col2im(dcol, a2, off, kh=3, kw=3, stride=1, dil=2, pad=2, dgroups=4)   # fp32 sums
+            if self.lowp:
+                doff16 = ops.cast_rows(doff, torch.bfloat16)
+                da2 = ops.cast_rows(da2, torch.bfloat16)
+                W(self.offset.bwd_weight, doff16, a2, sp, doff)
+                da2 = self.offset.bwd_data(doff16, (a2.shape[1], a2.shape[2]), out=da2, residual=da2)
+            else:
+                W(self.offset.bwd_weight, doff, a2, sp)
+                da2 = self.offset.bwd_data(doff, (a2.shape[1], a2.shape[2]), out=da2, residual=da2)
         else:
             W(self.conv2.bwd_weight, dc2, a2, sp)
             da2 = self.conv2.bwd_data(dc2, (a2.shape[1], a2.shape[2]))
@@ -456,7 +499,8 @@ class SniperResNet101:
             stride = 1 if stage in (1, 4) else 2
             for j in range(n):
                 u = Unit(P, "stage%d_unit%d" % (stage, j + 1), cin if j == 0 else cout, cout, stride if j == 0 else 1,
-                         dim_match=(j > 0), frozen=frozen, deform=deform, first_trainable=(stage == 2 and j == 0))
+                         dim_match=(j > 0), frozen=frozen, deform=deform, first_trainable=(stage == 2 and j == 0),
+                         lowp=bool(cfg.bf16))
                 self.units.append(u)
             cin = cout
         A = cfg.num_anchors
@@ -470,7 +514,8 @@ class SniperResNet101:
         self.fc_new_2 = Conv(P, "fc_new_2", 1024, 1024, 1, bias=True)
         # cls_score (81) and bbox_pred (4) fused: rows [0,81) | [81,85), padded to 96
         self.fc_out = Conv(P, "cls_bbox", 1024, cfg.num_classes + 4, 1, bias=True, cout_pad=96)
-        P.finalize(device)
+        P.finalize(device, lowp=bool(cfg.bf16))
+        self.act_dtype = torch.bfloat16 if cfg.bf16 else torch.float32
         self._init_weights(seed, deform_offset_std)
         self.loss_buf = torch.zeros(8, device=device)
         self.cnt_buf = torch.zeros(2, dtype=torch.int32, device=device)
@@ -498,7 +543,7 @@ class SniperResNet101:
                 o, _ = P.layout[c.name + "_weight"]
                 host[o:o + w.numel()] = w.view(-1)
             else:
-                c.frozen_w = w.to(dev)
+                c.frozen_w = w.to(dev, c.wdtype)
                 if c.bias:
                     c.frozen_b = torch.zeros(c.coutp).to(dev)
 
@@ -518,6 +563,7 @@ class SniperResNet101:
             fill(c, 0.01)
         fill(self.fc_offset, deform_offset_std and 0.001)                  # zeros in the reference (:476-477)
         P.w.copy_(host)
+        P.sync_lowp()
         pool.finalize()
         self.bn_pool = pool
         # bn_data: frozen, fix_gamma; realistic pixel statistics so that conv0 sees O(1) inputs
@@ -562,23 +608,33 @@ class SniperResNet101:
         ops.weight_transpose_batched(self._wt_table)
 
         # ---- backbone forward
+        lowp = bool(cfg.bf16)
         x = ops.stem_conv(data, self.conv0_w, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
-                          self.bn0.st.shift)
+                          self.bn0.st.shift, out_dtype=self.act_dtype)     # the reference's Cast sits right after conv0
         x = ops.maxpool3x3s2(x)
         n1, n2, n3, n4 = cfg.units
         Hf = data.shape[2] // cfg.feat_stride
-        cat = torch.empty(B, Hf, Hf, 3072, device=data.device)           # Concat(c4, c5) written in place
+        # Concat(c4, c5): fp32.  fp32 mode: the two producing convs write their channel slices in place.  Mixed
+        # precision: c4 / c5 are bf16 tensors and the reference's Cast(relu1, float32) (:250-252) fills the slices.
+        cat = torch.empty(B, Hf, Hf, 3072, device=data.device)
         last3 = n1 + n2 + n3 - 1
         has_stats = False
+        c4 = None
         for i, u in enumerate(self.units):
             out = None
-            if i == last3:
-                out = cat[..., :1024]
-            elif i == len(self.units) - 1:
-                out = cat[..., 1024:]
+            if not lowp:
+                if i == last3:
+                    out = cat[..., :1024]
+                elif i == len(self.units) - 1:
+                    out = cat[..., 1024:]
             nxt = self.units[i + 1].bn1 if i + 1 < len(self.units) else None
             x = u.fwd(x, cfg, out=out, x_has_stats=has_stats, next_bn=nxt)
             has_stats = nxt is not None and not nxt.frozen
+            if i == last3:
+                c4 = x
+        if lowp:
+            ops.cast_rows(c4, out=cat[..., :1024])
+            ops.cast_rows(x, out=cat[..., 1024:])
 
         # ---- RPN (get_rpn) + conv_new_1
         rpn = self.rpn_conv.fwd(cat, relu=True)
@@ -640,10 +696,12 @@ class SniperResNet101:
         W(self.rpn_conv.bwd_weight, drpn, cat, sp)
         dcat = self.rpn_conv.bwd_data(drpn, hw, out=dcat, residual=dcat)
         # ---- backbone backward (stage 4, then stage 3 with the c4 half of dcat added, then stage 2)
-        g = dcat[..., 1024:]
+        g, g4 = dcat[..., 1024:], dcat[..., :1024]
+        if lowp:      # backward of the Cast: the backbone's activation gradients are bf16
+            g, g4 = ops.cast_rows(g, torch.bfloat16), ops.cast_rows(g4, torch.bfloat16)
         for i in range(len(self.units) - 1, n1 - 1, -1):
             u = self.units[i]
-            g = u.bwd(g, cfg, extra_add=dcat[..., :1024] if i == last3 + 1 else None)
+            g = u.bwd(g, cfg, extra_add=g4 if i == last3 + 1 else None)
         ops.bn_param_grad_batched(self._bn_table)
         W.join()
         self.step_count += 1
@@ -661,15 +719,22 @@ class SniperResNet101:
         for b in self.train_bns():
             ops.bn_frozen(b.st, cfg.bn_eps)        # scale/shift from the moving statistics (the next training step
         x = ops.stem_conv(data, self.conv0_w, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
-                          self.bn0.st.shift)       # recomputes them from batch statistics)
+                          self.bn0.st.shift, out_dtype=self.act_dtype)       # recomputes them from batch statistics)
         x = ops.maxpool3x3s2(x)
         n1, n2, n3, n4 = cfg.units
         Hf, Wf = data.shape[2] // cfg.feat_stride, data.shape[3] // cfg.feat_stride
         cat = torch.empty(B, Hf, Wf, 3072, device=data.device)
         last3 = n1 + n2 + n3 - 1
+        lowp = bool(cfg.bf16)
         for i, u in enumerate(self.units):
-            out = cat[..., :1024] if i == last3 else (cat[..., 1024:] if i == len(self.units) - 1 else None)
+            out = None
+            if not lowp:
+                out = cat[..., :1024] if i == last3 else (cat[..., 1024:] if i == len(self.units) - 1 else None)
             x = u.fwd_infer(x, cfg, out=out)
+            if lowp and i == last3:
+                ops.cast_rows(x, out=cat[..., :1024])
+        if lowp:
+            ops.cast_rows(x, out=cat[..., 1024:])
         rpn = self.rpn_conv.fwd(cat, relu=True)
         head = self.rpn_head.fwd(rpn)
         feat = self.conv_new_1.fwd(cat, relu=True)
@@ -715,7 +780,7 @@ class SniperResNet101:
         self.conv0_w.copy_(t(arg["conv0_weight"].transpose(0, 2, 3, 1)))
         for c in self._named_convs():
             w, b = ck.conv_from_reference(c.name, c.cout, c.coutp, c.cin, c.k, c.bias, arg)
-            c.w.copy_(t(w))
+            c.master.copy_(t(w))
             if c.bias:
                 c.b.copy_(t(b))
         for bn in self._named_bns():
@@ -725,6 +790,7 @@ class SniperResNet101:
             bn.st.moving_var.copy_(t(aux[bn.name + "_moving_var"]))
             if bn.frozen:
                 ops.bn_frozen(bn.st, cfg.bn_eps, fix_gamma=bn.fix_gamma)
+        self.P.sync_lowp()
         self._wt_table = None      # data-gradient operands are rebuilt from the new weights on the next step
 
     def export_reference(self, grads=False):
@@ -742,7 +808,7 @@ class SniperResNet101:
         for c in self._named_convs():
             if grads and not c.trainable:
                 continue
-            w = self.P.grad(c.name + "_weight") if grads else c.w
+            w = self.P.grad(c.name + "_weight") if grads else c.master.float()
             b = (self.P.grad(c.name + "_bias") if grads else c.b) if c.bias else None
             ck.conv_to_reference(c.name, c.cout, c.cin, c.k, n(w), n(b) if c.bias else None, parts.get(c.name), arg)
         for bn in self._named_bns():

@@ -215,15 +215,34 @@ def _dt(t):
     return TF32 if t.dtype == torch.float32 else BF16
 
 
-def gemm_nt(a, b, *, out=None, scale=None, bias=None, residual=None, relu=False, accumulate=False, out_bf16=False,
+_gemm_ws = {}
+
+
+def _ensure_gemm_workspace(device):
+    """The tcgen05 kernel's tail-split scratch is caller-owned (the library never allocates): one zero-filled torch
+    buffer per device, registered once and kept alive for the life of the process."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _gemm_ws:
+        L = lib()
+        n = L.sniper_gemm_tail_workspace_bytes()
+        buf = torch.zeros(n, dtype=torch.uint8, device=torch.device("cuda", idx))
+        check(L.sniper_gemm_set_tail_workspace(buf.data_ptr(), n, idx))
+        _gemm_ws[idx] = buf
+
+
+def gemm_nt(a, b, *, out=None, scale=None, bias=None, residual=None, relu=False, accumulate=False, out_dtype=None,
             stats=None):
-    """C[M,N] = epi(A[M,K] @ B[N,K]^T) on tcgen05 tensor cores (fp32 storage -> TF32 math, or bf16)."""
+    """C[M,N] = epi(A[M,K] @ B[N,K]^T) on tcgen05 tensor cores (fp32 storage -> TF32 math, or bf16 operands with fp32
+    accumulation).  The output is fp32 or bf16 (default: the operands' dtype); a residual has the output's dtype."""
     assert a.is_cuda and a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1] and a.dtype == b.dtype
     assert a.stride(1) == 1 and b.stride(1) == 1
     M, K = a.shape
     N = b.shape[0]
+    _ensure_gemm_workspace(a.device)
     if out is None:
-        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+        out = torch.empty(M, N, device=a.device, dtype=out_dtype or a.dtype)
+    out_bf16 = out.dtype == torch.bfloat16
+    assert residual is None or residual.dtype == out.dtype, "bf16 output takes a bf16 residual"
     check(lib().sniper_gemm_nt(_ptr(a), a.stride(0), _ptr(b), b.stride(0), _ptr(out), out.stride(0), M, N, K, _dt(a),
                                _ptr(scale), _ptr(bias), _ptr(residual), 0 if residual is None else residual.stride(0),
                                int(relu), int(accumulate), int(out_bf16), _ptr(stats), _stream()))
@@ -238,8 +257,9 @@ def conv_taps(kh, kw, dil, pad):
 
 
 def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, bias=None, residual=None, relu=False,
-                accumulate=False, taps=None, out_hw=None, out_map=None, stats=None):
-    """NHWC implicit-GEMM convolution.  x: [N,H,W,Cin]; w: [Cout, kh*kw*Cin] (tap-major, channel-minor)."""
+                accumulate=False, taps=None, out_hw=None, out_map=None, stats=None, out_dtype=None):
+    """NHWC implicit-GEMM convolution.  x: [N,H,W,Cin]; w: [Cout, kh*kw*Cin] (tap-major, channel-minor).  fp32 tensors
+    run as TF32, bf16 tensors as bf16 (fp32 accumulation); the output (and the residual) may be fp32 or bf16."""
     NB, H, W, Cin = x.shape
     Cout = w.shape[0]
     dh, dw = taps if taps is not None else conv_taps(kh, kw, dil, pad)
@@ -252,15 +272,17 @@ def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, b
         Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     else:
         Ho, Wo = out_hw
+    _ensure_gemm_workspace(x.device)
     if out is None:
-        out = torch.empty(NB, Ho, Wo, Cout, device=x.device)
+        out = torch.empty(NB, Ho, Wo, Cout, device=x.device, dtype=out_dtype or x.dtype)
+    assert x.dtype == w.dtype and (residual is None or residual.dtype == out.dtype), "bf16 output takes a bf16 residual"
     oH, oW, os_, ooh, oow = (Ho, Wo, 1, 0, 0) if out_map is None else out_map
     _, dhp = _iarr(dh)
     _, dwp = _iarr(dw)
     check(lib().sniper_conv2d_nhwc(_ptr(x), x_ld, NB, H, W, Cin, _ptr(w), Cout, ntaps, dhp, dwp, stride, Ho, Wo,
                                    _ptr(out), _rows(out)[2], oH, oW, os_, ooh, oow, _dt(x), _ptr(scale), _ptr(bias),
                                    _ptr(residual), 0 if residual is None else _rows(residual)[2], int(relu),
-                                   int(accumulate), 0, _ptr(stats), _stream()))
+                                   int(accumulate), int(out.dtype == torch.bfloat16), _ptr(stats), _stream()))
     return out
 
 
@@ -270,6 +292,8 @@ def conv2d_wgrad_nhwc(dy, x, *, kh, kw, stride=1, dil=1, pad=0, dw_out=None, spl
     _, Ho, Wo, Cout = dy.shape
     dh, dw = taps if taps is not None else conv_taps(kh, kw, dil, pad)
     ntaps = len(dh)
+    _ensure_gemm_workspace(x.device)
+    assert dy.dtype == x.dtype
     if dw_out is None:
         dw_out = torch.zeros(Cout, ntaps * Cin, device=x.device)
     _, dhp = _iarr(dh)
@@ -292,12 +316,30 @@ def _rows(t):
     return M, C, ld
 
 
+def _sdt(t):
+    """storage dtype code of the C-ABI: 0 = fp32, 1 = bf16"""
+    if t.dtype == torch.float32:
+        return 0
+    assert t.dtype == torch.bfloat16, "activations are fp32 or bf16"
+    return 1
+
+
 def affine_act(x, scale, shift, relu=True, out=None):
     M, C, ldx = _rows(x)
     if out is None:
-        out = torch.empty(x.shape, device=x.device)
+        out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    assert out.dtype == x.dtype
     check(lib().sniper_affine_act(_ptr(x), ldx, _ptr(scale), _ptr(shift), _ptr(out), _rows(out)[2], M, C, int(relu),
-                                  _stream()))
+                                  _sdt(x), _stream()))
+    return out
+
+
+def cast_rows(x, dtype=None, out=None):
+    """out[M,C] = cast(x[M,C]) between fp32 and bf16; x / out may be channel slices (row-strided views)."""
+    M, C, ldx = _rows(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=dtype)
+    check(lib().sniper_cast_rows(_ptr(x), ldx, _sdt(x), _ptr(out), _rows(out)[2], _sdt(out), M, C, _stream()))
     return out
 
 
@@ -370,7 +412,7 @@ def bn_stats(x, bn, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=True)
     check(lib().sniper_bn_stats(_ptr(x), ldx, M, C, _ptr(bn.gamma), _ptr(bn.beta), float(eps), float(momentum),
                                 int(fix_gamma), _ptr(bn.moving_mean if update_moving else None),
                                 _ptr(bn.moving_var if update_moving else None), _ptr(bn.sums), _ptr(bn.mean),
-                                _ptr(bn.invstd), _ptr(bn.scale), _ptr(bn.shift), _stream()))
+                                _ptr(bn.invstd), _ptr(bn.scale), _ptr(bn.shift), _sdt(x), _stream()))
 
 
 def bn_finalize(bn, M, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=True):
@@ -391,11 +433,12 @@ def bn_relu_bwd(x, dy, bn, add=None, out=None, defer=False):
     defer=True leaves (s1, s2) in bn.sums for one bn_param_grad_batched call at the end of the backward pass."""
     M, C, ldx = _rows(x)
     if out is None:
-        out = torch.empty(x.shape, device=x.device)
+        out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    assert dy.dtype == x.dtype and out.dtype == x.dtype and (add is None or add.dtype == x.dtype)
     check(lib().sniper_bn_relu_bwd(_ptr(x), ldx, _ptr(dy), _rows(dy)[2], _ptr(bn.scale), _ptr(bn.shift), _ptr(bn.mean),
                                    _ptr(bn.invstd), _ptr(bn.sums), _ptr(add), 0 if add is None else _rows(add)[2],
                                    _ptr(out), _rows(out)[2], None if defer else _ptr(bn.dgamma),
-                                   None if defer else _ptr(bn.dbeta), M, C, _stream()))
+                                   None if defer else _ptr(bn.dbeta), M, C, _sdt(x), _stream()))
     return out
 
 
@@ -412,25 +455,26 @@ def affine_relu_bwd(x, dy, scale, shift, add=None, relu=True, out=None):
 def relu_bwd(y, dy, out=None):
     M, C, ldy = _rows(y)
     if out is None:
-        out = torch.empty(y.shape, device=y.device)
-    check(lib().sniper_relu_bwd(_ptr(y), ldy, _ptr(dy), _rows(dy)[2], _ptr(out), _rows(out)[2], M, C, _stream()))
+        out = torch.empty(y.shape, device=y.device, dtype=y.dtype)
+    assert dy.dtype == y.dtype and out.dtype == y.dtype
+    check(lib().sniper_relu_bwd(_ptr(y), ldy, _ptr(dy), _rows(dy)[2], _ptr(out), _rows(out)[2], M, C, _sdt(y), _stream()))
     return out
 
 
 def maxpool3x3s2(x):
     NB, H, W, C = x.shape
-    y = torch.empty(NB, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, device=x.device)
-    check(lib().sniper_maxpool3x3s2_nhwc(_ptr(x), _ptr(y), NB, H, W, C, _stream()))
+    y = torch.empty(NB, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, device=x.device, dtype=x.dtype)
+    check(lib().sniper_maxpool3x3s2_nhwc(_ptr(x), _ptr(y), NB, H, W, C, _sdt(x), _stream()))
     return y
 
 
-def stem_conv(x_nchw, w, in_scale, in_shift, out_scale, out_shift):
-    """bn_data -> conv0 7x7/2 pad 3 -> bn0 -> relu; NCHW fp32 in, NHWC out.  w: [64,7,7,3]."""
+def stem_conv(x_nchw, w, in_scale, in_shift, out_scale, out_shift, out_dtype=torch.float32):
+    """bn_data -> conv0 7x7/2 pad 3 -> bn0 -> relu; NCHW fp32 in, NHWC out (fp32 or bf16).  w: [64,7,7,3]."""
     NB, C, H, W = x_nchw.shape
     assert C == 3 and w.shape == (64, 7, 7, 3)
-    y = torch.empty(NB, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64, device=x_nchw.device)
+    y = torch.empty(NB, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 64, device=x_nchw.device, dtype=out_dtype)
     check(lib().sniper_stem_conv(_ptr(x_nchw), _ptr(w), _ptr(in_scale), _ptr(in_shift), _ptr(out_scale),
-                                 _ptr(out_shift), _ptr(y), NB, H, W, _stream()))
+                                 _ptr(out_shift), _ptr(y), NB, H, W, _sdt(y), _stream()))
     return y
 
 
@@ -444,11 +488,13 @@ def weight_transpose(w, Cout, T, Cin, sel_dev, out=None):
 
 
 def weight_transpose_jobs(jobs, device):
-    """jobs: list of (w, wt, sel_dev, Cout, T, Cin).  Returns the device job table for weight_transpose_batched."""
+    """jobs: list of (w fp32, wt fp32|bf16, sel_dev, Cout, T, Cin).  Returns the device job table for
+    weight_transpose_batched."""
     rows, b0 = [], 0
     for w, wt, sel, Cout, T, Cin in jobs:
         Tsel = sel.numel()
-        rows.append([w.data_ptr(), wt.data_ptr(), sel.data_ptr(), Cout, T, Cin, Tsel, b0])
+        assert w.dtype == torch.float32
+        rows.append([w.data_ptr(), wt.data_ptr(), sel.data_ptr(), Cout, T, Cin, Tsel, b0, _sdt(wt)])
         b0 += ((Cin + 31) // 32) * ((Cout + 31) // 32) * Tsel
     return torch.tensor(rows, dtype=torch.int64, device=device), len(rows), b0
 
@@ -527,21 +573,24 @@ def deform_im2col(x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroups=4, o
     Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     if out is None:
-        out = torch.empty(NB * Ho * Wo, kh * kw * C, device=x.device)
-    check(lib().sniper_deform_im2col(_ptr(_f32(x)), _ptr(offset), NB, H, W, C, kh, kw, stride, dil, pad, dgroups,
-                                     offset.stride(2), _ptr(out), _stream()))
+        out = torch.empty(NB * Ho * Wo, kh * kw * C, device=x.device, dtype=x.dtype)
+    assert x.is_contiguous() and offset.dtype == torch.float32 and out.dtype == x.dtype
+    check(lib().sniper_deform_im2col(_ptr(x), _ptr(offset), NB, H, W, C, kh, kw, stride, dil, pad, dgroups,
+                                     offset.stride(2), _ptr(out), _sdt(x), _stream()))
     return out
 
 
 def deform_col2im(dcol, x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroups=4, dx=None, doffset=None):
-    """Transposes of deform_im2col: dx (accumulated) and doffset (deformable_im2col.cuh:317-360, 419-480)."""
+    """Transposes of deform_im2col: dx (accumulated, always fp32) and doffset (fp32)
+    (deformable_im2col.cuh:317-360, 419-480).  dcol / x: fp32 or bf16."""
     NB, H, W, C = x.shape
     if dx is None:
-        dx = torch.zeros_like(x)
+        dx = torch.zeros(x.shape, device=x.device)
     if doffset is None:
         doffset = torch.zeros_like(offset)
+    assert dcol.dtype == x.dtype and dx.dtype == torch.float32 and doffset.dtype == torch.float32
     check(lib().sniper_deform_col2im(_ptr(dcol), _ptr(x), _ptr(offset), NB, H, W, C, kh, kw, stride, dil, pad, dgroups,
-                                     offset.stride(2), _ptr(dx), _ptr(doffset), _stream()))
+                                     offset.stride(2), _ptr(dx), _ptr(doffset), _sdt(x), _stream()))
     return dx, doffset
 
 

@@ -47,7 +47,7 @@ def test_gemm_epilogue_and_bf16():
     ref2 = ref + a.double() @ b.double().t()
     assert (c2.double() - ref2).abs().max().item() <= _tol(K, a, b, a.dtype) * 2.5
     ab, bb = a.bfloat16(), b.bfloat16()
-    c3 = ops.gemm_nt(ab, bb)
+    c3 = ops.gemm_nt(ab, bb, out_dtype=torch.float32)
     ref3 = ab.double() @ bb.double().t()
     assert (c3.double() - ref3).abs().max().item() <= 1e-2  # inputs already bf16: only fp32 accumulation error
 

@@ -49,14 +49,28 @@ def _build(B, seed, bf16=False):
     for bn in net._named_bns():          # non-trivial affine parameters / moving statistics everywhere
         if bn.name == "bn_data":
             continue
-        bn.st.gamma.copy_(torch.empty(bn.C, device="cuda").uniform_(0.8, 1.2, generator=g))
-        bn.st.beta.copy_(torch.empty(bn.C, device="cuda").normal_(0, 0.1, generator=g))
+        # bn3 scales the residual branch (a3 = relu(bn3(.)) feeds conv3, whose output is added to the shortcut): a
+        # small gamma makes every unit a near-identity map, as in a trained network.  With gamma ~ 1 a He-initialised
+        # ResNet-101 is chaotic -- it amplifies ANY perturbation by ~15 % per residual unit (measured: two float64
+        # evaluations that differ only by TF32 operand truncation are 9 % apart at c4, 30 % at c5, and their parameter
+        # gradients are uncorrelated), so no tolerance could separate a wiring error from rounding.
+        lo, hi, sd = (0.15, 0.25, 0.02) if bn.name.endswith("_bn3") else (0.8, 1.2, 0.1)
+        bn.st.gamma.copy_(torch.empty(bn.C, device="cuda").uniform_(lo, hi, generator=g))
+        bn.st.beta.copy_(torch.empty(bn.C, device="cuda").normal_(0, sd, generator=g))
         if bn.frozen:
             bn.st.moving_mean.copy_(torch.empty(bn.C, device="cuda").normal_(0, 0.1, generator=g))
             bn.st.moving_var.copy_(torch.empty(bn.C, device="cuda").uniform_(0.6, 1.6, generator=g))
             ops.bn_frozen(bn.st, cfg.bn_eps)
     batch = synth_batch.make_batch(B, seed=7, device="cuda")
     return cfg, net, batch
+
+
+# Gradient tolerances are set by ReLU: a forward deviation eps (relative to the activation scale) flips the sign of a
+# fraction ~0.4*eps of the pre-activations, and every flipped unit changes its gradient by 100 %, so gradients agree
+# only to ~sqrt(0.4*eps) per ReLU layer (eps = 4e-3 -> 4 %), accumulating over the ~100 ReLUs below the heads.  A wiring
+# error gives relative errors >= 0.7 (uncorrelated gradients) and norm ratios far from 1.
+TOL_TF32 = dict(act=1e-2, loss=5e-3, grad=0.25, grad_median=0.15, head=8e-2, norm=0.05)
+TOL_BF16 = dict(act=5e-2, loss=3e-2, grad=0.5, grad_median=0.3, head=0.2, norm=0.1)
 
 
 def _tf32_trunc(x):
@@ -106,9 +120,10 @@ def _reference(net, cfg, batch, prob_nchw, bbox_nchw, mode):
     return P, ref, res
 
 
-def test_training_graph_matches_float64_reference():
+@pytest.mark.parametrize("bf16", [False, True])
+def test_training_graph_matches_float64_reference(bf16):
     import torch
-    cfg, net, batch = _build(2, seed=5)
+    cfg, net, batch = _build(2, seed=5, bf16=bf16)
     out = net.forward_backward(batch)
     torch.cuda.synchronize()
     A = cfg.num_anchors
@@ -118,14 +133,14 @@ def test_training_graph_matches_float64_reference():
     ls = out["losses"][:4].double().cpu()
 
     # ================= sharp: float64 with TF32-truncated contraction operands
-    P, ref, res = _reference(net, cfg, batch, prob, bbox, "tf32")
+    P, ref, res = _reference(net, cfg, batch, prob, bbox, "bf16" if bf16 else "tf32")
     # ---- discrete outputs: bit-exact against the oracle on the same RPN outputs
     assert out["rois"].cpu().numpy().tobytes() == res["rois"].tobytes()
     assert np.array_equal(out["label"].cpu().numpy(), res["label"].reshape(-1))
     assert int((res["label"] > 0).sum()) > 0, "test batch yields no foreground roi"
     acts = dict(cat=_rel(out["cat"].permute(0, 3, 1, 2), ref["relu1"]), rpn_prob=_rel(prob, ref["rpn_cls_prob"]),
                 rpn_bbox=_rel(bbox, ref["rpn_bbox_pred"]), cls_prob=_rel(out["cls_prob"], ref["cls_prob"]))
-    print("activation errors (tf32 reference):", {k: "%.2e" % v for k, v in acts.items()})
+    print("activation errors (%s reference):" % ("bf16" if bf16 else "tf32"), {k: "%.2e" % v for k, v in acts.items()})
     lr = ref["loss_sums"].cpu()
     print("losses ours", ls.tolist(), "tf32-ref", lr.tolist())
     rows = []
@@ -146,13 +161,17 @@ def test_training_graph_matches_float64_reference():
     med = rows[len(rows) // 2][0]
     print("median gradient error %.2e over %d tensors" % (med, len(rows)))
     assert len(rows) == 297
+    tol = TOL_BF16 if getattr(cfg, "bf16", False) else TOL_TF32
     for k, v in acts.items():
-        assert v < 2e-3, (k, v)
+        assert v < tol["act"], (k, v)
     for i in range(4):
-        assert abs(ls[i] - lr[i]) <= 1e-3 * abs(lr[i]) + 1e-4, (i, ls[i].item(), lr[i].item())
-    for r, name, nrm, _ in rows:
-        assert r < 2e-2 or nrm < 1e-9, (name, r, nrm)
-    assert med < 3e-3
+        assert abs(ls[i] - lr[i]) <= tol["loss"] * abs(lr[i]) + 1e-4, (i, ls[i].item(), lr[i].item())
+    for r, name, nrm, ours_n in rows:
+        assert r < tol["grad"] or nrm < 1e-9, (name, r, nrm)
+        assert abs(ours_n / nrm - 1) < tol["norm"] or nrm < 1e-9, (name, ours_n, nrm)
+        if "stage" not in name:
+            assert r < tol["head"], (name, r)
+    assert med < tol["grad_median"]
 
     # ================= loose: real arithmetic (what TF32 costs on this network)
     P2, ref2, _ = _reference(net, cfg, batch, prob, bbox, "exact")
