@@ -64,10 +64,51 @@ struct RowBlock {
   dim3 grid;
 };
 
+// Vector width per thread: 16 bytes of storage either way = 4 fp32 or 8 bf16 channels.
+template <typename T> struct VT;
+// U = independent 16-byte loads per operand in flight per thread (bf16 carries twice the channels per load, so half
+// the unroll keeps the register footprint -- and two resident blocks per SM -- of the fp32 instantiation)
+template <> struct VT<float> { static constexpr int N = 4, U = 4; };
+template <> struct VT<bf16> { static constexpr int N = 8, U = 2; };
+
+template <int N>
+__device__ __forceinline__ void ldc(const float* p, float (&v)[N]) {   // N per-channel constants (fp32)
+#pragma unroll
+  for (int k = 0; k < N; k += 4) {
+    const float4 t = ld4(p + k);
+    v[k] = t.x; v[k + 1] = t.y; v[k + 2] = t.z; v[k + 3] = t.w;
+  }
+}
+__device__ __forceinline__ void ldv(const float* p, float (&v)[4]) {
+  const float4 t = ld4(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ldv(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+    v[2 * k] = f.x;
+    v[2 * k + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void stv(float* p, const float (&v)[4]) { st4(p, make_float4(v[0], v[1], v[2], v[3])); }
+__device__ __forceinline__ void stv(bf16* p, const float (&v)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+    w[k] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <int VEC>
 __device__ __forceinline__ bool rb_setup(int lx_shift, int C, int rows_per_block, long M, int& c, int& ry, int& RY,
                                          long& r0, long& r1) {
   const int lx = 1 << lx_shift;
-  c = ((int)blockIdx.y * lx + ((int)threadIdx.x & (lx - 1))) * 4;
+  c = ((int)blockIdx.y * lx + ((int)threadIdx.x & (lx - 1))) * VEC;
   ry = (int)threadIdx.x >> lx_shift;
   RY = 256 >> lx_shift;
   r0 = (long)blockIdx.x * rows_per_block;
@@ -82,23 +123,29 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x
                                                           const float* __restrict__ shift, T* __restrict__ y,
                                                           long ldy, long M, int C, int relu, int lx_shift,
                                                           int rows_per_block) {
+  constexpr int N = VT<T>::N, KU = VT<T>::U;
   int c, ry, RY;
   long r0, r1;
-  if (!rb_setup(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1)) return;
-  const float4 s = ld4(scale + c), t = ld4(shift + c);
-  for (long r = r0 + ry; r < r1; r += (long)kUnroll * RY) {
-    float4 v[kUnroll];
+  if (!rb_setup<N>(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1)) return;
+  float s[N], t[N];
+  ldc<N>(scale + c, s);
+  ldc<N>(shift + c, t);
+  for (long r = r0 + ry; r < r1; r += (long)KU * RY) {
+    float v[KU][N];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-      if (r + (long)u * RY < r1) v[u] = ld4(x + (r + (long)u * RY) * ldx + c);
+    for (int u = 0; u < KU; ++u)
+      if (r + (long)u * RY < r1) ldv(x + (r + (long)u * RY) * ldx + c, v[u]);
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < KU; ++u) {
       const long rr = r + (long)u * RY;
       if (rr >= r1) break;
-      float4 o = v[u];
-      o.x = fmaf(o.x, s.x, t.x); o.y = fmaf(o.y, s.y, t.y); o.z = fmaf(o.z, s.z, t.z); o.w = fmaf(o.w, s.w, t.w);
-      if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-      st4(y + rr * ldy + c, o);
+      float o[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        o[k] = fmaf(v[u][k], s[k], t[k]);
+        if (relu) o[k] = fmaxf(o[k], 0.f);
+      }
+      stv(y + rr * ldy + c, o);
     }
   }
 }
@@ -113,60 +160,61 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
                                                       long M, int C, int lx_shift, int rows_per_block,
                                                       double* __restrict__ sums) {
+  constexpr int N = VT<T>::N, KU = VT<T>::U;
   int c, ry, RY;
   long r0, r1;
-  const bool cok = rb_setup(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1);
-  float4 a = make_float4(0, 0, 0, 0), b = make_float4(0, 0, 0, 0);
-  if (cok) {
-    float4 sc, sh, mu, is;
-    if (MODE == 1) { sc = ld4(scale + c); sh = ld4(shift + c); mu = ld4(mean + c); is = ld4(invstd + c); }
-    for (long r = r0 + ry; r < r1; r += (long)kUnroll * RY) {
-      float4 v[kUnroll], g[kUnroll];
+  const bool cok = rb_setup<N>(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1);
+  float a[N], b[N];
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+  for (int k = 0; k < N; ++k) { a[k] = 0.f; b[k] = 0.f; }
+  if (cok) {
+    float sc[N], sh[N], mu[N], is[N];
+    if (MODE == 1) { ldc<N>(scale + c, sc); ldc<N>(shift + c, sh); ldc<N>(mean + c, mu); ldc<N>(invstd + c, is); }
+    for (long r = r0 + ry; r < r1; r += (long)KU * RY) {
+      float v[KU][N], g[KU][N];
+#pragma unroll
+      for (int u = 0; u < KU; ++u) {
         const long rr = r + (long)u * RY;
         if (rr < r1) {
-          v[u] = ld4(x + rr * ldx + c);
-          if (MODE == 1) g[u] = ld4(dy + rr * lddy + c);
+          ldv(x + rr * ldx + c, v[u]);
+          if (MODE == 1) ldv(dy + rr * lddy + c, g[u]);
         } else {
-          v[u] = make_float4(0, 0, 0, 0);           // contributes nothing in either mode (MODE 1: g = 0)
-          if (MODE == 1) g[u] = make_float4(0, 0, 0, 0);
+#pragma unroll
+          for (int k = 0; k < N; ++k) { v[u][k] = 0.f; if (MODE == 1) g[u][k] = 0.f; }   // contributes nothing
         }
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
-        if (MODE == 0) {
-          a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w;
-          b.x = fmaf(v[u].x, v[u].x, b.x); b.y = fmaf(v[u].y, v[u].y, b.y);
-          b.z = fmaf(v[u].z, v[u].z, b.z); b.w = fmaf(v[u].w, v[u].w, b.w);
-        } else {
-          float4 gg = g[u];
-          gg.x = fmaf(v[u].x, sc.x, sh.x) > 0.f ? gg.x : 0.f;
-          gg.y = fmaf(v[u].y, sc.y, sh.y) > 0.f ? gg.y : 0.f;
-          gg.z = fmaf(v[u].z, sc.z, sh.z) > 0.f ? gg.z : 0.f;
-          gg.w = fmaf(v[u].w, sc.w, sh.w) > 0.f ? gg.w : 0.f;
-          a.x += gg.x; a.y += gg.y; a.z += gg.z; a.w += gg.w;
-          b.x = fmaf(gg.x, (v[u].x - mu.x) * is.x, b.x); b.y = fmaf(gg.y, (v[u].y - mu.y) * is.y, b.y);
-          b.z = fmaf(gg.z, (v[u].z - mu.z) * is.z, b.z); b.w = fmaf(gg.w, (v[u].w - mu.w) * is.w, b.w);
+      for (int u = 0; u < KU; ++u) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+          if (MODE == 0) {
+            a[k] += v[u][k];
+            b[k] = fmaf(v[u][k], v[u][k], b[k]);
+          } else {
+            const float gg = fmaf(v[u][k], sc[k], sh[k]) > 0.f ? g[u][k] : 0.f;
+            a[k] += gg;
+            b[k] = fmaf(gg, (v[u][k] - mu[k]) * is[k], b[k]);
+          }
         }
       }
     }
   }
-  __shared__ __align__(16) float4 sa[256], sb[256];
-  sa[threadIdx.x] = a;
-  sb[threadIdx.x] = b;
+  __shared__ float sa[256][N + 1], sb[256][N + 1];
+#pragma unroll
+  for (int k = 0; k < N; ++k) { sa[threadIdx.x][k] = a[k]; sb[threadIdx.x][k] = b[k]; }
   __syncthreads();
   if (ry == 0 && cok) {
     const int lx = 1 << lx_shift;
-    double ax = 0, ay = 0, az = 0, aw = 0, bx = 0, by = 0, bz = 0, bw = 0;
-    for (int k = 0; k < RY; ++k) {
-      const float4 p = sa[k * lx + threadIdx.x], q = sb[k * lx + threadIdx.x];
-      ax += p.x; ay += p.y; az += p.z; aw += p.w;
-      bx += q.x; by += q.y; bz += q.z; bw += q.w;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      double ax = 0, bx = 0;
+      for (int j = 0; j < RY; ++j) {
+        ax += sa[j * lx + threadIdx.x][k];
+        bx += sb[j * lx + threadIdx.x][k];
+      }
+      atomicAdd(sums + c + k, ax);
+      atomicAdd(sums + C + c + k, bx);
     }
-    atomicAdd(sums + c, ax); atomicAdd(sums + c + 1, ay); atomicAdd(sums + c + 2, az); atomicAdd(sums + c + 3, aw);
-    atomicAdd(sums + C + c, bx); atomicAdd(sums + C + c + 1, by); atomicAdd(sums + C + c + 2, bz);
-    atomicAdd(sums + C + c + 3, bw);
   }
 }
 
@@ -219,44 +267,42 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const T* __restr
                                                                  const T* __restrict__ add, long ldadd,
                                                                  T* __restrict__ dx, long lddx, long M, int C,
                                                                  int lx_shift, int rows_per_block) {
+  constexpr int N = VT<T>::N, KU = VT<T>::U;
   int c, ry, RY;
   long r0, r1;
-  if (!rb_setup(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1)) return;
+  if (!rb_setup<N>(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1)) return;
   const float invM = 1.0f / (float)M;
-  const float4 sc4 = ld4(scale + c), sh4 = ld4(shift + c), mu4 = ld4(mean + c), is4 = ld4(invstd + c);
-  const float scv[4] = {sc4.x, sc4.y, sc4.z, sc4.w}, shv[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
-  const float muv[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, isv[4] = {is4.x, is4.y, is4.z, is4.w};
-  float s1[4], s2[4];
+  float scv[N], shv[N], muv[N], isv[N], s1[N], s2[N];
+  ldc<N>(scale + c, scv); ldc<N>(shift + c, shv); ldc<N>(mean + c, muv); ldc<N>(invstd + c, isv);
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
+  for (int k = 0; k < N; ++k) {
     s1[k] = (float)sums[c + k] * invM;
     s2[k] = (float)sums[C + c + k] * invM;
   }
-  for (long r = r0 + ry; r < r1; r += (long)kUnroll * RY) {
-    float4 v[kUnroll], g[kUnroll], ad[kUnroll];
+  for (long r = r0 + ry; r < r1; r += (long)KU * RY) {
+    float v[KU][N], g[KU][N], ad[KU][N];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < KU; ++u) {
       const long rr = r + (long)u * RY;
       if (rr < r1) {
-        v[u] = ld4(x + rr * ldx + c);
-        g[u] = ld4(dy + rr * lddy + c);
-        if (add) ad[u] = ld4(add + rr * ldadd + c);
+        ldv(x + rr * ldx + c, v[u]);
+        ldv(dy + rr * lddy + c, g[u]);
+        if (add) ldv(add + rr * ldadd + c, ad[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < KU; ++u) {
       const long rr = r + (long)u * RY;
       if (rr >= r1) break;
-      const float vv[4] = {v[u].x, v[u].y, v[u].z, v[u].w}, gg[4] = {g[u].x, g[u].y, g[u].z, g[u].w};
-      float o[4];
+      float o[N];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float gk = fmaf(vv[k], scv[k], shv[k]) > 0.f ? gg[k] : 0.f;
-        const float xhat = (vv[k] - muv[k]) * isv[k];
+      for (int k = 0; k < N; ++k) {
+        const float gk = fmaf(v[u][k], scv[k], shv[k]) > 0.f ? g[u][k] : 0.f;
+        const float xhat = (v[u][k] - muv[k]) * isv[k];
         o[k] = scv[k] * (gk - s1[k] - xhat * s2[k]);
+        if (add) o[k] += ad[u][k];
       }
-      if (add) { o[0] += ad[u].x; o[1] += ad[u].y; o[2] += ad[u].z; o[3] += ad[u].w; }
-      st4(dx + rr * lddx + c, make_float4(o[0], o[1], o[2], o[3]));
+      stv(dx + rr * lddx + c, o);
     }
   }
 }
@@ -598,12 +644,13 @@ int ew_grid(long work) {
 }
 
 // Row-blocked launch geometry: ~8 blocks per SM, rows per block a multiple of kUnroll * RY.
-RowBlock row_block(long M, int C) {
+RowBlock row_block(long M, int C, int vec = 4) {
   RowBlock rb;
-  const int c4 = C / 4;
-  rb.lx_shift = c4 >= 32 ? 5 : 4;
+  const int kUnroll = vec == 8 ? 2 : 4;         // VT<T>::U
+  const int cv = C / vec;                       // vectors per row
+  rb.lx_shift = cv >= 32 ? 5 : (cv >= 16 ? 4 : 3);
   const int lx = 1 << rb.lx_shift, RY = 256 >> rb.lx_shift;
-  const int by = sn::div_up(c4, lx);
+  const int by = sn::div_up(cv, lx);
   const int step = kUnroll * RY;
   long rpb = sn::div_up(M * by, (long)sn::kNumSMs * 8);
   rpb = (rpb + step - 1) / step * step;
@@ -622,7 +669,8 @@ int sniper_affine_act(const void* x, long ldx, const float* scale, const float* 
                       int C, int relu, int dtype, void* stream) {
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "affine_act: C/ld must be multiples of 4");
   SN_CHECK(dtype == 0 || dtype == 1, "affine_act: dtype must be 0 (fp32) or 1 (bf16)");
-  const RowBlock rb = row_block(M, C);
+  SN_CHECK(dtype == 0 || (C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0), "affine_act: bf16 needs C/ld multiples of 8");
+  const RowBlock rb = row_block(M, C, dtype == 0 ? 4 : 8);
   if (dtype == 0)
     affine_act_kernel<float><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
         static_cast<const float*>(x), ldx, scale, shift, static_cast<float*>(y), ldy, M, C, relu, rb.lx_shift,
@@ -642,7 +690,8 @@ int sniper_bn_stats(const void* x, long ldx, long M, int C, const float* gamma, 
                     float* invstd, float* scale, float* shift, int dtype, void* stream) {
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0, "bn_stats: C/ld must be multiples of 4");
   SN_CHECK(dtype == 0 || dtype == 1, "bn_stats: dtype must be 0 (fp32) or 1 (bf16)");
-  const RowBlock rb = row_block(M, C);
+  SN_CHECK(dtype == 0 || (C % 8 == 0 && ldx % 8 == 0), "bn_stats: bf16 needs C/ld multiples of 8");
+  const RowBlock rb = row_block(M, C, dtype == 0 ? 4 : 8);
   if (dtype == 0)
     colsum_kernel<0, float><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
         static_cast<const float*>(x), ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, M, C, rb.lx_shift,
@@ -684,7 +733,9 @@ int sniper_bn_relu_bwd(const void* x, long ldx, const void* dy, long lddy, const
                        long lddx, float* dgamma, float* dbeta, long M, int C, int dtype, void* stream) {
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "bn_relu_bwd: C/ld must be multiples of 4");
   SN_CHECK(dtype == 0 || dtype == 1, "bn_relu_bwd: dtype must be 0 (fp32) or 1 (bf16)");
-  const RowBlock rb = row_block(M, C);
+  SN_CHECK(dtype == 0 || (C % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && ldadd % 8 == 0),
+           "bn_relu_bwd: bf16 needs C/ld multiples of 8");
+  const RowBlock rb = row_block(M, C, dtype == 0 ? 4 : 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == 0) {
     colsum_kernel<1, float><<<rb.grid, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<const float*>(dy),

@@ -145,6 +145,7 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read3() { asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -586,11 +587,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           const int n0 = col_base + c;
           if (n0 >= p.N || !tile_ok) continue;       // warp-uniform
-          uint8_t* stg = stg_base + (size_t)sbuf * 4096;
+          // a bf16 chunk needs 2 KB: every 4 KB fp32 staging slot holds two of them (2 or 4 bulk stores in flight)
+          uint8_t* stg = stg_base + (size_t)sbuf * 2048;
           if (lane == 0) {
-            if (p.stg_bufs == 2) bulk_wait_read1(); else bulk_wait_read0();
+            if (p.stg_bufs == 2) bulk_wait_read3(); else bulk_wait_read1();
           }
-          if (p.stg_bufs == 2) sbuf ^= 1;
+          sbuf = (sbuf + 1) & (2 * p.stg_bufs - 1);
           __syncwarp();
           if (has_res) {
 #pragma unroll

@@ -162,6 +162,23 @@ class Trainer:
             self.net.update()
         return self.out
 
+    # ---- public end-to-end step from the iterator's raw batch (uint8 source rectangles + chip tables)
+    def step_raw(self, raw, input_stage, lr=None):
+        """One training step on a `iterator.RawBatch`: H2D of the raw bytes, GPU input stage (resize / mean / flip,
+        anchor matching, label subsampling), forward + backward + all-reduce + update, D2H of the losses."""
+        batch = input_stage.run(raw)
+        if self.static is None:
+            self.static = {k: torch.empty_like(v) for k, v in batch.items()}
+        for k, v in batch.items():
+            self.static[k].copy_(v, non_blocking=True)
+        if self.g_fb is None and self.use_graph:
+            self.capture()
+        out = self.step_device(lr)
+        self.loss_host.copy_(out["losses"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return {"rpn_cls_loss": float(self.loss_host[0]), "rpn_bbox_loss": float(self.loss_host[1]),
+                "rcnn_cls_loss": float(self.loss_host[2]), "rcnn_bbox_loss": float(self.loss_host[3]), "lr": self.lr}
+
     # ---- public end-to-end step: host batch in, host losses out
     def step(self, host_batch, prefetch=None, lr=None):
         """One training step on `host_batch` (pinned host tensors) -> host loss scalars.  `prefetch`: the batch of the

@@ -6,6 +6,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sniper_b200 import ops
 
+DT = torch.bfloat16 if os.environ.get("GT_DTYPE") == "bf16" else torch.float32      # operand / output storage
 CASES = [("gemm", 20480, 1024, 256), ("gemmres", 20480, 1024, 256), ("gemm", 327680, 256, 64), ("gemm", 81920, 512, 128),
          ("gemm", 81920, 128, 512), ("gemm", 20480, 256, 1024), ("conv3x3", 20, 32, 32, 256, 256)]
 SETTINGS = [{"SNIPER_GEMM_2SM": "0"}, {"SNIPER_GEMM_2SM": "1"}]
@@ -29,11 +30,11 @@ for case in CASES:
     if case[0] in ("gemm", "gemmres"):
         _, M, N, K = case
         nbuf = max(2, int(300e6 // (4 * (M * K + M * N))) + 1)
-        A = [torch.randn(M, K, device="cuda") for _ in range(nbuf)]
-        B = torch.randn(N, K, device="cuda")
-        C = [torch.empty(M, N, device="cuda") for _ in range(nbuf)]
+        A = [torch.randn(M, K, device="cuda").to(DT) for _ in range(nbuf)]
+        B = torch.randn(N, K, device="cuda").to(DT)
+        C = [torch.empty(M, N, device="cuda", dtype=DT) for _ in range(nbuf)]
         if case[0] == "gemmres":
-            R = [torch.randn(M, N, device="cuda") for _ in range(nbuf)]
+            R = [torch.randn(M, N, device="cuda").to(DT) for _ in range(nbuf)]
             stats_buf = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
             fn = lambda i: ops.gemm_nt(A[i % nbuf], B, out=C[i % nbuf], residual=R[(i + 1) % nbuf], stats=stats_buf)
         else:
@@ -42,9 +43,9 @@ for case in CASES:
     else:
         _, NB, H, W, Cin, Cout = case
         nbuf = max(2, int(300e6 // (4 * NB * H * W * (Cin + Cout))) + 1)
-        X = [torch.randn(NB, H, W, Cin, device="cuda") for _ in range(nbuf)]
-        Wt = torch.randn(Cout, 9 * Cin, device="cuda") * 0.02
-        Y = [torch.empty(NB, H, W, Cout, device="cuda") for _ in range(nbuf)]
+        X = [torch.randn(NB, H, W, Cin, device="cuda").to(DT) for _ in range(nbuf)]
+        Wt = (torch.randn(Cout, 9 * Cin, device="cuda") * 0.02).to(DT)
+        Y = [torch.empty(NB, H, W, Cout, device="cuda", dtype=DT) for _ in range(nbuf)]
         fn = lambda i: ops.conv2d_nhwc(X[i % nbuf], Wt, kh=3, kw=3, pad=1, out=Y[i % nbuf])
         flop = 2.0 * NB * H * W * Cout * 9 * Cin
     out = []
