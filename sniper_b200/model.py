@@ -101,15 +101,19 @@ class ParamStore:
         self.views = {}
         self.grads = {}
 
+    bucket = 0      # set by the model while it registers parameters: gradients of one bucket are complete at the same
+                    # point of the backward pass and form one contiguous all-reduce (0 = heads + stage 4, 1 = stage 3, ...)
+
     def add(self, name, shape, lr_mult=1.0):
         wd_mult = 1.0 if (name.endswith("_weight") or name.endswith("_gamma")) else 0.0
-        self.specs.append((name, tuple(shape), (lr_mult, wd_mult)))
+        self.specs.append((name, tuple(shape), (self.bucket, lr_mult, wd_mult)))
 
     def finalize(self, device, lowp=False):
         """lowp: also keep a bf16 copy of the whole buffer (`w16`, same offsets) for the mixed-precision backbone."""
-        groups = sorted(set(g for _, _, g in self.specs))
+        groups = sorted(set(g for _, _, g in self.specs))      # bucket-major: each bucket is one contiguous range
         off = 0
         self.segments = []
+        self.bucket_ranges = []
         layout = {}
         for g in groups:
             start = off
@@ -119,7 +123,12 @@ class ParamStore:
                 n = int(np.prod(shape))
                 layout[name] = (off, shape)
                 off += (n + 3) // 4 * 4          # keep every tensor 16-byte aligned
-            self.segments.append((start, off, g))
+            self.segments.append((start, off, g[1:]))
+            b = g[0]
+            while len(self.bucket_ranges) <= b:
+                self.bucket_ranges.append([start, start])
+            self.bucket_ranges[b][0] = min(self.bucket_ranges[b][0], start) if self.bucket_ranges[b][1] > self.bucket_ranges[b][0] else start
+            self.bucket_ranges[b][1] = off
         self.total = off
         self.w = torch.zeros(off, device=device)
         self.g = torch.zeros(off, device=device)
@@ -495,6 +504,8 @@ class SniperResNet101:
             stage = i + 1
             cout = fl[i + 1]
             frozen = (stage == 1)
+            # gradient buckets in the order the backward pass completes them: heads + stage 4, stage 3, stage 2
+            P.bucket = {4: 0, 3: 1, 2: 2}.get(stage, 2)
             deform = (stage == 4)
             stride = 1 if stage in (1, 4) else 2
             for j in range(n):
@@ -504,6 +515,7 @@ class SniperResNet101:
                 self.units.append(u)
             cin = cout
         A = cfg.num_anchors
+        P.bucket = 0
         # ---- heads (get_rpn :147-155, conv_new_1 :256-257, FCs :288-303)
         self.rpn_conv = Conv(P, "rpn_conv_3x3", 3072, 512, 3, 1, 1, 1, bias=True)
         # rpn_bbox_pred (4A) and rpn_cls_score (2A) fused into one 1x1 conv: rows [0,4A) | [4A,6A), padded to 128
@@ -585,8 +597,22 @@ class SniperResNet101:
         return cs
 
     # ---------------------------------------------------------------- one training step
-    def forward_backward(self, batch):
-        """batch: dict of device tensors named as MNIteratorE2E provides them (MNIteratorE2E.py:175-219):
+    def forward_backward(self, batch, on_bucket=None):
+        """One forward + backward pass; see fb_phases.  on_bucket(k): called when gradient bucket k (P.bucket_ranges[k])
+        is complete -- the eager form of the overlapped all-reduce."""
+        out = None
+        for k, out in enumerate(self.fb_phases(batch)):
+            if on_bucket is not None:
+                on_bucket(k)
+        return out
+
+    def fb_phases(self, batch):
+        """Generator form of the pass, one `yield` per completed gradient bucket (0: forward + heads + stage-4 backward,
+        1: stage-3 backward, 2: stage-2 backward), so that the trainer can capture each phase as its own CUDA graph and
+        start the bucket's all-reduce while the next phase computes.  Every phase ends with all its kernels (including the
+        weight-gradient side stream) joined on the current stream.  Yields the output dict each time.
+
+        batch: dict of device tensors named as MNIteratorE2E provides them (MNIteratorE2E.py:175-219):
         data [B,3,512,512], label [B,A*H*W], bbox_target/bbox_weight [B,4A,H,W], gt_boxes [B,100,5],
         valid_ranges [B,2], im_info [B,3].  Leaves parameter gradients in self.P.g and returns the outputs of
         the reference's Group([rpn_cls_prob, rpn_bbox_loss, cls_prob, bbox_loss, label]) (:338) as a dict."""
@@ -595,6 +621,7 @@ class SniperResNet101:
         A = cfg.num_anchors
         data = batch["data"]
         B = data.shape[0]
+        n1, n2, n3, n4 = cfg.units
         P.g.zero_()
         self.loss_buf.zero_()
         self.cnt_buf.zero_()
@@ -604,7 +631,9 @@ class SniperResNet101:
             self._wt_table = ops.weight_transpose_jobs(jobs, data.device)
             for b in self.train_bns():
                 b.defer = True
-            self._bn_table = ops.bn_param_grad_jobs([b.st for b in self.train_bns()], data.device)
+            self._bn_tables = []
+            for stage_units in (self.units[n1 + n2 + n3:], self.units[n1 + n2:n1 + n2 + n3], self.units[n1:n1 + n2]):
+                self._bn_tables.append(ops.bn_param_grad_jobs([b.st for u in stage_units for b in u.bns()], data.device))
         ops.weight_transpose_batched(self._wt_table)
 
         # ---- backbone forward
@@ -612,7 +641,6 @@ class SniperResNet101:
         x = ops.stem_conv(data, self.conv0_w, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
                           self.bn0.st.shift, out_dtype=self.act_dtype)     # the reference's Cast sits right after conv0
         x = ops.maxpool3x3s2(x)
-        n1, n2, n3, n4 = cfg.units
         Hf = data.shape[2] // cfg.feat_stride
         # Concat(c4, c5): fp32.  fp32 mode: the two producing convs write their channel slices in place.  Mixed
         # precision: c4 / c5 are bf16 tensors and the reference's Cast(relu1, float32) (:250-252) fills the slices.
@@ -699,15 +727,19 @@ class SniperResNet101:
         g, g4 = dcat[..., 1024:], dcat[..., :1024]
         if lowp:      # backward of the Cast: the backbone's activation gradients are bf16
             g, g4 = ops.cast_rows(g, torch.bfloat16), ops.cast_rows(g4, torch.bfloat16)
-        for i in range(len(self.units) - 1, n1 - 1, -1):
-            u = self.units[i]
-            g = u.bwd(g, cfg, extra_add=g4 if i == last3 + 1 else None)
-        ops.bn_param_grad_batched(self._bn_table)
-        W.join()
-        self.step_count += 1
-        return dict(rpn_cls_prob=prob, rpn_bbox_loss=self.loss_buf[1:2], cls_prob=cls_prob, bbox_loss=self.loss_buf[3:4],
-                    label=label, rois=rois, losses=self.loss_buf, rpn_head=head, cat=cat, bbox_target=bbox_target,
-                    bbox_weight=bbox_weight)
+        out = dict(rpn_cls_prob=prob, rpn_bbox_loss=self.loss_buf[1:2], cls_prob=cls_prob, bbox_loss=self.loss_buf[3:4],
+                   label=label, rois=rois, losses=self.loss_buf, rpn_head=head, cat=cat, bbox_target=bbox_target,
+                   bbox_weight=bbox_weight)
+        bounds = [len(self.units), n1 + n2 + n3, n1 + n2, n1]          # stage 4 | stage 3 | stage 2
+        for k in range(3):
+            for i in range(bounds[k] - 1, bounds[k + 1] - 1, -1):
+                u = self.units[i]
+                g = u.bwd(g, cfg, extra_add=g4 if i == last3 + 1 else None)
+            ops.bn_param_grad_batched(self._bn_tables[k])
+            W.join()
+            if k == 2:
+                self.step_count += 1
+            yield out
 
     def forward_inference(self, data, im_info, suppress_anchor_types=False):
         """get_symbol_rcnn(cfg, is_train=False) (resnet_mx_101_e2e.py:227-345 with the test branch :258-266, 321-326):

@@ -22,6 +22,8 @@ class Trainer:
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.world_size = world_size
+        self.overlap_allreduce = True     # False: one all-reduce of the whole buffer after the backward pass (A/B runs)
+        self._works = []
         self.net = model.SniperResNet101(self.cfg, device=self.device, seed=seed, deform_offset_std=deform_offset_std)
         self.use_graph = use_graph
         self.static = None
@@ -37,6 +39,8 @@ class Trainer:
         self.stage_free = [None, None]       # event: the step that consumed stage[i] has copied it out
         self.stage_owner = [None, None]      # the host batch object sitting in stage[i] (kept alive: identity match)
         self.next_stage = 0
+        import os
+        self.overlap_allreduce = os.environ.get("SNIPER_AR_OVERLAP", "1") == "1"
         # optimizer state of mxnet.optimizer.SGD that lives on the host: update count and LR schedule
         self.num_update = 0
         if scheduler == "config":
@@ -103,8 +107,27 @@ class Trainer:
         self.load(host_batch)
 
     def _allreduce(self):
+        """The whole gradient buffer in one collective (eager / warm-up path)."""
         if self.world_size > 1:
             torch.distributed.all_reduce(self.net.P.g, op=torch.distributed.ReduceOp.SUM)
+
+    def _allreduce_bucket(self, k):
+        """Starts the sum of gradient bucket k over the ranks on NCCL's own stream (it first waits for everything
+        enqueued so far on the current stream, i.e. the phase that produced the bucket) and returns at once, so the next
+        backward phase overlaps the transfer.  No 1/N: rescale_grad = 1.0 (lib/train_utils/utils.py:30,37)."""
+        if self.world_size > 1 and self.overlap_allreduce:
+            a, b = self.net.P.bucket_ranges[k]
+            self._works.append(torch.distributed.all_reduce(self.net.P.g[a:b], op=torch.distributed.ReduceOp.SUM,
+                                                            async_op=True))
+
+    def _allreduce_finish(self):
+        if self.world_size > 1:
+            if self.overlap_allreduce:
+                for w in self._works:
+                    w.wait()                      # the current stream waits for the collective
+                self._works = []
+            else:
+                self._allreduce()
 
     def _snapshot(self):
         P = self.net.P
@@ -140,11 +163,18 @@ class Trainer:
         self._restore(snap)
         if not self.use_graph:
             return
-        self.g_fb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_fb):
-            self.out = self.net.forward_backward(self.static)
+        # forward + backward as one CUDA graph per gradient bucket (model.fb_phases), sharing one memory pool: between
+        # the replays the trainer starts the bucket's all-reduce, which then runs under the next phase's kernels
+        pool = torch.cuda.graph_pool_handle()
+        self.g_fb = []
+        phases = self.net.fb_phases(self.static)
+        for _ in range(3):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self.out = next(phases)
+            self.g_fb.append(g)
         self.g_up = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_up):
+        with torch.cuda.graph(self.g_up, pool=pool):
             self.net.update()
         torch.cuda.synchronize()
 
@@ -153,12 +183,14 @@ class Trainer:
         (or `lr`) and reaches the captured update graph through the device hyper-parameter buffer."""
         self.net.set_lr(self.next_lr(lr))
         if self.g_fb is not None:
-            self.g_fb.replay()
-            self._allreduce()
+            for k, g in enumerate(self.g_fb):
+                g.replay()
+                self._allreduce_bucket(k)
+            self._allreduce_finish()
             self.g_up.replay()
         else:
-            self.out = self.net.forward_backward(self.static)
-            self._allreduce()
+            self.out = self.net.forward_backward(self.static, on_bucket=self._allreduce_bucket)
+            self._allreduce_finish()
             self.net.update()
         return self.out
 

@@ -19,17 +19,27 @@ def _worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     from sniper_b200 import model
     P = model.ParamStore()
+    P.bucket = 1
+    P.add("s_weight", (6, 2)); P.add("s_beta", (6,))
+    P.bucket = 0
     P.add("a_weight", (5, 3)); P.add("a_bias", (5,)); P.add("offset_weight", (7,), lr_mult=0.01); P.add("b_gamma", (4,))
     P.finalize("cpu")
     # every rank owns different chips -> different gradients; the update must see their SUM (rescale_grad=1)
     for i, (name, g) in enumerate(sorted(P.grads.items())):
         g.fill_(float(rank + 1) * (i + 1))
-    dist.all_reduce(P.g, op=dist.ReduceOp.SUM)          # ONE collective over the whole bucket
+    # one asynchronous collective per gradient bucket, in the order the backward pass completes them (the trainer
+    # starts bucket k while phase k+1 computes); together they cover the whole buffer exactly once
+    works = [dist.all_reduce(P.g[a:b], op=dist.ReduceOp.SUM, async_op=True) for a, b in P.bucket_ranges]
+    for w in works:
+        w.wait()
+    cover = sorted(P.bucket_ranges)
+    assert cover[0][0] == 0 and cover[-1][1] == P.total and all(x[1] == y[0] for x, y in zip(cover, cover[1:]))
     exp = {name: float(sum(r + 1 for r in range(world)) * (i + 1)) for i, name in enumerate(sorted(P.grads))}
     ok = all(bool((P.grad(n) == v).all()) for n, v in exp.items())
     # optimizer groups: (lr_mult, wd_mult) as MXNet assigns them
-    groups = sorted(g for _, _, g in P.segments)
+    groups = sorted(set(g for _, _, g in P.segments))
     ok = ok and groups == [(0.01, 1.0), (1.0, 0.0), (1.0, 1.0)]
+    ok = ok and all(any(a <= s0 and e0 <= b for a, b in P.bucket_ranges) for s0, e0, _ in P.segments)
     ok = ok and P.total % 4 == 0 and all(o % 4 == 0 for o, _ in P.layout.values())
     q.put((rank, ok))
     dist.destroy_process_group()

@@ -217,3 +217,47 @@ def test_deformable_im2col_kernels(big):
     e_off = (p_go[..., :72].permute(0, 3, 1, 2) - r_go).abs().max().item()
     print("col2im_coord product vs reference max |delta| %.3e (|grad| max %.3e)" % (e_off, r_go.abs().max().item()))
     assert e_off <= 2e-5 * r_go.abs().max().item() + 1e-5
+
+
+def test_deformable_psroi_full_config_vs_reference_kernel():
+    """The two pooling calls of the ResNet-101 head at the metric's size (B = 20 chips, 6000 rois, 256 channels, 7x7 bins,
+    4x4 samples; resnet_mx_101_e2e.py:286-293) on the product's NHWC hot-path kernels against the reference's own CUDA
+    kernels run on the same GPU: sample counts exact, oracle-order forward (SNIPER_PSROI_EXACT=1) bit-exact, default
+    separable forward <= 2e-6 * max|x|, backward (float atomics on both sides) to 2e-4 of the largest gradient."""
+    import torch
+    from sniper_b200 import ops, synth
+    rng = np.random.RandomState(17)
+    B, C, N = 20, 256, 6000
+    data = rng.randn(B, C, 32, 32).astype(np.float32)
+    rois = synth.rois_for_pool(rng, N, B)
+    rois[:, 0] = np.repeat(np.arange(B), N // B)                      # 300 rois per chip, as MultiProposalTarget emits them
+    trans = (rng.randn(N, 2, 7, 7) * 0.3).astype(np.float32)
+    kw = dict(spatial_scale=0.0625, output_dim=256, group_size=1, pooled=7, part_size=7, spp=4, trans_std=0.1)
+    pkw = dict(spatial_scale=0.0625, output_dim=256, group_size=1, pooled_size=7, part_size=7, sample_per_part=4,
+               trans_std=0.1, layout=ops.NHWC)
+    d_nchw, d_nhwc = _t(data), _t(data.transpose(0, 2, 3, 1))
+    r, tr = _t(rois), _t(trans)
+    g = _t(rng.randn(N, 256, 7, 7).astype(np.float32))
+    g_nhwc = g.permute(0, 2, 3, 1).contiguous()
+    for no_trans in (True, False):
+        t_ = None if no_trans else tr
+        r_out, r_cnt = R.dpsroi_fwd(d_nchw, r, t_, **kw)
+        os.environ["SNIPER_PSROI_EXACT"] = "1"
+        try:
+            e_out, e_cnt, _ = ops.deform_psroi_fwd(d_nhwc, r, t_, no_trans=no_trans, **pkw)
+        finally:
+            os.environ.pop("SNIPER_PSROI_EXACT", None)
+        assert torch.equal(e_cnt.permute(0, 3, 1, 2), r_cnt)
+        assert torch.equal(e_out.permute(0, 3, 1, 2), r_out), "oracle-order NHWC kernel differs from the reference kernel"
+        s_out, _, _ = ops.deform_psroi_fwd(d_nhwc, r, t_, no_trans=no_trans, want_count=False, **pkw)
+        err = (s_out.permute(0, 3, 1, 2) - r_out).abs().max().item()
+        assert err <= 2e-6 * np.abs(data).max(), err
+        r_dd, r_td = R.dpsroi_bwd(g, r_cnt, d_nchw, r, t_, **kw)
+        p_dd, p_td = ops.deform_psroi_bwd(g_nhwc, d_nhwc, r, t_, no_trans=no_trans, **pkw)
+        e_dd = (p_dd.permute(0, 3, 1, 2) - r_dd).abs().max().item() / r_dd.abs().max().item()
+        print("no_trans=%d: separable fwd max err %.2e, bwd data rel err %.2e" % (no_trans, err, e_dd))
+        assert e_dd < 2e-4
+        if not no_trans:
+            e_td = (p_td - r_td).abs().max().item() / r_td.abs().max().item()
+            print("           bwd trans rel err %.2e" % e_td)
+            assert e_td < 1e-3
