@@ -55,6 +55,7 @@ SIGNATURES = {
     "sniper_deform_im2col": ("i", "pp" "iiiiiiiiiii" "pip"),
     "sniper_deform_col2im": ("i", "ppp" "iiiiiiiiiii" "ppip"),
     "sniper_anchor_target": ("i", "ppippipp" "iiii" "pipi" "dd" "ppppp" "p"),
+    "sniper_soft_nms_batched": ("i", "ppifffuppp"),
     "sniper_chip_input": ("i", "ppppiip"),
     "sniper_anchor_subsample": ("i", "pppiiiiiiup"),
     "sniper_chips_generate": ("i", "piiiiipi"),

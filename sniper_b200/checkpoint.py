@@ -99,6 +99,33 @@ def write_params(path, arg, aux):
         f.write(b"".join(out))
 
 
+BBOX_STDS_TEST = (0.1, 0.1, 0.2, 0.2)      # hard-coded in the reference's checkpoint_callback (resnet_mx_101_e2e.py:11)
+
+
+def save_checkpoint(prefix, epoch, arg, aux, bbox_param_names=("bbox_pred_weight", "bbox_pred_bias")):
+    """`checkpoint_callback` (symbols/faster/resnet_mx_101_e2e.py:6-17) + the `.params` half of
+    mx.model.save_checkpoint: writes `<prefix>-%04d.params` with the extra `*_test` copies of the box-regression layer
+    (weight rows and bias scaled by the target stds, what the test-time symbol binds).  Returns the path."""
+    out = dict(arg)
+    if bbox_param_names[0] in arg:
+        stds = np.array(BBOX_STDS_TEST, dtype=arg[bbox_param_names[0]].dtype)
+        out[bbox_param_names[0] + "_test"] = (arg[bbox_param_names[0]].T * stds).T
+        out[bbox_param_names[1] + "_test"] = arg[bbox_param_names[1]] * stds
+    path = "%s-%04d.params" % (prefix, epoch)
+    write_params(path, out, aux)
+    return path
+
+
+def load_param(prefix, epoch, process=False):
+    """lib/train_utils/utils.py:77-100: (arg_params, aux_params) of `<prefix>-%04d.params`; process=True renames the
+    `*_test` tensors over the training ones (what main_test.py loads)."""
+    arg, aux = read_params("%s-%04d.params" % (prefix, epoch))
+    if process:
+        for k in [k for k in arg if "_test" in k]:
+            arg[k.replace("_test", "")] = arg.pop(k)
+    return arg, aux
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # layout conversions (numpy, pure functions)
 # ---------------------------------------------------------------------------------------------------------------

@@ -802,20 +802,35 @@ class SniperResNet101:
     def _named_bns(self):
         return [self.bn_data, self.bn0] + [b for u in self.units for b in u.bns()]
 
-    def load_reference(self, arg, aux):
+    def load_reference(self, arg, aux, allow_missing=False):
         """Loads a reference checkpoint (`arg_params`, `aux_params` as numpy dicts, e.g. checkpoint.read_params of a
-        released SNIPER `.params` file): OIHW -> tap-major rows, NCHW-flattened FC inputs -> NHWC, fused heads."""
+        released SNIPER `.params` file): OIHW -> tap-major rows, NCHW-flattened FC inputs -> NHWC, fused heads.
+        allow_missing=True is the reference's normal training start: an ImageNet ResNet-101 checkpoint holds only the
+        backbone, and `init_weight_rcnn` (resnet_mx_101_e2e.py:450-485) initialises the offset layers, the RPN and
+        the R-FCN head -- here those layers simply keep the values the constructor gave them (zeros for the offset layers,
+        N(0, 0.01) for the heads).  Returns the list of layers that were not in the checkpoint."""
         from . import checkpoint as ck
         cfg = self.cfg
         dev = self.device
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
-        self.conv0_w.copy_(t(arg["conv0_weight"].transpose(0, 2, 3, 1)))
+        skipped = []
+        if "conv0_weight" in arg or not allow_missing:
+            self.conv0_w.copy_(t(arg["conv0_weight"].transpose(0, 2, 3, 1)))
+        else:
+            skipped.append("conv0")
         for c in self._named_convs():
+            parts = ck.FUSED.get(c.name, (c.name,))
+            if allow_missing and any(p + "_weight" not in arg for p in parts):
+                skipped.append(c.name)
+                continue
             w, b = ck.conv_from_reference(c.name, c.cout, c.coutp, c.cin, c.k, c.bias, arg)
             c.master.copy_(t(w))
             if c.bias:
                 c.b.copy_(t(b))
         for bn in self._named_bns():
+            if allow_missing and bn.name + "_gamma" not in arg:
+                skipped.append(bn.name)
+                continue
             bn.st.gamma.copy_(t(arg[bn.name + "_gamma"]))
             bn.st.beta.copy_(t(arg[bn.name + "_beta"]))
             bn.st.moving_mean.copy_(t(aux[bn.name + "_moving_mean"]))
@@ -824,6 +839,7 @@ class SniperResNet101:
                 ops.bn_frozen(bn.st, cfg.bn_eps, fix_gamma=bn.fix_gamma)
         self.P.sync_lowp()
         self._wt_table = None      # data-gradient operands are rebuilt from the new weights on the next step
+        return skipped
 
     def export_reference(self, grads=False):
         """The inverse of load_reference: (arg_params, aux_params) under the reference's names and layouts.

@@ -617,3 +617,18 @@ def anchor_target(gt_valid, ngt, gt_invalid, ninv, im_info, *, H=32, W=32, feat_
                                      float(neg_thresh), _ptr(scratch), _ptr(label), _ptr(bt), _ptr(bw), _ptr(am),
                                      _stream()))
     return (label, bt, bw, am) if want_argmax else (label, bt, bw)
+
+
+def soft_nms_batched(dets, offsets, *, sigma=0.55, Nt=0.3, threshold=0.001, method=2):
+    """cpu_soft_nms (lib/nms/cpu_nms.pyx:17-110) on every segment dets[offsets[p]:offsets[p+1]] ([.,5] rows x1,y1,x2,y2,score)
+    at once.  Returns (dets_out, counts): the first counts[p] rows of segment p are its surviving detections in the
+    reference's output order; `dets` itself is not modified."""
+    assert dets.is_cuda and dets.dtype == torch.float32 and dets.dim() == 2 and dets.shape[1] == 5 and dets.is_contiguous()
+    assert offsets.dtype == torch.int32 and offsets.is_cuda
+    P = offsets.numel() - 1
+    out = dets.clone()
+    counts = torch.zeros(max(P, 1), dtype=torch.int32, device=dets.device)
+    scratch = torch.empty_like(dets)
+    check(lib().sniper_soft_nms_batched(_ptr(out), _ptr(offsets), P, float(sigma), float(Nt), float(threshold), int(method),
+                                        _ptr(counts), _ptr(scratch), _stream()))
+    return out, counts[:P]

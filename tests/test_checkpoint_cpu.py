@@ -86,3 +86,23 @@ def test_fused_heads_and_pooled_fcs_roundtrip():
         assert np.array_equal(out[k], arg[k]), k
     with pytest.raises(ValueError):
         C.conv_from_reference("cls_bbox", K + 4, 96, 512, 1, True, arg)
+
+
+def test_save_checkpoint_adds_test_time_bbox_weights(tmp_path):
+    """checkpoint_callback (resnet_mx_101_e2e.py:6-17): `bbox_pred_*_test` = weights / bias scaled by (0.1, 0.1, 0.2, 0.2);
+    load_param(process=True) (utils.py:77-100) renames them over the training tensors."""
+    import numpy as np
+    from sniper_b200 import checkpoint as ck
+    rng = np.random.RandomState(0)
+    arg = {"bbox_pred_weight": rng.randn(4, 1024).astype(np.float32), "bbox_pred_bias": rng.randn(4).astype(np.float32),
+           "cls_score_weight": rng.randn(81, 1024).astype(np.float32)}
+    aux = {"bn0_moving_mean": rng.randn(64).astype(np.float32)}
+    path = ck.save_checkpoint(str(tmp_path / "m"), 6, arg, aux)
+    assert path.endswith("m-0006.params")
+    a, x = ck.load_param(str(tmp_path / "m"), 6)
+    stds = np.array([0.1, 0.1, 0.2, 0.2], np.float32)
+    assert np.array_equal(a["bbox_pred_weight_test"], (arg["bbox_pred_weight"].T * stds).T)
+    assert np.array_equal(a["bbox_pred_bias_test"], arg["bbox_pred_bias"] * stds)
+    assert np.array_equal(a["bbox_pred_weight"], arg["bbox_pred_weight"]) and np.array_equal(x["bn0_moving_mean"], aux["bn0_moving_mean"])
+    a2, _ = ck.load_param(str(tmp_path / "m"), 6, process=True)
+    assert "bbox_pred_weight_test" not in a2 and np.array_equal(a2["bbox_pred_weight"], a["bbox_pred_weight_test"])

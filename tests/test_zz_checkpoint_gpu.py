@@ -37,3 +37,25 @@ def test_reference_checkpoint_roundtrip(tmp_path):
         assert np.array_equal(aux[k], aux3[k]), k
     out2 = net2.forward_inference(batch["data"], batch["im_info"])
     assert all(torch.equal(a, b) for a, b in zip(ref_out, out2))
+
+
+def test_backbone_only_checkpoint_loads_with_allow_missing():
+    """The reference's normal training start: an ImageNet ResNet-101 `.params` has no RPN / R-FCN / offset tensors
+    (init_weight_rcnn fills them, resnet_mx_101_e2e.py:450-485)."""
+    import torch
+    from sniper_b200 import model
+    cfg = model.Cfg()
+    net = model.SniperResNet101(cfg, seed=3)
+    arg, aux = net.export_reference()
+    heads = ("rpn_", "conv_new_1", "offset", "fc_new", "cls_score", "bbox_pred")
+    backbone = {k: v for k, v in arg.items() if not any(h in k for h in heads)}
+    net2 = model.SniperResNet101(cfg, seed=9)
+    keep = net2.fc_new_1.w.clone()
+    with pytest.raises(KeyError):
+        net2.load_reference(backbone, aux)
+    skipped = net2.load_reference(backbone, aux, allow_missing=True)
+    assert "rpn_head" in skipped and "cls_bbox" in skipped and "stage4_unit1_offset" in skipped and "fc_new_1" in skipped
+    assert not any(s.startswith("stage3") for s in skipped)
+    assert torch.equal(net2.fc_new_1.w, keep)                                           # untouched initialisation
+    assert torch.equal(net2.units[10].conv1.w, net.units[10].conv1.w)                   # backbone taken from the file
+    assert float(net2.units[-1].offset.w.abs().sum()) == 0.0                            # offset layers stay zero
