@@ -165,3 +165,4 @@ def test_batched_weight_transpose_and_bn_param_grad():
     for b, g0, b0, s0 in states:
         assert torch.equal(b.dbeta, b0 + s0[:b.C].float()) and torch.equal(b.dgamma, g0 + s0[b.C:].float())
         assert float(b.sums.abs().sum()) == 0.0
+

@@ -70,7 +70,9 @@ def _build(B, seed, bf16=False):
 # only to ~sqrt(0.4*eps) per ReLU layer (eps = 4e-3 -> 4 %), accumulating over the ~100 ReLUs below the heads.  A wiring
 # error gives relative errors >= 0.7 (uncorrelated gradients) and norm ratios far from 1.
 TOL_TF32 = dict(act=1e-2, loss=5e-3, grad=0.25, grad_median=0.15, head=8e-2, norm=0.05)
-TOL_BF16 = dict(act=5e-2, loss=3e-2, grad=0.5, grad_median=0.3, head=0.2, norm=0.1)
+# bf16: every stored activation is rounded to 8 bits (2e-3); rounding is discontinuous, so product and emulation part
+# ways at that level per tensor (measured: 3e-2 at c4|c5) and the ReLU argument above gives ~0.35 on backbone gradients
+TOL_BF16 = dict(act=5e-2, loss=3e-2, grad=0.6, grad_median=0.45, head=0.25, norm=0.1)
 
 
 def _tf32_trunc(x):
