@@ -38,7 +38,7 @@ def test_soft_nms_batched_matches_host(method, sigma, Nt):
         assert np.array_equal(got[:, :4], ref[:, :4]), p
         ulp = np.abs(got[:, 4].view(np.int32).astype(np.int64) - ref[:, 4].view(np.int32).astype(np.int64))
         assert ulp.max(initial=0) <= 1, (p, ulp.max())
-    assert counts[3] < sizes[3] or method == 1      # something was actually suppressed / decayed away
+    assert counts[5] < sizes[5] or method == 1      # among 1000 clustered boxes something is suppressed / decayed away
 
 
 def test_aggregate_device_equals_host_path():

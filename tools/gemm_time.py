@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from sniper_b200 import ops
 
 DT = torch.bfloat16 if os.environ.get("GT_DTYPE") == "bf16" else torch.float32      # operand / output storage
-CASES = [("gemm", 20480, 1024, 256), ("gemmres", 20480, 1024, 256), ("gemm", 327680, 256, 64), ("gemm", 81920, 512, 128),
+CASES = [("gemm", 20480, 1024, 256), ("gemmres", 20480, 1024, 256), ("gemmr", 20480, 1024, 256), ("gemmst", 20480, 1024, 256), ("gemm", 327680, 256, 64), ("gemm", 81920, 512, 128),
          ("gemm", 81920, 128, 512), ("gemm", 20480, 256, 1024), ("conv3x3", 20, 32, 32, 256, 256)]
 SETTINGS = [{"SNIPER_GEMM_2SM": "0"}, {"SNIPER_GEMM_2SM": "1"}]
 if len(sys.argv) > 1:
@@ -27,16 +27,17 @@ def timed(fn, reps=20):
 
 
 for case in CASES:
-    if case[0] in ("gemm", "gemmres"):
+    if case[0] in ("gemm", "gemmres", "gemmr", "gemmst"):
         _, M, N, K = case
         nbuf = max(2, int(300e6 // (4 * (M * K + M * N))) + 1)
         A = [torch.randn(M, K, device="cuda").to(DT) for _ in range(nbuf)]
         B = torch.randn(N, K, device="cuda").to(DT)
         C = [torch.empty(M, N, device="cuda", dtype=DT) for _ in range(nbuf)]
-        if case[0] == "gemmres":
-            R = [torch.randn(M, N, device="cuda").to(DT) for _ in range(nbuf)]
-            stats_buf = torch.zeros(2 * N, dtype=torch.float64, device="cuda")
-            fn = lambda i: ops.gemm_nt(A[i % nbuf], B, out=C[i % nbuf], residual=R[(i + 1) % nbuf], stats=stats_buf)
+        if case[0] != "gemm":      # gemmres: residual + BN statistics; gemmr: residual only; gemmst: statistics only
+            R = [torch.randn(M, N, device="cuda").to(DT) for _ in range(nbuf)] if case[0] != "gemmst" else None
+            stats_buf = torch.zeros(2 * N, dtype=torch.float64, device="cuda") if case[0] != "gemmr" else None
+            fn = lambda i: ops.gemm_nt(A[i % nbuf], B, out=C[i % nbuf], residual=None if R is None else R[(i + 1) % nbuf],
+                                       stats=stats_buf)
         else:
             fn = lambda i: ops.gemm_nt(A[i % nbuf], B, out=C[i % nbuf])
         flop = 2.0 * M * N * K
