@@ -247,6 +247,8 @@ def measure(args, cfg, rank, local_rank, world, pool, dev_pool, sampler=None):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
     out = {"ms": ms, "ms_e2e": ms_e2e, "losses": losses, "launches_per_step": trainer.launches_per_step}
+    if getattr(args, "iterator_leg", False):
+        out["iterator"] = iterator_leg(args, trainer, local_rank, barrier)
     if rank == 0:
         peaks, peak_src = load_peaks()
         peak_bf16 = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
@@ -258,6 +260,38 @@ def measure(args, cfg, rank, local_rank, world, pool, dev_pool, sampler=None):
     del trainer
     torch.cuda.empty_cache()
     return out
+
+
+def iterator_leg(args, trainer, local_rank, barrier):
+    """The same step fed by the REAL input path: synthetic COCO-shaped roidb (decoded uint8 images in memory) ->
+    chip_worker / MNIteratorE2E on the host (background prefetch thread) -> raw uint8 batch over PCIe -> GPU input stage
+    (resize, mean, anchor matching, label subsampling) -> training step -> losses back.  Reported next to `e2e`."""
+    import numpy as np
+    import torch
+    from sniper_b200 import iterator as IT
+    np.random.seed(1234 + local_rank)
+    cfg = IT.default_config()
+    roidb = IT.synthetic_roidb(24, seed=11 + local_rank, n_prop=300)
+    it = IT.MNIteratorE2E(roidb, cfg, batch_size=args.chips, n_buffers=6)
+    stage = IT.InputStage(cfg, "cuda:%d" % local_rank, args.chips)
+    pf = IT.PrefetchingIter(it, depth=3)
+    nbytes = []
+    for _ in range(3):
+        trainer.step_raw(next(pf), stage)
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    losses = None
+    for _ in range(args.steps):
+        raw = next(pf)
+        nbytes.append(raw.nbytes())
+        losses = trainer.step_raw(raw, stage)
+    t1.record()
+    barrier()
+    pf.close()
+    ms = t0.elapsed_time(t1)
+    return {"ms": ms, "h2d_bytes_per_step": int(sum(nbytes) / max(len(nbytes), 1)), "losses": losses,
+            "chips_in_epoch": int(it.chip_count)}
 
 
 def run_ours(args):
@@ -340,6 +374,13 @@ def run_ours(args):
             "losses": m["losses"],
             "clocks": sampler.summary(),
         }
+        if "iterator" in m:
+            itl = m["iterator"]
+            result["e2e_iterator"] = {
+                "value": round(chips / (itl["ms"] / 1e3), 2), "unit": "chips/s", "ms_per_step": round(itl["ms"] / args.steps, 3),
+                "h2d_bytes_per_step": itl["h2d_bytes_per_step"], "d2h_bytes_per_step": 32, "losses": itl["losses"],
+                "path": "synthetic roidb -> chip_worker / MNIteratorE2E (host, prefetch thread) -> raw uint8 crops over PCIe "
+                        "-> sniper_chip_input + sniper_anchor_target + sniper_anchor_subsample -> Trainer.step_raw"}
         if m3 is not None:
             v3, roof3 = block(m3, True)
             result["config3"] = {
@@ -400,7 +441,9 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--bf16", action="store_true", help="run the main measurement in mixed precision (configs[2])")
     ap.add_argument("--skip-config3", action="store_true", help="do not append the bf16 block to the JSON line")
+    ap.add_argument("--skip-iterator", action="store_true", help="do not measure the e2e_iterator block")
     args = ap.parse_args()
+    args.iterator_leg = not args.skip_iterator
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -268,6 +268,52 @@ class MNIteratorE2E(object):
         return raw
 
 
+class PrefetchingIter(object):
+    """Background-thread prefetch of raw batches (the role of mx.io.PrefetchingIter around MNIteratorE2E in
+    main_train.py): the host bookkeeping of batch i+1 runs while the GPU computes batch i.  The wrapped iterator must
+    own at least depth + 2 raw buffers (n_buffers)."""
+
+    def __init__(self, it, depth=2, epochs=None):
+        import queue
+        import threading
+        self.it = it
+        self.q = queue.Queue(maxsize=depth)
+        self.epochs = epochs
+        self._stop = False
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        ep = 0
+        while not self._stop:
+            for raw in self.it:
+                if self._stop:
+                    return
+                self.q.put(raw)
+            ep += 1
+            if self.epochs is not None and ep >= self.epochs:
+                self.q.put(None)
+                return
+            self.it.reset()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        raw = self.q.get()
+        if raw is None:
+            raise StopIteration
+        return raw
+
+    def close(self):
+        self._stop = True
+        try:
+            while True:
+                self.q.get_nowait()
+        except Exception:
+            pass
+
+
 class InputStage(object):
     """Device half of the iterator: raw batch -> the network's input tensors (all on `device`)."""
 

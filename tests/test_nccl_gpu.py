@@ -23,4 +23,6 @@ def test_two_rank_gradient_allreduce_and_replicated_update(tmp_path):
     print(res)
     assert res["allreduce_equals_sum_of_locals"] is True
     assert res["weights_identical"] is True
-    assert res["vs_sequential_rel"] < 1e-4
+    # run-to-run noise of one backward pass (float atomics in PSROI / col2im / split-K reductions) is ~1.5e-3 on the
+    # gradient norm (tests/test_trainer_gpu.py measures it); a wrong slice, a missing rank or a 1/N factor shows as O(1)
+    assert res["vs_sequential_rel"] < 1e-2
