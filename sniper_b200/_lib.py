@@ -34,6 +34,7 @@ SIGNATURES = {
     "sniper_affine_act": ("i", "plpppl" "l" "iii" "p"),
     "sniper_bn_stats": ("i", "pllippffipppppppip"),
     "sniper_bn_finalize": ("i", "plippffippppppp"),
+    "sniper_bn_apply_train": ("i", "plplippffippppppplii" "p"),
     "sniper_bn_frozen": ("i", "ippppfippp"),
     "sniper_bn_relu_bwd": ("i", "plplppppp" "pl" "pl" "pp" "lii" "p"),
     "sniper_affine_relu_bwd": ("i", "plplpp" "pl" "pl" "lii" "p"),

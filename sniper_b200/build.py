@@ -11,7 +11,7 @@ LIB = os.path.join(LIBDIR, "libsniper_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-Xcompiler", "-fopenmp",
-    "--expt-relaxed-constexpr",
+    "--expt-relaxed-constexpr", "-split-compile", "0",
 ]
 # translation units whose results are graded bit-exact: no FMA contraction anywhere
 NO_FMAD = {"mpt.cu", "psroi.cu", "anchor_target.cu", "nms.cu"}

@@ -7,8 +7,13 @@
 // smooth_l1 + MakeLoss (mshadow_op.h:642-678), SGD momentum (optimizer_op-inl.h:279-300).
 // All kernels: 128-bit vectorised loads/stores along C, grids sized in multiples of 148 SMs.
 #include "common.cuh"
+#include <cooperative_groups.h>
+#include <string.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 #include <math.h>
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -60,16 +65,18 @@ constexpr int kUnroll = 4;
 
 struct RowBlock {
   int lx_shift;         // log2(LX)
-  int rows_per_block;   // multiple of kUnroll * RY
+  int rows_per_block;   // multiple of RY
   dim3 grid;
 };
 
 // Vector width per thread: 16 bytes of storage either way = 4 fp32 or 8 bf16 channels.
 template <typename T> struct VT;
-// U = independent 16-byte loads per operand in flight per thread (bf16 carries twice the channels per load, so half
-// the unroll keeps the register footprint -- and two resident blocks per SM -- of the fp32 instantiation)
-template <> struct VT<float> { static constexpr int N = 4, U = 4; };
-template <> struct VT<bf16> { static constexpr int N = 8, U = 2; };
+// U = independent 16-byte loads per operand in flight per thread.  The loads are kept RAW (packed, 4 registers each)
+// until they are consumed: with bf16 unpacked at load time (8 floats per load) only U = 2 fitted the register budget
+// and the bf16 kernels, at 2 resident blocks per SM, had ~32 KB in flight per SM -- below the ~47 KB that HBM latency x
+// bandwidth needs -- and ran at 2-3 TB/s (tools/ew_time.py).
+template <> struct VT<float> { static constexpr int N = 4, U = 4; typedef float4 Raw; };
+template <> struct VT<bf16> { static constexpr int N = 8, U = 4; typedef uint4 Raw; };
 
 template <int N>
 __device__ __forceinline__ void ldc(const float* p, float (&v)[N]) {   // N per-channel constants (fp32)
@@ -104,6 +111,18 @@ __device__ __forceinline__ void stv(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+__device__ __forceinline__ float4 ldraw(const float* p) { return ld4(p); }
+__device__ __forceinline__ uint4 ldraw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void unpack(const float4& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+__device__ __forceinline__ void unpack(const uint4& u, float (&v)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {      // bf16 -> fp32 is a 16-bit shift: low half = element 2k, high half = 2k + 1
+    v[2 * k] = __uint_as_float(w[k] << 16);
+    v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+  }
+}
+
 template <int VEC>
 __device__ __forceinline__ bool rb_setup(int lx_shift, int C, int rows_per_block, long M, int& c, int& ry, int& RY,
                                          long& r0, long& r1) {
@@ -131,18 +150,83 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x
   ldc<N>(scale + c, s);
   ldc<N>(shift + c, t);
   for (long r = r0 + ry; r < r1; r += (long)KU * RY) {
-    float v[KU][N];
+    typename VT<T>::Raw raw[KU];
 #pragma unroll
     for (int u = 0; u < KU; ++u)
-      if (r + (long)u * RY < r1) ldv(x + (r + (long)u * RY) * ldx + c, v[u]);
+      if (r + (long)u * RY < r1) raw[u] = ldraw(x + (r + (long)u * RY) * ldx + c);
 #pragma unroll
     for (int u = 0; u < KU; ++u) {
       const long rr = r + (long)u * RY;
       if (rr >= r1) break;
-      float o[N];
+      float v[N], o[N];
+      unpack(raw[u], v);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        o[k] = fmaf(v[u][k], s[k], t[k]);
+        o[k] = fmaf(v[k], s[k], t[k]);
+        if (relu) o[k] = fmaxf(o[k], 0.f);
+      }
+      stv(y + rr * ldy + c, o);
+    }
+  }
+}
+
+// Train-mode BatchNorm apply with the finalisation folded in: the producing conv's epilogue left (sum, sum of squares)
+// of the input in `sums`; every thread derives scale / shift of its own channels from them (a handful of double ops),
+// the first row-block of each channel slab also publishes mean / invstd / scale / shift (the backward pass reads them)
+// and updates the moving statistics.  Same arithmetic as bn_finalize_kernel.  `sums` is NOT cleared here (other blocks
+// are still reading it): the caller clears it at the end of the step (sniper_bn_param_grad_batched).  Saves one tiny
+// launch per BatchNorm layer (90 per training step).
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_train_kernel(const T* __restrict__ x, long ldx,
+                                                              const double* __restrict__ sums,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, float momentum,
+                                                              int fix_gamma, float* __restrict__ moving_mean,
+                                                              float* __restrict__ moving_var, float* __restrict__ mean,
+                                                              float* __restrict__ invstd, float* __restrict__ scale,
+                                                              float* __restrict__ shift, T* __restrict__ y, long ldy,
+                                                              long M, int C, int relu, int lx_shift, int rows_per_block) {
+  constexpr int N = VT<T>::N, KU = VT<T>::U;
+  int c, ry, RY;
+  long r0, r1;
+  if (!rb_setup<N>(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1)) return;
+  float s[N], t[N];
+  const bool publish = blockIdx.x == 0 && ry == 0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double m = sums[c + k] / (double)M;
+    double var = sums[C + c + k] / (double)M - m * m;
+    if (var < 0) var = 0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = fix_gamma ? 1.0f : gamma[c + k];
+    s[k] = g * is;
+    t[k] = beta[c + k] - (float)m * g * is;
+    if (publish) {
+      mean[c + k] = (float)m;
+      invstd[c + k] = is;
+      scale[c + k] = s[k];
+      shift[c + k] = t[k];
+      if (moving_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        moving_mean[c + k] = moving_mean[c + k] * momentum + (float)m * (1.0f - momentum);
+        moving_var[c + k] = moving_var[c + k] * momentum + (float)unbiased * (1.0f - momentum);
+      }
+    }
+  }
+  for (long r = r0 + ry; r < r1; r += (long)KU * RY) {
+    typename VT<T>::Raw raw[KU];
+#pragma unroll
+    for (int u = 0; u < KU; ++u)
+      if (r + (long)u * RY < r1) raw[u] = ldraw(x + (r + (long)u * RY) * ldx + c);
+#pragma unroll
+    for (int u = 0; u < KU; ++u) {
+      const long rr = r + (long)u * RY;
+      if (rr >= r1) break;
+      float v[N], o[N];
+      unpack(raw[u], v);
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        o[k] = fmaf(v[k], s[k], t[k]);
         if (relu) o[k] = fmaxf(o[k], 0.f);
       }
       stv(y + rr * ldy + c, o);
@@ -171,40 +255,47 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
     float sc[N], sh[N], mu[N], is[N];
     if (MODE == 1) { ldc<N>(scale + c, sc); ldc<N>(shift + c, sh); ldc<N>(mean + c, mu); ldc<N>(invstd + c, is); }
     for (long r = r0 + ry; r < r1; r += (long)KU * RY) {
-      float v[KU][N], g[KU][N];
+      typename VT<T>::Raw rx[KU], rg[KU];
 #pragma unroll
       for (int u = 0; u < KU; ++u) {
         const long rr = r + (long)u * RY;
         if (rr < r1) {
-          ldv(x + rr * ldx + c, v[u]);
-          if (MODE == 1) ldv(dy + rr * lddy + c, g[u]);
-        } else {
-#pragma unroll
-          for (int k = 0; k < N; ++k) { v[u][k] = 0.f; if (MODE == 1) g[u][k] = 0.f; }   // contributes nothing
+          rx[u] = ldraw(x + rr * ldx + c);
+          if (MODE == 1) rg[u] = ldraw(dy + rr * lddy + c);
         }
       }
 #pragma unroll
       for (int u = 0; u < KU; ++u) {
+        if (r + (long)u * RY >= r1) break;
+        float v[N], g[N];
+        unpack(rx[u], v);
+        if (MODE == 1) unpack(rg[u], g);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           if (MODE == 0) {
-            a[k] += v[u][k];
-            b[k] = fmaf(v[u][k], v[u][k], b[k]);
+            a[k] += v[k];
+            b[k] = fmaf(v[k], v[k], b[k]);
           } else {
-            const float gg = fmaf(v[u][k], sc[k], sh[k]) > 0.f ? g[u][k] : 0.f;
+            const float gg = fmaf(v[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
             a[k] += gg;
-            b[k] = fmaf(gg, (v[u][k] - mu[k]) * is[k], b[k]);
+            b[k] = fmaf(gg, (v[k] - mu[k]) * is[k], b[k]);
           }
         }
       }
     }
   }
+  // Block partials -> cluster partials -> one double atomic per (cluster, channel, sum).  The row blocks of one channel
+  // slab are launched as thread-block clusters along x; rank 0 gathers the other blocks' partials through distributed
+  // shared memory.  Without this step every block issued its own atomics: ~600 same-address double atomics per channel
+  // for a 20480-row tensor, and their serialisation in L2 -- not the loads -- set the kernel time (it GREW with the
+  // block count: 15.6 / 19.1 / 40.8 us at 2 / 8 / 16 blocks per SM for 20480 x 256 fp32, tools/ew_time.py).
   __shared__ float sa[256][N + 1], sb[256][N + 1];
+  __shared__ double part[2][32 * N];
 #pragma unroll
   for (int k = 0; k < N; ++k) { sa[threadIdx.x][k] = a[k]; sb[threadIdx.x][k] = b[k]; }
   __syncthreads();
-  if (ry == 0 && cok) {
-    const int lx = 1 << lx_shift;
+  const int lx = 1 << lx_shift;
+  if (ry == 0) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       double ax = 0, bx = 0;
@@ -212,10 +303,54 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
         ax += sa[j * lx + threadIdx.x][k];
         bx += sb[j * lx + threadIdx.x][k];
       }
-      atomicAdd(sums + c + k, ax);
-      atomicAdd(sums + C + c + k, bx);
+      part[0][threadIdx.x * N + k] = ax;     // threadIdx.x < lx here; channel = slab base + threadIdx.x * N + k
+      part[1][threadIdx.x * N + k] = bx;
     }
   }
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned nblk = cluster.num_blocks();
+  if (nblk > 1) cluster.sync(); else __syncthreads();
+  if (cluster.block_rank() == 0) {
+    const int per = lx * N;                  // channels of this slab
+    const int cbase = (int)blockIdx.y * per;
+    for (int i = threadIdx.x; i < 2 * per; i += 256) {
+      const int which = i >= per ? 1 : 0, j = i - which * per;
+      if (cbase + j >= C) continue;
+      double t = part[which][j];
+      for (unsigned r = 1; r < nblk; ++r) t += cluster.map_shared_rank(&part[0][0], r)[which * 32 * N + j];
+      if (t != 0.0) atomicAdd(sums + which * C + cbase + j, t);
+    }
+  }
+  if (nblk > 1) cluster.sync();              // keep every block's shared memory alive until rank 0 has read it
+}
+
+// Launches colsum_kernel with its row blocks grouped into thread-block clusters (SNIPER_EW_CLUSTER = 1 | 2 | 4 | 8, A/B).
+RowBlock row_block(long M, int C, int vec, int occ);
+template <typename K> int resident_blocks(K kernel);
+
+template <int MODE, typename T>
+int launch_colsum(cudaStream_t st, const T* x, long ldx, const T* dy, long lddy, const float* scale,
+                  const float* shift, const float* mean, const float* invstd, long M, int C, double* sums) {
+  const RowBlock rb = row_block(M, C, VT<T>::N, resident_blocks(colsum_kernel<MODE, T>));
+  int cl = 1;   // measured: clusters only help the smallest tensors and cost 20-30 % on the large ones
+  if (const char* e = getenv("SNIPER_EW_CLUSTER")) cl = atoi(e);
+  if (cl != 1 && cl != 2 && cl != 4 && cl != 8) cl = 1;
+  while (cl > 1 && rb.grid.x < (unsigned)cl) cl >>= 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((rb.grid.x + cl - 1) / cl * cl, rb.grid.y, 1);    // padding blocks own no rows
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cl > 1 ? 1 : 0;
+  SN_CUDA(cudaLaunchKernelEx(&cfg, colsum_kernel<MODE, T>, x, ldx, dy, lddy, scale, shift, mean, invstd, M, C,
+                             rb.lx_shift, rb.rows_per_block, sums));
+  return 0;
 }
 
 // sums -> mean/invstd/scale/shift (+ moving statistics, cuDNN convention: running var unbiased); zeroes sums
@@ -280,27 +415,30 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const T* __restr
     s2[k] = (float)sums[C + c + k] * invM;
   }
   for (long r = r0 + ry; r < r1; r += (long)KU * RY) {
-    float v[KU][N], g[KU][N], ad[KU][N];
+    typename VT<T>::Raw rx[KU], rg[KU], ra[KU];
 #pragma unroll
     for (int u = 0; u < KU; ++u) {
       const long rr = r + (long)u * RY;
       if (rr < r1) {
-        ldv(x + rr * ldx + c, v[u]);
-        ldv(dy + rr * lddy + c, g[u]);
-        if (add) ldv(add + rr * ldadd + c, ad[u]);
+        rx[u] = ldraw(x + rr * ldx + c);
+        rg[u] = ldraw(dy + rr * lddy + c);
+        if (add) ra[u] = ldraw(add + rr * ldadd + c);
       }
     }
 #pragma unroll
     for (int u = 0; u < KU; ++u) {
       const long rr = r + (long)u * RY;
       if (rr >= r1) break;
-      float o[N];
+      float v[N], g[N], ad[N], o[N];
+      unpack(rx[u], v);
+      unpack(rg[u], g);
+      if (add) unpack(ra[u], ad);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        const float gk = fmaf(v[u][k], scv[k], shv[k]) > 0.f ? g[u][k] : 0.f;
-        const float xhat = (v[u][k] - muv[k]) * isv[k];
+        const float gk = fmaf(v[k], scv[k], shv[k]) > 0.f ? g[k] : 0.f;
+        const float xhat = (v[k] - muv[k]) * isv[k];
         o[k] = scv[k] * (gk - s1[k] - xhat * s2[k]);
-        if (add) o[k] += ad[u][k];
+        if (add) o[k] += ad[k];
       }
       stv(dx + rr * lddx + c, o);
     }
@@ -522,10 +660,12 @@ __global__ void weight_transpose_batched_kernel(const long long* __restrict__ jo
   }
 }
 
-// dgamma / dbeta of every BatchNorm of the network in ONE launch.  jobs: njobs x 4 int64 = {sums, dgamma, dbeta, C};
-// block = job, threads stride over the channels; accumulates and zeroes the sums (as bn_param_grad_kernel).
+// dgamma / dbeta of every BatchNorm of the network in ONE launch.  jobs: njobs x 5 int64 = {sums, dgamma, dbeta, C,
+// fwd_sums}; block = job, threads stride over the channels; accumulates and zeroes the sums (as bn_param_grad_kernel)
+// and clears the layer's forward-statistics accumulator (fwd_sums, may be 0) for the next step.
 __global__ void bn_param_grad_batched_kernel(const long long* __restrict__ jobs) {
-  const long long* jb = jobs + (size_t)blockIdx.x * 4;
+  const long long* jb = jobs + (size_t)blockIdx.x * 5;
+  double* fwd = reinterpret_cast<double*>(jb[4]);
   double* sums = reinterpret_cast<double*>(jb[0]);
   float* dgamma = reinterpret_cast<float*>(jb[1]);
   float* dbeta = reinterpret_cast<float*>(jb[2]);
@@ -535,6 +675,10 @@ __global__ void bn_param_grad_batched_kernel(const long long* __restrict__ jobs)
     if (dgamma) dgamma[c] += (float)sums[C + c];
     sums[c] = 0.0;
     sums[C + c] = 0.0;
+    if (fwd) {
+      fwd[c] = 0.0;
+      fwd[C + c] = 0.0;
+    }
   }
 }
 
@@ -643,21 +787,45 @@ int ew_grid(long work) {
   return (int)(g > cap ? cap : (g < 1 ? 1 : g));
 }
 
-// Row-blocked launch geometry: ~8 blocks per SM, rows per block a multiple of kUnroll * RY.
-RowBlock row_block(long M, int C, int vec = 4) {
+
+// Grid of a row-blocked kernel: ONE wave of resident blocks.  `occ` = blocks of that kernel an SM can hold (occupancy
+// API, cached per kernel); the rows are cut so that every slab's row blocks together fill <= 148 * occ slots.  Sizing the
+// grid independently of the kernel's occupancy cost up to 2x: e.g. 640 blocks of the bf16 reduction kernel (2 resident
+// blocks per SM = 296 slots) ran as three waves of latency-bound blocks (tools/ew_time.py: 20480 x 256 bf16 backward
+// 47 us for 52 MB).  SNIPER_EW_BPS=<n> overrides occ (A/B runs).
+RowBlock row_block(long M, int C, int vec, int occ) {
   RowBlock rb;
-  const int kUnroll = vec == 8 ? 2 : 4;         // VT<T>::U
   const int cv = C / vec;                       // vectors per row
   rb.lx_shift = cv >= 32 ? 5 : (cv >= 16 ? 4 : 3);
   const int lx = 1 << rb.lx_shift, RY = 256 >> rb.lx_shift;
   const int by = sn::div_up(cv, lx);
-  const int step = kUnroll * RY;
-  long rpb = sn::div_up(M * by, (long)sn::kNumSMs * 8);
-  rpb = (rpb + step - 1) / step * step;
-  if (rpb < step) rpb = step;
+  if (const char* e = getenv("SNIPER_EW_BPS")) occ = atoi(e) > 0 ? atoi(e) : occ;
+  if (occ < 1) occ = 1;
+  long slots = (long)sn::kNumSMs * occ - by;    // ceil() of the row split can add one block per slab
+  if (slots < by) slots = by;
+  long rpb = sn::div_up(M * by, slots);
+  rpb = (rpb + RY - 1) / RY * RY;               // whole thread rows; the kernels guard the unrolled tail
+  if (rpb < RY) rpb = RY;
   rb.rows_per_block = (int)rpb;
   rb.grid = dim3((unsigned)sn::div_up(M, rpb), (unsigned)by, 1);
   return rb;
+}
+
+template <typename K>
+int resident_blocks(K kernel) {
+  // keyed on (kernel address, device): a process may drive several GPUs.  Benign race: worst case two threads query twice.
+  struct Entry { const void* fn; int dev, n; };
+  static Entry table[64];
+  static int used = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < used; ++i)
+    if (table[i].fn == key && table[i].dev == dev) return table[i].n;
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 256, 0) != cudaSuccess || n < 1) n = 4;
+  if (used < 64) { table[used].fn = key; table[used].dev = dev; table[used].n = n; ++used; }
+  return n;
 }
 
 }  // namespace
@@ -670,7 +838,8 @@ int sniper_affine_act(const void* x, long ldx, const float* scale, const float* 
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "affine_act: C/ld must be multiples of 4");
   SN_CHECK(dtype == 0 || dtype == 1, "affine_act: dtype must be 0 (fp32) or 1 (bf16)");
   SN_CHECK(dtype == 0 || (C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0), "affine_act: bf16 needs C/ld multiples of 8");
-  const RowBlock rb = row_block(M, C, dtype == 0 ? 4 : 8);
+  const RowBlock rb = dtype == 0 ? row_block(M, C, 4, resident_blocks(affine_act_kernel<float>))
+                                 : row_block(M, C, 8, resident_blocks(affine_act_kernel<bf16>));
   if (dtype == 0)
     affine_act_kernel<float><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
         static_cast<const float*>(x), ldx, scale, shift, static_cast<float*>(y), ldy, M, C, relu, rb.lx_shift,
@@ -691,15 +860,14 @@ int sniper_bn_stats(const void* x, long ldx, long M, int C, const float* gamma, 
   SN_CHECK(C % 4 == 0 && ldx % 4 == 0, "bn_stats: C/ld must be multiples of 4");
   SN_CHECK(dtype == 0 || dtype == 1, "bn_stats: dtype must be 0 (fp32) or 1 (bf16)");
   SN_CHECK(dtype == 0 || (C % 8 == 0 && ldx % 8 == 0), "bn_stats: bf16 needs C/ld multiples of 8");
-  const RowBlock rb = row_block(M, C, dtype == 0 ? 4 : 8);
+  int rc;
   if (dtype == 0)
-    colsum_kernel<0, float><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
-        static_cast<const float*>(x), ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, M, C, rb.lx_shift,
-        rb.rows_per_block, sums);
+    rc = launch_colsum<0, float>((cudaStream_t)stream, static_cast<const float*>(x), ldx, nullptr, 0, nullptr, nullptr,
+                                 nullptr, nullptr, M, C, sums);
   else
-    colsum_kernel<0, bf16><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
-        static_cast<const bf16*>(x), ldx, nullptr, 0, nullptr, nullptr, nullptr, nullptr, M, C, rb.lx_shift,
-        rb.rows_per_block, sums);
+    rc = launch_colsum<0, bf16>((cudaStream_t)stream, static_cast<const bf16*>(x), ldx, nullptr, 0, nullptr, nullptr,
+                                nullptr, nullptr, M, C, sums);
+  if (rc) return rc;
   SN_LAUNCH_CHECK();
   bn_finalize_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, M, C, gamma, beta, eps, momentum,
                                                                           fix_gamma, moving_mean, moving_var, mean,
@@ -715,6 +883,29 @@ int sniper_bn_finalize(double* sums, long M, int C, const float* gamma, const fl
   bn_finalize_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, M, C, gamma, beta, eps, momentum,
                                                                           fix_gamma, moving_mean, moving_var, mean,
                                                                           invstd, scale, shift);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// sniper_bn_finalize + sniper_affine_act in one launch: y = relu?(bn_train(x)) with the statistics of x already in `sums`
+// (double[2C], left untouched: clear it with sniper_bn_param_grad_batched's fwd_sums column before the next accumulation).
+int sniper_bn_apply_train(const void* x, long ldx, const double* sums, long M, int C, const float* gamma,
+                          const float* beta, float eps, float momentum, int fix_gamma, float* moving_mean,
+                          float* moving_var, float* mean, float* invstd, float* scale, float* shift, void* y, long ldy,
+                          int relu, int dtype, void* stream) {
+  SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "bn_apply_train: C/ld must be multiples of 4");
+  SN_CHECK(dtype == 0 || dtype == 1, "bn_apply_train: dtype must be 0 (fp32) or 1 (bf16)");
+  SN_CHECK(dtype == 0 || (C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0), "bn_apply_train: bf16 needs C/ld multiples of 8");
+  const RowBlock rb = dtype == 0 ? row_block(M, C, 4, resident_blocks(bn_apply_train_kernel<float>))
+                                 : row_block(M, C, 8, resident_blocks(bn_apply_train_kernel<bf16>));
+  if (dtype == 0)
+    bn_apply_train_kernel<float><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const float*>(x), ldx, sums, gamma, beta, eps, momentum, fix_gamma, moving_mean, moving_var, mean,
+        invstd, scale, shift, static_cast<float*>(y), ldy, M, C, relu, rb.lx_shift, rb.rows_per_block);
+  else
+    bn_apply_train_kernel<bf16><<<rb.grid, 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const bf16*>(x), ldx, sums, gamma, beta, eps, momentum, fix_gamma, moving_mean, moving_var, mean,
+        invstd, scale, shift, static_cast<bf16*>(y), ldy, M, C, relu, rb.lx_shift, rb.rows_per_block);
   SN_LAUNCH_CHECK();
   return 0;
 }
@@ -735,20 +926,21 @@ int sniper_bn_relu_bwd(const void* x, long ldx, const void* dy, long lddy, const
   SN_CHECK(dtype == 0 || dtype == 1, "bn_relu_bwd: dtype must be 0 (fp32) or 1 (bf16)");
   SN_CHECK(dtype == 0 || (C % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && ldadd % 8 == 0),
            "bn_relu_bwd: bf16 needs C/ld multiples of 8");
-  const RowBlock rb = row_block(M, C, dtype == 0 ? 4 : 8);
+  const RowBlock rb = dtype == 0 ? row_block(M, C, 4, resident_blocks(bn_relu_bwd_apply_kernel<float>))
+                                 : row_block(M, C, 8, resident_blocks(bn_relu_bwd_apply_kernel<bf16>));
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == 0) {
-    colsum_kernel<1, float><<<rb.grid, 256, 0, st>>>(static_cast<const float*>(x), ldx, static_cast<const float*>(dy),
-                                                     lddy, scale, shift, mean, invstd, M, C, rb.lx_shift,
-                                                     rb.rows_per_block, sums);
+    if (launch_colsum<1, float>(st, static_cast<const float*>(x), ldx, static_cast<const float*>(dy), lddy, scale,
+                                shift, mean, invstd, M, C, sums))
+      return -1;
     SN_LAUNCH_CHECK();
     bn_relu_bwd_apply_kernel<float><<<rb.grid, 256, 0, st>>>(
         static_cast<const float*>(x), ldx, static_cast<const float*>(dy), lddy, scale, shift, mean, invstd, sums,
         static_cast<const float*>(add), ldadd, static_cast<float*>(dx), lddx, M, C, rb.lx_shift, rb.rows_per_block);
   } else {
-    colsum_kernel<1, bf16><<<rb.grid, 256, 0, st>>>(static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(dy),
-                                                    lddy, scale, shift, mean, invstd, M, C, rb.lx_shift,
-                                                    rb.rows_per_block, sums);
+    if (launch_colsum<1, bf16>(st, static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(dy), lddy, scale, shift,
+                               mean, invstd, M, C, sums))
+      return -1;
     SN_LAUNCH_CHECK();
     bn_relu_bwd_apply_kernel<bf16><<<rb.grid, 256, 0, st>>>(
         static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(dy), lddy, scale, shift, mean, invstd, sums,
@@ -853,8 +1045,8 @@ int sniper_weight_transpose_batched(const void* jobs_dev, int njobs, int total_b
   return 0;
 }
 
-// Second half of sniper_bn_relu_bwd for callers that defer it (defer_param_grad != 0 there): jobs_dev = njobs x 4
-// int64 {sums, dgamma, dbeta, C}.  dgamma += s2, dbeta += s1, sums zeroed.
+// Second half of sniper_bn_relu_bwd for callers that defer it (defer_param_grad != 0 there): jobs_dev = njobs x 5
+// int64 {sums, dgamma, dbeta, C, fwd_sums}.  dgamma += s2, dbeta += s1, sums zeroed, fwd_sums (if not 0) zeroed.
 int sniper_bn_param_grad_batched(const void* jobs_dev, int njobs, void* stream) {
   if (njobs <= 0) return 0;
   bn_param_grad_batched_kernel<<<njobs, 256, 0, (cudaStream_t)stream>>>(static_cast<const long long*>(jobs_dev));

@@ -313,7 +313,14 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int u, int 
 // bf16 output, ragged N), EPI_STATS = EPI_DIRECT + fused BatchNorm statistics, EPI_TMA = staged TMA store / reduce,
 // EPI_TMA16 = the same for bf16 output (and bf16 residual): 32 x 32 chunks staged as 32 rows x 64 B with the 64-byte
 // TMA swizzle.
-template <int DT, int CG, int EPI>
+// FEAT (TMA epilogues only): which optional epilogue stages are COMPILED IN -- bit 0 per-column scale / bias, bit 1
+// residual, bit 2 ReLU, bit 3 fused BatchNorm statistics.  kFeatAll keeps every stage behind its runtime flag (the
+// generic kernel); any other mask is a specialisation for launches that use exactly those stages, with the unused
+// ones (and their predicated-off instructions: the short-K launches are bound by the ~400 issue slots per 32 x 32
+// chunk of the generic epilogue) removed at compile time.
+enum { FEAT_AFFINE = 1, FEAT_RES = 2, FEAT_RELU = 4, FEAT_STATS = 8, kFeatAll = 15 };
+
+template <int DT, int CG, int EPI, int FEAT = kFeatAll>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_bp,
@@ -500,6 +507,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     const int m_local = q * 32 + lane;
+    constexpr bool kGen = FEAT == kFeatAll;
+    const bool f_scale = (FEAT & FEAT_AFFINE) && p.scale != nullptr;
+    const bool f_bias = (FEAT & FEAT_AFFINE) && p.bias != nullptr;
+    const bool f_res = (FEAT & FEAT_RES) && (!kGen || p.residual != nullptr);
+    const bool f_relu = (FEAT & FEAT_RELU) && (!kGen || p.relu != 0);
+    const bool f_stats = (FEAT & FEAT_STATS) && (!kGen || p.stats != nullptr);
     int sbuf = 0;   // staging buffer the next chunk uses (EPI_TMA)
     uint32_t lt = 0;
     // Fused BatchNorm statistics (EPI_TMA / EPI_TMA16): per-lane column sums are carried in registers across the tiles
@@ -553,7 +566,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         col_base = tap * (p.wg_cin_blocks * p.block_n) + (tc.tile_n - tap * p.wg_cin_blocks) * p.block_n;
       }
       col_base += half * cols_per_warp;
-      if ((EPI == EPI_TMA || EPI == EPI_TMA16) && p.stats && col_base != st_base) {
+      if ((EPI == EPI_TMA || EPI == EPI_TMA16) && f_stats && col_base != st_base) {
         st_flush();
         st_base = col_base;
       }
@@ -594,7 +607,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
         }
         const __nv_bfloat16* res16 = reinterpret_cast<const __nv_bfloat16*>(p.residual);
-        const bool has_res = res16 != nullptr;
+        const bool has_res = f_res;
         uint4 rn[4];
         if (has_res) {
 #pragma unroll
@@ -647,13 +660,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]);
-            if (p.scale) {
+            if (f_scale) {
               const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + 2 * j);
               const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + 2 * j + 1);
               f[0] *= s0.x; f[1] *= s0.y; f[2] *= s0.z; f[3] *= s0.w;
               f[4] *= s1.x; f[5] *= s1.y; f[6] *= s1.z; f[7] *= s1.w;
             }
-            if (p.bias) {
+            if (f_bias) {
               const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * j);
               const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * j + 1);
               f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
@@ -670,7 +683,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 f[2 * e + 1] += rf.y;
               }
             }
-            if (p.relu) {
+            if (f_relu) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
             }
@@ -684,7 +697,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           }
           fence_proxy_async();
           __syncwarp();
-          if (p.stats) {
+          if (f_stats) {
             // lane l sums column n0 + l of the staged (rounded) chunk over the rows that exist in the tensor
             float sm = 0.f, sq = 0.f;
             const uint8_t* colp = stg + ((lane & 7) << 1);
@@ -742,7 +755,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             rowi[i] = (rr < p.M && tile_ok) ? rr : -1;
           }
         }
-        const bool has_res = p.residual != nullptr;
+        const bool has_res = f_res;
         float4 rn[8];
         if (has_res) {
 #pragma unroll
@@ -844,11 +857,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int j = 0; j < 8; ++j) {
             float4 f = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                    __uint_as_float(v[4 * j + 3]));
-            if (p.scale) {
+            if (f_scale) {
               const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.scale + n0) + j);
               f.x *= s4.x; f.y *= s4.y; f.z *= s4.z; f.w *= s4.w;
             }
-            if (p.bias) {
+            if (f_bias) {
               const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
               f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
             }
@@ -857,14 +870,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               const float4 r4 = *slot;
               f.x += r4.x; f.y += r4.y; f.z += r4.z; f.w += r4.w;
             }
-            if (p.relu) {
+            if (f_relu) {
               f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); f.z = fmaxf(f.z, 0.f); f.w = fmaxf(f.w, 0.f);
             }
             *slot = f;
           }
           fence_proxy_async();
           __syncwarp();
-          if (p.stats) {
+          if (f_stats) {
             // fused BatchNorm statistics of the consumer: lane l sums column n0 + l of the staged chunk over the
             // rows that exist in the tensor (a prefix of the 32), conflict-free through the 128B swizzle
             float sm = 0.f, sq = 0.f;
@@ -1039,7 +1052,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
     }
-    if ((EPI == EPI_TMA || EPI == EPI_TMA16) && p.stats) st_flush();   // this CTA has no more tiles
+    if ((EPI == EPI_TMA || EPI == EPI_TMA16) && f_stats) st_flush();   // this CTA has no more tiles
   }
   if ((EPI == EPI_TMA || EPI == EPI_TMA16) && warp >= 2 && lane == 0) bulk_wait_read0();   // staging buffers are read by in-flight bulk stores
   tc_fence_before();
@@ -1271,6 +1284,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
   }
   const size_t smem = smem_bytes(p.stages, p.block_n, p.stg_bufs);
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const GemmParams);
+  // [operand type][cluster - 1][epilogue]: the generic kernels (every optional epilogue stage behind its runtime flag)
   static const KernelFn kernels[2][2][4] = {
       {{gemm_tc_kernel<DT_TF32, 1, EPI_DIRECT>, gemm_tc_kernel<DT_TF32, 1, EPI_STATS>, gemm_tc_kernel<DT_TF32, 1, EPI_TMA>,
         gemm_tc_kernel<DT_TF32, 1, EPI_TMA16>},
@@ -1280,16 +1294,41 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
         gemm_tc_kernel<DT_BF16, 1, EPI_TMA16>},
        {gemm_tc_kernel<DT_BF16, 2, EPI_DIRECT>, gemm_tc_kernel<DT_BF16, 2, EPI_STATS>, gemm_tc_kernel<DT_BF16, 2, EPI_TMA>,
         gemm_tc_kernel<DT_BF16, 2, EPI_TMA16>}}};
+  // [operand type][EPI_TMA | EPI_TMA16][mask]: 1-SM TMA-epilogue kernels specialised for the stage combinations the
+  // training step launches most: plain (data gradients), statistics (conv -> train BN), residual (data gradient +
+  // shortcut gradient), residual + statistics (conv3 + shortcut -> next unit's BN), scale/bias + ReLU (frozen BN folded)
+  static const int kMasks[5] = {0, FEAT_STATS, FEAT_RES, FEAT_RES | FEAT_STATS, FEAT_AFFINE | FEAT_RELU};
+#define SN_SPEC(DT, EPI)                                                                                         \
+  {gemm_tc_kernel<DT, 1, EPI, 0>, gemm_tc_kernel<DT, 1, EPI, FEAT_STATS>, gemm_tc_kernel<DT, 1, EPI, FEAT_RES>,   \
+   gemm_tc_kernel<DT, 1, EPI, FEAT_RES | FEAT_STATS>, gemm_tc_kernel<DT, 1, EPI, FEAT_AFFINE | FEAT_RELU>}
+  static const KernelFn spec[2][2][5] = {{SN_SPEC(DT_TF32, EPI_TMA), SN_SPEC(DT_TF32, EPI_TMA16)},
+                                         {SN_SPEC(DT_BF16, EPI_TMA), SN_SPEC(DT_BF16, EPI_TMA16)}};
+#undef SN_SPEC
   // per-device one-time setup (a process may drive several GPUs)
   static bool attr_done[64] = {false};
   int dev = 0;
   SN_CUDA(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !attr_done[dev]) {
     for (int a = 0; a < 2; ++a)
-      for (int b = 0; b < 2; ++b)
+      for (int b = 0; b < 2; ++b) {
         for (int c = 0; c < 4; ++c)
           SN_CUDA(cudaFuncSetAttribute(kernels[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        for (int c = 0; c < 5; ++c)
+          SN_CUDA(cudaFuncSetAttribute(spec[a][b][c], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      }
     attr_done[dev] = true;
+  }
+  const int ti = p.dtype == DT_TF32 ? 0 : 1;
+  KernelFn fn = kernels[ti][p.cluster == 2 ? 1 : 0]
+                       [p.epi_tma ? (p.out_bf16 ? EPI_TMA16 : EPI_TMA) : (p.stats ? EPI_STATS : EPI_DIRECT)];
+  {
+    const char* e = getenv("SNIPER_GEMM_SPEC");   // A/B: 0 = always the generic kernel
+    if (p.epi_tma && p.cluster == 1 && !(e && e[0] == '0')) {
+      const int mask = ((p.scale || p.bias) ? FEAT_AFFINE : 0) | (p.residual ? FEAT_RES : 0) | (p.relu ? FEAT_RELU : 0) |
+                       (p.stats ? FEAT_STATS : 0);
+      for (int c = 0; c < 5; ++c)
+        if (kMasks[c] == mask) fn = spec[ti][p.out_bf16 ? 1 : 0][c];
+    }
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1307,7 +1346,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, GemmParams& p, dim3 til
     const char* e = getenv("SNIPER_GEMM_CLUSTER_ATTR");   // A/B: force the (1,1,1) cluster attribute on 1-SM launches
     cfg.numAttrs = (p.cluster > 1 || (e && e[0] == '1')) ? 1 : 0;
   }
-  SN_CUDA(cudaLaunchKernelEx(&cfg, kernels[p.dtype == DT_TF32 ? 0 : 1][p.cluster == 2 ? 1 : 0][p.epi_tma ? (p.out_bf16 ? EPI_TMA16 : EPI_TMA) : (p.stats ? EPI_STATS : EPI_DIRECT)], ma, mb, mc, mbp, p));
+  SN_CUDA(cudaLaunchKernelEx(&cfg, fn, ma, mb, mc, mbp, p));
   SN_LAUNCH_CHECK();
   return 0;
 }

@@ -339,6 +339,8 @@ class BN:
         """have_stats: the producer of x already accumulated sum / sum-of-squares into self.st.sums."""
         if self.frozen:
             return ops.affine_act(x, self.st.scale, self.st.shift, relu=relu)
+        if have_stats and self.fused_apply:
+            return ops.bn_apply_train(x, self.st, eps=cfg.bn_eps, momentum=cfg.bn_momentum, relu=relu)
         if have_stats:
             ops.bn_finalize(self.st, x.numel() // self.C, eps=cfg.bn_eps, momentum=cfg.bn_momentum)
         else:
@@ -347,9 +349,14 @@ class BN:
 
     fuse = False   # set from Cfg.fuse_bn_stats by SniperResNet101
 
+    fused_apply = False   # set per instance by SniperResNet101: statistics go to st.sums_f and the finalisation rides in
+                          # the apply kernel (sums_f is cleared by the end-of-step bn_param_grad_batched launch)
+
     def stats_sink(self):
         """The scratch a producer may accumulate this BN's input statistics into (None: compute them here)."""
-        return None if (self.frozen or not BN.fuse) else self.st.sums
+        if self.frozen or not BN.fuse:
+            return None
+        return self.st.sums_f if self.fused_apply else self.st.sums
 
     defer = False   # set per instance by SniperResNet101: dgamma/dbeta of all layers by one bn_param_grad_batched launch
 
@@ -529,6 +536,8 @@ class SniperResNet101:
         P.finalize(device, lowp=bool(cfg.bf16))
         self.act_dtype = torch.bfloat16 if cfg.bf16 else torch.float32
         self._init_weights(seed, deform_offset_std)
+        for b in self.train_bns():
+            b.fused_apply = bool(cfg.fuse_bn_stats) and os.environ.get("SNIPER_BN_APPLY_FUSED", "1") == "1"
         self.loss_buf = torch.zeros(8, device=device)
         self.cnt_buf = torch.zeros(2, dtype=torch.int32, device=device)
         self.step_count = 0

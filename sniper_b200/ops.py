@@ -351,7 +351,7 @@ class BNPool:
     def __init__(self, total_channels, device):
         self.device = device
         self.f = torch.zeros(8 * total_channels)         # host side until finalize()
-        self.d_len = 2 * total_channels
+        self.d_len = 4 * total_channels
         self.fo = 0
         self.do = 0
         self.pending = []
@@ -389,12 +389,14 @@ class BNState:
             self.moving_mean, self.moving_var = z(), torch.ones(C, device=device)
             self.mean, self.invstd, self.scale, self.shift = z(), z(), z(), z()
             self.sums = torch.zeros(2 * C, dtype=torch.float64, device=device)
+            self.sums_f = torch.zeros(2 * C, dtype=torch.float64, device=device)
             return
         og = pool.take(C, ones=True) if gamma is None else None
         ob = pool.take(C) if beta is None else None
         om, ov = pool.take(C), pool.take(C, ones=True)
         rest = [pool.take(C) for _ in range(4)]
         osum = pool.take_sums(C)
+        osum_f = pool.take_sums(C)
 
         def bind():
             v = lambda o: pool.f[o:o + C]
@@ -403,6 +405,7 @@ class BNState:
             self.moving_mean, self.moving_var = v(om), v(ov)
             self.mean, self.invstd, self.scale, self.shift = [v(o) for o in rest]
             self.sums = pool.d[osum:osum + 2 * C]
+            self.sums_f = pool.d[osum_f:osum_f + 2 * C]       # forward statistics accumulated by the producing conv
         pool.pending.append(bind)
 
 
@@ -421,6 +424,20 @@ def bn_finalize(bn, M, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=Tr
                                    int(fix_gamma), _ptr(bn.moving_mean if update_moving else None),
                                    _ptr(bn.moving_var if update_moving else None), _ptr(bn.mean), _ptr(bn.invstd),
                                    _ptr(bn.scale), _ptr(bn.shift), _stream()))
+
+
+def bn_apply_train(x, bn, eps=2e-5, momentum=0.9, relu=True, fix_gamma=False, update_moving=True, out=None):
+    """relu?(bn_train(x)) when the statistics of x already sit in bn.sums_f (accumulated by the producing conv's
+    epilogue): finalisation + apply in one launch.  bn.sums_f is left as is -- it is cleared by bn_param_grad_batched."""
+    M, C, ldx = _rows(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    check(lib().sniper_bn_apply_train(_ptr(x), ldx, _ptr(bn.sums_f), M, C, _ptr(bn.gamma), _ptr(bn.beta), float(eps),
+                                      float(momentum), int(fix_gamma), _ptr(bn.moving_mean if update_moving else None),
+                                      _ptr(bn.moving_var if update_moving else None), _ptr(bn.mean), _ptr(bn.invstd),
+                                      _ptr(bn.scale), _ptr(bn.shift), _ptr(out), _rows(out)[2], int(relu), _sdt(x),
+                                      _stream()))
+    return out
 
 
 def bn_frozen(bn, eps=2e-5, fix_gamma=False):
@@ -507,7 +524,7 @@ def weight_transpose_batched(table):
 def bn_param_grad_jobs(states, device):
     """states: BNState objects whose backward ran with defer=True."""
     rows = [[b.sums.data_ptr(), 0 if b.dgamma is None else b.dgamma.data_ptr(),
-             0 if b.dbeta is None else b.dbeta.data_ptr(), b.C] for b in states]
+             0 if b.dbeta is None else b.dbeta.data_ptr(), b.C, b.sums_f.data_ptr()] for b in states]
     return torch.tensor(rows, dtype=torch.int64, device=device), len(rows)
 
 

@@ -33,6 +33,36 @@ def test_bn_train_fwd_bwd_matches_torch():
     assert float(bn.sums.abs().sum()) == 0.0  # scratch left zeroed
 
 
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_bn_apply_train_equals_finalize_then_apply(dtype):
+    """sniper_bn_apply_train (finalisation folded into the apply pass) == sniper_bn_finalize + sniper_affine_act, bit for
+    bit, including the published mean / invstd / scale / shift and the moving statistics; the forward accumulator is
+    cleared by the batched parameter-gradient launch."""
+    import torch
+    from sniper_b200 import ops
+    torch.manual_seed(3)
+    dt = getattr(torch, dtype)
+    M, C = 20480 + 24, 256
+    x = (torch.randn(M, C, device="cuda") * 1.5 + 0.3).to(dt)
+    a, b = ops.BNState(C, "cuda"), ops.BNState(C, "cuda")
+    for st in (a, b):
+        st.gamma.copy_(torch.linspace(0.5, 1.5, C)); st.beta.copy_(torch.linspace(-1, 1, C))
+        st.moving_mean.fill_(0.25); st.moving_var.fill_(2.0)
+    xs = x.double()
+    sums = torch.cat([xs.sum(0), (xs * xs).sum(0)])
+    a.sums.copy_(sums); b.sums_f.copy_(sums)
+    ops.bn_finalize(a, M, eps=2e-5, momentum=0.9)
+    ya = ops.affine_act(x, a.scale, a.shift, relu=True)
+    yb = ops.bn_apply_train(x, b, eps=2e-5, momentum=0.9, relu=True)
+    assert torch.equal(ya, yb)
+    for f in ("mean", "invstd", "scale", "shift", "moving_mean", "moving_var"):
+        assert torch.equal(getattr(a, f), getattr(b, f)), f
+    assert torch.equal(b.sums_f, sums)                      # untouched by the apply pass
+    b.dgamma = torch.zeros(C, device="cuda"); b.dbeta = torch.zeros(C, device="cuda")
+    ops.bn_param_grad_batched(ops.bn_param_grad_jobs([b], "cuda"))
+    assert float(b.sums_f.abs().sum()) == 0.0
+
+
 def test_strided_rows_and_frozen_bn():
     import torch
     from sniper_b200 import ops

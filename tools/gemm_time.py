@@ -8,16 +8,35 @@ from sniper_b200 import ops
 
 DT = torch.bfloat16 if os.environ.get("GT_DTYPE") == "bf16" else torch.float32      # operand / output storage
 CASES = [("gemm", 20480, 1024, 256), ("gemmres", 20480, 1024, 256), ("gemmr", 20480, 1024, 256), ("gemmst", 20480, 1024, 256), ("gemm", 327680, 256, 64), ("gemm", 81920, 512, 128),
-         ("gemm", 81920, 128, 512), ("gemm", 20480, 256, 1024), ("conv3x3", 20, 32, 32, 256, 256)]
+         ("gemm", 81920, 128, 512), ("gemm", 20480, 256, 1024), ("conv3x3", 20, 32, 32, 256, 256),
+         ("gemm", 20480, 256, 2304), ("gemm", 18944, 256, 2304), ("gemm", 37888, 256, 2304), ("conv3x3", 37, 32, 32, 256, 256)]
 SETTINGS = [{"SNIPER_GEMM_2SM": "0"}, {"SNIPER_GEMM_2SM": "1"}]
+if os.environ.get("GT_CASES"):          # e.g. GT_CASES="gemm:20480:1024:256;gemmr:20480:1024:256"
+    CASES = [tuple([c.split(":")[0]] + [int(v) for v in c.split(":")[1:]]) for c in os.environ["GT_CASES"].split(";")]
 if len(sys.argv) > 1:
     SETTINGS = [dict(kv.split("=") for kv in a.split(",") if kv) for a in sys.argv[1:]]
 
 
 def timed(fn, reps=20):
+    """Median-free mean over `reps` back-to-back launches replayed from a CUDA graph (no host launch floor: an eager
+    ops call costs ~20 us on the host, more than the short-K kernels take)."""
     for _ in range(3):
         fn(0)
     torch.cuda.synchronize()
+    if os.environ.get("GT_EAGER") != "1":
+        g = torch.cuda.CUDAGraph()
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            with torch.cuda.graph(g, stream=st):
+                for i in range(reps):
+                    fn(i)
+        ts = []
+        for _ in range(5):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); g.replay(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return sorted(ts)[2] * 1e3 / reps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     for i, (a, b) in enumerate(ev):
         a.record(); fn(i); b.record()
@@ -51,7 +70,7 @@ for case in CASES:
         flop = 2.0 * NB * H * W * Cout * 9 * Cin
     out = []
     for st in SETTINGS:
-        for k in ("SNIPER_GEMM_STG", "SNIPER_GEMM_TAIL", "SNIPER_GEMM_TAIL_MAXS", "SNIPER_GEMM_TAIL_MAXP", "SNIPER_GEMM_BN", "SNIPER_GEMM_2SM", "SNIPER_GEMM_TMA_STORE"):
+        for k in ("SNIPER_GEMM_STG", "SNIPER_GEMM_TAIL", "SNIPER_GEMM_TAIL_MAXS", "SNIPER_GEMM_TAIL_MAXP", "SNIPER_GEMM_BN", "SNIPER_GEMM_2SM", "SNIPER_GEMM_TMA_STORE", "SNIPER_GEMM_SPEC"):
             os.environ.pop(k, None)
         os.environ.update(st)
         us = timed(fn)
