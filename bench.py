@@ -80,6 +80,16 @@ def ncu_traffic():
         return None
 
 
+def gpu_head_start(ms=150.0):
+    """Keeps the GPU busy for ~ms milliseconds (a spin kernel on the current stream) so that the host can enqueue a whole
+    eager step behind it: the launches then run back to back and a CUDA-event pair around one launch measures that
+    kernel only.  Without it the per-launch events also count the host's launch latency wherever the GPU has caught up
+    with the host (after the BatchNorm kernels got faster the eager pass became host-bound in places and the summed
+    tcgen05 time read 80 ms instead of 25 ms)."""
+    import torch
+    torch.cuda._sleep(int(ms * 1e-3 * 1.9e9))
+
+
 def entry_point_breakdown(trainer, path):
     """CUDA-event time per C-ABI entry point over one eager, single-stream training step -> markdown table at `path`
     (a cheap complement to the ncu launch list: SNIPER_BREAKDOWN=<file>)."""
@@ -104,6 +114,7 @@ def entry_point_breakdown(trainer, path):
     ws = trainer.net.cfg.wsched
     ws_enabled, ws.enabled = ws.enabled, False
     try:
+        gpu_head_start()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         trainer.net.forward_backward(trainer.static)
@@ -166,6 +177,7 @@ def tc_kernel_time(trainer, peak_bf16):
     ws = trainer.net.cfg.wsched
     ws_enabled, ws.enabled = ws.enabled, False     # single stream: per-launch events must not overlap other kernels
     try:
+        gpu_head_start()
         trainer.net.forward_backward(trainer.static)
         torch.cuda.synchronize()
     finally:

@@ -702,12 +702,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             float sm = 0.f, sq = 0.f;
             const uint8_t* colp = stg + ((lane & 7) << 1);
             const int jc = lane >> 3;
+            if (nvalid == 32) {
+              // full chunk: four independent accumulation chains (the single chain was ~130 dependent cycles per chunk)
+              float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const float xv = __bfloat162float(
+                    *reinterpret_cast<const __nv_bfloat16*>(colp + r * 64 + ((jc ^ ((r >> 1) & 3)) << 4)));
+                s4[r & 3] += xv;
+                q4[r & 3] = fmaf(xv, xv, q4[r & 3]);
+              }
+              sm = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+            } else {
 #pragma unroll 8
-            for (int r = 0; r < nvalid; ++r) {
-              const float xv = __bfloat162float(
-                  *reinterpret_cast<const __nv_bfloat16*>(colp + r * 64 + ((jc ^ ((r >> 1) & 3)) << 4)));
-              sm += xv;
-              sq = fmaf(xv, xv, sq);
+              for (int r = 0; r < nvalid; ++r) {
+                const float xv = __bfloat162float(
+                    *reinterpret_cast<const __nv_bfloat16*>(colp + r * 64 + ((jc ^ ((r >> 1) & 3)) << 4)));
+                sm += xv;
+                sq = fmaf(xv, xv, sq);
+              }
             }
             if (nvalid > 0) st_add(c >> 5, sm, sq);
           }
@@ -883,11 +897,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             float sm = 0.f, sq = 0.f;
             const uint8_t* colp = stg + ((lane & 3) << 2);
             const int jc = lane >> 2;
+            if (nvalid == 32) {
+              float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                const float xv = *reinterpret_cast<const float*>(colp + r * 128 + ((jc ^ (r & 7)) << 4));
+                s4[r & 3] += xv;
+                q4[r & 3] = fmaf(xv, xv, q4[r & 3]);
+              }
+              sm = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+            } else {
 #pragma unroll 8
-            for (int r = 0; r < nvalid; ++r) {
-              const float xv = *reinterpret_cast<const float*>(colp + r * 128 + ((jc ^ (r & 7)) << 4));
-              sm += xv;
-              sq = fmaf(xv, xv, sq);
+              for (int r = 0; r < nvalid; ++r) {
+                const float xv = *reinterpret_cast<const float*>(colp + r * 128 + ((jc ^ (r & 7)) << 4));
+                sm += xv;
+                sq = fmaf(xv, xv, sq);
+              }
             }
             if (nvalid > 0) st_add(c >> 5, sm, sq);
           }

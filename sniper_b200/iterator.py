@@ -306,12 +306,17 @@ class PrefetchingIter(object):
         return raw
 
     def close(self):
+        """Stops and JOINS the worker (a daemon thread still inside a ctypes call when the interpreter exits aborts the
+        process): keep draining the queue so that a worker blocked in put() can see the stop flag."""
+        import queue
         self._stop = True
-        try:
-            while True:
-                self.q.get_nowait()
-        except Exception:
-            pass
+        while self.th.is_alive():
+            try:
+                while True:
+                    self.q.get_nowait()
+            except queue.Empty:
+                pass
+            self.th.join(timeout=0.02)
 
 
 class InputStage(object):
