@@ -1,0 +1,230 @@
+"""Symbol-class facade: the object `main_train.py` / `main_test.py` get from `symbols/faster/resnet_mx_101_e2e.py`.
+
+Mirrors the reference's `Symbol` base class (symbols/symbol.py:9-61) and `resnet_mx_101_e2e`
+(symbols/faster/resnet_mx_101_e2e.py:20-35 constructor, :227-345 get_symbol_rcnn, :450-485 init_weight_rcnn,
+:6-17 checkpoint_callback) with the same method names, argument meaning and dictionary keys, so that the driver code
+around them reads the same:
+
+    sym_inst = resnet_mx_101_e2e(n_proposals=400, momentum=args.momentum)
+    sym = sym_inst.get_symbol_rcnn(config)
+    sym_inst.infer_shape({'data': (20, 3, 512, 512), ...})
+    arg_params, aux_params = load_param(pretrained, epoch)          # sniper_b200.checkpoint.load_param
+    sym_inst.init_weight_rcnn(config, arg_params, aux_params)
+    sym_inst.check_parameter_shapes(arg_params, aux_params, data_shape_dict)
+    net = sym.bind('cuda:0', batch_images=20)                        # -> sniper_b200.model.SniperResNet101
+    net.load_reference(arg_params, aux_params)
+
+What `get_symbol_rcnn` returns is not an MXNet graph: it is a `NetSymbol` that knows the reference's argument / auxiliary /
+output names and shapes (pure host code, usable without a GPU) and binds to the one hand-scheduled network this package
+implements.  Reference symbol FILES are not executed; the graph they describe is `model.SniperResNet101`.
+"""
+import numpy as np
+
+from . import checkpoint as ck
+
+UNITS = (3, 4, 23, 3)
+FILTER_LIST = (64, 256, 512, 1024, 2048)
+
+
+class NetSymbol(object):
+    """Names and shapes of the SNIPER ResNet-101 R-FCN graph as `mx.sym.Symbol` exposes them."""
+
+    def __init__(self, cfg, is_train=True, num_classes=81, num_anchors=21, rois_per_chip=300, max_gt=100):
+        self.cfg, self.is_train = cfg, is_train
+        self.num_classes, self.num_anchors, self.rois, self.max_gt = num_classes, num_anchors, rois_per_chip, max_gt
+        self._args, self._aux = [], []
+        self._build()
+
+    # ---- graph description (resnet_mx_101_e2e.py:36-69 residual_unit, :106-145 residual_unit_deform, :394-448, :227-345)
+    def _conv(self, n, o, i, k, bias=False):
+        self._args.append((n + "_weight", (o, i, k, k)))
+        if bias:
+            self._args.append((n + "_bias", (o,)))
+
+    def _bn(self, n, c):
+        self._args += [(n + "_gamma", (c,)), (n + "_beta", (c,))]
+        self._aux += [(n + "_moving_mean", (c,)), (n + "_moving_var", (c,))]
+
+    def _fc(self, n, o, i):
+        self._args += [(n + "_weight", (o, i)), (n + "_bias", (o,))]
+
+    def _build(self):
+        A, K = self.num_anchors, self.num_classes
+        self._bn("bn_data", 3)
+        self._conv("conv0", 64, 3, 7)
+        self._bn("bn0", 64)
+        cin = FILTER_LIST[0]
+        for si, n in enumerate(UNITS):
+            cout = FILTER_LIST[si + 1]
+            mid = cout // 4
+            for j in range(n):
+                nm = "stage%d_unit%d" % (si + 1, j + 1)
+                ci = cin if j == 0 else cout
+                self._bn(nm + "_bn1", ci); self._conv(nm + "_conv1", mid, ci, 1)
+                self._bn(nm + "_bn2", mid)
+                if si == 3:
+                    self._conv(nm + "_offset", 72, mid, 3, bias=True)
+                self._conv(nm + "_conv2", mid, mid, 3)
+                self._bn(nm + "_bn3", mid); self._conv(nm + "_conv3", cout, mid, 1)
+                if j == 0:
+                    self._conv(nm + "_sc", cout, ci, 1)
+            cin = cout
+        self._conv("rpn_conv_3x3", 512, 3072, 3, True)
+        self._conv("rpn_cls_score", 2 * A, 512, 1, True)
+        self._conv("rpn_bbox_pred", 4 * A, 512, 1, True)
+        self._conv("conv_new_1", 256, 3072, 1, True)
+        self._fc("offset", 2 * 7 * 7, 256 * 7 * 7)
+        self._fc("fc_new_1", 1024, 256 * 7 * 7)
+        self._fc("fc_new_2", 1024, 1024)
+        self._fc("cls_score", K, 1024)
+        self._fc("bbox_pred", 4, 1024)
+
+    # ---- mx.sym.Symbol surface
+    def data_names(self):
+        if self.is_train:
+            return ["data", "im_info", "gt_boxes", "valid_ranges", "label", "bbox_target", "bbox_weight"]
+        return ["data", "im_info", "im_ids", "chip_ids"]
+
+    def list_arguments(self):
+        return self.data_names() + [n for n, _ in self._args]
+
+    def list_auxiliary_states(self):
+        return [n for n, _ in self._aux]
+
+    def list_outputs(self):
+        if self.is_train:      # mx.sym.Group order of get_symbol_rcnn (resnet_mx_101_e2e.py:336-341); metric.py reads it by position
+            return ["rpn_cls_prob_output", "rpn_bbox_loss_output", "cls_prob_reshape_output", "bbox_loss_reshape_output",
+                    "blockgrad0_output"]
+        # test-time group (:386-389): rois, cls_prob, bbox_pred and the three pass-through inputs
+        return ["rois_output", "cls_prob_reshape_output", "bbox_pred_reshape_output", "im_ids", "im_info", "chip_ids"]
+
+    def infer_shape(self, **data_shapes):
+        """(arg_shapes, out_shapes, aux_shapes) in list_arguments / list_outputs / list_auxiliary_states order."""
+        B = data_shapes["data"][0]
+        H, W = data_shapes["data"][2] // 16, data_shapes["data"][3] // 16
+        A, K, R = self.num_anchors, self.num_classes, self.rois
+        dflt = {"data": data_shapes["data"], "im_info": (B, 3), "im_ids": (B,), "chip_ids": (B,),
+                "gt_boxes": (B, self.max_gt, 5), "valid_ranges": (B, 2),
+                "label": (B, A * H * W), "bbox_target": (B, 4 * A, H, W), "bbox_weight": (B, 4 * A, H, W)}
+        arg = [tuple(data_shapes.get(n, dflt[n])) for n in self.data_names()] + [s for _, s in self._args]
+        if self.is_train:
+            out = [(B, 2, A * H, W), (B, 4 * A, H, W), (B, R, K), (B, R, 4), (B, R)]
+        else:
+            out = [(B * R, 5), (B, R, K), (B, R, 4), (B,), (B, 3), (B,)]
+        return arg, out, [s for _, s in self._aux]
+
+    def bind(self, device="cuda:0", batch_images=20, bf16=False, seed=5, **cfg_overrides):
+        """The executor: `model.SniperResNet101` on `device` (needs the CUDA library; fails loudly without a GPU)."""
+        from . import model
+        c = model.Cfg()
+        c.batch_images = batch_images
+        c.bf16 = bool(bf16)
+        for k, v in cfg_overrides.items():
+            setattr(c, k, v)
+        return model.SniperResNet101(c, device=device, seed=seed)
+
+
+class Symbol(object):
+    """symbols/symbol.py:9-61."""
+
+    def __init__(self):
+        self.arg_shape_dict = None
+        self.out_shape_dict = None
+        self.aux_shape_dict = None
+        self.sym = None
+
+    @property
+    def symbol(self):
+        return self.sym
+
+    def get_bbox_param_names(self):
+        raise NotImplementedError()
+
+    def get_symbol(self, cfg, is_train=True):
+        raise NotImplementedError()
+
+    def init_weights(self, cfg, arg_params, aux_params):
+        raise NotImplementedError()
+
+    def get_msra_std(self, shape):
+        fan_in = float(shape[1])
+        if len(shape) > 2:
+            fan_in *= np.prod(shape[2:])
+        return np.sqrt(2 / fan_in)
+
+    def infer_shape(self, data_shape_dict):
+        arg_shape, out_shape, aux_shape = self.sym.infer_shape(**data_shape_dict)
+        self.arg_shape_dict = dict(zip(self.sym.list_arguments(), arg_shape))
+        self.out_shape_dict = dict(zip(self.sym.list_outputs(), out_shape))
+        self.aux_shape_dict = dict(zip(self.sym.list_auxiliary_states(), aux_shape))
+
+    def check_parameter_shapes(self, arg_params, aux_params, data_shape_dict, is_train=True):
+        for k in self.sym.list_arguments():
+            if k in data_shape_dict or (False if is_train else 'label' in k):
+                continue
+            assert k in arg_params, k + ' not initialized'
+            assert tuple(arg_params[k].shape) == tuple(self.arg_shape_dict[k]), \
+                'shape inconsistent for ' + k + ' inferred ' + str(self.arg_shape_dict[k]) + ' provided ' + str(
+                    arg_params[k].shape)
+        for k in self.sym.list_auxiliary_states():
+            assert k in aux_params, k + ' not initialized'
+            assert tuple(aux_params[k].shape) == tuple(self.aux_shape_dict[k]), \
+                'shape inconsistent for ' + k + ' inferred ' + str(self.aux_shape_dict[k]) + ' provided ' + str(
+                    aux_params[k].shape)
+
+
+def checkpoint_callback(bbox_param_names, prefix, means, stds):
+    """resnet_mx_101_e2e.py:6-17: epoch-end callback writing `<prefix>-%04d.params` with the `*_test` box-regression
+    copies.  `arg` / `aux`: dicts of numpy arrays under the reference's names (model.export_reference())."""
+    def _callback(iter_no, sym, arg, aux):
+        if bbox_param_names[0] in arg:
+            ck.save_checkpoint(prefix, iter_no + 1, arg, aux, bbox_param_names=tuple(bbox_param_names))
+    return _callback
+
+
+class resnet_mx_101_e2e(Symbol):
+    """symbols/faster/resnet_mx_101_e2e.py:20-35."""
+
+    def __init__(self, n_proposals=400, momentum=0.95, fix_bn=False, test_nbatch=1):
+        Symbol.__init__(self)
+        self.momentum = momentum
+        self.use_global_stats = True
+        self.workspace = 512
+        self.units = UNITS
+        self.filter_list = list(FILTER_LIST)
+        self.fix_bn = fix_bn
+        self.test_nbatch = test_nbatch
+        self.n_proposals = n_proposals
+
+    def get_bbox_param_names(self):
+        return ['bbox_pred_weight', 'bbox_pred_bias']
+
+    def get_symbol_rcnn(self, cfg, is_train=True):
+        num_classes = getattr(getattr(cfg, "dataset", None), "NUM_CLASSES", 81)
+        net = getattr(cfg, "network", None)
+        num_anchors = getattr(net, "NUM_ANCHORS", 21) if net is not None else 21
+        self.sym = NetSymbol(cfg, is_train=is_train, num_classes=num_classes, num_anchors=num_anchors)
+        return self.sym
+
+    get_symbol = get_symbol_rcnn
+
+    def init_weight_rcnn(self, cfg, arg_params, aux_params, seed=None):
+        """:450-485 -- zeros for every offset layer, N(0, 0.01) weights + zero biases for the RPN and the R-FCN head.
+        Arrays are numpy float32 (the reference's mx.nd arrays); `seed` makes the draw reproducible."""
+        rng = np.random.RandomState(seed) if seed is not None else np.random
+        sh = self.arg_shape_dict
+        zeros = lambda n: np.zeros(sh[n], np.float32)
+        normal = lambda n: (rng.standard_normal(sh[n]) * 0.01).astype(np.float32)
+        for u in (1, 2, 3):
+            arg_params['stage4_unit%d_offset_weight' % u] = zeros('stage4_unit%d_offset_weight' % u)
+            arg_params['stage4_unit%d_offset_bias' % u] = zeros('stage4_unit%d_offset_bias' % u)
+        for n in ('rpn_conv_3x3', 'rpn_cls_score', 'rpn_bbox_pred', 'conv_new_1'):
+            arg_params[n + '_weight'] = normal(n + '_weight')
+            arg_params[n + '_bias'] = zeros(n + '_bias')
+        arg_params['offset_weight'] = zeros('offset_weight')
+        arg_params['offset_bias'] = zeros('offset_bias')
+        for n in ('fc_new_1', 'fc_new_2', 'cls_score', 'bbox_pred'):
+            arg_params[n + '_weight'] = normal(n + '_weight')
+            arg_params[n + '_bias'] = zeros(n + '_bias')
+
+    init_weights = init_weight_rcnn
