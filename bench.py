@@ -288,7 +288,7 @@ def iterator_leg(args, trainer, local_rank, barrier):
     stage = IT.InputStage(cfg, "cuda:%d" % local_rank, args.chips)
     pf = IT.PrefetchingIter(it, depth=3)
     nbytes = []
-    for _ in range(3):
+    for _ in range(8):        # more than n_buffers: every pinned staging buffer is allocated (cudaHostAlloc) before the clock starts
         trainer.step_raw(next(pf), stage)
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -280,6 +280,12 @@ class PrefetchingIter(object):
         self.q = queue.Queue(maxsize=depth)
         self.epochs = epochs
         self._stop = False
+        # Every ctypes call of the training step releases the GIL and has to win it back from the producer thread; with
+        # the default 5 ms switch interval each of those hand-overs can stall the step by up to 5 ms (measured: step_raw
+        # 56 ms instead of 36 ms next to a busy producer).  0.5 ms keeps the hand-over cost small.
+        import sys
+        self._switch = sys.getswitchinterval()
+        sys.setswitchinterval(5e-4)
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
 
@@ -317,6 +323,8 @@ class PrefetchingIter(object):
             except queue.Empty:
                 pass
             self.th.join(timeout=0.02)
+        import sys
+        sys.setswitchinterval(self._switch)
 
 
 class InputStage(object):

@@ -12,7 +12,8 @@ cfg = IT.default_config()
 roidb = IT.synthetic_roidb(24, seed=11, n_prop=300)
 it = IT.MNIteratorE2E(roidb, cfg, batch_size=20, n_buffers=6)
 pf = IT.PrefetchingIter(it, depth=3)
-next(pf)
+for _ in range(12):       # every staging buffer allocated, page-faulted and (with a GPU) pinned
+    next(pf)
 t = time.time()
 n = 30
 for _ in range(n):
@@ -27,7 +28,7 @@ if torch.cuda.is_available():
     tr.load(synth_batch.make_batch(20, seed=100, device="cpu", pinned=True))
     tr.capture()
     stage = IT.InputStage(cfg, "cuda:0", 20)
-    for _ in range(3):
+    for _ in range(8):
         tr.step_raw(next(pf), stage)
     torch.cuda.synchronize()
     tw = ts = 0.0
