@@ -4,6 +4,7 @@ Every function launches on torch's current CUDA stream, allocates outputs with t
 `SniperError` when the native call fails.  There is no CPU fallback.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -162,11 +163,30 @@ def deform_psroi_fwd(data, rois, trans, *, spatial_scale, output_dim, group_size
     S = sample_per_part
     sidx = torch.empty(N * output_dim * P * P, S * S, 4, dtype=torch.int32, device=data.device) if want_sample_idx else None
     ncls = 1 if no_trans else trans.shape[1] // 2
+    if _psroi_tiled(layout, group_size, ncls, C, H, W, S) and not want_sample_idx:
+        rc = lib().sniper_deform_psroi_fwd_tiled(_ptr(data), _ptr(rois), _ptr(None if no_trans else _f32(trans)), N, B, C,
+                                                 H, W, float(spatial_scale), output_dim, group_size, P, part_size, S,
+                                                 float(trans_std), int(no_trans), ncls, _ptr(out), _ptr(cnt), _stream())
+        if rc != -2:
+            check(rc)
+            return out, cnt, sidx
     check(lib().sniper_deform_psroi_fwd(_ptr(data), _ptr(rois), _ptr(None if no_trans else _f32(trans)), N, C, H, W,
                                         float(spatial_scale), output_dim, group_size, P, part_size, S,
                                         float(trans_std), int(no_trans), ncls, layout, _ptr(out), _ptr(cnt),
                                         _ptr(sidx), _stream()))
     return out, cnt, sidx
+
+
+_psroi_ws = {}
+
+
+def _psroi_tiled(layout, group_size, ncls, C, H, W, S):
+    """True when the chip-tiled PSROI kernels are requested (SNIPER_PSROI_TILED=1) and apply; the library re-checks and
+    answers -2 otherwise.  Opt-in: measured 4x SLOWER than the warp-per-bin kernels on B200 (forward 2.0 vs 0.48 ms,
+    backward 4.1 vs 0.85 ms per call at 6000 ROIs) -- with one lane per bin the shared-memory accesses of a warp scatter
+    over pixels (bank conflicts, CAS-loop float atomics), which costs more than the global gathers / REDs it removes."""
+    return (layout == NHWC and group_size == 1 and ncls == 1 and C % 16 == 0 and H * W * 17 * 4 <= 100 * 1024 and S <= 4
+            and os.environ.get("SNIPER_PSROI_TILED", "0") == "1" and os.environ.get("SNIPER_PSROI_EXACT") != "1")
 
 
 def deform_psroi_bwd(top_diff, data, rois, trans, *, spatial_scale, output_dim, group_size, pooled_size,
@@ -181,6 +201,24 @@ def deform_psroi_bwd(top_diff, data, rois, trans, *, spatial_scale, output_dim, 
     if trans_diff is None and not no_trans:
         trans_diff = torch.zeros_like(trans)
     ncls = 1 if no_trans else trans.shape[1] // 2
+    if _psroi_tiled(layout, group_size, ncls, C, H, W, sample_per_part):
+        need = int(lib().sniper_deform_psroi_bwd_tiled_workspace_bytes(N, C, pooled_size, int(no_trans)))
+        ws = None
+        if need:      # caller-owned scratch, kept per device and grown on demand (allocated outside any graph capture
+            key = (data.device.index, "psroi_bwd")      # by the first eager step; the captured steps reuse it)
+            ws = _psroi_ws.get(key)
+            if ws is None or ws.numel() < need:
+                ws = _psroi_ws[key] = torch.empty(need, dtype=torch.uint8, device=data.device)
+        rc = lib().sniper_deform_psroi_bwd_tiled(_ptr(top_diff), _ptr(data), _ptr(rois), _ptr(None if no_trans else trans),
+                                                 N, B, C, H, W, float(spatial_scale), output_dim, group_size, pooled_size,
+                                                 part_size, sample_per_part, float(trans_std), int(no_trans), ncls,
+                                                 _ptr(data_diff), _ptr(trans_diff), _ptr(ws), 0 if ws is None else ws.numel(),
+                                                 _stream())
+        if rc != -2:
+            check(rc)
+            if not no_trans:
+                _libmod.launches[0] += 1          # + trans_reduce_kernel (the counting proxy adds one per call)
+            return data_diff, trans_diff
     check(lib().sniper_deform_psroi_bwd(_ptr(top_diff), _ptr(data), _ptr(rois), _ptr(None if no_trans else trans), N, C,
                                         H, W, float(spatial_scale), output_dim, group_size, pooled_size, part_size,
                                         sample_per_part, float(trans_std), int(no_trans), ncls, layout,
