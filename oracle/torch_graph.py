@@ -45,12 +45,15 @@ def is_fixed(name):
 # tests/test_graph_parity_gpu.py measures that on the device) -- and the products are accumulated exactly (float64).
 # This models the product path's only systematic deviation from real arithmetic, so the whole graph can be compared
 # with a tolerance ~100x tighter than against MODE "exact" (random-init ResNet-101 amplifies each unit's TF32 error by
-# ~4 % per residual unit: 1e-3 after stage 1 grows to ~1e-1 at c4).  conv0 is exempt: the product runs it in fp32 FMA.
+# ~4 % per residual unit: 1e-3 after stage 1 grows to ~1e-1 at c4).  conv0: STEM "tc" (the product's default: im2col +
+# tcgen05 GEMM, operands reduced like every other contraction; in MODE "bf16" the im2col buffer and the weight rows are
+# bf16) or "fma" (SNIPER_STEM_TC=0: exact fp32 FMA kernel).
 # MODE "bf16": the mixed-precision path (Cfg.bf16).  Inside the backbone (LOWP) every tensor the product STORES --
 # activations, the im2col buffer, the bf16 weight copies, and on the way back the gradients of those activations -- is
 # rounded to bf16 (round-to-nearest-even), contractions accumulate exactly; the heads behave as in MODE "tf32".
 MODE = ["exact"]
 LOWP = [False]
+STEM = ["tc"]
 
 
 def _bf16(x):
@@ -260,7 +263,12 @@ def _unit(P, A, x, name, stride, dim_match, train, deform, eps, taps=None):
 def backbone(P, A, data, eps=2e-5, taps=None):
     """resnetc4 + resnetc5(deform=True) + Concat (:243-249).  Returns relu1 = cat(conv_feat, relut) [B,3072,H/16,W/16]."""
     x = _bn(P, A, data, "bn_data", eps, False, relu=False, fix_gamma=True)
-    x = conv2d(x, P["conv0_weight"], None, 2, 3, exact=True)
+    if STEM[0] == "fma" or MODE[0] == "exact":
+        x = conv2d(x, P["conv0_weight"], None, 2, 3, exact=True)
+    elif MODE[0] == "bf16":               # bf16 im2col buffer x bf16 weight rows, exact accumulation
+        x = F.conv2d(_bf16(x), _bf16(P["conv0_weight"]), None, 2, 3)
+    else:
+        x = conv2d(x, P["conv0_weight"], None, 2, 3)
     LOWP[0] = True                        # the reference's Cast(float16) sits here (:405-406)
     x = qs(_bn(P, A, x, "bn0", eps, False))
     if taps is not None:

@@ -45,6 +45,7 @@ SIGNATURES = {
     "sniper_cast_rows": ("i", "plipli" "li" "p"),
     "sniper_maxpool3x3s2_nhwc": ("i", "ppiiiiip"),
     "sniper_stem_conv": ("i", "pppppppiiiip"),
+    "sniper_stem_im2col": ("i", "pppp" "iiiii" "p"),
     "sniper_weight_transpose": ("i", "ppiiiipp"),
     "sniper_weight_transpose_batched": ("i", "piip"),
     "sniper_bn_param_grad_batched": ("i", "pip"),

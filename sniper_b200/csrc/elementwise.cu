@@ -538,6 +538,56 @@ __global__ void __launch_bounds__(kTPB) maxpool3x3s2_kernel(const T* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ stem as a tensor-core contraction: im2col of
+// bn_data(x) for conv0 (7x7, stride 2, pad 3, 3 channels; resnet_mx_101_e2e.py:402-404).  col[(n, oy, ox)][k], k =
+// (kh * 7 + kw) * 3 + c for k < 147 and 0 up to Kp (the MMA's K granularity: 160 for fp32/TF32 rows, 192 for bf16);
+// padding pixels are zero AFTER bn_data, as in the reference graph.  One block = 64 consecutive output pixels of one
+// output row: the 7 x 133 x 3 input patch is staged (normalised) in shared memory, the 64 x Kp block of col is
+// written fully coalesced, two elements per thread.  The 7x7 conv itself then runs on the tcgen05 kernel (M = NB*Ho*Wo,
+// N = 64, K = Kp) with bn0 + ReLU in its epilogue; the FP32-FMA kernel below took 1.0 ms for 24.6 GFLOP.
+constexpr int kStemCols = 64;
+template <typename T>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, const float* __restrict__ in_scale,
+                                                           const float* __restrict__ in_shift, T* __restrict__ col,
+                                                           int H, int W, int Ho, int Wo, int Kp) {
+  constexpr int PW = kStemCols * 2 + 5;            // 133 input columns
+  __shared__ float patch[3][7][PW + 1];
+  const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * kStemCols;
+  const int iy0 = oy * 2 - 3, ix0 = ox0 * 2 - 3;
+  for (int i = threadIdx.x; i < 3 * 7 * PW; i += blockDim.x) {
+    const int c = i / (7 * PW), r = (i / PW) % 7, q = i % PW;
+    const int iy = iy0 + r, ix = ix0 + q;
+    float v = 0.f;
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = fmaf(__ldg(x + (((size_t)n * 3 + c) * H + iy) * W + ix), in_scale[c], in_shift[c]);
+    patch[c][r][q] = v;
+  }
+  __syncthreads();
+  const int half = Kp >> 1;
+  const int cols = min(kStemCols, Wo - ox0);
+  T* dst = col + (((size_t)n * Ho + oy) * Wo + ox0) * Kp;
+  for (int e = threadIdx.x; e < cols * half; e += blockDim.x) {
+    const int row = e / half, k = (e - row * half) * 2;
+    float v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int kk = k + j;
+      if (kk < 147) {
+        const int tap = kk / 3, c = kk - tap * 3, kh = tap / 7, kw = tap - kh * 7;
+        v[j] = patch[c][kh][row * 2 + kw];
+      } else {
+        v[j] = 0.f;
+      }
+    }
+    if (sizeof(T) == 4) {
+      *reinterpret_cast<float2*>(reinterpret_cast<float*>(dst) + (size_t)row * Kp + k) = make_float2(v[0], v[1]);
+    } else {
+      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(dst) + (size_t)row * Kp + k) =
+          __floats2bfloat162_rn(v[0], v[1]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ stem: bn_data -> conv0 7x7/2 -> bn0 -> relu
 // (resnet_mx_101_e2e.py:402-408).  Input NCHW fp32 [NB,3,H,W] (the iterator's layout), output NHWC
 // [NB,H/2,W/2,64].  One block = 8x16 output pixels x 64 channels; weights [64][7][7][3] and the input
@@ -1023,6 +1073,24 @@ int sniper_stem_conv(const float* x_nchw, const float* w /*[64,7,7,3]*/, const f
   else   // the reference casts to fp16 right after conv0 (resnet_mx_101_e2e.py:405-406); bn0 + relu ride in the same pass
     stem_conv_kernel<bf16><<<grid, 128, 0, (cudaStream_t)stream>>>(x_nchw, w, in_scale, in_shift, out_scale, out_shift,
                                                                    static_cast<bf16*>(y_nhwc), NB, H, W, Ho, Wo);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// col [NB*Ho*Wo, Kp] (fp32: Kp a multiple of 32 >= 147; bf16: a multiple of 64) = im2col of bn_data(x) for conv0;
+// feed it to sniper_gemm_nt with the [64, Kp] weight rows ((kh, kw, c)-major, zero-padded) and bn0 + ReLU as epilogue.
+int sniper_stem_im2col(const float* x_nchw, const float* in_scale, const float* in_shift, void* col, int NB, int H,
+                       int W, int Kp, int dtype, void* stream) {
+  SN_CHECK(dtype == 0 || dtype == 1, "stem_im2col: dtype must be 0 (fp32) or 1 (bf16)");
+  SN_CHECK(Kp >= 148 && Kp % 2 == 0, "stem_im2col: Kp must be even and >= 148");
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  dim3 grid(sn::div_up(Wo, kStemCols), Ho, NB);
+  if (dtype == 0)
+    stem_im2col_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, in_scale, in_shift,
+                                                                      static_cast<float*>(col), H, W, Ho, Wo, Kp);
+  else
+    stem_im2col_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(x_nchw, in_scale, in_shift,
+                                                                     static_cast<bf16*>(col), H, W, Ho, Wo, Kp);
   SN_LAUNCH_CHECK();
   return 0;
 }

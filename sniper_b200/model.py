@@ -569,6 +569,7 @@ class SniperResNet101:
                     c.frozen_b = torch.zeros(c.coutp).to(dev)
 
         self.conv0_w = torch.zeros(64, 7, 7, 3).normal_(0, math.sqrt(2.0 / 147), generator=g).to(dev)
+        self._stem_rows = None
         all_bns = [self.bn_data, self.bn0] + [b for u in self.units for b in u.bns()]
         pool = ops.BNPool(sum(b.C for b in all_bns), dev)
         for bn in all_bns:
@@ -647,8 +648,7 @@ class SniperResNet101:
 
         # ---- backbone forward
         lowp = bool(cfg.bf16)
-        x = ops.stem_conv(data, self.conv0_w, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
-                          self.bn0.st.shift, out_dtype=self.act_dtype)     # the reference's Cast sits right after conv0
+        x = self.stem(data)                                             # the reference's Cast sits right after conv0
         x = ops.maxpool3x3s2(x)
         Hf = data.shape[2] // cfg.feat_stride
         # Concat(c4, c5): fp32.  fp32 mode: the two producing convs write their channel slices in place.  Mixed
@@ -759,8 +759,7 @@ class SniperResNet101:
         B = data.shape[0]
         for b in self.train_bns():
             ops.bn_frozen(b.st, cfg.bn_eps)        # scale/shift from the moving statistics (the next training step
-        x = ops.stem_conv(data, self.conv0_w, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
-                          self.bn0.st.shift, out_dtype=self.act_dtype)       # recomputes them from batch statistics)
+        x = self.stem(data)                                               # recomputes them from batch statistics)
         x = ops.maxpool3x3s2(x)
         n1, n2, n3, n4 = cfg.units
         Hf, Wf = data.shape[2] // cfg.feat_stride, data.shape[3] // cfg.feat_stride
@@ -811,6 +810,17 @@ class SniperResNet101:
     def _named_bns(self):
         return [self.bn_data, self.bn0] + [b for u in self.units for b in u.bns()]
 
+    def stem(self, data):
+        """bn_data -> conv0 -> bn0 -> ReLU (resnetc4 :402-408), NHWC out.  Default: im2col + tcgen05 GEMM (TF32 for the
+        fp32 configuration, bf16 operands in the mixed-precision one); SNIPER_STEM_TC=0: the FP32-FMA direct kernel."""
+        if os.environ.get("SNIPER_STEM_TC", "1") != "1":
+            return ops.stem_conv(data, self.conv0_w, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
+                                 self.bn0.st.shift, out_dtype=self.act_dtype)
+        if self._stem_rows is None:            # frozen layer: built once (load_reference resets it)
+            self._stem_rows = ops.stem_rows(self.conv0_w, self.act_dtype)
+        return ops.stem_conv_tc(data, self._stem_rows, self.bn_data.st.scale, self.bn_data.st.shift, self.bn0.st.scale,
+                                self.bn0.st.shift, out_dtype=self.act_dtype)
+
     def load_reference(self, arg, aux, allow_missing=False):
         """Loads a reference checkpoint (`arg_params`, `aux_params` as numpy dicts, e.g. checkpoint.read_params of a
         released SNIPER `.params` file): OIHW -> tap-major rows, NCHW-flattened FC inputs -> NHWC, fused heads.
@@ -823,6 +833,7 @@ class SniperResNet101:
         dev = self.device
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
         skipped = []
+        self._stem_rows = None
         if "conv0_weight" in arg or not allow_missing:
             self.conv0_w.copy_(t(arg["conv0_weight"].transpose(0, 2, 3, 1)))
         else:

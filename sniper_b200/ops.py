@@ -533,6 +533,28 @@ def stem_conv(x_nchw, w, in_scale, in_shift, out_scale, out_shift, out_dtype=tor
     return y
 
 
+def stem_rows(w, dtype=torch.float32):
+    """conv0 weights [64,7,7,3] -> the B operand of the tensor-core stem: [64, Kp] rows in (kh, kw, c) order, zero-padded
+    to the MMA's K granularity (160 fp32 / 192 bf16)."""
+    Kp = 160 if dtype == torch.float32 else 192
+    rows = torch.zeros(64, Kp, device=w.device, dtype=torch.float32)
+    rows[:, :147] = w.reshape(64, 147)
+    return rows.to(dtype)
+
+
+def stem_conv_tc(x_nchw, rows, in_scale, in_shift, out_scale, out_shift, out_dtype=torch.float32):
+    """The stem on the tensor cores: im2col of bn_data(x) (sniper_stem_im2col) + tcgen05 GEMM with bn0 + ReLU in the
+    epilogue.  rows = stem_rows(conv0_w, dtype): fp32 rows run as TF32, bf16 rows as bf16 (fp32 accumulation)."""
+    NB, C, H, W = x_nchw.shape
+    assert C == 3 and rows.shape[0] == 64
+    Ho, Wo, Kp = (H - 1) // 2 + 1, (W - 1) // 2 + 1, rows.shape[1]
+    col = torch.empty(NB * Ho * Wo, Kp, device=x_nchw.device, dtype=rows.dtype)
+    check(lib().sniper_stem_im2col(_ptr(x_nchw), _ptr(in_scale), _ptr(in_shift), _ptr(col), NB, H, W, Kp, _sdt(col),
+                                   _stream()))
+    y = gemm_nt(col, rows, scale=out_scale, bias=out_shift, relu=True, out_dtype=out_dtype)
+    return y.view(NB, Ho, Wo, 64)
+
+
 def weight_transpose(w, Cout, T, Cin, sel_dev, out=None):
     """w [Cout,T,Cin] -> [Cin, len(sel), Cout] with out[ci,j,co] = w[co, sel[j], ci] (data-gradient operand)."""
     Tsel = sel_dev.numel()

@@ -107,6 +107,44 @@ def test_maxpool_stem_transpose_sgd():
     assert (mom - m1).abs().max().item() < 1e-6 and (wv - (w0 + m1)).abs().max().item() < 1e-6
 
 
+@pytest.mark.parametrize("dtype", ["float32", "bfloat16"])
+def test_stem_on_tensor_cores(dtype):
+    """im2col of bn_data(x) (bit-exact against its definition, odd sizes and a ragged last block of columns) + tcgen05
+    GEMM with bn0 + ReLU: equals the float64 convolution of the operands the MMA really reads (fp32 words truncated to
+    TF32, or the stored bf16 values) to accumulation rounding, and the FP32-FMA stem kernel to TF32 / bf16 precision."""
+    import torch
+    import torch.nn.functional as F
+    from sniper_b200 import ops
+    torch.manual_seed(4)
+    dt = getattr(torch, dtype)
+    NB, H, W = 2, 70, 200                      # Ho 35, Wo 100: one full block of 64 columns + a ragged one of 36
+    img = torch.randn(NB, 3, H, W, device="cuda") * 50
+    w = torch.randn(64, 7, 7, 3, device="cuda") * 0.05
+    isc, ish = torch.rand(3, device="cuda") / 50 + 0.01, torch.randn(3, device="cuda") * 0.1
+    osc, osh = torch.rand(64, device="cuda") + 0.5, torch.randn(64, device="cuda")
+    rows = ops.stem_rows(w, dt)
+    Kp = rows.shape[1]
+    assert Kp == (160 if dt == torch.float32 else 192) and float(rows[:, 147:].abs().max()) == 0.0
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    col = torch.empty(NB * Ho * Wo, Kp, device="cuda", dtype=dt)
+    ops.check(ops.lib().sniper_stem_im2col(img.data_ptr(), isc.data_ptr(), ish.data_ptr(), col.data_ptr(), NB, H, W, Kp,
+                                           0 if dt == torch.float32 else 1, torch.cuda.current_stream().cuda_stream))
+    xin = torch.addcmul(ish.view(1, 3, 1, 1), img, isc.view(1, 3, 1, 1))          # one fma, like the kernel
+    ref = F.unfold(xin, 7, padding=3, stride=2).view(NB, 3, 49, Ho * Wo).permute(0, 3, 2, 1).reshape(NB * Ho * Wo, 147)
+    assert torch.equal(col[:, :147], ref.to(dt)) and float(col[:, 147:].abs().max()) == 0.0
+    y = ops.stem_conv_tc(img, rows, isc, ish, osc, osh, out_dtype=dt)
+    if dt == torch.float32:
+        trunc = lambda t: (t.contiguous().view(torch.int32) & -8192).view(torch.float32)
+        a, b = trunc(col), trunc(rows)
+    else:
+        a, b = col, rows
+    r = torch.relu((a.double() @ b.double().t()) * osc.double() + osh.double()).view(NB, Ho, Wo, 64)
+    tol = 2e-5 if dt == torch.float32 else 1e-2            # accumulation order / the bf16 rounding of the stored output
+    assert y.shape == r.shape and float((y.double() - r).abs().max()) <= tol * float(r.abs().max())
+    fma = ops.stem_conv(img, w, isc, ish, osc, osh)
+    assert float((y.float() - fma).abs().max()) <= (2e-3 if dt == torch.float32 else 2e-2) * float(fma.abs().max())
+
+
 def test_losses_match_torch():
     import torch
     import torch.nn.functional as F

@@ -35,6 +35,7 @@ DOC = {
     "sniper_affine_relu_bwd": "Backward of relu?(x*scale+shift) for frozen BN.",
     "sniper_relu_bwd": "dx = dy * (y > 0).",
     "sniper_maxpool3x3s2_nhwc": "Pooling max 3x3 stride 2 pad 1 (resnet_mx_101_e2e.py:409; nn/pool.cuh).",
+    "sniper_stem_im2col": "im2col of bn_data(x) for conv0 (resnet_mx_101_e2e.py:402-404) so that the 7x7 stem runs on the tcgen05 kernel (sniper_gemm_nt with bn0 + ReLU as epilogue).",
     "sniper_stem_conv": "bn_data -> conv0 7x7/2 -> bn0 -> relu (resnet_mx_101_e2e.py:402-408), NCHW in, NHWC out.",
     "sniper_weight_transpose": "wt[ci, j, co] = w[co, sel[j], ci]: operand layout for data gradients.",
     "sniper_weight_transpose_batched": "Every sniper_weight_transpose of a training step in one launch (device job table).",
