@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(kTPB) maxpool3x3s2_kernel(const T* __restrict_
 // (kh * 7 + kw) * 3 + c for k < 147 and 0 up to Kp (the MMA's K granularity: 160 for fp32/TF32 rows, 192 for bf16);
 // padding pixels are zero AFTER bn_data, as in the reference graph.  One block = 64 consecutive output pixels of one
 // output row: the 7 x 133 x 3 input patch is staged (normalised) in shared memory, the 64 x Kp block of col is
-// written fully coalesced, two elements per thread.  The 7x7 conv itself then runs on the tcgen05 kernel (M = NB*Ho*Wo,
+// written fully coalesced, 16 bytes per thread.  The 7x7 conv itself then runs on the tcgen05 kernel (M = NB*Ho*Wo,
 // N = 64, K = Kp) with bn0 + ReLU in its epilogue; the FP32-FMA kernel below took 1.0 ms for 24.6 GFLOP.
 constexpr int kStemCols = 64;
 template <typename T>
@@ -563,14 +563,15 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     patch[c][r][q] = v;
   }
   __syncthreads();
-  const int half = Kp >> 1;
+  constexpr int V = 16 / (int)sizeof(T);           // elements per 16-byte store: 4 fp32 / 8 bf16
+  const int vecs = Kp / V;
   const int cols = min(kStemCols, Wo - ox0);
   T* dst = col + (((size_t)n * Ho + oy) * Wo + ox0) * Kp;
-  for (int e = threadIdx.x; e < cols * half; e += blockDim.x) {
-    const int row = e / half, k = (e - row * half) * 2;
-    float v[2];
+  for (int e = threadIdx.x; e < cols * vecs; e += blockDim.x) {
+    const int row = e / vecs, k = (e - row * vecs) * V;
+    float v[V];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
+    for (int j = 0; j < V; ++j) {
       const int kk = k + j;
       if (kk < 147) {
         const int tap = kk / 3, c = kk - tap * 3, kh = tap / 7, kw = tap - kh * 7;
@@ -579,11 +580,17 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
         v[j] = 0.f;
       }
     }
+    T* o = dst + (size_t)row * Kp + k;
     if (sizeof(T) == 4) {
-      *reinterpret_cast<float2*>(reinterpret_cast<float*>(dst) + (size_t)row * Kp + k) = make_float2(v[0], v[1]);
+      *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
     } else {
-      *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<bf16*>(dst) + (size_t)row * Kp + k) =
-          __floats2bfloat162_rn(v[0], v[1]);
+      uint32_t w[V / 2];
+#pragma unroll
+      for (int j = 0; j < V / 2; ++j) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2 % (V / 2)], w[3 % (V / 2)]);
     }
   }
 }
@@ -1082,7 +1089,8 @@ int sniper_stem_conv(const float* x_nchw, const float* w /*[64,7,7,3]*/, const f
 int sniper_stem_im2col(const float* x_nchw, const float* in_scale, const float* in_shift, void* col, int NB, int H,
                        int W, int Kp, int dtype, void* stream) {
   SN_CHECK(dtype == 0 || dtype == 1, "stem_im2col: dtype must be 0 (fp32) or 1 (bf16)");
-  SN_CHECK(Kp >= 148 && Kp % 2 == 0, "stem_im2col: Kp must be even and >= 148");
+  SN_CHECK(Kp >= 148 && Kp % (dtype == 0 ? 4 : 8) == 0 && ((uintptr_t)col & 15) == 0,
+           "stem_im2col: Kp must be >= 148 and a multiple of 4 (fp32) / 8 (bf16), col 16-byte aligned");
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   dim3 grid(sn::div_up(Wo, kStemCols), Ho, NB);
   if (dtype == 0)
