@@ -306,6 +306,47 @@ def iterator_leg(args, trainer, local_rank, barrier):
             "chips_in_epoch": int(it.chip_count)}
 
 
+def run_config5(args):
+    """BASELINE config 5: AutoFocus inference over TEST.SCALES (480,512) -> (800,1280) -> (1400,2000) with
+    DO_PRUNING [F,T,T] on synthetic 1333x800 images, random-init weights (so the FocusPixel maps and detections are
+    noise: the numbers measure the machinery, not accuracy).  One JSON line: imgs/s over the whole pyramid (second pass,
+    after a warm-up pass), per-scale seconds, device soft-NMS latency and the host `cpu_soft_nms` time on the same
+    problems for comparison."""
+    import numpy as np
+    import torch
+    from sniper_b200 import inference, iterator as IT, model, synth_batch, tester as TS
+    n = int(args.config5)
+    cfg = IT.default_config()
+    rng = np.random.RandomState(5)
+    roidb = [dict(width=W, height=H, image_data=rng.randint(0, 256, (H, W, 3)).astype(np.uint8))
+             for (W, H) in [((1333, 800) if rng.rand() < 0.7 else (800, 1333)) for _ in range(n)]]
+    mc = model.Cfg()
+    mc.batch_images = 2
+    net = model.SniperResNet101(mc, deform_offset_std=0.01)
+    net.train_step(synth_batch.make_batch(2, seed=7, device="cuda"), lr=0.001)
+    net.enable_autofocus(seed=3)
+    TS.imdb_detection_wrapper(net, cfg, roidb)          # warm-up pass over the same images (allocator, lazy kernel loading)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    boxes, stats = TS.imdb_detection_wrapper(net, cfg, roidb, nms_backend="device")
+    torch.cuda.synchronize()
+    total = time.time() - t0
+    t1 = time.time()
+    TS.imdb_detection_wrapper(net, cfg, roidb, nms_backend="host")
+    host_total = time.time() - t1
+    ndet = int(sum(len(boxes[j][i]) for j in range(1, 81) for i in range(n)))
+    print(json.dumps({"metric": "AutoFocus inference images/sec (ResNet-101, 3 scales)", "value": round(n / total, 3),
+                      "unit": "images/s", "n_gpus": 1, "images": n, "seconds": round(total, 3),
+                      "config": {"workload": "BASELINE.json configs[4]: AutoFocus inference pyramid, synthetic 1333x800 images, "
+                                             "random-init weights", "scales": [list(s) for s in cfg.TEST.SCALES],
+                                 "batch_images": list(cfg.TEST.BATCH_IMAGES)},
+                      "per_scale": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in st.items()}
+                                    for st in stats["scales"]],
+                      "soft_nms_device_s": round(stats["nms_s"], 4),
+                      "same_pyramid_with_host_soft_nms_s": round(host_total, 3), "detections": ndet,
+                      "data": "synthetic"}))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -454,9 +495,14 @@ def main():
     ap.add_argument("--bf16", action="store_true", help="run the main measurement in mixed precision (configs[2])")
     ap.add_argument("--skip-config3", action="store_true", help="do not append the bf16 block to the JSON line")
     ap.add_argument("--skip-iterator", action="store_true", help="do not measure the e2e_iterator block")
+    ap.add_argument("--config5", type=int, default=0, metavar="N_IMAGES",
+                    help="instead of the training bench: BASELINE config 5, the AutoFocus inference pyramid on N synthetic "
+                         "1333x800 images (imgs/s, per-scale detect / post-processing time, soft-NMS latency)")
     args = ap.parse_args()
     args.iterator_leg = not args.skip_iterator
-    if args.impl == "reference":
+    if args.config5:
+        run_config5(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

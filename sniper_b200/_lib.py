@@ -62,6 +62,7 @@ SIGNATURES = {
     "sniper_anchor_target": ("i", "ppippipp" "iiii" "pipi" "dd" "ppppp" "p"),
     "sniper_soft_nms_batched": ("i", "ppifffuppp"),
     "sniper_chip_input": ("i", "ppppiip"),
+    "sniper_chip_input_hw": ("i", "ppppiiip"),
     "sniper_anchor_subsample": ("i", "pppiiiiiiup"),
     "sniper_chips_generate": ("i", "piiiiipi"),
     "sniper_cpu_nms": ("i", "ppidp"),

@@ -1492,8 +1492,12 @@ int sniper_conv2d_nhwc(const void* X, long x_ld, int NB, int H, int W, int Cin, 
   SN_CHECK(Cin % E == 0, "conv: Cin (%d) must be a multiple of %d", Cin, E);
   SN_CHECK(ntaps >= 1 && ntaps <= kMaxTaps, "conv: ntaps (%d) out of range", ntaps);
   SN_CHECK(stride == 1 || stride == 2, "conv: stride must be 1 or 2");
-  int tile_w = Wo >= 128 ? 128 : Wo;
-  SN_CHECK(128 % tile_w == 0 && Wo % tile_w == 0, "conv: Wo (%d) must divide or be a multiple of 128", Wo);
+  // 128 output pixels per tile as tile_h rows x tile_w columns, tile_w = the largest power of two <= 128 dividing Wo
+  // (training shapes: Wo = 32 ... 128 -> whole rows; inference canvases of any width that is a multiple of 8 pixels at
+  // this layer's stride: narrower, taller tiles; rows past Ho are clipped by the TMA)
+  int tile_w = 128;
+  while (tile_w > 1 && Wo % tile_w != 0) tile_w >>= 1;
+  SN_CHECK(tile_w >= 8, "conv: Wo (%d) must be a multiple of 8", Wo);
   int tile_h = 128 / tile_w;
   SN_CHECK(tile_w * stride <= 256, "conv: TMA box too wide");
   GemmParams p;

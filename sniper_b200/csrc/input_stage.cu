@@ -41,15 +41,15 @@ __device__ __forceinline__ void taps(int d, double inv_scale, int n_src, int& i0
   c1 = (int)rintf(f * 2048.f);
 }
 
-// data[b, j, y, x] (fp32 NCHW, S x S) = resized(chip b)[y, x, 2 - j] - mean[2 - j] inside the resized extent, 0 outside
+// data[b, j, y, x] (fp32 NCHW, SH x SW) = resized(chip b)[y, x, 2 - j] - mean[2 - j] inside the resized extent, 0 outside
 __global__ void __launch_bounds__(256) chip_input_kernel(const uint8_t* __restrict__ src, const ChipDesc* __restrict__ tab,
                                                          const float* __restrict__ means_bgr, float* __restrict__ data,
-                                                         int B, int S) {
-  const long total = (long)B * S * S;
+                                                         int B, int SH, int SW) {
+  const long total = (long)B * SH * SW;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % S);
-    const int y = (int)((i / S) % S);
-    const int b = (int)(i / ((long)S * S));
+    const int x = (int)(i % SW);
+    const int y = (int)((i / SW) % SH);
+    const int b = (int)(i / ((long)SH * SW));
     const ChipDesc d = tab[b];
     float out[3] = {0.f, 0.f, 0.f};
     if (y < d.dst_h && x < d.dst_w && d.src_h > 0 && d.src_w > 0) {
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) chip_input_kernel(const uint8_t* __restri
     const bool inside = (y < d.dst_h && x < d.dst_w);
 #pragma unroll
     for (int j = 0; j < 3; ++j)     // output channel j = BGR channel 2 - j, mean-subtracted; padding stays 0
-      data[(((long)b * 3 + j) * S + y) * S + x] = inside ? out[2 - j] - means_bgr[2 - j] : 0.f;
+      data[(((long)b * 3 + j) * SH + y) * SW + x] = inside ? out[2 - j] - means_bgr[2 - j] : 0.f;
   }
 }
 
@@ -189,14 +189,24 @@ extern "C" {
 // src: device copy of the host staging buffer (uint8 BGR HWC rectangles back to back); table: device int64[B][8] =
 // {src_off, src_h, src_w, dst_h, dst_w, flipped, bits of the float64 scale, 0}; means_bgr: device float[3]
 // (cfg.network.PIXEL_MEANS order); data: [B,3,S,S] fp32, fully written.
+int sniper_chip_input_hw(const void* src, const void* table, const float* means_bgr, float* data, int B, int SH, int SW,
+                         void* stream);
+
 int sniper_chip_input(const void* src, const void* table, const float* means_bgr, float* data, int B, int S,
                       void* stream) {
-  SN_CHECK(B > 0 && S > 0, "chip_input: empty batch");
-  const long total = (long)B * S * S;
+  return sniper_chip_input_hw(src, table, means_bgr, data, B, S, S, stream);
+}
+
+// The same with a rectangular canvas [B,3,SH,SW]: the test iterator pads a batch of chips to the largest resized chip
+// (MNIteratorTestAutoFocus._get_batch, im_worker.worker_autofocus lib/data_utils/data_workers.py:51-78).
+int sniper_chip_input_hw(const void* src, const void* table, const float* means_bgr, float* data, int B, int SH, int SW,
+                         void* stream) {
+  SN_CHECK(B > 0 && SH > 0 && SW > 0, "chip_input: empty batch");
+  const long total = (long)B * SH * SW;
   long g = (total + 255) / 256;
   const long cap = (long)sn::kNumSMs * 16;
   chip_input_kernel<<<(int)(g > cap ? cap : g), 256, 0, (cudaStream_t)stream>>>(
-      static_cast<const uint8_t*>(src), static_cast<const ChipDesc*>(table), means_bgr, data, B, S);
+      static_cast<const uint8_t*>(src), static_cast<const ChipDesc*>(table), means_bgr, data, B, SH, SW);
   SN_LAUNCH_CHECK();
   return 0;
 }

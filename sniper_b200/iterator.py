@@ -404,4 +404,9 @@ def default_config(neg=True):
                        ANCHOR_RATIOS=[0.5, 1, 2], RPN_FEAT_STRIDE=16, NUM_ANCHORS=21),
              TRAIN=S(SCALES=[(1400, 2000), (800, 1280), (-1, 512)], VALID_RANGES=[(-1, 80), (32, 150), (120, -1)],
                      CPP_CHIPS=True, USE_NEG_CHIPS=neg, RPN_BATCH_SIZE=256, RPN_FG_FRACTION=0.5,
-                     RPN_POSITIVE_OVERLAP=0.5, RPN_NEGATIVE_OVERLAP=0.4, BATCH_IMAGES=16))
+                     RPN_POSITIVE_OVERLAP=0.5, RPN_NEGATIVE_OVERLAP=0.4, BATCH_IMAGES=16),
+             # TEST block of configs/faster/sniper_res101_e2e_autofocus.yml:191-245 (AutoFocus inference, BASELINE config 5)
+             TEST=S(SCALES=[(480, 512), (800, 1280), (1400, 2000)], BATCH_IMAGES=[8, 8, 2], MAX_PER_IMAGE=200,
+                    VALID_RANGES=[(75, -1), (32, 180), (-1, 75)], AUTO_FOCUS=True, DO_PRUNING=[False, True, True],
+                    CHIP_HYPERPARAMS=[(3, 0.02, 16), (3, 0.2, 20)], NMS=0.45, NMS_SIGMA=0.55),
+             dataset=S(NUM_CLASSES=81))

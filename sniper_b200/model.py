@@ -541,6 +541,41 @@ class SniperResNet101:
         self.loss_buf = torch.zeros(8, device=device)
         self.cnt_buf = torch.zeros(2, dtype=torch.int32, device=device)
         self.step_count = 0
+        self.af = None          # AutoFocus branch (inference): enable_autofocus()
+
+    # ---------------------------------------------------------------- AutoFocus branch (resnet_mx_101_e2e.py:259-267, 385-386)
+    def enable_autofocus(self, seed=9, arg=None):
+        """conv_new_2 (3x3, 3072 -> 256) + ReLU -> conv_new_3 (1x1) + ReLU -> conv_new_out (1x1 -> 2) on the concat
+        feature map; `forward_inference(autofocus=True)` returns its channel softmax, the FocusPixel map of
+        `cfg.TEST.AUTO_FOCUS`.  Inference-only here (the AutoFocus training label `scale_label` is not built): the three
+        layers live outside the parameter store.  arg: reference-named weights (`conv_new_2_weight` OIHW ...), else
+        N(0, 0.01) like init_weight_rcnn (:468-474)."""
+        from . import checkpoint as ck
+        dev = self.device
+        g = torch.Generator()
+        g.manual_seed(seed)
+        specs = (("conv_new_2", 3072, 256, 3, 1, None), ("conv_new_3", 256, 256, 1, 0, None), ("conv_new_out", 256, 2, 1, 0, 32))
+        convs = []
+        for name, cin, cout, k, pad, cpad in specs:
+            c = Conv(self.P, name, cin, cout, k, pad=pad, bias=True, trainable=False, cout_pad=cpad)
+            w = torch.zeros(c.coutp, c.K)
+            b = torch.zeros(c.coutp)
+            if arg is not None and name + "_weight" in arg:
+                w[:cout] = torch.from_numpy(ck.conv_to_rows(np.asarray(arg[name + "_weight"], np.float32)))
+                b[:cout] = torch.from_numpy(np.asarray(arg[name + "_bias"], np.float32))
+            else:
+                w[:cout].normal_(0, 0.01, generator=g)
+            c.frozen_w, c.frozen_b = w.to(dev), b.to(dev)
+            convs.append(c)
+        self.af = convs
+
+    def focus_map(self, cat):
+        """scale_prob[:, 1] = softmax over the two channels of conv_new_out: [B, Hf, Wf] probability of 'focus'."""
+        c2, c3, co = self.af
+        x = c2.fwd(cat, relu=True)
+        x = c3.fwd(x, relu=True)
+        z = co.fwd(x)[..., :2]
+        return torch.softmax(z, dim=-1)[..., 1]
 
     # ---------------------------------------------------------------- init (init_weight_rcnn :450-485)
     def _init_weights(self, seed, deform_offset_std):
@@ -750,7 +785,7 @@ class SniperResNet101:
                 self.step_count += 1
             yield out
 
-    def forward_inference(self, data, im_info, suppress_anchor_types=False):
+    def forward_inference(self, data, im_info, suppress_anchor_types=False, autofocus=False):
         """get_symbol_rcnn(cfg, is_train=False) (resnet_mx_101_e2e.py:227-345 with the test branch :258-266, 321-326):
         backbone with moving-statistics BN -> RPN -> MultiProposal (device inference proposal op) -> deformable
         R-FCN head -> (rois [B*R,5], rpn scores [B*R], cls_prob [B*R,K], bbox_pred [B*R,4]).  No parameter is touched."""
@@ -778,6 +813,11 @@ class SniperResNet101:
         rpn = self.rpn_conv.fwd(cat, relu=True)
         head = self.rpn_head.fwd(rpn)
         feat = self.conv_new_1.fwd(cat, relu=True)
+        fmap = None
+        if autofocus:
+            if self.af is None:
+                raise RuntimeError("forward_inference(autofocus=True): call enable_autofocus() first")
+            fmap = self.focus_map(cat)
         prob = torch.empty(B, Hf, Wf, 2 * A, device=data.device)
         ignore = torch.full((B, A * Hf * Wf), -1.0, device=data.device)
         cnt = torch.ones(1, dtype=torch.int32, device=data.device)
@@ -800,6 +840,8 @@ class SniperResNet101:
         cls_prob = torch.empty(N, K, device=data.device)
         lab = torch.full((N,), -1.0, device=data.device)
         ops.softmax_ce(out, lab, K, 1.0, cnt, cls_prob, None, loss)
+        if autofocus:
+            return rois, scores, cls_prob, out[:, K:K + 4], fmap
         return rois, scores, cls_prob, out[:, K:K + 4]
 
     # ---------------------------------------------------------------- reference checkpoints (utils.py:45-100)

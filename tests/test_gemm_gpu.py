@@ -65,7 +65,19 @@ CONVS = [
 ]
 
 
-@pytest.mark.parametrize("NB,H,W,Cin,Cout,k,stride,dil,pad", CONVS)
+# inference canvases: any height, widths that are multiples of 8 at the layer's stride (narrow, tall tiles; rows past Ho
+# clipped by the TMA); rectangular maps; a width of 136 = 8 * 17 (tile_w 8), 88 (tile_w 8), 160 (tile_w 32), 50 rows
+RECT_CONVS = [
+    (2, 20, 24, 64, 64, 3, 1, 1, 1),
+    (1, 50, 88, 128, 256, 1, 1, 1, 0),
+    (1, 9, 136, 64, 96, 3, 1, 1, 1),
+    (2, 36, 160, 64, 128, 3, 2, 1, 1),
+    (1, 44, 80, 256, 512, 1, 2, 1, 0),
+    (1, 22, 40, 512, 64, 3, 1, 2, 2),
+]
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,k,stride,dil,pad", CONVS + RECT_CONVS)
 def test_conv2d_nhwc_tf32(NB, H, W, Cin, Cout, k, stride, dil, pad):
     import torch
     import torch.nn.functional as F
