@@ -184,14 +184,8 @@ def check_valid(det, chip, im_width, im_height, delta=10):
     return True
 
 
-def project_and_prune(cls_dets, chip, im_width, im_height, delta=10):
-    """Detections of one chip (chip coordinates, rows x1 y1 x2 y2 score) -> image coordinates, border-cut ones removed
-    (`do_pruning` branch, lib/inference.py:335-351).  Vectorised form of the per-detection loop."""
-    d = np.array(cls_dets, dtype=np.float64, copy=True).reshape(-1, 5)
-    if d.shape[0] == 0:
-        return np.zeros((0, 5))
-    d[:, 0] += chip[0]; d[:, 2] += chip[0]
-    d[:, 1] += chip[1]; d[:, 3] += chip[1]
+def prune_mask(d, chip, im_width, im_height, delta=10):
+    """check_valid for every row of d ([n, >=4], image coordinates) at once."""
     keep = np.ones(d.shape[0], dtype=bool)
     if chip[0] >= 0.5:
         keep &= ~(np.abs(d[:, 0] - chip[0]) < delta)
@@ -201,5 +195,16 @@ def project_and_prune(cls_dets, chip, im_width, im_height, delta=10):
         keep &= ~(np.abs(d[:, 2] - chip[2]) < delta)
     if chip[3] < im_height - 0.5:
         keep &= ~(np.abs(d[:, 3] - chip[3]) < delta)
-    d = d[keep]
+    return keep
+
+
+def project_and_prune(cls_dets, chip, im_width, im_height, delta=10):
+    """Detections of one chip (chip coordinates, rows x1 y1 x2 y2 score) -> image coordinates, border-cut ones removed
+    (`do_pruning` branch, lib/inference.py:335-351).  Vectorised form of the per-detection loop."""
+    d = np.array(cls_dets, dtype=np.float64, copy=True).reshape(-1, 5)
+    if d.shape[0] == 0:
+        return np.zeros((0, 5))
+    d[:, 0] += chip[0]; d[:, 2] += chip[0]
+    d[:, 1] += chip[1]; d[:, 3] += chip[1]
+    d = d[prune_mask(d, chip, im_width, im_height, delta)]
     return d if d.shape[0] > 0 else np.zeros((0, 5))

@@ -58,13 +58,26 @@ def detect_postprocess(rois, cls_prob, bbox_deltas, im_info, batch_size):
     return scores, preds
 
 
-def threshold_detections(cscores, cboxes, num_classes, cls_thresh=1e-3):
-    """get_detections :291-301: per class j >= 1 the rows with score > cls_thresh as [n,5] (x1,y1,x2,y2,score)."""
-    out = [np.zeros((0, 5), np.float32)]
-    for j in range(1, num_classes):
-        inds = np.where(cscores[:, j] > cls_thresh)[0]
-        out.append(np.hstack((cboxes[inds, 0:4], cscores[inds, j, np.newaxis])).astype(np.float32))
-    return out
+def threshold_detections(cscores, cboxes, num_classes, cls_thresh=1e-3, prune=None):
+    """get_detections :291-301: per class j >= 1 the rows with score > cls_thresh as [n,5] (x1,y1,x2,y2,score).
+    prune = (chip [x1,y1,x2,y2], im_width, im_height): additionally the `do_pruning` step (:335-351) -- rows moved to image
+    coordinates and detections cut by a chip border dropped (chips_inference.project_and_prune), on all classes at once."""
+    # one pass over the [R, K] score matrix instead of K np.where calls: (class, roi) pairs in class-major, roi-minor
+    # order = the order the per-class loop of the reference produces
+    cls_idx, roi_idx = np.nonzero(cscores[:, 1:num_classes].T > cls_thresh)
+    rows = np.empty((len(roi_idx), 5), np.float32)
+    rows[:, :4] = cboxes[roi_idx, 0:4]
+    rows[:, 4] = cscores[roi_idx, cls_idx + 1]
+    if prune is not None:
+        from .chips_inference import prune_mask
+        chip, im_w, im_h = prune
+        rows = rows.astype(np.float64)
+        rows[:, 0] += chip[0]; rows[:, 2] += chip[0]
+        rows[:, 1] += chip[1]; rows[:, 3] += chip[1]
+        keep = prune_mask(rows, chip, im_w, im_h)
+        rows, cls_idx = rows[keep], cls_idx[keep]
+    cuts = np.searchsorted(cls_idx, np.arange(1, num_classes - 1))
+    return [np.zeros((0, 5), rows.dtype)] + np.split(rows, cuts)
 
 
 def _valid_range_filter(cls_dets, valid_range):
@@ -83,16 +96,38 @@ def aggregate(scale_cls_dets, valid_ranges, num_images, num_classes, sigma=0.55,
     at scale s.  Returns all_boxes[j][i] = [n,5] after the valid-range filter, Gaussian soft-NMS (sigma, threshold
     0.001; nms_worker -> nms_wrapper -> cpu_soft_nms) and the MAX_PER_IMAGE cut."""
     assert len(scale_cls_dets) == len(valid_ranges), 'A valid range should be specified for each test scale'
-    problems = []
-    for i in range(num_images):
+    # Gather every detection of the run once, tagged with its (image, class) problem, apply each scale's valid range to
+    # the whole block, and cut the (stably) sorted block into the per-problem arrays: rows of a problem keep the
+    # (scale, chip, row) order in which the reference's nested loops stack them.
+    blocks, keys = [], []
+    for all_cls_dets, vr in zip(scale_cls_dets, valid_ranges):
+        sb, sk = [], []
         for j in range(1, num_classes):
-            agg = np.empty((0, 5), dtype=np.float32)
-            for all_cls_dets, vr in zip(scale_cls_dets, valid_ranges):
+            for i in range(num_images):
                 for cls_dets in all_cls_dets[j][i]:
-                    cls_dets = _valid_range_filter(np.asarray(cls_dets, np.float32).reshape(-1, 5), vr)
-                    if cls_dets.shape[0] > 0:
-                        agg = np.vstack((agg, cls_dets))
-            problems.append(np.ascontiguousarray(agg, np.float32))
+                    d = np.asarray(cls_dets, np.float32).reshape(-1, 5)
+                    if d.shape[0]:
+                        sb.append(d)
+                        sk.append(np.full(d.shape[0], i * (num_classes - 1) + (j - 1), np.int64))
+        if sb:
+            d, k = np.concatenate(sb, 0), np.concatenate(sk)
+            areas = (d[:, 3] - d[:, 1]) * (d[:, 2] - d[:, 0])          # as _valid_range_filter (no +1)
+            keep = np.ones(len(d), bool)
+            if vr[0] > 0:
+                keep &= areas > vr[0] * vr[0]
+            if vr[1] > 0:
+                keep &= areas <= vr[1] * vr[1]
+            blocks.append(d[keep])
+            keys.append(k[keep])
+    nprob = num_images * (num_classes - 1)
+    if blocks:
+        d, k = np.concatenate(blocks, 0), np.concatenate(keys)
+        order = np.argsort(k, kind="stable")
+        d, k = np.ascontiguousarray(d[order]), k[order]
+        cuts = np.searchsorted(k, np.arange(1, nprob))
+        problems = np.split(d, cuts)
+    else:
+        problems = [np.zeros((0, 5), np.float32) for _ in range(nprob)]
     if backend == "device":
         sizes = [len(p) for p in problems]
         offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)

@@ -199,14 +199,13 @@ class Tester(object):
             for i, (cscores, cboxes, im_id, chip_id) in enumerate(zip(scores, boxes, im_ids, chip_ids)):
                 if autofocus and maps:
                     all_maps[im_id][chip_id] = (None, maps[i])
-                dets = inference.threshold_detections(cscores, cboxes, self.num_classes, cls_thresh)
-                chip = self.roidb[im_id]['inference_crops'][chip_id]
+                # score threshold per class; with do_pruning also: project back to the image and drop detections cut
+                # by a chip border (:335-351), for all classes in one pass
+                r = self.roidb[im_id]
+                prune = (r['inference_crops'][chip_id], r['width'], r['height']) if do_pruning else None
+                dets = inference.threshold_detections(cscores, cboxes, self.num_classes, cls_thresh, prune=prune)
                 for j in range(1, self.num_classes):
-                    cls_dets = dets[j]
-                    if do_pruning:      # project back to the image and drop detections cut by a chip border (:335-351)
-                        cls_dets = chips_inference.project_and_prune(cls_dets, chip, self.roidb[im_id]['width'],
-                                                                     self.roidb[im_id]['height'])
-                    all_boxes[j][im_id][chip_id] = cls_dets
+                    all_boxes[j][im_id][chip_id] = dets[j]
             self.post_time += time.time() - t0
         return all_boxes, all_maps
 
