@@ -108,7 +108,8 @@ class NetSymbol(object):
                 "label": (B, A * H * W), "bbox_target": (B, 4 * A, H, W), "bbox_weight": (B, 4 * A, H, W)}
         arg = [tuple(data_shapes.get(n, dflt[n])) for n in self.data_names()] + [s for _, s in self._args]
         if self.is_train:
-            out = [(B, 2, A * H, W), (B, 4 * A, H, W), (B, R, K), (B, R, 4), (B, R)]
+            # the last head is BlockGrad(label_reshape): Reshape(label, (-1,)) (resnet_mx_101_e2e.py:281,334) -> (B*R,)
+            out = [(B, 2, A * H, W), (B, 4 * A, H, W), (B, R, K), (B, R, 4), (B * R,)]
         else:
             out = [(B * R, 5), (B, R, K), (B, R, 4), (B,), (B, 3), (B,)]
         return arg, out, [s for _, s in self._aux]
@@ -122,6 +123,62 @@ class NetSymbol(object):
         for k, v in cfg_overrides.items():
             setattr(c, k, v)
         return model.SniperResNet101(c, device=device, seed=seed)
+
+
+def recognise_graph(sym):
+    """Host-only: decides whether a graph built by the reference's own symbol file through `mxnet_compat` (or loaded from
+    a `-symbol.json`) is one this package executes, by its parameter set: every non-data argument / auxiliary state must
+    be exactly what `NetSymbol` (the hand-written description of model.SniperResNet101) lists, with the same shapes.
+    Returns the executor settings read off the graph's own attributes: batch_images (MultiProposalTarget batch_size),
+    num_anchors (rpn_cls_score num_filter / 2), num_classes (cls_score num_hidden), bf16 (a Cast to float16 inside the
+    backbone = TRAIN.fp16), is_train.  Raises NotImplementedError naming the first differences otherwise."""
+    from . import mxnet_compat as MC
+    nodes = {n.name: n for n in MC._dfs(sym._heads)}
+    is_train = "multi_proposal_target" in nodes
+    if "rpn_cls_score" not in nodes or "cls_score" not in nodes:
+        raise NotImplementedError("not a SNIPER Faster-R-CNN / R-FCN graph (no rpn_cls_score / cls_score nodes)")
+    A = int(nodes["rpn_cls_score"].attrs["num_filter"]) // 2
+    K = int(nodes["cls_score"].attrs["num_hidden"])
+    B = int(nodes["multi_proposal_target"].attrs.get("batch_size", 16)) if is_train else \
+        int(nodes["rois"].attrs.get("batch_size", 1)) if "rois" in nodes else 1
+    fp16 = any(n.op == "Cast" and n.attrs.get("dtype") == "float16" for n in nodes.values())
+    ours = NetSymbol(None, is_train=is_train, num_classes=K, num_anchors=A)
+    data = set(ours.data_names()) | {"scale_label", "crowd_boxes"}
+    H = 512
+    shapes = {"data": (B, 3, H, H)}
+    if is_train:
+        Hf = H // 16
+        shapes.update({"label": (B, A * Hf * Hf), "bbox_target": (B, 4 * A, Hf, Hf), "bbox_weight": (B, 4 * A, Hf, Hf),
+                       "gt_boxes": (B, 100, 5), "valid_ranges": (B, 2), "im_info": (B, 3)})
+    else:
+        shapes.update({"im_info": (B, 3), "im_ids": (B,), "chip_ids": (B,)})
+    args, _, auxs = sym.infer_shape_partial(**shapes)
+    theirs = {n: tuple(s) for n, s in zip(sym.list_arguments(), args) if n not in data}
+    theirs_aux = {n: tuple(s) for n, s in zip(sym.list_auxiliary_states(), auxs)}
+    mine = {n: tuple(s) for n, s in ours._args}
+    mine_aux = {n: tuple(s) for n, s in ours._aux}
+    # the AutoFocus branch (conv_new_2/3/out) is optional: model.enable_autofocus()
+    af = {k for k in theirs if k.startswith(("conv_new_2_", "conv_new_3_", "conv_new_out_"))}
+    diff = sorted((set(theirs) - af) ^ set(mine)) + sorted(set(theirs_aux) ^ set(mine_aux))
+    diff += sorted(k for k in mine if k in theirs and theirs[k] != mine[k])
+    if diff:
+        raise NotImplementedError("this package executes the ResNet-101 SNIPER R-FCN graph only; the given graph differs in "
+                                  "%d parameters, e.g. %s" % (len(diff), ", ".join(diff[:6])))
+    return dict(batch_images=B, num_anchors=A, num_classes=K, bf16=fp16, is_train=is_train, autofocus=bool(af))
+
+
+def bind_graph(sym, device="cuda:0", **overrides):
+    """`mxnet_compat.Symbol.bind`: the executor for a recognised graph (model.SniperResNet101; fp16 graphs run the bf16
+    mixed-precision configuration).  Needs the CUDA library -- fails loudly without it."""
+    info = recognise_graph(sym)
+    ours = NetSymbol(None, is_train=info["is_train"], num_classes=info["num_classes"], num_anchors=info["num_anchors"])
+    kw = dict(batch_images=info["batch_images"], bf16=info["bf16"], num_classes=info["num_classes"],
+              num_anchors=info["num_anchors"])
+    kw.update(overrides)
+    net = ours.bind(device, **kw)
+    if info["autofocus"]:
+        net.enable_autofocus()
+    return net
 
 
 class Symbol(object):

@@ -33,7 +33,7 @@ def test_names_and_shapes_match_the_oracle_parameter_set():
     for k, v in aux.items():
         assert tuple(inst.aux_shape_dict[k]) == v.shape, k
     assert inst.arg_shape_dict['label'] == (20, 21504)
-    assert list(inst.out_shape_dict.values()) == [(20, 2, 672, 32), (20, 84, 32, 32), (20, 300, 81), (20, 300, 4), (20, 300)]
+    assert list(inst.out_shape_dict.values()) == [(20, 2, 672, 32), (20, 84, 32, 32), (20, 300, 81), (20, 300, 4), (6000,)]
     inst.check_parameter_shapes(arg, aux, data_shapes)
     bad = dict(arg); bad['conv0_weight'] = np.zeros((64, 3, 3, 3), np.float32)
     try:
