@@ -40,7 +40,13 @@ SIGNATURES = {
     "sniper_bn_apply_train": ("i", "plplippffippppppplii" "p"),
     "sniper_bn_frozen": ("i", "ippppfippp"),
     "sniper_bn_relu_bwd": ("i", "plplppppp" "pl" "pl" "pp" "lii" "p"),
+    "sniper_bn_act_bwd": ("i", "plplppppp" "pl" "pl" "pp" "liii" "p"),
     "sniper_affine_relu_bwd": ("i", "plplpp" "pl" "pl" "lii" "p"),
+    "sniper_depthwise3x3_fwd": ("i", "plppl" "iiiiii" "p"),
+    "sniper_depthwise3x3_dgrad": ("i", "plppl" "iiiiii" "p"),
+    "sniper_depthwise3x3_wgrad": ("i", "plplp" "iiiiii" "p"),
+    "sniper_im2col3x3s2_nchw": ("i", "pp" "iiiiii" "p"),
+    "sniper_add_rows": ("i", "plplpl" "lii" "p"),
     "sniper_relu_bwd": ("i", "plplplli" "i" "p"),
     "sniper_cast_rows": ("i", "plipli" "li" "p"),
     "sniper_maxpool3x3s2_nhwc": ("i", "ppiiiiip"),
@@ -76,7 +82,7 @@ _lib = None
 KERNELS_PER_CALL = {
     "sniper_last_error": 0, "sniper_abi_version": 0, "sniper_multi_proposal_target_workspace_bytes": 0,
     "sniper_generate_anchors": 0, "sniper_chips_generate": 0, "sniper_cpu_nms": 0, "sniper_cpu_soft_nms": 0,
-    "sniper_bbox_overlaps": 0, "sniper_gemm_plan": 0, "sniper_deform_psroi_bwd_tiled_workspace_bytes": 0, "sniper_gemm_tail_workspace_bytes": 0, "sniper_gemm_set_tail_workspace": 0, "sniper_multi_proposal_target_fwd": 2, "sniper_multi_proposal_workspace_bytes": 0, "sniper_multi_proposal_fwd": 4, "sniper_anchor_target": 2, "sniper_bn_stats": 2, "sniper_bn_relu_bwd": 2,
+    "sniper_bbox_overlaps": 0, "sniper_gemm_plan": 0, "sniper_deform_psroi_bwd_tiled_workspace_bytes": 0, "sniper_gemm_tail_workspace_bytes": 0, "sniper_gemm_set_tail_workspace": 0, "sniper_multi_proposal_target_fwd": 2, "sniper_multi_proposal_workspace_bytes": 0, "sniper_multi_proposal_fwd": 4, "sniper_anchor_target": 2, "sniper_bn_stats": 2, "sniper_bn_relu_bwd": 2, "sniper_bn_act_bwd": 2,
 }
 launches = [0]
 

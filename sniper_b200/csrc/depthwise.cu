@@ -1,0 +1,185 @@
+// Depthwise 3x3 convolution (forward, data gradient, weight gradient), the first-layer im2col and the shortcut add of
+// the MobileNetV2 SNIPER backbone (BASELINE config 4; symbols/faster/mobilenetv2_e2e.py:27-91, 204-212).
+//
+// These layers carry 9 MACs per loaded element: they are HBM / L1 bound, not tensor-core work, so they are plain
+// coalesced NHWC kernels (4 channels per thread, consecutive threads on consecutive channel vectors of a pixel, fp32
+// accumulation); the 1x1 expand / project convolutions around them run on the tcgen05 kernel (gemm_tc.cu).  The
+// per-thread bodies live in depthwise_core.cuh so that the CPU test can execute the same index arithmetic.
+// Reference kernels replaced: src/operator/nn/depthwise_convolution-inl.h (DepthwiseConvolutionOp::Forward / Backward,
+// depthwise_convolution_tf.cuh), elemwise_add, im2col of nn/convolution-inl.h for the 3-channel first layer.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "depthwise_core.cuh"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+constexpr int kTPB = 256;
+
+template <typename T, int S, int PW>
+__global__ void __launch_bounds__(kTPB) dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                       T* __restrict__ y, dwc::Params p, long nthreads) {
+  const long tid = (long)blockIdx.x * kTPB + threadIdx.x;
+  if (tid < nthreads) dwc::fwd<T, S, PW>(tid, x, w, y, p);
+}
+
+template <typename T, int S>
+__global__ void __launch_bounds__(kTPB) dw_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w,
+                                                         T* __restrict__ dx, dwc::Params p, long nthreads) {
+  const long tid = (long)blockIdx.x * kTPB + threadIdx.x;
+  if (tid < nthreads) dwc::dgrad<T, S>(tid, dy, w, dx, p);
+}
+
+// block = 32 channel lanes (128 channels) x 8 pixel lanes; partial sums of the 8 pixel lanes are combined in shared
+// memory, then one float atomic per (block, tap, channel): gridDim.x * 9 * C atomics in total
+constexpr int kWgTY = 8;
+template <typename T, int S>
+__global__ void __launch_bounds__(32 * kWgTY) dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                                               float* __restrict__ dw, dwc::Params p) {
+  __shared__ float red[kWgTY][32][37];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  float acc[9][4];
+  dwc::wgrad_partial<T, S>((int)blockIdx.x, (int)blockIdx.y, tx, ty, kWgTY, (int)gridDim.x, x, dy, p, acc);
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[ty][tx][t * 4 + k] = acc[t][k];
+  __syncthreads();
+  for (int i = ty * 32 + tx; i < 32 * 36; i += 32 * kWgTY) {
+    const int lane = i / 36, e = i - lane * 36;
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < kWgTY; ++j) s += red[j][lane][e];
+    const int c = (((int)blockIdx.y * 32 + lane) << 2) + (e & 3);
+    if (c < p.C && s != 0.f) atomicAdd(dw + (long)(e >> 2) * p.C + c, s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTPB) im2col3x3s2_kernel(const float* __restrict__ x, T* __restrict__ col, int NB,
+                                                            int H, int W, int Ho, int Wo, int Kp, long nthreads) {
+  const long tid = (long)blockIdx.x * kTPB + threadIdx.x;
+  if (tid < nthreads) dwc::im2col3x3s2<T, 3>(tid, x, col, NB, H, W, Ho, Wo, Kp);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTPB) add_rows_kernel(const T* a, long lda, const T* b,
+                                                         long ldb, T* o, long ldo, long M, int C,
+                                                         long nthreads) {
+  const long tid = (long)blockIdx.x * kTPB + threadIdx.x;
+  if (tid < nthreads) dwc::add_rows<T>(tid, a, lda, b, ldb, o, ldo, M, C);
+}
+
+int fill_params(dwc::Params& p, int NB, int H, int W, int C, int stride, long ld_in, long ld_out, int dtype,
+                const char* who) {
+  SN_CHECK(dtype == 0 || dtype == 1, "%s: dtype must be 0 (fp32) or 1 (bf16)", who);
+  SN_CHECK(stride == 1 || stride == 2, "%s: stride must be 1 or 2", who);
+  SN_CHECK(NB > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "%s: C (%d) must be a positive multiple of 4", who, C);
+  SN_CHECK(ld_in >= C && ld_out >= C && ld_in % 4 == 0 && ld_out % 4 == 0, "%s: pixel strides must be multiples of 4 and >= C",
+           who);
+  p.NB = NB; p.H = H; p.W = W; p.C = C; p.stride = stride;
+  p.Ho = (H - 1) / stride + 1;          // (H + 2*1 - 3) / stride + 1
+  p.Wo = (W - 1) / stride + 1;
+  p.ldx = ld_in; p.ldy = ld_out;
+  return 0;
+}
+
+inline unsigned blocks_for(long nthreads) { return (unsigned)((nthreads + kTPB - 1) / kTPB); }
+
+}  // namespace
+
+extern "C" {
+
+// y[NB,Ho,Wo,C] = depthwise3x3(x[NB,H,W,C], w[9,C]), pad 1, stride 1 | 2.  ldx / ldy: elements between pixels.
+int sniper_depthwise3x3_fwd(const void* x, long ldx, const float* w, void* y, long ldy, int NB, int H, int W, int C,
+                            int stride, int dtype, void* stream) {
+  dwc::Params p;
+  if (fill_params(p, NB, H, W, C, stride, ldx, ldy, dtype, "depthwise3x3_fwd")) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+#define DW_FWD(T, S, PW)                                                                                       \
+  do {                                                                                                         \
+    const long nt = dwc::fwd_threads<S, PW>(p);                                                                \
+    dw_fwd_kernel<T, S, PW><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const T*>(x), w, static_cast<T*>(y), p, nt); \
+  } while (0)
+  if (dtype == 0) { if (stride == 1) DW_FWD(float, 1, 4); else DW_FWD(float, 2, 2); }
+  else            { if (stride == 1) DW_FWD(bf16, 1, 4);  else DW_FWD(bf16, 2, 2); }
+#undef DW_FWD
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// dx[NB,H,W,C] = depthwise3x3^T(dy[NB,Ho,Wo,C], w[9,C]); H, W, stride describe the FORWARD convolution.
+int sniper_depthwise3x3_dgrad(const void* dy, long lddy, const float* w, void* dx, long lddx, int NB, int H, int W,
+                              int C, int stride, int dtype, void* stream) {
+  dwc::Params p;
+  if (fill_params(p, NB, H, W, C, stride, lddx, lddy, dtype, "depthwise3x3_dgrad")) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long nt = dwc::dgrad_threads(p);
+#define DW_DG(T, S) dw_dgrad_kernel<T, S><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const T*>(dy), w, static_cast<T*>(dx), p, nt)
+  if (dtype == 0) { if (stride == 1) DW_DG(float, 1); else DW_DG(float, 2); }
+  else            { if (stride == 1) DW_DG(bf16, 1);  else DW_DG(bf16, 2); }
+#undef DW_DG
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// dw[9,C] += sum over pixels of dy * shifted x  (fp32, accumulated with atomics: zero it for kWriteTo).
+int sniper_depthwise3x3_wgrad(const void* x, long ldx, const void* dy, long lddy, float* dw, int NB, int H, int W,
+                              int C, int stride, int dtype, void* stream) {
+  dwc::Params p;
+  if (fill_params(p, NB, H, W, C, stride, ldx, lddy, dtype, "depthwise3x3_wgrad")) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int gy = sn::div_up(C, 128);
+  const long total = (long)NB * p.Ho * p.Wo;
+  long gx = (sn::kNumSMs * 4 + gy - 1) / gy;          // ~4 blocks of 256 threads per SM over the whole grid
+  const long gx_max = (total + kWgTY - 1) / kWgTY;
+  if (gx > gx_max) gx = gx_max;
+  if (gx < 1) gx = 1;
+  const dim3 grid((unsigned)gx, (unsigned)gy, 1), block(32, kWgTY, 1);
+#define DW_WG(T, S) dw_wgrad_kernel<T, S><<<grid, block, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(dy), dw, p)
+  if (dtype == 0) { if (stride == 1) DW_WG(float, 1); else DW_WG(float, 2); }
+  else            { if (stride == 1) DW_WG(bf16, 1);  else DW_WG(bf16, 2); }
+#undef DW_WG
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// col[NB*Ho*Wo, Kp] = im2col of a 3x3 / stride 2 / pad 1 convolution over an fp32 NCHW image with 3 channels, K order
+// (kh, kw, ci), zero-padded to Kp (a multiple of the tcgen05 kernel's K atom: 32 fp32 / 64 bf16 elements).
+int sniper_im2col3x3s2_nchw(const float* x, void* col, int NB, int H, int W, int Cin, int Kp, int dtype, void* stream) {
+  SN_CHECK(dtype == 0 || dtype == 1, "im2col3x3s2: dtype must be 0 (fp32) or 1 (bf16)");
+  SN_CHECK(Cin == 3, "im2col3x3s2: built for the 3-channel first layer (Cin = %d)", Cin);
+  SN_CHECK(Kp >= 27 && Kp % 4 == 0, "im2col3x3s2: Kp (%d) must be a multiple of 4 and >= 27", Kp);
+  SN_CHECK(NB > 0 && H > 0 && W > 0, "im2col3x3s2: empty input");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long nt = (long)NB * Ho * Wo * (Kp >> 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 0)
+    im2col3x3s2_kernel<float><<<blocks_for(nt), kTPB, 0, st>>>(x, static_cast<float*>(col), NB, H, W, Ho, Wo, Kp, nt);
+  else
+    im2col3x3s2_kernel<bf16><<<blocks_for(nt), kTPB, 0, st>>>(x, static_cast<bf16*>(col), NB, H, W, Ho, Wo, Kp, nt);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+// out[M,C] = a[M,C] + b[M,C] (row strides in elements; out may alias a or b).
+int sniper_add_rows(const void* a, long lda, const void* b, long ldb, void* out, long ldo, long M, int C, int dtype,
+                    void* stream) {
+  SN_CHECK(dtype == 0 || dtype == 1, "add_rows: dtype must be 0 (fp32) or 1 (bf16)");
+  SN_CHECK(M > 0 && C > 0 && C % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ldo % 4 == 0,
+           "add_rows: C and the row strides must be multiples of 4");
+  const long nt = M * (C >> 2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 0)
+    add_rows_kernel<float><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const float*>(a), lda, static_cast<const float*>(b),
+                                                            ldb, static_cast<float*>(out), ldo, M, C, nt);
+  else
+    add_rows_kernel<bf16><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const bf16*>(a), lda, static_cast<const bf16*>(b),
+                                                           ldb, static_cast<bf16*>(out), ldo, M, C, nt);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

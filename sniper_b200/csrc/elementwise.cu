@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x
   int c, ry, RY;
   long r0, r1;
   if (!rb_setup<N>(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1)) return;
+  const float act_hi = relu == 2 ? 6.f : __int_as_float(0x7f800000);     // relu 2 = clip(y, 0, 6) (mobilenetv2_e2e.py:18-19)
   float s[N], t[N];
   ldc<N>(scale + c, s);
   ldc<N>(shift + c, t);
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(256) affine_act_kernel(const T* __restrict__ x
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         o[k] = fmaf(v[k], s[k], t[k]);
-        if (relu) o[k] = fmaxf(o[k], 0.f);
+        if (relu) o[k] = fminf(fmaxf(o[k], 0.f), act_hi);
       }
       stv(y + rr * ldy + c, o);
     }
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(256) bn_apply_train_kernel(const T* __restrict
   int c, ry, RY;
   long r0, r1;
   if (!rb_setup<N>(lx_shift, C, rows_per_block, M, c, ry, RY, r0, r1)) return;
+  const float act_hi = relu == 2 ? 6.f : __int_as_float(0x7f800000);     // relu 2 = clip(y, 0, 6)
   float s[N], t[N];
   const bool publish = blockIdx.x == 0 && ry == 0;
 #pragma unroll
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(256) bn_apply_train_kernel(const T* __restrict
 #pragma unroll
       for (int k = 0; k < N; ++k) {
         o[k] = fmaf(v[k], s[k], t[k]);
-        if (relu) o[k] = fmaxf(o[k], 0.f);
+        if (relu) o[k] = fminf(fmaxf(o[k], 0.f), act_hi);
       }
       stv(y + rr * ldy + c, o);
     }
@@ -237,6 +239,8 @@ __global__ void __launch_bounds__(256) bn_apply_train_kernel(const T* __restrict
 // ------------------------------------------------------------------ per-channel sums over rows
 // MODE 0: sums[c] += x, sums[C+c] += x*x                              (BN forward statistics)
 // MODE 1: g = dy * (x*scale+shift > 0); sums[c] += g; sums[C+c] += g * (x-mean)*invstd   (BN+ReLU backward)
+// MODE 2: the same with the clip(y, 0, 6) mask 0 <= y <= 6 (clip_grad, tensor/matrix_op-inl.h:1319-1332); MODE 3: no
+//         activation (g = dy): the BatchNorm of MobileNetV2's linear bottleneck (mobilenetv2_e2e.py:68-77)
 template <int MODE, typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ldx,
                                                       const T* __restrict__ dy, long lddy,
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
   for (int k = 0; k < N; ++k) { a[k] = 0.f; b[k] = 0.f; }
   if (cok) {
     float sc[N], sh[N], mu[N], is[N];
-    if (MODE == 1) { ldc<N>(scale + c, sc); ldc<N>(shift + c, sh); ldc<N>(mean + c, mu); ldc<N>(invstd + c, is); }
+    if (MODE >= 1) { ldc<N>(scale + c, sc); ldc<N>(shift + c, sh); ldc<N>(mean + c, mu); ldc<N>(invstd + c, is); }
     for (long r = r0 + ry; r < r1; r += (long)KU * RY) {
       typename VT<T>::Raw rx[KU], rg[KU];
 #pragma unroll
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
         const long rr = r + (long)u * RY;
         if (rr < r1) {
           rx[u] = ldraw(x + rr * ldx + c);
-          if (MODE == 1) rg[u] = ldraw(dy + rr * lddy + c);
+          if (MODE >= 1) rg[u] = ldraw(dy + rr * lddy + c);
         }
       }
 #pragma unroll
@@ -269,14 +273,15 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, lo
         if (r + (long)u * RY >= r1) break;
         float v[N], g[N];
         unpack(rx[u], v);
-        if (MODE == 1) unpack(rg[u], g);
+        if (MODE >= 1) unpack(rg[u], g);
 #pragma unroll
         for (int k = 0; k < N; ++k) {
           if (MODE == 0) {
             a[k] += v[k];
             b[k] = fmaf(v[k], v[k], b[k]);
           } else {
-            const float gg = fmaf(v[k], sc[k], sh[k]) > 0.f ? g[k] : 0.f;
+            const float yv = fmaf(v[k], sc[k], sh[k]);
+            const float gg = MODE == 3 ? g[k] : MODE == 2 ? ((yv >= 0.f && yv <= 6.f) ? g[k] : 0.f) : (yv > 0.f ? g[k] : 0.f);
             a[k] += gg;
             b[k] = fmaf(gg, (v[k] - mu[k]) * is[k], b[k]);
           }
@@ -391,7 +396,7 @@ __global__ void bn_frozen_kernel(int C, const float* gamma, const float* beta, c
 }
 
 // dx = scale * (g - s1/M - xhat * s2/M) (+add), g = dy * (x*scale+shift > 0), xhat = (x-mean)*invstd; sums = (s1, s2)
-template <typename T>
+template <typename T, int ACT = 1>      // ACT 1: ReLU, 2: clip(0, 6), 3: none -- the masks of colsum_kernel MODE 1 / 2 / 3
 __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const T* __restrict__ x, long ldx,
                                                                  const T* __restrict__ dy, long lddy,
                                                                  const float* __restrict__ scale,
@@ -435,7 +440,8 @@ __global__ void __launch_bounds__(256) bn_relu_bwd_apply_kernel(const T* __restr
       if (add) unpack(ra[u], ad);
 #pragma unroll
       for (int k = 0; k < N; ++k) {
-        const float gk = fmaf(v[k], scv[k], shv[k]) > 0.f ? g[k] : 0.f;
+        const float yv = fmaf(v[k], scv[k], shv[k]);
+        const float gk = ACT == 3 ? g[k] : ACT == 2 ? ((yv >= 0.f && yv <= 6.f) ? g[k] : 0.f) : (yv > 0.f ? g[k] : 0.f);
         const float xhat = (v[k] - muv[k]) * isv[k];
         o[k] = scv[k] * (gk - s1[k] - xhat * s2[k]);
         if (add) o[k] += ad[k];
@@ -887,6 +893,24 @@ int resident_blocks(K kernel) {
 
 }  // namespace
 
+namespace {
+template <typename T, int ACT>
+int bn_act_bwd_launch(const void* x, long ldx, const void* dy, long lddy, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, double* sums, const void* add, long ldadd, void* dx,
+                      long lddx, long M, int C, cudaStream_t st) {
+  const RowBlock rb = row_block(M, C, VT<T>::N, resident_blocks(bn_relu_bwd_apply_kernel<T, ACT>));
+  if (launch_colsum<ACT, T>(st, static_cast<const T*>(x), ldx, static_cast<const T*>(dy), lddy, scale, shift, mean,
+                            invstd, M, C, sums))
+    return -1;
+  SN_LAUNCH_CHECK();
+  bn_relu_bwd_apply_kernel<T, ACT><<<rb.grid, 256, 0, st>>>(
+      static_cast<const T*>(x), ldx, static_cast<const T*>(dy), lddy, scale, shift, mean, invstd, sums,
+      static_cast<const T*>(add), ldadd, static_cast<T*>(dx), lddx, M, C, rb.lx_shift, rb.rows_per_block);
+  SN_LAUNCH_CHECK();
+  return 0;
+}
+}  // namespace
+
 extern "C" {
 
 // dtype (here and below): storage type of the activation tensors, 0 = fp32, 1 = bf16 (arithmetic is fp32 either way)
@@ -975,40 +999,40 @@ int sniper_bn_frozen(int C, const float* gamma, const float* beta, const float* 
   return 0;
 }
 
-// Backward of y = relu(bn_train(x)):  dx (+add), dgamma += , dbeta += .  sums: zeroed double[2C], left zeroed.
-int sniper_bn_relu_bwd(const void* x, long ldx, const void* dy, long lddy, const float* scale, const float* shift,
-                       const float* mean, const float* invstd, double* sums, const void* add, long ldadd, void* dx,
-                       long lddx, float* dgamma, float* dbeta, long M, int C, int dtype, void* stream) {
-  SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "bn_relu_bwd: C/ld must be multiples of 4");
-  SN_CHECK(dtype == 0 || dtype == 1, "bn_relu_bwd: dtype must be 0 (fp32) or 1 (bf16)");
+// Backward of y = act(bn_train(x)):  dx (+add), dgamma += , dbeta += .  sums: zeroed double[2C], left zeroed.
+// act 1: ReLU (Activation, y > 0), 2: clip(y, 0, 6) (mobilenetv2_e2e.py:18-19; gradient where 0 <= y <= 6,
+// tensor/matrix_op-inl.h:1319-1332), 3: no activation (linear bottleneck).
+int sniper_bn_act_bwd(const void* x, long ldx, const void* dy, long lddy, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, double* sums, const void* add, long ldadd, void* dx,
+                      long lddx, float* dgamma, float* dbeta, long M, int C, int act, int dtype, void* stream) {
+  SN_CHECK(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "bn_act_bwd: C/ld must be multiples of 4");
+  SN_CHECK(dtype == 0 || dtype == 1, "bn_act_bwd: dtype must be 0 (fp32) or 1 (bf16)");
+  SN_CHECK(act >= 1 && act <= 3, "bn_act_bwd: act must be 1 (relu), 2 (relu6) or 3 (none)");
   SN_CHECK(dtype == 0 || (C % 8 == 0 && ldx % 8 == 0 && lddy % 8 == 0 && lddx % 8 == 0 && ldadd % 8 == 0),
-           "bn_relu_bwd: bf16 needs C/ld multiples of 8");
-  const RowBlock rb = dtype == 0 ? row_block(M, C, 4, resident_blocks(bn_relu_bwd_apply_kernel<float>))
-                                 : row_block(M, C, 8, resident_blocks(bn_relu_bwd_apply_kernel<bf16>));
+           "bn_act_bwd: bf16 needs C/ld multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+#define SN_BN_BWD(T, A) rc = bn_act_bwd_launch<T, A>(x, ldx, dy, lddy, scale, shift, mean, invstd, sums, add, ldadd, dx, lddx, M, C, st)
   if (dtype == 0) {
-    if (launch_colsum<1, float>(st, static_cast<const float*>(x), ldx, static_cast<const float*>(dy), lddy, scale,
-                                shift, mean, invstd, M, C, sums))
-      return -1;
-    SN_LAUNCH_CHECK();
-    bn_relu_bwd_apply_kernel<float><<<rb.grid, 256, 0, st>>>(
-        static_cast<const float*>(x), ldx, static_cast<const float*>(dy), lddy, scale, shift, mean, invstd, sums,
-        static_cast<const float*>(add), ldadd, static_cast<float*>(dx), lddx, M, C, rb.lx_shift, rb.rows_per_block);
+    if (act == 1) SN_BN_BWD(float, 1); else if (act == 2) SN_BN_BWD(float, 2); else SN_BN_BWD(float, 3);
   } else {
-    if (launch_colsum<1, bf16>(st, static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(dy), lddy, scale, shift,
-                               mean, invstd, M, C, sums))
-      return -1;
-    SN_LAUNCH_CHECK();
-    bn_relu_bwd_apply_kernel<bf16><<<rb.grid, 256, 0, st>>>(
-        static_cast<const bf16*>(x), ldx, static_cast<const bf16*>(dy), lddy, scale, shift, mean, invstd, sums,
-        static_cast<const bf16*>(add), ldadd, static_cast<bf16*>(dx), lddx, M, C, rb.lx_shift, rb.rows_per_block);
+    if (act == 1) SN_BN_BWD(bf16, 1); else if (act == 2) SN_BN_BWD(bf16, 2); else SN_BN_BWD(bf16, 3);
   }
-  SN_LAUNCH_CHECK();
+#undef SN_BN_BWD
+  if (rc) return -1;
   if (dgamma || dbeta) {   // both null: the caller finishes with sniper_bn_param_grad_batched (sums stay live)
     bn_param_grad_kernel<<<sn::div_up(C, 128), 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta);
     SN_LAUNCH_CHECK();
   }
   return 0;
+}
+
+// Backward of y = relu(bn_train(x)) (residual_unit, resnet_mx_101_e2e.py:36-69): sniper_bn_act_bwd with act = 1.
+int sniper_bn_relu_bwd(const void* x, long ldx, const void* dy, long lddy, const float* scale, const float* shift,
+                       const float* mean, const float* invstd, double* sums, const void* add, long ldadd, void* dx,
+                       long lddx, float* dgamma, float* dbeta, long M, int C, int dtype, void* stream) {
+  return sniper_bn_act_bwd(x, ldx, dy, lddy, scale, shift, mean, invstd, sums, add, ldadd, dx, lddx, dgamma, dbeta, M, C,
+                           1, dtype, stream);
 }
 
 int sniper_affine_relu_bwd(const float* x, long ldx, const float* dy, long lddy, const float* scale,

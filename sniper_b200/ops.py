@@ -497,6 +497,19 @@ def bn_relu_bwd(x, dy, bn, add=None, out=None, defer=False):
     return out
 
 
+def bn_act_bwd(x, dy, bn, act, add=None, out=None, defer=False):
+    """Backward of act(bn_train(x)), act 1 = ReLU, 2 = clip(y, 0, 6), 3 = none; otherwise as bn_relu_bwd."""
+    M, C, ldx = _rows(x)
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=x.dtype)
+    assert dy.dtype == x.dtype and out.dtype == x.dtype and (add is None or add.dtype == x.dtype)
+    check(lib().sniper_bn_act_bwd(_ptr(x), ldx, _ptr(dy), _rows(dy)[2], _ptr(bn.scale), _ptr(bn.shift), _ptr(bn.mean),
+                                  _ptr(bn.invstd), _ptr(bn.sums), _ptr(add), 0 if add is None else _rows(add)[2],
+                                  _ptr(out), _rows(out)[2], None if defer else _ptr(bn.dgamma),
+                                  None if defer else _ptr(bn.dbeta), M, C, int(act), _sdt(x), _stream()))
+    return out
+
+
 def affine_relu_bwd(x, dy, scale, shift, add=None, relu=True, out=None):
     M, C, ldx = _rows(x)
     if out is None:
@@ -709,3 +722,63 @@ def soft_nms_batched(dets, offsets, *, sigma=0.55, Nt=0.3, threshold=0.001, meth
     check(lib().sniper_soft_nms_batched(_ptr(out), _ptr(offsets), P, float(sigma), float(Nt), float(threshold), int(method),
                                         _ptr(counts), _ptr(scratch), _stream()))
     return out, counts[:P]
+
+
+# ---------------------------------------------------------------------------------------------
+# MobileNetV2 layers (symbols/faster/mobilenetv2_e2e.py): depthwise 3x3, first-layer im2col, shortcut add
+# ---------------------------------------------------------------------------------------------
+def depthwise3x3(x, w, stride=1, out=None):
+    """x: [N,H,W,C] (fp32 | bf16), w: [9,C] fp32 tap-major -> [N,Ho,Wo,C]; pad 1."""
+    NB, H, W, C = x.shape
+    assert w.shape == (9, C) and w.dtype == torch.float32 and w.is_contiguous() and x.stride(3) == 1
+    ldx = x.stride(2)
+    assert x.stride(1) == W * ldx and x.stride(0) == H * W * ldx
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    if out is None:
+        out = torch.empty(NB, Ho, Wo, C, device=x.device, dtype=x.dtype)
+    assert out.dtype == x.dtype and out.shape == (NB, Ho, Wo, C)
+    check(lib().sniper_depthwise3x3_fwd(_ptr(x), ldx, _ptr(w), _ptr(out), out.stride(2), NB, H, W, C, stride, _sdt(x),
+                                        _stream()))
+    return out
+
+
+def depthwise3x3_dgrad(dy, w, in_hw, stride=1, out=None):
+    """dx [N,H,W,C] of depthwise3x3 for dy [N,Ho,Wo,C]."""
+    NB, Ho, Wo, C = dy.shape
+    H, W = in_hw
+    assert (H - 1) // stride + 1 == Ho and (W - 1) // stride + 1 == Wo and dy.is_contiguous()
+    if out is None:
+        out = torch.empty(NB, H, W, C, device=dy.device, dtype=dy.dtype)
+    check(lib().sniper_depthwise3x3_dgrad(_ptr(dy), dy.stride(2), _ptr(w), _ptr(out), out.stride(2), NB, H, W, C, stride,
+                                          _sdt(dy), _stream()))
+    return out
+
+
+def depthwise3x3_wgrad(x, dy, dw, stride=1):
+    """dw[9,C] (fp32) += correlation of dy with the shifted input."""
+    NB, H, W, C = x.shape
+    assert dw.shape == (9, C) and dw.dtype == torch.float32 and dw.is_contiguous() and x.dtype == dy.dtype
+    assert x.is_contiguous() and dy.is_contiguous()
+    check(lib().sniper_depthwise3x3_wgrad(_ptr(x), x.stride(2), _ptr(dy), dy.stride(2), _ptr(dw), NB, H, W, C, stride,
+                                          _sdt(x), _stream()))
+    return dw
+
+
+def im2col3x3s2(x_nchw, Kp, dtype=torch.float32, out=None):
+    """[N,3,H,W] fp32 -> [N,Ho,Wo,Kp] rows of the first layer's 3x3 / stride-2 patches, K order (kh, kw, ci)."""
+    NB, Cin, H, W = x_nchw.shape
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    if out is None:
+        out = torch.empty(NB, Ho, Wo, Kp, device=x_nchw.device, dtype=dtype)
+    check(lib().sniper_im2col3x3s2_nchw(_ptr(x_nchw), _ptr(out), NB, H, W, Cin, Kp, _sdt(out), _stream()))
+    return out
+
+
+def add_rows(a, b, out=None):
+    M, C, lda = _rows(a)
+    if out is None:
+        out = torch.empty(a.shape, device=a.device, dtype=a.dtype)
+    assert a.dtype == b.dtype == out.dtype and a.shape == b.shape
+    check(lib().sniper_add_rows(_ptr(a), lda, _ptr(b), _rows(b)[2], _ptr(out), _rows(out)[2], M, C, _sdt(a), _stream()))
+    return out

@@ -1,0 +1,73 @@
+// TEST INFRASTRUCTURE: runs the per-thread bodies of sniper_b200/csrc/depthwise_core.cuh on the CPU, thread index by
+// thread index and block by block, exactly as depthwise.cu launches them (same thread counts, same wgrad grid rule).
+// Built on the fly by tests/test_depthwise_cpu.py (nvcc compiles the __host__ side of the __host__ __device__ bodies);
+// never linked into the product library.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include "../sniper_b200/csrc/depthwise_core.cuh"
+
+typedef __nv_bfloat16 bf16;
+
+static void fill(dwc::Params& p, int NB, int H, int W, int C, int stride, long ld_in, long ld_out) {
+  p.NB = NB; p.H = H; p.W = W; p.C = C; p.stride = stride;
+  p.Ho = (H - 1) / stride + 1; p.Wo = (W - 1) / stride + 1;
+  p.ldx = ld_in; p.ldy = ld_out;
+}
+
+template <typename T>
+static void fwd_t(const void* x, long ldx, const float* w, void* y, long ldy, int NB, int H, int W, int C, int stride) {
+  dwc::Params p; fill(p, NB, H, W, C, stride, ldx, ldy);
+  if (stride == 1) { const long nt = dwc::fwd_threads<1, 4>(p); for (long t = 0; t < nt; ++t) dwc::fwd<T, 1, 4>(t, (const T*)x, w, (T*)y, p); }
+  else             { const long nt = dwc::fwd_threads<2, 2>(p); for (long t = 0; t < nt; ++t) dwc::fwd<T, 2, 2>(t, (const T*)x, w, (T*)y, p); }
+}
+template <typename T>
+static void dgrad_t(const void* dy, long lddy, const float* w, void* dx, long lddx, int NB, int H, int W, int C, int stride) {
+  dwc::Params p; fill(p, NB, H, W, C, stride, lddx, lddy);
+  const long nt = dwc::dgrad_threads(p);
+  for (long t = 0; t < nt; ++t) { if (stride == 1) dwc::dgrad<T, 1>(t, (const T*)dy, w, (T*)dx, p); else dwc::dgrad<T, 2>(t, (const T*)dy, w, (T*)dx, p); }
+}
+template <typename T>
+static void wgrad_t(const void* x, long ldx, const void* dy, long lddy, float* dw, int NB, int H, int W, int C, int stride) {
+  dwc::Params p; fill(p, NB, H, W, C, stride, ldx, lddy);
+  const int TY = 8;
+  const int gy = (C + 127) / 128;
+  const long total = (long)NB * p.Ho * p.Wo;
+  long gx = (148 * 4 + gy - 1) / gy;
+  const long gx_max = (total + TY - 1) / TY;
+  if (gx > gx_max) gx = gx_max;
+  if (gx < 1) gx = 1;
+  for (int by = 0; by < gy; ++by)
+    for (int bx = 0; bx < (int)gx; ++bx)
+      for (int ty = 0; ty < TY; ++ty)
+        for (int tx = 0; tx < 32; ++tx) {
+          float acc[9][4];
+          bool ok = stride == 1 ? dwc::wgrad_partial<T, 1>(bx, by, tx, ty, TY, (int)gx, (const T*)x, (const T*)dy, p, acc)
+                                : dwc::wgrad_partial<T, 2>(bx, by, tx, ty, TY, (int)gx, (const T*)x, (const T*)dy, p, acc);
+          if (!ok) continue;
+          const int c = (by * 32 + tx) * 4;
+          for (int t = 0; t < 9; ++t) for (int k = 0; k < 4; ++k) dw[(long)t * C + c + k] += acc[t][k];
+        }
+}
+
+extern "C" {
+void emu_dw_fwd(const void* x, long ldx, const float* w, void* y, long ldy, int NB, int H, int W, int C, int stride, int dtype) {
+  if (dtype == 0) fwd_t<float>(x, ldx, w, y, ldy, NB, H, W, C, stride); else fwd_t<bf16>(x, ldx, w, y, ldy, NB, H, W, C, stride);
+}
+void emu_dw_dgrad(const void* dy, long lddy, const float* w, void* dx, long lddx, int NB, int H, int W, int C, int stride, int dtype) {
+  if (dtype == 0) dgrad_t<float>(dy, lddy, w, dx, lddx, NB, H, W, C, stride); else dgrad_t<bf16>(dy, lddy, w, dx, lddx, NB, H, W, C, stride);
+}
+void emu_dw_wgrad(const void* x, long ldx, const void* dy, long lddy, float* dw, int NB, int H, int W, int C, int stride, int dtype) {
+  if (dtype == 0) wgrad_t<float>(x, ldx, dy, lddy, dw, NB, H, W, C, stride); else wgrad_t<bf16>(x, ldx, dy, lddy, dw, NB, H, W, C, stride);
+}
+void emu_im2col3x3s2(const float* x, void* col, int NB, int H, int W, int Kp, int dtype) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long nt = (long)NB * Ho * Wo * (Kp >> 2);
+  for (long t = 0; t < nt; ++t) { if (dtype == 0) dwc::im2col3x3s2<float, 3>(t, x, (float*)col, NB, H, W, Ho, Wo, Kp); else dwc::im2col3x3s2<bf16, 3>(t, x, (bf16*)col, NB, H, W, Ho, Wo, Kp); }
+}
+void emu_add_rows(const void* a, long lda, const void* b, long ldb, void* o, long ldo, long M, int C, int dtype) {
+  const long nt = M * (C >> 2);
+  for (long t = 0; t < nt; ++t) { if (dtype == 0) dwc::add_rows<float>(t, (const float*)a, lda, (const float*)b, ldb, (float*)o, ldo, M, C); else dwc::add_rows<bf16>(t, (const bf16*)a, lda, (const bf16*)b, ldb, (bf16*)o, ldo, M, C); }
+}
+}

@@ -27,12 +27,18 @@ DOC = {
     "sniper_gemm_set_tail_workspace": "Registers that scratch (zero-filled, caller-owned, must outlive later launches); the library itself never allocates device memory.",
     "sniper_conv2d_nhwc": "NHWC implicit-GEMM convolution on tcgen05; also the stride-1/stride-2 data gradient (flipped / parity-split weights, strided output map). Replaces cudnnConvolutionForward / BackwardData (nn/cudnn/cudnn_convolution-inl.h:144,211-266).",
     "sniper_conv2d_wgrad_nhwc": "Weight gradient dW[Cout, taps*Cin] += dY^T * im2col(X) on tcgen05 with MN-major operands and split-K. Replaces cudnnConvolutionBackwardFilter (nn/cudnn/cudnn_convolution-inl.h:211-266).",
-    "sniper_affine_act": "y = relu?(x*scale[c] + shift[c]) on [M,C] rows (BatchNorm apply + Activation; nn/batch_norm.cu:658-700).",
+    "sniper_affine_act": "y = act(x*scale[c] + shift[c]) on [M,C] rows (BatchNorm apply + Activation; nn/batch_norm.cu:658-700); relu 0 = none, 1 = ReLU, 2 = clip(y, 0, 6).",
     "sniper_bn_stats": "Train-mode BatchNorm statistics -> mean, invstd, scale, shift and moving statistics (cuDNN convention, nn/cudnn/cudnn_batch_norm-inl.h).",
     "sniper_bn_apply_train": "BatchNorm(train) + Activation in one launch when the input statistics were accumulated by the producing conv's epilogue: finalisation (mean / invstd / scale / shift / moving statistics, nn/batch_norm.cu:658-700 semantics) folded into the apply pass.",
     "sniper_bn_frozen": "use_global_stats BatchNorm: scale/shift from the moving statistics (nn/batch_norm.cu:671-674 path).",
     "sniper_bn_relu_bwd": "Backward of relu(bn_train(x)): dx (+add), dgamma +=, dbeta +=.",
+    "sniper_bn_act_bwd": "Backward of act(bn_train(x)) with act 1 = ReLU (Activation), 2 = clip(y, 0, 6) (mx.sym.clip: relu6 of symbols/faster/mobilenetv2_e2e.py:18-19, gradient mask of tensor/matrix_op-inl.h:1319-1332), 3 = none (linear bottleneck): dx (+add), dgamma +=, dbeta +=.",
     "sniper_affine_relu_bwd": "Backward of relu?(x*scale+shift) for frozen BN.",
+    "sniper_depthwise3x3_fwd": "Depthwise 3x3 convolution, pad 1, stride 1|2, NHWC, weights [9,C] fp32: Convolution(num_group = num_filter = C) of mobilenetv2_e2e.py:58-66 (src/operator/nn/depthwise_convolution-inl.h DepthwiseConvolutionOp::Forward).",
+    "sniper_depthwise3x3_dgrad": "Data gradient of the depthwise convolution (depthwise_convolution-inl.h Backward, DepthwiseConv2dBackwardDataGpu), gather form.",
+    "sniper_depthwise3x3_wgrad": "Weight gradient of the depthwise convolution (DepthwiseConv2dBackwardFilterGpu): dw[9,C] += per-channel correlation of dy with the shifted input.",
+    "sniper_im2col3x3s2_nchw": "im2col of MobileNetV2's first layer (3x3 / stride 2 / pad 1 over the 3-channel fp32 NCHW `data`, mobilenetv2_e2e.py:204-212) so that it runs on the tcgen05 GEMM; K order (kh, kw, ci), zero-padded to Kp.",
+    "sniper_add_rows": "out = a + b on [M,C] rows: elemwise_add of the inverted-residual shortcut (mobilenetv2_e2e.py:22-24).",
     "sniper_relu_bwd": "dx = dy * (y > 0).",
     "sniper_maxpool3x3s2_nhwc": "Pooling max 3x3 stride 2 pad 1 (resnet_mx_101_e2e.py:409; nn/pool.cuh).",
     "sniper_stem_im2col": "im2col of bn_data(x) for conv0 (resnet_mx_101_e2e.py:402-404) so that the 7x7 stem runs on the tcgen05 kernel (sniper_gemm_nt with bn0 + ReLU as epilogue).",
