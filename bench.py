@@ -347,6 +347,145 @@ def run_config5(args):
                       "data": "synthetic"}))
 
 
+def hbm_kernel_table(B, lowp, peak_gbs):
+    """The depthwise / BatchNorm-backward kernels of the MobileNetV2 step alone, at the step's largest shapes: CUDA-event
+    time per launch (after warm-up, inputs >> L2) and ALGORITHMIC bytes (each operand once) / time against the measured
+    HBM copy bandwidth.  These are the HBM-bound launches of config 4 (depthwise.cu, elementwise.cu)."""
+    import torch
+    from sniper_b200 import ops
+    dt = torch.bfloat16 if lowp else torch.float32
+    es = 2 if lowp else 4
+    rows = []
+
+    def timed(name, fn, nbytes, reps=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        gbs = nbytes / us / 1e3
+        rows.append({"kernel": name, "us": round(us, 1), "algorithmic_mb": round(nbytes / 1e6, 1), "gbs": round(gbs, 1),
+                     "frac_of_hbm_peak": round(gbs / peak_gbs, 3)})
+
+    for (H, C, s) in ((256, 64, 1), (256, 128, 2), (128, 192, 1), (32, 384, 1)):
+        x = torch.randn(B, H, H, C, device="cuda").to(dt)
+        w = torch.randn(9, C, device="cuda")
+        Ho = (H - 1) // s + 1
+        dy = torch.randn(B, Ho, Ho, C, device="cuda").to(dt)
+        y = torch.empty_like(dy)
+        dx = torch.empty_like(x)
+        dw = torch.zeros(9, C, device="cuda")
+        nin, nout = x.numel() * es, dy.numel() * es
+        tag = "%dx%dx%d s%d" % (H, H, C, s)
+        timed("dw_fwd " + tag, lambda: ops.depthwise3x3(x, w, s, out=y), nin + nout)
+        timed("dw_dgrad " + tag, lambda: ops.depthwise3x3_dgrad(dy, w, (H, H), s, out=dx), nin + nout)
+        timed("dw_wgrad " + tag, lambda: ops.depthwise3x3_wgrad(x, dy, dw, s), nin + nout)
+        if s == 1:
+            st = ops.BNState(C, "cuda")
+            ops.bn_stats(x, st, eps=1e-5, momentum=0.9)
+            # reduction pass reads x, dy; apply pass reads x, dy and writes dx: 5 tensor passes
+            timed("bn_act_bwd(clip) " + tag, lambda: ops.bn_act_bwd(x, dy, st, 2, out=dx), 5 * nin)
+        del x, dy, y, dx
+    return rows
+
+
+def run_config4(args):
+    """BASELINE config 4: MobileNetV2 SNIPER, 512x512 chips, mixed precision (bf16 in place of the reference's fp16),
+    B = args.config4 chips per GPU (BASELINE: 40 = 320 / 8), synthetic chips + boxes, random-init weights.  One JSON line:
+    chips/s device-resident (`value`) and end to end from pinned host batches (`e2e`), the HBM kernel table, clocks."""
+    import torch
+    import torch.distributed as dist
+    from sniper_b200 import model_mnv2 as MM
+    from sniper_b200 import ops, synth_batch
+    from sniper_b200.trainer import Trainer
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B = int(args.config4)
+    cfg = MM.MCfg()
+    cfg.batch_images = B
+    cfg.bf16 = not args.fp32
+    npool = 3
+    pool = [synth_batch.make_batch(B, seed=300 + 17 * rank + i, device="cpu", pinned=True, A=cfg.num_anchors,
+                                   stride=cfg.feat_stride) for i in range(npool)]
+    dev_pool = [{k: v.to("cuda:%d" % local_rank) for k, v in b.items()} for b in pool]
+    h2d = sum(v.numel() * v.element_size() for v in pool[0].values())
+    net = MM.SniperMobileNetV2(cfg, device="cuda:%d" % local_rank)
+    trainer = Trainer(cfg, device="cuda:%d" % local_rank, world_size=world, use_graph=not args.no_graph, net=net)
+    trainer.load(pool[0])
+    trainer.capture()
+    sampler = ClockSampler(local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def dev_step(i):
+        b = dev_pool[i % npool]
+        for k, v in b.items():
+            trainer.static[k].copy_(v, non_blocking=True)
+        trainer.step_device()
+
+    for i in range(max(args.warmup, 3)):
+        dev_step(i)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        dev_step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    for i in range(2):
+        trainer.step(pool[i % npool], prefetch=pool[(i + 1) % npool])
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    losses = None
+    for i in range(args.steps):
+        losses = trainer.step(pool[(i + 2) % npool], prefetch=pool[(i + 3) % npool])
+    t1.record()
+    barrier()
+    ms_e2e = t0.elapsed_time(t1)
+    sampler.stop_flag = True
+    t = torch.tensor([ms, ms_e2e], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    peaks, peak_src = load_peaks()
+    launches = trainer.launches_per_step
+    del trainer, net
+    torch.cuda.empty_cache()
+    table = hbm_kernel_table(min(B, 8), bool(cfg.bf16), peaks["hbm_gbs"])
+    chips = B * world * args.steps
+    print(json.dumps({
+        "metric": "512x512 chips/sec train (MobileNetV2 SNIPER)", "value": round(chips / (ms / 1e3), 2), "unit": "chips/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if cfg.bf16 else "tf32",
+        "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[3]: MobileNetV2 SNIPER, 512x512 chips, %d chips/GPU, stride 32, 15 "
+                               "anchors, mixed precision (bf16 for the reference's fp16); random-init weights; the step's "
+                               "working set (GBs of activations) exceeds L2, inputs rotate over %d HBM-resident batches"
+                               % (B, npool), "global_batch": B * world, "parallelism": "dp%d" % world},
+        "e2e": {"value": round(chips / (ms_e2e / 1e3), 2), "unit": "chips/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 32, "ms_per_step": round(ms_e2e / args.steps, 3)},
+        "gpu_launches": launches * args.steps, "launches_per_step": launches, "losses": losses,
+        "hbm_kernels": table, "hbm_peak_gbs": peaks["hbm_gbs"], "peak_source": peak_src, "clocks": sampler.summary()}))
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -498,9 +637,15 @@ def main():
     ap.add_argument("--config5", type=int, default=0, metavar="N_IMAGES",
                     help="instead of the training bench: BASELINE config 5, the AutoFocus inference pyramid on N synthetic "
                          "1333x800 images (imgs/s, per-scale detect / post-processing time, soft-NMS latency)")
+    ap.add_argument("--config4", type=int, default=0, metavar="CHIPS_PER_GPU",
+                    help="instead of the ResNet-101 bench: BASELINE config 4, the MobileNetV2 SNIPER training step with this "
+                         "many chips per GPU (BASELINE: 40), mixed precision unless --fp32")
+    ap.add_argument("--fp32", action="store_true", help="--config4 in fp32 storage / TF32 math")
     args = ap.parse_args()
     args.iterator_leg = not args.skip_iterator
-    if args.config5:
+    if args.config4:
+        run_config4(args)
+    elif args.config5:
         run_config5(args)
     elif args.impl == "reference":
         run_reference(args)

@@ -15,16 +15,19 @@ from . import lr_scheduler, model, ops
 
 class Trainer:
     def __init__(self, cfg=None, device="cuda:0", world_size=1, use_graph=True, seed=5, deform_offset_std=0.0,
-                 scheduler="config"):
+                 scheduler="config", net=None):
         """scheduler: "config" = the reference's WarmupMultiBatchScheduler built from cfg (lr, lr_step, warmup*), None =
-        constant cfg.lr, or any callable num_update -> lr."""
-        self.cfg = cfg or model.Cfg()
+        constant cfg.lr, or any callable num_update -> lr.  net: an already constructed network exposing the same
+        surface as model.SniperResNet101 (P, fb_phases, forward_backward, train_bns, set_lr, update), e.g.
+        model_mnv2.SniperMobileNetV2; default: the ResNet-101 graph built from cfg."""
+        self.cfg = cfg or (net.cfg if net is not None else model.Cfg())
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         self.world_size = world_size
         self.overlap_allreduce = True     # False: one all-reduce of the whole buffer after the backward pass (A/B runs)
         self._works = []
-        self.net = model.SniperResNet101(self.cfg, device=self.device, seed=seed, deform_offset_std=deform_offset_std)
+        self.net = net if net is not None else model.SniperResNet101(self.cfg, device=self.device, seed=seed,
+                                                                     deform_offset_std=deform_offset_std)
         self.use_graph = use_graph
         self.static = None
         self.g_fb = None
@@ -168,7 +171,7 @@ class Trainer:
         pool = torch.cuda.graph_pool_handle()
         self.g_fb = []
         phases = self.net.fb_phases(self.static)
-        for _ in range(3):
+        for _ in range(getattr(self.net, "n_phases", 3)):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, pool=pool):
                 self.out = next(phases)

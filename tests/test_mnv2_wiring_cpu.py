@@ -1,0 +1,124 @@
+"""MobileNetV2 SNIPER graph, host logic: the hand-scheduled forward / backward of `model_mnv2.SniperMobileNetV2`
+executed on the CPU in float64 through tests/fake_ops.py (torch restatements of each C-ABI call's contract) against the
+autograd oracle oracle/torch_graph_mnv2.py, whose parameter set is exactly the graph the reference's own
+mobilenetv2_e2e.py builds (tests/golden/ref_symbols.json).  Compared: rois / labels (equal: both sides call the C
+oracle on the same RPN outputs), the four loss sums, every parameter gradient in the reference's names and layouts,
+exact zeros in the padded channels, the checkpoint round trip, and one SGD update."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+@pytest.fixture
+def f64():
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
+
+
+def _net(monkeypatch, B, seed=3):
+    import fake_ops
+    from sniper_b200 import model_mnv2 as MM
+    from sniper_b200 import ops
+    fake_ops.install(monkeypatch, ops)
+    cfg = MM.MCfg()
+    cfg.batch_images = B
+    cfg.bf16 = False
+    cfg.wgrad_stream = False
+    net = MM.SniperMobileNetV2(cfg, device="cpu", seed=seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    for bn in net.all_bns():               # non-trivial affine parameters on the real channels
+        bn.st.gamma[:bn.C] = torch.empty(bn.C).uniform_(0.8, 1.2, generator=g)
+        bn.st.beta[:bn.C] = torch.empty(bn.C).normal_(0, 0.1, generator=g)
+    return cfg, net
+
+
+def _batch(B, chip):
+    from sniper_b200 import synth_batch
+    b = synth_batch.make_batch(B, seed=7, device="cpu", chip=chip, A=15, stride=32)
+    return {k: v.double() for k, v in b.items()}
+
+
+def test_parameter_set_is_the_reference_symbols(monkeypatch, f64):
+    cfg, net = _net(monkeypatch, 1)
+    arg, aux = net.export_reference()
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_symbols.json")))["mobilenetv2_train"]
+    data = {"data", "label", "bbox_target", "bbox_weight", "gt_boxes", "valid_ranges", "im_info", "crowd_boxes"}
+    ref = {n: tuple(s) for n, s in g["arguments"] if n not in data}
+    assert {k: v.shape for k, v in arg.items()} == ref
+    assert {k: v.shape for k, v in aux.items()} == {n: tuple(s) for n, s in g["auxiliary"]}
+    assert g["cfg"]["num_anchors"] == cfg.num_anchors and g["cfg"]["feat_stride"] == cfg.feat_stride
+    assert tuple(g["cfg"]["scales"]) == cfg.scales and tuple(g["cfg"]["ratios"]) == cfg.ratios
+    # round trip through load_reference
+    before = net.P.w.clone()
+    net.P.w.zero_()
+    net.load_reference(arg, aux)
+    assert float((net.P.w - before).abs().max()) < 1e-6        # (load_reference stages through float32)
+
+
+def test_forward_backward_matches_the_autograd_oracle(monkeypatch, f64):
+    import oracle_lib as O
+    import torch_graph as TG
+    import torch_graph_mnv2 as TM
+    B, chip = 2, 256
+    cfg, net = _net(monkeypatch, B)
+    batch = _batch(B, chip)
+    out = net.forward_backward(batch)
+    A = cfg.num_anchors
+    prob = out["rpn_cls_prob"].permute(0, 3, 1, 2).contiguous()
+    bbox = out["rpn_head"][..., :4 * A].permute(0, 3, 1, 2).contiguous()
+    res = O.multi_proposal_target(prob.numpy(), bbox.numpy(), batch["im_info"].numpy(), batch["gt_boxes"].numpy(),
+                                  batch["valid_ranges"].numpy(), feat_stride=32, scales=cfg.scales, ratios=cfg.ratios)
+    assert out["rois"].numpy().astype(np.float32).tobytes() == res["rois"].tobytes()
+    assert int((res["label"] > 0).sum()) > 0, "test batch yields no foreground roi"
+    arg, aux = net.export_reference()
+    P, Aux = TM.params_to_torch(arg, aux)
+    TG.MODE[0] = "exact"
+    obj, ref = TM.forward_train(P, Aux, batch, lambda *_: res, batch_images=B)
+    obj.backward()
+    rel = lambda a, b: float((a.detach().double() - b.detach().double()).norm() / (b.detach().double().norm() + 1e-30))
+    errs = dict(last_fm=rel(out["last_fm"].permute(0, 3, 1, 2), ref["last_fm"]), rpn_prob=rel(prob, ref["rpn_cls_prob"]),
+                cls_prob=rel(out["cls_prob"], ref["cls_prob"]))
+    print("activation errors", errs)
+    assert max(errs.values()) < 1e-5                       # (float32 PSROI oracle inside both graphs)
+    ls, lr = out["losses"][:4], ref["loss_sums"]
+    assert torch.allclose(ls, lr, rtol=1e-4), (ls, lr)
+    garg, _ = net.export_reference(grads=True)
+    worst = []
+    for name, p in P.items():
+        if not p.requires_grad:
+            assert name not in garg
+            continue
+        worst.append((rel(torch.from_numpy(garg[name]), p.grad), name))
+        assert garg[name].shape == tuple(p.grad.shape), name
+    worst.sort(reverse=True)
+    print("worst gradient errors", worst[:5])
+    assert len(worst) == 177 - 2 * 53                      # every tensor except the 53 fixed gamma / beta pairs
+    assert worst[0][0] < 2e-3, worst[:5]                   # (float32 exported weights, float32 PSROI oracle)
+    # ---- padded channels: exactly zero activations, exactly zero gradients (rows and columns of every padded tensor)
+    for c in net.backbone_convs():
+        gw = net.P.grad(c.name + "_weight")
+        assert not gw[c.cout:].any() and not gw[:, c.cin_real:].any(), c.name
+    for u in net.units:
+        assert not net.P.grad(u.dw.name + "_weight")[:, u.dw.C:].any()
+    assert not out["first"][..., cfg.first_c:].any()
+    # ---- one SGD step: real entries move, padding stays zero, gamma / beta fixed
+    w0 = net.P.w.clone()
+    net.update(lr=0.01)
+    assert not torch.equal(net.P.w, w0)
+    for bn in net.all_bns():
+        o, _ = net.P.layout[bn.name + "_gamma"]
+        assert torch.equal(net.P.w[o:o + bn.Cp], w0[o:o + bn.Cp])
+    for c in net.backbone_convs():
+        w = net.P[c.name + "_weight"]
+        assert not w[c.cout:].any() and not w[:, c.cin_real:].any()
