@@ -133,7 +133,7 @@ def _build(B, bf16, seed=5):
 # As in tests/test_graph_parity_gpu.py: forward deviations flip activation masks, so gradients agree to ~sqrt(eps) per
 # layer; a wiring error gives >= 0.7 and norm ratios far from 1.
 TOL = {False: dict(act=2e-2, loss=1e-2, grad=0.35, median=0.15, head=0.1, norm=0.08),
-       True: dict(act=8e-2, loss=5e-2, grad=0.8, median=0.5, head=0.3, norm=0.15)}
+       True: dict(act=0.12, loss=5e-2, grad=0.8, median=0.5, head=0.3, norm=0.15)}
 
 
 @pytest.mark.parametrize("bf16", [False, True])
@@ -209,9 +209,9 @@ def test_trainer_runs_the_mobilenet_graph_under_cuda_graphs():
     cfg = MM.MCfg()
     cfg.batch_images = 2
     cfg.bf16 = True
-    cfg.warmup_step = 10
+    cfg.lr = 0.01
     net = MM.SniperMobileNetV2(cfg, device="cuda:0", seed=3)
-    tr = Trainer(cfg, device="cuda:0", use_graph=True, net=net)
+    tr = Trainer(cfg, device="cuda:0", use_graph=True, net=net, scheduler=None)       # constant lr
     host = [synth_batch.make_batch(2, seed=20 + i, device="cpu", pinned=True, A=cfg.num_anchors, stride=cfg.feat_stride)
             for i in range(2)]
     w0 = net.P.w.clone()
