@@ -125,6 +125,74 @@ class NetSymbol(object):
         return model.SniperResNet101(c, device=device, seed=seed)
 
 
+MNV2_BOTTLENECKS = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1))
+
+
+class MobileNetSymbol(NetSymbol):
+    """Names and shapes of the MobileNetV2 SNIPER graph (symbols/faster/mobilenetv2_e2e.py:171-305; train graph)."""
+    feat_stride = 32
+
+    def __init__(self, cfg, is_train=True, num_classes=81, num_anchors=15, rois_per_chip=300, max_gt=100):
+        NetSymbol.__init__(self, cfg, is_train, num_classes, num_anchors, rois_per_chip, max_gt)
+
+    def _unit(self, prefix, o, i, k, groups=1):
+        self._args.append((prefix + "-conv2d_weight", (o, i // groups, k, k)))
+        self._bn(prefix + "-batchnorm", o)
+
+    def _build(self):
+        A, K = self.num_anchors, self.num_classes
+        self._unit("first-3x3-conv", 32, 3, 3)
+        in_c = 32
+        for si, (t, c, n, st) in enumerate(MNV2_BOTTLENECKS):
+            for j in range(n):
+                ci = in_c if j == 0 else c
+                e = int(round(ci * t))
+                p = "seq-%d-block%d" % (si, j)
+                self._unit(p + "-exp", e, ci, 1)
+                self._unit(p + "-depthwise", e, e, 3, groups=e)
+                self._unit(p + "-linear", c, e, 1)
+            in_c = c
+        self._unit("last-1x1-conv", 1280, in_c, 1)
+        self._conv("rpn_conv_3x3", 256, 1280, 3, True)
+        self._conv("rpn_cls_score", 2 * A, 256, 1, True)
+        self._conv("rpn_bbox_pred", 4 * A, 256, 1, True)
+        self._conv("conv_new_1", 256, 1280, 1, True)
+        self._fc("offset", 2 * 7 * 7, 256 * 7 * 7)
+        self._fc("fc_new_1", 512, 256 * 7 * 7)
+        self._fc("fc_new_2", 512, 512)
+        self._fc("cls_score", K, 512)
+        self._fc("bbox_pred", 4, 512)
+
+    def data_names(self):
+        if self.is_train:
+            return ["data", "im_info", "gt_boxes", "valid_ranges", "crowd_boxes", "label", "bbox_target", "bbox_weight"]
+        return ["data", "im_info", "im_ids", "chip_ids"]
+
+    def infer_shape(self, **data_shapes):
+        B = data_shapes["data"][0]
+        H, W = data_shapes["data"][2] // 32, data_shapes["data"][3] // 32
+        A, K, R = self.num_anchors, self.num_classes, self.rois
+        dflt = {"data": data_shapes["data"], "im_info": (B, 3), "im_ids": (B,), "chip_ids": (B,),
+                "gt_boxes": (B, self.max_gt, 5), "valid_ranges": (B, 2), "crowd_boxes": (B, 10, 5),
+                "label": (B, A * H * W), "bbox_target": (B, 4 * A, H, W), "bbox_weight": (B, 4 * A, H, W)}
+        arg = [tuple(data_shapes.get(n, dflt[n])) for n in self.data_names()] + [s for _, s in self._args]
+        if self.is_train:
+            out = [(B, 2, A * H, W), (B, 4 * A, H, W), (B, R, K), (B, R, 4), (B * R,)]
+        else:
+            out = [(B * R, 5), (B, R, K), (B, R, 4), (B,), (B, 3), (B,)]
+        return arg, out, [s for _, s in self._aux]
+
+    def bind(self, device="cuda:0", batch_images=40, bf16=True, seed=5, **cfg_overrides):
+        """The executor: `model_mnv2.SniperMobileNetV2` (training graph)."""
+        from . import model_mnv2
+        c = model_mnv2.MCfg()
+        c.batch_images = batch_images
+        c.bf16 = bool(bf16)
+        for k, v in cfg_overrides.items():
+            setattr(c, k, v)
+        return model_mnv2.SniperMobileNetV2(c, device=device, seed=seed)
+
+
 def recognise_graph(sym):
     """Host-only: decides whether a graph built by the reference's own symbol file through `mxnet_compat` (or loaded from
     a `-symbol.json`) is one this package executes, by its parameter set: every non-data argument / auxiliary state must
@@ -142,14 +210,16 @@ def recognise_graph(sym):
     B = int(nodes["multi_proposal_target"].attrs.get("batch_size", 16)) if is_train else \
         int(nodes["rois"].attrs.get("batch_size", 1)) if "rois" in nodes else 1
     fp16 = any(n.op == "Cast" and n.attrs.get("dtype") == "float16" for n in nodes.values())
-    ours = NetSymbol(None, is_train=is_train, num_classes=K, num_anchors=A)
+    mnv2 = "first-3x3-conv-conv2d" in nodes
+    stride = 32 if mnv2 else 16
+    ours = (MobileNetSymbol if mnv2 else NetSymbol)(None, is_train=is_train, num_classes=K, num_anchors=A)
     data = set(ours.data_names()) | {"scale_label", "crowd_boxes"}
     H = 512
     shapes = {"data": (B, 3, H, H)}
     if is_train:
-        Hf = H // 16
+        Hf = H // stride
         shapes.update({"label": (B, A * Hf * Hf), "bbox_target": (B, 4 * A, Hf, Hf), "bbox_weight": (B, 4 * A, Hf, Hf),
-                       "gt_boxes": (B, 100, 5), "valid_ranges": (B, 2), "im_info": (B, 3)})
+                       "gt_boxes": (B, 100, 5), "valid_ranges": (B, 2), "im_info": (B, 3), "crowd_boxes": (B, 10, 5)})
     else:
         shapes.update({"im_info": (B, 3), "im_ids": (B,), "chip_ids": (B,)})
     args, _, auxs = sym.infer_shape_partial(**shapes)
@@ -162,16 +232,22 @@ def recognise_graph(sym):
     diff = sorted((set(theirs) - af) ^ set(mine)) + sorted(set(theirs_aux) ^ set(mine_aux))
     diff += sorted(k for k in mine if k in theirs and theirs[k] != mine[k])
     if diff:
-        raise NotImplementedError("this package executes the ResNet-101 SNIPER R-FCN graph only; the given graph differs in "
-                                  "%d parameters, e.g. %s" % (len(diff), ", ".join(diff[:6])))
-    return dict(batch_images=B, num_anchors=A, num_classes=K, bf16=fp16, is_train=is_train, autofocus=bool(af))
+        raise NotImplementedError("this package executes the ResNet-101 and MobileNetV2 SNIPER R-FCN graphs only; the given "
+                                  "graph differs in %d parameters, e.g. %s" % (len(diff), ", ".join(diff[:6])))
+    if mnv2 and not is_train:
+        raise NotImplementedError("MobileNetV2: only the training graph is executable")
+    info = dict(batch_images=B, num_anchors=A, num_classes=K, bf16=fp16, is_train=is_train, autofocus=bool(af))
+    if mnv2:
+        info["network"] = "mobilenetv2"
+    return info
 
 
 def bind_graph(sym, device="cuda:0", **overrides):
     """`mxnet_compat.Symbol.bind`: the executor for a recognised graph (model.SniperResNet101; fp16 graphs run the bf16
     mixed-precision configuration).  Needs the CUDA library -- fails loudly without it."""
     info = recognise_graph(sym)
-    ours = NetSymbol(None, is_train=info["is_train"], num_classes=info["num_classes"], num_anchors=info["num_anchors"])
+    cls = MobileNetSymbol if info.get("network") == "mobilenetv2" else NetSymbol
+    ours = cls(None, is_train=info["is_train"], num_classes=info["num_classes"], num_anchors=info["num_anchors"])
     kw = dict(batch_images=info["batch_images"], bf16=info["bf16"], num_classes=info["num_classes"],
               num_anchors=info["num_anchors"])
     kw.update(overrides)
@@ -283,5 +359,38 @@ class resnet_mx_101_e2e(Symbol):
         for n in ('fc_new_1', 'fc_new_2', 'cls_score', 'bbox_pred'):
             arg_params[n + '_weight'] = normal(n + '_weight')
             arg_params[n + '_bias'] = zeros(n + '_bias')
+
+    init_weights = init_weight_rcnn
+
+
+class mobilenetv2_e2e(Symbol):
+    """symbols/faster/mobilenetv2_e2e.py:152-158 (constructor), :171-305 (get_symbol_rcnn), :364-391 (init_weight_rcnn)."""
+
+    def __init__(self, n_proposals=400, momentum=0.95, fix_bn=False, test_nbatch=1):
+        Symbol.__init__(self)
+        self.multiplier = 1
+        self.test_nbatch = test_nbatch
+
+    def get_bbox_param_names(self):
+        return ['bbox_pred_weight', 'bbox_pred_bias']
+
+    def get_symbol_rcnn(self, cfg, is_train=True):
+        num_classes = getattr(getattr(cfg, "dataset", None), "NUM_CLASSES", 81)
+        net = getattr(cfg, "network", None)
+        num_anchors = getattr(net, "NUM_ANCHORS", 15) if net is not None else 15
+        self.sym = MobileNetSymbol(cfg, is_train=is_train, num_classes=num_classes, num_anchors=num_anchors)
+        return self.sym
+
+    get_symbol = get_symbol_rcnn
+
+    def init_weight_rcnn(self, cfg, arg_params, aux_params, seed=None):
+        rng = np.random.RandomState(seed) if seed is not None else np.random
+        sh = self.arg_shape_dict
+        for n in ('rpn_conv_3x3', 'rpn_cls_score', 'rpn_bbox_pred', 'conv_new_1', 'fc_new_1', 'fc_new_2', 'cls_score',
+                  'bbox_pred'):
+            arg_params[n + '_weight'] = (rng.standard_normal(sh[n + '_weight']) * 0.01).astype(np.float32)
+            arg_params[n + '_bias'] = np.zeros(sh[n + '_bias'], np.float32)
+        arg_params['offset_weight'] = np.zeros(sh['offset_weight'], np.float32)
+        arg_params['offset_bias'] = np.zeros(sh['offset_bias'], np.float32)
 
     init_weights = init_weight_rcnn

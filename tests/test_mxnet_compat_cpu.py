@@ -201,3 +201,42 @@ def test_recognise_graph_accepts_the_resnet_graphs_and_refuses_others():
         s50 = r50.resnet_mx_50_e2e(n_proposals=400, momentum=0.995).get_symbol_rcnn(cfg)
     with pytest.raises(NotImplementedError):
         symbols.recognise_graph(s50)
+
+
+def test_mobilenet_symbol_equals_the_graph_the_reference_builds():
+    from types import SimpleNamespace
+    from sniper_b200 import symbols
+    g = _gold()["mobilenetv2_train"]
+    cfg = SimpleNamespace(dataset=SimpleNamespace(NUM_CLASSES=81), network=SimpleNamespace(NUM_ANCHORS=15))
+    inst = symbols.mobilenetv2_e2e()
+    sym = inst.get_symbol_rcnn(cfg)
+    data = {n: tuple(s) for n, s in g["arguments"] if n in sym.data_names()}
+    assert set(data) == set(sym.data_names())
+    arg, out, aux = sym.infer_shape(**data)
+    assert dict(zip(sym.list_arguments(), map(tuple, arg))) == {n: tuple(s) for n, s in g["arguments"]}
+    assert list(zip(sym.list_auxiliary_states(), map(tuple, aux))) == [(n, tuple(s)) for n, s in g["auxiliary"]]
+    assert list(zip(sym.list_outputs(), map(tuple, out))) == [(n, tuple(s)) for n, s in g["outputs"]]
+    inst.infer_shape(data)
+    a, x = {}, {}
+    inst.init_weight_rcnn(cfg, a, x, seed=0)
+    assert a["fc_new_1_weight"].shape == (512, 12544) and not a["offset_weight"].any()
+
+
+@needs_ref
+def test_recognise_graph_accepts_the_mobilenet_training_graph():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import run_ref_symbols as R
+    from sniper_b200 import mxnet_compat as MC
+    from sniper_b200 import symbols
+    mob = MC.load_symbol_file(os.path.join(REF, "symbols/faster/mobilenetv2_e2e.py"))
+    cfg = R.load_config("sniper_mobilenetv2_e2e.yml")
+    cfg.TRAIN.BATCH_IMAGES = 40
+    with MC.NameManager():
+        sym = mob.mobilenetv2_e2e(n_proposals=400, momentum=0.995).get_symbol_rcnn(cfg)
+    info = symbols.recognise_graph(sym)
+    assert info == dict(batch_images=40, num_anchors=15, num_classes=81, bf16=True, is_train=True, autofocus=False,
+                        network="mobilenetv2")
+    with MC.NameManager():
+        test_sym = mob.mobilenetv2_e2e(test_nbatch=2).get_symbol_rcnn(cfg, is_train=False)
+    with pytest.raises(NotImplementedError):
+        symbols.recognise_graph(test_sym)
