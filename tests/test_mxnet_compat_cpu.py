@@ -195,6 +195,19 @@ def test_recognise_graph_accepts_the_resnet_graphs_and_refuses_others():
     inst.init_weight_rcnn(cfg, arg, aux)
     assert arg["rpn_conv_3x3_weight"].shape == (512, 3072, 3, 3) and not np.asarray(arg["offset_weight"]).any()
     assert abs(float(np.asarray(arg["fc_new_1_weight"]).std()) - 0.01) < 1e-3
+    # the reference's own checkpoint_callback (:6-17) writes -symbol.json + .params with the *_test copies
+    import tempfile
+    from sniper_b200 import checkpoint as ck
+    with tempfile.TemporaryDirectory() as d:
+        prefix = os.path.join(d, "e2e")
+        small = {"bbox_pred_weight": np.asarray(arg["bbox_pred_weight"]), "bbox_pred_bias": np.asarray(arg["bbox_pred_bias"]) + 1}
+        res.checkpoint_callback(inst.get_bbox_param_names(), prefix, None, None)(3, inst.symbol, small, {})
+        a2, x2 = ck.read_params(prefix + "-0004.params")
+        assert set(a2) == {"bbox_pred_weight", "bbox_pred_bias", "bbox_pred_weight_test", "bbox_pred_bias_test"} and not x2
+        assert np.allclose(a2["bbox_pred_bias_test"], small["bbox_pred_bias"] * np.array([0.1, 0.1, 0.2, 0.2]))
+        assert set(small) == {"bbox_pred_weight", "bbox_pred_bias"}
+        back = MC.load(prefix + "-symbol.json")
+        assert back.list_arguments() == inst.symbol.list_arguments() and back.tojson() == inst.symbol.tojson()
     # a ResNet-50 graph is not ours
     r50 = MC.load_symbol_file(os.path.join(REF, "symbols/faster/resnet_mx_50_e2e.py"))
     with MC.NameManager():
