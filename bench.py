@@ -467,6 +467,8 @@ def run_config4(args):
         return
     peaks, peak_src = load_peaks()
     launches = trainer.launches_per_step
+    if os.environ.get("SNIPER_BREAKDOWN"):
+        entry_point_breakdown(trainer, os.environ["SNIPER_BREAKDOWN"])
     del trainer, net
     torch.cuda.empty_cache()
     table = hbm_kernel_table(B, bool(cfg.bf16), peaks["hbm_gbs"])

@@ -32,8 +32,9 @@ __global__ void __launch_bounds__(kTPB) dw_dgrad_kernel(const T* __restrict__ dy
   if (tid < nthreads) dwc::dgrad<T, S>(tid, dy, w, dx, p);
 }
 
-// block = 32 channel lanes (128 channels) x 8 pixel lanes; partial sums of the 8 pixel lanes are combined in shared
-// memory, then one float atomic per (block, tap, channel): gridDim.x * 9 * C atomics in total
+// block = 32 x 8 threads; a warp row covers LC channel vectors x 32/LC pixels (depthwise_core.cuh).  Partial sums of
+// the pixel lanes are combined in shared memory, then one float atomic per (block, tap, channel): gridDim.x * 9 * C
+// atomics in total
 constexpr int kWgTY = 8;
 template <typename T, int S>
 __global__ void __launch_bounds__(32 * kWgTY) dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy,
@@ -47,12 +48,14 @@ __global__ void __launch_bounds__(32 * kWgTY) dw_wgrad_kernel(const T* __restric
 #pragma unroll
     for (int k = 0; k < 4; ++k) red[ty][tx][t * 4 + k] = acc[t][k];
   __syncthreads();
-  for (int i = ty * 32 + tx; i < 32 * 36; i += 32 * kWgTY) {
+  const int LC = dwc::wgrad_lc(p.C), PPW = 32 / LC;
+  for (int i = ty * 32 + tx; i < LC * 36; i += 32 * kWgTY) {
     const int lane = i / 36, e = i - lane * 36;
     float s = 0.f;
+    for (int ps = 0; ps < PPW; ++ps)
 #pragma unroll
-    for (int j = 0; j < kWgTY; ++j) s += red[j][lane][e];
-    const int c = (((int)blockIdx.y * 32 + lane) << 2) + (e & 3);
+      for (int j = 0; j < kWgTY; ++j) s += red[j][ps * LC + lane][e];
+    const int c = (((int)blockIdx.y * LC + lane) << 2) + (e & 3);
     if (c < p.C && s != 0.f) atomicAdd(dw + (long)(e >> 2) * p.C + c, s);
   }
 }
@@ -131,10 +134,11 @@ int sniper_depthwise3x3_wgrad(const void* x, long ldx, const void* dy, long lddy
   dwc::Params p;
   if (fill_params(p, NB, H, W, C, stride, ldx, lddy, dtype, "depthwise3x3_wgrad")) return -1;
   cudaStream_t st = (cudaStream_t)stream;
-  const int gy = sn::div_up(C, 128);
+  const int LC = dwc::wgrad_lc(C), PL = kWgTY * (32 / LC);
+  const int gy = sn::div_up(C >> 2, LC);
   const long total = (long)NB * p.Ho * p.Wo;
   long gx = (sn::kNumSMs * 4 + gy - 1) / gy;          // ~4 blocks of 256 threads per SM over the whole grid
-  const long gx_max = (total + kWgTY - 1) / kWgTY;
+  const long gx_max = (total + PL - 1) / PL;
   if (gx > gx_max) gx = gx_max;
   if (gx < 1) gx = 1;
   const dim3 grid((unsigned)gx, (unsigned)gy, 1), block(32, kWgTY, 1);

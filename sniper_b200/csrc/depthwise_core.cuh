@@ -58,9 +58,18 @@ DW_HD void store4(__nv_bfloat16* p, const float (&v)[4]) {
   *reinterpret_cast<uint2*>(p) = u;
 }
 
+DW_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+DW_HD void zero4(float (&v)[4]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
+
+// Border handling in all three kernels: every load is issued UNCONDITIONALLY from a clamped (always valid) address
+// and the value is zeroed afterwards when the tap falls outside the map.  With the loads behind per-thread branches
+// (first version: `if (outside) continue;`) the compiler could not hoist them and each warp had one load in flight at
+// a time: 0.03-0.3 of the HBM roof (profiles/config4_r02.json).
+
 // ---- forward: y[n,ho,wo,c] = sum_{kh,kw} x[n, ho*S+kh-1, wo*S+kw-1, c] * w[kh*3+kw, c]
 // One thread = PW consecutive output pixels of one row x 4 channels: the (PW-1)*S+3 input columns of a row are loaded
-// once and feed every output they belong to (stride 1, PW 4: 18 loads for 4 outputs instead of 36).
+// once (all of them in flight together) and feed every output they belong to (stride 1, PW 4: 18 loads for 4 outputs
+// instead of 36).
 template <typename T, int S, int PW>
 DW_HD void fwd(long tid, const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, const Params& p) {
   const int CV = p.C >> 2;
@@ -75,28 +84,28 @@ DW_HD void fwd(long tid, const T* __restrict__ x, const float* __restrict__ w, T
   const int wo0 = wb * PW;
   float acc[PW][4];
 #pragma unroll
-  for (int q = 0; q < PW; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f; }
+  for (int q = 0; q < PW; ++q) zero4(acc[q]);
   constexpr int NCOL = (PW - 1) * S + 3;
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
     const int hi = ho * S + kh - 1;
-    if (hi < 0 || hi >= p.H) continue;
-    float wk[3][4];
+    const bool hv = hi >= 0 && hi < p.H;
+    const T* row = x + ((n * p.H + clampi(hi, 0, p.H - 1)) * (long)p.W) * p.ldx + c;
+    float v[NCOL][4], wk[3][4];
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) load4(row + (long)clampi(wo0 * S + j - 1, 0, p.W - 1) * p.ldx, v[j]);
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) load4(w + (long)(kh * 3 + kw) * p.C + c, wk[kw]);
-    const T* row = x + ((n * p.H + hi) * (long)p.W) * p.ldx + c;
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) {
       const int wi = wo0 * S + j - 1;
-      if (wi < 0 || wi >= p.W) continue;
-      float v[4];
-      load4(row + (long)wi * p.ldx, v);
+      if (!(hv && wi >= 0 && wi < p.W)) zero4(v[j]);
 #pragma unroll
       for (int q = 0; q < PW; ++q) {
         const int kw = j - q * S;          // compile-time after unrolling
         if (kw >= 0 && kw < 3) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) acc[q][k] = fmaf(v[k], wk[kw][k], acc[q][k]);
+          for (int k = 0; k < 4; ++k) acc[q][k] = fmaf(v[j][k], wk[kw][k], acc[q][k]);
         }
       }
     }
@@ -112,8 +121,9 @@ DW_HD long fwd_threads(const Params& p) {
 
 // ---- data gradient: dx[n,h,w,c] = sum_{kh,kw : (h+1-kh) % S == 0, (w+1-kw) % S == 0}
 //                                   dy[n, (h+1-kh)/S, (w+1-kw)/S, c] * w[kh*3+kw, c]
-// One thread = one input pixel x 4 channels (gather form: no atomics, deterministic).  Params describe the FORWARD
-// convolution (H, W = dx map; Ho, Wo = dy map; ldx = dx pixel stride, ldy = dy pixel stride).
+// One thread = one input pixel x 4 channels (gather form: no atomics, deterministic).  Stride 1: 3 x 3 taps.  Stride 2:
+// only the taps of matching parity exist -- kh = 1 for even h, kh in {0, 2} for odd h (same for w): at most 2 x 2 loads.
+// Params describe the FORWARD convolution (H, W = dx map; Ho, Wo = dy map; ldx = dx pixel stride, ldy = dy pixel stride).
 template <typename T, int S>
 DW_HD void dgrad(long tid, const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx, const Params& p) {
   const int CV = p.C >> 2;
@@ -124,65 +134,87 @@ DW_HD void dgrad(long tid, const T* __restrict__ dy, const float* __restrict__ w
   const long n = t / p.H;
   if (n >= p.NB) return;
   const int c = cv << 2;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  constexpr int NK = S == 1 ? 3 : 2;
+  int khs[NK], kws[NK], hos[NK], wos[NK];
+  bool hval[NK], wval[NK];
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int a = hi + 1 - kh;
-    if (a < 0 || (S == 2 && (a & 1))) continue;
-    const int ho = a / S;
-    if (ho >= p.Ho) continue;
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int b = wi + 1 - kw;
-      if (b < 0 || (S == 2 && (b & 1))) continue;
-      const int wo = b / S;
-      if (wo >= p.Wo) continue;
-      float g[4], wk[4];
-      load4(dy + ((n * p.Ho + ho) * (long)p.Wo + wo) * p.ldy + c, g);
-      load4(w + (long)(kh * 3 + kw) * p.C + c, wk);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[k] = fmaf(g[k], wk[k], acc[k]);
-    }
+  for (int i = 0; i < NK; ++i) {
+    khs[i] = S == 1 ? i : (i == 0 ? ((hi & 1) ? 0 : 1) : 2);
+    kws[i] = S == 1 ? i : (i == 0 ? ((wi & 1) ? 0 : 1) : 2);
+    const int a = hi + 1 - khs[i], b = wi + 1 - kws[i];          // = ho * S, wo * S when the tap exists
+    hos[i] = a / S;
+    wos[i] = b / S;
+    hval[i] = a >= 0 && hos[i] < p.Ho && (S == 1 || i == 0 || (hi & 1));
+    wval[i] = b >= 0 && wos[i] < p.Wo && (S == 1 || i == 0 || (wi & 1));
+    hos[i] = clampi(hos[i], 0, p.Ho - 1);
+    wos[i] = clampi(wos[i], 0, p.Wo - 1);
   }
+  float g[NK][NK][4], wk[NK][NK][4];
+#pragma unroll
+  for (int i = 0; i < NK; ++i)
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      load4(dy + ((n * p.Ho + hos[i]) * (long)p.Wo + wos[j]) * p.ldy + c, g[i][j]);
+      load4(w + (long)(khs[i] * 3 + kws[j]) * p.C + c, wk[i][j]);
+    }
+  float acc[4];
+  zero4(acc);
+#pragma unroll
+  for (int i = 0; i < NK; ++i)
+#pragma unroll
+    for (int j = 0; j < NK; ++j) {
+      if (!(hval[i] && wval[j])) zero4(g[i][j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = fmaf(g[i][j][k], wk[i][j][k], acc[k]);
+    }
   store4(dx + ((n * p.H + hi) * (long)p.W + wi) * p.ldx + c, acc);
 }
 DW_HD long dgrad_threads(const Params& p) { return (long)p.NB * p.H * p.W * (p.C >> 2); }
 
 // ---- weight gradient, per-thread partial: acc[t][k] = sum over this thread's output pixels of
-//      dy[q, c+k] * x[n, ho*S+kh-1, wo*S+kw-1, c+k].  Thread (tx, ty) of block (bx, by): channels (by*32 + tx)*4 .. +3,
-//      output pixels q = bx*TY + ty, + gridx*TY, ...  (neighbouring ty lanes take neighbouring pixels: their input
-//      windows overlap in L1).  Returns false when the thread's channels are beyond C.
+//      dy[q, c+k] * x[n, ho*S+kh-1, wo*S+kw-1, c+k].
+// Block = 32 x TY threads.  A warp row (32 lanes) covers LC channel vectors x 32/LC pixels, LC = 32 when C/4 is a
+// multiple of 32, else 16 (C is a multiple of 64): no idle lanes for C = 64 / 192 / 320 / 576 / 960.  Thread (tx, ty) of
+// block (bx, by): channel vector by*LC + tx%LC, pixel lane ty*(32/LC) + tx/LC of TY*(32/LC); output pixels
+// q = bx*PL + lane, + gridx*PL, ...  (neighbouring lanes take neighbouring pixels: their windows overlap in L1).
+// Returns the first channel of the thread, or -1 when it is beyond C.
+DW_HD int wgrad_lc(int C) { return ((C >> 2) % 32 == 0) ? 32 : 16; }
 template <typename T, int S>
-DW_HD bool wgrad_partial(int bx, int by, int tx, int ty, int TY, int gridx, const T* __restrict__ x,
-                         const T* __restrict__ dy, const Params& p, float (&acc)[9][4]) {
+DW_HD int wgrad_partial(int bx, int by, int tx, int ty, int TY, int gridx, const T* __restrict__ x,
+                        const T* __restrict__ dy, const Params& p, float (&acc)[9][4]) {
 #pragma unroll
-  for (int t = 0; t < 9; ++t) { acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f; }
-  const int c = (by * 32 + tx) << 2;
-  if (c >= p.C) return false;
+  for (int t = 0; t < 9; ++t) zero4(acc[t]);
+  const int LC = wgrad_lc(p.C), PPW = 32 / LC;
+  const int c = (by * LC + (tx % LC)) << 2;
+  if (c >= p.C) return -1;
+  const int PL = TY * PPW;
   const long total = (long)p.NB * p.Ho * p.Wo;
-  for (long q = (long)bx * TY + ty; q < total; q += (long)gridx * TY) {
+  for (long q = (long)bx * PL + ty * PPW + tx / LC; q < total; q += (long)gridx * PL) {
     const int wo = (int)(q % p.Wo);
     const long r = q / p.Wo;
     const int ho = (int)(r % p.Ho);
     const long n = r / p.Ho;
-    float g[4];
+    float g[4], v[9][4];
     load4(dy + q * p.ldy + c, g);
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
+      const T* row = x + ((n * p.H + clampi(ho * S + kh - 1, 0, p.H - 1)) * (long)p.W) * p.ldx + c;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) load4(row + (long)clampi(wo * S + kw - 1, 0, p.W - 1) * p.ldx, v[kh * 3 + kw]);
+    }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
       const int hi = ho * S + kh - 1;
-      if (hi < 0 || hi >= p.H) continue;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int wi = wo * S + kw - 1;
-        if (wi < 0 || wi >= p.W) continue;
-        float v[4];
-        load4(x + ((n * p.H + hi) * (long)p.W + wi) * p.ldx + c, v);
+        if (!(hi >= 0 && hi < p.H && wi >= 0 && wi < p.W)) zero4(v[kh * 3 + kw]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[kh * 3 + kw][k] = fmaf(g[k], v[k], acc[kh * 3 + kw][k]);
+        for (int k = 0; k < 4; ++k) acc[kh * 3 + kw][k] = fmaf(g[k], v[kh * 3 + kw][k], acc[kh * 3 + kw][k]);
       }
     }
   }
-  return true;
+  return c;
 }
 
 // ---- im2col of the first layer: 3x3 / stride 2 / pad 1 over an fp32 NCHW image with CIN channels

@@ -32,10 +32,11 @@ template <typename T>
 static void wgrad_t(const void* x, long ldx, const void* dy, long lddy, float* dw, int NB, int H, int W, int C, int stride) {
   dwc::Params p; fill(p, NB, H, W, C, stride, ldx, lddy);
   const int TY = 8;
-  const int gy = (C + 127) / 128;
+  const int LC = dwc::wgrad_lc(C), PL = TY * (32 / LC);
+  const int gy = ((C >> 2) + LC - 1) / LC;
   const long total = (long)NB * p.Ho * p.Wo;
   long gx = (148 * 4 + gy - 1) / gy;
-  const long gx_max = (total + TY - 1) / TY;
+  const long gx_max = (total + PL - 1) / PL;
   if (gx > gx_max) gx = gx_max;
   if (gx < 1) gx = 1;
   for (int by = 0; by < gy; ++by)
@@ -43,10 +44,9 @@ static void wgrad_t(const void* x, long ldx, const void* dy, long lddy, float* d
       for (int ty = 0; ty < TY; ++ty)
         for (int tx = 0; tx < 32; ++tx) {
           float acc[9][4];
-          bool ok = stride == 1 ? dwc::wgrad_partial<T, 1>(bx, by, tx, ty, TY, (int)gx, (const T*)x, (const T*)dy, p, acc)
-                                : dwc::wgrad_partial<T, 2>(bx, by, tx, ty, TY, (int)gx, (const T*)x, (const T*)dy, p, acc);
-          if (!ok) continue;
-          const int c = (by * 32 + tx) * 4;
+          const int c = stride == 1 ? dwc::wgrad_partial<T, 1>(bx, by, tx, ty, TY, (int)gx, (const T*)x, (const T*)dy, p, acc)
+                                    : dwc::wgrad_partial<T, 2>(bx, by, tx, ty, TY, (int)gx, (const T*)x, (const T*)dy, p, acc);
+          if (c < 0) continue;
           for (int t = 0; t < 9; ++t) for (int k = 0; k < 4; ++k) dw[(long)t * C + c + k] += acc[t][k];
         }
 }

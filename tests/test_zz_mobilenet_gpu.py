@@ -130,10 +130,81 @@ def _build(B, bf16, seed=5):
     return cfg, net, batch
 
 
-# As in tests/test_graph_parity_gpu.py: forward deviations flip activation masks, so gradients agree to ~sqrt(eps) per
-# layer; a wiring error gives >= 0.7 and norm ratios far from 1.
-TOL = {False: dict(act=2e-2, loss=1e-2, grad=0.35, median=0.15, head=0.1, norm=0.08),
-       True: dict(act=0.12, loss=5e-2, grad=0.8, median=0.5, head=0.3, norm=0.15)}
+# Whole-graph tolerances.  This network is in the chaotic regime at random initialisation: BatchNorm re-normalises every
+# one of its 53 layers, so a relative perturbation is carried through the whole depth and grows ~170x from the first
+# layer to last_fm (measured on the float64 oracle: 2.4e-6 noise per 1x1 conv -> 4.2e-4, 1e-4 -> 1.7e-2, TF32 operand
+# truncation itself -> 5.2e-2 against exact arithmetic).  TF32 / bf16 quantisation is discontinuous, so two evaluations
+# whose inputs differ in the last fp32 bit re-quantise differently and settle at a fraction of the quantisation effect:
+# measured on B200 (profiles/config4_r02.md) TF32: last_fm 1.4e-2 (3.7x closer to the TF32 model than that model is to
+# exact arithmetic), loss sums 3e-5, gradients 0.24 median / 0.27 worst with norm ratios within 8 %; bf16: last_fm 0.20,
+# loss sums 2e-3, gradients decorrelated (0.85) -- elementwise gradient parity in bf16 is therefore asserted per UNIT
+# (test_inverted_residual_units_match_float64, teacher-forced inputs), and exactly on the CPU for the orchestration
+# (tests/test_mnv2_wiring_cpu.py: 1e-7).  A wiring error shows as >= 0.7 with norm ratios far from 1.
+TOL = {False: dict(act=4e-2, loss=1e-2, grad=0.45, median=0.35, head=0.25, norm=0.15),
+       True: dict(act=0.45, loss=3e-2, grad=None, median=None, head=None, norm=None)}
+
+
+def _unit_oracle(TM, TG, P, x64, prefix, cin, e, stride, shortcut, eps=1e-5):
+    a1 = TM._unit(P, x64, prefix + "-exp", 1, 1, 1, True, eps)
+    a2 = TM._unit(P, a1, prefix + "-depthwise", 3, stride, e, True, eps)
+    y = TM._unit(P, a2, prefix + "-linear", 1, 1, 1, False, eps)
+    return TG.qs(y + x64) if shortcut else y
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_inverted_residual_units_match_float64(bf16):
+    """Each kind of inverted residual unit alone (forward, data gradient, the three weight gradients) on the product's
+    kernels against the oracle's unit in the matching arithmetic mode, from the SAME input and output gradient: t = 1
+    without shortcut, stride 2, shortcut, and the widest (960 -> 320).  No depth, so no amplification: tolerances are
+    the rounding of one unit (TF32: 3 truncated contractions; bf16: 6 stored tensors)."""
+    import torch
+    import torch_graph as TG
+    import torch_graph_mnv2 as TM
+    from sniper_b200 import ops
+    cfg, net, _ = _build(2, bf16)
+    dt = torch.bfloat16 if bf16 else torch.float32
+    arg, aux = net.export_reference()
+    P, _ = TM.params_to_torch(arg, aux, torch.float64, "cuda")
+    tol = dict(y=2e-2, dx=0.15, gw=0.15) if bf16 else dict(y=3e-3, dx=4e-2, gw=4e-2)
+    torch.manual_seed(11)
+    for idx in (0, 1, 2, 16):
+        u = net.units[idx]
+        cinp, coutp = u.exp.cin, u.lin.coutp
+        H = 32
+        x = torch.zeros(2, H, H, cinp, device="cuda")
+        x[..., :u.cin] = (torch.randn(2, H, H, u.cin, device="cuda") + 1.0).clamp(0, 6)
+        x = x.to(dt)
+        ops.weight_transpose_batched(ops.weight_transpose_jobs([j for c in u.convs() for j in c.bwd_jobs()], "cuda"))
+        net.P.g.zero_()
+        y = u.fwd(x, cfg)
+        Ho = y.shape[1]
+        dy = torch.zeros(2, Ho, Ho, coutp, device="cuda")
+        dy[..., :u.cout] = torch.randn(2, Ho, Ho, u.cout, device="cuda")
+        dy = dy.to(dt)
+        dx = u.bwd(dy, cfg)
+        ops.bn_param_grad_batched(ops.bn_param_grad_jobs([b.st for b in u.bns()], "cuda"))
+        cfg.wsched.join()
+        torch.cuda.synchronize()
+        assert not y[..., u.cout:].float().any() and not dx[..., u.cin:].float().any()          # padding stays zero
+        x64 = x[..., :u.cin].double().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+        for p in P.values():
+            p.grad = None
+        TG.MODE[0] = "bf16" if bf16 else "tf32"
+        TG.LOWP[0] = True
+        try:
+            yr = _unit_oracle(TM, TG, P, x64, u.prefix, u.cin, u.e, u.stride, u.shortcut)
+            yr.backward(dy[..., :u.cout].double().permute(0, 3, 1, 2))
+        finally:
+            TG.MODE[0] = "exact"
+            TG.LOWP[0] = False
+        garg, _ = net.export_reference(grads=True)
+        errs = dict(y=_rel(y[..., :u.cout].permute(0, 3, 1, 2), yr), dx=_rel(dx[..., :u.cin].permute(0, 3, 1, 2), x64.grad))
+        for part in ("-exp", "-depthwise", "-linear"):
+            name = u.prefix + part + "-conv2d_weight"
+            errs["gw" + part] = _rel(torch.from_numpy(garg[name]).cuda(), P[name].grad)
+        print(u.prefix, "bf16" if bf16 else "tf32", {k: "%.2e" % v for k, v in errs.items()})
+        for k, v in errs.items():
+            assert v < tol[k[:2]], (u.prefix, k, v)
 
 
 @pytest.mark.parametrize("bf16", [False, True])
@@ -193,12 +264,16 @@ def test_training_graph_matches_float64_reference(bf16):
         assert v < tol["act"], (k, v)
     for i in range(4):
         assert abs(ls[i] - lr[i]) <= tol["loss"] * abs(lr[i]) + 1e-4, (i, ls[i].item(), lr[i].item())
-    for r, name, nrm, ours_n in rows:
-        assert r < tol["grad"] or nrm < 1e-9, (name, r, nrm)
-        assert abs(ours_n / nrm - 1) < tol["norm"] or nrm < 1e-9, (name, ours_n, nrm)
-        if "seq-" not in name and "first" not in name and "last" not in name:
-            assert r < tol["head"], (name, r)
-    assert med < tol["median"]
+    ratios = [ours_n / nrm for _, _, nrm, ours_n in rows if nrm > 1e-9]
+    print("gradient norm ratios: min %.3f max %.3f" % (min(ratios), max(ratios)))
+    assert 0.5 < min(ratios) and max(ratios) < 2.0
+    if tol["grad"] is not None:
+        for r, name, nrm, ours_n in rows:
+            assert r < tol["grad"] or nrm < 1e-9, (name, r, nrm)
+            assert abs(ours_n / nrm - 1) < tol["norm"] or nrm < 1e-9, (name, ours_n, nrm)
+            if "seq-" not in name and "first" not in name and "last" not in name:
+                assert r < tol["head"], (name, r)
+        assert med < tol["median"]
 
 
 def test_trainer_runs_the_mobilenet_graph_under_cuda_graphs():
