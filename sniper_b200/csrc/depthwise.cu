@@ -18,31 +18,31 @@ namespace {
 typedef __nv_bfloat16 bf16;
 constexpr int kTPB = 256;
 
-template <typename T, int S, int PW>
+template <typename T, int S, int PW, bool FLIP>
 __global__ void __launch_bounds__(kTPB) dw_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                        T* __restrict__ y, dwc::Params p, long nthreads) {
   const long tid = (long)blockIdx.x * kTPB + threadIdx.x;
-  if (tid < nthreads) dwc::fwd<T, S, PW>(tid, x, w, y, p);
+  if (tid < nthreads) dwc::fwd<T, S, PW, FLIP>(tid, x, w, y, p);
 }
 
-template <typename T, int S>
-__global__ void __launch_bounds__(kTPB) dw_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w,
-                                                         T* __restrict__ dx, dwc::Params p, long nthreads) {
+template <typename T>
+__global__ void __launch_bounds__(kTPB) dw_dgrad_s2_kernel(const T* __restrict__ dy, const float* __restrict__ w,
+                                                            T* __restrict__ dx, dwc::Params p, long nthreads) {
   const long tid = (long)blockIdx.x * kTPB + threadIdx.x;
-  if (tid < nthreads) dwc::dgrad<T, S>(tid, dy, w, dx, p);
+  if (tid < nthreads) dwc::dgrad_s2<T>(tid, dy, w, dx, p);
 }
 
-// block = 32 x 8 threads; a warp row covers LC channel vectors x 32/LC pixels (depthwise_core.cuh).  Partial sums of
-// the pixel lanes are combined in shared memory, then one float atomic per (block, tap, channel): gridDim.x * 9 * C
-// atomics in total
+// block = 32 x 8 threads; a warp row covers LC channel vectors x 32/LC strips (depthwise_core.cuh).  Partial sums of
+// the strip lanes are combined in shared memory, then one float atomic per (block, tap, channel): gridDim.x * 9 * C
+// atomics in total.  The grid is ONE wave of resident blocks (occupancy API): each thread loops over its strips.
 constexpr int kWgTY = 8;
-template <typename T, int S>
+template <typename T, int S, int PW>
 __global__ void __launch_bounds__(32 * kWgTY) dw_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy,
                                                                float* __restrict__ dw, dwc::Params p) {
   __shared__ float red[kWgTY][32][37];
   const int tx = threadIdx.x, ty = threadIdx.y;
   float acc[9][4];
-  dwc::wgrad_partial<T, S>((int)blockIdx.x, (int)blockIdx.y, tx, ty, kWgTY, (int)gridDim.x, x, dy, p, acc);
+  dwc::wgrad_partial<T, S, PW>((int)blockIdx.x, (int)blockIdx.y, tx, ty, kWgTY, (int)gridDim.x, x, dy, p, acc);
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
@@ -58,6 +58,13 @@ __global__ void __launch_bounds__(32 * kWgTY) dw_wgrad_kernel(const T* __restric
     const int c = (((int)blockIdx.y * LC + lane) << 2) + (e & 3);
     if (c < p.C && s != 0.f) atomicAdd(dw + (long)(e >> 2) * p.C + c, s);
   }
+}
+
+template <typename K>
+int wgrad_blocks_per_sm(K kernel) {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, 32 * kWgTY, 0) != cudaSuccess || n < 1) n = 2;
+  return n;
 }
 
 template <typename T>
@@ -104,7 +111,7 @@ int sniper_depthwise3x3_fwd(const void* x, long ldx, const float* w, void* y, lo
 #define DW_FWD(T, S, PW)                                                                                       \
   do {                                                                                                         \
     const long nt = dwc::fwd_threads<S, PW>(p);                                                                \
-    dw_fwd_kernel<T, S, PW><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const T*>(x), w, static_cast<T*>(y), p, nt); \
+    dw_fwd_kernel<T, S, PW, false><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const T*>(x), w, static_cast<T*>(y), p, nt); \
   } while (0)
   if (dtype == 0) { if (stride == 1) DW_FWD(float, 1, 4); else DW_FWD(float, 2, 2); }
   else            { if (stride == 1) DW_FWD(bf16, 1, 4);  else DW_FWD(bf16, 2, 2); }
@@ -114,16 +121,26 @@ int sniper_depthwise3x3_fwd(const void* x, long ldx, const float* w, void* y, lo
 }
 
 // dx[NB,H,W,C] = depthwise3x3^T(dy[NB,Ho,Wo,C], w[9,C]); H, W, stride describe the FORWARD convolution.
+// stride 1: the forward kernel on dy with the flipped filter; stride 2: one thread per dy pixel -> 2 x 2 block of dx.
 int sniper_depthwise3x3_dgrad(const void* dy, long lddy, const float* w, void* dx, long lddx, int NB, int H, int W,
                               int C, int stride, int dtype, void* stream) {
   dwc::Params p;
-  if (fill_params(p, NB, H, W, C, stride, lddx, lddy, dtype, "depthwise3x3_dgrad")) return -1;
   cudaStream_t st = (cudaStream_t)stream;
-  const long nt = dwc::dgrad_threads(p);
-#define DW_DG(T, S) dw_dgrad_kernel<T, S><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const T*>(dy), w, static_cast<T*>(dx), p, nt)
-  if (dtype == 0) { if (stride == 1) DW_DG(float, 1); else DW_DG(float, 2); }
-  else            { if (stride == 1) DW_DG(bf16, 1);  else DW_DG(bf16, 2); }
-#undef DW_DG
+  if (stride == 1) {
+    if (fill_params(p, NB, H, W, C, 1, lddy, lddx, dtype, "depthwise3x3_dgrad")) return -1;   // "input" = dy, "output" = dx
+    const long nt = dwc::fwd_threads<1, 4>(p);
+    if (dtype == 0)
+      dw_fwd_kernel<float, 1, 4, true><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const float*>(dy), w, static_cast<float*>(dx), p, nt);
+    else
+      dw_fwd_kernel<bf16, 1, 4, true><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const bf16*>(dy), w, static_cast<bf16*>(dx), p, nt);
+  } else {
+    if (fill_params(p, NB, H, W, C, stride, lddx, lddy, dtype, "depthwise3x3_dgrad")) return -1;
+    const long nt = dwc::dgrad_s2_threads(p);
+    if (dtype == 0)
+      dw_dgrad_s2_kernel<float><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const float*>(dy), w, static_cast<float*>(dx), p, nt);
+    else
+      dw_dgrad_s2_kernel<bf16><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const bf16*>(dy), w, static_cast<bf16*>(dx), p, nt);
+  }
   SN_LAUNCH_CHECK();
   return 0;
 }
@@ -136,15 +153,19 @@ int sniper_depthwise3x3_wgrad(const void* x, long ldx, const void* dy, long lddy
   cudaStream_t st = (cudaStream_t)stream;
   const int LC = dwc::wgrad_lc(C), PL = kWgTY * (32 / LC);
   const int gy = sn::div_up(C >> 2, LC);
-  const long total = (long)NB * p.Ho * p.Wo;
-  long gx = (sn::kNumSMs * 4 + gy - 1) / gy;          // ~4 blocks of 256 threads per SM over the whole grid
-  const long gx_max = (total + PL - 1) / PL;
-  if (gx > gx_max) gx = gx_max;
-  if (gx < 1) gx = 1;
-  const dim3 grid((unsigned)gx, (unsigned)gy, 1), block(32, kWgTY, 1);
-#define DW_WG(T, S) dw_wgrad_kernel<T, S><<<grid, block, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(dy), dw, p)
-  if (dtype == 0) { if (stride == 1) DW_WG(float, 1); else DW_WG(float, 2); }
-  else            { if (stride == 1) DW_WG(bf16, 1);  else DW_WG(bf16, 2); }
+  const dim3 block(32, kWgTY, 1);
+#define DW_WG(T, S, PW)                                                                                              \
+  do {                                                                                                               \
+    const long strips = (long)NB * p.Ho * ((p.Wo + PW - 1) / PW);                                                    \
+    long gx = ((long)sn::kNumSMs * wgrad_blocks_per_sm(dw_wgrad_kernel<T, S, PW>) + gy - 1) / gy;   /* one wave */    \
+    const long gx_max = (strips + PL - 1) / PL;                                                                      \
+    if (gx > gx_max) gx = gx_max;                                                                                    \
+    if (gx < 1) gx = 1;                                                                                              \
+    dw_wgrad_kernel<T, S, PW><<<dim3((unsigned)gx, (unsigned)gy, 1), block, 0, st>>>(                                \
+        static_cast<const T*>(x), static_cast<const T*>(dy), dw, p);                                                \
+  } while (0)
+  if (dtype == 0) { if (stride == 1) DW_WG(float, 1, 4); else DW_WG(float, 2, 2); }
+  else            { if (stride == 1) DW_WG(bf16, 1, 4);  else DW_WG(bf16, 2, 2); }
 #undef DW_WG
   SN_LAUNCH_CHECK();
   return 0;

@@ -12,6 +12,7 @@
 #include <string.h>
 
 #define DW_HD __host__ __device__ __forceinline__
+// (scheduling of the loads: see `join_loads` below)
 
 namespace dwc {
 
@@ -61,16 +62,42 @@ DW_HD void store4(__nv_bfloat16* p, const float (&v)[4]) {
 DW_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 DW_HD void zero4(float (&v)[4]) { v[0] = v[1] = v[2] = v[3] = 0.f; }
 
-// Border handling in all three kernels: every load is issued UNCONDITIONALLY from a clamped (always valid) address
-// and the value is zeroed afterwards when the tap falls outside the map.  With the loads behind per-thread branches
-// (first version: `if (outside) continue;`) the compiler could not hoist them and each warp had one load in flight at
-// a time: 0.03-0.3 of the HBM roof (profiles/config4_r02.json).
+// Packed form of a 4-channel vector as it sits in memory (16 bytes fp32, 8 bytes bf16): loads are kept packed until they
+// are consumed, so that a thread can hold a whole 3 x 6 window in flight (18 loads = 36 registers in bf16).
+template <typename T> struct Raw;
+template <> struct Raw<float> { typedef float4 type; };
+template <> struct Raw<__nv_bfloat16> { typedef uint2 type; };
+DW_HD float4 loadraw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+DW_HD uint2 loadraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+DW_HD void unpack(const float4& t, float (&v)[4]) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+DW_HD void unpack(const uint2& u, float (&v)[4]) {
+  v[0] = bits2f(u.x << 16); v[1] = bits2f(u.x & 0xffff0000u);
+  v[2] = bits2f(u.y << 16); v[3] = bits2f(u.y & 0xffff0000u);
+}
+
+// join_loads: how "issue EVERY load of the window, then consume" is enforced.  Left alone, ptxas sinks loads towards
+// their first use to save registers, so a warp pays the memory latency once per small group of loads (5-8 dependent
+// stalls per thread in these kernels; a warp-level fence is optimised away, a CTA-level one costs a MEMBAR).  Here
+// every packed load is folded into one checksum word and the accumulators are INITIALISED with a value that depends on
+// it: `(m == magic) & (p.NB < 0) ? 1 : 0` is always 0 at run time (the launcher rejects NB <= 0) but not provably so at
+// compile time.  Every FMA chain therefore starts after all loads of the window have returned -- one latency per
+// thread instead of one per group -- at the price of ~20 integer instructions.  Results are unchanged (the host
+// emulation executes the same expression).
+DW_HD uint32_t fold(uint32_t m, const float4& r) { return m ^ f2bits(r.x) ^ f2bits(r.y) ^ f2bits(r.z) ^ f2bits(r.w); }
+DW_HD uint32_t fold(uint32_t m, const uint2& r) { return m ^ r.x ^ r.y; }
+DW_HD float join_loads(uint32_t m, const Params& p) { return ((m == 0x9e3779b9u) & (p.NB < 0)) ? 1.f : 0.f; }
+
+// Border handling and load scheduling in all kernels: every load is issued UNCONDITIONALLY from a clamped (always valid)
+// address, ALL loads of a thread's window are issued before the first use, and values of taps outside the map are zeroed
+// afterwards.  History (profiles/config4_r02.md): loads behind per-thread branches (`if (outside) continue;`) could not be
+// hoisted -> one load in flight per warp, 0.03-0.3 of the HBM roof; unconditional loads issued row by row -> the forward
+// kernel sat exactly at (resident warps x one row of loads) / latency = 1.5 TB/s.
 
 // ---- forward: y[n,ho,wo,c] = sum_{kh,kw} x[n, ho*S+kh-1, wo*S+kw-1, c] * w[kh*3+kw, c]
-// One thread = PW consecutive output pixels of one row x 4 channels: the (PW-1)*S+3 input columns of a row are loaded
-// once (all of them in flight together) and feed every output they belong to (stride 1, PW 4: 18 loads for 4 outputs
-// instead of 36).
-template <typename T, int S, int PW>
+// One thread = PW consecutive output pixels of one row x 4 channels: the 3 x ((PW-1)*S+3) input window is loaded once
+// and feeds every output it belongs to (stride 1, PW 4: 18 loads for 4 outputs instead of 36).  FLIP: taps taken in
+// reverse order (w[8 - t]) -- the stride-1 DATA GRADIENT is this kernel run on dy with the flipped filter.
+template <typename T, int S, int PW, bool FLIP>
 DW_HD void fwd(long tid, const T* __restrict__ x, const float* __restrict__ w, T* __restrict__ y, const Params& p) {
   const int CV = p.C >> 2;
   const int WB = (p.Wo + PW - 1) / PW;
@@ -82,30 +109,42 @@ DW_HD void fwd(long tid, const T* __restrict__ x, const float* __restrict__ w, T
   if (n >= p.NB) return;
   const int c = cv << 2;
   const int wo0 = wb * PW;
+  constexpr int NCOL = (PW - 1) * S + 3;
+  typename Raw<T>::type raw[3][NCOL];
+  float wk[9][4];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const T* row = x + ((n * p.H + clampi(ho * S + kh - 1, 0, p.H - 1)) * (long)p.W) * p.ldx + c;
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) raw[kh][j] = loadraw(row + (long)clampi(wo0 * S + j - 1, 0, p.W - 1) * p.ldx);
+  }
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp) load4(w + (long)(FLIP ? 8 - tp : tp) * p.C + c, wk[tp]);
+  uint32_t m = 0;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int j = 0; j < NCOL; ++j) m = fold(m, raw[kh][j]);
+  const float a0 = join_loads(m, p);
   float acc[PW][4];
 #pragma unroll
-  for (int q = 0; q < PW; ++q) zero4(acc[q]);
-  constexpr int NCOL = (PW - 1) * S + 3;
+  for (int q = 0; q < PW; ++q) { acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = a0; }
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
     const int hi = ho * S + kh - 1;
     const bool hv = hi >= 0 && hi < p.H;
-    const T* row = x + ((n * p.H + clampi(hi, 0, p.H - 1)) * (long)p.W) * p.ldx + c;
-    float v[NCOL][4], wk[3][4];
-#pragma unroll
-    for (int j = 0; j < NCOL; ++j) load4(row + (long)clampi(wo0 * S + j - 1, 0, p.W - 1) * p.ldx, v[j]);
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) load4(w + (long)(kh * 3 + kw) * p.C + c, wk[kw]);
 #pragma unroll
     for (int j = 0; j < NCOL; ++j) {
       const int wi = wo0 * S + j - 1;
-      if (!(hv && wi >= 0 && wi < p.W)) zero4(v[j]);
+      float v[4];
+      unpack(raw[kh][j], v);
+      if (!(hv && wi >= 0 && wi < p.W)) zero4(v);
 #pragma unroll
       for (int q = 0; q < PW; ++q) {
         const int kw = j - q * S;          // compile-time after unrolling
         if (kw >= 0 && kw < 3) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) acc[q][k] = fmaf(v[j][k], wk[kw][k], acc[q][k]);
+          for (int k = 0; k < 4; ++k) acc[q][k] = fmaf(v[k], wk[kh * 3 + kw][k], acc[q][k]);
         }
       }
     }
@@ -119,67 +158,66 @@ DW_HD long fwd_threads(const Params& p) {
   return (long)p.NB * p.Ho * ((p.Wo + PW - 1) / PW) * (p.C >> 2);
 }
 
-// ---- data gradient: dx[n,h,w,c] = sum_{kh,kw : (h+1-kh) % S == 0, (w+1-kw) % S == 0}
-//                                   dy[n, (h+1-kh)/S, (w+1-kw)/S, c] * w[kh*3+kw, c]
-// One thread = one input pixel x 4 channels (gather form: no atomics, deterministic).  Stride 1: 3 x 3 taps.  Stride 2:
-// only the taps of matching parity exist -- kh = 1 for even h, kh in {0, 2} for odd h (same for w): at most 2 x 2 loads.
+// ---- data gradient, stride 2: one thread = one dy pixel (a, b) x 4 channels -> the 2 x 2 block of dx at (2a + i, 2b + j).
+// With x index h = 2*ho + kh - 1 only taps of matching parity exist:
+//   dx[2a  , 2b  ] = dy[a][b] w11
+//   dx[2a  , 2b+1] = dy[a][b+1] w10 + dy[a][b] w12
+//   dx[2a+1, 2b  ] = dy[a+1][b] w01 + dy[a][b] w21
+//   dx[2a+1, 2b+1] = dy[a+1][b+1] w00 + dy[a+1][b] w02 + dy[a][b+1] w20 + dy[a][b] w22
+// 4 dy loads + 9 weight loads for 4 outputs (the gather-per-input-pixel form needed up to 4 + 4 loads per output).
 // Params describe the FORWARD convolution (H, W = dx map; Ho, Wo = dy map; ldx = dx pixel stride, ldy = dy pixel stride).
-template <typename T, int S>
-DW_HD void dgrad(long tid, const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx, const Params& p) {
+// Stride 1 uses fwd<T, 1, 4, true> on dy.
+template <typename T>
+DW_HD void dgrad_s2(long tid, const T* __restrict__ dy, const float* __restrict__ w, T* __restrict__ dx, const Params& p) {
   const int CV = p.C >> 2;
   long t = tid;
   const int cv = (int)(t % CV); t /= CV;
-  const int wi = (int)(t % p.W); t /= p.W;
-  const int hi = (int)(t % p.H);
-  const long n = t / p.H;
+  const int b = (int)(t % p.Wo); t /= p.Wo;
+  const int a = (int)(t % p.Ho);
+  const long n = t / p.Ho;
   if (n >= p.NB) return;
   const int c = cv << 2;
-  constexpr int NK = S == 1 ? 3 : 2;
-  int khs[NK], kws[NK], hos[NK], wos[NK];
-  bool hval[NK], wval[NK];
+  const bool a1 = a + 1 < p.Ho, b1 = b + 1 < p.Wo;
+  const T* r0 = dy + ((n * p.Ho + a) * (long)p.Wo) * p.ldy + c;
+  const T* r1 = dy + ((n * p.Ho + (a1 ? a + 1 : a)) * (long)p.Wo) * p.ldy + c;
+  const long o0 = (long)b * p.ldy, o1 = (long)(b1 ? b + 1 : b) * p.ldy;
+  typename Raw<T>::type q00 = loadraw(r0 + o0), q01 = loadraw(r0 + o1), q10 = loadraw(r1 + o0), q11 = loadraw(r1 + o1);
+  float wk[9][4];
 #pragma unroll
-  for (int i = 0; i < NK; ++i) {
-    khs[i] = S == 1 ? i : (i == 0 ? ((hi & 1) ? 0 : 1) : 2);
-    kws[i] = S == 1 ? i : (i == 0 ? ((wi & 1) ? 0 : 1) : 2);
-    const int a = hi + 1 - khs[i], b = wi + 1 - kws[i];          // = ho * S, wo * S when the tap exists
-    hos[i] = a / S;
-    wos[i] = b / S;
-    hval[i] = a >= 0 && hos[i] < p.Ho && (S == 1 || i == 0 || (hi & 1));
-    wval[i] = b >= 0 && wos[i] < p.Wo && (S == 1 || i == 0 || (wi & 1));
-    hos[i] = clampi(hos[i], 0, p.Ho - 1);
-    wos[i] = clampi(wos[i], 0, p.Wo - 1);
+  for (int tp = 0; tp < 9; ++tp) load4(w + (long)tp * p.C + c, wk[tp]);
+  float g00[4], g01[4], g10[4], g11[4];
+  unpack(q00, g00); unpack(q01, g01); unpack(q10, g10); unpack(q11, g11);
+  if (!b1) zero4(g01);
+  if (!a1) zero4(g10);
+  if (!(a1 && b1)) zero4(g11);
+  float o[2][2][4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    o[0][0][k] = g00[k] * wk[4][k];
+    o[0][1][k] = fmaf(g01[k], wk[3][k], g00[k] * wk[5][k]);
+    o[1][0][k] = fmaf(g10[k], wk[1][k], g00[k] * wk[7][k]);
+    o[1][1][k] = fmaf(g11[k], wk[0][k], fmaf(g10[k], wk[2][k], fmaf(g01[k], wk[6][k], g00[k] * wk[8][k])));
   }
-  float g[NK][NK][4], wk[NK][NK][4];
 #pragma unroll
-  for (int i = 0; i < NK; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < NK; ++j) {
-      load4(dy + ((n * p.Ho + hos[i]) * (long)p.Wo + wos[j]) * p.ldy + c, g[i][j]);
-      load4(w + (long)(khs[i] * 3 + kws[j]) * p.C + c, wk[i][j]);
+    for (int j = 0; j < 2; ++j) {
+      const int h = 2 * a + i, ww = 2 * b + j;
+      if (h < p.H && ww < p.W) store4(dx + ((n * p.H + h) * (long)p.W + ww) * p.ldx + c, o[i][j]);
     }
-  float acc[4];
-  zero4(acc);
-#pragma unroll
-  for (int i = 0; i < NK; ++i)
-#pragma unroll
-    for (int j = 0; j < NK; ++j) {
-      if (!(hval[i] && wval[j])) zero4(g[i][j]);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[k] = fmaf(g[i][j][k], wk[i][j][k], acc[k]);
-    }
-  store4(dx + ((n * p.H + hi) * (long)p.W + wi) * p.ldx + c, acc);
 }
-DW_HD long dgrad_threads(const Params& p) { return (long)p.NB * p.H * p.W * (p.C >> 2); }
+DW_HD long dgrad_s2_threads(const Params& p) { return (long)p.NB * p.Ho * p.Wo * (p.C >> 2); }
 
 // ---- weight gradient, per-thread partial: acc[t][k] = sum over this thread's output pixels of
 //      dy[q, c+k] * x[n, ho*S+kh-1, wo*S+kw-1, c+k].
-// Block = 32 x TY threads.  A warp row (32 lanes) covers LC channel vectors x 32/LC pixels, LC = 32 when C/4 is a
-// multiple of 32, else 16 (C is a multiple of 64): no idle lanes for C = 64 / 192 / 320 / 576 / 960.  Thread (tx, ty) of
-// block (bx, by): channel vector by*LC + tx%LC, pixel lane ty*(32/LC) + tx/LC of TY*(32/LC); output pixels
-// q = bx*PL + lane, + gridx*PL, ...  (neighbouring lanes take neighbouring pixels: their windows overlap in L1).
-// Returns the first channel of the thread, or -1 when it is beyond C.
+// Block = 32 x TY threads.  A warp row (32 lanes) covers LC channel vectors x 32/LC strips, LC = 32 when C/4 is a
+// multiple of 32, else 16 (C is a multiple of 64): no idle lanes for C = 64 / 192 / 320 / 576 / 960.  A thread walks over
+// STRIPS of PW consecutive output pixels of a row (3 x ((PW-1)*S+3) input window + PW dy vectors, all in flight
+// together); thread (tx, ty) of block (bx, by): channel vector by*LC + tx%LC, strip lane ty*(32/LC) + tx/LC of
+// PL = TY*(32/LC); strips bx*PL + lane, + gridx*PL, ...  The result does not depend on gridx (any grid gives the same
+// sums up to fp32 association).  Returns the first channel of the thread, or -1 when it is beyond C.
 DW_HD int wgrad_lc(int C) { return ((C >> 2) % 32 == 0) ? 32 : 16; }
-template <typename T, int S>
+template <typename T, int S, int PW>
 DW_HD int wgrad_partial(int bx, int by, int tx, int ty, int TY, int gridx, const T* __restrict__ x,
                         const T* __restrict__ dy, const Params& p, float (&acc)[9][4]) {
 #pragma unroll
@@ -188,29 +226,58 @@ DW_HD int wgrad_partial(int bx, int by, int tx, int ty, int TY, int gridx, const
   const int c = (by * LC + (tx % LC)) << 2;
   if (c >= p.C) return -1;
   const int PL = TY * PPW;
-  const long total = (long)p.NB * p.Ho * p.Wo;
-  for (long q = (long)bx * PL + ty * PPW + tx / LC; q < total; q += (long)gridx * PL) {
-    const int wo = (int)(q % p.Wo);
-    const long r = q / p.Wo;
+  const int WB = (p.Wo + PW - 1) / PW;
+  const long total = (long)p.NB * p.Ho * WB;
+  constexpr int NCOL = (PW - 1) * S + 3;
+  for (long sidx = (long)bx * PL + ty * PPW + tx / LC; sidx < total; sidx += (long)gridx * PL) {
+    const int wo0 = (int)(sidx % WB) * PW;
+    const long r = sidx / WB;
     const int ho = (int)(r % p.Ho);
     const long n = r / p.Ho;
-    float g[4], v[9][4];
-    load4(dy + q * p.ldy + c, g);
+    typename Raw<T>::type rg[PW], rx[3][NCOL];
+    const T* grow = dy + ((n * p.Ho + ho) * (long)p.Wo) * p.ldy + c;
+#pragma unroll
+    for (int q = 0; q < PW; ++q) rg[q] = loadraw(grow + (long)clampi(wo0 + q, 0, p.Wo - 1) * p.ldy);
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const T* row = x + ((n * p.H + clampi(ho * S + kh - 1, 0, p.H - 1)) * (long)p.W) * p.ldx + c;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) load4(row + (long)clampi(wo * S + kw - 1, 0, p.W - 1) * p.ldx, v[kh * 3 + kw]);
+      for (int j = 0; j < NCOL; ++j) rx[kh][j] = loadraw(row + (long)clampi(wo0 * S + j - 1, 0, p.W - 1) * p.ldx);
+    }
+      uint32_t m = 0;
+#pragma unroll
+    for (int q = 0; q < PW; ++q) m = fold(m, rg[q]);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) m = fold(m, rx[kh][j]);
+    const float a0 = join_loads(m, p);
+    float g[PW][4];
+#pragma unroll
+    for (int q = 0; q < PW; ++q) {
+      unpack(rg[q], g[q]);
+      if (wo0 + q >= p.Wo) zero4(g[q]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) g[q][k] += a0;          // every product of this strip waits for the whole window
     }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int hi = ho * S + kh - 1;
+      const bool hv = hi >= 0 && hi < p.H;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int wi = wo * S + kw - 1;
-        if (!(hi >= 0 && hi < p.H && wi >= 0 && wi < p.W)) zero4(v[kh * 3 + kw]);
+      for (int j = 0; j < NCOL; ++j) {
+        const int wi = wo0 * S + j - 1;
+        float v[4];
+        unpack(rx[kh][j], v);
+        if (!(hv && wi >= 0 && wi < p.W)) zero4(v);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) acc[kh * 3 + kw][k] = fmaf(g[k], v[kh * 3 + kw][k], acc[kh * 3 + kw][k]);
+        for (int q = 0; q < PW; ++q) {
+          const int kw = j - q * S;
+          if (kw >= 0 && kw < 3) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[kh * 3 + kw][k] = fmaf(g[q][k], v[k], acc[kh * 3 + kw][k]);
+          }
+        }
       }
     }
   }

@@ -19,33 +19,35 @@ static void fill(dwc::Params& p, int NB, int H, int W, int C, int stride, long l
 template <typename T>
 static void fwd_t(const void* x, long ldx, const float* w, void* y, long ldy, int NB, int H, int W, int C, int stride) {
   dwc::Params p; fill(p, NB, H, W, C, stride, ldx, ldy);
-  if (stride == 1) { const long nt = dwc::fwd_threads<1, 4>(p); for (long t = 0; t < nt; ++t) dwc::fwd<T, 1, 4>(t, (const T*)x, w, (T*)y, p); }
-  else             { const long nt = dwc::fwd_threads<2, 2>(p); for (long t = 0; t < nt; ++t) dwc::fwd<T, 2, 2>(t, (const T*)x, w, (T*)y, p); }
+  if (stride == 1) { const long nt = dwc::fwd_threads<1, 4>(p); for (long t = 0; t < nt; ++t) dwc::fwd<T, 1, 4, false>(t, (const T*)x, w, (T*)y, p); }
+  else             { const long nt = dwc::fwd_threads<2, 2>(p); for (long t = 0; t < nt; ++t) dwc::fwd<T, 2, 2, false>(t, (const T*)x, w, (T*)y, p); }
 }
 template <typename T>
 static void dgrad_t(const void* dy, long lddy, const float* w, void* dx, long lddx, int NB, int H, int W, int C, int stride) {
-  dwc::Params p; fill(p, NB, H, W, C, stride, lddx, lddy);
-  const long nt = dwc::dgrad_threads(p);
-  for (long t = 0; t < nt; ++t) { if (stride == 1) dwc::dgrad<T, 1>(t, (const T*)dy, w, (T*)dx, p); else dwc::dgrad<T, 2>(t, (const T*)dy, w, (T*)dx, p); }
+  dwc::Params p;
+  if (stride == 1) {           // as sniper_depthwise3x3_dgrad: the forward body on dy with the flipped filter
+    fill(p, NB, H, W, C, 1, lddy, lddx);
+    const long nt = dwc::fwd_threads<1, 4>(p);
+    for (long t = 0; t < nt; ++t) dwc::fwd<T, 1, 4, true>(t, (const T*)dy, w, (T*)dx, p);
+  } else {
+    fill(p, NB, H, W, C, stride, lddx, lddy);
+    const long nt = dwc::dgrad_s2_threads(p);
+    for (long t = 0; t < nt; ++t) dwc::dgrad_s2<T>(t, (const T*)dy, w, (T*)dx, p);
+  }
 }
 template <typename T>
-static void wgrad_t(const void* x, long ldx, const void* dy, long lddy, float* dw, int NB, int H, int W, int C, int stride) {
+static void wgrad_t(const void* x, long ldx, const void* dy, long lddy, float* dw, int NB, int H, int W, int C, int stride, int gx) {
   dwc::Params p; fill(p, NB, H, W, C, stride, ldx, lddy);
   const int TY = 8;
-  const int LC = dwc::wgrad_lc(C), PL = TY * (32 / LC);
+  const int LC = dwc::wgrad_lc(C);
   const int gy = ((C >> 2) + LC - 1) / LC;
-  const long total = (long)NB * p.Ho * p.Wo;
-  long gx = (148 * 4 + gy - 1) / gy;
-  const long gx_max = (total + PL - 1) / PL;
-  if (gx > gx_max) gx = gx_max;
-  if (gx < 1) gx = 1;
   for (int by = 0; by < gy; ++by)
-    for (int bx = 0; bx < (int)gx; ++bx)
+    for (int bx = 0; bx < gx; ++bx)
       for (int ty = 0; ty < TY; ++ty)
         for (int tx = 0; tx < 32; ++tx) {
           float acc[9][4];
-          const int c = stride == 1 ? dwc::wgrad_partial<T, 1>(bx, by, tx, ty, TY, (int)gx, (const T*)x, (const T*)dy, p, acc)
-                                    : dwc::wgrad_partial<T, 2>(bx, by, tx, ty, TY, (int)gx, (const T*)x, (const T*)dy, p, acc);
+          const int c = stride == 1 ? dwc::wgrad_partial<T, 1, 4>(bx, by, tx, ty, TY, gx, (const T*)x, (const T*)dy, p, acc)
+                                    : dwc::wgrad_partial<T, 2, 2>(bx, by, tx, ty, TY, gx, (const T*)x, (const T*)dy, p, acc);
           if (c < 0) continue;
           for (int t = 0; t < 9; ++t) for (int k = 0; k < 4; ++k) dw[(long)t * C + c + k] += acc[t][k];
         }
@@ -58,8 +60,8 @@ void emu_dw_fwd(const void* x, long ldx, const float* w, void* y, long ldy, int 
 void emu_dw_dgrad(const void* dy, long lddy, const float* w, void* dx, long lddx, int NB, int H, int W, int C, int stride, int dtype) {
   if (dtype == 0) dgrad_t<float>(dy, lddy, w, dx, lddx, NB, H, W, C, stride); else dgrad_t<bf16>(dy, lddy, w, dx, lddx, NB, H, W, C, stride);
 }
-void emu_dw_wgrad(const void* x, long ldx, const void* dy, long lddy, float* dw, int NB, int H, int W, int C, int stride, int dtype) {
-  if (dtype == 0) wgrad_t<float>(x, ldx, dy, lddy, dw, NB, H, W, C, stride); else wgrad_t<bf16>(x, ldx, dy, lddy, dw, NB, H, W, C, stride);
+void emu_dw_wgrad(const void* x, long ldx, const void* dy, long lddy, float* dw, int NB, int H, int W, int C, int stride, int dtype, int gx) {
+  if (dtype == 0) wgrad_t<float>(x, ldx, dy, lddy, dw, NB, H, W, C, stride, gx); else wgrad_t<bf16>(x, ldx, dy, lddy, dw, NB, H, W, C, stride, gx);
 }
 void emu_im2col3x3s2(const float* x, void* col, int NB, int H, int W, int Kp, int dtype) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;

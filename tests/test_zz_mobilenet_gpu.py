@@ -165,7 +165,7 @@ def test_inverted_residual_units_match_float64(bf16):
     dt = torch.bfloat16 if bf16 else torch.float32
     arg, aux = net.export_reference()
     P, _ = TM.params_to_torch(arg, aux, torch.float64, "cuda")
-    tol = dict(y=2e-2, dx=0.15, gw=0.15) if bf16 else dict(y=3e-3, dx=4e-2, gw=4e-2)
+    tol = dict(y=5e-3, dx=2e-2, gw=2e-2) if bf16 else dict(y=2e-4, dx=2e-3, gw=3e-3)      # measured: bf16 5e-4 / 2e-3 / 1.5e-3, TF32 1e-5 / 1e-4 / 2e-4
     torch.manual_seed(11)
     for idx in (0, 1, 2, 16):
         u = net.units[idx]
