@@ -9,6 +9,7 @@
 // depthwise_convolution_tf.cuh), elemwise_add, im2col of nn/convolution-inl.h for the 3-channel first layer.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "depthwise_core.cuh"
@@ -23,6 +24,35 @@ __global__ void __launch_bounds__(kTPB) dw_fwd_kernel(const T* __restrict__ x, c
                                                        T* __restrict__ y, dwc::Params p, long nthreads) {
   const long tid = (long)blockIdx.x * kTPB + threadIdx.x;
   if (tid < nthreads) dwc::fwd<T, S, PW, FLIP>(tid, x, w, y, p);
+}
+
+// shared-memory tiled forward (bf16, C % 64 == 0); grid = (tiles, C / 64)
+template <int S, bool FLIP>
+__global__ void __launch_bounds__(kTPB) dw_fwd_tiled_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                             bf16* __restrict__ y, dwc::Params p) {
+  __shared__ __align__(16) bf16 tile[dwc::Tile<S>::ELEMS];
+  const dwc::TileId t = dwc::tile_id<S>((long)blockIdx.x, (int)blockIdx.y, p);
+  dwc::tile_stage<S>((int)threadIdx.x, kTPB, t, x, tile, p);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  dwc::tile_compute<S, FLIP>((int)threadIdx.x, kTPB, t, tile, w, y, p);
+}
+
+template <int S, bool FLIP>
+int launch_fwd_tiled(const void* x, const float* w, void* y, const dwc::Params& p, cudaStream_t st) {
+  const long blocks = dwc::tile_blocks<S>(p);
+  SN_CHECK(blocks < (1L << 31), "depthwise3x3: too many tiles");
+  dw_fwd_tiled_kernel<S, FLIP><<<dim3((unsigned)blocks, (unsigned)(p.C / 64), 1), kTPB, 0, st>>>(
+      static_cast<const bf16*>(x), w, static_cast<bf16*>(y), p);
+  return 0;
+}
+
+// SNIPER_DW_TILED=0 selects the register-window kernels for bf16 too (A/B runs)
+bool use_tiled(int dtype, int C, long ld_in) {
+  static int flag = -1;
+  if (flag < 0) { const char* e = getenv("SNIPER_DW_TILED"); flag = (e && e[0] == '0') ? 0 : 1; }
+  return flag == 1 && dtype == 1 && C % 64 == 0 && ld_in % 8 == 0;       // 16-byte aligned pixel rows for cp.async
 }
 
 template <typename T>
@@ -108,6 +138,11 @@ int sniper_depthwise3x3_fwd(const void* x, long ldx, const float* w, void* y, lo
   dwc::Params p;
   if (fill_params(p, NB, H, W, C, stride, ldx, ldy, dtype, "depthwise3x3_fwd")) return -1;
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tiled(dtype, C, ldx)) {
+    if (stride == 1 ? launch_fwd_tiled<1, false>(x, w, y, p, st) : launch_fwd_tiled<2, false>(x, w, y, p, st)) return -1;
+    SN_LAUNCH_CHECK();
+    return 0;
+  }
 #define DW_FWD(T, S, PW)                                                                                       \
   do {                                                                                                         \
     const long nt = dwc::fwd_threads<S, PW>(p);                                                                \
@@ -128,6 +163,11 @@ int sniper_depthwise3x3_dgrad(const void* dy, long lddy, const float* w, void* d
   cudaStream_t st = (cudaStream_t)stream;
   if (stride == 1) {
     if (fill_params(p, NB, H, W, C, 1, lddy, lddx, dtype, "depthwise3x3_dgrad")) return -1;   // "input" = dy, "output" = dx
+    if (use_tiled(dtype, C, lddy)) {
+      if (launch_fwd_tiled<1, true>(dy, w, dx, p, st)) return -1;
+      SN_LAUNCH_CHECK();
+      return 0;
+    }
     const long nt = dwc::fwd_threads<1, 4>(p);
     if (dtype == 0)
       dw_fwd_kernel<float, 1, 4, true><<<blocks_for(nt), kTPB, 0, st>>>(static_cast<const float*>(dy), w, static_cast<float*>(dx), p, nt);

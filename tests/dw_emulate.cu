@@ -53,7 +53,27 @@ static void wgrad_t(const void* x, long ldx, const void* dy, long lddy, float* d
         }
 }
 
+template <int S, bool FLIP>
+static void tiled_t(const void* x, long ldx, const float* w, void* y, long ldy, int NB, int H, int W, int C) {
+  dwc::Params p; fill(p, NB, H, W, C, S, ldx, ldy);
+  const long blocks = dwc::tile_blocks<S>(p);
+  bf16* smem = (bf16*)malloc(sizeof(bf16) * dwc::Tile<S>::ELEMS);
+  for (int by = 0; by < C / 64; ++by)
+    for (long bx = 0; bx < blocks; ++bx) {
+      const dwc::TileId t = dwc::tile_id<S>(bx, by, p);
+      memset(smem, 0x7f, sizeof(bf16) * dwc::Tile<S>::ELEMS);        // poison: every element must be staged
+      for (int tid = 0; tid < 256; ++tid) dwc::tile_stage<S>(tid, 256, t, (const bf16*)x, smem, p);
+      for (int tid = 0; tid < 256; ++tid) dwc::tile_compute<S, FLIP>(tid, 256, t, smem, w, (bf16*)y, p);
+    }
+  free(smem);
+}
+
 extern "C" {
+// the shared-memory tiled bf16 kernels, block by block (stage phase, then compute phase); flip = stride-1 data gradient
+void emu_dw_tiled(const void* x, long ldx, const float* w, void* y, long ldy, int NB, int H, int W, int C, int stride, int flip) {
+  if (stride == 1) { if (flip) tiled_t<1, true>(x, ldx, w, y, ldy, NB, H, W, C); else tiled_t<1, false>(x, ldx, w, y, ldy, NB, H, W, C); }
+  else tiled_t<2, false>(x, ldx, w, y, ldy, NB, H, W, C);
+}
 void emu_dw_fwd(const void* x, long ldx, const float* w, void* y, long ldy, int NB, int H, int W, int C, int stride, int dtype) {
   if (dtype == 0) fwd_t<float>(x, ldx, w, y, ldy, NB, H, W, C, stride); else fwd_t<bf16>(x, ldx, w, y, ldy, NB, H, W, C, stride);
 }

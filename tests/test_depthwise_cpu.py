@@ -78,6 +78,31 @@ def test_depthwise_cores_match_float64(emu, dtype, NB, H, W, C, stride, ld_extra
         assert torch.allclose(dw.double() - 1.0, dw_ref, rtol=1e-4, atol=1e-5 * scale), gx
 
 
+@pytest.mark.parametrize("NB,H,W,C,stride,ld_extra", [(2, 8, 32, 64, 1, 0), (1, 19, 45, 128, 1, 0), (2, 9, 7, 64, 1, 64), (1, 16, 32, 64, 2, 0),
+                                                      (2, 11, 37, 192, 2, 0), (1, 1, 1, 64, 1, 0), (1, 40, 70, 64, 2, 0)])
+def test_tiled_bf16_kernels_match_float64(emu, NB, H, W, C, stride, ld_extra):
+    """The shared-memory tiled forward (and, flipped, the stride-1 data gradient): stage + compute phases per block."""
+    x, w, dy, Ho, Wo = _case(NB, H, W, C, stride, torch.bfloat16, ld_extra, seed=4)
+    ld = C + ld_extra
+    y_ref, dx_ref, _ = _ref(x, w, dy, C, stride)
+    y = torch.full((NB, Ho, Wo, ld), 7.0).to(torch.bfloat16)
+    emu.emu_dw_tiled(_p(x), ctypes.c_long(ld), _p(w), _p(y), ctypes.c_long(ld), NB, H, W, C, stride, 0)
+    assert torch.allclose(y[..., :C].double(), y_ref, rtol=1e-2, atol=3e-2)
+    if ld_extra:
+        assert (y[..., C:].float() == 7.0).all()
+    if stride == 1:
+        dx = torch.full((NB, H, W, ld), 7.0).to(torch.bfloat16)
+        emu.emu_dw_tiled(_p(dy), ctypes.c_long(ld), _p(w), _p(dx), ctypes.c_long(ld), NB, H, W, C, 1, 1)
+        assert torch.allclose(dx[..., :C].double(), dx_ref, rtol=1e-2, atol=3e-2)
+        # identical to the register-window kernels (same products, same order within a row)
+        dx2 = torch.zeros_like(dx)
+        emu.emu_dw_dgrad(_p(dy), ctypes.c_long(ld), _p(w), _p(dx2), ctypes.c_long(ld), NB, H, W, C, 1, 1)
+        assert torch.equal(dx[..., :C].float(), dx2[..., :C].float())
+    y2 = torch.zeros_like(y)
+    emu.emu_dw_fwd(_p(x), ctypes.c_long(ld), _p(w), _p(y2), ctypes.c_long(ld), NB, H, W, C, stride, 1)
+    assert torch.equal(y[..., :C].float(), y2[..., :C].float())
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_first_layer_im2col_and_add(emu, dtype):
     dt = 0 if dtype == torch.float32 else 1
