@@ -394,25 +394,18 @@ def hbm_kernel_table(B, lowp, peak_gbs):
     return rows
 
 
-def run_config4(args):
-    """BASELINE config 4: MobileNetV2 SNIPER, 512x512 chips, mixed precision (bf16 in place of the reference's fp16),
-    B = args.config4 chips per GPU (BASELINE: 40 = 320 / 8), synthetic chips + boxes, random-init weights.  One JSON line:
-    chips/s device-resident (`value`) and end to end from pinned host batches (`e2e`), the HBM kernel table, clocks."""
+def measure_config4(args, rank, local_rank, world, B, bf16=True, kernel_table=True):
+    """One measurement of BASELINE config 4 (MobileNetV2 SNIPER training step) on the already initialised process group:
+    device-resident chips/s (`value`) and end to end from pinned host batches (`e2e`), max over ranks.  Returns the block
+    on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
     from sniper_b200 import model_mnv2 as MM
-    from sniper_b200 import ops, synth_batch
+    from sniper_b200 import synth_batch
     from sniper_b200.trainer import Trainer
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    B = int(args.config4)
     cfg = MM.MCfg()
     cfg.batch_images = B
-    cfg.bf16 = not args.fp32
+    cfg.bf16 = bool(bf16)
     npool = 3
     pool = [synth_batch.make_batch(B, seed=300 + 17 * rank + i, device="cpu", pinned=True, A=cfg.num_anchors,
                                    stride=cfg.feat_stride) for i in range(npool)]
@@ -463,17 +456,16 @@ def run_config4(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
-    if rank != 0:
-        return
-    peaks, peak_src = load_peaks()
     launches = trainer.launches_per_step
-    if os.environ.get("SNIPER_BREAKDOWN"):
-        entry_point_breakdown(trainer, os.environ["SNIPER_BREAKDOWN"])
-    del trainer, net
+    if rank == 0 and os.environ.get("SNIPER_BREAKDOWN"):
+        entry_point_breakdown(trainer, os.environ["SNIPER_BREAKDOWN"].replace(".md", "") + "_config4.md")
+    del trainer, net, dev_pool
     torch.cuda.empty_cache()
-    table = hbm_kernel_table(B, bool(cfg.bf16), peaks["hbm_gbs"])
+    if rank != 0:
+        return None
+    peaks, peak_src = load_peaks()
     chips = B * world * args.steps
-    print(json.dumps({
+    block = {
         "metric": "512x512 chips/sec train (MobileNetV2 SNIPER)", "value": round(chips / (ms / 1e3), 2), "unit": "chips/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if cfg.bf16 else "tf32",
@@ -485,7 +477,32 @@ def run_config4(args):
         "e2e": {"value": round(chips / (ms_e2e / 1e3), 2), "unit": "chips/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 32, "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches * args.steps, "launches_per_step": launches, "losses": losses,
-        "hbm_kernels": table, "hbm_peak_gbs": peaks["hbm_gbs"], "peak_source": peak_src, "clocks": sampler.summary()}))
+        "clocks": sampler.summary()}
+    if kernel_table:
+        block["hbm_kernels"] = hbm_kernel_table(B, bool(cfg.bf16), peaks["hbm_gbs"])
+        block["hbm_peak_gbs"] = peaks["hbm_gbs"]
+        block["peak_source"] = peak_src
+    return block
+
+
+def run_config4(args):
+    """`bench.py --config4 B`: BASELINE config 4 alone -- MobileNetV2 SNIPER, 512x512 chips, mixed precision (bf16 in place
+    of the reference's fp16; --fp32 for TF32), B chips per GPU (BASELINE: 40 = 320 / 8), synthetic chips + boxes,
+    random-init weights.  One JSON line."""
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    block = measure_config4(args, rank, local_rank, world, int(args.config4), bf16=not args.fp32)
+    if rank == 0:
+        print(json.dumps(block), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def run_ours(args):
@@ -516,6 +533,13 @@ def run_ours(args):
         cfg3.batch_images = args.chips
         cfg3.bf16 = True
         m3 = measure(args, cfg3, rank, local_rank, world, pool, dev_pool)
+    # ---- configs[3]: the MobileNetV2 SNIPER step (40 chips/GPU, mixed precision) as one more extra block
+    m4 = None
+    if not args.bf16 and not args.skip_config4:
+        try:
+            m4 = measure_config4(args, rank, local_rank, world, 40, bf16=True, kernel_table=(world == 1))
+        except Exception as e:      # an extra block must not take the metric's line down with it
+            m4 = {"error": "%s: %s" % (type(e).__name__, e)} if rank == 0 else None
     result = None
     if rank == 0:
         chips = args.chips * world * args.steps
@@ -584,6 +608,8 @@ def run_ours(args):
                 "e2e": {"value": round(chips / (m3["ms_e2e"] / 1e3), 2), "unit": "chips/s",
                         "ms_per_step": round(m3["ms_e2e"] / args.steps, 3)},
                 "speedup_vs_tf32": round(v3 / value, 3), "roofline": roof3, "losses": m3["losses"]}
+        if m4 is not None:
+            result["config4"] = m4
         if cpu is not None:
             result["cpu_baseline"] = cpu
         print(json.dumps(result), flush=True)
@@ -643,6 +669,7 @@ def main():
                     help="instead of the ResNet-101 bench: BASELINE config 4, the MobileNetV2 SNIPER training step with this "
                          "many chips per GPU (BASELINE: 40), mixed precision unless --fp32")
     ap.add_argument("--fp32", action="store_true", help="--config4 in fp32 storage / TF32 math")
+    ap.add_argument("--skip-config4", action="store_true", help="do not append the MobileNetV2 block to the JSON line")
     args = ap.parse_args()
     args.iterator_leg = not args.skip_iterator
     if args.config4:
