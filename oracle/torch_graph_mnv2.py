@@ -74,8 +74,9 @@ def params_to_torch(arg, aux, dtype=torch.float64, device="cpu"):
     return P, A
 
 
-def _unit(P, x, prefix, k, stride, groups, act, eps, first=False):
-    """mobilenet_unit: Convolution(no_bias) -> BatchNorm(batch statistics) -> clip(0, 6) | identity."""
+def _unit(P, x, prefix, k, stride, groups, act, eps, first=False, aux=None):
+    """mobilenet_unit: Convolution(no_bias) -> BatchNorm -> clip(0, 6) | identity.  aux = None: batch statistics (training
+    graph); aux = the auxiliary states: moving statistics (is_train=False)."""
     w = P[prefix + "-conv2d_weight"]
     if groups > 1:
         c = F.conv2d(x, w, None, stride, 1, 1, groups)               # depthwise: exact FMA kernel in the product
@@ -84,15 +85,19 @@ def _unit(P, x, prefix, k, stride, groups, act, eps, first=False):
     else:
         c = TG.conv2d(x, w, None, stride, (k - 1) // 2)
     c = TG.qs(c)
-    y = F.batch_norm(c, None, None, P[prefix + "-batchnorm_gamma"], P[prefix + "-batchnorm_beta"], True, 0.0, eps)
+    if aux is not None:
+        y = F.batch_norm(c, aux[prefix + "-batchnorm_moving_mean"], aux[prefix + "-batchnorm_moving_var"],
+                         P[prefix + "-batchnorm_gamma"], P[prefix + "-batchnorm_beta"], False, 0.0, eps)
+    else:
+        y = F.batch_norm(c, None, None, P[prefix + "-batchnorm_gamma"], P[prefix + "-batchnorm_beta"], True, 0.0, eps)
     if act:
         y = torch.clamp(y, 0.0, 6.0)
     return TG.qs(y)
 
 
-def backbone(P, data, eps=1e-5, taps=None):
+def backbone(P, data, eps=1e-5, taps=None, aux=None):
     TG.LOWP[0] = True                      # the product's bf16 region starts at the first layer's im2col buffer
-    x = _unit(P, data, "first-3x3-conv", 3, 2, 1, True, eps, first=True)
+    x = _unit(P, data, "first-3x3-conv", 3, 2, 1, True, eps, first=True, aux=aux)
     if taps is not None:
         taps["first"] = x
     in_c = FIRST_C
@@ -101,14 +106,14 @@ def backbone(P, data, eps=1e-5, taps=None):
             p = "seq-%d-block%d" % (i, j)
             ci = in_c if j == 0 else c
             e = int(round(ci * t))
-            a1 = _unit(P, x, p + "-exp", 1, 1, 1, True, eps)
-            a2 = _unit(P, a1, p + "-depthwise", 3, s if j == 0 else 1, e, True, eps)
-            y = _unit(P, a2, p + "-linear", 1, 1, 1, False, eps)
+            a1 = _unit(P, x, p + "-exp", 1, 1, 1, True, eps, aux=aux)
+            a2 = _unit(P, a1, p + "-depthwise", 3, s if j == 0 else 1, e, True, eps, aux=aux)
+            y = _unit(P, a2, p + "-linear", 1, 1, 1, False, eps, aux=aux)
             x = TG.qs(y + x) if j > 0 else y
             if taps is not None:
                 taps[p] = x
         in_c = c
-    x = _unit(P, x, "last-1x1-conv", 1, 1, 1, True, eps)
+    x = _unit(P, x, "last-1x1-conv", 1, 1, 1, True, eps, aux=aux)
     TG.LOWP[0] = False                     # Cast(float32) (:226)
     return x
 
@@ -167,3 +172,29 @@ def forward_train(P, A, batch, proposals, batch_images, rpn_batch_size=256, num_
                cls_prob=lp.exp(), bbox_pred=bbox_pred, trans=trans, pooled=pooled,
                loss_sums=torch.stack([rpn_cls_sum, rpn_bbox_sum, cls_sum, bbox_sum]).detach(), rois=rois, label=label)
     return objective, out
+
+
+def forward_test(P, A, data, proposals, num_anchors=15, eps=1e-5):
+    """get_symbol_rcnn(cfg, is_train=False) (:306-362): moving-statistics BatchNorm, SoftmaxActivation(mode=channel) over
+    the reshaped RPN scores, MultiProposal (callback: (rpn_cls_prob [B,2A,H,W], rpn_bbox_pred) -> rois [N,5] numpy), the
+    deformable R-FCN head, softmax.  Returns dict(rois, cls_prob [N,K], bbox_pred [N,4], rpn_cls_prob, rpn_bbox_pred)."""
+    B = data.shape[0]
+    An = num_anchors
+    with torch.no_grad():
+        fm = backbone(P, data, eps, aux=A)
+        rpn = F.relu(TG.conv2d(fm, P["rpn_conv_3x3_weight"], P["rpn_conv_3x3_bias"], 1, 1))
+        score = TG.conv2d(rpn, P["rpn_cls_score_weight"], P["rpn_cls_score_bias"])
+        rpn_bbox_pred = TG.conv2d(rpn, P["rpn_bbox_pred_weight"], P["rpn_bbox_pred_bias"])
+        feat = F.relu(TG.conv2d(fm, P["conv_new_1_weight"], P["conv_new_1_bias"]))
+        H, W = score.shape[2], score.shape[3]
+        prob = F.softmax(score.reshape(B, 2, An * H, W), 1).reshape(B, 2 * An, H, W)
+        rois = np.ascontiguousarray(proposals(prob, rpn_bbox_pred), dtype=np.float32)
+        N = rois.shape[0]
+        offset_t = TG.DeformPSROI.apply(feat, None, rois, PSROI_KW)
+        trans = TG.linear(offset_t.reshape(N, -1), P["offset_weight"], P["offset_bias"]).reshape(N, 2, 7, 7)
+        pooled = TG.DeformPSROI.apply(feat, trans, rois, PSROI_KW)
+        fc1 = F.relu(TG.linear(pooled.reshape(N, -1), P["fc_new_1_weight"], P["fc_new_1_bias"]))
+        fc2 = F.relu(TG.linear(fc1, P["fc_new_2_weight"], P["fc_new_2_bias"]))
+        cls_prob = F.softmax(TG.linear(fc2, P["cls_score_weight"], P["cls_score_bias"]), 1)
+        bbox_pred = TG.linear(fc2, P["bbox_pred_weight"], P["bbox_pred_bias"])
+    return dict(rois=rois, cls_prob=cls_prob, bbox_pred=bbox_pred, rpn_cls_prob=prob, rpn_bbox_pred=rpn_bbox_pred, last_fm=fm)

@@ -368,6 +368,59 @@ class SniperMobileNetV2:
                    label=label, rois=rois, losses=self.loss_buf, rpn_head=head, last_fm=feat_in, first=a0,
                    bbox_target=bbox_target, bbox_weight=bbox_weight)
 
+    # ---------------------------------------------------------------- inference graph
+    def forward_inference(self, data, im_info, rpn_pre_nms_top_n=6000):
+        """mobilenetv2_e2e.get_symbol_rcnn(cfg, is_train=False) (:306-362): every BatchNorm on its moving statistics,
+        SoftmaxActivation over the RPN scores, MultiProposal (TEST.RPN_PRE_NMS_TOP_N 6000, 300 rois per image, stride 32),
+        deformable R-FCN head -> (rois [B*R,5], rpn scores [B*R], cls_prob [B*R,K], bbox_pred [B*R,4]).  No parameter is
+        touched.  BatchNorm + clip run as one `sniper_affine_act` pass per layer (the tcgen05 epilogue has ReLU, not clip)."""
+        cfg = self.cfg
+        A = cfg.num_anchors
+        B = data.shape[0]
+        dev = data.device
+        lowp = bool(cfg.bf16)
+        for b in self.all_bns():
+            ops.bn_frozen(b.st, cfg.bn_eps)            # scale / shift from the moving statistics (the next training
+        act = lambda bn, t: ops.affine_act(t, bn.st.scale, bn.st.shift, relu=bn.act)    # step recomputes them)
+        col = ops.im2col3x3s2(data, cfg.first_kp, dtype=self.act_dtype)
+        x = act(self.bn_first, self.first.fwd(col))
+        for u in self.units:
+            a1 = act(u.bn1, u.exp.fwd(x))
+            a2 = act(u.bn2, u.dw.fwd(a1))
+            y = act(u.bn3, u.lin.fwd(a2))
+            if u.shortcut:
+                ops.add_rows(y, x, out=y)
+            x = y
+        al = act(self.bn_last, self.last.fwd(x))
+        feat_in = ops.cast_rows(al, torch.float32) if lowp else al
+        Hf, Wf = data.shape[2] // cfg.feat_stride, data.shape[3] // cfg.feat_stride
+        rpn = self.rpn_conv.fwd(feat_in, relu=True)
+        head = self.rpn_head.fwd(rpn)
+        feat = self.conv_new_1.fwd(feat_in, relu=True)
+        prob = torch.empty(B, Hf, Wf, 2 * A, device=dev)
+        ignore = torch.full((B, A * Hf * Wf), -1.0, device=dev)
+        cnt = torch.ones(1, dtype=torch.int32, device=dev)
+        loss = torch.zeros(1, device=dev)
+        ops.rpn_softmax_loss(head[..., 4 * A:6 * A], ignore, A, 1.0, cnt, prob, None, loss)
+        rois, scores = ops.multi_proposal(prob, head, im_info, feat_stride=cfg.feat_stride, scales=cfg.scales,
+                                          ratios=cfg.ratios, rpn_pre_nms_top_n=rpn_pre_nms_top_n,
+                                          rpn_post_nms_top_n=cfg.rpn_post_nms_top_n, layout=ops.NHWC)
+        N = rois.shape[0]
+        ps = dict(spatial_scale=1.0 / cfg.feat_stride, output_dim=256, group_size=1, pooled_size=7, part_size=7,
+                  sample_per_part=4, layout=ops.NHWC)
+        offset_t, _, _ = ops.deform_psroi_fwd(feat, rois, None, no_trans=True, want_count=False, **ps)
+        off = ops.gemm_nt(offset_t.view(N, -1), self.fc_offset.w, bias=self.fc_offset.b)
+        trans = off[:, :98].contiguous().view(N, 2, 7, 7)
+        pooled, _, _ = ops.deform_psroi_fwd(feat, rois, trans, no_trans=False, trans_std=0.1, want_count=False, **ps)
+        fc1 = ops.gemm_nt(pooled.view(N, -1), self.fc_new_1.w, bias=self.fc_new_1.b, relu=True)
+        fc2 = ops.gemm_nt(fc1, self.fc_new_2.w, bias=self.fc_new_2.b, relu=True)
+        out = ops.gemm_nt(fc2, self.fc_out.w, bias=self.fc_out.b)
+        K = cfg.num_classes
+        cls_prob = torch.empty(N, K, device=dev)
+        lab = torch.full((N,), -1.0, device=dev)
+        ops.softmax_ce(out, lab, K, 1.0, cnt, cls_prob, None, loss)
+        return rois, scores, cls_prob, out[:, K:K + 4]
+
     # ---------------------------------------------------------------- optimizer
     def set_lr(self, lr=None):
         self.P.set_hyper(float(self.cfg.lr if lr is None else lr), float(self.cfg.wd))

@@ -124,6 +124,12 @@ def bn_finalize(bn, M, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=Tr
     bn.sums.zero_()
 
 
+def bn_frozen(bn, eps=2e-5, fix_gamma=False):
+    g = torch.ones_like(bn.gamma) if fix_gamma else bn.gamma
+    bn.scale.copy_(g / torch.sqrt(bn.moving_var + eps))
+    bn.shift.copy_(bn.beta - bn.moving_mean * bn.scale)
+
+
 def affine_act(x, scale, shift, relu=True, out=None):
     y = x * scale + shift
     r = int(relu)
@@ -270,6 +276,18 @@ def multi_proposal_target(cls_prob, bbox_pred, im_info, gt_boxes, valid_ranges, 
                                   post=rpn_post_nms_top_n)
     t = lambda a: torch.from_numpy(a).to(cls_prob.dtype)
     return t(res["rois"]), t(res["label"].reshape(-1)), t(res["bbox_target"]), t(res["bbox_weight"])
+
+
+def multi_proposal(cls_prob, bbox_pred, im_info, *, feat_stride=16, scales=(), ratios=(), rpn_pre_nms_top_n=12000,
+                   rpn_post_nms_top_n=300, threshold=0.7, suppress_anchor_types=False, fast_nms=False, roi_iou_thresh=0.3,
+                   layout=NCHW, return_keep=False):
+    A = len(scales) * len(ratios)
+    assert layout == NHWC and not suppress_anchor_types and not fast_nms
+    n = lambda t: np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32)
+    res = O.multi_proposal(n(_nchw(cls_prob[..., :2 * A])), n(_nchw(bbox_pred[..., :4 * A])), n(im_info),
+                           feat_stride=feat_stride, scales=scales, ratios=ratios, pre=rpn_pre_nms_top_n,
+                           post=rpn_post_nms_top_n)
+    return torch.from_numpy(res["rois"]).to(cls_prob.dtype), torch.from_numpy(res["scores"]).to(cls_prob.dtype)
 
 
 _last_cnt = {}

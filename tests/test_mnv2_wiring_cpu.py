@@ -122,3 +122,35 @@ def test_forward_backward_matches_the_autograd_oracle(monkeypatch, f64):
     for c in net.backbone_convs():
         w = net.P[c.name + "_weight"]
         assert not w[c.cout:].any() and not w[:, c.cin_real:].any()
+
+
+def test_inference_graph_matches_the_oracle(monkeypatch, f64):
+    """forward_inference (is_train=False: moving-statistics BatchNorm, MultiProposal, R-FCN head) on the fake ops against
+    oracle/torch_graph_mnv2.forward_test with the same C-oracle proposals; nothing is modified."""
+    import oracle_lib as O
+    import torch_graph as TG
+    import torch_graph_mnv2 as TM
+    B, chip = 2, 256
+    cfg, net = _net(monkeypatch, B)
+    batch = _batch(B, chip)
+    net.train_step(batch, lr=0.01)                          # non-trivial moving statistics and weights
+    g = torch.Generator().manual_seed(9)
+    for bn in net.all_bns():                                # (momentum 0.995 leaves them close to 0 / 1: spread them)
+        bn.st.moving_mean[:bn.C] += torch.empty(bn.C).normal_(0, 0.2, generator=g)
+        bn.st.moving_var[:bn.C] *= torch.empty(bn.C).uniform_(0.5, 2.0, generator=g)
+    w0 = net.P.w.clone()
+    rois, scores, cls_prob, bbox_pred = net.forward_inference(batch["data"], batch["im_info"])
+    assert torch.equal(net.P.w, w0)
+    arg, aux = net.export_reference()
+    P, Aux = TM.params_to_torch(arg, aux)
+    TG.MODE[0] = "exact"
+
+    def proposals(prob, bbox):
+        res = O.multi_proposal(prob.numpy(), bbox.numpy(), batch["im_info"].numpy(), feat_stride=32, scales=cfg.scales,
+                               ratios=cfg.ratios, pre=6000, post=300)
+        return res["rois"]
+    ref = TM.forward_test(P, Aux, batch["data"], proposals)
+    assert rois.shape == (B * 300, 5) and np.array_equal(rois.numpy().astype(np.float32), ref["rois"])
+    rel = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+    assert rel(cls_prob, ref["cls_prob"]) < 1e-5 and rel(bbox_pred, ref["bbox_pred"]) < 1e-4
+    assert (cls_prob.sum(1) - 1).abs().max() < 1e-9

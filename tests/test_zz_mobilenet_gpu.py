@@ -303,3 +303,22 @@ def test_trainer_runs_the_mobilenet_graph_under_cuda_graphs():
     for c in net.backbone_convs():
         w = net.P[c.name + "_weight"]
         assert not w[c.cout:].any() and not w[:, c.cin_real:].any()
+
+
+def test_inference_forward_path():
+    """mobilenetv2_e2e.get_symbol_rcnn(is_train=False) as SniperMobileNetV2.forward_inference: proposals from the device
+    MultiProposal op at stride 32, class probabilities that sum to one, boxes inside the chip, bit-identical on a second
+    call, parameters untouched (the comparison with the float64 test graph runs on the CPU: test_mnv2_wiring_cpu.py)."""
+    import torch
+    cfg, net, batch = _build(2, True)
+    net.train_step(batch, lr=0.001)
+    w0 = net.P.w.clone()
+    rois, scores, cls_prob, bbox_pred = net.forward_inference(batch["data"], batch["im_info"])
+    torch.cuda.synchronize()
+    assert rois.shape == (600, 5) and scores.shape == (600,) and cls_prob.shape == (600, 81) and bbox_pred.shape == (600, 4)
+    assert torch.isfinite(cls_prob).all() and torch.isfinite(bbox_pred).all()
+    assert (cls_prob.sum(1) - 1).abs().max().item() < 1e-4
+    assert (rois[:, 1:] >= 0).all() and (rois[:, 1:] <= 511).all()
+    r2 = net.forward_inference(batch["data"], batch["im_info"])
+    assert all(torch.equal(a, b) for a, b in zip((rois, scores, cls_prob, bbox_pred), r2))
+    assert torch.equal(w0, net.P.w)
