@@ -535,7 +535,10 @@ def run_ours(args):
         m3 = measure(args, cfg3, rank, local_rank, world, pool, dev_pool)
     # ---- configs[3]: the MobileNetV2 SNIPER step (40 chips/GPU, mixed precision) as one more extra block
     m4 = None
-    if not args.bf16 and not args.skip_config4:
+    # (only at N = 1 unless --config4-multi: its multi-GPU path shares the trainer's bucketed all-reduce but has not been
+    # run on more than one GPU, and an exception on one rank would leave the others waiting in a collective and take the
+    # metric's own scaling run down with it)
+    if not args.bf16 and not args.skip_config4 and (world == 1 or args.config4_multi):
         try:
             m4 = measure_config4(args, rank, local_rank, world, 40, bf16=True, kernel_table=(world == 1))
         except Exception as e:      # an extra block must not take the metric's line down with it
@@ -670,6 +673,7 @@ def main():
                          "many chips per GPU (BASELINE: 40), mixed precision unless --fp32")
     ap.add_argument("--fp32", action="store_true", help="--config4 in fp32 storage / TF32 math")
     ap.add_argument("--skip-config4", action="store_true", help="do not append the MobileNetV2 block to the JSON line")
+    ap.add_argument("--config4-multi", action="store_true", help="append the MobileNetV2 block at N > 1 too")
     args = ap.parse_args()
     args.iterator_leg = not args.skip_iterator
     if args.config4:
