@@ -71,3 +71,58 @@ def test_reference_arm_prints_once_under_torchrun():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "chips/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def _mnv2_worker(rank, world, port, q):
+    """Data-parallel MobileNetV2 step (config 4) on two gloo ranks: same weights, different chips, ONE all-reduce over the
+    model's single gradient bucket (sum, rescale_grad = 1), identical fused SGD update on every rank."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    torch.set_default_dtype(torch.float64)
+    torch.set_num_threads(2)
+    import fake_ops
+    from sniper_b200 import model_mnv2 as MM
+    from sniper_b200 import ops, synth_batch
+
+    class _MP:
+        def setattr(self, m, k, v):
+            setattr(m, k, v)
+    fake_ops.install(_MP(), ops)
+    cfg = MM.MCfg()
+    cfg.batch_images, cfg.bf16, cfg.wgrad_stream = 1, False, False
+
+    def grads_of(seed):
+        net = MM.SniperMobileNetV2(cfg, device="cpu", seed=3)
+        b = synth_batch.make_batch(1, seed=seed, device="cpu", chip=256, A=15, stride=32)
+        net.forward_backward({k: v.double() for k, v in b.items()})
+        return net
+    net = grads_of(50 + rank)                                   # this rank's chip
+    assert len(net.P.bucket_ranges) == 1 and tuple(net.P.bucket_ranges[0]) == (0, net.P.total)
+    a, b = net.P.bucket_ranges[0]
+    dist.all_reduce(net.P.g[a:b], op=dist.ReduceOp.SUM)
+    ok = True
+    if rank == 0:                                                # == the two chips' gradients summed in one process
+        want = grads_of(50).P.g + grads_of(51).P.g
+        ok = bool(torch.allclose(net.P.g, want, rtol=1e-12, atol=1e-14))
+    net.update(lr=0.01)
+    w = net.P.w.clone()
+    gathered = [torch.empty_like(w) for _ in range(world)]
+    dist.all_gather(gathered, w)
+    ok = ok and all(torch.equal(gathered[0], t) for t in gathered)       # replicas stay identical
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_mobilenet_data_parallel_step_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mnv2_worker, args=(r, 2, 29613, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
