@@ -478,10 +478,20 @@ def measure_config4(args, rank, local_rank, world, B, bf16=True, kernel_table=Tr
                 "d2h_bytes_per_step": 32, "ms_per_step": round(ms_e2e / args.steps, 3)},
         "gpu_launches": launches * args.steps, "launches_per_step": launches, "losses": losses,
         "clocks": sampler.summary()}
+    # MobileNetV2 forward 9.73 GFLOP / chip (backbone 3.26 incl. 0.216 depthwise, heads 6.47); a training step
+    # ~3x that.  At these rates the tensor cores idle: the configuration is HBM bound (BatchNorm, depthwise, PSROI).
+    block["algorithmic_gflop_per_chip"] = {"fwd": 9.73, "train_step": 29.2}
+    block["tensor_tflops_at_this_rate"] = round(block["value"] * 29.2e9 / 1e12, 1)
     if kernel_table:
-        block["hbm_kernels"] = hbm_kernel_table(B, bool(cfg.bf16), peaks["hbm_gbs"])
+        table = hbm_kernel_table(B, bool(cfg.bf16), peaks["hbm_gbs"])
+        block["hbm_kernels"] = table
         block["hbm_peak_gbs"] = peaks["hbm_gbs"]
         block["peak_source"] = peak_src
+        dom = max((r for r in table if r["kernel"].startswith("bn_act_bwd")), key=lambda r: r["us"])
+        block["roofline"] = {"bound": "hbm", "kernel": "sniper_bn_act_bwd (largest per-step share of this configuration; shape "
+                             + dom["kernel"].split(") ")[1] + ", timed alone)", "achieved": dom["gbs"], "peak": peaks["hbm_gbs"],
+                             "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": None,
+                             "algorithmic_bytes_per_launch": int(dom["algorithmic_mb"] * 1e6)}
     return block
 
 
