@@ -253,3 +253,24 @@ def test_recognise_graph_accepts_the_mobilenet_training_graph():
         test_sym = mob.mobilenetv2_e2e(test_nbatch=2).get_symbol_rcnn(cfg, is_train=False)
     with pytest.raises(NotImplementedError):
         symbols.recognise_graph(test_sym)
+
+
+@needs_ref
+def test_reference_custom_operator_file_registers_on_the_shim():
+    """lib/operator_py/box_annotator_ohem.py (the reference's Python custom operator, written against mx.operator) loads
+    unchanged: its `@mx.operator.register` lands in sniper_b200.operator_py's registry and its CustomOpProp answers the
+    shape / argument queries (the OHEM operator's arithmetic itself is outside the hot path)."""
+    import importlib.util
+    from sniper_b200 import mxnet_compat as MC
+    from sniper_b200 import operator_py
+    MC.install()
+    spec = importlib.util.spec_from_file_location("ref_box_annotator_ohem",
+                                                  os.path.join(REF, "lib/operator_py/box_annotator_ohem.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    assert "BoxAnnotatorOHEM" in operator_py._REGISTRY and issubclass(m.BoxAnnotatorOHEMProp, operator_py.CustomOpProp)
+    prop = operator_py._REGISTRY["BoxAnnotatorOHEM"](num_classes="81", num_reg_classes="1", roi_per_img="300")
+    assert prop.list_arguments() == ['cls_score', 'bbox_pred', 'labels', 'bbox_targets', 'bbox_weights']
+    ins, outs = prop.infer_shape([(16, 300, 81), (16, 300, 4), (16, 300), (16, 300, 4), (16, 300, 4)])[:2]
+    assert tuple(outs[0]) == (16, 300) and len(outs) == len(prop.list_outputs())
+    assert isinstance(prop.create_operator(None, ins, None), operator_py.CustomOp)
