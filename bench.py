@@ -492,6 +492,14 @@ def measure_config4(args, rank, local_rank, world, B, bf16=True, kernel_table=Tr
                              + dom["kernel"].split(") ")[1] + ", timed alone)", "achieved": dom["gbs"], "peak": peaks["hbm_gbs"],
                              "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": None,
                              "algorithmic_bytes_per_launch": int(dom["algorithmic_mb"] * 1e6)}
+    if kernel_table and not getattr(args, "skip_cpu", False):
+        # the same step on the host cores (oracle port, bounded sample; a reported baseline, not a target)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import cpu_train_step
+            block["cpu_baseline"] = cpu_train_step.run_mnv2(1, steps=3, warmup=1, budget_s=20)
+        except Exception as e:
+            block["cpu_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
     return block
 
 

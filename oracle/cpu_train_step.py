@@ -168,6 +168,71 @@ def run(sample_chips=1, threads=None, steps=2, warmup=1, budget_s=None):
             "cpu": cpu_model}
 
 
+def run_mnv2(sample_chips=1, threads=None, steps=2, warmup=1, budget_s=None):
+    """The same for BASELINE config 4: MobileNetV2 SNIPER training steps (symbols/faster/mobilenetv2_e2e.py:171-305 as
+    restated by oracle/torch_graph_mnv2.py) in float32 on the host cores -- oneDNN dense / depthwise layers, the
+    C oracle's MultiProposalTarget at stride 32 / 15 anchors (oracle/mpt.c), C-oracle PSROI (OpenMP), SGD-momentum on every convolution / FC tensor (gamma / beta are FIXED_PARAMS)."""
+    import torch
+    import torch.nn.functional as F
+    import oracle_lib as O
+    import torch_graph as TG
+    import torch_graph_mnv2 as TM
+    from sniper_b200 import synth_batch
+    threads = threads or pick_threads(torch, F)
+    torch.set_num_threads(threads)
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    B = sample_chips
+    arg, aux = TM.make_params(seed=5)
+    P, A = TM.params_to_torch(arg, aux, torch.float32, "cpu")
+    mom = {k: torch.zeros_like(v) for k, v in P.items() if v.requires_grad}
+    batches = [synth_batch.make_batch(B, seed=300 + i, device="cpu", A=15, stride=32) for i in range(2)]
+    kw = dict(feat_stride=32, scales=(1, 2, 4, 8, 12), ratios=(0.5, 1, 2))
+    TG.MODE[0] = "exact"
+
+    def proposals(b):
+        def fn(prob, bbox):
+            # (the C oracle, not the reference's CPU operator binary: that one is written for the 21-anchor 32x32 geometry
+            #  of the ResNet configuration -- multi_proposal_target-inl.h:118 -- and crashes on 15 anchors at 16x16)
+            return O.multi_proposal_target(prob.numpy(), bbox.numpy(), b["im_info"].numpy(), b["gt_boxes"].numpy(),
+                                           b["valid_ranges"].numpy(), **kw)
+        return fn
+
+    def one_step(i, lr=0.0005):
+        b = batches[i % len(batches)]
+        for v in P.values():
+            v.grad = None
+        obj, _ = TM.forward_train(P, A, b, proposals(b), batch_images=B)
+        obj.backward()
+        with torch.no_grad():
+            for k, m in mom.items():
+                g = P[k].grad
+                if g is None:
+                    continue
+                wd = 1e-4 if k.endswith("_weight") else 0.0
+                m.mul_(0.9).add_(P[k], alpha=-lr * wd).add_(g, alpha=-lr)
+                P[k].add_(m)
+        return float(obj.detach())
+
+    for i in range(warmup):
+        one_step(i)
+    times, t_all = [], time.time()
+    for i in range(steps):
+        t0 = time.time()
+        one_step(warmup + i)
+        times.append(time.time() - t0)
+        if budget_s is not None and len(times) >= 2 and time.time() - t_all > budget_s:
+            break
+    sec, n = sum(times), len(times)
+    return {"value": round(B * n / sec, 4), "unit": "chips/s", "cores": threads, "kind": "port", "steps_timed": n,
+            "warmup_steps": warmup, "sec_per_step": round(sec / n, 3),
+            "sample": "%d timed step(s) of %d chip(s) of the MobileNetV2 SNIPER step after %d warm-up step(s), %.1f s "
+                      "(PyTorch-CPU fp32 dense + depthwise layers, C-oracle MultiProposalTarget and PSROI (OpenMP), SGD; stand-in "
+                      "for the MXNet CPU stack)" % (n, B, warmup, sec)}
+
+
 if __name__ == "__main__":
     import json
-    print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 1)))
+    if len(sys.argv) > 1 and sys.argv[1] == "mnv2":
+        print(json.dumps(run_mnv2(int(sys.argv[2]) if len(sys.argv) > 2 else 1)))
+    else:
+        print(json.dumps(run(int(sys.argv[1]) if len(sys.argv) > 1 else 1)))
