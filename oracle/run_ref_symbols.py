@@ -100,6 +100,17 @@ def build():
         inst = res.resnet_mx_101_e2e(n_proposals=400, momentum=0.995, test_nbatch=2)
         sym = inst.get_symbol_rcnn(cfg, is_train=False)
     out["resnet101_test_autofocus"] = describe(sym, {"data": (2, 3, 512, 512), "im_info": (2, 3), "im_ids": (2,), "chip_ids": (2,)})
+    # the RPN-only graphs (get_symbol_rpn :157-225)
+    cfg = load_config("sniper_res101_e2e.yml")
+    cfg.TRAIN.fp16 = False
+    cfg.TRAIN.BATCH_IMAGES = 20
+    with MC.NameManager():
+        sym = res.resnet_mx_101_e2e(n_proposals=400, momentum=0.995).get_symbol_rpn(cfg)
+    d = train_shapes(cfg, 20, 16)
+    out["resnet101_rpn_train"] = describe(sym, {k: d[k] for k in ("data", "label", "bbox_target", "bbox_weight")})
+    with MC.NameManager():
+        sym = res.resnet_mx_101_e2e(n_proposals=400, momentum=0.995, test_nbatch=2).get_symbol_rpn(cfg, is_train=False)
+    out["resnet101_rpn_test"] = describe(sym, {"data": (2, 3, 512, 512), "im_info": (2, 3), "im_ids": (2,)})
     mob = MC.load_symbol_file(os.path.join(REF, "symbols/faster/mobilenetv2_e2e.py"))
     cfg = load_config("sniper_mobilenetv2_e2e.yml")
     cfg.TRAIN.BATCH_IMAGES = 40

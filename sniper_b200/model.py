@@ -844,6 +844,42 @@ class SniperResNet101:
             return rois, scores, cls_prob, out[:, K:K + 4], fmap
         return rois, scores, cls_prob, out[:, K:K + 4]
 
+    def forward_rpn(self, data, im_info, suppress_anchor_types=False):
+        """get_symbol_rpn(cfg, is_train=False) (resnet_mx_101_e2e.py:157-225): backbone with moving-statistics BatchNorm ->
+        RPN head -> MultiProposal -> (rois [B*R,5], rpn scores [B*R]); the proposal-extraction half of
+        `forward_inference` (same launches up to the proposal operator)."""
+        cfg = self.cfg
+        A = cfg.num_anchors
+        B = data.shape[0]
+        for b in self.train_bns():
+            ops.bn_frozen(b.st, cfg.bn_eps)
+        x = self.stem(data)
+        x = ops.maxpool3x3s2(x)
+        n1, n2, n3, n4 = cfg.units
+        Hf, Wf = data.shape[2] // cfg.feat_stride, data.shape[3] // cfg.feat_stride
+        cat = torch.empty(B, Hf, Wf, 3072, device=data.device)
+        last3 = n1 + n2 + n3 - 1
+        lowp = bool(cfg.bf16)
+        for i, u in enumerate(self.units):
+            out = None
+            if not lowp:
+                out = cat[..., :1024] if i == last3 else (cat[..., 1024:] if i == len(self.units) - 1 else None)
+            x = u.fwd_infer(x, cfg, out=out)
+            if lowp and i == last3:
+                ops.cast_rows(x, out=cat[..., :1024])
+        if lowp:
+            ops.cast_rows(x, out=cat[..., 1024:])
+        rpn = self.rpn_conv.fwd(cat, relu=True)
+        head = self.rpn_head.fwd(rpn)
+        prob = torch.empty(B, Hf, Wf, 2 * A, device=data.device)
+        ignore = torch.full((B, A * Hf * Wf), -1.0, device=data.device)
+        cnt = torch.ones(1, dtype=torch.int32, device=data.device)
+        loss = torch.zeros(1, device=data.device)
+        ops.rpn_softmax_loss(head[..., 4 * A:6 * A], ignore, A, 1.0, cnt, prob, None, loss)
+        return ops.multi_proposal(prob, head, im_info, feat_stride=cfg.feat_stride, scales=cfg.scales, ratios=cfg.ratios,
+                                  rpn_post_nms_top_n=cfg.rpn_post_nms_top_n, suppress_anchor_types=suppress_anchor_types,
+                                  layout=ops.NHWC)
+
     # ---------------------------------------------------------------- reference checkpoints (utils.py:45-100)
     def _named_convs(self):
         cs = [c for u in self.units for c in u.convs()]

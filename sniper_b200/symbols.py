@@ -29,9 +29,12 @@ FILTER_LIST = (64, 256, 512, 1024, 2048)
 class NetSymbol(object):
     """Names and shapes of the SNIPER ResNet-101 R-FCN graph as `mx.sym.Symbol` exposes them."""
 
-    def __init__(self, cfg, is_train=True, num_classes=81, num_anchors=21, rois_per_chip=300, max_gt=100):
+    rpn_only = False        # get_symbol_rpn (resnet_mx_101_e2e.py:157-225): backbone + RPN head (+ MultiProposal at test time)
+
+    def __init__(self, cfg, is_train=True, num_classes=81, num_anchors=21, rois_per_chip=300, max_gt=100, rpn_only=False):
         self.cfg, self.is_train = cfg, is_train
         self.num_classes, self.num_anchors, self.rois, self.max_gt = num_classes, num_anchors, rois_per_chip, max_gt
+        self.rpn_only = rpn_only
         self._args, self._aux = [], []
         self._build()
 
@@ -72,6 +75,8 @@ class NetSymbol(object):
         self._conv("rpn_conv_3x3", 512, 3072, 3, True)
         self._conv("rpn_cls_score", 2 * A, 512, 1, True)
         self._conv("rpn_bbox_pred", 4 * A, 512, 1, True)
+        if self.rpn_only:
+            return
         self._conv("conv_new_1", 256, 3072, 1, True)
         self._fc("offset", 2 * 7 * 7, 256 * 7 * 7)
         self._fc("fc_new_1", 1024, 256 * 7 * 7)
@@ -81,6 +86,8 @@ class NetSymbol(object):
 
     # ---- mx.sym.Symbol surface
     def data_names(self):
+        if self.rpn_only:
+            return ["data", "label", "bbox_target", "bbox_weight"] if self.is_train else ["data", "im_info", "im_ids"]
         if self.is_train:
             return ["data", "im_info", "gt_boxes", "valid_ranges", "label", "bbox_target", "bbox_weight"]
         return ["data", "im_info", "im_ids", "chip_ids"]
@@ -92,6 +99,8 @@ class NetSymbol(object):
         return [n for n, _ in self._aux]
 
     def list_outputs(self):
+        if self.rpn_only:      # Group([rpn_cls_prob, rpn_bbox_loss]) / Group([rois, rpn_scores, im_ids]) (:214, :222)
+            return ["rpn_cls_prob_output", "rpn_bbox_loss_output"] if self.is_train else ["rois_output", "rois_score", "im_ids"]
         if self.is_train:      # mx.sym.Group order of get_symbol_rcnn (resnet_mx_101_e2e.py:336-341); metric.py reads it by position
             return ["rpn_cls_prob_output", "rpn_bbox_loss_output", "cls_prob_reshape_output", "bbox_loss_reshape_output",
                     "blockgrad0_output"]
@@ -107,6 +116,9 @@ class NetSymbol(object):
                 "gt_boxes": (B, self.max_gt, 5), "valid_ranges": (B, 2),
                 "label": (B, A * H * W), "bbox_target": (B, 4 * A, H, W), "bbox_weight": (B, 4 * A, H, W)}
         arg = [tuple(data_shapes.get(n, dflt[n])) for n in self.data_names()] + [s for _, s in self._args]
+        if self.rpn_only:
+            out = [(B, 2, A * H, W), (B, 4 * A, H, W)] if self.is_train else [(B * R, 5), (B * R,), (B,)]
+            return arg, out, [s for _, s in self._aux]
         if self.is_train:
             # the last head is BlockGrad(label_reshape): Reshape(label, (-1,)) (resnet_mx_101_e2e.py:281,334) -> (B*R,)
             out = [(B, 2, A * H, W), (B, 4 * A, H, W), (B, R, K), (B, R, 4), (B * R,)]
@@ -203,16 +215,22 @@ def recognise_graph(sym):
     from . import mxnet_compat as MC
     nodes = {n.name: n for n in MC._dfs(sym._heads)}
     is_train = "multi_proposal_target" in nodes
-    if "rpn_cls_score" not in nodes or "cls_score" not in nodes:
-        raise NotImplementedError("not a SNIPER Faster-R-CNN / R-FCN graph (no rpn_cls_score / cls_score nodes)")
+    if "rpn_cls_score" not in nodes:
+        raise NotImplementedError("not a SNIPER Faster-R-CNN / R-FCN graph (no rpn_cls_score node)")
+    rpn_only = "cls_score" not in nodes                        # get_symbol_rpn: backbone + RPN head (+ MultiProposal)
+    if rpn_only:
+        is_train = "rois" not in nodes
     A = int(nodes["rpn_cls_score"].attrs["num_filter"]) // 2
-    K = int(nodes["cls_score"].attrs["num_hidden"])
-    B = int(nodes["multi_proposal_target"].attrs.get("batch_size", 16)) if is_train else \
+    K = 81 if rpn_only else int(nodes["cls_score"].attrs["num_hidden"])
+    B = int(nodes["multi_proposal_target"].attrs.get("batch_size", 16)) if "multi_proposal_target" in nodes else \
         int(nodes["rois"].attrs.get("batch_size", 1)) if "rois" in nodes else 1
     fp16 = any(n.op == "Cast" and n.attrs.get("dtype") == "float16" for n in nodes.values())
     mnv2 = "first-3x3-conv-conv2d" in nodes
     stride = 32 if mnv2 else 16
-    ours = (MobileNetSymbol if mnv2 else NetSymbol)(None, is_train=is_train, num_classes=K, num_anchors=A)
+    if rpn_only and mnv2:
+        raise NotImplementedError("MobileNetV2: no RPN-only graph in the reference")
+    ours = NetSymbol(None, is_train=is_train, num_anchors=A, rpn_only=True) if rpn_only else \
+        (MobileNetSymbol if mnv2 else NetSymbol)(None, is_train=is_train, num_classes=K, num_anchors=A)
     data = set(ours.data_names()) | {"scale_label", "crowd_boxes"}
     H = 512
     shapes = {"data": (B, 3, H, H)}
@@ -222,6 +240,8 @@ def recognise_graph(sym):
                        "gt_boxes": (B, 100, 5), "valid_ranges": (B, 2), "im_info": (B, 3), "crowd_boxes": (B, 10, 5)})
     else:
         shapes.update({"im_info": (B, 3), "im_ids": (B,), "chip_ids": (B,)})
+    if rpn_only:
+        shapes = {k: v for k, v in shapes.items() if k in ours.data_names()}
     args, _, auxs = sym.infer_shape_partial(**shapes)
     theirs = {n: tuple(s) for n, s in zip(sym.list_arguments(), args) if n not in data}
     theirs_aux = {n: tuple(s) for n, s in zip(sym.list_auxiliary_states(), auxs)}
@@ -239,6 +259,11 @@ def recognise_graph(sym):
     info = dict(batch_images=B, num_anchors=A, num_classes=K, bf16=fp16, is_train=is_train, autofocus=bool(af))
     if mnv2:
         info["network"] = "mobilenetv2"
+    if rpn_only:
+        if is_train:
+            raise NotImplementedError("RPN-only TRAINING (get_symbol_rpn, is_train=True) has no executor here: the end-to-end "
+                                      "graph trains the RPN; the RPN-only test graph binds to SniperResNet101.forward_rpn")
+        info["rpn_only"] = True
     return info
 
 
@@ -248,6 +273,7 @@ def bind_graph(sym, device="cuda:0", **overrides):
     info = recognise_graph(sym)
     cls = MobileNetSymbol if info.get("network") == "mobilenetv2" else NetSymbol
     ours = cls(None, is_train=info["is_train"], num_classes=info["num_classes"], num_anchors=info["num_anchors"])
+    # (an RPN-only test graph binds to the full network object: its executor is `forward_rpn`)
     kw = dict(batch_images=info["batch_images"], bf16=info["bf16"], num_classes=info["num_classes"],
               num_anchors=info["num_anchors"])
     kw.update(overrides)
@@ -340,6 +366,24 @@ class resnet_mx_101_e2e(Symbol):
         return self.sym
 
     get_symbol = get_symbol_rcnn
+
+    def get_symbol_rpn(self, cfg, is_train=True):
+        """:157-225 -- the RPN-only graph (proposal extraction); its executor is `SniperResNet101.forward_rpn`."""
+        net = getattr(cfg, "network", None)
+        num_anchors = getattr(net, "NUM_ANCHORS", 21) if net is not None else 21
+        self.sym = NetSymbol(cfg, is_train=is_train, num_anchors=num_anchors, rpn_only=True)
+        return self.sym
+
+    def init_weight_rpn(self, cfg, arg_params, aux_params, seed=None):
+        """:487-500 -- zero offset layers, N(0, 0.01) RPN head."""
+        rng = np.random.RandomState(seed) if seed is not None else np.random
+        sh = self.arg_shape_dict
+        for u in (1, 2, 3):
+            for sfx in ('_weight', '_bias'):
+                arg_params['stage4_unit%d_offset%s' % (u, sfx)] = np.zeros(sh['stage4_unit%d_offset%s' % (u, sfx)], np.float32)
+        for n in ('rpn_conv_3x3', 'rpn_cls_score', 'rpn_bbox_pred'):
+            arg_params[n + '_weight'] = (rng.standard_normal(sh[n + '_weight']) * 0.01).astype(np.float32)
+            arg_params[n + '_bias'] = np.zeros(sh[n + '_bias'], np.float32)
 
     def init_weight_rcnn(self, cfg, arg_params, aux_params, seed=None):
         """:450-485 -- zeros for every offset layer, N(0, 0.01) weights + zero biases for the RPN and the R-FCN head.

@@ -208,6 +208,14 @@ def test_recognise_graph_accepts_the_resnet_graphs_and_refuses_others():
         assert set(small) == {"bbox_pred_weight", "bbox_pred_bias"}
         back = MC.load(prefix + "-symbol.json")
         assert back.list_arguments() == inst.symbol.list_arguments() and back.tojson() == inst.symbol.tojson()
+    # the RPN-only graphs: the test graph is recognised (executor: forward_rpn), the training graph is refused
+    with MC.NameManager():
+        rpn_test = res.resnet_mx_101_e2e(test_nbatch=2).get_symbol_rpn(cfg, is_train=False)
+    assert symbols.recognise_graph(rpn_test)["rpn_only"] is True and symbols.recognise_graph(rpn_test)["batch_images"] == 2
+    with MC.NameManager():
+        rpn_train = res.resnet_mx_101_e2e().get_symbol_rpn(cfg)
+    with pytest.raises(NotImplementedError):
+        symbols.recognise_graph(rpn_train)
     # a ResNet-50 graph is not ours
     r50 = MC.load_symbol_file(os.path.join(REF, "symbols/faster/resnet_mx_50_e2e.py"))
     with MC.NameManager():
@@ -274,3 +282,24 @@ def test_reference_custom_operator_file_registers_on_the_shim():
     ins, outs = prop.infer_shape([(16, 300, 81), (16, 300, 4), (16, 300), (16, 300, 4), (16, 300, 4)])[:2]
     assert tuple(outs[0]) == (16, 300) and len(outs) == len(prop.list_outputs())
     assert isinstance(prop.create_operator(None, ins, None), operator_py.CustomOp)
+
+
+@pytest.mark.parametrize("is_train", [True, False])
+def test_rpn_symbol_equals_the_graph_the_reference_builds(is_train):
+    from types import SimpleNamespace
+    from sniper_b200 import symbols
+    g = _gold()["resnet101_rpn_train" if is_train else "resnet101_rpn_test"]
+    cfg = SimpleNamespace(network=SimpleNamespace(NUM_ANCHORS=21))
+    inst = symbols.resnet_mx_101_e2e()
+    sym = inst.get_symbol_rpn(cfg, is_train=is_train)
+    data = {n: tuple(s) for n, s in g["arguments"] if n in sym.data_names()}
+    assert set(data) == set(sym.data_names())
+    arg, out, aux = sym.infer_shape(**data)
+    assert dict(zip(sym.list_arguments(), map(tuple, arg))) == {n: tuple(s) for n, s in g["arguments"]}
+    assert list(zip(sym.list_auxiliary_states(), map(tuple, aux))) == [(n, tuple(s)) for n, s in g["auxiliary"]]
+    assert list(zip(sym.list_outputs(), map(tuple, out))) == [(n, tuple(s)) for n, s in g["outputs"]]
+    inst.infer_shape(data)
+    a = {}
+    inst.init_weight_rpn(cfg, a, {}, seed=0)
+    assert set(a) == {n + s for n in ("rpn_conv_3x3", "rpn_cls_score", "rpn_bbox_pred", "stage4_unit1_offset",
+                                      "stage4_unit2_offset", "stage4_unit3_offset") for s in ("_weight", "_bias")}
