@@ -954,7 +954,7 @@ class SniperResNet101:
         for c in self._named_convs():
             if grads and not c.trainable:
                 continue
-            w = self.P.grad(c.name + "_weight") if grads else c.master.float()
+            w = self.P.grad(c.name + "_weight") if grads else (c.master.float() if c.master.dtype == torch.bfloat16 else c.master)
             b = (self.P.grad(c.name + "_bias") if grads else c.b) if c.bias else None
             ck.conv_to_reference(c.name, c.cout, c.cin, c.k, n(w), n(b) if c.bias else None, parts.get(c.name), arg)
         for bn in self._named_bns():

@@ -59,15 +59,44 @@ def gemm_nt(a, b, *, out=None, scale=None, bias=None, residual=None, relu=False,
     return _emit(y, out)
 
 
+def conv_taps(kh, kw, dil, pad):
+    dh = [i * dil - pad for i in range(kh) for _ in range(kw)]
+    dw = [j * dil - pad for _ in range(kh) for j in range(kw)]
+    return dh, dw
+
+
 def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, bias=None, residual=None, relu=False,
                 accumulate=False, taps=None, out_hw=None, out_map=None, stats=None, out_dtype=None):
-    assert taps is None and out_hw is None and out_map is None, "strided data-gradient maps are not used by this model"
-    Cout, Cin = w.shape[0], x.shape[3]
-    w4 = w.to(x.dtype).view(Cout, kh, kw, Cin).permute(0, 3, 1, 2)
-    y = _nhwc(F.conv2d(_nchw(x), w4, None, stride, pad, dil))
-    y = _epi(y, scale, bias, residual, relu)
+    """The documented contract of sniper_conv2d_nhwc: y[n,oh,ow,co] = sum_t sum_ci x[n, oh*stride + dh[t], ow*stride +
+    dw[t], ci] * w[co, t*Cin + ci] (zero outside the map), epilogue *scale +bias +residual relu, written to the positions
+    (oh*os + ooh, ow*os + oow) of an oH x oW map when out_map is given (the strided data gradients)."""
+    NB, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    dh, dw = taps if taps is not None else conv_taps(kh, kw, dil, pad)
+    if out_hw is None:
+        Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
+    else:
+        Ho, Wo = out_hw
+    wd = w.to(x.dtype)
+    y = x.new_zeros(NB, Ho, Wo, Cout)
+    ah, aw = torch.arange(Ho) * stride, torch.arange(Wo) * stride
+    for t in range(len(dh)):
+        hi, wi = ah + dh[t], aw + dw[t]
+        m = ((hi >= 0) & (hi < H))[:, None] & ((wi >= 0) & (wi < W))[None, :]
+        xs = x[:, hi.clamp(0, H - 1)][:, :, wi.clamp(0, W - 1)] * m[None, :, :, None].to(x.dtype)
+        y = y + xs @ wd[:, t * Cin:(t + 1) * Cin].t()
+    if out_map is None:
+        y = _epi(y, scale, bias, residual, relu)
+        _stats(y, stats)
+        return _emit(y, out)
+    oH, oW, os_, ooh, oow = out_map
+    res = None if residual is None else residual[:, ooh::os_, oow::os_][:, :Ho, :Wo]
+    y = _epi(y, scale, bias, res, relu)
     _stats(y, stats)
-    return _emit(y, out)
+    assert out is not None and out.shape[1] == oH and out.shape[2] == oW
+    out[:, ooh::os_, oow::os_][:, :Ho, :Wo] = y
+    return out
 
 
 def conv2d_wgrad_nhwc(dy, x, *, kh, kw, stride=1, dil=1, pad=0, dw_out=None, splits=8, taps=None):
@@ -94,9 +123,11 @@ def bn_param_grad_jobs(states, device):
 def bn_param_grad_batched(table):
     for st in table:
         C = st.C
-        st.dbeta += st.sums[:C].to(st.dbeta.dtype)
-        st.dgamma += st.sums[C:].to(st.dgamma.dtype)
+        if st.dbeta is not None:
+            st.dbeta += st.sums[:C].to(st.dbeta.dtype)
+            st.dgamma += st.sums[C:].to(st.dgamma.dtype)
         st.sums.zero_()
+        st.sums_f.zero_()               # the forward statistics of the fused-apply path are cleared here
 
 
 def _finish_stats(bn, mean, var, M, eps, momentum, fix_gamma, update_moving):
@@ -128,6 +159,87 @@ def bn_frozen(bn, eps=2e-5, fix_gamma=False):
     g = torch.ones_like(bn.gamma) if fix_gamma else bn.gamma
     bn.scale.copy_(g / torch.sqrt(bn.moving_var + eps))
     bn.shift.copy_(bn.beta - bn.moving_mean * bn.scale)
+
+
+def bn_apply_train(x, bn, eps=2e-5, momentum=0.9, relu=True, fix_gamma=False, update_moving=True, out=None):
+    """finalisation from bn.sums_f (left as is) + apply, one launch in the product"""
+    C = bn.C
+    M = x.numel() // C
+    mean = (bn.sums_f[:C] / M).to(bn.mean.dtype)
+    var = ((bn.sums_f[C:] / M).to(bn.mean.dtype) - mean * mean).clamp(min=0)
+    _finish_stats(bn, mean, var, M, eps, momentum, fix_gamma, update_moving)
+    return affine_act(x, bn.scale, bn.shift, relu=relu, out=out)
+
+
+def bn_relu_bwd(x, dy, bn, add=None, out=None, defer=False):
+    return bn_act_bwd(x, dy, bn, 1, add=add, out=out, defer=defer)
+
+
+def maxpool3x3s2(x):
+    return _nhwc(F.max_pool2d(_nchw(x), 3, 2, 1)).contiguous()
+
+
+def stem_rows(w, dtype=None):
+    return w                                  # [64,7,7,3]: the fake stem convolves directly
+
+
+def stem_conv_tc(x_nchw, rows, in_scale, in_shift, out_scale, out_shift, out_dtype=None):
+    """bn_data -> conv0 7x7/2 pad 3 (zero padding of the NORMALISED image) -> bn0 -> relu, NHWC out"""
+    xn = x_nchw * in_scale.view(1, 3, 1, 1) + in_shift.view(1, 3, 1, 1)
+    y = F.conv2d(xn, rows.to(xn.dtype).permute(0, 3, 1, 2), None, 2, 3)
+    y = (y * out_scale.view(1, -1, 1, 1) + out_shift.view(1, -1, 1, 1)).clamp(min=0)
+    return _nhwc(y).contiguous()
+
+
+stem_conv = stem_conv_tc
+
+
+def _deform_cols(x, offset, dil, pad, dg):
+    """Differentiable deformable im2col (deformable_im2col.cuh:78-113, 216-263), NHWC: x [N,H,W,C], offset
+    [N,H,W,>=dg*18] with channel g*18 + 2*tap (+1) = (dy, dx) -> col [N,H,W,9,C] (same sampling rule as
+    oracle/torch_graph.deform_conv2d)."""
+    N, H, W, C = x.shape
+    cpg = C // dg
+    hh, ww = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    n_idx = torch.arange(N).view(N, 1, 1).expand(N, H, W)
+    cols = []
+    for tap in range(9):
+        i, j = divmod(tap, 3)
+        per_g = []
+        for g in range(dg):
+            oh, ow = offset[..., g * 18 + 2 * tap], offset[..., g * 18 + 2 * tap + 1]
+            h_im = (hh - pad + i * dil).to(x.dtype) + oh
+            w_im = (ww - pad + j * dil).to(x.dtype) + ow
+            valid = (h_im >= 0) & (w_im >= 0) & (h_im < H) & (w_im < W)
+            h_low = torch.floor(h_im).clamp(max=H - 1)
+            w_low = torch.floor(w_im).clamp(max=W - 1)
+            hc = torch.where(torch.floor(h_im) >= H - 1, h_low, h_im)
+            wc = torch.where(torch.floor(w_im) >= W - 1, w_low, w_im)
+            h_high, w_high = (h_low + 1).clamp(max=H - 1), (w_low + 1).clamp(max=W - 1)
+            lh, lw = hc - h_low, wc - w_low
+            xg = x[..., g * cpg:(g + 1) * cpg]
+            at = lambda hi, wi: xg[n_idx, hi.long().clamp(0, H - 1), wi.long().clamp(0, W - 1)]
+            v = ((1 - lh) * (1 - lw)).unsqueeze(-1) * at(h_low, w_low) + ((1 - lh) * lw).unsqueeze(-1) * at(h_low, w_high) \
+                + (lh * (1 - lw)).unsqueeze(-1) * at(h_high, w_low) + (lh * lw).unsqueeze(-1) * at(h_high, w_high)
+            per_g.append(v * valid.unsqueeze(-1).to(x.dtype))
+        cols.append(torch.cat(per_g, -1))
+    return torch.stack(cols, 3)
+
+
+def deform_im2col(x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroups=4, out=None):
+    N, H, W, C = x.shape
+    return _deform_cols(x, offset.to(x.dtype), dil, pad, dgroups).reshape(N * H * W, 9 * C)
+
+
+def deform_col2im(dcol, x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroups=4, dx=None, doffset=None):
+    N, H, W, C = x.shape
+    xr = x.detach().clone().requires_grad_(True)
+    orr = offset.detach().to(x.dtype).clone().requires_grad_(True)
+    col = _deform_cols(xr, orr, dil, pad, dgroups)
+    gx, go = torch.autograd.grad(col, (xr, orr), dcol.reshape(col.shape))
+    dx = gx if dx is None else dx + gx
+    doffset = go if doffset is None else doffset + go
+    return dx, doffset
 
 
 def affine_act(x, scale, shift, relu=True, out=None):

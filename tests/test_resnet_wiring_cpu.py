@@ -1,0 +1,112 @@
+"""ResNet-101 SNIPER graph (the metric's configuration), host logic: the hand-scheduled forward / backward of
+`model.SniperResNet101` -- frozen stem and stage 1, fused BatchNorm statistics, in-place concat slices, the deformable
+units, strided data gradients through parity-split weights, the fused RPN / R-FCN heads, the gradient cut below stage 2 --
+executed on the CPU in float64 through tests/fake_ops.py (torch restatements of each C-ABI call's contract) against the
+autograd oracle oracle/torch_graph.py.  The GPU whole-graph test (tests/test_graph_parity_gpu.py) makes the same
+comparison through the real kernels at TF32 / bf16 tolerances; here the ORCHESTRATION is pinned to 1e-7: rois / labels
+equal (both sides call the C oracle), activations, the four loss sums, all 297 parameter gradients in the reference's
+names and layouts, and the inference graphs (forward_inference, forward_rpn)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+@pytest.fixture
+def f64():
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
+
+
+def _net(monkeypatch, B, seed=5):
+    import fake_ops
+    from sniper_b200 import model, ops
+    fake_ops.install(monkeypatch, ops)
+    cfg = model.Cfg()
+    cfg.batch_images, cfg.bf16, cfg.wgrad_stream = B, False, False
+    net = model.SniperResNet101(cfg, device="cpu", seed=seed, deform_offset_std=0.01)
+    g = torch.Generator().manual_seed(seed + 1)
+    for bn in net._named_bns():
+        if bn.name == "bn_data":
+            continue
+        lo, hi, sd = (0.15, 0.25, 0.02) if bn.name.endswith("_bn3") else (0.8, 1.2, 0.1)
+        bn.st.gamma.copy_(torch.empty(bn.C).uniform_(lo, hi, generator=g))
+        bn.st.beta.copy_(torch.empty(bn.C).normal_(0, sd, generator=g))
+        if bn.frozen:
+            bn.st.moving_mean.copy_(torch.empty(bn.C).normal_(0, 0.1, generator=g))
+            bn.st.moving_var.copy_(torch.empty(bn.C).uniform_(0.6, 1.6, generator=g))
+            ops.bn_frozen(bn.st, cfg.bn_eps)
+    return cfg, net
+
+
+def _batch(B, chip):
+    from sniper_b200 import synth_batch
+    b = synth_batch.make_batch(B, seed=7, device="cpu", chip=chip)
+    return {k: v.double() for k, v in b.items()}
+
+
+def _rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_training_graph_matches_the_autograd_oracle(monkeypatch, f64):
+    import oracle_lib as O
+    import torch_graph as TG
+    B, chip = 1, 256
+    cfg, net = _net(monkeypatch, B)
+    batch = _batch(B, chip)
+    out = net.forward_backward(batch)
+    A = cfg.num_anchors
+    prob = out["rpn_cls_prob"].permute(0, 3, 1, 2).contiguous()
+    bbox = out["rpn_head"][..., :4 * A].permute(0, 3, 1, 2).contiguous()
+    res = O.multi_proposal_target(prob.numpy(), bbox.numpy(), batch["im_info"].numpy(), batch["gt_boxes"].numpy(),
+                                  batch["valid_ranges"].numpy())
+    assert out["rois"].numpy().astype(np.float32).tobytes() == res["rois"].tobytes()
+    assert int((res["label"] > 0).sum()) > 0, "test batch yields no foreground roi"
+    arg, aux = net.export_reference()
+    P, Aux = TG.params_to_torch(arg, aux)
+    TG.MODE[0] = "exact"
+    obj, ref = TG.forward_train(P, Aux, batch, lambda *_: res, batch_images=B)
+    obj.backward()
+    errs = dict(cat=_rel(out["cat"].permute(0, 3, 1, 2), ref["relu1"]), rpn_prob=_rel(prob, ref["rpn_cls_prob"]),
+                cls_prob=_rel(out["cls_prob"], ref["cls_prob"]))
+    print("activation errors", errs)
+    assert max(errs.values()) < 1e-9
+    assert torch.allclose(out["losses"][:4], ref["loss_sums"], rtol=1e-5)
+    garg, _ = net.export_reference(grads=True)
+    rows = []
+    for name, p in P.items():
+        if not p.requires_grad:
+            assert name not in garg, name
+            continue
+        assert p.grad is not None and garg[name].shape == tuple(p.grad.shape), name
+        rows.append((_rel(torch.from_numpy(garg[name]), p.grad), name))
+    rows.sort(reverse=True)
+    print("worst gradient errors", rows[:5])
+    assert len(rows) == 297
+    assert rows[0][0] < 1e-5, rows[:5]                      # (limit: fp32 storage of the data-gradient operands)
+
+
+def test_inference_graphs(monkeypatch, f64):
+    """forward_inference == the oracle's test-mode evaluation on the C oracle's proposals; forward_rpn == its proposal
+    half, bit for bit."""
+    B, chip = 1, 256
+    cfg, net = _net(monkeypatch, B)
+    batch = _batch(B, chip)
+    net.train_step(batch, lr=0.001)                      # moving statistics of the trainable BatchNorms become non-trivial
+    w0 = net.P.w.clone()
+    rois, scores, cls_prob, bbox_pred = net.forward_inference(batch["data"], batch["im_info"])
+    r2, s2 = net.forward_rpn(batch["data"], batch["im_info"])
+    assert torch.equal(rois, r2) and torch.equal(scores, s2) and torch.equal(net.P.w, w0)
+    assert rois.shape == (B * 300, 5) and (cls_prob.sum(1) - 1).abs().max() < 1e-9
+    assert (rois[:, 1:] >= 0).all() and (rois[:, 1:] <= chip - 1).all()
