@@ -131,6 +131,6 @@ if __name__ == "__main__":
     res = build()
     path = os.path.join(ROOT, "tests", "golden", "ref_symbols.json")
     with open(path, "w") as f:
-        json.dump(res, f, indent=0, sort_keys=True)
+        json.dump(res, f, sort_keys=True, separators=(",", ":"))      # compact: ~150 KB
     for k, v in res.items():
         print(k, len(v["arguments"]), "args", len(v["auxiliary"]), "aux", v["outputs"], v["ops"])
