@@ -148,3 +148,39 @@ def test_bf16_rounding_helper_is_round_to_nearest_even(emu):
     want = (x.float() * w[4]).to(torch.bfloat16)
     fin = torch.isfinite(want.float())
     assert torch.equal(y.float()[fin], want.float()[fin])
+
+
+def test_depthwise_cores_random_shapes(emu):
+    """Seeded sweep over odd shapes (maps down to 1x1, widths that leave ragged strips / tiles, channel counts around the
+    lane-mapping thresholds, padded rows): every kernel body against float64, tiled == register-window bit for bit."""
+    rng = np.random.RandomState(12)
+    for it in range(40):
+        NB, H, W = int(rng.randint(1, 4)), int(rng.randint(1, 21)), int(rng.randint(1, 41))
+        C = int(rng.choice([4, 8, 60, 64, 68, 124, 128, 192]))
+        stride = int(rng.randint(1, 3))
+        dtype = torch.bfloat16 if rng.rand() < 0.5 else torch.float32
+        extra = int(rng.choice([0, 4, 8]))
+        dt = 0 if dtype == torch.float32 else 1
+        x, w, dy, Ho, Wo = _case(NB, H, W, C, stride, dtype, extra, seed=100 + it)
+        ld = C + extra
+        y_ref, dx_ref, dw_ref = _ref(x, w, dy, C, stride)
+        tol = 1e-5 if dtype == torch.float32 else 1e-2
+        tag = (NB, H, W, C, stride, str(dtype), extra)
+        y = torch.zeros(NB, Ho, Wo, ld).to(dtype)
+        emu.emu_dw_fwd(_p(x), ctypes.c_long(ld), _p(w), _p(y), ctypes.c_long(ld), NB, H, W, C, stride, dt)
+        assert torch.allclose(y[..., :C].double(), y_ref, rtol=tol, atol=3 * tol), tag
+        dx = torch.zeros(NB, H, W, ld).to(dtype)
+        emu.emu_dw_dgrad(_p(dy), ctypes.c_long(ld), _p(w), _p(dx), ctypes.c_long(ld), NB, H, W, C, stride, dt)
+        assert torch.allclose(dx[..., :C].double(), dx_ref, rtol=tol, atol=3 * tol), tag
+        dw = torch.zeros(9, C)
+        emu.emu_dw_wgrad(_p(x), ctypes.c_long(ld), _p(dy), ctypes.c_long(ld), _p(dw), NB, H, W, C, stride, dt,
+                         int(rng.randint(1, 50)))
+        assert torch.allclose(dw.double(), dw_ref, rtol=1e-4, atol=1e-5 * (float(dw_ref.abs().max()) + 1.0)), tag
+        if dt == 1 and C % 64 == 0 and ld % 8 == 0:
+            y2 = torch.zeros_like(y)
+            emu.emu_dw_tiled(_p(x), ctypes.c_long(ld), _p(w), _p(y2), ctypes.c_long(ld), NB, H, W, C, stride, 0)
+            assert torch.equal(y2[..., :C].float(), y[..., :C].float()), tag
+            if stride == 1:
+                dx2 = torch.zeros_like(dx)
+                emu.emu_dw_tiled(_p(dy), ctypes.c_long(ld), _p(w), _p(dx2), ctypes.c_long(ld), NB, H, W, C, 1, 1)
+                assert torch.equal(dx2[..., :C].float(), dx[..., :C].float()), tag
