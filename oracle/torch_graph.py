@@ -83,11 +83,11 @@ class _RoundWeight(torch.autograd.Function):
 
 
 def qs(x):
-    return _RoundStored.apply(x) if (MODE[0] == "bf16" and LOWP[0]) else x
+    return _RoundStored.apply(x) if (MODE[0] in ("bf16", "bf16x") and LOWP[0]) else x
 
 
 def qw(w):
-    return _RoundWeight.apply(w) if (MODE[0] == "bf16" and LOWP[0]) else w
+    return _RoundWeight.apply(w) if (MODE[0] in ("bf16", "bf16x") and LOWP[0]) else w
 
 
 def tf32(x):
@@ -132,8 +132,10 @@ class _TF32MatmulNT(torch.autograd.Function):
 def conv2d(x, w, b=None, stride=1, padding=0, dilation=1, exact=False):
     if MODE[0] == "exact" or exact:
         return F.conv2d(x, w, b, stride, padding, dilation)
-    if MODE[0] == "bf16" and LOWP[0]:          # operands are stored bf16 tensors already; exact accumulation
+    if MODE[0] in ("bf16", "bf16x") and LOWP[0]:          # operands are stored bf16 tensors already; exact accumulation
         return F.conv2d(x, qw(w), b, stride, padding, dilation)
+    if MODE[0] == "bf16x":                     # "bf16x": bf16 storage between the Casts, EXACT arithmetic in the heads (the
+        return F.conv2d(x, w, b, stride, padding, dilation)      # CPU orchestration tests; "bf16" models the TF32 heads too)
     y = _TF32Conv.apply(x, w, stride, padding, dilation)
     return y if b is None else y + b.view(1, -1, 1, 1)
 
@@ -141,8 +143,10 @@ def conv2d(x, w, b=None, stride=1, padding=0, dilation=1, exact=False):
 def linear(x, w, b=None):
     if MODE[0] == "exact":
         return F.linear(x, w, b)
-    if MODE[0] == "bf16" and LOWP[0]:
+    if MODE[0] in ("bf16", "bf16x") and LOWP[0]:
         return F.linear(x, qw(w), b)
+    if MODE[0] == "bf16x":
+        return F.linear(x, w, b)
     y = _TF32MatmulNT.apply(x, w)
     return y if b is None else y + b
 
@@ -265,7 +269,7 @@ def backbone(P, A, data, eps=2e-5, taps=None):
     x = _bn(P, A, data, "bn_data", eps, False, relu=False, fix_gamma=True)
     if STEM[0] == "fma" or MODE[0] == "exact":
         x = conv2d(x, P["conv0_weight"], None, 2, 3, exact=True)
-    elif MODE[0] == "bf16":               # bf16 im2col buffer x bf16 weight rows, exact accumulation
+    elif MODE[0] in ("bf16", "bf16x"):    # bf16 im2col buffer x bf16 weight rows, exact accumulation
         x = F.conv2d(_bf16(x), _bf16(P["conv0_weight"]), None, 2, 3)
     else:
         x = conv2d(x, P["conv0_weight"], None, 2, 3)

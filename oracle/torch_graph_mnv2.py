@@ -80,7 +80,7 @@ def _unit(P, x, prefix, k, stride, groups, act, eps, first=False, aux=None):
     w = P[prefix + "-conv2d_weight"]
     if groups > 1:
         c = F.conv2d(x, w, None, stride, 1, 1, groups)               # depthwise: exact FMA kernel in the product
-    elif first and TG.MODE[0] == "bf16":
+    elif first and TG.MODE[0] in ("bf16", "bf16x"):
         c = F.conv2d(TG._bf16(x), TG._RoundWeight.apply(w), None, stride, 1)       # bf16 im2col buffer x bf16 weight rows
     else:
         c = TG.conv2d(x, w, None, stride, (k - 1) // 2)

@@ -23,17 +23,31 @@ def _nhwc(x):
     return x.permute(0, 2, 3, 1)
 
 
-def _emit(y, out):
+# Storage semantics.  Every stand-in computes in float64 ("exact arithmetic") and rounds ONCE to the dtype the product
+# stores the result in: bf16 tensors through float32 (the kernels accumulate in fp32 and convert; oracle/torch_graph._bf16
+# does the same), float32 tensors to float32, float64 (the default dtype of the sharp tests) not at all.
+def _d(t):
+    return None if t is None else t.double()
+
+
+def _st(y, dtype):
+    if dtype == torch.bfloat16:
+        return y.float().to(torch.bfloat16)
+    return y.to(dtype)
+
+
+def _emit(y, out, dtype=None):
     if out is None:
-        return y.contiguous()
-    out.copy_(y)
+        return _st(y, dtype if dtype is not None else y.dtype).contiguous()
+    out.copy_(_st(y, out.dtype))
     return out
 
 
-def _stats(y, stats):
+def _stats(y, stats, dtype):
+    """sum / sum of squares of the STORED values"""
     if stats is not None:
         C = y.shape[-1]
-        f = y.reshape(-1, C).double()
+        f = _st(y, dtype).reshape(-1, C).double()
         stats[:C] += f.sum(0)
         stats[C:2 * C] += (f * f).sum(0)
 
@@ -52,11 +66,12 @@ def _epi(y, scale, bias, residual, relu):
 
 def gemm_nt(a, b, *, out=None, scale=None, bias=None, residual=None, relu=False, accumulate=False, out_dtype=None,
             stats=None):
-    y = _epi(a @ b.to(a.dtype).t(), scale, bias, residual, relu)      # (data-gradient operands are stored fp32)
+    y = _epi(_d(a) @ _d(b).t(), _d(scale), _d(bias), _d(residual), relu)
     if accumulate:
-        y = y + out
-    _stats(y, stats)
-    return _emit(y, out)
+        y = y + _d(out)
+    dt = out.dtype if out is not None else _exact(out_dtype or a.dtype)
+    _stats(y, stats, dt)
+    return _emit(y, out, dt)
 
 
 def conv_taps(kh, kw, dil, pad):
@@ -78,7 +93,10 @@ def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, b
         Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     else:
         Ho, Wo = out_hw
-    wd = w.to(x.dtype)
+    wd, xin = _d(w), x
+    x = _d(x)
+    scale, bias, residual = _d(scale), _d(bias), _d(residual)
+    dt = out.dtype if (out is not None and out_map is None) else _exact(out_dtype or xin.dtype)
     y = x.new_zeros(NB, Ho, Wo, Cout)
     ah, aw = torch.arange(Ho) * stride, torch.arange(Wo) * stride
     for t in range(len(dh)):
@@ -88,21 +106,21 @@ def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, b
         y = y + xs @ wd[:, t * Cin:(t + 1) * Cin].t()
     if out_map is None:
         y = _epi(y, scale, bias, residual, relu)
-        _stats(y, stats)
-        return _emit(y, out)
+        _stats(y, stats, dt)
+        return _emit(y, out, dt)
     oH, oW, os_, ooh, oow = out_map
     res = None if residual is None else residual[:, ooh::os_, oow::os_][:, :Ho, :Wo]
     y = _epi(y, scale, bias, res, relu)
-    _stats(y, stats)
     assert out is not None and out.shape[1] == oH and out.shape[2] == oW
-    out[:, ooh::os_, oow::os_][:, :Ho, :Wo] = y
+    _stats(y, stats, out.dtype)
+    out[:, ooh::os_, oow::os_][:, :Ho, :Wo] = _st(y, out.dtype)
     return out
 
 
 def conv2d_wgrad_nhwc(dy, x, *, kh, kw, stride=1, dil=1, pad=0, dw_out=None, splits=8, taps=None):
     Cout, Cin = dy.shape[3], x.shape[3]
-    g = torch.nn.grad.conv2d_weight(_nchw(x).contiguous(), (Cout, Cin, kh, kw), _nchw(dy).contiguous(), stride, pad, dil)
-    dw_out += g.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin)
+    g = torch.nn.grad.conv2d_weight(_nchw(_d(x)).contiguous(), (Cout, Cin, kh, kw), _nchw(_d(dy)).contiguous(), stride, pad, dil)
+    dw_out += g.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin).to(dw_out.dtype)
     return dw_out
 
 
@@ -113,7 +131,7 @@ def weight_transpose_jobs(jobs, device):
 def weight_transpose_batched(table):
     for w, wt, sel, Cout, T, Cin in table:
         s = sel.long()
-        wt.view(Cin, len(s), Cout).copy_(w.view(Cout, T, Cin)[:, s, :].permute(2, 1, 0))
+        wt.view(Cin, len(s), Cout).copy_(_st(_d(w).view(Cout, T, Cin)[:, s, :].permute(2, 1, 0), wt.dtype))
 
 
 def bn_param_grad_jobs(states, device):
@@ -131,42 +149,43 @@ def bn_param_grad_batched(table):
 
 
 def _finish_stats(bn, mean, var, M, eps, momentum, fix_gamma, update_moving):
-    g = torch.ones_like(bn.gamma) if fix_gamma else bn.gamma
+    g = torch.ones_like(bn.gamma).double() if fix_gamma else _d(bn.gamma)
     invstd = 1.0 / torch.sqrt(var + eps)
     bn.mean.copy_(mean); bn.invstd.copy_(invstd)
-    bn.scale.copy_(g * invstd); bn.shift.copy_(bn.beta - mean * g * invstd)
+    bn.scale.copy_(g * invstd); bn.shift.copy_(_d(bn.beta) - mean * g * invstd)
     if update_moving:
         unb = var * M / (M - 1) if M > 1 else var
-        bn.moving_mean.copy_(bn.moving_mean * momentum + mean * (1 - momentum))
-        bn.moving_var.copy_(bn.moving_var * momentum + unb * (1 - momentum))
+        bn.moving_mean.copy_(_d(bn.moving_mean) * momentum + mean * (1 - momentum))
+        bn.moving_var.copy_(_d(bn.moving_var) * momentum + unb * (1 - momentum))
 
 
 def bn_stats(x, bn, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=True):
-    f = x.reshape(-1, x.shape[-1])
+    f = _d(x).reshape(-1, x.shape[-1])
     M = f.shape[0]
     _finish_stats(bn, f.mean(0), f.var(0, unbiased=False), M, eps, momentum, fix_gamma, update_moving)
 
 
 def bn_finalize(bn, M, eps=2e-5, momentum=0.9, fix_gamma=False, update_moving=True):
     C = bn.C
-    mean = (bn.sums[:C] / M).to(bn.mean.dtype)
-    var = (bn.sums[C:] / M).to(bn.mean.dtype) - mean * mean
+    mean = bn.sums[:C] / M
+    var = bn.sums[C:] / M - mean * mean
     _finish_stats(bn, mean, var.clamp(min=0), M, eps, momentum, fix_gamma, update_moving)
     bn.sums.zero_()
 
 
 def bn_frozen(bn, eps=2e-5, fix_gamma=False):
-    g = torch.ones_like(bn.gamma) if fix_gamma else bn.gamma
-    bn.scale.copy_(g / torch.sqrt(bn.moving_var + eps))
-    bn.shift.copy_(bn.beta - bn.moving_mean * bn.scale)
+    g = torch.ones_like(bn.gamma).double() if fix_gamma else _d(bn.gamma)
+    sc = g / torch.sqrt(_d(bn.moving_var) + eps)
+    bn.scale.copy_(sc)
+    bn.shift.copy_(_d(bn.beta) - _d(bn.moving_mean) * sc)
 
 
 def bn_apply_train(x, bn, eps=2e-5, momentum=0.9, relu=True, fix_gamma=False, update_moving=True, out=None):
     """finalisation from bn.sums_f (left as is) + apply, one launch in the product"""
     C = bn.C
     M = x.numel() // C
-    mean = (bn.sums_f[:C] / M).to(bn.mean.dtype)
-    var = ((bn.sums_f[C:] / M).to(bn.mean.dtype) - mean * mean).clamp(min=0)
+    mean = bn.sums_f[:C] / M
+    var = (bn.sums_f[C:] / M - mean * mean).clamp(min=0)
     _finish_stats(bn, mean, var, M, eps, momentum, fix_gamma, update_moving)
     return affine_act(x, bn.scale, bn.shift, relu=relu, out=out)
 
@@ -243,57 +262,60 @@ def deform_col2im(dcol, x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroup
 
 
 def affine_act(x, scale, shift, relu=True, out=None):
-    y = x * scale + shift
+    y = _d(x) * _d(scale) + _d(shift)
     r = int(relu)
     if r:
         y = y.clamp(min=0)
     if r == 2:
         y = y.clamp(max=6)
-    return _emit(y, out)
+    return _emit(y, out, x.dtype)
 
 
 def bn_act_bwd(x, dy, bn, act, add=None, out=None, defer=False):
     C = bn.C
-    y = x * bn.scale + bn.shift
+    xin = x
+    x, dy = _d(x), _d(dy)
+    scale, shift, mean, invstd = _d(bn.scale), _d(bn.shift), _d(bn.mean), _d(bn.invstd)
+    y = x * scale + shift
     if act == 1:
         g = dy * (y > 0)
     elif act == 2:
         g = dy * ((y >= 0) & (y <= 6))
     else:
         g = dy
-    xhat = (x - bn.mean) * bn.invstd
+    xhat = (x - mean) * invstd
     gf, xf = g.reshape(-1, C), xhat.reshape(-1, C)
     M = gf.shape[0]
     S1, S2 = gf.sum(0), (gf * xf).sum(0)
-    dx = bn.scale * (g - S1 / M - xhat * (S2 / M))
+    dx = scale * (g - S1 / M - xhat * (S2 / M))
     if add is not None:
-        dx = dx + add
+        dx = dx + _d(add)
     if defer:
-        bn.sums[:C] += S1.double()
-        bn.sums[C:] += S2.double()
+        bn.sums[:C] += S1
+        bn.sums[C:] += S2
     else:
-        bn.dbeta += S1
-        bn.dgamma += S2
-    return _emit(dx, out)
+        bn.dbeta += S1.to(bn.dbeta.dtype)
+        bn.dgamma += S2.to(bn.dgamma.dtype)
+    return _emit(dx, out, xin.dtype)
 
 
 def depthwise3x3(x, w, stride=1, out=None):
     C = x.shape[3]
-    w4 = w.t().reshape(C, 1, 3, 3)
-    return _emit(_nhwc(F.conv2d(_nchw(x), w4, None, stride, 1, 1, C)), out)
+    w4 = _d(w).t().reshape(C, 1, 3, 3)
+    return _emit(_nhwc(F.conv2d(_nchw(_d(x)), w4, None, stride, 1, 1, C)), out, x.dtype)
 
 
 def depthwise3x3_dgrad(dy, w, in_hw, stride=1, out=None):
     NB, Ho, Wo, C = dy.shape
-    w4 = w.t().reshape(C, 1, 3, 3)
-    g = torch.nn.grad.conv2d_input((NB, C, in_hw[0], in_hw[1]), w4, _nchw(dy).contiguous(), stride, 1, 1, C)
-    return _emit(_nhwc(g), out)
+    w4 = _d(w).t().reshape(C, 1, 3, 3)
+    g = torch.nn.grad.conv2d_input((NB, C, in_hw[0], in_hw[1]), w4, _nchw(_d(dy)).contiguous(), stride, 1, 1, C)
+    return _emit(_nhwc(g), out, dy.dtype)
 
 
 def depthwise3x3_wgrad(x, dy, dw, stride=1):
     C = x.shape[3]
-    g = torch.nn.grad.conv2d_weight(_nchw(x).contiguous(), (C, 1, 3, 3), _nchw(dy).contiguous(), stride, 1, 1, C)
-    dw += g.reshape(C, 9).t()
+    g = torch.nn.grad.conv2d_weight(_nchw(_d(x)).contiguous(), (C, 1, 3, 3), _nchw(_d(dy)).contiguous(), stride, 1, 1, C)
+    dw += g.reshape(C, 9).t().to(dw.dtype)
     return dw
 
 
@@ -303,22 +325,28 @@ def im2col3x3s2(x_nchw, Kp, dtype=None, out=None):
     u = F.unfold(x_nchw, 3, padding=1, stride=2).view(NB, Cin, 9, Ho, Wo).permute(0, 3, 4, 2, 1).reshape(NB, Ho, Wo, 9 * Cin)
     col = x_nchw.new_zeros(NB, Ho, Wo, Kp)
     col[..., :9 * Cin] = u
-    return col
+    return _st(col, dtype if dtype is not None else x_nchw.dtype) if dtype in (torch.bfloat16,) else col
 
 
 def add_rows(a, b, out=None):
-    return _emit(a + b, out)
+    return _emit(_d(a) + _d(b), out, a.dtype)
+
+
+def _exact(dtype):
+    """In the float64 tests "fp32" means "the exact type": a float32 request becomes float64 (a bf16 -> fp32 Cast is exact
+    anyway), so that nothing but the bf16 storage rounds."""
+    return torch.float64 if (dtype == torch.float32 and torch.get_default_dtype() == torch.float64) else dtype
 
 
 def cast_rows(x, dtype=None, out=None):
     if out is not None:
-        out.copy_(x)
+        out.copy_(_st(_d(x), out.dtype))
         return out
-    return x.to(dtype).contiguous()
+    return _st(_d(x), _exact(dtype)).contiguous()
 
 
 def relu_bwd(y, dy, out=None):
-    return _emit(dy * (y > 0), out)
+    return _emit(_d(dy) * (y > 0), out, dy.dtype)
 
 
 def colsum_accum(x, out):
@@ -438,6 +466,8 @@ def sgd_mom_dev(w, mom, g, hyper, lr_mult, wd_mult, momentum, rescale=1.0, w_bf1
     lr, wd = float(hyper[0]) * lr_mult, float(hyper[1]) * wd_mult
     mom.mul_(momentum).sub_(lr * (rescale * g + wd * w))
     w.add_(mom)
+    if w_bf16 is not None:
+        w_bf16.copy_(w)
 
 
 PATCHED = [k for k, v in list(globals().items()) if callable(v) and not k.startswith("_") and k not in ("F", "O")]

@@ -154,3 +154,76 @@ def test_inference_graph_matches_the_oracle(monkeypatch, f64):
     rel = lambda a, b: float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
     assert rel(cls_prob, ref["cls_prob"]) < 1e-5 and rel(bbox_pred, ref["bbox_pred"]) < 1e-4
     assert (cls_prob.sum(1) - 1).abs().max() < 1e-9
+
+
+def test_mixed_precision_orchestration_matches_the_bf16_oracle(monkeypatch, f64):
+    """Cfg.bf16 (config 4's precision) on dtype-faithful stand-ins: bf16 activations, weight copies and activation
+    gradients between the two Casts, every stand-in computing exactly and rounding ONCE to the dtype the product stores
+    (tests/fake_ops.py; everything that is fp32 in the product is float64 here, so bf16 storage is the only rounding).
+    Reference: the oracle in mode "bf16x" (every stored backbone tensor rounded to bf16, forward and backward, exact
+    arithmetic elsewhere).  Where to round and what to keep wide is ORCHESTRATION -- the casts, the bf16 weight copies and
+    their transposes, fp32 master gradients, unrounded depthwise filters, statistics of the ROUNDED convolution output,
+    the shortcut summed before it is stored, the residual gradient added before the data gradient is stored -- and the
+    two sides agree to the last bit of every stored tensor (last_fm error 0.0, all 71 gradients to 2e-15).
+    It also shows why the GPU whole-graph comparison in bf16 is loose: seed ONE float32-level difference (the second
+    part: BatchNorm vectors stored as float32, 6e-8) and the same two evaluations part ways to 0.17 at last_fm with
+    decorrelated gradients -- bf16 re-quantisation turns last-bit differences into 4e-3 ones at every layer."""
+    import oracle_lib as O
+    import torch_graph as TG
+    import torch_graph_mnv2 as TM
+    import fake_ops
+    from sniper_b200 import model_mnv2 as MM
+    from sniper_b200 import ops, synth_batch
+    fake_ops.install(monkeypatch, ops)
+    B, chip = 2, 256
+    rel = lambda a, b: float((a.detach().double() - b.detach().double()).norm() / (b.detach().double().norm() + 1e-30))
+
+    def run(bn_state_dtype):
+        cfg = MM.MCfg()
+        cfg.batch_images, cfg.bf16, cfg.wgrad_stream = B, True, False
+        net = MM.SniperMobileNetV2(cfg, device="cpu", seed=3)
+        g = torch.Generator().manual_seed(4)
+        for bn in net.all_bns():
+            bn.st.gamma[:bn.C] = torch.empty(bn.C).uniform_(0.8, 1.2, generator=g)
+            bn.st.beta[:bn.C] = torch.empty(bn.C).normal_(0, 0.1, generator=g)
+            if bn_state_dtype != torch.float64:      # the product's storage of the per-step BatchNorm vectors
+                for k in ("mean", "invstd", "scale", "shift"):
+                    setattr(bn.st, k, getattr(bn.st, k).to(bn_state_dtype))
+        net.P.w16.copy_(net.P.w.float())            # bf16 copy of the fp32 masters (double -> float -> bf16, as the oracle)
+        for c in net.head_convs():                  # the heads' data-gradient operands: fp32 in the product = exact here
+            c.wdtype = torch.float64
+        batch = {k: v.double() for k, v in synth_batch.make_batch(B, seed=7, device="cpu", chip=chip, A=15, stride=32).items()}
+        out = net.forward_backward(batch)
+        assert out["first"].dtype == torch.bfloat16
+        A = cfg.num_anchors
+        prob = out["rpn_cls_prob"].permute(0, 3, 1, 2).contiguous()
+        bbox = out["rpn_head"][..., :4 * A].permute(0, 3, 1, 2).contiguous()
+        res = O.multi_proposal_target(prob.numpy(), bbox.numpy(), batch["im_info"].numpy(), batch["gt_boxes"].numpy(),
+                                      batch["valid_ranges"].numpy(), feat_stride=32, scales=cfg.scales, ratios=cfg.ratios)
+        assert out["rois"].numpy().astype(np.float32).tobytes() == res["rois"].tobytes()
+        arg, aux = net.export_reference()
+        P, Aux = TM.params_to_torch(arg, aux)
+        TG.MODE[0] = "bf16x"
+        try:
+            obj, ref = TM.forward_train(P, Aux, batch, lambda *_: res, batch_images=B)
+            obj.backward()
+        finally:
+            TG.MODE[0] = "exact"
+            TG.LOWP[0] = False
+        errs = dict(last_fm=rel(out["last_fm"].permute(0, 3, 1, 2), ref["last_fm"]), rpn_prob=rel(prob, ref["rpn_cls_prob"]),
+                    cls_prob=rel(out["cls_prob"], ref["cls_prob"]))
+        garg, _ = net.export_reference(grads=True)
+        rows = sorted(((rel(torch.from_numpy(garg[n]), p.grad), n) for n, p in P.items() if p.requires_grad), reverse=True)
+        assert len(rows) == 71
+        for c in net.backbone_convs():
+            gw = net.P.grad(c.name + "_weight")
+            assert not gw[c.cout:].any() and not gw[:, c.cin_real:].any(), c.name
+        return errs, rows
+
+    errs, rows = run(torch.float64)
+    print("exact emulation: activation errors", errs, "worst gradient errors", rows[:3])
+    assert max(errs.values()) < 1e-12 and rows[0][0] < 1e-11, (errs, rows[:5])
+    errs32, rows32 = run(torch.float32)
+    print("with float32 BatchNorm vectors: activation errors", errs32, "median gradient error", rows32[len(rows32) // 2])
+    # one 6e-8 seed is enough: the figures of the B200 run (last_fm 0.195, gradients 0.85; profiles/config4_r02.md) reappear
+    assert errs32["last_fm"] > 1e-2 and rows32[len(rows32) // 2][0] > 0.2

@@ -81,7 +81,7 @@ def test_training_graph_matches_the_autograd_oracle(monkeypatch, f64):
     errs = dict(cat=_rel(out["cat"].permute(0, 3, 1, 2), ref["relu1"]), rpn_prob=_rel(prob, ref["rpn_cls_prob"]),
                 cls_prob=_rel(out["cls_prob"], ref["cls_prob"]))
     print("activation errors", errs)
-    assert max(errs.values()) < 1e-9
+    assert max(errs.values()) < 1e-7                       # (the deformable offsets are float32 tensors by contract)
     assert torch.allclose(out["losses"][:4], ref["loss_sums"], rtol=1e-5)
     garg, _ = net.export_reference(grads=True)
     rows = []
