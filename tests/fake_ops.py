@@ -30,6 +30,21 @@ def _d(t):
     return None if t is None else t.double()
 
 
+# TF32[0] = True: the operands of every tensor-core contraction (gemm_nt, conv2d_nhwc, conv2d_wgrad_nhwc) that are NOT
+# bf16 are reduced the way `tcgen05.mma kind::tf32` reads fp32 words -- fp32, low 13 mantissa bits dropped -- as
+# oracle/torch_graph.py's MODE "tf32" does.
+TF32 = [False]
+
+
+def _mma(t):
+    if t is None:
+        return None
+    if TF32[0] and t.dtype != torch.bfloat16:
+        i = t.detach().to(torch.float32).contiguous().view(torch.int32)
+        return (i & -8192).view(torch.float32).double()
+    return t.double()
+
+
 def _st(y, dtype):
     if dtype == torch.bfloat16:
         return y.float().to(torch.bfloat16)
@@ -66,7 +81,7 @@ def _epi(y, scale, bias, residual, relu):
 
 def gemm_nt(a, b, *, out=None, scale=None, bias=None, residual=None, relu=False, accumulate=False, out_dtype=None,
             stats=None):
-    y = _epi(_d(a) @ _d(b).t(), _d(scale), _d(bias), _d(residual), relu)
+    y = _epi(_mma(a) @ _mma(b).t(), _d(scale), _d(bias), _d(residual), relu)
     if accumulate:
         y = y + _d(out)
     dt = out.dtype if out is not None else _exact(out_dtype or a.dtype)
@@ -93,8 +108,8 @@ def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, b
         Wo = (W + 2 * pad - dil * (kw - 1) - 1) // stride + 1
     else:
         Ho, Wo = out_hw
-    wd, xin = _d(w), x
-    x = _d(x)
+    wd, xin = _mma(w), x
+    x = _mma(x)
     scale, bias, residual = _d(scale), _d(bias), _d(residual)
     dt = out.dtype if (out is not None and out_map is None) else _exact(out_dtype or xin.dtype)
     y = x.new_zeros(NB, Ho, Wo, Cout)
@@ -119,7 +134,7 @@ def conv2d_nhwc(x, w, *, kh, kw, stride=1, dil=1, pad=0, out=None, scale=None, b
 
 def conv2d_wgrad_nhwc(dy, x, *, kh, kw, stride=1, dil=1, pad=0, dw_out=None, splits=8, taps=None):
     Cout, Cin = dy.shape[3], x.shape[3]
-    g = torch.nn.grad.conv2d_weight(_nchw(_d(x)).contiguous(), (Cout, Cin, kh, kw), _nchw(_d(dy)).contiguous(), stride, pad, dil)
+    g = torch.nn.grad.conv2d_weight(_nchw(_mma(x)).contiguous(), (Cout, Cin, kh, kw), _nchw(_mma(dy)).contiguous(), stride, pad, dil)
     dw_out += g.permute(0, 2, 3, 1).reshape(Cout, kh * kw * Cin).to(dw_out.dtype)
     return dw_out
 

@@ -227,3 +227,53 @@ def test_mixed_precision_orchestration_matches_the_bf16_oracle(monkeypatch, f64)
     print("with float32 BatchNorm vectors: activation errors", errs32, "median gradient error", rows32[len(rows32) // 2])
     # one 6e-8 seed is enough: the figures of the B200 run (last_fm 0.195, gradients 0.85; profiles/config4_r02.md) reappear
     assert errs32["last_fm"] > 1e-2 and rows32[len(rows32) // 2][0] > 0.2
+
+
+def test_tf32_orchestration_matches_the_tf32_oracle(monkeypatch, f64):
+    """The fp32-storage configuration with the stand-ins' contractions reading TF32-truncated operands (fake_ops.TF32)
+    against the oracle in mode "tf32": which operands go through the tensor cores -- the first layer's im2col rows, the
+    1x1 convolutions, the heads, both operands of every data and weight gradient; NOT the depthwise layers, BatchNorm or
+    the losses -- is orchestration and agrees exactly.  Seeding one float32-level difference gives the B200's TF32
+    whole-graph figure (last_fm ~1e-2)."""
+    import oracle_lib as O
+    import torch_graph as TG
+    import torch_graph_mnv2 as TM
+    import fake_ops
+    B, chip = 2, 256
+    rel = lambda a, b: float((a.detach().double() - b.detach().double()).norm() / (b.detach().double().norm() + 1e-30))
+
+    def run(seed32):
+        cfg, net = _net(monkeypatch, B)
+        monkeypatch.setattr(fake_ops, "TF32", [True])
+        for c in net.backbone_convs() + net.head_convs():
+            c.wdtype = torch.float64                     # fp32 in the product = the exact type here
+        if seed32:
+            for bn in net.all_bns():
+                for k in ("mean", "invstd", "scale", "shift"):
+                    setattr(bn.st, k, getattr(bn.st, k).float())
+        batch = _batch(B, chip)
+        out = net.forward_backward(batch)
+        A = cfg.num_anchors
+        prob = out["rpn_cls_prob"].permute(0, 3, 1, 2).contiguous()
+        bbox = out["rpn_head"][..., :4 * A].permute(0, 3, 1, 2).contiguous()
+        res = O.multi_proposal_target(prob.numpy(), bbox.numpy(), batch["im_info"].numpy(), batch["gt_boxes"].numpy(),
+                                      batch["valid_ranges"].numpy(), feat_stride=32, scales=cfg.scales, ratios=cfg.ratios)
+        arg, aux = net.export_reference()
+        P, Aux = TM.params_to_torch(arg, aux)
+        TG.MODE[0] = "tf32"
+        try:
+            obj, ref = TM.forward_train(P, Aux, batch, lambda *_: res, batch_images=B)
+            obj.backward()
+        finally:
+            TG.MODE[0] = "exact"
+            TG.LOWP[0] = False
+        garg, _ = net.export_reference(grads=True)
+        rows = sorted(((rel(torch.from_numpy(garg[n]), p.grad), n) for n, p in P.items() if p.requires_grad), reverse=True)
+        return rel(out["last_fm"].permute(0, 3, 1, 2), ref["last_fm"]), rows
+
+    e, rows = run(False)
+    print("exact TF32 emulation: last_fm", e, "worst gradient errors", rows[:3])
+    assert e < 1e-12 and rows[0][0] < 1e-10, (e, rows[:5])
+    e32, rows32 = run(True)
+    print("seeded: last_fm", e32, "median gradient error", rows32[len(rows32) // 2])
+    assert e32 > 1e-3          # measured here 1.36e-2 / 0.242: the B200 run gave 1.42e-2 / 0.24 (profiles/config4_r02.md)
