@@ -219,10 +219,10 @@ def stem_rows(w, dtype=None):
 
 def stem_conv_tc(x_nchw, rows, in_scale, in_shift, out_scale, out_shift, out_dtype=None):
     """bn_data -> conv0 7x7/2 pad 3 (zero padding of the NORMALISED image) -> bn0 -> relu, NHWC out"""
-    xn = x_nchw * in_scale.view(1, 3, 1, 1) + in_shift.view(1, 3, 1, 1)
-    y = F.conv2d(xn, rows.to(xn.dtype).permute(0, 3, 1, 2), None, 2, 3)
-    y = (y * out_scale.view(1, -1, 1, 1) + out_shift.view(1, -1, 1, 1)).clamp(min=0)
-    return _nhwc(y).contiguous()
+    xn = _d(x_nchw) * _d(in_scale).view(1, 3, 1, 1) + _d(in_shift).view(1, 3, 1, 1)
+    y = F.conv2d(_mma(xn), _mma(rows).permute(0, 3, 1, 2), None, 2, 3)       # the im2col GEMM reads TF32 operands
+    y = (y * _d(out_scale).view(1, -1, 1, 1) + _d(out_shift).view(1, -1, 1, 1)).clamp(min=0)
+    return _st(_nhwc(y), x_nchw.dtype).contiguous()
 
 
 stem_conv = stem_conv_tc

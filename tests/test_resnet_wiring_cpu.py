@@ -81,7 +81,7 @@ def test_training_graph_matches_the_autograd_oracle(monkeypatch, f64):
     errs = dict(cat=_rel(out["cat"].permute(0, 3, 1, 2), ref["relu1"]), rpn_prob=_rel(prob, ref["rpn_cls_prob"]),
                 cls_prob=_rel(out["cls_prob"], ref["cls_prob"]))
     print("activation errors", errs)
-    assert max(errs.values()) < 1e-7                       # (the deformable offsets are float32 tensors by contract)
+    assert max(errs.values()) < 1e-12
     assert torch.allclose(out["losses"][:4], ref["loss_sums"], rtol=1e-5)
     garg, _ = net.export_reference(grads=True)
     rows = []
@@ -110,3 +110,52 @@ def test_inference_graphs(monkeypatch, f64):
     assert torch.equal(rois, r2) and torch.equal(scores, s2) and torch.equal(net.P.w, w0)
     assert rois.shape == (B * 300, 5) and (cls_prob.sum(1) - 1).abs().max() < 1e-9
     assert (rois[:, 1:] >= 0).all() and (rois[:, 1:] <= chip - 1).all()
+
+
+def test_tf32_orchestration_matches_the_tf32_oracle(monkeypatch, f64):
+    """The metric's configuration (fp32 storage, TF32 tensor-core math) with the stand-ins' contractions reading
+    TF32-truncated operands against the oracle's "tf32" mode: the stem's im2col GEMM, every convolution and data / weight
+    gradient, the deformable GEMMs and the FCs truncate, BatchNorm / PSROI / losses do not -- exact agreement.  The GPU
+    whole-graph test (tests/test_graph_parity_gpu.py) compares the real kernels with the same oracle mode and reports
+    3.7e-3 at c4|c5; seeding one float32-level difference into the exact evaluations shows what last-bit noise does."""
+    import oracle_lib as O
+    import torch_graph as TG
+    import fake_ops
+    B, chip = 1, 256
+
+    def run(seed32):
+        cfg, net = _net(monkeypatch, B)
+        monkeypatch.setattr(fake_ops, "TF32", [True])
+        for c in net._named_convs():
+            c.wdtype = torch.float64                     # fp32 in the product = the exact type here
+        if seed32:
+            for bn in net.train_bns():
+                for k in ("mean", "invstd", "scale", "shift"):
+                    setattr(bn.st, k, getattr(bn.st, k).float())
+        batch = _batch(B, chip)
+        out = net.forward_backward(batch)
+        A = cfg.num_anchors
+        prob = out["rpn_cls_prob"].permute(0, 3, 1, 2).contiguous()
+        bbox = out["rpn_head"][..., :4 * A].permute(0, 3, 1, 2).contiguous()
+        res = O.multi_proposal_target(prob.numpy(), bbox.numpy(), batch["im_info"].numpy(), batch["gt_boxes"].numpy(),
+                                      batch["valid_ranges"].numpy())
+        arg, aux = net.export_reference()
+        P, Aux = TG.params_to_torch(arg, aux)
+        TG.MODE[0], TG.STEM[0] = "tf32", "tc"
+        try:
+            obj, ref = TG.forward_train(P, Aux, batch, lambda *_: res, batch_images=B)
+            obj.backward()
+        finally:
+            TG.MODE[0] = "exact"
+            TG.LOWP[0] = False
+        garg, _ = net.export_reference(grads=True)
+        rows = sorted(((_rel(torch.from_numpy(garg[n]), p.grad), n) for n, p in P.items() if p.requires_grad), reverse=True)
+        return _rel(out["cat"].permute(0, 3, 1, 2), ref["relu1"]), rows
+
+    e, rows = run(False)
+    print("exact TF32 emulation: c4|c5", e, "worst gradient errors", rows[:3])
+    assert e < 1e-12 and rows[0][0] < 1e-10, (e, rows[:5])
+    e32, rows32 = run(True)
+    print("seeded: c4|c5", e32, "median gradient error", rows32[len(rows32) // 2])
+    # measured here 4.5e-3 / 0.088; the B200 run of the real kernels against the same oracle mode: 3.7e-3 / ~0.10 (DESIGN.md 4)
+    assert 1e-4 < e32 < 5e-2
