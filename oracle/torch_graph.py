@@ -82,6 +82,23 @@ class _RoundWeight(torch.autograd.Function):
         return g
 
 
+class _RoundGrad(torch.autograd.Function):
+    """identity forward, bf16-rounded gradient: a point where the product stores a GRADIENT in bf16 although the forward
+    tensor there is wide (the deformable units: the offset gradient is cast to bf16 for the offset convolution's backward
+    GEMMs, and the im2col path's share of the activation gradient is cast before the offset path's share is added)"""
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf16(g)
+
+
+def qg(x):
+    return _RoundGrad.apply(x) if (MODE[0] in ("bf16", "bf16x") and LOWP[0]) else x
+
+
 def qs(x):
     return _RoundStored.apply(x) if (MODE[0] in ("bf16", "bf16x") and LOWP[0]) else x
 
@@ -248,11 +265,15 @@ def _unit(P, A, x, name, stride, dim_match, train, deform, eps, taps=None):
     # it); a frozen unit folds BN + ReLU into the producing conv's epilogue, so c1 / c2 never exist in memory there.
     qc = qs if train else (lambda t: t)
     a1 = qs(_bn(P, A, x, name + "_bn1", eps, train))
-    c1 = qc(conv2d(a1, P[name + "_conv1_weight"]))
+    # (the product stores conv1's data gradient in bf16 BEFORE the shortcut convolution's is added to it: qg)
+    c1 = qc(conv2d(qg(a1) if train else a1, P[name + "_conv1_weight"]))
     a2 = qs(_bn(P, A, c1, name + "_bn2", eps, train))
     if deform:
-        off = conv2d(a2, P[name + "_offset_weight"], P[name + "_offset_bias"], 1, 2, 2)     # kept fp32 by the product
-        c2 = qc(deform_conv2d(a2, off, P[name + "_conv2_weight"]))
+        # offsets are kept fp32 by the product; their gradient goes through the offset convolution's backward GEMMs in
+        # bf16 (the bias gradient is taken from the fp32 tensor), and the im2col path's activation gradient is stored in
+        # bf16 before the offset path's is added
+        off = qg(conv2d(a2, P[name + "_offset_weight"], None, 1, 2, 2)) + P[name + "_offset_bias"].view(1, -1, 1, 1)
+        c2 = qc(deform_conv2d(qg(a2), off, P[name + "_conv2_weight"]))
     else:
         c2 = qc(conv2d(a2, P[name + "_conv2_weight"], None, stride, 1))
     a3 = qs(_bn(P, A, c2, name + "_bn3", eps, train))
@@ -289,6 +310,7 @@ def backbone(P, A, data, eps=2e-5, taps=None):
             x = _unit(P, A, x, name, stride, j > 0, train=stage > 1, deform=stage == 4, eps=eps, taps=taps)
         if stage == 3:
             c4 = x
+    c4 = qg(c4)                           # the concat's share of c4's gradient is cast to bf16 before stage 4's is added
     LOWP[0] = False                       # Cast(relu1, float32) (:250-252): the heads are fp32
     return torch.cat([c4, x], 1)
 

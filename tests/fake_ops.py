@@ -210,19 +210,23 @@ def bn_relu_bwd(x, dy, bn, add=None, out=None, defer=False):
 
 
 def maxpool3x3s2(x):
-    return _nhwc(F.max_pool2d(_nchw(x), 3, 2, 1)).contiguous()
+    return _st(_nhwc(F.max_pool2d(_nchw(_d(x)), 3, 2, 1)), x.dtype).contiguous()
 
 
 def stem_rows(w, dtype=None):
-    return w                                  # [64,7,7,3]: the fake stem convolves directly
+    """[64,7,7,3]: the stand-in stem convolves directly; bf16 rows in the mixed-precision configuration"""
+    return _st(_d(w), torch.bfloat16) if dtype == torch.bfloat16 else w
 
 
 def stem_conv_tc(x_nchw, rows, in_scale, in_shift, out_scale, out_shift, out_dtype=None):
-    """bn_data -> conv0 7x7/2 pad 3 (zero padding of the NORMALISED image) -> bn0 -> relu, NHWC out"""
+    """bn_data -> conv0 7x7/2 pad 3 (zero padding of the NORMALISED image) -> bn0 -> relu, NHWC out.  The im2col buffer
+    has the rows' dtype: bf16 rows = a bf16 im2col of bn_data(x); fp32 rows are read as TF32 by the GEMM."""
     xn = _d(x_nchw) * _d(in_scale).view(1, 3, 1, 1) + _d(in_shift).view(1, 3, 1, 1)
-    y = F.conv2d(_mma(xn), _mma(rows).permute(0, 3, 1, 2), None, 2, 3)       # the im2col GEMM reads TF32 operands
+    if rows.dtype == torch.bfloat16:
+        xn = _st(xn, torch.bfloat16).double()
+    y = F.conv2d(_mma(xn) if rows.dtype != torch.bfloat16 else xn, _mma(rows).permute(0, 3, 1, 2), None, 2, 3)
     y = (y * _d(out_scale).view(1, -1, 1, 1) + _d(out_shift).view(1, -1, 1, 1)).clamp(min=0)
-    return _st(_nhwc(y), x_nchw.dtype).contiguous()
+    return _st(_nhwc(y), _exact(out_dtype) if out_dtype is not None else x_nchw.dtype).contiguous()
 
 
 stem_conv = stem_conv_tc
@@ -262,17 +266,18 @@ def _deform_cols(x, offset, dil, pad, dg):
 
 def deform_im2col(x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroups=4, out=None):
     N, H, W, C = x.shape
-    return _deform_cols(x, offset.to(x.dtype), dil, pad, dgroups).reshape(N * H * W, 9 * C)
+    return _st(_deform_cols(_d(x), _d(offset), dil, pad, dgroups).reshape(N * H * W, 9 * C), x.dtype)       # col has x's dtype
 
 
 def deform_col2im(dcol, x, offset, *, kh=3, kw=3, stride=1, dil=1, pad=1, dgroups=4, dx=None, doffset=None):
     N, H, W, C = x.shape
-    xr = x.detach().clone().requires_grad_(True)
-    orr = offset.detach().to(x.dtype).clone().requires_grad_(True)
+    xr = _d(x).detach().clone().requires_grad_(True)
+    orr = _d(offset).detach().clone().requires_grad_(True)
     col = _deform_cols(xr, orr, dil, pad, dgroups)
-    gx, go = torch.autograd.grad(col, (xr, orr), dcol.reshape(col.shape))
-    dx = gx if dx is None else dx + gx
-    doffset = go if doffset is None else doffset + go
+    gx, go = torch.autograd.grad(col, (xr, orr), _d(dcol).reshape(col.shape))
+    wide = _exact(torch.float32)                      # the sums are fp32 tensors in the product whatever x's dtype
+    dx = _st(gx, wide) if dx is None else dx + gx
+    doffset = _st(go, wide) if doffset is None else doffset + go
     return dx, doffset
 
 
