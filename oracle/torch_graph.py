@@ -285,8 +285,9 @@ def _unit(P, A, x, name, stride, dim_match, train, deform, eps, taps=None):
     return out
 
 
-def backbone(P, A, data, eps=2e-5, taps=None):
-    """resnetc4 + resnetc5(deform=True) + Concat (:243-249).  Returns relu1 = cat(conv_feat, relut) [B,3072,H/16,W/16]."""
+def backbone(P, A, data, eps=2e-5, taps=None, is_train=True):
+    """resnetc4 + resnetc5(deform=True) + Concat (:243-249).  Returns relu1 = cat(conv_feat, relut) [B,3072,H/16,W/16].
+    is_train=False: every BatchNorm on its moving statistics (the test graph)."""
     x = _bn(P, A, data, "bn_data", eps, False, relu=False, fix_gamma=True)
     if STEM[0] == "fma" or MODE[0] == "exact":
         x = conv2d(x, P["conv0_weight"], None, 2, 3, exact=True)
@@ -307,7 +308,7 @@ def backbone(P, A, data, eps=2e-5, taps=None):
         for j in range(n):
             name = "stage%d_unit%d" % (stage, j + 1)
             stride = 2 if (j == 0 and stage in (2, 3)) else 1
-            x = _unit(P, A, x, name, stride, j > 0, train=stage > 1, deform=stage == 4, eps=eps, taps=taps)
+            x = _unit(P, A, x, name, stride, j > 0, train=is_train and stage > 1, deform=stage == 4, eps=eps, taps=taps)
         if stage == 3:
             c4 = x
     c4 = qg(c4)                           # the concat's share of c4's gradient is cast to bf16 before stage 4's is added
@@ -373,3 +374,35 @@ def forward_train(P, A, batch, proposals, batch_images, rpn_batch_size=256, num_
                cls_prob=lp.exp(), bbox_pred=bbox_pred, trans=trans, pooled=pooled, offset_t=offset_t,
                loss_sums=torch.stack([rpn_cls_sum, rpn_bbox_sum, cls_sum, bbox_sum]).detach(), rois=rois, label=label)
     return objective, out
+
+
+def forward_test(P, A, data, proposals, num_anchors=21, eps=2e-5, autofocus=False):
+    """get_symbol_rcnn(cfg, is_train=False) (resnet_mx_101_e2e.py:227-267, 346-389): moving-statistics BatchNorm everywhere,
+    SoftmaxActivation(mode=channel) over the reshaped RPN scores, MultiProposal (callback: (rpn_cls_prob [B,2A,H,W],
+    rpn_bbox_pred) -> rois [N,5] numpy), the deformable R-FCN head, softmax; autofocus: the FocusPixel branch conv_new_2 ->
+    relu -> conv_new_3 -> relu -> conv_new_out -> softmax over its two channels (:259-267, 385-386), channel 1 returned."""
+    B = data.shape[0]
+    An = num_anchors
+    with torch.no_grad():
+        relu1 = backbone(P, A, data, eps, is_train=False)
+        rpn = F.relu(conv2d(relu1, P["rpn_conv_3x3_weight"], P["rpn_conv_3x3_bias"], 1, 1))
+        score = conv2d(rpn, P["rpn_cls_score_weight"], P["rpn_cls_score_bias"])
+        rpn_bbox_pred = conv2d(rpn, P["rpn_bbox_pred_weight"], P["rpn_bbox_pred_bias"])
+        feat = F.relu(conv2d(relu1, P["conv_new_1_weight"], P["conv_new_1_bias"]))
+        H, W = score.shape[2], score.shape[3]
+        prob = F.softmax(score.reshape(B, 2, An * H, W), 1).reshape(B, 2 * An, H, W)
+        rois = np.ascontiguousarray(proposals(prob, rpn_bbox_pred), dtype=np.float32)
+        N = rois.shape[0]
+        offset_t = DeformPSROI.apply(feat, None, rois, PSROI_KW)
+        trans = linear(offset_t.reshape(N, -1), P["offset_weight"], P["offset_bias"]).reshape(N, 2, 7, 7)
+        pooled = DeformPSROI.apply(feat, trans, rois, PSROI_KW)
+        fc1 = F.relu(linear(pooled.reshape(N, -1), P["fc_new_1_weight"], P["fc_new_1_bias"]))
+        fc2 = F.relu(linear(fc1, P["fc_new_2_weight"], P["fc_new_2_bias"]))
+        out = dict(rois=rois, cls_prob=F.softmax(linear(fc2, P["cls_score_weight"], P["cls_score_bias"]), 1),
+                   bbox_pred=linear(fc2, P["bbox_pred_weight"], P["bbox_pred_bias"]), rpn_cls_prob=prob, relu1=relu1)
+        if autofocus:
+            f = F.relu(conv2d(relu1, P["conv_new_2_weight"], P["conv_new_2_bias"], 1, 1))
+            f = F.relu(conv2d(f, P["conv_new_3_weight"], P["conv_new_3_bias"]))
+            f = conv2d(f, P["conv_new_out_weight"], P["conv_new_out_bias"])
+            out["focus"] = F.softmax(f, 1)[:, 1]
+    return out

@@ -98,18 +98,42 @@ def test_training_graph_matches_the_autograd_oracle(monkeypatch, f64):
 
 
 def test_inference_graphs(monkeypatch, f64):
-    """forward_inference == the oracle's test-mode evaluation on the C oracle's proposals; forward_rpn == its proposal
-    half, bit for bit."""
+    """forward_inference (get_symbol_rcnn, is_train=False, with the AutoFocus branch) == oracle/torch_graph.forward_test on
+    the C oracle's MultiProposal output: moving-statistics BatchNorm folded into the convolution epilogues, the proposal
+    operator's rois, class probabilities, box deltas, the FocusPixel map; forward_rpn == its proposal half, bit for bit."""
+    import oracle_lib as O
+    import torch_graph as TG
     B, chip = 1, 256
     cfg, net = _net(monkeypatch, B)
     batch = _batch(B, chip)
     net.train_step(batch, lr=0.001)                      # moving statistics of the trainable BatchNorms become non-trivial
+    g = torch.Generator().manual_seed(11)
+    for bn in net.train_bns():                           # (momentum 0.995 leaves them close to 0 / 1: spread them)
+        bn.st.moving_mean.add_(torch.empty(bn.C).normal_(0, 0.1, generator=g))
+        bn.st.moving_var.mul_(torch.empty(bn.C).uniform_(0.6, 1.6, generator=g))
+    af = {}
+    for name, shape in (("conv_new_2", (256, 3072, 3, 3)), ("conv_new_3", (256, 256, 1, 1)), ("conv_new_out", (2, 256, 1, 1))):
+        af[name + "_weight"] = (torch.randn(shape, generator=g) * 0.01).numpy()
+        af[name + "_bias"] = (torch.randn(shape[0], generator=g) * 0.1).numpy()
+    net.enable_autofocus(arg=af)
     w0 = net.P.w.clone()
-    rois, scores, cls_prob, bbox_pred = net.forward_inference(batch["data"], batch["im_info"])
+    rois, scores, cls_prob, bbox_pred, fmap = net.forward_inference(batch["data"], batch["im_info"], autofocus=True)
     r2, s2 = net.forward_rpn(batch["data"], batch["im_info"])
     assert torch.equal(rois, r2) and torch.equal(scores, s2) and torch.equal(net.P.w, w0)
     assert rois.shape == (B * 300, 5) and (cls_prob.sum(1) - 1).abs().max() < 1e-9
     assert (rois[:, 1:] >= 0).all() and (rois[:, 1:] <= chip - 1).all()
+    arg, aux = net.export_reference()
+    arg.update(af)
+    P, Aux = TG.params_to_torch(arg, aux)
+    TG.MODE[0] = "exact"
+
+    def proposals(prob, bbox):
+        return O.multi_proposal(prob.numpy(), bbox.numpy(), batch["im_info"].numpy())["rois"]
+    ref = TG.forward_test(P, Aux, batch["data"], proposals, autofocus=True)
+    assert np.array_equal(rois.numpy().astype(np.float32), ref["rois"])
+    errs = dict(cls_prob=_rel(cls_prob, ref["cls_prob"]), bbox_pred=_rel(bbox_pred, ref["bbox_pred"]), focus=_rel(fmap, ref["focus"]))
+    print("inference errors", errs)
+    assert max(errs.values()) < 1e-5                     # (float32 PSROI oracle, float32 AutoFocus weights)
 
 
 def test_tf32_orchestration_matches_the_tf32_oracle(monkeypatch, f64):
