@@ -253,3 +253,49 @@ def test_mixed_precision_orchestration_matches_the_bf16_oracle(monkeypatch, f64)
     e32, rows32 = run(True)
     print("seeded: c4|c5", e32, "median gradient error", rows32[len(rows32) // 2])
     assert e32 > 1e-3
+
+
+def test_two_sgd_steps_match_the_reference_update_rule(monkeypatch, f64):
+    """forward_backward + update() twice, with two different learning rates, against the oracle graph followed by MXNet's
+    SGD-momentum rule written out (optimizer_op-inl.h:279-300: mom = momentum * mom - lr * (rescale * g + wd * w); w += mom)
+    with MXNet's multipliers: wd_mult 0 for every name not ending in _weight / _gamma (optimizer.py set_wd_mult), lr_mult
+    0.01 for the `offset` FullyConnected (its symbol attribute, resnet_mx_101_e2e.py:282), frozen tensors untouched.  Pins
+    the flat-buffer segments (bucket, lr_mult, wd_mult), the device-side hyper-parameters and the moving statistics."""
+    import oracle_lib as O
+    import torch_graph as TG
+    B, chip = 1, 256
+    cfg, net = _net(monkeypatch, B)
+    batches = [_batch(B, chip)]
+    from sniper_b200 import synth_batch
+    batches.append({k: v.double() for k, v in synth_batch.make_batch(B, seed=9, device="cpu", chip=chip).items()})
+    arg, aux = net.export_reference()
+    P, Aux = TG.params_to_torch(arg, aux)
+    mom = {k: torch.zeros_like(v) for k, v in P.items() if v.requires_grad}
+    TG.MODE[0] = "exact"
+    A = cfg.num_anchors
+    for step, lr in enumerate((0.004, 0.011)):
+        batch = batches[step]
+        out = net.forward_backward(batch)
+        prob = out["rpn_cls_prob"].permute(0, 3, 1, 2).contiguous()
+        bbox = out["rpn_head"][..., :4 * A].permute(0, 3, 1, 2).contiguous()
+        res = O.multi_proposal_target(prob.numpy(), bbox.numpy(), batch["im_info"].numpy(), batch["gt_boxes"].numpy(),
+                                      batch["valid_ranges"].numpy())
+        net.update(lr=lr)
+        for v in P.values():
+            v.grad = None
+        obj, _ = TG.forward_train(P, Aux, batch, lambda *_: res, batch_images=B)
+        obj.backward()
+        with torch.no_grad():
+            for k, m in mom.items():
+                wd = cfg.wd if (k.endswith("_weight") or k.endswith("_gamma")) else 0.0
+                lr_k = lr * (0.01 if k in ("offset_weight", "offset_bias") else 1.0)
+                m.mul_(cfg.momentum).sub_(lr_k * (P[k].grad + wd * P[k]))
+                P[k].add_(m)
+    got, _ = net.export_reference()
+    worst = sorted(((_rel(torch.from_numpy(got[k]), P[k]), k) for k in P), reverse=True)
+    print("worst parameter errors after two updates", worst[:4])
+    assert worst[0][0] < 2e-7, worst[:5]              # (lr / wd live in a float32 device buffer: 6e-8)
+    moved = [k for k in mom if not torch.equal(torch.from_numpy(arg[k]), P[k].detach())]
+    assert len(moved) == len(mom)                                   # every trainable tensor moved ...
+    frozen = [k for k, v in P.items() if not v.requires_grad]
+    assert frozen and all(np.array_equal(got[k], arg[k]) for k in frozen)      # ... and no frozen one did
