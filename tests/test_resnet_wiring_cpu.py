@@ -269,6 +269,7 @@ def test_two_sgd_steps_match_the_reference_update_rule(monkeypatch, f64):
     from sniper_b200 import synth_batch
     batches.append({k: v.double() for k, v in synth_batch.make_batch(B, seed=9, device="cpu", chip=chip).items()})
     arg, aux = net.export_reference()
+    arg0 = {k: v.copy() for k, v in arg.items()}                    # (params_to_torch shares memory with `arg`)
     P, Aux = TG.params_to_torch(arg, aux)
     mom = {k: torch.zeros_like(v) for k, v in P.items() if v.requires_grad}
     TG.MODE[0] = "exact"
@@ -295,7 +296,7 @@ def test_two_sgd_steps_match_the_reference_update_rule(monkeypatch, f64):
     worst = sorted(((_rel(torch.from_numpy(got[k]), P[k]), k) for k in P), reverse=True)
     print("worst parameter errors after two updates", worst[:4])
     assert worst[0][0] < 2e-7, worst[:5]              # (lr / wd live in a float32 device buffer: 6e-8)
-    moved = [k for k in mom if not torch.equal(torch.from_numpy(arg[k]), P[k].detach())]
+    moved = [k for k in mom if not np.array_equal(got[k], arg0[k])]
     assert len(moved) == len(mom)                                   # every trainable tensor moved ...
     frozen = [k for k, v in P.items() if not v.requires_grad]
-    assert frozen and all(np.array_equal(got[k], arg[k]) for k in frozen)      # ... and no frozen one did
+    assert frozen and all(np.array_equal(got[k], arg0[k]) for k in frozen)     # ... and no frozen one did
